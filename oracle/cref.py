@@ -1,0 +1,171 @@
+"""oracle/cref.py -- TEST INFRASTRUCTURE, not product code.
+
+ctypes front-ends for the two native oracles:
+
+* ``ref``  -- oracle/_ref/libvbhem_ref.so: the reference's own C E-step
+  (/root/reference/src/vbhem/vbhem_hmm_bwd_fwd_mex.c) compiled unmodified and in
+  place behind oracle/mxshim (recipe: oracle/Makefile).  ``kind = "reference"``.
+* ``port`` -- oracle/_build/libvbhem_oracle.so: this repo's plain-C restatement
+  (oracle/estep_oracle.c).  ``kind = "port"``.
+
+Both take the same packed column-major arrays (see estep_oracle.c header).  All
+array arguments here are numpy arrays in *numpy C order with the packed axes
+reversed*, i.e. ``prior[N, maxSb]``, ``A[N, to, from]`` ... so that their memory
+is exactly the column-major layout the C side expects.  Use ``pack.py``-style
+helpers in the package (or tests/util.py) to build them.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SO = os.path.join(HERE, "_ref", "libvbhem_ref.so")
+PORT_SO = os.path.join(HERE, "_build", "libvbhem_oracle.so")
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+def build(verbose: bool = False) -> None:
+    """Build the port always, and the in-place reference build when /root/reference exists."""
+    out = subprocess.run(["make", "-C", HERE, "all"], capture_output=True, text=True)
+    if verbose or out.returncode != 0:
+        print(out.stdout, out.stderr)
+    if out.returncode != 0:
+        raise RuntimeError("oracle build failed")
+
+
+def have_ref() -> bool:
+    return os.path.exists(REF_SO)
+
+
+_libs = {}
+
+
+def _lib(which: str):
+    if which not in _libs:
+        path = REF_SO if which == "ref" else PORT_SO
+        if not os.path.exists(path):
+            build()
+        _libs[which] = C.CDLL(path)
+    return _libs[which]
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def alloc_pair_outputs(N, K, maxSr, d, covmode, fill=0.0):
+    dd = d * d if covmode else d
+    P = N * K
+    mk = lambda *s: np.full(s, fill, dtype=np.float64)
+    return dict(L_elbo=mk(K, N), nu1=mk(K, N, maxSr), xi=mk(K, N, maxSr, maxSr), pr=mk(K, N, maxSr),
+                mu=mk(K, N, d, maxSr), Mu=mk(K, N, dd, maxSr))
+
+
+def ref_estep_pairs(base: dict, cen: dict, T: int) -> dict:
+    """Reference C through the MEX gateway signature.  cen needs W and v (not vW)."""
+    lib = _lib("ref")
+    N, maxSb = base["prior"].shape
+    K, maxSr = cen["logPi"].shape
+    d, covmode = base["d"], base["covmode"]
+    o = alloc_pair_outputs(N, K, maxSr, d, covmode)
+    fn = lib.shim_estep_pairs
+    fn.restype = C.c_int
+    rc = fn(C.c_int(N), _i(_i32(base["Sb"])), C.c_int(maxSb), C.c_int(d), C.c_int(covmode),
+            _d(_f64(base["prior"])), _d(_f64(base["A"])), _d(_f64(base["mu"])), _d(_f64(base["cov"])),
+            C.c_int(K), _i(_i32(cen["Sr"])), C.c_int(maxSr),
+            _d(_f64(cen["logPi"])), _d(_f64(cen["logA"])), _d(_f64(cen["m"])), _d(_f64(cen["W"])),
+            _d(_f64(cen["v"])), _d(_f64(cen["cterm"])), C.c_int(T),
+            _d(o["L_elbo"]), _d(o["nu1"]), _d(o["xi"]), _d(o["pr"]), _d(o["mu"]), _d(o["Mu"]))
+    if rc != 0:
+        lib.shim_last_error_id.restype = C.c_char_p
+        lib.shim_last_error_msg.restype = C.c_char_p
+        raise RuntimeError(f"{lib.shim_last_error_id().decode()}: {lib.shim_last_error_msg().decode()}")
+    return o
+
+
+def ref_call_malformed(mode: int):
+    lib = _lib("ref")
+    lib.shim_last_error_id.restype = C.c_char_p
+    rc = lib.shim_call_malformed(C.c_int(mode))
+    return rc, lib.shim_last_error_id().decode()
+
+
+def port_estep_pairs(base: dict, cen: dict, T: int, lonly: bool = False) -> dict:
+    lib = _lib("port")
+    N, maxSb = base["prior"].shape
+    K, maxSr = cen["logPi"].shape
+    d, covmode = base["d"], base["covmode"]
+    o = alloc_pair_outputs(N, K, maxSr, d, covmode) if not lonly else dict(L_elbo=np.zeros((K, N)))
+    g = (lambda k: None) if lonly else (lambda k: _d(o[k]))
+    lib.oracle_estep_pairs(
+        C.c_int(N), _i(_i32(base["Sb"])), C.c_int(maxSb), C.c_int(d), C.c_int(covmode),
+        _d(_f64(base["prior"])), _d(_f64(base["A"])), _d(_f64(base["mu"])), _d(_f64(base["cov"])),
+        C.c_int(K), _i(_i32(cen["Sr"])), C.c_int(maxSr),
+        _d(_f64(cen["logPi"])), _d(_f64(cen["logA"])), _d(_f64(cen["m"])), _d(_f64(cen["vW"])),
+        _d(_f64(cen["cterm"])), C.c_int(T),
+        _d(o["L_elbo"]), g("nu1"), g("xi"), g("pr"), g("mu"), g("Mu"))
+    return o
+
+
+def port_zhat(L_elbo, logOmega, Ntilde, group=None):
+    lib = _lib("port")
+    K, N = L_elbo.shape
+    group = np.zeros(K, np.int32) if group is None else _i32(group)
+    ng = int(group.max()) + 1
+    zhat, Z, Nj, lb = np.zeros((K, N)), np.zeros((K, N)), np.zeros(K), np.zeros(2 * ng)
+    lib.oracle_zhat(C.c_int(N), C.c_int(K), _d(_f64(L_elbo)), _d(_f64(logOmega)), _d(_f64(Ntilde)),
+                    _i(group), C.c_int(ng), _d(zhat), _d(Z), _d(Nj), _d(lb))
+    return dict(zhat=zhat, Z=Z, Nj=Nj, lb=lb)
+
+
+def port_reduce(Z, o, maxSr, d, covmode):
+    lib = _lib("port")
+    K, N = Z.shape
+    dd = d * d if covmode else d
+    S = dict(nu1=np.zeros((K, maxSr)), xi=np.zeros((K, maxSr, maxSr)), pr=np.zeros((K, maxSr)),
+             mu=np.zeros((K, d, maxSr)), Mu=np.zeros((K, dd, maxSr)))
+    lib.oracle_reduce(C.c_int(N), C.c_int(K), C.c_int(maxSr), C.c_int(d), C.c_int(covmode), _d(_f64(Z)),
+                      _d(o["nu1"]), _d(o["xi"]), _d(o["pr"]), _d(o["mu"]), _d(o["Mu"]),
+                      _d(S["nu1"]), _d(S["xi"]), _d(S["pr"]), _d(S["mu"]), _d(S["Mu"]))
+    return S
+
+
+def port_estep_fused(base: dict, cen: dict, T: int, want_pairs: bool = True) -> dict:
+    lib = _lib("port")
+    N, maxSb = base["prior"].shape
+    K, maxSr = cen["logPi"].shape
+    d, covmode = base["d"], base["covmode"]
+    dd = d * d if covmode else d
+    L = np.zeros((K, N)) if want_pairs else None
+    z = np.zeros((K, N)) if want_pairs else None
+    S = dict(Nj=np.zeros(K), lb=np.zeros(2), nu1=np.zeros((K, maxSr)), xi=np.zeros((K, maxSr, maxSr)),
+             pr=np.zeros((K, maxSr)), mu=np.zeros((K, d, maxSr)), Mu=np.zeros((K, dd, maxSr)))
+    lib.oracle_estep_fused(
+        C.c_int(N), _i(_i32(base["Sb"])), C.c_int(maxSb), C.c_int(d), C.c_int(covmode),
+        _d(_f64(base["prior"])), _d(_f64(base["A"])), _d(_f64(base["mu"])), _d(_f64(base["cov"])),
+        _d(_f64(base["Ntilde"])),
+        C.c_int(K), _i(_i32(cen["Sr"])), C.c_int(maxSr),
+        _d(_f64(cen["logPi"])), _d(_f64(cen["logA"])), _d(_f64(cen["m"])), _d(_f64(cen["vW"])),
+        _d(_f64(cen["cterm"])), _d(_f64(cen["logOmega"])), C.c_int(T),
+        _d(L), _d(z), _d(S["Nj"]), _d(S["lb"]),
+        _d(S["nu1"]), _d(S["xi"]), _d(S["pr"]), _d(S["mu"]), _d(S["Mu"]))
+    S["L_elbo"], S["zhat"] = L, z
+    return S

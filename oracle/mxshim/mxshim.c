@@ -1,0 +1,303 @@
+/* oracle/mxshim/mxshim.c -- TEST INFRASTRUCTURE, not product code.
+ *
+ * (1) An implementation of the mx / mex symbols declared in ./mex.h, backed by
+ *     a per-thread bump arena (MATLAB's own allocator is proprietary; the MEX
+ *     contract only needs create/get/set semantics).
+ * (2) A flat C driver, shim_estep_pairs(), that builds the cell/struct trees
+ *     the MEX gateway signature expects
+ *       [L_elbo,nu_1,emit_pr,emit_mu,emit_M,sum_xi] =
+ *           vbhem_hmm_bwd_fwd_mex(h3m_b.hmm,h3m_r.hmm,T,maxN,maxN2[,logdetCovPlusDdivlamR,invCovR])
+ *     (call sites: /root/reference/src/vbhem/vbhem_h3m_c_step_fc.m:175-176,193-194;
+ *      argument walk: /root/reference/src/vbhem/vbhem_hmm_bwd_fwd_mex.c:433-473)
+ *     from packed column-major arrays, calls whatever mexFunction this file is
+ *     linked with, and flattens the six outputs back into packed arrays.
+ *
+ * Linked with the reference C file it yields oracle/_ref/libvbhem_ref.so (the
+ * oracle / CPU baseline).  Linked with mex/vbhem_hmm_bwd_fwd_mex.cpp it
+ * exercises this repo's own MEX gateway through the very same driver.
+ */
+#include "mex.h"
+
+#include <setjmp.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------ arena */
+typedef struct chunk { struct chunk *next; size_t cap, used; } chunk;
+static __thread chunk *g_chunks = NULL;
+
+static void *arena_alloc(size_t n) {
+  n = (n + 15u) & ~(size_t)15u;
+  if (!g_chunks || g_chunks->used + n > g_chunks->cap) {
+    size_t cap = (size_t)1 << 24;
+    if (cap < n) cap = n;
+    chunk *c = (chunk *)malloc(sizeof(chunk) + 16 + cap);
+    if (!c) { fprintf(stderr, "mxshim: out of memory\n"); abort(); }
+    c->next = g_chunks; c->cap = cap; c->used = 0;
+    g_chunks = c;
+  }
+  char *base = (char *)(g_chunks + 1);
+  base = (char *)(((size_t)base + 15u) & ~(size_t)15u);
+  void *p = base + g_chunks->used;
+  g_chunks->used += n;
+  return p;
+}
+static void arena_reset(void) {
+  while (g_chunks) { chunk *n = g_chunks->next; free(g_chunks); g_chunks = n; }
+}
+
+/* ---------------------------------------------------------------- mxArray */
+#define SHIM_MAXFIELDS 16
+struct mxArray_tag {
+  mxClassID cls;
+  mwSize ndim;
+  mwSize dims[4];
+  size_t nel;
+  double *pr;             /* double data */
+  mxArray **cells;        /* cell / struct-field payload */
+  int nfields;
+  const char *fnames[SHIM_MAXFIELDS];
+};
+
+static mxArray *new_array(mxClassID cls, mwSize ndim, const mwSize *dims) {
+  mxArray *a = (mxArray *)arena_alloc(sizeof(mxArray));
+  memset(a, 0, sizeof(*a));
+  a->cls = cls;
+  a->ndim = ndim < 2 ? 2 : ndim;
+  a->nel = 1;
+  for (mwSize i = 0; i < 4; i++) a->dims[i] = 1;
+  for (mwSize i = 0; i < ndim && i < 4; i++) { a->dims[i] = dims[i]; a->nel *= dims[i]; }
+  return a;
+}
+
+int mxIsCell(const mxArray *a) { return a && a->cls == mxCELL_CLASS; }
+int mxIsDouble(const mxArray *a) { return a && a->cls == mxDOUBLE_CLASS; }
+int mxIsComplex(const mxArray *a) { (void)a; return 0; }
+size_t mxGetM(const mxArray *a) { return a->dims[0]; }
+size_t mxGetN(const mxArray *a) {          /* MATLAB: product of dims 2..end */
+  size_t n = 1;
+  for (mwSize i = 1; i < a->ndim; i++) n *= a->dims[i];
+  return n;
+}
+mwSize mxGetNumberOfDimensions(const mxArray *a) { return a->ndim; }
+const mwSize *mxGetDimensions(const mxArray *a) { return a->dims; }
+size_t mxGetNumberOfElements(const mxArray *a) { return a->nel; }
+double *mxGetPr(const mxArray *a) { return a->pr; }
+double mxGetScalar(const mxArray *a) { return a->pr[0]; }
+mxArray *mxGetCell(const mxArray *a, mwIndex i) { return a->cells[i]; }
+mxArray *mxGetField(const mxArray *a, mwIndex i, const char *name) {
+  (void)i;
+  for (int f = 0; f < a->nfields; f++)
+    if (strcmp(a->fnames[f], name) == 0) return a->cells[f];
+  return NULL;
+}
+
+mxArray *mxCreateNumericArray(mwSize ndim, const mwSize *dims, mxClassID cls, mxComplexity c) {
+  (void)c;
+  mxArray *a = new_array(cls, ndim, dims);
+  a->pr = (double *)arena_alloc(sizeof(double) * (a->nel ? a->nel : 1));
+  memset(a->pr, 0, sizeof(double) * a->nel);
+  return a;
+}
+mxArray *mxCreateDoubleMatrix(mwSize m, mwSize n, mxComplexity c) {
+  mwSize dims[2]; dims[0] = m; dims[1] = n;
+  return mxCreateNumericArray(2, dims, mxDOUBLE_CLASS, c);
+}
+mxArray *mxCreateCellMatrix(mwSize m, mwSize n) {
+  mwSize dims[2]; dims[0] = m; dims[1] = n;
+  mxArray *a = new_array(mxCELL_CLASS, 2, dims);
+  a->cells = (mxArray **)arena_alloc(sizeof(mxArray *) * (a->nel ? a->nel : 1));
+  memset(a->cells, 0, sizeof(mxArray *) * a->nel);
+  return a;
+}
+void mxSetCell(mxArray *a, mwIndex i, mxArray *v) { a->cells[i] = v; }
+
+void *mxMalloc(size_t n) { return arena_alloc(n ? n : 1); }
+void *mxCalloc(size_t n, size_t sz) { void *p = arena_alloc(n * sz ? n * sz : 1); memset(p, 0, n * sz); return p; }
+void mxFree(void *p) { (void)p; }
+
+/* ------------------------------------------------------------------ errors */
+static __thread jmp_buf g_jmp;
+static __thread int g_jmp_armed = 0;
+static __thread char g_errid[128];
+static __thread char g_errmsg[512];
+
+void mexErrMsgIdAndTxt(const char *id, const char *fmt, ...) {
+  va_list ap;
+  snprintf(g_errid, sizeof g_errid, "%s", id ? id : "");
+  va_start(ap, fmt);
+  vsnprintf(g_errmsg, sizeof g_errmsg, fmt, ap);
+  va_end(ap);
+  if (g_jmp_armed) longjmp(g_jmp, 1);
+  fprintf(stderr, "mexErrMsgIdAndTxt(%s): %s\n", g_errid, g_errmsg);
+  abort();
+}
+int mexPrintf(const char *fmt, ...) {
+  va_list ap; va_start(ap, fmt);
+  int r = vprintf(fmt, ap);
+  va_end(ap);
+  return r;
+}
+const char *shim_last_error_id(void) { return g_errid; }
+const char *shim_last_error_msg(void) { return g_errmsg; }
+
+/* ------------------------------------------------------------ tree builders */
+static mxArray *new_struct(void) {
+  mwSize dims[2] = {1, 1};
+  mxArray *a = new_array(mxSTRUCT_CLASS, 2, dims);
+  a->cells = (mxArray **)arena_alloc(sizeof(mxArray *) * SHIM_MAXFIELDS);
+  return a;
+}
+static void set_field(mxArray *s, const char *name, mxArray *v) {
+  s->fnames[s->nfields] = name;
+  s->cells[s->nfields] = v;
+  s->nfields++;
+}
+static mxArray *dbl_matrix(mwSize m, mwSize n, const double *src, size_t ld, int transpose_unused) {
+  (void)transpose_unused;
+  mxArray *a = mxCreateDoubleMatrix(m, n, mxREAL);
+  for (mwSize j = 0; j < n; j++)
+    for (mwSize i = 0; i < m; i++) a->pr[i + j * m] = src[i + j * ld];
+  return a;
+}
+static mxArray *dbl_scalar(double v) {
+  mxArray *a = mxCreateDoubleMatrix(1, 1, mxREAL);
+  a->pr[0] = v;
+  return a;
+}
+
+/* shim_estep_pairs
+ *
+ * Packed inputs (all column-major, fp64):
+ *   base set  : Sb[Kb]; prior[maxSb,Kb]; A[maxSb,maxSb,Kb] (A[from,to]);
+ *               mu[d,maxSb,Kb]; cov[d,d,maxSb,Kb] (full) or [d,maxSb,Kb] (diag)
+ *   centres   : Sr[Kr]; logPi[maxSr,Kr]; logA[maxSr,maxSr,Kr] (row = from);
+ *               m[d,maxSr,Kr]; W[d,d,maxSr,Kr] or [d,maxSr,Kr]; v[maxSr,Kr];
+ *               cterm[maxSr,Kr]  (= -logLambdaTilde + d/lambda)
+ *   covmode   : 0 diag, 1 full;  what: 5-arg or 7-arg gateway call.
+ * Packed outputs (pair index p = i + Kb*j):
+ *   L_elbo[Kb,Kr]; nu1[maxSr,p]; xi[maxSr,maxSr,p]; pr[maxSr,p];
+ *   mu_out[maxSr,d,p]; Mu_out[maxSr,d,d,p] (full) or [maxSr,d,p] (diag).
+ *   Entries beyond a pair's own (Sr_j) extent are left untouched.
+ * Returns 0, or 1 if the gateway raised mexErrMsgIdAndTxt (see shim_last_error_*).
+ */
+int shim_estep_pairs(int Kb, const int *Sb, int maxSb, int d, int covmode,
+                     const double *prior, const double *A, const double *mu, const double *cov,
+                     int Kr, const int *Sr, int maxSr,
+                     const double *logPi, const double *logA, const double *m, const double *W,
+                     const double *v, const double *cterm, int T,
+                     double *L_elbo, double *nu1, double *xi, double *pr, double *mu_out, double *Mu_out) {
+  const int dd = covmode ? d * d : d;
+  int rc = 0;
+  g_jmp_armed = 1;
+  if (setjmp(g_jmp)) { g_jmp_armed = 0; arena_reset(); return 1; }
+
+  /* h3m_b.hmm : {1 x Kb} of struct(A, prior, emit{1 x Sb} of struct(centres, covars, nin)) */
+  mxArray *hb = mxCreateCellMatrix(1, (mwSize)Kb);
+  for (int i = 0; i < Kb; i++) {
+    const int S = Sb[i];
+    mxArray *h = new_struct();
+    set_field(h, "prior", dbl_matrix(S, 1, prior + (size_t)maxSb * i, maxSb, 0));
+    set_field(h, "A", dbl_matrix(S, S, A + (size_t)maxSb * maxSb * i, maxSb, 0));
+    mxArray *em = mxCreateCellMatrix(1, (mwSize)S);
+    for (int k = 0; k < S; k++) {
+      mxArray *e = new_struct();
+      set_field(e, "centres", dbl_matrix(1, d, mu + (size_t)d * (k + (size_t)maxSb * i), 1, 0));
+      if (covmode)
+        set_field(e, "covars", dbl_matrix(d, d, cov + (size_t)dd * (k + (size_t)maxSb * i), d, 0));
+      else
+        set_field(e, "covars", dbl_matrix(1, d, cov + (size_t)dd * (k + (size_t)maxSb * i), 1, 0));
+      set_field(e, "nin", dbl_scalar((double)d));
+      mxSetCell(em, k, e);
+    }
+    set_field(h, "emit", em);
+    mxSetCell(hb, i, h);
+  }
+  /* h3m_r.hmm : {1 x Kr} of struct(logATilde, logPiTilde, emit{1 x Sr} of struct(m, W, v, logLambdaTildePlusDdivlamda)) */
+  mxArray *hr = mxCreateCellMatrix(1, (mwSize)Kr);
+  mxArray *c5 = mxCreateCellMatrix(1, (mwSize)Kr);
+  mxArray *c6 = mxCreateCellMatrix(1, (mwSize)Kr);
+  for (int j = 0; j < Kr; j++) {
+    const int S = Sr[j];
+    mxArray *h = new_struct();
+    set_field(h, "logATilde", dbl_matrix(S, S, logA + (size_t)maxSr * maxSr * j, maxSr, 0));
+    set_field(h, "logPiTilde", dbl_matrix(S, 1, logPi + (size_t)maxSr * j, maxSr, 0));
+    mxArray *em = mxCreateCellMatrix(1, (mwSize)S);
+    mwSize d3[3]; d3[0] = d; d3[1] = d; d3[2] = S;
+    mxArray *ld = mxCreateDoubleMatrix(1, S, mxREAL);
+    mxArray *ic = mxCreateNumericArray(3, d3, mxDOUBLE_CLASS, mxREAL);
+    for (int k = 0; k < S; k++) {
+      const size_t s = k + (size_t)maxSr * j;
+      mxArray *e = new_struct();
+      set_field(e, "m", dbl_matrix(1, d, m + (size_t)d * s, 1, 0));
+      if (covmode) set_field(e, "W", dbl_matrix(d, d, W + (size_t)dd * s, d, 0));
+      else         set_field(e, "W", dbl_matrix(1, d, W + (size_t)dd * s, 1, 0));
+      set_field(e, "v", dbl_scalar(v[s]));
+      set_field(e, "logLambdaTildePlusDdivlamda", dbl_scalar(cterm[s]));
+      mxSetCell(em, k, e);
+      ld->pr[k] = cterm[s];
+      if (covmode)   /* invCovR{j}(:,:,n) = v .* W   (vbhem_h3m_c_step_fc.m:189) */
+        for (int q = 0; q < dd; q++) ic->pr[q + (size_t)dd * k] = v[s] * W[(size_t)dd * s + q];
+    }
+    set_field(h, "emit", em);
+    mxSetCell(hr, j, h);
+    mxSetCell(c5, j, ld);
+    mxSetCell(c6, j, ic);
+  }
+
+  const mxArray *prhs[7];
+  mxArray *plhs[6] = {0, 0, 0, 0, 0, 0};
+  prhs[0] = hb; prhs[1] = hr;
+  prhs[2] = dbl_scalar((double)T);
+  prhs[3] = dbl_scalar((double)maxSb);
+  prhs[4] = dbl_scalar((double)maxSr);
+  prhs[5] = c5; prhs[6] = c6;
+  mexFunction(6, plhs, covmode ? 7 : 5, prhs);
+
+  /* flatten outputs */
+  memcpy(L_elbo, mxGetPr(plhs[0]), sizeof(double) * (size_t)Kb * Kr);
+  for (int j = 0; j < Kr; j++) {
+    const int S = Sr[j];
+    for (int i = 0; i < Kb; i++) {
+      const size_t p = (size_t)i + (size_t)Kb * j;
+      const double *s;
+      s = mxGetPr(mxGetCell(plhs[1], p));
+      for (int a = 0; a < S; a++) nu1[a + (size_t)maxSr * p] = s[a];
+      s = mxGetPr(mxGetCell(plhs[2], p));
+      for (int a = 0; a < S; a++) pr[a + (size_t)maxSr * p] = s[a];
+      s = mxGetPr(mxGetCell(plhs[3], p));
+      for (int k = 0; k < d; k++)
+        for (int a = 0; a < S; a++) mu_out[a + (size_t)maxSr * (k + (size_t)d * p)] = s[a + S * k];
+      s = mxGetPr(mxGetCell(plhs[4], p));
+      for (int k = 0; k < dd; k++)
+        for (int a = 0; a < S; a++) Mu_out[a + (size_t)maxSr * (k + (size_t)dd * p)] = s[a + S * k];
+      s = mxGetPr(mxGetCell(plhs[5], p));
+      for (int b = 0; b < S; b++)
+        for (int a = 0; a < S; a++) xi[a + (size_t)maxSr * (b + (size_t)maxSr * p)] = s[a + S * b];
+    }
+  }
+  g_jmp_armed = 0;
+  arena_reset();
+  return rc;
+}
+
+/* Calls the linked gateway with a deliberately malformed argument list so the
+ * tests can check the error ids the boundary raises
+ * (vbhem_hmm_bwd_fwd_mex.c:335-366).  mode 0: wrong nrhs; 1: wrong nlhs;
+ * 2: first arg not a cell; 3: second arg not a cell. */
+int shim_call_malformed(int mode) {
+  g_jmp_armed = 1;
+  if (setjmp(g_jmp)) { g_jmp_armed = 0; arena_reset(); return 1; }
+  const mxArray *prhs[7];
+  mxArray *plhs[6] = {0, 0, 0, 0, 0, 0};
+  mxArray *cellb = mxCreateCellMatrix(1, 0), *cellr = mxCreateCellMatrix(1, 0);
+  for (int i = 0; i < 7; i++) prhs[i] = dbl_scalar(1.0);
+  prhs[0] = (mode == 2) ? dbl_scalar(1.0) : cellb;
+  prhs[1] = (mode == 3) ? dbl_scalar(1.0) : cellr;
+  mexFunction(mode == 1 ? 5 : 6, plhs, mode == 0 ? 4 : 5, prhs);
+  g_jmp_armed = 0;
+  arena_reset();
+  return 0;
+}
