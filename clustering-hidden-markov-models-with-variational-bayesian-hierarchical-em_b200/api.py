@@ -1,0 +1,175 @@
+"""Python host mirror of the E-step boundary (thin wrapper over the C ABI).
+
+``BaseSet`` is the resident base mixture (reference type ``h3m_b``); its methods
+mirror the two boundaries of include/vbhem_b200.h:
+
+* ``estep_pairs``  -- the six outputs of the reference's MEX plug-in
+  ``vbhem_hmm_bwd_fwd_mex`` (/root/reference/src/vbhem/vbhem_hmm_bwd_fwd_mex.c:288-289,
+  call sites /root/reference/src/vbhem/vbhem_h3m_c_step_fc.m:175-176,193-194);
+* ``estep`` / ``estep_hyp`` -- the fused E-step: MEX call + responsibilities
+  (vbhem_h3m_c_step_fc.m:271-283) + statistics reduction
+  (/root/reference/src/vbhem/vbhem_compute_Statistics.m:33-82).
+
+Arrays are *natural* numpy arrays (see pack.py); all compute happens in the CUDA
+library -- there is no numpy implementation behind these calls.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import pack
+from ._lib import check, dp, ip, lib
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(dp)
+
+
+def _i(a):
+    return None if a is None else a.ctypes.data_as(ip)
+
+
+class BaseSet:
+    """A base HMM set packed once into HBM (``vbhem_pack_base``)."""
+
+    def __init__(self, base: dict, device: int = 0, packed: bool = False):
+        pb = base if packed else pack.pack_base(base)
+        self.N, self.maxSb, self.d, self.covmode = pb["N"], pb["maxSb"], pb["d"], pb["covmode"]
+        self.dd = self.d * self.d if self.covmode else self.d
+        self._h = C.c_void_p()
+        self.device = device
+        check(lib().vbhem_pack_base(device, self.N, _i(pb["Sb"]), self.maxSb, self.d, self.covmode,
+                                    _d(pb["prior"]), _d(pb["A"]), _d(pb["mu"]), _d(pb["cov"]), _d(pb["Ntilde"]),
+                                    C.byref(self._h)))
+
+    # -- lifetime -----------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().vbhem_free_base(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- knobs --------------------------------------------------------------
+    def set_kernel(self, which: str = "auto"):
+        check(lib().vbhem_set_kernel(self._h, {"auto": 0, "general": 1}[which]))
+
+    def set_stream(self, cuda_stream: int | None):
+        check(lib().vbhem_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def synchronize(self):
+        check(lib().vbhem_synchronize(self._h))
+
+    def counters(self) -> dict:
+        out = (C.c_longlong * 8)()
+        check(lib().vbhem_last_counters(self._h, out))
+        return dict(launches=out[0], lattice_pairs=out[1], general_pairs=out[2], active_pairs=out[3])
+
+    # -- Boundary-1 ---------------------------------------------------------
+    def estep_pairs(self, cen: dict, tau: int, L_only: bool = False, packed: bool = False) -> dict:
+        """Literal per-pair outputs (natural layout, see pack.pairs_to_natural)."""
+        pc = cen if packed else pack.pack_centres(cen)
+        K, r, N, d, dd = pc["K"], pc["maxSr"], self.N, self.d, self.dd
+        L = np.zeros((K, N))
+        if L_only:
+            check(lib().vbhem_estep_pairs(self._h, K, _i(pc["Sr"]), r, tau, _d(pc["logPi"]), _d(pc["logA"]),
+                                          _d(pc["m"]), _d(pc["vW"]), _d(pc["cterm"]), _d(L),
+                                          None, None, None, None, None))
+            return dict(L_elbo=L.T.copy())
+        o = dict(L_elbo=L, nu1=np.zeros((K, N, r)), xi=np.zeros((K, N, r, r)), pr=np.zeros((K, N, r)),
+                 mu=np.zeros((K, N, d, r)), Mu=np.zeros((K, N, dd, r)))
+        check(lib().vbhem_estep_pairs(self._h, K, _i(pc["Sr"]), r, tau, _d(pc["logPi"]), _d(pc["logA"]),
+                                      _d(pc["m"]), _d(pc["vW"]), _d(pc["cterm"]), _d(o["L_elbo"]), _d(o["nu1"]),
+                                      _d(o["xi"]), _d(o["pr"]), _d(o["mu"]), _d(o["Mu"])))
+        return pack.pairs_to_natural(o, d, self.covmode)
+
+    # -- Boundary-2 ---------------------------------------------------------
+    def _split_stats(self, buf, K, r, ng):
+        off = (C.c_size_t * 7)()
+        lib().vbhem_stats_offsets(K, r, self.d, self.covmode, ng, off)
+        d, dd = self.d, self.dd
+        S = dict(Nj=buf[off[0]:off[1]], nu1=buf[off[1]:off[2]].reshape(K, r),
+                 xi=buf[off[2]:off[3]].reshape(K, r, r), pr=buf[off[3]:off[4]].reshape(K, r),
+                 mu=buf[off[4]:off[5]].reshape(K, d, r), Mu=buf[off[5]:off[6]].reshape(K, dd, r),
+                 lb=buf[off[6]:off[6] + 2 * ng])
+        return S
+
+    def stats_size(self, K, r, ng=1):
+        return int(lib().vbhem_stats_size(K, r, self.d, self.covmode, ng))
+
+    def estep(self, cen: dict, tau: int, want_pairs: bool = True, packed: bool = False, raw: bool = False) -> dict:
+        """Fused E-step from pre-pass results (cen: logPi, logA, m, vW, cterm, logOmega[, group])."""
+        pc = cen if packed else pack.pack_centres(cen)
+        K, r = pc["K"], pc["maxSr"]
+        grp = pc.get("group")
+        ng = int(grp.max()) + 1 if grp is not None else 1
+        buf = np.zeros(self.stats_size(K, r, ng))
+        L = np.zeros((K, self.N)) if want_pairs else None
+        z = np.zeros((K, self.N)) if want_pairs else None
+        check(lib().vbhem_estep(self._h, K, _i(pc["Sr"]), r, _i(grp), ng, tau, _d(pc["logPi"]), _d(pc["logA"]),
+                                _d(pc["m"]), _d(pc["vW"]), _d(pc["cterm"]), _d(pc["logOmega"]),
+                                _d(L), _d(z), _d(buf)))
+        if raw:
+            return dict(buf=buf, L_elbo=L, zhat=z)
+        S = self._split_stats(buf, K, r, ng)
+        S["L_elbo"], S["zhat"] = L, z
+        out = pack.stats_to_natural(S, self.d, self.covmode)
+        out["buf"] = buf
+        return out
+
+    def estep_hyp(self, hyp: dict, tau: int, want_pairs: bool = True, group=None) -> dict:
+        """Fused E-step from centre hyper-parameters; the pre-pass runs on the device.
+
+        hyp (natural): Sr[K], alpha[K], eta[K,S], epsilon[K,S,S], m[K,S,d], W[K,S,d,d]|[K,S,d], v[K,S], lam[K,S].
+        Also returns the pre-pass results the host-side lower bound needs
+        (logOmega, logPi, logA (from,to), logLambdaTilde)."""
+        c = np.ascontiguousarray
+        K, r = hyp["eta"].shape
+        Sr = c(hyp.get("Sr", np.full(K, r)), dtype=np.int32)
+        full = self.covmode == 1
+        W = np.asarray(hyp["W"], dtype=np.float64)
+        Wp = c(np.transpose(W, (0, 1, 3, 2))) if full else c(W)
+        eps = c(np.transpose(hyp["epsilon"], (0, 2, 1)), dtype=np.float64)
+        grp = None if group is None else c(group, dtype=np.int32)
+        ng = int(grp.max()) + 1 if grp is not None else 1
+        buf = np.zeros(self.stats_size(K, r, ng))
+        pre = np.zeros(K + r * K * (2 + r))
+        L = np.zeros((K, self.N)) if want_pairs else None
+        z = np.zeros((K, self.N)) if want_pairs else None
+        f64 = lambda a: c(a, dtype=np.float64)
+        al, et, m, v, lam = f64(hyp["alpha"]), f64(hyp["eta"]), f64(hyp["m"]), f64(hyp["v"]), f64(hyp["lam"])
+        check(lib().vbhem_estep_hyp(self._h, K, _i(Sr), r, _i(grp), ng, tau, _d(al), _d(et), _d(eps), _d(m),
+                                    _d(Wp), _d(v), _d(lam), _d(L), _d(z), _d(buf), _d(pre)))
+        S = self._split_stats(buf, K, r, ng)
+        S["L_elbo"], S["zhat"] = L, z
+        out = pack.stats_to_natural(S, self.d, self.covmode)
+        out["buf"] = buf
+        o = 0
+        out["logOmega"] = pre[o:o + K].copy(); o += K
+        out["logPi"] = pre[o:o + r * K].reshape(K, r).copy(); o += r * K
+        out["logA"] = np.transpose(pre[o:o + r * r * K].reshape(K, r, r), (0, 2, 1)).copy(); o += r * r * K
+        out["logLambdaTilde"] = pre[o:o + r * K].reshape(K, r).copy()
+        return out
+
+    def finalize(self, buf: np.ndarray, Sr, r: int, ng: int = 1) -> dict:
+        """vbhem_compute_Statistics.m:57-82 on a raw stats buffer (e.g. after an all-reduce)."""
+        Sr = np.ascontiguousarray(Sr, dtype=np.int32)
+        K = Sr.shape[0]
+        buf = np.ascontiguousarray(buf, dtype=np.float64).copy()
+        check(lib().vbhem_finalize_stats(self._h, K, _i(Sr), r, ng, _d(buf)))
+        S = self._split_stats(buf, K, r, ng)
+        out = pack.stats_to_natural(S, self.d, self.covmode)
+        return dict(Nj=out["Nj"], Nj_rho1=out["nu1"], Nj_rho2rho=out["xi"], Nj_rho=out["pr"], y_bar=out["mu"],
+                    S_plus_C=out["Mu"], lb=out["lb"])

@@ -1,0 +1,492 @@
+// vbhem_aux.cu -- the small kernels around the pair kernels:
+//   * centre pre-pass on the device (digamma terms, log det W, v*W)
+//       /root/reference/src/vbhem/vbhem_h3m_c_step_fc.m:118-165,180-191,271-273
+//   * linear-domain centre records for the lattice kernel
+//   * responsibilities z_hat, Nj, Lt1, Lt7      vbhem_h3m_c_step_fc.m:271-283, vbhemh3m_lb.m:90,107
+//   * deterministic list of the pairs with Z > 1e-8 (vbhem_compute_Statistics.m:35),
+//     centre-major and base-ascending, cut in fixed-length chunks
+//   * fixed-order reduction of the per-chunk partial sums, and the normalisation of
+//     vbhem_compute_Statistics.m:57-82.
+// Every sum over bases uses a fixed tree (thread -> warp -> block -> sequential over
+// blocks), so results are bit-identical from run to run.
+#include "vbhem_internal.cuh"
+
+namespace vbhem {
+
+namespace {
+
+// ---- digamma ----------------------------------------------------------------
+// psi(x) for x >= 0: upward recurrence to x >= 10, then the asymptotic series.
+__device__ double digamma(double x) {
+  if (!(x >= 0.0)) return NAN;
+  double r = 0.0;
+  while (x < 10.0) { r -= 1.0 / x; x += 1.0; }
+  const double f = 1.0 / (x * x);
+  const double ser = f * (1.0 / 12 - f * (1.0 / 120 - f * (1.0 / 252 - f * (1.0 / 240 - f * (1.0 / 132 -
+                     f * (691.0 / 32760 - f * (1.0 / 12)))))));
+  return r + log(x) - 0.5 / x - ser;
+}
+
+constexpr int kMaxDim = 8;
+
+// log(det(W)) by LU with partial pivoting, W is d x d column-major.
+__device__ double logdet(const double *W, int d) {
+  double a[kMaxDim * kMaxDim];
+  for (int q = 0; q < d * d; q++) a[q] = W[q];
+  double det = 1.0;
+  for (int c = 0; c < d; c++) {
+    int piv = c;
+    for (int r = c + 1; r < d; r++)
+      if (fabs(a[r + d * c]) > fabs(a[piv + d * c])) piv = r;
+    if (piv != c) {
+      for (int k = 0; k < d; k++) { const double t = a[c + d * k]; a[c + d * k] = a[piv + d * k]; a[piv + d * k] = t; }
+      det = -det;
+    }
+    det *= a[c + d * c];
+    for (int r = c + 1; r < d; r++) {
+      const double f = a[r + d * c] / a[c + d * c];
+      for (int k = c + 1; k < d; k++) a[r + d * k] -= f * a[c + d * k];
+    }
+  }
+  return log(det);
+}
+
+// One block per centre.
+__global__ void k_prepass(int K, int maxSr, int d, int covmode, const int *Sr, const int *gstart, int ngroups,
+                          const double *alpha, const double *eta, const double *epsilon, const double *W,
+                          const double *v, const double *lambda, double *logOmega, double *logPi, double *logA,
+                          double *logLam, double *cterm, double *vW) {
+  const int j = blockIdx.x;
+  const int r = Sr[j];
+  const int dd = covmode ? d * d : d;
+  // per state: logLambdaTilde, cterm, v*W
+  for (int k = threadIdx.x; k < maxSr; k += blockDim.x) {
+    const size_t s = k + (size_t)maxSr * j;
+    if (k < r) {
+      double t1 = 0.0;
+      for (int i = 1; i <= d; i++) t1 += digamma(0.5 * (v[s] + 1.0) - 0.5 * i);
+      double ld;
+      if (covmode) ld = logdet(W + (size_t)dd * s, d);
+      else { ld = 0.0; for (int q = 0; q < d; q++) ld += log(W[(size_t)dd * s + q]); }
+      const double ll = t1 + d * log(2.0) + ld;
+      logLam[s] = ll;
+      cterm[s] = -ll + d / lambda[s];
+      for (int q = 0; q < dd; q++) vW[(size_t)dd * s + q] = v[s] * W[(size_t)dd * s + q];
+    } else {
+      logLam[s] = 0.0; cterm[s] = 0.0;
+      for (int q = 0; q < dd; q++) vW[(size_t)dd * s + q] = 0.0;
+    }
+  }
+  // transition rows: logA[k,:] = psi(eps[k,:]) - psi(sum_k' eps[k,k'])
+  for (int x = threadIdx.x; x < maxSr * maxSr; x += blockDim.x) {
+    const int k = x % maxSr, c = x / maxSr;
+    const double *e = epsilon + (size_t)maxSr * maxSr * j;
+    double out = 0.0;
+    if (k < r && c < r) {
+      double sum = 0.0;
+      for (int cc = 0; cc < r; cc++) sum += e[k + maxSr * cc];
+      out = digamma(e[x]) - digamma(sum);
+    }
+    logA[(size_t)maxSr * maxSr * j + x] = out;
+  }
+  for (int k = threadIdx.x; k < maxSr; k += blockDim.x) {
+    const double *e = eta + (size_t)maxSr * j;
+    double out = 0.0;
+    if (k < r) {
+      double sum = 0.0;
+      for (int kk = 0; kk < r; kk++) sum += e[kk];
+      out = digamma(e[k]) - digamma(sum);
+    }
+    logPi[k + (size_t)maxSr * j] = out;
+  }
+  if (threadIdx.x == 0) {
+    int g = 0;
+    while (g + 1 < ngroups && gstart[g + 1] <= j) g++;
+    double sum = 0.0;
+    for (int jj = gstart[g]; jj < gstart[g + 1]; jj++) sum += alpha[jj];
+    logOmega[j] = digamma(alpha[j]) - digamma(sum);
+  }
+}
+
+// One block per centre: the padded linear-domain record of the lattice kernel.
+__global__ void k_build_records(CentreView C, int d, int dd, double *rec) {
+  const int j = blockIdx.x;
+  const int r = C.Sr[j], ld = C.maxSr;
+  double *o = rec + (size_t)C.rec_stride * j;
+  const double *logA = C.logA + (size_t)ld * ld * j;
+  for (int x = threadIdx.x; x < 64; x += blockDim.x) {
+    const int rho = x / 8, sg = x % 8;
+    double val;
+    if (sg >= r) val = 0.0;                       // padded to-state: never entered
+    else if (rho >= r) val = 1.0;                 // padded from-state: keeps S finite
+    else val = exp(logA[rho + ld * sg]);
+    o[x] = val;
+  }
+  for (int k = threadIdx.x; k < 8; k += blockDim.x) {
+    o[64 + k] = k < r ? exp(C.logPi[k + (size_t)ld * j]) : 0.0;
+    o[72 + k] = k < r ? d * log(kTwoPi) + C.cterm[k + (size_t)ld * j] : INFINITY;
+    for (int q = 0; q < d; q++) o[80 + k * d + q] = k < r ? C.m[q + d * (k + (size_t)ld * j)] : 0.0;
+    for (int q = 0; q < dd; q++) o[80 + 8 * d + k * dd + q] = k < r ? C.vW[q + dd * (k + (size_t)ld * j)] : 0.0;
+  }
+}
+
+// Zero everything beyond each base HMM's own state count (the kernels rely on it).
+__global__ void k_sanitize_base(BaseView B, double *prior, double *A, double *mu, double *cov) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B.N) return;
+  const int b = B.Sb[i], ld = B.maxSb;
+  for (int k = 0; k < ld; k++) {
+    if (k >= b) {
+      prior[k + (size_t)ld * i] = 0.0;
+      for (int q = 0; q < B.d; q++) mu[q + B.d * (k + (size_t)ld * i)] = 0.0;
+      for (int q = 0; q < B.dd; q++) cov[q + B.dd * (k + (size_t)ld * i)] = 0.0;
+    }
+    for (int c = 0; c < ld; c++)
+      if (k >= b || c >= b) A[k + ld * (c + (size_t)ld * i)] = 0.0;
+  }
+}
+
+// ---- responsibilities ---------------------------------------------------------
+constexpr int kZThreads = 256;   // bases per block
+constexpr int kZWarps = kZThreads / 32;
+constexpr int kJT = 32;          // centres per reduction tile
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// zhat[N,K]; per block: Nj_part[blk][K] (sum of Z), cnt[blk][K] (#Z > 1e-8),
+// lb_part[blk][2*ngroups] (Lt1, Lt7 partial sums).
+__global__ void __launch_bounds__(kZThreads)
+k_zhat(int N, int K, int ngroups, const int *gstart, const double *L_elbo, const double *logOmega,
+       const double *Ntilde, double *zhat, double *Nj_part, int *cnt, double *lb_part) {
+  __shared__ double red[kZWarps][kJT];
+  __shared__ int redc[kZWarps][kJT];
+  __shared__ double redl[kZWarps][2];
+  const int i = blockIdx.x * kZThreads + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool live = i < N;
+  const double Nt = live ? Ntilde[i] : 0.0;
+  for (int g = 0; g < ngroups; g++) {
+    const int ja = gstart[g], jb = gstart[g + 1];
+    double mv = -INFINITY, lse = 0.0;
+    if (live) {
+      // max shift then sum, in centre order (logtrick.m:15-18)
+      mv = Nt * (logOmega[ja] + L_elbo[i + (size_t)N * ja]);
+      for (int j = ja + 1; j < jb; j++) {
+        const double lz = Nt * (logOmega[j] + L_elbo[i + (size_t)N * j]);
+        if (lz > mv) mv = lz;
+      }
+      double s = 0.0;
+      for (int j = ja; j < jb; j++) s += exp(Nt * (logOmega[j] + L_elbo[i + (size_t)N * j]) - mv);
+      lse = mv + log(s);
+    }
+    double t1 = 0.0, t7 = 0.0;
+    for (int j0 = ja; j0 < jb; j0 += kJT) {
+      double mine = 0.0;
+      int minec = 0;
+      const int nt = min(kJT, jb - j0);
+      for (int jj = 0; jj < nt; jj++) {
+        const int j = j0 + jj;
+        double Z = 0.0;
+        int act = 0;
+        if (live) {
+          const double Le = L_elbo[i + (size_t)N * j];
+          const double z = exp(Nt * (logOmega[j] + Le) - lse) + 1e-50;
+          zhat[i + (size_t)N * j] = z;
+          Z = z * Nt;
+          act = Z > kSkipZ;
+          t1 += Z * Le;
+          t7 += z * log(z);
+        }
+        const double ws = warp_sum(Z);
+        const int wc = __popc(__ballot_sync(0xffffffffu, act));
+        if (lane == jj) { mine = ws; minec = wc; }
+      }
+      red[warp][lane] = mine;
+      redc[warp][lane] = minec;
+      __syncthreads();
+      if (warp == 0 && lane < nt) {
+        double s = 0.0;
+        int c = 0;
+        for (int w = 0; w < kZWarps; w++) { s += red[w][lane]; c += redc[w][lane]; }
+        Nj_part[(size_t)blockIdx.x * K + j0 + lane] = s;
+        cnt[(size_t)blockIdx.x * K + j0 + lane] = c;
+      }
+      __syncthreads();
+    }
+    t1 = warp_sum(t1);
+    t7 = warp_sum(t7);
+    if (lane == 0) { redl[warp][0] = t1; redl[warp][1] = t7; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a = 0.0, b = 0.0;
+      for (int w = 0; w < kZWarps; w++) { a += redl[w][0]; b += redl[w][1]; }
+      lb_part[(size_t)blockIdx.x * 2 * ngroups + 2 * g] = a;
+      lb_part[(size_t)blockIdx.x * 2 * ngroups + 2 * g + 1] = b;
+    }
+    __syncthreads();
+  }
+}
+
+// Sequential (fixed-order) sums over the blocks of k_zhat.
+__global__ void k_zhat_reduce(int nblocks, int K, int ngroups, const double *Nj_part, const double *lb_part,
+                              double *Nj, double *lb) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x < K) {
+    double s = 0.0;
+    for (int b = 0; b < nblocks; b++) s += Nj_part[(size_t)b * K + x];
+    Nj[x] = s;
+  } else if (x < K + 2 * ngroups) {
+    const int y = x - K;
+    double s = 0.0;
+    for (int b = 0; b < nblocks; b++) s += lb_part[(size_t)b * 2 * ngroups + y];
+    lb[y] = s;
+  }
+}
+
+// offs[blk][j]: exclusive prefix over blocks of cnt[.][j]; seg_start[j], chunk_start[j]
+// (K+1 entries each): exclusive prefix over centres; totals = {#active, #chunks}.
+__global__ void k_list_scan(int nblocks, int K, int chunk_len, const int *cnt, int *offs, int *seg_start,
+                            int *chunk_start, int *totals) {
+  extern __shared__ int segcnt[];
+  for (int j = threadIdx.x; j < K; j += blockDim.x) {
+    int run = 0;
+    for (int b = 0; b < nblocks; b++) {
+      offs[(size_t)b * K + j] = run;
+      run += cnt[(size_t)b * K + j];
+    }
+    segcnt[j] = run;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int a = 0, c = 0;
+    for (int j = 0; j < K; j++) {
+      seg_start[j] = a;
+      chunk_start[j] = c;
+      a += segcnt[j];
+      c += (segcnt[j] + chunk_len - 1) / chunk_len;
+    }
+    seg_start[K] = a;
+    chunk_start[K] = c;
+    totals[0] = a;
+    totals[1] = c;
+  }
+}
+
+__global__ void __launch_bounds__(kZThreads)
+k_list_fill(int N, int K, const double *zhat, const double *Ntilde, const int *offs, const int *seg_start,
+            PairItem *items) {
+  __shared__ int wcnt[kZWarps][kJT];
+  const int i = blockIdx.x * kZThreads + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool live = i < N;
+  const double Nt = live ? Ntilde[i] : 0.0;
+  for (int j0 = 0; j0 < K; j0 += kJT) {
+    const int nt = min(kJT, K - j0);
+    int minec = 0;
+    for (int jj = 0; jj < nt; jj++) {
+      const double Z = live ? zhat[i + (size_t)N * (j0 + jj)] * Nt : 0.0;
+      const int wc = __popc(__ballot_sync(0xffffffffu, Z > kSkipZ));
+      if (lane == jj) minec = wc;
+    }
+    wcnt[warp][lane] = minec;
+    __syncthreads();
+    for (int jj = 0; jj < nt; jj++) {
+      const int j = j0 + jj;
+      const double Z = live ? zhat[i + (size_t)N * j] * Nt : 0.0;
+      const bool act = Z > kSkipZ;
+      const unsigned bal = __ballot_sync(0xffffffffu, act);
+      if (act) {
+        int pos = seg_start[j] + offs[(size_t)blockIdx.x * K + j] + __popc(bal & ((1u << lane) - 1u));
+        for (int w = 0; w < warp; w++) pos += wcnt[w][jj];
+        items[pos] = PairItem{i, j, Z};
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void k_chunks(int K, int chunk_len, const int *seg_start, const int *chunk_start, int2 *chunks) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= chunk_start[K]) return;
+  int lo = 0, hi = K;                      // largest j with chunk_start[j] <= c
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (chunk_start[mid] <= c) lo = mid; else hi = mid;
+  }
+  const int k = c - chunk_start[lo];
+  const int start = seg_start[lo] + k * chunk_len;
+  const int len = min(chunk_len, seg_start[lo + 1] - start);
+  chunks[c] = make_int2(start, len);
+}
+
+// S_*[., j] = sum over the centre's chunks, in chunk order.
+__global__ void k_partial_reduce(int K, int per, const int *chunk_start, const double *partial, double *S_nu1,
+                                 double *S_xi, double *S_pr, double *S_mu, double *S_Mu, int r, int d, int dd) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= K * per) return;
+  const int j = x / per, q = x % per;
+  double s = 0.0;
+  for (int c = chunk_start[j]; c < chunk_start[j + 1]; c++) s += partial[(size_t)c * per + q];
+  if (q < r) S_nu1[q + (size_t)r * j] = s;
+  else if (q < r + r * r) S_xi[(q - r) + (size_t)r * r * j] = s;
+  else if (q < 2 * r + r * r) S_pr[(q - r - r * r) + (size_t)r * j] = s;
+  else if (q < 2 * r + r * r + r * d) S_mu[(q - 2 * r - r * r) + (size_t)r * d * j] = s;
+  else S_Mu[(q - 2 * r - r * r - r * d) + (size_t)r * dd * j] = s;
+}
+
+// vbhem_compute_Statistics.m:57-82 in place on a stats buffer; one thread per (state, centre).
+__global__ void k_finalize(int K, int r, int d, int covmode, const int *Sr, double *Nj, double *S_xi, double *S_pr,
+                           double *S_mu, double *S_Mu) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= K * r) return;
+  const int k = x % r, j = x / r;
+  const int dd = covmode ? d * d : d;
+  if (k == 0) {
+    Nj[j] += 1e-50;
+    if (Sr[j] == 1) S_xi[(size_t)r * r * j] = 1e-12;
+  }
+  if (k >= Sr[j]) return;
+  const double nr = S_pr[x] + 1e-50;
+  S_pr[x] = nr;
+  double yb[kMaxDim];
+  for (int q = 0; q < d; q++) {
+    yb[q] = S_mu[k + r * (q + (size_t)d * j)] / nr;
+    S_mu[k + r * (q + (size_t)d * j)] = yb[q];
+  }
+  for (int q = 0; q < dd; q++) {
+    const size_t o = k + r * (q + (size_t)dd * j);
+    const double yy = covmode ? yb[q / d] * yb[q % d] : yb[q] * yb[q];
+    S_Mu[o] = S_Mu[o] / nr - yy;
+  }
+}
+
+// ---- fp64 peak chains (roofline denominator measured on the device itself) ----
+__global__ void k_peak_dmma(double *out, int iters, double a, double b) {
+  double c0[8], c1[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { c0[i] = threadIdx.x * 1e-9; c1[i] = i; }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c0[i]), "+d"(c1[i]) : "d"(a), "d"(b));
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += c0[i] + c1[i];
+  if (s == 12345.678) out[0] = s;
+}
+__global__ void k_peak_dfma(double *out, int iters, double a, double b) {
+  double acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) acc[i] = threadIdx.x * 1e-9 + i;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = fma(acc[i], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += acc[i];
+  if (s == 12345.678) out[0] = s;
+}
+
+}  // namespace
+
+int measure_fp64_peak(double out[2]) {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  double *buf = nullptr;
+  if (cudaMalloc(&buf, 64) != cudaSuccess) return -1;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int threads = 512, blocks = sms * 4, iters = 4000;
+  const double nthr = (double)threads * blocks;
+  for (int which = 0; which < 2; which++) {
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+      cudaEventRecord(e0);
+      if (which == 0) k_peak_dmma<<<blocks, threads>>>(buf, iters, 0.999999, 1e-7);
+      else k_peak_dfma<<<blocks, threads>>>(buf, iters, 0.999999, 1e-7);
+      cudaEventRecord(e1);
+      cudaEventSynchronize(e1);
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e0, e1);
+      if (rep > 0 && ms < best) best = ms;
+    }
+    const double flop = which == 0 ? (nthr / 32) * iters * 8 * 512.0 : nthr * iters * 8 * 2.0;
+    out[which] = flop / (best * 1e-3) / 1e12;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int launch_prepass(int K, int maxSr, int d, int covmode, const int *Sr, const int *gstart, int ngroups,
+                   const double *alpha, const double *eta, const double *epsilon, const double *W, const double *v,
+                   const double *lambda, double *logOmega, double *logPi, double *logA, double *logLam, double *cterm,
+                   double *vW, cudaStream_t st) {
+  k_prepass<<<K, 64, 0, st>>>(K, maxSr, d, covmode, Sr, gstart, ngroups, alpha, eta, epsilon, W, v, lambda, logOmega,
+                              logPi, logA, logLam, cterm, vW);
+  return 1;
+}
+
+int launch_build_records(const CentreView &C, int d, int dd, double *rec, cudaStream_t st) {
+  k_build_records<<<C.K, 64, 0, st>>>(C, d, dd, rec);
+  return 1;
+}
+
+int launch_sanitize_base(BaseView B, double *prior, double *A, double *mu, double *cov, cudaStream_t st) {
+  k_sanitize_base<<<(B.N + 127) / 128, 128, 0, st>>>(B, prior, A, mu, cov);
+  return 1;
+}
+
+int zhat_blocks(int N) { return (N + kZThreads - 1) / kZThreads; }
+
+int launch_zhat(int N, int K, int ngroups, const int *gstart, const double *L_elbo, const double *logOmega,
+                const double *Ntilde, double *zhat, double *Nj_part, int *cnt, double *lb_part, double *Nj, double *lb,
+                cudaStream_t st) {
+  const int nb = zhat_blocks(N);
+  k_zhat<<<nb, kZThreads, 0, st>>>(N, K, ngroups, gstart, L_elbo, logOmega, Ntilde, zhat, Nj_part, cnt, lb_part);
+  const int tot = K + 2 * ngroups;
+  k_zhat_reduce<<<(tot + 127) / 128, 128, 0, st>>>(nb, K, ngroups, Nj_part, lb_part, Nj, lb);
+  return 2;
+}
+
+int launch_list_scan(int N, int K, int chunk_len, const int *cnt, int *offs, int *seg_start, int *chunk_start,
+                     int *totals, cudaStream_t st) {
+  k_list_scan<<<1, 1024, sizeof(int) * K, st>>>(zhat_blocks(N), K, chunk_len, cnt, offs, seg_start, chunk_start,
+                                                totals);
+  return 1;
+}
+
+int launch_list_fill(int N, int K, int chunk_len, int nchunks, const double *zhat, const double *Ntilde,
+                     const int *offs, const int *seg_start, const int *chunk_start, PairItem *items, int2 *chunks,
+                     cudaStream_t st) {
+  k_list_fill<<<zhat_blocks(N), kZThreads, 0, st>>>(N, K, zhat, Ntilde, offs, seg_start, items);
+  if (nchunks > 0) k_chunks<<<(nchunks + 255) / 256, 256, 0, st>>>(K, chunk_len, seg_start, chunk_start, chunks);
+  return nchunks > 0 ? 2 : 1;
+}
+
+int launch_partial_reduce(int K, int per, const int *chunk_start, const double *partial, double *S_nu1, double *S_xi,
+                          double *S_pr, double *S_mu, double *S_Mu, int r, int d, int dd, cudaStream_t st) {
+  const int tot = K * per;
+  k_partial_reduce<<<(tot + 127) / 128, 128, 0, st>>>(K, per, chunk_start, partial, S_nu1, S_xi, S_pr, S_mu, S_Mu, r,
+                                                      d, dd);
+  return 1;
+}
+
+int launch_finalize(int K, int maxSr, int d, int covmode, const int *Sr, double *Nj, double *S_xi, double *S_pr,
+                    double *S_mu, double *S_Mu, cudaStream_t st) {
+  const int tot = K * maxSr;
+  k_finalize<<<(tot + 127) / 128, 128, 0, st>>>(K, maxSr, d, covmode, Sr, Nj, S_xi, S_pr, S_mu, S_Mu);
+  return 1;
+}
+
+}  // namespace vbhem

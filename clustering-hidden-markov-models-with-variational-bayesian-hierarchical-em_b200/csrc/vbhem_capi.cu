@@ -1,0 +1,709 @@
+// vbhem_capi.cu -- the C ABI declared in include/vbhem_b200.h.
+//
+// Host-side orchestration only: argument checks (the reference's gateway checks,
+// /root/reference/src/vbhem/vbhem_hmm_bwd_fwd_mex.c:334-377), device buffers, and
+// the launch sequence of one E-step.  All arithmetic is in the kernels.
+#include "../../include/vbhem_b200.h"
+#include "vbhem_internal.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace vbhem;
+
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(x)                                                                                  \
+  do {                                                                                         \
+    cudaError_t e_ = (x);                                                                      \
+    if (e_ != cudaSuccess)                                                                     \
+      return fail(e_ == cudaErrorMemoryAllocation ? VBHEM_ENOMEM : VBHEM_ECUDA, "%s: %s (%s:%d)", #x, \
+                  cudaGetErrorString(e_), __FILE__, __LINE__);                                 \
+  } while (0)
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+
+constexpr int kChunkLen = 16;
+
+}  // namespace
+
+struct vbhem_base {
+  int device = 0;
+  cudaStream_t own = nullptr, st = nullptr;
+  BaseView B{};
+  DevBuf bSb, bprior, bA, bmu, bcov, bNt;
+  // centre set (per call)
+  DevBuf cen_i, cen_d, hyp_d, rec;
+  // results and work lists
+  DevBuf L, z, flags, fbcount, Njp, lbp, cnt, offs, segs, items, chunks, partial, itemflags, scratch, pairs_out,
+      stats;
+  int *h_totals = nullptr;   // pinned
+  bool profile = false;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  double timings[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int kernel_choice = 0;
+  long long counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int lastK = 0;
+};
+
+namespace {
+
+struct CentreArgs {
+  int K, maxSr, ngroups, tau;
+  const int32_t *Sr, *group;
+  // log-domain (vbhem_estep) ...
+  const double *logPi, *logA, *m, *vW, *cterm, *logOmega;
+  // ... or hyper-parameters (vbhem_estep_hyp)
+  const double *alpha, *eta, *epsilon, *W, *v, *lambda;
+  bool hyp;
+};
+
+int check_common(vbhem_base *h, const CentreArgs &a, bool need_omega) {
+  if (!h) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: base handle is NULL");
+  if (a.K < 1) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: K must be >= 1");
+  if (a.maxSr < 1) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: maxSr must be >= 1");
+  if (a.tau < 1) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: tau must be >= 1");
+  if (!a.Sr) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: Sr is NULL");
+  for (int j = 0; j < a.K; j++)
+    if (a.Sr[j] < 1 || a.Sr[j] > a.maxSr)
+      return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: Sr[%d]=%d outside 1..maxSr=%d", j, a.Sr[j], a.maxSr);
+  if (a.hyp) {
+    if (!a.alpha || !a.eta || !a.epsilon || !a.m || !a.W || !a.v || !a.lambda)
+      return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: a centre hyper-parameter array is NULL");
+    if (h->B.d > 8) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: device pre-pass supports d <= 8");
+  } else {
+    if (!a.logPi || !a.logA || !a.m || !a.vW || !a.cterm || (need_omega && !a.logOmega))
+      return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: a centre array is NULL");
+  }
+  if (a.ngroups < 1) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: ngroups must be >= 1");
+  if (a.group) {
+    int prev = 0;
+    for (int j = 0; j < a.K; j++) {
+      if (a.group[j] < prev || a.group[j] > prev + 1 || a.group[j] >= a.ngroups || (j == 0 && a.group[0] != 0))
+        return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: group[] must be 0..ngroups-1, contiguous and ascending");
+      prev = a.group[j];
+    }
+    if (prev != a.ngroups - 1) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: group[] does not reach ngroups-1");
+  } else if (a.ngroups != 1) {
+    return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: ngroups > 1 needs group[]");
+  }
+  return VBHEM_OK;
+}
+
+// Device layout of the per-call centre buffers.
+struct CentreDev {
+  CentreView C{};
+  int *gstart = nullptr;
+  double *logLam = nullptr;
+};
+
+// Upload the centre set (running the pre-pass on the device if it is given as
+// hyper-parameters) and build the lattice records.  `launches` is incremented.
+int stage_centres(vbhem_base *h, const CentreArgs &a, CentreDev &cd, double *pre_host, long long &launches) {
+  const int K = a.K, r = a.maxSr, d = h->B.d, dd = h->B.dd;
+  CU(h->cen_i.ensure(sizeof(int) * (size_t)(K + a.ngroups + 1)));
+  int *dSr = h->cen_i.as<int>();
+  int *dgs = dSr + K;
+  std::vector<int> gs(a.ngroups + 1, 0);
+  if (a.group) {
+    for (int j = 0; j < K; j++) gs[a.group[j] + 1] = j + 1;
+  } else {
+    gs[1] = K;
+  }
+  CU(cudaMemcpyAsync(dSr, a.Sr, sizeof(int) * K, cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(dgs, gs.data(), sizeof(int) * (a.ngroups + 1), cudaMemcpyHostToDevice, h->st));
+  // log-domain block: logOmega[K] | logPi[rK] | logA[rrK] | logLam[rK] | cterm[rK] | m[d r K] | vW[dd r K]
+  const size_t nK = K, nr = (size_t)r * K, nrr = (size_t)r * r * K;
+  const size_t tot = nK + nr + nrr + nr + nr + d * nr + dd * nr;
+  CU(h->cen_d.ensure(sizeof(double) * tot));
+  double *p = h->cen_d.as<double>();
+  double *dOm = p; p += nK;
+  double *dPi = p; p += nr;
+  double *dA = p; p += nrr;
+  double *dLam = p; p += nr;
+  double *dCt = p; p += nr;
+  double *dm = p; p += d * nr;
+  double *dvW = p;
+  CU(cudaMemcpyAsync(dm, a.m, sizeof(double) * d * nr, cudaMemcpyHostToDevice, h->st));
+  if (a.hyp) {
+    const size_t th = nK + nr + nrr + dd * nr + nr + nr;
+    CU(h->hyp_d.ensure(sizeof(double) * th));
+    double *q = h->hyp_d.as<double>();
+    double *hal = q; q += nK;
+    double *het = q; q += nr;
+    double *hep = q; q += nrr;
+    double *hW = q; q += dd * nr;
+    double *hv = q; q += nr;
+    double *hl = q;
+    CU(cudaMemcpyAsync(hal, a.alpha, sizeof(double) * nK, cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemcpyAsync(het, a.eta, sizeof(double) * nr, cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemcpyAsync(hep, a.epsilon, sizeof(double) * nrr, cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemcpyAsync(hW, a.W, sizeof(double) * dd * nr, cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemcpyAsync(hv, a.v, sizeof(double) * nr, cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemcpyAsync(hl, a.lambda, sizeof(double) * nr, cudaMemcpyHostToDevice, h->st));
+    launches += launch_prepass(K, r, d, h->B.covmode, dSr, dgs, a.ngroups, hal, het, hep, hW, hv, hl, dOm, dPi, dA,
+                               dLam, dCt, dvW, h->st);
+    if (pre_host)   // logOmega | logPi | logA | logLambdaTilde are contiguous by construction
+      CU(cudaMemcpyAsync(pre_host, dOm, sizeof(double) * (nK + nr + nrr + nr), cudaMemcpyDeviceToHost, h->st));
+  } else {
+    if (a.logOmega) CU(cudaMemcpyAsync(dOm, a.logOmega, sizeof(double) * nK, cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemcpyAsync(dPi, a.logPi, sizeof(double) * nr, cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemcpyAsync(dA, a.logA, sizeof(double) * nrr, cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemcpyAsync(dCt, a.cterm, sizeof(double) * nr, cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemcpyAsync(dvW, a.vW, sizeof(double) * dd * nr, cudaMemcpyHostToDevice, h->st));
+  }
+  cd.C.K = K; cd.C.maxSr = r; cd.C.Sr = dSr; cd.C.group = nullptr;
+  cd.C.logPi = dPi; cd.C.logA = dA; cd.C.m = dm; cd.C.vW = dvW; cd.C.cterm = dCt; cd.C.logOmega = dOm;
+  cd.gstart = dgs; cd.logLam = dLam;
+  cd.C.rec = nullptr; cd.C.rec_stride = 0;
+  if (h->kernel_choice == 0 && h->B.maxSb <= kS8 && r <= kS8 && d <= 3) {
+    cd.C.rec_stride = lattice_rec_stride(d, dd);
+    CU(h->rec.ensure(sizeof(double) * (size_t)cd.C.rec_stride * K));
+    cd.C.rec = h->rec.as<double>();
+    launches += launch_build_records(cd.C, d, dd, h->rec.as<double>(), h->st);
+  }
+  return VBHEM_OK;
+}
+
+int ensure_scratch(vbhem_base *h, int maxSr, int T, long long want_warps, size_t &doubles) {
+  const size_t pw = general_scratch_per_warp(h->B.maxSb, maxSr, h->B.d, h->B.dd, T);
+  const size_t cap_bytes = (size_t)2 << 30;
+  long long warps = want_warps < 4 ? 4 : want_warps;
+  while (warps > 4 && warps * pw * sizeof(double) > cap_bytes) warps /= 2;
+  doubles = (size_t)warps * pw;
+  CU(h->scratch.ensure(sizeof(double) * doubles));
+  return VBHEM_OK;
+}
+
+// L_elbo for every pair into h->L (first pass).
+int first_pass(vbhem_base *h, const CentreDev &cd, int T, long long &launches) {
+  const long long np = (long long)h->B.N * cd.C.K;
+  CU(h->L.ensure(sizeof(double) * np));
+  PairWork W{nullptr, nullptr, 0, np};
+  PairOut O{};
+  O.mode = 0;
+  O.L_elbo = h->L.as<double>();
+  if (cd.C.rec && lattice_supported(h->B, cd.C, T, false)) {
+    CU(h->flags.ensure(np));
+    CU(h->fbcount.ensure(2 * sizeof(int)));
+    CU(cudaMemsetAsync(h->flags.p, 0, np, h->st));
+    CU(cudaMemsetAsync(h->fbcount.p, 0, 2 * sizeof(int), h->st));
+    Fallback fb{h->flags.as<unsigned char>(), h->fbcount.as<int>()};
+    launches += launch_lattice_bwd(h->B, cd.C, T, O.L_elbo, fb, h->st);
+    size_t sd;
+    int rc = ensure_scratch(h, cd.C.maxSr, T, 296, sd);
+    if (rc) return rc;
+    const int n = launch_general(h->B, cd.C, T, W, O, fb.flags, fb.count, h->scratch.as<double>(), sd, h->st);
+    if (n < 0) return fail(VBHEM_ENOMEM, "general kernel scratch too small");
+    launches += n;
+    h->counters[1] += np;
+  } else {
+    size_t sd;
+    int rc = ensure_scratch(h, cd.C.maxSr, T, np < 2368 ? np : 2368, sd);
+    if (rc) return rc;
+    const int n = launch_general(h->B, cd.C, T, W, O, nullptr, nullptr, h->scratch.as<double>(), sd, h->st);
+    if (n < 0) return fail(VBHEM_ENOMEM, "general kernel scratch too small");
+    launches += n;
+    h->counters[2] += np;
+  }
+  return VBHEM_OK;
+}
+
+struct StatsPtr { double *Nj, *nu1, *xi, *pr, *mu, *Mu, *lb; };
+
+StatsPtr carve_stats(double *s, int K, int r, int d, int dd, int ng) {
+  (void)ng;
+  StatsPtr p;
+  p.Nj = s; s += K;
+  p.nu1 = s; s += (size_t)r * K;
+  p.xi = s; s += (size_t)r * r * K;
+  p.pr = s; s += (size_t)r * K;
+  p.mu = s; s += (size_t)r * d * K;
+  p.Mu = s; s += (size_t)r * dd * K;
+  p.lb = s;
+  return p;
+}
+
+// The fused E-step on device buffers; stats_dev receives the raw sums.
+int estep_device(vbhem_base *h, const CentreArgs &a, double *stats_dev, double *pre_host) {
+  const int N = h->B.N, K = a.K, r = a.maxSr, d = h->B.d, dd = h->B.dd, T = a.tau;
+  long long launches = 0;
+  memset(h->counters, 0, sizeof h->counters);
+  auto mark = [&](int k) { if (h->profile) cudaEventRecord(h->ev[k], h->st); };
+  mark(0);
+  CentreDev cd;
+  int rc = stage_centres(h, a, cd, pre_host, launches);
+  if (rc) return rc;
+  mark(1);
+  rc = first_pass(h, cd, T, launches);
+  if (rc) return rc;
+  mark(2);
+
+  // responsibilities + deterministic active list
+  const long long np = (long long)N * K;
+  const int nb = zhat_blocks(N);
+  CU(h->z.ensure(sizeof(double) * np));
+  CU(h->Njp.ensure(sizeof(double) * (size_t)nb * K));
+  CU(h->lbp.ensure(sizeof(double) * (size_t)nb * 2 * a.ngroups));
+  CU(h->cnt.ensure(sizeof(int) * (size_t)nb * K));
+  CU(h->offs.ensure(sizeof(int) * (size_t)nb * K));
+  CU(h->segs.ensure(sizeof(int) * (size_t)(2 * (K + 1) + 2)));
+  StatsPtr S = carve_stats(stats_dev, K, r, d, dd, a.ngroups);
+  launches += launch_zhat(N, K, a.ngroups, cd.gstart, h->L.as<double>(), cd.C.logOmega, h->B.Ntilde,
+                          h->z.as<double>(), h->Njp.as<double>(), h->cnt.as<int>(), h->lbp.as<double>(), S.Nj, S.lb,
+                          h->st);
+  int *seg_start = h->segs.as<int>(), *chunk_start = seg_start + (K + 1), *totals = chunk_start + (K + 1);
+  launches += launch_list_scan(N, K, kChunkLen, h->cnt.as<int>(), h->offs.as<int>(), seg_start, chunk_start, totals,
+                               h->st);
+  CU(cudaMemcpyAsync(h->h_totals, totals, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  const int nact = h->h_totals[0], nch = h->h_totals[1];
+  h->counters[3] = nact;
+  const int per = stat_per(r, d, dd);
+  CU(h->items.ensure(sizeof(PairItem) * (size_t)(nact > 0 ? nact : 1)));
+  CU(h->chunks.ensure(sizeof(int2) * (size_t)(nch > 0 ? nch : 1)));
+  CU(h->partial.ensure(sizeof(double) * (size_t)per * (nch > 0 ? nch : 1)));
+  launches += launch_list_fill(N, K, kChunkLen, nch, h->z.as<double>(), h->B.Ntilde, h->offs.as<int>(), seg_start,
+                               chunk_start, h->items.as<PairItem>(), h->chunks.as<int2>(), h->st);
+  mark(3);
+  if (nch > 0) {
+    PairWork W{h->items.as<PairItem>(), h->chunks.as<int2>(), nch, nact};
+    PairOut O{};
+    O.mode = 2;
+    O.partial = h->partial.as<double>();
+    O.per = per;
+    if (cd.C.rec && lattice_supported(h->B, cd.C, T, true)) {
+      CU(h->itemflags.ensure(nact));
+      CU(cudaMemsetAsync(h->itemflags.p, 0, nact, h->st));
+      CU(cudaMemsetAsync(h->fbcount.as<int>() + 1, 0, sizeof(int), h->st));
+      Fallback fb{h->itemflags.as<unsigned char>(), h->fbcount.as<int>() + 1};
+      const int n1 = launch_lattice_full(h->B, cd.C, T, W, O, fb, h->st);
+      if (n1 < 0) return fail(VBHEM_ECUDA, "lattice kernel launch configuration failed");
+      launches += n1;
+      size_t sd;
+      rc = ensure_scratch(h, r, T, 296, sd);
+      if (rc) return rc;
+      const int n2 = launch_general(h->B, cd.C, T, W, O, fb.flags, fb.count, h->scratch.as<double>(), sd, h->st);
+      if (n2 < 0) return fail(VBHEM_ENOMEM, "general kernel scratch too small");
+      launches += n2;
+      h->counters[1] += nact;
+    } else {
+      size_t sd;
+      rc = ensure_scratch(h, r, T, nch < 2368 ? nch : 2368, sd);
+      if (rc) return rc;
+      const int n2 = launch_general(h->B, cd.C, T, W, O, nullptr, nullptr, h->scratch.as<double>(), sd, h->st);
+      if (n2 < 0) return fail(VBHEM_ENOMEM, "general kernel scratch too small");
+      launches += n2;
+      h->counters[2] += nact;
+    }
+  }
+  mark(4);
+  // chunk_start is all-zero when nothing is active, so the reduction writes zeros
+  launches += launch_partial_reduce(K, per, chunk_start, h->partial.as<double>(), S.nu1, S.xi, S.pr, S.mu, S.Mu, r, d,
+                                    dd, h->st);
+  mark(5);
+  CU(cudaGetLastError());
+  h->counters[0] = launches;
+  h->lastK = K;
+  return VBHEM_OK;
+}
+
+int estep_host(vbhem_base *h, const CentreArgs &a, double *L_elbo, double *zhat, double *stats, double *pre) {
+  if (!stats) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: stats is NULL");
+  const size_t ns = vbhem_stats_size(a.K, a.maxSr, h->B.d, h->B.covmode, a.ngroups);
+  CU(cudaSetDevice(h->device));
+  CU(h->stats.ensure(sizeof(double) * ns));
+  int rc = estep_device(h, a, h->stats.as<double>(), pre);
+  if (rc) return rc;
+  const size_t np = (size_t)h->B.N * a.K;
+  CU(cudaMemcpyAsync(stats, h->stats.p, sizeof(double) * ns, cudaMemcpyDeviceToHost, h->st));
+  if (L_elbo) CU(cudaMemcpyAsync(L_elbo, h->L.p, sizeof(double) * np, cudaMemcpyDeviceToHost, h->st));
+  if (zhat) CU(cudaMemcpyAsync(zhat, h->z.p, sizeof(double) * np, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  if (h->fbcount.p) {
+    int fb[2] = {0, 0};
+    CU(cudaMemcpy(fb, h->fbcount.p, sizeof fb, cudaMemcpyDeviceToHost));
+    h->counters[2] += fb[0] + fb[1];
+  }
+  return VBHEM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vbhem_version(void) { return 100; }
+const char *vbhem_last_error(void) { return g_err.c_str(); }
+
+int vbhem_device_count(int *count) {
+  if (!count) return fail(VBHEM_EINVAL, "count is NULL");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { *count = 0; return fail(VBHEM_ENODEVICE, "no CUDA device: %s", cudaGetErrorString(e)); }
+  *count = n;
+  return VBHEM_OK;
+}
+
+int vbhem_pack_base(int device, int N, const int32_t *Sb, int maxSb, int d, int covmode, const double *prior,
+                    const double *A, const double *mu, const double *cov, const double *Ntilde, vbhem_base_t **out) {
+  if (!out) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: out is NULL");
+  *out = nullptr;
+  if (N < 1 || maxSb < 1 || d < 1) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: N, maxSb, d must be >= 1");
+  if (covmode != VBHEM_COV_DIAG && covmode != VBHEM_COV_FULL)
+    return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: covmode must be 0 (diag) or 1 (full)");
+  if (!Sb || !prior || !A || !mu || !cov) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: a base array is NULL");
+  for (int i = 0; i < N; i++)
+    if (Sb[i] < 1 || Sb[i] > maxSb)
+      return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: Sb[%d]=%d outside 1..maxSb=%d", i, Sb[i], maxSb);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+    return fail(VBHEM_ENODEVICE, "no CUDA device (this library has no CPU path)");
+  if (device < 0 || device >= ndev) return fail(VBHEM_EINVAL, "device %d out of range (have %d)", device, ndev);
+  CU(cudaSetDevice(device));
+  vbhem_base *h = new (std::nothrow) vbhem_base;
+  if (!h) return fail(VBHEM_ENOMEM, "out of host memory");
+  h->device = device;
+  const int dd = covmode ? d * d : d;
+  auto bail = [&](int code) { vbhem_free_base(h); return code; };
+#define CUB(x)                                                                                                   \
+  do {                                                                                                           \
+    cudaError_t e_ = (x);                                                                                        \
+    if (e_ != cudaSuccess)                                                                                       \
+      return bail(fail(e_ == cudaErrorMemoryAllocation ? VBHEM_ENOMEM : VBHEM_ECUDA, "%s: %s", #x,               \
+                       cudaGetErrorString(e_)));                                                                 \
+  } while (0)
+  CUB(cudaStreamCreateWithFlags(&h->own, cudaStreamNonBlocking));
+  h->st = h->own;
+  CUB(cudaMallocHost(&h->h_totals, 4 * sizeof(int)));
+  for (int k = 0; k < 6; k++) CUB(cudaEventCreate(&h->ev[k]));
+  const size_t nS = (size_t)maxSb * N;
+  CUB(h->bSb.ensure(sizeof(int) * N));
+  CUB(h->bprior.ensure(sizeof(double) * nS));
+  CUB(h->bA.ensure(sizeof(double) * nS * maxSb));
+  CUB(h->bmu.ensure(sizeof(double) * nS * d));
+  CUB(h->bcov.ensure(sizeof(double) * nS * dd));
+  CUB(h->bNt.ensure(sizeof(double) * N));
+  CUB(cudaMemcpyAsync(h->bSb.p, Sb, sizeof(int) * N, cudaMemcpyHostToDevice, h->st));
+  CUB(cudaMemcpyAsync(h->bprior.p, prior, sizeof(double) * nS, cudaMemcpyHostToDevice, h->st));
+  CUB(cudaMemcpyAsync(h->bA.p, A, sizeof(double) * nS * maxSb, cudaMemcpyHostToDevice, h->st));
+  CUB(cudaMemcpyAsync(h->bmu.p, mu, sizeof(double) * nS * d, cudaMemcpyHostToDevice, h->st));
+  CUB(cudaMemcpyAsync(h->bcov.p, cov, sizeof(double) * nS * dd, cudaMemcpyHostToDevice, h->st));
+  if (Ntilde) {
+    CUB(cudaMemcpyAsync(h->bNt.p, Ntilde, sizeof(double) * N, cudaMemcpyHostToDevice, h->st));
+  } else {
+    std::vector<double> ones(N, 1.0);
+    CUB(cudaMemcpyAsync(h->bNt.p, ones.data(), sizeof(double) * N, cudaMemcpyHostToDevice, h->st));
+    CUB(cudaStreamSynchronize(h->st));
+  }
+  h->B.N = N; h->B.maxSb = maxSb; h->B.d = d; h->B.covmode = covmode; h->B.dd = dd;
+  h->B.Sb = h->bSb.as<int>(); h->B.prior = h->bprior.as<double>(); h->B.A = h->bA.as<double>();
+  h->B.mu = h->bmu.as<double>(); h->B.cov = h->bcov.as<double>(); h->B.Ntilde = h->bNt.as<double>();
+  launch_sanitize_base(h->B, h->bprior.as<double>(), h->bA.as<double>(), h->bmu.as<double>(), h->bcov.as<double>(),
+                       h->st);
+  CUB(cudaStreamSynchronize(h->st));
+  CUB(cudaGetLastError());
+#undef CUB
+  *out = h;
+  return VBHEM_OK;
+}
+
+int vbhem_free_base(vbhem_base_t *h) {
+  if (!h) return VBHEM_OK;
+  cudaSetDevice(h->device);
+  if (h->own) cudaStreamSynchronize(h->own);
+  DevBuf *all[] = {&h->bSb, &h->bprior, &h->bA, &h->bmu, &h->bcov, &h->bNt, &h->cen_i, &h->cen_d, &h->hyp_d, &h->rec,
+                   &h->L, &h->z, &h->flags, &h->fbcount, &h->Njp, &h->lbp, &h->cnt, &h->offs, &h->segs, &h->items,
+                   &h->chunks, &h->partial, &h->itemflags, &h->scratch, &h->pairs_out, &h->stats};
+  for (DevBuf *b : all) b->release();
+  if (h->h_totals) cudaFreeHost(h->h_totals);
+  for (int k = 0; k < 6; k++) if (h->ev[k]) cudaEventDestroy(h->ev[k]);
+  if (h->own) cudaStreamDestroy(h->own);
+  delete h;
+  return VBHEM_OK;
+}
+
+int vbhem_set_stream(vbhem_base_t *h, void *cuda_stream) {
+  if (!h) return fail(VBHEM_EINVAL, "base handle is NULL");
+  h->st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->own;
+  return VBHEM_OK;
+}
+
+int vbhem_synchronize(vbhem_base_t *h) {
+  if (!h) return fail(VBHEM_EINVAL, "base handle is NULL");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->st));
+  return VBHEM_OK;
+}
+
+int vbhem_set_kernel(vbhem_base_t *h, int which) {
+  if (!h) return fail(VBHEM_EINVAL, "base handle is NULL");
+  if (which != 0 && which != 1) return fail(VBHEM_EINVAL, "kernel must be 0 (auto) or 1 (general)");
+  h->kernel_choice = which;
+  return VBHEM_OK;
+}
+
+size_t vbhem_stats_size(int K, int maxSr, int d, int covmode, int ngroups) {
+  const int dd = covmode ? d * d : d;
+  return (size_t)K * (1 + stat_per(maxSr, d, dd)) + 2 * (size_t)ngroups;
+}
+
+int vbhem_stats_offsets(int K, int maxSr, int d, int covmode, int ngroups, size_t off[7]) {
+  (void)ngroups;
+  const int dd = covmode ? d * d : d;
+  const size_t r = maxSr;
+  off[0] = 0;
+  off[1] = off[0] + K;
+  off[2] = off[1] + r * K;
+  off[3] = off[2] + r * r * K;
+  off[4] = off[3] + r * K;
+  off[5] = off[4] + r * d * K;
+  off[6] = off[5] + r * dd * K;
+  return VBHEM_OK;
+}
+
+int vbhem_estep_pairs(vbhem_base_t *h, int K, const int32_t *Sr, int maxSr, int tau, const double *logPi,
+                      const double *logA, const double *m, const double *vW, const double *cterm, double *L_elbo,
+                      double *nu1, double *xi, double *pr, double *mu_out, double *Mu_out) {
+  CentreArgs a{};
+  a.K = K; a.maxSr = maxSr; a.ngroups = 1; a.tau = tau; a.Sr = Sr; a.group = nullptr;
+  a.logPi = logPi; a.logA = logA; a.m = m; a.vW = vW; a.cterm = cterm; a.logOmega = nullptr; a.hyp = false;
+  int rc = check_common(h, a, false);
+  if (rc) return rc;
+  if (!L_elbo) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: L_elbo is NULL");
+  const bool want = nu1 || xi || pr || mu_out || Mu_out;
+  if (want && !(nu1 && xi && pr && mu_out && Mu_out))
+    return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: per-pair outputs must be all NULL or all non-NULL");
+  CU(cudaSetDevice(h->device));
+  long long launches = 0;
+  memset(h->counters, 0, sizeof h->counters);
+  CentreDev cd;
+  rc = stage_centres(h, a, cd, nullptr, launches);
+  if (rc) return rc;
+  const int N = h->B.N, d = h->B.d, dd = h->B.dd, r = maxSr;
+  const size_t np = (size_t)N * K;
+  if (!want) {
+    rc = first_pass(h, cd, tau, launches);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(L_elbo, h->L.p, sizeof(double) * np, cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    h->counters[0] = launches;
+    return VBHEM_OK;
+  }
+  const int per = stat_per(r, d, dd);
+  CU(h->L.ensure(sizeof(double) * np));
+  CU(h->pairs_out.ensure(sizeof(double) * np * per));
+  CU(cudaMemsetAsync(h->pairs_out.p, 0, sizeof(double) * np * per, h->st));
+  double *po = h->pairs_out.as<double>();
+  PairOut O{};
+  O.mode = 1;
+  O.L_elbo = h->L.as<double>();
+  O.nu1 = po; po += np * r;
+  O.xi = po; po += np * r * r;
+  O.pr = po; po += np * r;
+  O.mu = po; po += np * r * d;
+  O.Mu = po;
+  PairWork W{nullptr, nullptr, 0, (long long)np};
+  if (cd.C.rec && lattice_supported(h->B, cd.C, tau, true)) {
+    CU(h->flags.ensure(np));
+    CU(h->fbcount.ensure(2 * sizeof(int)));
+    CU(cudaMemsetAsync(h->flags.p, 0, np, h->st));
+    CU(cudaMemsetAsync(h->fbcount.p, 0, 2 * sizeof(int), h->st));
+    Fallback fb{h->flags.as<unsigned char>(), h->fbcount.as<int>()};
+    const int n1 = launch_lattice_full(h->B, cd.C, tau, W, O, fb, h->st);
+    if (n1 < 0) return fail(VBHEM_ECUDA, "lattice kernel launch configuration failed");
+    launches += n1;
+    size_t sd;
+    rc = ensure_scratch(h, r, tau, 296, sd);
+    if (rc) return rc;
+    const int n2 = launch_general(h->B, cd.C, tau, W, O, fb.flags, fb.count, h->scratch.as<double>(), sd, h->st);
+    if (n2 < 0) return fail(VBHEM_ENOMEM, "general kernel scratch too small");
+    launches += n2;
+    h->counters[1] = (long long)np;
+  } else {
+    size_t sd;
+    rc = ensure_scratch(h, r, tau, np < 2368 ? (long long)np : 2368, sd);
+    if (rc) return rc;
+    const int n2 = launch_general(h->B, cd.C, tau, W, O, nullptr, nullptr, h->scratch.as<double>(), sd, h->st);
+    if (n2 < 0) return fail(VBHEM_ENOMEM, "general kernel scratch too small");
+    launches += n2;
+    h->counters[2] = (long long)np;
+  }
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(L_elbo, h->L.p, sizeof(double) * np, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaMemcpyAsync(nu1, O.nu1, sizeof(double) * np * r, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaMemcpyAsync(xi, O.xi, sizeof(double) * np * r * r, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaMemcpyAsync(pr, O.pr, sizeof(double) * np * r, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaMemcpyAsync(mu_out, O.mu, sizeof(double) * np * r * d, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaMemcpyAsync(Mu_out, O.Mu, sizeof(double) * np * r * dd, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  if (h->fbcount.p) {
+    int fbc[2] = {0, 0};
+    CU(cudaMemcpy(fbc, h->fbcount.p, sizeof fbc, cudaMemcpyDeviceToHost));
+    h->counters[2] += fbc[0];
+  }
+  h->counters[0] = launches;
+  return VBHEM_OK;
+}
+
+int vbhem_estep(vbhem_base_t *h, int K, const int32_t *Sr, int maxSr, const int32_t *group, int ngroups, int tau,
+                const double *logPi, const double *logA, const double *m, const double *vW, const double *cterm,
+                const double *logOmega, double *L_elbo, double *zhat, double *stats) {
+  CentreArgs a{};
+  a.K = K; a.maxSr = maxSr; a.ngroups = ngroups; a.tau = tau; a.Sr = Sr; a.group = group;
+  a.logPi = logPi; a.logA = logA; a.m = m; a.vW = vW; a.cterm = cterm; a.logOmega = logOmega; a.hyp = false;
+  int rc = check_common(h, a, true);
+  if (rc) return rc;
+  return estep_host(h, a, L_elbo, zhat, stats, nullptr);
+}
+
+int vbhem_estep_hyp(vbhem_base_t *h, int K, const int32_t *Sr, int maxSr, const int32_t *group, int ngroups, int tau,
+                    const double *alpha, const double *eta, const double *epsilon, const double *m, const double *W,
+                    const double *v, const double *lambda, double *L_elbo, double *zhat, double *stats, double *pre) {
+  CentreArgs a{};
+  a.K = K; a.maxSr = maxSr; a.ngroups = ngroups; a.tau = tau; a.Sr = Sr; a.group = group;
+  a.alpha = alpha; a.eta = eta; a.epsilon = epsilon; a.m = m; a.W = W; a.v = v; a.lambda = lambda; a.hyp = true;
+  int rc = check_common(h, a, true);
+  if (rc) return rc;
+  return estep_host(h, a, L_elbo, zhat, stats, pre);
+}
+
+int vbhem_estep_dev(vbhem_base_t *h, int K, const int32_t *Sr, int maxSr, const int32_t *group, int ngroups, int tau,
+                    const double *logPi, const double *logA, const double *m, const double *vW, const double *cterm,
+                    const double *logOmega, double *stats_dev) {
+  CentreArgs a{};
+  a.K = K; a.maxSr = maxSr; a.ngroups = ngroups; a.tau = tau; a.Sr = Sr; a.group = group;
+  a.logPi = logPi; a.logA = logA; a.m = m; a.vW = vW; a.cterm = cterm; a.logOmega = logOmega; a.hyp = false;
+  int rc = check_common(h, a, true);
+  if (rc) return rc;
+  if (!stats_dev) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: stats_dev is NULL");
+  CU(cudaSetDevice(h->device));
+  return estep_device(h, a, stats_dev, nullptr);
+}
+
+int vbhem_estep_hyp_dev(vbhem_base_t *h, int K, const int32_t *Sr, int maxSr, const int32_t *group, int ngroups,
+                        int tau, const double *alpha, const double *eta, const double *epsilon, const double *m,
+                        const double *W, const double *v, const double *lambda, double *stats_dev, double *pre) {
+  CentreArgs a{};
+  a.K = K; a.maxSr = maxSr; a.ngroups = ngroups; a.tau = tau; a.Sr = Sr; a.group = group;
+  a.alpha = alpha; a.eta = eta; a.epsilon = epsilon; a.m = m; a.W = W; a.v = v; a.lambda = lambda; a.hyp = true;
+  int rc = check_common(h, a, true);
+  if (rc) return rc;
+  if (!stats_dev) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: stats_dev is NULL");
+  CU(cudaSetDevice(h->device));
+  return estep_device(h, a, stats_dev, pre);
+}
+
+int vbhem_fetch(vbhem_base_t *h, double *L_elbo, double *zhat) {
+  if (!h) return fail(VBHEM_EINVAL, "base handle is NULL");
+  if (h->lastK < 1) return fail(VBHEM_EINVAL, "no E-step has run on this handle");
+  CU(cudaSetDevice(h->device));
+  const size_t np = (size_t)h->B.N * h->lastK;
+  if (L_elbo) CU(cudaMemcpyAsync(L_elbo, h->L.p, sizeof(double) * np, cudaMemcpyDeviceToHost, h->st));
+  if (zhat) CU(cudaMemcpyAsync(zhat, h->z.p, sizeof(double) * np, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  return VBHEM_OK;
+}
+
+int vbhem_finalize_stats(vbhem_base_t *h, int K, const int32_t *Sr, int maxSr, int ngroups, double *stats) {
+  if (!h || !Sr || !stats) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: NULL argument");
+  if (K < 1 || maxSr < 1 || ngroups < 1) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: bad sizes");
+  CU(cudaSetDevice(h->device));
+  const int d = h->B.d, dd = h->B.dd;
+  const size_t ns = vbhem_stats_size(K, maxSr, d, h->B.covmode, ngroups);
+  CU(h->stats.ensure(sizeof(double) * ns));
+  CU(h->cen_i.ensure(sizeof(int) * (size_t)(K + ngroups + 1)));
+  CU(cudaMemcpyAsync(h->cen_i.p, Sr, sizeof(int) * K, cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(h->stats.p, stats, sizeof(double) * ns, cudaMemcpyHostToDevice, h->st));
+  StatsPtr S = carve_stats(h->stats.as<double>(), K, maxSr, d, dd, ngroups);
+  launch_finalize(K, maxSr, d, h->B.covmode, h->cen_i.as<int>(), S.Nj, S.xi, S.pr, S.mu, S.Mu, h->st);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(stats, h->stats.p, sizeof(double) * ns, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  return VBHEM_OK;
+}
+
+int vbhem_finalize_stats_dev(vbhem_base_t *h, int K, const int32_t *Sr, int maxSr, int ngroups, double *stats_dev) {
+  if (!h || !Sr || !stats_dev) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: NULL argument");
+  if (K < 1 || maxSr < 1 || ngroups < 1) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: bad sizes");
+  CU(cudaSetDevice(h->device));
+  CU(h->cen_i.ensure(sizeof(int) * (size_t)(K + ngroups + 1)));
+  CU(cudaMemcpyAsync(h->cen_i.p, Sr, sizeof(int) * K, cudaMemcpyHostToDevice, h->st));
+  StatsPtr S = carve_stats(stats_dev, K, maxSr, h->B.d, h->B.dd, ngroups);
+  launch_finalize(K, maxSr, h->B.d, h->B.covmode, h->cen_i.as<int>(), S.Nj, S.xi, S.pr, S.mu, S.Mu, h->st);
+  CU(cudaGetLastError());
+  return VBHEM_OK;
+}
+
+int vbhem_set_profile(vbhem_base_t *h, int on) {
+  if (!h) return fail(VBHEM_EINVAL, "base handle is NULL");
+  h->profile = on != 0;
+  return VBHEM_OK;
+}
+
+int vbhem_last_timings(vbhem_base_t *h, double out[8]) {
+  if (!h || !out) return fail(VBHEM_EINVAL, "NULL argument");
+  if (!h->profile) return fail(VBHEM_EINVAL, "profiling is off (vbhem_set_profile)");
+  CU(cudaSetDevice(h->device));
+  CU(cudaEventSynchronize(h->ev[5]));
+  for (int k = 0; k < 8; k++) out[k] = 0.0;
+  for (int k = 0; k < 5; k++) {
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, h->ev[k], h->ev[k + 1]));
+    out[k] = ms;
+  }
+  float tot = 0.f;
+  CU(cudaEventElapsedTime(&tot, h->ev[0], h->ev[5]));
+  out[5] = tot;
+  return VBHEM_OK;
+}
+
+int vbhem_measure_fp64_peak(int device, double out[2]) {
+  if (!out) return fail(VBHEM_EINVAL, "NULL argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return fail(VBHEM_ENODEVICE, "no CUDA device");
+  if (device < 0 || device >= ndev) return fail(VBHEM_EINVAL, "device out of range");
+  CU(cudaSetDevice(device));
+  if (measure_fp64_peak(out) != 0) return fail(VBHEM_ECUDA, "fp64 peak measurement failed");
+  return VBHEM_OK;
+}
+
+int vbhem_last_counters(vbhem_base_t *h, long long out[8]) {
+  if (!h || !out) return fail(VBHEM_EINVAL, "NULL argument");
+  memcpy(out, h->counters, sizeof h->counters);
+  return VBHEM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,113 @@
+// vbhem_internal.cuh -- device-side views and launch entry points shared by the
+// kernels (vbhem_general.cu, vbhem_lattice.cu, vbhem_aux.cu) and the C ABI
+// (vbhem_capi.cu).  Not part of the public boundary (include/vbhem_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vbhem {
+
+constexpr double kTwoPi = 6.283185307179586476925286766559;
+constexpr double kTiny = 1e-280;     // below this a linear-domain lattice sum is not trusted
+constexpr double kSkipZ = 1e-8;      // vbhem_compute_Statistics.m:35
+constexpr int kS8 = 8;               // lattice kernel tile: 8 x 8 states
+
+// Base HMM set in HBM: the C-ABI column-major arrays, zero padded beyond Sb[i].
+struct BaseView {
+  int N, maxSb, d, covmode, dd;
+  const int *Sb;          // [N]
+  const double *prior;    // [maxSb, N]
+  const double *A;        // [maxSb(from), maxSb(to), N]
+  const double *mu;       // [d, maxSb, N]
+  const double *cov;      // [dd, maxSb, N]
+  const double *Ntilde;   // [N]
+};
+
+// Centre set after the pre-pass (log domain), C-ABI layout.
+struct CentreView {
+  int K, maxSr;
+  const int *Sr;          // [K]
+  const int *group;       // [K]
+  const double *logPi;    // [maxSr, K]
+  const double *logA;     // [maxSr(from), maxSr(to), K]
+  const double *m;        // [d, maxSr, K]
+  const double *vW;       // [dd, maxSr, K]
+  const double *cterm;    // [maxSr, K]
+  const double *logOmega; // [K]
+  // Linear-domain records for the lattice kernel (see build_records), one per centre:
+  //   expA[8][8] (row rho, col sigma) | expPi[8] | c0[8] | m[8][d] | vW[8][dd]
+  const double *rec;
+  int rec_stride;         // doubles per record
+};
+
+// One unit of second-pass work.
+struct PairItem { int i, j; double w; };
+
+// Where a pair kernel puts its results.
+//   mode 0: L_elbo only
+//   mode 1: literal per-pair outputs (Boundary-1)
+//   mode 2: weighted accumulation of the per-pair statistics into per-chunk
+//           partial sums (deterministic second pass of the fused E-step)
+struct PairOut {
+  int mode;
+  double *L_elbo;                               // [N, K]
+  double *nu1, *xi, *pr, *mu, *Mu;              // mode 1, leading dim maxSr, pair index p = i + N*j
+  double *partial;                              // mode 2: [nchunks][per] raw sums of one centre
+  int per;                                      // doubles per centre statistic block
+};
+
+// Work description: either every (i, j) pair or an explicit list cut in chunks
+// that never straddle two centres.
+struct PairWork {
+  const PairItem *items;  // nullptr => all pairs
+  const int2 *chunks;     // [nchunks] (start, len) into items; nullptr when items == nullptr
+  int nchunks;
+  long long npairs;
+};
+
+// Pairs the lattice kernel could not finish in the linear domain: one byte per
+// pair (first pass) or per work item (second pass) plus a device counter.
+struct Fallback { unsigned char *flags; int *count; };
+
+inline __host__ __device__ int stat_per(int r, int d, int dd) { return r + r * r + r + r * d + r * dd; }
+
+// ---- launchers (each returns the number of kernels it launched) -------------
+int launch_general(const BaseView &B, const CentreView &C, int T, const PairWork &W, const PairOut &O,
+                   const unsigned char *flags, const int *count, double *scratch, size_t scratch_doubles,
+                   cudaStream_t st);
+size_t general_scratch_per_warp(int maxSb, int maxSr, int d, int dd, int T);
+
+bool lattice_supported(const BaseView &B, const CentreView &C, int T, bool need_forward);
+int launch_lattice_bwd(const BaseView &B, const CentreView &C, int T, double *L_elbo, Fallback fb,
+                       cudaStream_t st);
+int launch_lattice_full(const BaseView &B, const CentreView &C, int T, const PairWork &W, const PairOut &O,
+                        Fallback fb, cudaStream_t st);
+int lattice_rec_stride(int d, int dd);
+
+// aux kernels (vbhem_aux.cu)
+int zhat_blocks(int N);
+int launch_prepass(int K, int maxSr, int d, int covmode, const int *Sr, const int *gstart, int ngroups,
+                   const double *alpha, const double *eta, const double *epsilon, const double *W, const double *v,
+                   const double *lambda, double *logOmega, double *logPi, double *logA, double *logLam, double *cterm,
+                   double *vW, cudaStream_t st);
+int launch_build_records(const CentreView &C, int d, int dd, double *rec, cudaStream_t st);
+int launch_sanitize_base(BaseView B, double *prior, double *A, double *mu, double *cov, cudaStream_t st);
+// zhat, Nj, lb (fixed-order sums) and the per-block counts of pairs with Z > 1e-8
+int launch_zhat(int N, int K, int ngroups, const int *gstart, const double *L_elbo, const double *logOmega,
+                const double *Ntilde, double *zhat, double *Nj_part, int *cnt, double *lb_part, double *Nj, double *lb,
+                cudaStream_t st);
+// deterministic (centre-major, base-ascending) list of those pairs, cut in chunks of chunk_len
+int launch_list_scan(int N, int K, int chunk_len, const int *cnt, int *offs, int *seg_start, int *chunk_start,
+                     int *totals, cudaStream_t st);
+int launch_list_fill(int N, int K, int chunk_len, int nchunks, const double *zhat, const double *Ntilde,
+                     const int *offs, const int *seg_start, const int *chunk_start, PairItem *items, int2 *chunks,
+                     cudaStream_t st);
+int launch_partial_reduce(int K, int per, const int *chunk_start, const double *partial, double *S_nu1, double *S_xi,
+                          double *S_pr, double *S_mu, double *S_Mu, int r, int d, int dd, cudaStream_t st);
+int launch_finalize(int K, int maxSr, int d, int covmode, const int *Sr, double *Nj, double *S_xi, double *S_pr,
+                    double *S_mu, double *S_Mu, cudaStream_t st);
+
+// fp64 peak micro-benchmark (vbhem_aux.cu): out[0] DMMA, out[1] DFMA TFLOP/s; returns 0 on success
+int measure_fp64_peak(double out[2]);
+
+}  // namespace vbhem

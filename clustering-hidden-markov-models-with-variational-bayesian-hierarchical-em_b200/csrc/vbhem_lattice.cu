@@ -1,0 +1,489 @@
+// vbhem_lattice.cu -- the tensor-core lattice kernels (sm_100a, fp64 DMMA).
+//
+// One warp owns one (base i, centre j) pair whose state lattice fits an 8 x 8
+// tile (Sb, Sr <= 8; smaller HMMs are padded).  Every 8x8 matrix of the
+// recursion lives in the accumulator layout of mma.sync.m8n8k4.f64 -- lane
+// (g = lane/4, q = lane%4) holds elements [g][2q] and [g][2q+1] -- and every
+// contraction is two DMMAs:  D(m|n) = sum_c A[m][c] * X[n][c]   ("mma_nt").
+// Feeding the *variable* matrix as the B operand makes each product come out
+// transposed, which is exactly what the alternation "contract over centre
+// states, then over base states" of the recursion needs, so the backward pass
+// runs with no data movement between lanes except one 4-lane max and one
+// 2-value shuffle per step.
+//
+// Arithmetic: the reference evaluates, per time step and per rho, a max-shifted
+// log-sum-exp over sigma of  logA[rho,sigma] + E[beta,sigma] + L[beta,sigma]
+// (/root/reference/src/vbhem/vbhem_hmm_bwd_fwd_mex.c:920-1000: 2*Sb*Sr^2 exp per
+// step).  Here the shift is taken per beta only,
+//     c[beta] = max_sigma G[beta,sigma],  G = E + L,
+//     Bm[beta,sigma] = exp(G[beta,sigma] - c[beta]),
+//     S[beta,rho] = sum_sigma expA[rho,sigma] * Bm[beta,sigma]      (DMMA)
+//     lse[beta,rho] = c[beta] + log S[beta,rho]
+//     Theta[rho,sigma,beta] = expA[rho,sigma] * Bm[beta,sigma] / S[beta,rho]
+// which needs Sb*Sr exp + Sb*Sr log per step and is the same number up to
+// rounding whenever S does not underflow.  When it does (S < 1e-280, or
+// NaN/Inf in the data) the pair is flagged and redone by the general log-space
+// kernel, so every result the caller sees keeps the reference's semantics.
+// The forward pass (vbhem_hmm_bwd_fwd_mex.c:1100-1298) needs only Bm and 1/S of
+// each step (2 x 64 doubles instead of the 512-double Theta slice), kept in
+// shared memory and read back transposed.
+#include "vbhem_internal.cuh"
+
+#include <type_traits>
+
+namespace vbhem {
+
+namespace {
+
+constexpr int kLd = 10;           // padded row stride of an 8x8 tile in shared memory (doubles)
+constexpr int kTile = 8 * kLd;    // doubles per tile
+
+struct Frag { double x0, x1; };
+
+__device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+// D(m|n) = sum_c A[m][c] * X[n][c], all three in accumulator layout.
+__device__ __forceinline__ void mma_nt_acc(Frag &D, const Frag &A, const Frag &X) {
+  dmma(D.x0, D.x1, A.x0, X.x0);
+  dmma(D.x0, D.x1, A.x1, X.x1);
+}
+__device__ __forceinline__ Frag mma_nt(const Frag &A, const Frag &X) {
+  Frag D{0.0, 0.0};
+  mma_nt_acc(D, A, X);
+  return D;
+}
+
+__device__ __forceinline__ double quad_max(double v) {
+  v = fmax(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  v = fmax(v, __shfl_xor_sync(0xffffffffu, v, 2));
+  return v;
+}
+__device__ __forceinline__ double quad_sum(double v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+__device__ __forceinline__ double across_sum(double v) {   // over g, for one q
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  return v;
+}
+
+__device__ __forceinline__ void tile_store(double *tile, int g, int q, const Frag &f) {
+  *reinterpret_cast<double2 *>(tile + g * kLd + 2 * q) = make_double2(f.x0, f.x1);
+}
+__device__ __forceinline__ Frag tile_load_t(const double *tile, int g, int q) {   // transposed fragment
+  return Frag{tile[(2 * q) * kLd + g], tile[(2 * q + 1) * kLd + g]};
+}
+
+// ---- per-pair constants -----------------------------------------------------
+template <int D, bool FULL>
+struct BaseConst {
+  static constexpr int DD = FULL ? D * D : D;
+  Frag Ab;        // Ab(beta' = g | beta = 2q+e)  = A[from g, to 2q+e]
+  Frag AbT;       // [g][2q+e] = A[from 2q+e, to g]
+  double prior;   // prior[g]
+  double mu[D];   // centres of state g
+  double cov[DD]; // covars of state g
+  int Sb;
+};
+
+template <int D, bool FULL>
+__device__ __forceinline__ void load_base(BaseConst<D, FULL> &b, const BaseView &B, int i, int g, int q) {
+  constexpr int DD = BaseConst<D, FULL>::DD;
+  const int ld = B.maxSb;
+  const double *A = B.A + (size_t)ld * ld * i;
+  b.Sb = B.Sb[i];
+  const int c0 = 2 * q, c1 = 2 * q + 1;
+  b.Ab.x0 = (g < ld && c0 < ld) ? A[g + ld * c0] : 0.0;
+  b.Ab.x1 = (g < ld && c1 < ld) ? A[g + ld * c1] : 0.0;
+  b.AbT.x0 = (g < ld && c0 < ld) ? A[c0 + ld * g] : 0.0;
+  b.AbT.x1 = (g < ld && c1 < ld) ? A[c1 + ld * g] : 0.0;
+  b.prior = g < ld ? B.prior[g + (size_t)ld * i] : 0.0;
+#pragma unroll
+  for (int k = 0; k < D; k++) b.mu[k] = g < ld ? B.mu[k + D * (g + (size_t)ld * i)] : 0.0;
+#pragma unroll
+  for (int k = 0; k < DD; k++) b.cov[k] = g < ld ? B.cov[k + DD * (g + (size_t)ld * i)] : 0.0;
+}
+
+// Centre record (built by k_build_records in vbhem_aux.cu), doubles:
+//   [0,64) expA[rho][sigma] | [64,72) expPi | [72,80) c0 = d*log(2pi)+cterm (+inf when padded)
+//   [80, 80+8D) m[sigma][k] | [80+8D, 80+8D+8DD) vW[sigma][kl]
+template <int D, bool FULL>
+struct CentreConst {
+  Frag expA;      // (rho = g | sigma = 2q+e)
+  Frag expAT;     // [g][2q+e] = expA[rho = 2q+e][sigma = g]
+  Frag expPi;     // sigma = 2q+e
+};
+
+template <int D, bool FULL>
+__device__ __forceinline__ void load_centre(CentreConst<D, FULL> &c, const double *rec, int g, int q) {
+  c.expA = Frag{rec[g * 8 + 2 * q], rec[g * 8 + 2 * q + 1]};
+  c.expAT = Frag{rec[(2 * q) * 8 + g], rec[(2 * q + 1) * 8 + g]};
+  c.expPi = Frag{rec[64 + 2 * q], rec[64 + 2 * q + 1]};
+}
+
+// E(beta = g | sigma = 2q+e), vbhem_hmm_bwd_fwd_mex.c:796-843 (full) / :744-759 (diag).
+template <int D, bool FULL>
+__device__ __forceinline__ Frag emission(const BaseConst<D, FULL> &b, const double *rec, int g, int q) {
+  constexpr int DD = BaseConst<D, FULL>::DD;
+  double out[2];
+#pragma unroll
+  for (int e = 0; e < 2; e++) {
+    const int sg = 2 * q + e;
+    const double *m = rec + 80 + sg * D;
+    const double *P = rec + 80 + 8 * D + sg * DD;
+    double acc = rec[72 + sg];
+    if (FULL) {
+#pragma unroll
+      for (int k = 0; k < DD; k++) acc += P[k] * b.cov[k];
+#pragma unroll
+      for (int tj = 0; tj < D; tj++) {
+        double t = 0.0;
+#pragma unroll
+        for (int ti = 0; ti < D; ti++) t += (b.mu[ti] - m[ti]) * P[ti + D * tj];
+        acc += t * (b.mu[tj] - m[tj]);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < D; k++) {
+        const double df = b.mu[k] - m[k];
+        acc += P[k] * b.cov[k];
+        acc += P[k] * (df * df);
+      }
+    }
+    // padded base states: any finite row works (their weights are zero); 0 keeps S = rowsum(expA)
+    out[e] = (g < b.Sb) ? -0.5 * acc : (isinf(rec[72 + sg]) ? -INFINITY : 0.0);
+  }
+  return Frag{out[0], out[1]};
+}
+
+// One backward step (t = T-1 .. 1).  In: L(beta|sigma).  Out: L(beta'|rho) of the
+// previous time step.  With STORE the step's Bm(beta|sigma) and 1/S^T(rho|beta)
+// go to shared memory for the forward pass.  Returns false if a sum underflowed.
+template <bool STORE>
+__device__ __forceinline__ bool bwd_step(const Frag &E, Frag &L, const Frag &expA, const Frag &Ab, double *sBm,
+                                         double *sInvS, int g, int q) {
+  const Frag G{E.x0 + L.x0, E.x1 + L.x1};
+  const double c = quad_max(fmax(G.x0, G.x1));                 // c[beta = g]
+  const Frag Bm{exp(G.x0 - c), exp(G.x1 - c)};
+  const Frag ST = mma_nt(expA, Bm);                            // S^T(rho = g | beta = 2q+e)
+  const bool ok = (ST.x0 >= kTiny) && (ST.x1 >= kTiny);
+  const double cb0 = __shfl_sync(0xffffffffu, c, (2 * q) * 4);
+  const double cb1 = __shfl_sync(0xffffffffu, c, (2 * q + 1) * 4);
+  const Frag ell{cb0 + log(ST.x0), cb1 + log(ST.x1)};          // lse^T(rho | beta)
+  L = mma_nt(Ab, ell);                                         // L(beta' = g | rho = 2q+e)
+  if (STORE) {
+    tile_store(sBm, g, q, Bm);
+    tile_store(sInvS, g, q, Frag{1.0 / ST.x0, 1.0 / ST.x1});
+  }
+  return ok;
+}
+
+// Termination (vbhem_hmm_bwd_fwd_mex.c:1029-1080).  Returns L_elbo (all lanes) and
+// nu_1(beta = g | sigma = 2q+e) = prior * Theta_1.
+__device__ __forceinline__ double terminate(const Frag &E, const Frag &L, const Frag &expPi, double prior, int q,
+                                            Frag &nu1, bool &ok) {
+  const Frag G{E.x0 + L.x0, E.x1 + L.x1};
+  const double c = quad_max(fmax(G.x0, G.x1));
+  const Frag Bm{exp(G.x0 - c), exp(G.x1 - c)};
+  const double s = quad_sum(expPi.x0 * Bm.x0 + expPi.x1 * Bm.x1);
+  ok = ok && (s >= kTiny);
+  const double ell = c + log(s);
+  const double Lq = across_sum(q == 0 ? prior * ell : 0.0);    // valid in lanes with q == 0
+  const double w = prior / s;
+  nu1 = Frag{w * expPi.x0 * Bm.x0, w * expPi.x1 * Bm.x1};
+  return __shfl_sync(0xffffffffu, Lq, 0);
+}
+
+// ---- first pass: L_elbo for every pair --------------------------------------
+constexpr int kBwdWarps = 8;
+
+template <int D, bool FULL>
+__global__ void __launch_bounds__(kBwdWarps * 32, 2)
+k_lattice_bwd(BaseView B, CentreView C, int T, int kc, double *L_elbo, Fallback fb) {
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+  const int warp = threadIdx.x >> 5;
+  const int j0 = blockIdx.y * kc;
+  const int nj = min(kc, C.K - j0);
+  const int rs = C.rec_stride;
+  for (int x = threadIdx.x; x < nj * rs; x += blockDim.x) smem[x] = C.rec[(size_t)j0 * rs + x];
+  __syncthreads();
+
+  for (int i = blockIdx.x * kBwdWarps + warp; i < B.N; i += gridDim.x * kBwdWarps) {
+    BaseConst<D, FULL> b;
+    load_base(b, B, i, g, q);
+    for (int jj = 0; jj < nj; jj++) {
+      const double *rec = smem + jj * rs;
+      CentreConst<D, FULL> c;
+      load_centre(c, rec, g, q);
+      const Frag E = emission(b, rec, g, q);
+      Frag L{0.0, 0.0};
+      bool ok = true;
+      for (int t = T - 1; t >= 1; t--) ok = bwd_step<false>(E, L, c.expA, b.Ab, nullptr, nullptr, g, q) && ok;
+      Frag nu1;
+      const double Le = terminate(E, L, c.expPi, b.prior, q, nu1, ok);
+      ok = __all_sync(0xffffffffu, ok);
+      if (lane == 0) {
+        const size_t p = (size_t)i + (size_t)B.N * (j0 + jj);
+        L_elbo[p] = Le;
+        if (!ok) { fb.flags[p] = 1; atomicAdd(fb.count, 1); }
+      }
+    }
+  }
+}
+
+// ---- full pass: backward + forward + statistics -----------------------------
+template <int D, bool FULL>
+struct PairStats {
+  static constexpr int DD = FULL ? D * D : D;
+  double nu1, pr, mu[D], Mu[DD];   // row sigma = g, replicated over q
+  Frag xi;                         // (sigma = g | rho = 2q+e)
+};
+
+// smem (per warp): (T-1) x {Bm tile, invS tile} + one exchange tile.
+template <int D, bool FULL>
+__device__ __forceinline__ bool pair_full(const BaseView &B, int i, const BaseConst<D, FULL> &b,
+                                          const CentreConst<D, FULL> &c, const double *rec, int T, double *sm,
+                                          int g, int q, double &Lout, PairStats<D, FULL> &st) {
+  constexpr int DD = BaseConst<D, FULL>::DD;
+  double *xch = sm + (size_t)2 * kTile * (T - 1);
+  const Frag E = emission(b, rec, g, q);
+  Frag L{0.0, 0.0};
+  bool ok = true;
+  for (int t = T - 1; t >= 1; t--) {
+    double *s = sm + (size_t)2 * kTile * (t - 1);
+    ok = bwd_step<true>(E, L, c.expA, b.Ab, s, s + kTile, g, q) && ok;
+  }
+  Frag nu1;
+  Lout = terminate(E, L, c.expPi, b.prior, q, nu1, ok);
+  ok = __all_sync(0xffffffffu, ok);
+  if (!ok) return false;
+
+  // nu_1 (beta|sigma) -> nuT (sigma = g | gamma = 2q+e)
+  tile_store(xch, g, q, nu1);
+  __syncwarp();
+  Frag nuT = tile_load_t(xch, g, q);
+  __syncwarp();
+  st.nu1 = quad_sum(nuT.x0 + nuT.x1);
+  Frag n = nuT;
+  Frag Xi{0.0, 0.0};
+  for (int t = 1; t < T; t++) {
+    const double *s = sm + (size_t)2 * kTile * (t - 1);
+    const Frag BmT = tile_load_t(s, g, q);                 // (sigma' = g | gamma' = 2q+e)
+    const Frag invS = tile_load_t(s + kTile, g, q);        // (gamma' = g | rho = 2q+e)
+    const Frag foo = mma_nt(b.AbT, nuT);                   // (gamma' | rho): sum_gamma A[gamma,gamma'] nu[rho,gamma]
+    const Frag h{foo.x0 * invS.x0, foo.x1 * invS.x1};
+    tile_store(xch, g, q, h);
+    const Frag M = mma_nt(c.expAT, h);                     // (sigma' | gamma'): sum_rho expA[rho,sigma'] h[gamma',rho]
+    nuT = Frag{BmT.x0 * M.x0, BmT.x1 * M.x1};
+    n.x0 += nuT.x0; n.x1 += nuT.x1;
+    __syncwarp();
+    const Frag hT = tile_load_t(xch, g, q);                // (rho = g | gamma' = 2q+e)
+    __syncwarp();
+    mma_nt_acc(Xi, BmT, hT);                               // (sigma | rho): sum_gamma Bm[gamma,sigma] h[gamma,rho]
+  }
+  st.xi = Frag{c.expAT.x0 * Xi.x0, c.expAT.x1 * Xi.x1};    // xi_hat[rho = 2q+e, sigma = g]
+
+  // emission statistics (vbhem_hmm_bwd_fwd_mex.c:1348-1469): row sigma = g, gamma = 2q+e
+  st.pr = quad_sum(n.x0 + n.x1);
+  const int ld = B.maxSb;
+  const int s0 = 2 * q, s1 = 2 * q + 1;
+  double m0[D], m1[D], c0[DD], c1[DD];
+#pragma unroll
+  for (int k = 0; k < D; k++) {
+    m0[k] = s0 < ld ? B.mu[k + D * (s0 + (size_t)ld * i)] : 0.0;
+    m1[k] = s1 < ld ? B.mu[k + D * (s1 + (size_t)ld * i)] : 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < DD; k++) {
+    c0[k] = s0 < ld ? B.cov[k + DD * (s0 + (size_t)ld * i)] : 0.0;
+    c1[k] = s1 < ld ? B.cov[k + DD * (s1 + (size_t)ld * i)] : 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < D; k++) st.mu[k] = quad_sum(n.x0 * m0[k] + n.x1 * m1[k]);
+#pragma unroll
+  for (int kl = 0; kl < DD; kl++) {
+    const int k = FULL ? kl / D : kl, l = FULL ? kl % D : kl;
+    st.Mu[kl] = quad_sum(n.x0 * (m0[k] * m0[l] + c0[kl]) + n.x1 * (m1[k] * m1[l] + c1[kl]));
+  }
+  return true;
+}
+
+template <int D, bool FULL>
+__global__ void __launch_bounds__(512, 1)
+k_lattice_full(BaseView B, CentreView C, int T, PairWork W, PairOut O, Fallback fb, int warps_per_block) {
+  extern __shared__ __align__(16) double smem[];
+  constexpr int DD = BaseConst<D, FULL>::DD;
+  const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+  const int warp = threadIdx.x >> 5;
+  double *sm = smem + (size_t)warp * ((size_t)2 * kTile * (T - 1) + kTile);
+  const long long gw = (long long)blockIdx.x * warps_per_block + warp;
+  const long long nw = (long long)gridDim.x * warps_per_block;
+  const int ro = C.maxSr;
+
+  if (W.items == nullptr) {
+    // every pair, literal outputs (mode 1) or L_elbo only (mode 0 is served by k_lattice_bwd)
+    for (long long p = gw; p < W.npairs; p += nw) {
+      const int i = (int)(p % B.N), j = (int)(p / B.N);
+      BaseConst<D, FULL> b;
+      CentreConst<D, FULL> c;
+      const double *rec = C.rec + (size_t)C.rec_stride * j;
+      load_base(b, B, i, g, q);
+      load_centre(c, rec, g, q);
+      PairStats<D, FULL> st;
+      double Le;
+      const bool ok = pair_full(B, i, b, c, rec, T, sm, g, q, Le, st);
+      if (!ok) {
+        if (lane == 0) { fb.flags[p] = 1; atomicAdd(fb.count, 1); }
+        continue;
+      }
+      if (lane == 0 && O.L_elbo) O.L_elbo[p] = Le;
+      if (g < ro) {
+        if (2 * q < ro) O.xi[(2 * q) + ro * (g + (size_t)ro * p)] = st.xi.x0;
+        if (2 * q + 1 < ro) O.xi[(2 * q + 1) + ro * (g + (size_t)ro * p)] = st.xi.x1;
+        if (q == 0) {
+          O.nu1[g + (size_t)ro * p] = st.nu1;
+          O.pr[g + (size_t)ro * p] = st.pr;
+#pragma unroll
+          for (int k = 0; k < D; k++) O.mu[g + ro * (k + (size_t)D * p)] = st.mu[k];
+#pragma unroll
+          for (int k = 0; k < DD; k++) O.Mu[g + ro * (k + (size_t)DD * p)] = st.Mu[k];
+        }
+      }
+    }
+    return;
+  }
+
+  // second pass of the fused E-step: one warp per chunk (single centre), weighted sums in registers
+  for (int ch = (int)gw; ch < W.nchunks; ch += (int)nw) {
+    const int2 cr = W.chunks[ch];
+    const int j = W.items[cr.x].j;
+    CentreConst<D, FULL> c;
+    const double *rec = C.rec + (size_t)C.rec_stride * j;
+    load_centre(c, rec, g, q);
+    PairStats<D, FULL> acc;
+    acc.nu1 = acc.pr = 0.0;
+    acc.xi = Frag{0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < D; k++) acc.mu[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < DD; k++) acc.Mu[k] = 0.0;
+    for (int e = 0; e < cr.y; e++) {
+      const PairItem it = W.items[cr.x + e];
+      BaseConst<D, FULL> b;
+      load_base(b, B, it.i, g, q);
+      PairStats<D, FULL> st;
+      double Le;
+      const bool ok = pair_full(B, it.i, b, c, rec, T, sm, g, q, Le, st);
+      if (!ok) {
+        if (lane == 0) { fb.flags[cr.x + e] = 1; atomicAdd(fb.count, 1); }
+        continue;
+      }
+      acc.nu1 += it.w * st.nu1;
+      acc.pr += it.w * st.pr;
+      acc.xi.x0 += it.w * st.xi.x0;
+      acc.xi.x1 += it.w * st.xi.x1;
+#pragma unroll
+      for (int k = 0; k < D; k++) acc.mu[k] += it.w * st.mu[k];
+#pragma unroll
+      for (int k = 0; k < DD; k++) acc.Mu[k] += it.w * st.Mu[k];
+    }
+    double *part = O.partial + (size_t)O.per * ch;
+    double *p_nu1 = part, *p_xi = part + ro, *p_pr = p_xi + ro * ro, *p_mu = p_pr + ro, *p_Mu = p_mu + ro * D;
+    if (g < ro) {
+      if (2 * q < ro) p_xi[(2 * q) + ro * g] = acc.xi.x0;
+      if (2 * q + 1 < ro) p_xi[(2 * q + 1) + ro * g] = acc.xi.x1;
+      if (q == 0) {
+        p_nu1[g] = acc.nu1;
+        p_pr[g] = acc.pr;
+#pragma unroll
+        for (int k = 0; k < D; k++) p_mu[g + ro * k] = acc.mu[k];
+#pragma unroll
+        for (int k = 0; k < DD; k++) p_Mu[g + ro * k] = acc.Mu[k];
+      }
+    }
+  }
+}
+
+constexpr size_t kSmemBudget = 200 * 1024;
+
+size_t full_smem_per_warp(int T) { return sizeof(double) * ((size_t)2 * kTile * (T > 1 ? T - 1 : 0) + kTile); }
+
+template <typename F>
+int dispatch(int d, int covmode, F f) {
+  if (covmode) {
+    if (d == 1) return f(std::integral_constant<int, 1>{}, std::true_type{});
+    if (d == 2) return f(std::integral_constant<int, 2>{}, std::true_type{});
+    if (d == 3) return f(std::integral_constant<int, 3>{}, std::true_type{});
+  } else {
+    if (d == 1) return f(std::integral_constant<int, 1>{}, std::false_type{});
+    if (d == 2) return f(std::integral_constant<int, 2>{}, std::false_type{});
+    if (d == 3) return f(std::integral_constant<int, 3>{}, std::false_type{});
+  }
+  return -1;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+}  // namespace
+
+int lattice_rec_stride(int d, int dd) { return 80 + 8 * d + 8 * dd; }
+
+bool lattice_supported(const BaseView &B, const CentreView &C, int T, bool need_forward) {
+  if (B.maxSb > kS8 || C.maxSr > kS8 || B.d < 1 || B.d > 3 || T < 1) return false;
+  if (need_forward && full_smem_per_warp(T) > kSmemBudget) return false;
+  return true;
+}
+
+int launch_lattice_bwd(const BaseView &B, const CentreView &C, int T, double *L_elbo, Fallback fb,
+                       cudaStream_t st) {
+  const int rs = C.rec_stride;
+  int kc = (int)((96 * 1024) / (sizeof(double) * rs));
+  if (kc > C.K) kc = C.K;
+  const size_t smem = sizeof(double) * (size_t)kc * rs;
+  const int ny = (C.K + kc - 1) / kc;
+  int nx = (B.N + kBwdWarps - 1) / kBwdWarps;
+  const int cap = 2 * sm_count();
+  if (nx > cap) nx = cap;
+  return dispatch(B.d, B.covmode, [&](auto Dc, auto Fc) {
+    auto kern = k_lattice_bwd<decltype(Dc)::value, decltype(Fc)::value>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<dim3(nx, ny), kBwdWarps * 32, smem, st>>>(B, C, T, kc, L_elbo, fb);
+    return 1;
+  });
+}
+
+int launch_lattice_full(const BaseView &B, const CentreView &C, int T, const PairWork &W, const PairOut &O,
+                        Fallback fb, cudaStream_t st) {
+  const size_t pw = full_smem_per_warp(T);
+  int wpb = (int)(kSmemBudget / pw);
+  if (wpb > 16) wpb = 16;
+  if (wpb < 1) return -1;
+  const long long units = W.items ? W.nchunks : W.npairs;
+  if (units <= 0) return 0;
+  long long blocks = (units + wpb - 1) / wpb;
+  const long long cap = sm_count();
+  if (blocks > cap) blocks = cap;
+  const size_t smem = pw * wpb;
+  return dispatch(B.d, B.covmode, [&](auto Dc, auto Fc) {
+    auto kern = k_lattice_full<decltype(Dc)::value, decltype(Fc)::value>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<(unsigned)blocks, wpb * 32, smem, st>>>(B, C, T, W, O, fb, wpb);
+    return 1;
+  });
+}
+
+}  // namespace vbhem

@@ -1,0 +1,179 @@
+/* vbhem_b200.h -- C ABI of the B200-native VBHEM-H3M E-step (libvbhem_b200.so).
+ *
+ * This is the drop-in boundary for ONE path of the reference toolbox: the
+ * E-step that the reference runs through its MEX plug-in
+ *     [L_elbo,nu_1,emit_pr,emit_mu,emit_M,sum_xi] =
+ *         vbhem_hmm_bwd_fwd_mex(h3m_b.hmm,h3m_r.hmm,T,maxN,maxN2[,logdetCovPlusDdivlamR,invCovR])
+ * (gateway:  /root/reference/src/vbhem/vbhem_hmm_bwd_fwd_mex.c:288-289;
+ *  call sites: /root/reference/src/vbhem/vbhem_h3m_c_step_fc.m:175-176,193-194)
+ * together with the MATLAB statements that consume its outputs every
+ * iteration (pre-pass :118-165,180-191; responsibilities :271-283; statistics
+ * reduction /root/reference/src/vbhem/vbhem_compute_Statistics.m:33-82; the
+ * N-sized lower-bound terms /root/reference/src/vbhem/vbhemh3m_lb.m:90,93,107).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every array is fp64 (or int32 where
+ *     stated), COLUMN-MAJOR, exactly what mxGetPr() of the corresponding MATLAB
+ *     array yields, so a MEX gateway needs no transposes;
+ *   - ragged sets are padded: leading dimensions are maxSb / maxSr, entries
+ *     beyond an HMM's own state count are ignored on input and zero on output;
+ *   - every function returns VBHEM_OK (0) or a negative VBHEM_E* code and never
+ *     throws; vbhem_last_error() gives the message of the calling thread's last
+ *     failure.  NaN / Inf in the data are data, not errors: they propagate into
+ *     L_elbo exactly as in the reference so the caller's NaN guard
+ *     (vbhem_h3m_c_step_fc.m:338-354) still fires;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry
+ *     point fails with VBHEM_ENODEVICE.
+ *
+ * Index names: N = number of base HMMs (Kb), K = number of centre HMMs (Kr),
+ * b = base states, r = centre states, d = emission dimension, dd = d*d (full
+ * covariance) or d (diagonal), T = tau, pair index p = i + N*j.
+ */
+#ifndef VBHEM_B200_H
+#define VBHEM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VBHEM_OK          0
+#define VBHEM_EINVAL     -1   /* bad argument (the reference raises vbhem_mex:invalidinput) */
+#define VBHEM_ENODEVICE  -2   /* no usable CUDA device */
+#define VBHEM_ECUDA      -3   /* CUDA runtime failure; see vbhem_last_error() */
+#define VBHEM_ENOMEM     -4
+
+#define VBHEM_COV_DIAG 0
+#define VBHEM_COV_FULL 1
+
+/* Opaque: a base HMM set (reference type h3m_b,
+ * /root/reference/src/vbhem/hmms_to_h3m_hem.m:19-140) packed once and resident in
+ * HBM, plus the device scratch, stream and per-iteration buffers that go with it.
+ * One handle = one device = one stream; calls on one handle must not overlap. */
+typedef struct vbhem_base vbhem_base_t;
+
+int         vbhem_version(void);
+const char *vbhem_last_error(void);
+int         vbhem_device_count(int *count);
+
+/* Pack the base set (replaces the per-call cell/struct walk of
+ * vbhem_hmm_bwd_fwd_mex.c:459-473, done once instead of every iteration).
+ *   Sb[N] int32          states per base HMM (1..maxSb)
+ *   prior[maxSb,N]       hmm{i}.prior
+ *   A[maxSb,maxSb,N]     hmm{i}.A, A(from,to)
+ *   mu[d,maxSb,N]        hmm{i}.emit{k}.centres
+ *   cov[d,d,maxSb,N] (full) | [d,maxSb,N] (diag)   hmm{i}.emit{k}.covars
+ *   Ntilde[N]            tilde_N_k = Nv*Kb*omega (vbhem_h3m_c_step_fc.m:26-30); may be NULL (= 1)
+ * All pointers are HOST pointers. */
+int vbhem_pack_base(int device, int N, const int32_t *Sb, int maxSb, int d, int covmode,
+                    const double *prior, const double *A, const double *mu, const double *cov,
+                    const double *Ntilde, vbhem_base_t **out);
+int vbhem_free_base(vbhem_base_t *base);
+
+/* Run subsequent work of this handle on an existing CUDA stream (a cudaStream_t
+ * passed as void*), e.g. torch's current stream.  NULL = the handle's own stream. */
+int vbhem_set_stream(vbhem_base_t *base, void *cuda_stream);
+int vbhem_synchronize(vbhem_base_t *base);
+
+/* Kernel selection, for tests and benchmarks: 0 = automatic (tensor-core
+ * lattice kernel when maxSb,maxSr <= 8 and d <= 3, else the general kernel),
+ * 1 = force the general (any-size, literal log-space) kernel. */
+int vbhem_set_kernel(vbhem_base_t *base, int which);
+
+/* ---- Boundary-1: the literal per-pair outputs of the MEX gateway ------------
+ * Centre inputs (HOST), the pre-pass results the reference passes to the MEX:
+ *   Sr[K] int32; logPi[maxSr,K] = logPiTilde; logA[maxSr,maxSr,K] = logATilde (row = from);
+ *   m[d,maxSr,K]; vW[d,d,maxSr,K] | [d,maxSr,K] = v*W (invCovR{j}, vbhem_h3m_c_step_fc.m:189);
+ *   cterm[maxSr,K] = logLambdaTildePlusDdivlamda.
+ * Outputs (HOST, any of nu1..Mu may be NULL together => L_elbo only):
+ *   L_elbo[N,K]; nu1[maxSr,p]; xi[maxSr,maxSr,p] (row = from); pr[maxSr,p];
+ *   mu_out[maxSr,d,p]; Mu_out[maxSr,dd,p]
+ * (plhs[0..5] of vbhem_hmm_bwd_fwd_mex.c:396-409 flattened over p = i + N*j). */
+int vbhem_estep_pairs(vbhem_base_t *base, int K, const int32_t *Sr, int maxSr, int tau,
+                      const double *logPi, const double *logA, const double *m, const double *vW,
+                      const double *cterm,
+                      double *L_elbo, double *nu1, double *xi, double *pr, double *mu_out, double *Mu_out);
+
+/* ---- Boundary-2: the fused E-step ------------------------------------------
+ * One call = MEX call + responsibilities + statistics reduction + the N-sized
+ * lower-bound terms, without materialising the N*K per-pair statistics.
+ * Extra inputs: logOmega[K] = psi(alpha)-psi(sum alpha); group[K] int32 softmax
+ * segment of each centre (NULL = all in one H3M; the (K,S) model-selection grid
+ * batches several H3Ms in one call), ngroups.
+ * Outputs (HOST; L_elbo, zhat may be NULL):
+ *   L_elbo[N,K], zhat[N,K]
+ *   stats: one contiguous fp64 buffer of vbhem_stats_size() doubles holding the RAW sums
+ *     Nj[K] | S_nu1[maxSr,K] | S_xi[maxSr,maxSr,K] | S_pr[maxSr,K] | S_mu[maxSr,d,K] |
+ *     S_Mu[maxSr,dd,K] | lb[2,ngroups] (Lt1 = sum Z.*L_elbo, Lt7 = sum zhat.*log zhat)
+ *   i.e. vbhem_compute_Statistics.m:33-55 before the normalisation of :57-82, with the
+ *   Z_Ni > 1e-8 rule applied; Nj WITHOUT the final +1e-50.  Raw sums are what a
+ *   multi-GPU caller all-reduces; vbhem_finalize_stats() then applies :57-82. */
+size_t vbhem_stats_size(int K, int maxSr, int d, int covmode, int ngroups);
+int    vbhem_stats_offsets(int K, int maxSr, int d, int covmode, int ngroups, size_t off[7]);
+
+int vbhem_estep(vbhem_base_t *base, int K, const int32_t *Sr, int maxSr, const int32_t *group, int ngroups,
+                int tau, const double *logPi, const double *logA, const double *m, const double *vW,
+                const double *cterm, const double *logOmega,
+                double *L_elbo, double *zhat, double *stats);
+
+/* Same, but the centre set is given by its hyper-parameters and the pre-pass
+ * (vbhem_h3m_c_step_fc.m:118-165,180-191,271-273) runs on the device:
+ *   alpha[K]; eta[maxSr,K]; epsilon[maxSr,maxSr,K] (row = from); m[d,maxSr,K];
+ *   W[d,d,maxSr,K] | [d,maxSr,K]; v[maxSr,K]; lambda[maxSr,K].
+ * pre (HOST, may be NULL) receives what the host-side lower bound needs:
+ *   logOmega[K] | logPi[maxSr,K] | logA[maxSr,maxSr,K] | logLambdaTilde[maxSr,K]
+ * contiguous, (K + maxSr*K*(2+maxSr)) doubles. */
+int vbhem_estep_hyp(vbhem_base_t *base, int K, const int32_t *Sr, int maxSr, const int32_t *group, int ngroups,
+                    int tau, const double *alpha, const double *eta, const double *epsilon, const double *m,
+                    const double *W, const double *v, const double *lambda,
+                    double *L_elbo, double *zhat, double *stats, double *pre);
+
+/* Device-resident variants for multi-GPU hosts: identical to vbhem_estep /
+ * vbhem_estep_hyp, but `stats_dev` is a DEVICE pointer (e.g. a torch tensor the
+ * caller then all-reduces with NCCL) and nothing is copied back; the work is
+ * enqueued on the handle's stream and the call returns without synchronising.
+ * L_elbo / zhat stay in the handle (vbhem_fetch). */
+int vbhem_estep_dev(vbhem_base_t *base, int K, const int32_t *Sr, int maxSr, const int32_t *group, int ngroups,
+                    int tau, const double *logPi, const double *logA, const double *m, const double *vW,
+                    const double *cterm, const double *logOmega, double *stats_dev);
+int vbhem_estep_hyp_dev(vbhem_base_t *base, int K, const int32_t *Sr, int maxSr, const int32_t *group, int ngroups,
+                        int tau, const double *alpha, const double *eta, const double *epsilon, const double *m,
+                        const double *W, const double *v, const double *lambda, double *stats_dev, double *pre);
+/* Copy the handle's last L_elbo[N,K] / zhat[N,K] to HOST buffers (either may be NULL). */
+int vbhem_fetch(vbhem_base_t *base, double *L_elbo, double *zhat);
+
+/* vbhem_compute_Statistics.m:57-82 applied in place to a stats buffer (HOST
+ * pointer; O(K*maxSr*dd) work, run on the device): Nj += 1e-50;
+ * S_pr -> Nj_rho = S_pr + 1e-50; S_mu -> y_bar = S_mu / Nj_rho;
+ * S_Mu -> S_plus_C = S_Mu / Nj_rho - y_bar*y_bar'; centres with Sr == 1 get
+ * Nj_rho2rho = 1e-12. */
+int vbhem_finalize_stats(vbhem_base_t *base, int K, const int32_t *Sr, int maxSr, int ngroups, double *stats);
+
+/* As vbhem_finalize_stats, on a DEVICE stats buffer, enqueued on the handle's stream. */
+int vbhem_finalize_stats_dev(vbhem_base_t *base, int K, const int32_t *Sr, int maxSr, int ngroups, double *stats_dev);
+
+/* Phase timing of the handle's E-steps, for bench.py: when enabled, CUDA events are
+ * recorded on the handle's stream around each phase and vbhem_last_timings() returns the
+ * milliseconds of the last E-step:
+ *   out[0] centre staging + pre-pass + records, out[1] first pass (L_elbo of every pair),
+ *   out[2] responsibilities + active list, out[3] second pass (forward + statistics),
+ *   out[4] reduction, out[5] total, out[6..7] reserved. */
+int vbhem_set_profile(vbhem_base_t *base, int on);
+int vbhem_last_timings(vbhem_base_t *base, double out[8]);
+
+/* Measures the device's fp64 peaks with dependent-free chains, in TFLOP/s:
+ *   out[0] DMMA (mma.sync.m8n8k4.f64), out[1] DFMA.  ~50 ms. */
+int vbhem_measure_fp64_peak(int device, double out[2]);
+
+/* Counters of the handle's last E-step, for bench.py / tests:
+ *   out[0] kernels launched, out[1] pairs through the tensor-core kernel,
+ *   out[2] pairs through the general kernel (incl. numerical fall-backs),
+ *   out[3] pairs with Z > 1e-8 (second pass), out[4..7] reserved. */
+int vbhem_last_counters(vbhem_base_t *base, long long out[8]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VBHEM_B200_H */

@@ -1,0 +1,47 @@
+"""Generates tests/golden/*.npz from the REFERENCE's own native code.
+
+Run in the dev container (needs /root/reference):
+    python tests/golden/make_golden.py
+It builds oracle/_ref/libvbhem_ref.so -- the reference's
+src/vbhem/vbhem_hmm_bwd_fwd_mex.c compiled unmodified behind oracle/mxshim -- and
+stores its six outputs for a few small seeded cases, together with the exact inputs.
+The fixtures are what pins oracle/estep_oracle.c, oracle/numpy_ref.py and the CUDA
+path on machines where /root/reference does not exist (the GPU box).
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import vbhem_b200  # noqa: E402,F401
+from oracle import cref  # noqa: E402
+from util import make_case, oracle_pairs  # noqa: E402
+
+CASES = {
+    # name: (make_case kwargs, tau)
+    "full_ragged_d2": (dict(N=7, K=3, Sb=4, Sr=3, d=2, covmode="full", ragged=True, seed=5), 5),
+    "diag_ragged_d3": (dict(N=6, K=4, Sb=3, Sr=4, d=3, covmode="diag", ragged=True, seed=11), 4),
+    "full_s8_d2_tau10": (dict(N=5, K=4, Sb=8, Sr=8, d=2, covmode="full", ragged=False, seed=1001), 10),
+    "full_tau1": (dict(N=4, K=2, Sb=2, Sr=2, d=2, covmode="full", ragged=False, seed=3), 1),
+    "exprmt1_shape": (dict(N=40, K=2, Sb=2, Sr=2, d=2, covmode="full", ragged=False, seed=7, Nv=100.0), 50),
+}
+
+if __name__ == "__main__":
+    assert os.path.exists("/root/reference/src/vbhem/vbhem_hmm_bwd_fwd_mex.c"), "needs the reference checkout"
+    cref.build()
+    here = os.path.dirname(os.path.abspath(__file__))
+    for name, (kw, tau) in CASES.items():
+        base, hyp, cen = make_case(**kw)
+        out = oracle_pairs(base, cen, tau, which="ref")
+        blob = {f"base_{k}": v for k, v in base.items()}
+        blob.update({f"cen_{k}": v for k, v in cen.items()})
+        blob.update({f"hyp_{k}": v for k, v in hyp.items()})
+        blob.update({f"out_{k}": v for k, v in out.items()})
+        blob["tau"] = np.int64(tau)
+        blob["covmode"] = np.array(kw["covmode"])
+        np.savez_compressed(os.path.join(here, name + ".npz"), **blob)
+        print(name, "L_elbo[0,:]=", out["L_elbo"][0])

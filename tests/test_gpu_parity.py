@@ -1,0 +1,256 @@
+"""GPU tier: the CUDA path through the C ABI against the oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): L_elbo rtol 1e-9; z_hat rtol 1e-9 with
+atol 1e-12; per-pair statistics and reduced sums 1e-9 relative to the largest entry of the same
+block.  Both kernels are exercised: the tensor-core lattice kernel ("auto") and the general
+log-space kernel ("general").
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from test_oracle import load_golden
+from util import assert_pairs_close, make_case, oracle_fused, oracle_pairs
+
+pytestmark = pytest.mark.gpu
+
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+RTOL = 1e-9
+
+
+def BaseSet(*a, **k):
+    from vbhem_b200.api import BaseSet as B
+    return B(*a, **k)
+
+
+@pytest.mark.parametrize("kernel", ["auto", "general"])
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+def test_pairs_match_reference_golden(path, kernel):
+    base, hyp, cen, want, tau, covmode = load_golden(path)
+    with BaseSet(base) as bs:
+        bs.set_kernel(kernel)
+        got = bs.estep_pairs(cen, tau)
+        c = bs.counters()
+    assert_pairs_close(got, want, rtol=RTOL, what=f"cuda({kernel}) vs reference golden")
+    assert c["launches"] > 0
+    if kernel == "general":
+        assert c["lattice_pairs"] == 0
+
+
+SHAPES = [
+    # N, K, Sb, Sr, d, covmode, ragged, T
+    (13, 5, 8, 8, 2, "full", False, 10),
+    (13, 5, 8, 8, 2, "full", True, 10),
+    (9, 4, 4, 3, 2, "diag", True, 5),
+    (9, 4, 3, 4, 3, "full", True, 5),
+    (9, 4, 3, 4, 3, "diag", False, 2),
+    (7, 3, 1, 1, 2, "full", False, 4),
+    (7, 3, 2, 1, 1, "full", True, 3),
+    (6, 2, 8, 8, 1, "diag", True, 1),
+    (5, 3, 6, 7, 2, "full", True, 50),
+]
+
+
+@pytest.mark.parametrize("kernel", ["auto", "general"])
+@pytest.mark.parametrize("shape", SHAPES, ids=[f"N{s[0]}K{s[1]}b{s[2]}r{s[3]}d{s[4]}{s[5]}{'R' if s[6] else ''}T{s[7]}"
+                                                for s in SHAPES])
+def test_pairs_match_oracle(shape, kernel):
+    N, K, Sb, Sr, d, covmode, ragged, T = shape
+    base, hyp, cen = make_case(N=N, K=K, Sb=Sb, Sr=Sr, d=d, covmode=covmode, ragged=ragged, seed=100 + N + d)
+    want = oracle_pairs(base, cen, T)
+    with BaseSet(base) as bs:
+        bs.set_kernel(kernel)
+        got = bs.estep_pairs(cen, T)
+        L = bs.estep_pairs(cen, T, L_only=True)["L_elbo"]
+    assert_pairs_close(got, want, rtol=RTOL, what=f"cuda({kernel}) vs oracle")
+    np.testing.assert_allclose(L, want["L_elbo"], rtol=RTOL)
+
+
+def test_general_kernel_for_large_state_counts():
+    """More than 8 states and d = 4: only the general kernel applies (automatic selection)."""
+    base, hyp, cen = make_case(N=5, K=2, Sb=11, Sr=9, d=2, covmode="full", ragged=True, seed=77)
+    want = oracle_pairs(base, cen, 4)
+    with BaseSet(base) as bs:
+        got = bs.estep_pairs(cen, 4)
+        c = bs.counters()
+    assert_pairs_close(got, want, rtol=RTOL)
+    assert c["lattice_pairs"] == 0 and c["general_pairs"] == 10
+
+
+def check_fused(got, want, N):
+    np.testing.assert_allclose(got["L_elbo"], want["L_elbo"], rtol=RTOL)
+    np.testing.assert_allclose(got["zhat"], want["zhat"], rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(got["Nj"] + 1e-50, want["Nj"], rtol=RTOL)
+    # Lt1 relative; Lt7 = sum z log z is a sum of O(eps * |log_Z|) rounding residues when z_hat is
+    # sharp, so it is held to the scale it enters the lower bound with (LB = Lt1 - Lt7 + ...)
+    np.testing.assert_allclose(got["lb"][0::2], want["lb"][0::2], rtol=RTOL)
+    np.testing.assert_allclose(got["lb"][1::2], want["lb"][1::2], rtol=RTOL, atol=1e-12 * np.abs(want["lb"][0::2]).max())
+    for k in ("nu1", "xi", "pr", "mu", "Mu"):
+        g, w = got[k], want[k]
+        scale = np.maximum(np.max(np.abs(w), axis=tuple(range(1, w.ndim)), keepdims=True), 1e-300)
+        err = np.max(np.abs(g - w) / scale)
+        assert err <= RTOL, f"{k}: {err:.3e}"
+
+
+@pytest.mark.parametrize("kernel", ["auto", "general"])
+@pytest.mark.parametrize("Nv", [100.0, 3.0])
+def test_fused_estep_matches_oracle(kernel, Nv):
+    """Boundary-2: responsibilities, Z > 1e-8 skip rule, reduced sums, Lt1 / Lt7.  Nv = 100 gives the
+    reference's sharp z_hat (most pairs skipped), Nv = 3 soft ones (most pairs kept)."""
+    base, hyp, cen = make_case(N=300, K=6, Sb=5, Sr=4, d=2, covmode="full", ragged=True, seed=31, Nv=Nv)
+    want = oracle_fused(base, cen, 6)
+    with BaseSet(base) as bs:
+        bs.set_kernel(kernel)
+        got = bs.estep(cen, 6)
+        c = bs.counters()
+    check_fused(got, want, 300)
+    Z = want["zhat"] * base["Ntilde"][:, None]
+    assert c["active_pairs"] == int((Z > 1e-8).sum())
+
+
+def test_fused_estep_from_hyperparameters():
+    """Device pre-pass (digamma, log det) + fused E-step against numpy pre-pass + oracle."""
+    base, hyp, cen = make_case(N=120, K=5, Sb=4, Sr=4, d=2, covmode="full", ragged=True, seed=41, Nv=30.0)
+    want = oracle_fused(base, cen, 5)
+    with BaseSet(base) as bs:
+        got = bs.estep_hyp(hyp, 5)
+    np.testing.assert_allclose(got["logOmega"], cen["logOmega"], rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(got["logPi"], cen["logPi"], rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(got["logA"], cen["logA"], rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(got["logLambdaTilde"], cen["logLambdaTilde"], rtol=1e-12, atol=1e-13)
+    check_fused(got, want, 120)
+
+
+def test_prepass_diag_d3():
+    base, hyp, cen = make_case(N=20, K=3, Sb=3, Sr=3, d=3, covmode="diag", ragged=False, seed=43, Nv=30.0)
+    want = oracle_fused(base, cen, 3)
+    with BaseSet(base) as bs:
+        got = bs.estep_hyp(hyp, 3)
+    np.testing.assert_allclose(got["logLambdaTilde"], cen["logLambdaTilde"], rtol=1e-12, atol=1e-13)
+    check_fused(got, want, 20)
+
+
+def test_grouped_centres_one_call():
+    """The (K,S) grid batches several H3Ms: per-group softmax and per-group Lt1 / Lt7."""
+    base, hyp, cen = make_case(N=90, K=5, Sb=3, Sr=3, d=2, covmode="full", ragged=False, seed=47, Nv=10.0)
+    cen = dict(cen)
+    cen["group"] = np.array([0, 0, 1, 1, 1], np.int32)
+    # per-group logOmega, as the reference would compute for two separate H3Ms
+    from oracle import numpy_ref as nr
+    cen["logOmega"] = np.concatenate([nr.log_omega_tilde(hyp["alpha"][:2]), nr.log_omega_tilde(hyp["alpha"][2:])])
+    want = oracle_fused(base, cen, 4)
+    with BaseSet(base) as bs:
+        got = bs.estep(cen, 4)
+    assert got["lb"].shape == (4,)
+    check_fused(got, want, 90)
+
+
+def test_finalize_matches_numpy():
+    from oracle import numpy_ref as nr
+    base, hyp, cen = make_case(N=60, K=4, Sb=3, Sr=3, d=2, covmode="full", ragged=True, seed=53, Nv=10.0,
+                               sr_list=[3, 1, 2, 3])
+    with BaseSet(base) as bs:
+        got = bs.estep(cen, 4)
+        fin = bs.finalize(got["buf"], cen["Sr"], 3)
+    for j in range(4):
+        r = int(cen["Sr"][j])
+        a = nr.finalize_stats(got["nu1"][j, :r], got["xi"][j, :r, :r], got["pr"][j, :r], got["mu"][j, :r],
+                              got["Mu"][j, :r])
+        np.testing.assert_allclose(fin["Nj_rho1"][j, :r], a[0], rtol=1e-13)
+        np.testing.assert_allclose(fin["Nj_rho2rho"][j, :r, :r], a[1], rtol=1e-13)
+        np.testing.assert_allclose(fin["Nj_rho"][j, :r], a[2], rtol=1e-13)
+        np.testing.assert_allclose(fin["y_bar"][j, :r], a[3], rtol=1e-13)
+        np.testing.assert_allclose(fin["S_plus_C"][j, :r], a[4], rtol=1e-9, atol=1e-9 * np.abs(a[4]).max())
+    np.testing.assert_allclose(fin["Nj"], got["Nj"] + 1e-50, rtol=1e-15)
+
+
+def test_nan_and_inf_propagate_like_the_reference():
+    """NaN / Inf are data (SURVEY 8b 'Errors'): they must reach L_elbo exactly where the reference puts them,
+    through the in-GPU fall-back of the lattice kernel."""
+    base, hyp, cen = make_case(N=6, K=3, Sb=4, Sr=4, d=2, covmode="full", ragged=False, seed=61)
+    base = {k: np.array(v) for k, v in base.items()}
+    cen = {k: np.array(v) for k, v in cen.items()}
+    base["mu"][1, 2, 0] = np.nan            # NaN in one base emission
+    cen["logA"][2, 1, :] = -np.inf          # a centre state with no way out
+    cen["cterm"][0, 3] = np.inf             # a centre state nobody can emit from
+    want = oracle_pairs(base, cen, 4)
+    for kernel in ("auto", "general"):
+        with BaseSet(base) as bs:
+            bs.set_kernel(kernel)
+            got = bs.estep_pairs(cen, 4)
+            c = bs.counters()
+        assert np.array_equal(np.isnan(got["L_elbo"]), np.isnan(want["L_elbo"])), kernel
+        assert np.isnan(want["L_elbo"]).any()
+        ok = ~np.isnan(want["L_elbo"])
+        np.testing.assert_allclose(got["L_elbo"][ok], want["L_elbo"][ok], rtol=RTOL)
+        if kernel == "auto":
+            assert c["general_pairs"] > 0, "the poisoned pairs must have gone through the fall-back"
+
+
+def test_underflow_falls_back_in_gpu():
+    """A transition row whose only large entries point at states the emissions rule out: the
+    linear-domain sum underflows, the pair is redone in log space, results still match."""
+    base, hyp, cen = make_case(N=5, K=2, Sb=3, Sr=3, d=2, covmode="full", ragged=False, seed=67)
+    cen = {k: np.array(v) for k, v in cen.items()}
+    cen["logA"][0, 0, :] = [-0.001, -900.0, -900.0]
+    cen["cterm"][0, 0] += 3000.0            # state 0 of centre 0 is ~e^-1500 less likely than the others
+    want = oracle_pairs(base, cen, 5)
+    with BaseSet(base) as bs:
+        got = bs.estep_pairs(cen, 5)
+        c = bs.counters()
+    assert np.isfinite(want["L_elbo"]).all()
+    assert_pairs_close(got, want, rtol=RTOL)
+    assert c["general_pairs"] > 0
+
+
+def test_bitwise_deterministic():
+    base, hyp, cen = make_case(N=500, K=8, Sb=6, Sr=5, d=2, covmode="full", ragged=True, seed=71, Nv=8.0)
+    with BaseSet(base) as bs:
+        a = bs.estep(cen, 7)["buf"].copy()
+        b = bs.estep(cen, 7)["buf"].copy()
+    assert np.array_equal(a, b)
+
+
+def test_error_codes():
+    from vbhem_b200._lib import VbhemError
+    base, hyp, cen = make_case(N=4, K=2, Sb=2, Sr=2, d=2, covmode="full", ragged=False, seed=73)
+    with BaseSet(base) as bs:
+        with pytest.raises(VbhemError) as ei:
+            bs.estep_pairs(cen, 0)
+        assert ei.value.code == -1 and "tau" in ei.value.msg
+        bad = dict(cen)
+        bad["Sr"] = np.array([2, 5], np.int32)
+        with pytest.raises(VbhemError) as ei:
+            bs.estep_pairs(bad, 3)
+        assert ei.value.code == -1 and "vbhem_mex:invalidinput" in ei.value.msg
+
+
+def test_north_star_shape_properties():
+    """BASELINE configs[2] shape at a size the GPU finishes in a blink but the oracle would not:
+    size-independent properties instead of element-wise comparison, plus an oracle spot check."""
+    from vbhem_b200 import synth
+    from util import prepass_natural
+    N, K = 20000, 64
+    base, hyp, _ = synth.north_star(N=N, K=K)
+    cen = prepass_natural(hyp, "full")
+    with BaseSet(base) as bs:
+        got = bs.estep(cen, 10)
+        c = bs.counters()
+    z = got["zhat"]
+    np.testing.assert_allclose(z.sum(1), 1.0, rtol=1e-12)                     # softmax rows
+    np.testing.assert_allclose(got["Nj"].sum(), base["Ntilde"].sum(), rtol=1e-12)
+    Z = z * base["Ntilde"][:, None]
+    act = Z > 1e-8
+    assert c["active_pairs"] == int(act.sum())
+    # mass conservation through the skip rule: sum_sigma S_nu1[j] = sum_{i active} Z_ij * sum(prior_i)
+    np.testing.assert_allclose(got["nu1"].sum(1), (np.where(act, Z, 0.0) * base["prior"].sum(1)[:, None]).sum(0),
+                               rtol=1e-10)
+    np.testing.assert_allclose(got["xi"].sum((1, 2)) + got["nu1"].sum(1), got["pr"].sum(1), rtol=1e-10)
+    np.testing.assert_allclose(got["lb"][0], np.sum(Z * got["L_elbo"]), rtol=1e-12)
+    # spot check 40 bases against the oracle
+    idx = np.arange(0, N, N // 40)[:40]
+    sub = {k: v[idx] for k, v in base.items()}
+    want = oracle_pairs(sub, cen, 10)
+    np.testing.assert_allclose(got["L_elbo"][idx], want["L_elbo"], rtol=RTOL)
