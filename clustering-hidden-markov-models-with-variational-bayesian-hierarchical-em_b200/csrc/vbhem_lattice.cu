@@ -28,6 +28,7 @@
 // each step (2 x 64 doubles instead of the 512-double Theta slice), kept in
 // shared memory and read back transposed.
 #include "vbhem_internal.cuh"
+#include "vbhem_math.cuh"
 
 #include <type_traits>
 
@@ -39,6 +40,14 @@ constexpr int kLd = 10;           // padded row stride of an 8x8 tile in shared 
 constexpr int kTile = 8 * kLd;    // doubles per tile
 
 struct Frag { double x0, x1; };
+
+// (invc, logc) pairs of log_pos(); copied to shared memory by every CTA (random per-lane index)
+__device__ const double g_log_table[2 * VBHEM_LOG_BINS] = VBHEM_LOG_TABLE;
+constexpr int kTabDoubles = 2 * VBHEM_LOG_BINS;
+
+__device__ __forceinline__ void load_log_table(double *dst) {
+  for (int x = threadIdx.x; x < kTabDoubles; x += blockDim.x) dst[x] = g_log_table[x];
+}
 
 __device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -55,11 +64,6 @@ __device__ __forceinline__ Frag mma_nt(const Frag &A, const Frag &X) {
   return D;
 }
 
-__device__ __forceinline__ double quad_max(double v) {
-  v = fmax(v, __shfl_xor_sync(0xffffffffu, v, 1));
-  v = fmax(v, __shfl_xor_sync(0xffffffffu, v, 2));
-  return v;
-}
 __device__ __forceinline__ double quad_sum(double v) {
   v += __shfl_xor_sync(0xffffffffu, v, 1);
   v += __shfl_xor_sync(0xffffffffu, v, 2);
@@ -161,21 +165,39 @@ __device__ __forceinline__ Frag emission(const BaseConst<D, FULL> &b, const doub
   return Frag{out[0], out[1]};
 }
 
-// One backward step (t = T-1 .. 1).  In: L(beta|sigma).  Out: L(beta'|rho) of the
-// previous time step.  With STORE the step's Bm(beta|sigma) and 1/S^T(rho|beta)
-// go to shared memory for the forward pass.  Returns false if a sum underflowed.
+// Shift of one lattice row: any number close to (and not below) the row maximum works, because the
+// same c enters exp(G - c) and c + log(sum).  A float max needs half the shuffles of a double one;
+// nudging it up by one float ulp keeps G - c <= 0.
+__device__ __forceinline__ float row_shift_f(const Frag &G) {
+  float m = fmaxf(__double2float_rn(G.x0), __double2float_rn(G.x1));
+  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+  return m;
+}
+__device__ __forceinline__ double shift_of(float m) {
+  const double c = (double)m;
+  return fma(fabs(c), 1.2e-7, c);
+}
+
+// One backward step (t = T-1 .. 1).  In: G(beta|sigma) = E + L of this step.  Out: G of the
+// previous time step, G(beta'|rho) = E + sum_beta Ab[beta',beta] lse[beta,rho].  With STORE the
+// step's Bm(beta|sigma) and 1/S^T(rho|beta) go to shared memory for the forward pass.  Returns
+// false if a sum underflowed or the inputs held NaN / +Inf.
 template <bool STORE>
-__device__ __forceinline__ bool bwd_step(const Frag &E, Frag &L, const Frag &expA, const Frag &Ab, double *sBm,
-                                         double *sInvS, int g, int q) {
-  const Frag G{E.x0 + L.x0, E.x1 + L.x1};
-  const double c = quad_max(fmax(G.x0, G.x1));                 // c[beta = g]
-  const Frag Bm{exp(G.x0 - c), exp(G.x1 - c)};
+__device__ __forceinline__ bool bwd_step(const Frag &E, Frag &G, const Frag &expA, const Frag &Ab,
+                                         const double *ltab, double *sBm, double *sInvS, int g, int q) {
+  const float mf = row_shift_f(G);
+  const double c = shift_of(mf);                               // c[beta = g]
+  const double x0 = G.x0 - c, x1 = G.x1 - c;
+  const Frag Bm{exp_nonpos(x0), exp_nonpos(x1)};
   const Frag ST = mma_nt(expA, Bm);                            // S^T(rho = g | beta = 2q+e)
-  const bool ok = (ST.x0 >= kTiny) && (ST.x1 >= kTiny);
-  const double cb0 = __shfl_sync(0xffffffffu, c, (2 * q) * 4);
-  const double cb1 = __shfl_sync(0xffffffffu, c, (2 * q + 1) * 4);
-  const Frag ell{cb0 + log(ST.x0), cb1 + log(ST.x1)};          // lse^T(rho | beta)
-  L = mma_nt(Ab, ell);                                         // L(beta' = g | rho = 2q+e)
+  const double chk = x0 + x1;                                  // NaN iff NaN / +Inf upstream
+  const bool ok = (ST.x0 >= kTiny) && (ST.x1 >= kTiny) && (chk == chk);
+  const double cb0 = shift_of(__shfl_sync(0xffffffffu, mf, (2 * q) * 4));
+  const double cb1 = shift_of(__shfl_sync(0xffffffffu, mf, (2 * q + 1) * 4));
+  const Frag ell{cb0 + log_pos(ST.x0, ltab), cb1 + log_pos(ST.x1, ltab)};   // lse^T(rho | beta)
+  G = E;
+  mma_nt_acc(G, Ab, ell);                                      // G(beta' = g | rho = 2q+e)
   if (STORE) {
     tile_store(sBm, g, q, Bm);
     tile_store(sInvS, g, q, Frag{1.0 / ST.x0, 1.0 / ST.x1});
@@ -185,14 +207,15 @@ __device__ __forceinline__ bool bwd_step(const Frag &E, Frag &L, const Frag &exp
 
 // Termination (vbhem_hmm_bwd_fwd_mex.c:1029-1080).  Returns L_elbo (all lanes) and
 // nu_1(beta = g | sigma = 2q+e) = prior * Theta_1.
-__device__ __forceinline__ double terminate(const Frag &E, const Frag &L, const Frag &expPi, double prior, int q,
-                                            Frag &nu1, bool &ok) {
-  const Frag G{E.x0 + L.x0, E.x1 + L.x1};
-  const double c = quad_max(fmax(G.x0, G.x1));
-  const Frag Bm{exp(G.x0 - c), exp(G.x1 - c)};
+__device__ __forceinline__ double terminate(const Frag &G, const Frag &expPi, double prior, const double *ltab,
+                                            int q, Frag &nu1, bool &ok) {
+  const double c = shift_of(row_shift_f(G));
+  const double x0 = G.x0 - c, x1 = G.x1 - c;
+  const Frag Bm{exp_nonpos(x0), exp_nonpos(x1)};
   const double s = quad_sum(expPi.x0 * Bm.x0 + expPi.x1 * Bm.x1);
-  ok = ok && (s >= kTiny);
-  const double ell = c + log(s);
+  const double chk = x0 + x1;
+  ok = ok && (s >= kTiny) && (chk == chk);
+  const double ell = c + log_pos(s, ltab);
   const double Lq = across_sum(q == 0 ? prior * ell : 0.0);    // valid in lanes with q == 0
   const double w = prior / s;
   nu1 = Frag{w * expPi.x0 * Bm.x0, w * expPi.x1 * Bm.x1};
@@ -203,7 +226,7 @@ __device__ __forceinline__ double terminate(const Frag &E, const Frag &L, const 
 constexpr int kBwdWarps = 8;
 
 template <int D, bool FULL>
-__global__ void __launch_bounds__(kBwdWarps * 32, 2)
+__global__ void __launch_bounds__(kBwdWarps * 32, 3)
 k_lattice_bwd(BaseView B, CentreView C, int T, int kc, double *L_elbo, Fallback fb) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
@@ -211,22 +234,26 @@ k_lattice_bwd(BaseView B, CentreView C, int T, int kc, double *L_elbo, Fallback 
   const int j0 = blockIdx.y * kc;
   const int nj = min(kc, C.K - j0);
   const int rs = C.rec_stride;
-  for (int x = threadIdx.x; x < nj * rs; x += blockDim.x) smem[x] = C.rec[(size_t)j0 * rs + x];
+  const double *ltab = smem;
+  double *recs = smem + kTabDoubles;
+  load_log_table(smem);
+  for (int x = threadIdx.x; x < nj * rs; x += blockDim.x) recs[x] = C.rec[(size_t)j0 * rs + x];
   __syncthreads();
 
   for (int i = blockIdx.x * kBwdWarps + warp; i < B.N; i += gridDim.x * kBwdWarps) {
     BaseConst<D, FULL> b;
     load_base(b, B, i, g, q);
     for (int jj = 0; jj < nj; jj++) {
-      const double *rec = smem + jj * rs;
+      const double *rec = recs + jj * rs;
       CentreConst<D, FULL> c;
       load_centre(c, rec, g, q);
       const Frag E = emission(b, rec, g, q);
-      Frag L{0.0, 0.0};
+      Frag G = E;
       bool ok = true;
-      for (int t = T - 1; t >= 1; t--) ok = bwd_step<false>(E, L, c.expA, b.Ab, nullptr, nullptr, g, q) && ok;
+      for (int t = T - 1; t >= 1; t--)
+        ok = bwd_step<false>(E, G, c.expA, b.Ab, ltab, nullptr, nullptr, g, q) && ok;
       Frag nu1;
-      const double Le = terminate(E, L, c.expPi, b.prior, q, nu1, ok);
+      const double Le = terminate(G, c.expPi, b.prior, ltab, q, nu1, ok);
       ok = __all_sync(0xffffffffu, ok);
       if (lane == 0) {
         const size_t p = (size_t)i + (size_t)B.N * (j0 + jj);
@@ -248,19 +275,20 @@ struct PairStats {
 // smem (per warp): (T-1) x {Bm tile, invS tile} + one exchange tile.
 template <int D, bool FULL>
 __device__ __forceinline__ bool pair_full(const BaseView &B, int i, const BaseConst<D, FULL> &b,
-                                          const CentreConst<D, FULL> &c, const double *rec, int T, double *sm,
-                                          int g, int q, double &Lout, PairStats<D, FULL> &st) {
+                                          const CentreConst<D, FULL> &c, const double *rec, int T,
+                                          const double *ltab, double *sm, int g, int q, double &Lout,
+                                          PairStats<D, FULL> &st) {
   constexpr int DD = BaseConst<D, FULL>::DD;
   double *xch = sm + (size_t)2 * kTile * (T - 1);
   const Frag E = emission(b, rec, g, q);
-  Frag L{0.0, 0.0};
+  Frag G = E;
   bool ok = true;
   for (int t = T - 1; t >= 1; t--) {
     double *s = sm + (size_t)2 * kTile * (t - 1);
-    ok = bwd_step<true>(E, L, c.expA, b.Ab, s, s + kTile, g, q) && ok;
+    ok = bwd_step<true>(E, G, c.expA, b.Ab, ltab, s, s + kTile, g, q) && ok;
   }
   Frag nu1;
-  Lout = terminate(E, L, c.expPi, b.prior, q, nu1, ok);
+  Lout = terminate(G, c.expPi, b.prior, ltab, q, nu1, ok);
   ok = __all_sync(0xffffffffu, ok);
   if (!ok) return false;
 
@@ -321,7 +349,10 @@ k_lattice_full(BaseView B, CentreView C, int T, PairWork W, PairOut O, Fallback 
   constexpr int DD = BaseConst<D, FULL>::DD;
   const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
   const int warp = threadIdx.x >> 5;
-  double *sm = smem + (size_t)warp * ((size_t)2 * kTile * (T - 1) + kTile);
+  const double *ltab = smem;
+  load_log_table(smem);
+  __syncthreads();
+  double *sm = smem + kTabDoubles + (size_t)warp * ((size_t)2 * kTile * (T - 1) + kTile);
   const long long gw = (long long)blockIdx.x * warps_per_block + warp;
   const long long nw = (long long)gridDim.x * warps_per_block;
   const int ro = C.maxSr;
@@ -337,7 +368,7 @@ k_lattice_full(BaseView B, CentreView C, int T, PairWork W, PairOut O, Fallback 
       load_centre(c, rec, g, q);
       PairStats<D, FULL> st;
       double Le;
-      const bool ok = pair_full(B, i, b, c, rec, T, sm, g, q, Le, st);
+      const bool ok = pair_full(B, i, b, c, rec, T, ltab, sm, g, q, Le, st);
       if (!ok) {
         if (lane == 0) { fb.flags[p] = 1; atomicAdd(fb.count, 1); }
         continue;
@@ -379,7 +410,7 @@ k_lattice_full(BaseView B, CentreView C, int T, PairWork W, PairOut O, Fallback 
       load_base(b, B, it.i, g, q);
       PairStats<D, FULL> st;
       double Le;
-      const bool ok = pair_full(B, it.i, b, c, rec, T, sm, g, q, Le, st);
+      const bool ok = pair_full(B, it.i, b, c, rec, T, ltab, sm, g, q, Le, st);
       if (!ok) {
         if (lane == 0) { fb.flags[cr.x + e] = 1; atomicAdd(fb.count, 1); }
         continue;
@@ -451,12 +482,12 @@ bool lattice_supported(const BaseView &B, const CentreView &C, int T, bool need_
 int launch_lattice_bwd(const BaseView &B, const CentreView &C, int T, double *L_elbo, Fallback fb,
                        cudaStream_t st) {
   const int rs = C.rec_stride;
-  int kc = (int)((96 * 1024) / (sizeof(double) * rs));
+  int kc = (int)((64 * 1024) / (sizeof(double) * rs));
   if (kc > C.K) kc = C.K;
-  const size_t smem = sizeof(double) * (size_t)kc * rs;
+  const size_t smem = sizeof(double) * ((size_t)kc * rs + kTabDoubles);
   const int ny = (C.K + kc - 1) / kc;
   int nx = (B.N + kBwdWarps - 1) / kBwdWarps;
-  const int cap = 2 * sm_count();
+  const int cap = 3 * sm_count();
   if (nx > cap) nx = cap;
   return dispatch(B.d, B.covmode, [&](auto Dc, auto Fc) {
     auto kern = k_lattice_bwd<decltype(Dc)::value, decltype(Fc)::value>;
@@ -477,7 +508,7 @@ int launch_lattice_full(const BaseView &B, const CentreView &C, int T, const Pai
   long long blocks = (units + wpb - 1) / wpb;
   const long long cap = sm_count();
   if (blocks > cap) blocks = cap;
-  const size_t smem = pw * wpb;
+  const size_t smem = pw * wpb + sizeof(double) * kTabDoubles;
   return dispatch(B.d, B.covmode, [&](auto Dc, auto Fc) {
     auto kern = k_lattice_full<decltype(Dc)::value, decltype(Fc)::value>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
