@@ -42,15 +42,19 @@ constexpr int kTile = 8 * kLd;    // doubles per tile
 struct Frag { double x0, x1; };
 
 // (invc, logc) pairs of log_pos(); copied to shared memory by every CTA (random per-lane index)
+// and the 2^(j/32) table of exp_nonpos_tab() behind it
 __device__ const double g_log_table[2 * VBHEM_LOG_BINS] = VBHEM_LOG_TABLE;
-constexpr int kTabDoubles = 2 * VBHEM_LOG_BINS;
+__device__ const double g_exp_table[VBHEM_EXP_BINS] = VBHEM_EXP_TABLE;
+constexpr int kLogDoubles = 2 * VBHEM_LOG_BINS;
+constexpr int kTabDoubles = kLogDoubles + VBHEM_EXP_BINS;
 
 __device__ __forceinline__ void load_log_table(double *dst) {
-  for (int x = threadIdx.x; x < kTabDoubles; x += blockDim.x) dst[x] = g_log_table[x];
+  for (int x = threadIdx.x; x < kLogDoubles; x += blockDim.x) dst[x] = g_log_table[x];
+  for (int x = threadIdx.x; x < VBHEM_EXP_BINS; x += blockDim.x) dst[kLogDoubles + x] = g_exp_table[x];
 }
 
 __device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 // D(m|n) = sum_c A[m][c] * X[n][c], all three in accumulator layout.
@@ -166,17 +170,14 @@ __device__ __forceinline__ Frag emission(const BaseConst<D, FULL> &b, const doub
 }
 
 // Shift of one lattice row: any number close to (and not below) the row maximum works, because the
-// same c enters exp(G - c) and c + log(sum).  A float max needs half the shuffles of a double one;
-// nudging it up by one float ulp keeps G - c <= 0.
-__device__ __forceinline__ float row_shift_f(const Frag &G) {
-  float m = fmaxf(__double2float_rn(G.x0), __double2float_rn(G.x1));
-  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-  return m;
-}
-__device__ __forceinline__ double shift_of(float m) {
-  const double c = (double)m;
-  return fma(fabs(c), 1.2e-7, c);
+// same c enters exp(G - c) and c + log(sum).  The maximum is taken over an order-preserving int32
+// key of the high words (integer pipe, 32-bit shuffles); key + 1 is >= every element of the row and
+// exceeds the true maximum by at most 2^-20 of its magnitude.
+__device__ __forceinline__ int row_shift_key(const Frag &G) {
+  int m = max(order_key(G.x0), order_key(G.x1));
+  m = max(m, __shfl_xor_sync(0xffffffffu, m, 1));
+  m = max(m, __shfl_xor_sync(0xffffffffu, m, 2));
+  return m + 1;
 }
 
 // One backward step (t = T-1 .. 1).  In: G(beta|sigma) = E + L of this step.  Out: G of the
@@ -186,15 +187,16 @@ __device__ __forceinline__ double shift_of(float m) {
 template <bool STORE>
 __device__ __forceinline__ bool bwd_step(const Frag &E, Frag &G, const Frag &expA, const Frag &Ab,
                                          const double *ltab, double *sBm, double *sInvS, int g, int q) {
-  const float mf = row_shift_f(G);
-  const double c = shift_of(mf);                               // c[beta = g]
+  const double *etab = ltab + kLogDoubles;
+  const int key = row_shift_key(G);
+  const double c = key_to_double(key);                         // c[beta = g]
   const double x0 = G.x0 - c, x1 = G.x1 - c;
-  const Frag Bm{exp_nonpos(x0), exp_nonpos(x1)};
+  const Frag Bm{exp_nonpos_tab(x0, etab), exp_nonpos_tab(x1, etab)};
   const Frag ST = mma_nt(expA, Bm);                            // S^T(rho = g | beta = 2q+e)
   const double chk = x0 + x1;                                  // NaN iff NaN / +Inf upstream
-  const bool ok = (ST.x0 >= kTiny) && (ST.x1 >= kTiny) && (chk == chk);
-  const double cb0 = shift_of(__shfl_sync(0xffffffffu, mf, (2 * q) * 4));
-  const double cb1 = shift_of(__shfl_sync(0xffffffffu, mf, (2 * q + 1) * 4));
+  const bool ok = sum_is_safe(ST.x0) && sum_is_safe(ST.x1) && (chk == chk);
+  const double cb0 = key_to_double(__shfl_sync(0xffffffffu, key, (2 * q) * 4));
+  const double cb1 = key_to_double(__shfl_sync(0xffffffffu, key, (2 * q + 1) * 4));
   const Frag ell{cb0 + log_pos(ST.x0, ltab), cb1 + log_pos(ST.x1, ltab)};   // lse^T(rho | beta)
   G = E;
   mma_nt_acc(G, Ab, ell);                                      // G(beta' = g | rho = 2q+e)
@@ -209,12 +211,13 @@ __device__ __forceinline__ bool bwd_step(const Frag &E, Frag &G, const Frag &exp
 // nu_1(beta = g | sigma = 2q+e) = prior * Theta_1.
 __device__ __forceinline__ double terminate(const Frag &G, const Frag &expPi, double prior, const double *ltab,
                                             int q, Frag &nu1, bool &ok) {
-  const double c = shift_of(row_shift_f(G));
+  const double *etab = ltab + kLogDoubles;
+  const double c = key_to_double(row_shift_key(G));
   const double x0 = G.x0 - c, x1 = G.x1 - c;
-  const Frag Bm{exp_nonpos(x0), exp_nonpos(x1)};
+  const Frag Bm{exp_nonpos_tab(x0, etab), exp_nonpos_tab(x1, etab)};
   const double s = quad_sum(expPi.x0 * Bm.x0 + expPi.x1 * Bm.x1);
   const double chk = x0 + x1;
-  ok = ok && (s >= kTiny) && (chk == chk);
+  ok = ok && sum_is_safe(s) && (chk == chk);
   const double ell = c + log_pos(s, ltab);
   const double Lq = across_sum(q == 0 ? prior * ell : 0.0);    // valid in lanes with q == 0
   const double w = prior / s;
@@ -223,10 +226,48 @@ __device__ __forceinline__ double terminate(const Frag &G, const Frag &expPi, do
 }
 
 // ---- first pass: L_elbo for every pair --------------------------------------
+// Each warp keeps NP pairs (one base, NP consecutive centres) in flight: the recursion of one pair
+// is a single dependent chain (shift -> exp -> DMMA -> log -> DMMA), so independent pairs are the
+// only instruction-level parallelism there is; every phase below is written across the NP pairs.
 constexpr int kBwdWarps = 8;
+constexpr int kNP = 2;
+
+template <int NP>
+__device__ __forceinline__ void bwd_step_n(const Frag (&E)[NP], Frag (&G)[NP], const Frag (&expA)[NP],
+                                           const Frag &Ab, const double *ltab, bool (&ok)[NP], int q) {
+  const double *etab = ltab + kLogDoubles;
+  int key[NP];
+  double x0[NP], x1[NP];
+  Frag Bm[NP], ST[NP], ell[NP];
+#pragma unroll
+  for (int p = 0; p < NP; p++) key[p] = row_shift_key(G[p]);
+#pragma unroll
+  for (int p = 0; p < NP; p++) {
+    const double c = key_to_double(key[p]);
+    x0[p] = G[p].x0 - c;
+    x1[p] = G[p].x1 - c;
+  }
+#pragma unroll
+  for (int p = 0; p < NP; p++) Bm[p] = Frag{exp_nonpos_tab(x0[p], etab), exp_nonpos_tab(x1[p], etab)};
+#pragma unroll
+  for (int p = 0; p < NP; p++) ST[p] = mma_nt(expA[p], Bm[p]);
+#pragma unroll
+  for (int p = 0; p < NP; p++) {
+    const double chk = x0[p] + x1[p];
+    ok[p] = ok[p] && sum_is_safe(ST[p].x0) && sum_is_safe(ST[p].x1) && (chk == chk);
+    const double cb0 = key_to_double(__shfl_sync(0xffffffffu, key[p], (2 * q) * 4));
+    const double cb1 = key_to_double(__shfl_sync(0xffffffffu, key[p], (2 * q + 1) * 4));
+    ell[p] = Frag{cb0 + log_pos(ST[p].x0, ltab), cb1 + log_pos(ST[p].x1, ltab)};
+  }
+#pragma unroll
+  for (int p = 0; p < NP; p++) {
+    G[p] = E[p];
+    mma_nt_acc(G[p], Ab, ell[p]);
+  }
+}
 
 template <int D, bool FULL>
-__global__ void __launch_bounds__(kBwdWarps * 32, 3)
+__global__ void __launch_bounds__(kBwdWarps * 32, 2)
 k_lattice_bwd(BaseView B, CentreView C, int T, int kc, double *L_elbo, Fallback fb) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
@@ -243,22 +284,31 @@ k_lattice_bwd(BaseView B, CentreView C, int T, int kc, double *L_elbo, Fallback 
   for (int i = blockIdx.x * kBwdWarps + warp; i < B.N; i += gridDim.x * kBwdWarps) {
     BaseConst<D, FULL> b;
     load_base(b, B, i, g, q);
-    for (int jj = 0; jj < nj; jj++) {
-      const double *rec = recs + jj * rs;
-      CentreConst<D, FULL> c;
-      load_centre(c, rec, g, q);
-      const Frag E = emission(b, rec, g, q);
-      Frag G = E;
-      bool ok = true;
-      for (int t = T - 1; t >= 1; t--)
-        ok = bwd_step<false>(E, G, c.expA, b.Ab, ltab, nullptr, nullptr, g, q) && ok;
-      Frag nu1;
-      const double Le = terminate(G, c.expPi, b.prior, ltab, q, nu1, ok);
-      ok = __all_sync(0xffffffffu, ok);
-      if (lane == 0) {
-        const size_t p = (size_t)i + (size_t)B.N * (j0 + jj);
-        L_elbo[p] = Le;
-        if (!ok) { fb.flags[p] = 1; atomicAdd(fb.count, 1); }
+    for (int jj = 0; jj < nj; jj += kNP) {
+      Frag E[kNP], G[kNP], expA[kNP], expPi[kNP];
+      bool ok[kNP];
+#pragma unroll
+      for (int p = 0; p < kNP; p++) {
+        const double *rec = recs + min(jj + p, nj - 1) * rs;   // odd tail: redo the last centre, not stored
+        CentreConst<D, FULL> c;
+        load_centre(c, rec, g, q);
+        expA[p] = c.expA;
+        expPi[p] = c.expPi;
+        E[p] = emission(b, rec, g, q);
+        G[p] = E[p];
+        ok[p] = true;
+      }
+      for (int t = T - 1; t >= 1; t--) bwd_step_n<kNP>(E, G, expA, b.Ab, ltab, ok, q);
+#pragma unroll
+      for (int p = 0; p < kNP; p++) {
+        Frag nu1;
+        const double Le = terminate(G[p], expPi[p], b.prior, ltab, q, nu1, ok[p]);
+        const bool good = __all_sync(0xffffffffu, ok[p]);
+        if (lane == 0 && jj + p < nj) {
+          const size_t pi = (size_t)i + (size_t)B.N * (j0 + jj + p);
+          L_elbo[pi] = Le;
+          if (!good) { fb.flags[pi] = 1; atomicAdd(fb.count, 1); }
+        }
       }
     }
   }
@@ -487,7 +537,7 @@ int launch_lattice_bwd(const BaseView &B, const CentreView &C, int T, double *L_
   const size_t smem = sizeof(double) * ((size_t)kc * rs + kTabDoubles);
   const int ny = (C.K + kc - 1) / kc;
   int nx = (B.N + kBwdWarps - 1) / kBwdWarps;
-  const int cap = 3 * sm_count();
+  const int cap = 2 * sm_count();
   if (nx > cap) nx = cap;
   return dispatch(B.d, B.covmode, [&](auto Dc, auto Fc) {
     auto kern = k_lattice_bwd<decltype(Dc)::value, decltype(Fc)::value>;
