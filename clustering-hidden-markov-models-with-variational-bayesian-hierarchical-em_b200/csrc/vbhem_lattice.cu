@@ -32,6 +32,10 @@
 
 #include <type_traits>
 
+#ifndef VB_EXPERIMENT
+#define VB_EXPERIMENT 0
+#endif
+
 namespace vbhem {
 
 namespace {
@@ -59,8 +63,12 @@ __device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b)
 }
 // D(m|n) = sum_c A[m][c] * X[n][c], all three in accumulator layout.
 __device__ __forceinline__ void mma_nt_acc(Frag &D, const Frag &A, const Frag &X) {
+#if VB_EXPERIMENT == 1 || VB_EXPERIMENT == 5 // timing experiment only: no tensor-core work
+  D.x0 = fma(A.x0, X.x0, D.x0) + 1.0; D.x1 = fma(A.x1, X.x1, D.x1) + 1.0;
+#else
   dmma(D.x0, D.x1, A.x0, X.x0);
   dmma(D.x0, D.x1, A.x1, X.x1);
+#endif
 }
 __device__ __forceinline__ Frag mma_nt(const Frag &A, const Frag &X) {
   Frag D{0.0, 0.0};
@@ -169,56 +177,62 @@ __device__ __forceinline__ Frag emission(const BaseConst<D, FULL> &b, const doub
   return Frag{out[0], out[1]};
 }
 
-// Shift of one lattice row: any number close to (and not below) the row maximum works, because the
+// Shift of one lattice row: any number within a few hundred of the row maximum works, because the
 // same c enters exp(G - c) and c + log(sum).  The maximum is taken over an order-preserving int32
-// key of the high words (integer pipe, 32-bit shuffles); key + 1 is >= every element of the row and
-// exceeds the true maximum by at most 2^-20 of its magnitude.
+// key of the high words (integer pipe, 32-bit shuffles); the shift differs from the true maximum by
+// at most 2^-20 of its magnitude.
 __device__ __forceinline__ int row_shift_key(const Frag &G) {
   int m = max(order_key(G.x0), order_key(G.x1));
   m = max(m, __shfl_xor_sync(0xffffffffu, m, 1));
   m = max(m, __shfl_xor_sync(0xffffffffu, m, 2));
-  return m + 1;
+  return m;
+}
+
+// The linear-domain recursion cannot create a NaN out of clean inputs (sums of non-negative
+// products, logs of range-checked sums), so NaN / Inf are screened once per pair, not per step:
+// the pair is bad if any transition / prior / centre weight is non-finite or an emission term is
+// NaN or +Inf.  Such pairs go to the general log-space kernel, which reproduces the reference.
+__device__ __forceinline__ bool pair_inputs_bad(double base_chk, const Frag &expA, const Frag &expPi,
+                                                const Frag &E) {
+  const double chk = base_chk + ((expA.x0 + expA.x1) + (expPi.x0 + expPi.x1));
+  return nonfinite(chk) | nan_or_posinf(E.x0) | nan_or_posinf(E.x1);
 }
 
 // One backward step (t = T-1 .. 1).  In: G(beta|sigma) = E + L of this step.  Out: G of the
 // previous time step, G(beta'|rho) = E + sum_beta Ab[beta',beta] lse[beta,rho].  With STORE the
-// step's Bm(beta|sigma) and 1/S^T(rho|beta) go to shared memory for the forward pass.  Returns
-// false if a sum underflowed or the inputs held NaN / +Inf.
+// step's Bm(beta|sigma) and 1/S^T(rho|beta) go to shared memory for the forward pass.  `rng`
+// accumulates the range excess of the step's sums (see range_excess).
 template <bool STORE>
-__device__ __forceinline__ bool bwd_step(const Frag &E, Frag &G, const Frag &expA, const Frag &Ab,
-                                         const double *ltab, double *sBm, double *sInvS, int g, int q) {
+__device__ __forceinline__ void bwd_step(const Frag &E, Frag &G, const Frag &expA, const Frag &Ab,
+                                         const double *ltab, double *sBm, double *sInvS, unsigned &rng, int g,
+                                         int q) {
   const double *etab = ltab + kLogDoubles;
   const int key = row_shift_key(G);
   const double c = key_to_double(key);                         // c[beta = g]
-  const double x0 = G.x0 - c, x1 = G.x1 - c;
-  const Frag Bm{exp_nonpos_tab(x0, etab), exp_nonpos_tab(x1, etab)};
+  const Frag Bm{exp_nonpos_tab(G.x0 - c, etab), exp_nonpos_tab(G.x1 - c, etab)};
   const Frag ST = mma_nt(expA, Bm);                            // S^T(rho = g | beta = 2q+e)
-  const double chk = x0 + x1;                                  // NaN iff NaN / +Inf upstream
-  const bool ok = sum_is_safe(ST.x0) && sum_is_safe(ST.x1) && (chk == chk);
+  rng = max(rng, max(range_excess(ST.x0), range_excess(ST.x1)));
   const double cb0 = key_to_double(__shfl_sync(0xffffffffu, key, (2 * q) * 4));
   const double cb1 = key_to_double(__shfl_sync(0xffffffffu, key, (2 * q + 1) * 4));
-  const Frag ell{cb0 + log_pos(ST.x0, ltab), cb1 + log_pos(ST.x1, ltab)};   // lse^T(rho | beta)
+  const Frag ell{log_pos_plus(ST.x0, ltab, cb0), log_pos_plus(ST.x1, ltab, cb1)};   // lse^T(rho | beta)
   G = E;
   mma_nt_acc(G, Ab, ell);                                      // G(beta' = g | rho = 2q+e)
   if (STORE) {
     tile_store(sBm, g, q, Bm);
     tile_store(sInvS, g, q, Frag{1.0 / ST.x0, 1.0 / ST.x1});
   }
-  return ok;
 }
 
 // Termination (vbhem_hmm_bwd_fwd_mex.c:1029-1080).  Returns L_elbo (all lanes) and
 // nu_1(beta = g | sigma = 2q+e) = prior * Theta_1.
 __device__ __forceinline__ double terminate(const Frag &G, const Frag &expPi, double prior, const double *ltab,
-                                            int q, Frag &nu1, bool &ok) {
+                                            int q, Frag &nu1, unsigned &rng) {
   const double *etab = ltab + kLogDoubles;
   const double c = key_to_double(row_shift_key(G));
-  const double x0 = G.x0 - c, x1 = G.x1 - c;
-  const Frag Bm{exp_nonpos_tab(x0, etab), exp_nonpos_tab(x1, etab)};
+  const Frag Bm{exp_nonpos_tab(G.x0 - c, etab), exp_nonpos_tab(G.x1 - c, etab)};
   const double s = quad_sum(expPi.x0 * Bm.x0 + expPi.x1 * Bm.x1);
-  const double chk = x0 + x1;
-  ok = ok && sum_is_safe(s) && (chk == chk);
-  const double ell = c + log_pos(s, ltab);
+  rng = max(rng, range_excess(s));
+  const double ell = log_pos_plus(s, ltab, c);
   const double Lq = across_sum(q == 0 ? prior * ell : 0.0);    // valid in lanes with q == 0
   const double w = prior / s;
   nu1 = Frag{w * expPi.x0 * Bm.x0, w * expPi.x1 * Bm.x1};
@@ -229,35 +243,42 @@ __device__ __forceinline__ double terminate(const Frag &G, const Frag &expPi, do
 // Each warp keeps NP pairs (one base, NP consecutive centres) in flight: the recursion of one pair
 // is a single dependent chain (shift -> exp -> DMMA -> log -> DMMA), so independent pairs are the
 // only instruction-level parallelism there is; every phase below is written across the NP pairs.
-constexpr int kBwdWarps = 8;
-constexpr int kNP = 2;
+#ifndef VB_BWD_WARPS
+#define VB_BWD_WARPS 8      // warps per CTA
+#endif
+#ifndef VB_BWD_MINB
+#define VB_BWD_MINB 2       // CTAs per SM the register budget is set for
+#endif
+#ifndef VB_NP
+#define VB_NP 2             // pairs in flight per warp
+#endif
+#ifndef VB_KC_BYTES
+#define VB_KC_BYTES (64 * 1024)   // shared-memory budget for centre records per CTA
+#endif
+constexpr int kBwdWarps = VB_BWD_WARPS;
+constexpr int kNP = VB_NP;
 
 template <int NP>
 __device__ __forceinline__ void bwd_step_n(const Frag (&E)[NP], Frag (&G)[NP], const Frag (&expA)[NP],
-                                           const Frag &Ab, const double *ltab, bool (&ok)[NP], int q) {
+                                           const Frag &Ab, const double *ltab, unsigned (&rng)[NP], int q) {
   const double *etab = ltab + kLogDoubles;
   int key[NP];
-  double x0[NP], x1[NP];
   Frag Bm[NP], ST[NP], ell[NP];
 #pragma unroll
   for (int p = 0; p < NP; p++) key[p] = row_shift_key(G[p]);
 #pragma unroll
   for (int p = 0; p < NP; p++) {
     const double c = key_to_double(key[p]);
-    x0[p] = G[p].x0 - c;
-    x1[p] = G[p].x1 - c;
+    Bm[p] = Frag{exp_nonpos_tab(G[p].x0 - c, etab), exp_nonpos_tab(G[p].x1 - c, etab)};
   }
-#pragma unroll
-  for (int p = 0; p < NP; p++) Bm[p] = Frag{exp_nonpos_tab(x0[p], etab), exp_nonpos_tab(x1[p], etab)};
 #pragma unroll
   for (int p = 0; p < NP; p++) ST[p] = mma_nt(expA[p], Bm[p]);
 #pragma unroll
   for (int p = 0; p < NP; p++) {
-    const double chk = x0[p] + x1[p];
-    ok[p] = ok[p] && sum_is_safe(ST[p].x0) && sum_is_safe(ST[p].x1) && (chk == chk);
+    rng[p] = max(rng[p], max(range_excess(ST[p].x0), range_excess(ST[p].x1)));
     const double cb0 = key_to_double(__shfl_sync(0xffffffffu, key[p], (2 * q) * 4));
     const double cb1 = key_to_double(__shfl_sync(0xffffffffu, key[p], (2 * q + 1) * 4));
-    ell[p] = Frag{cb0 + log_pos(ST[p].x0, ltab), cb1 + log_pos(ST[p].x1, ltab)};
+    ell[p] = Frag{log_pos_plus(ST[p].x0, ltab, cb0), log_pos_plus(ST[p].x1, ltab, cb1)};
   }
 #pragma unroll
   for (int p = 0; p < NP; p++) {
@@ -267,7 +288,7 @@ __device__ __forceinline__ void bwd_step_n(const Frag (&E)[NP], Frag (&G)[NP], c
 }
 
 template <int D, bool FULL>
-__global__ void __launch_bounds__(kBwdWarps * 32, 2)
+__global__ void __launch_bounds__(kBwdWarps * 32, VB_BWD_MINB)
 k_lattice_bwd(BaseView B, CentreView C, int T, int kc, double *L_elbo, Fallback fb) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
@@ -284,9 +305,11 @@ k_lattice_bwd(BaseView B, CentreView C, int T, int kc, double *L_elbo, Fallback 
   for (int i = blockIdx.x * kBwdWarps + warp; i < B.N; i += gridDim.x * kBwdWarps) {
     BaseConst<D, FULL> b;
     load_base(b, B, i, g, q);
+    const double base_chk = (b.Ab.x0 + b.Ab.x1) + b.prior;
     for (int jj = 0; jj < nj; jj += kNP) {
       Frag E[kNP], G[kNP], expA[kNP], expPi[kNP];
-      bool ok[kNP];
+      unsigned rng[kNP];
+      bool bad[kNP];
 #pragma unroll
       for (int p = 0; p < kNP; p++) {
         const double *rec = recs + min(jj + p, nj - 1) * rs;   // odd tail: redo the last centre, not stored
@@ -296,14 +319,15 @@ k_lattice_bwd(BaseView B, CentreView C, int T, int kc, double *L_elbo, Fallback 
         expPi[p] = c.expPi;
         E[p] = emission(b, rec, g, q);
         G[p] = E[p];
-        ok[p] = true;
+        rng[p] = 0u;
+        bad[p] = pair_inputs_bad(base_chk, expA[p], expPi[p], E[p]);
       }
-      for (int t = T - 1; t >= 1; t--) bwd_step_n<kNP>(E, G, expA, b.Ab, ltab, ok, q);
+      for (int t = T - 1; t >= 1; t--) bwd_step_n<kNP>(E, G, expA, b.Ab, ltab, rng, q);
 #pragma unroll
       for (int p = 0; p < kNP; p++) {
         Frag nu1;
-        const double Le = terminate(G[p], expPi[p], b.prior, ltab, q, nu1, ok[p]);
-        const bool good = __all_sync(0xffffffffu, ok[p]);
+        const double Le = terminate(G[p], expPi[p], b.prior, ltab, q, nu1, rng[p]);
+        const bool good = __all_sync(0xffffffffu, (rng[p] < kRangeBound) & !bad[p]);
         if (lane == 0 && jj + p < nj) {
           const size_t pi = (size_t)i + (size_t)B.N * (j0 + jj + p);
           L_elbo[pi] = Le;
@@ -332,15 +356,15 @@ __device__ __forceinline__ bool pair_full(const BaseView &B, int i, const BaseCo
   double *xch = sm + (size_t)2 * kTile * (T - 1);
   const Frag E = emission(b, rec, g, q);
   Frag G = E;
-  bool ok = true;
+  unsigned rng = 0u;
+  const bool bad = pair_inputs_bad((b.Ab.x0 + b.Ab.x1) + b.prior, c.expA, c.expPi, E);
   for (int t = T - 1; t >= 1; t--) {
     double *s = sm + (size_t)2 * kTile * (t - 1);
-    ok = bwd_step<true>(E, G, c.expA, b.Ab, ltab, s, s + kTile, g, q) && ok;
+    bwd_step<true>(E, G, c.expA, b.Ab, ltab, s, s + kTile, rng, g, q);
   }
   Frag nu1;
-  Lout = terminate(G, c.expPi, b.prior, ltab, q, nu1, ok);
-  ok = __all_sync(0xffffffffu, ok);
-  if (!ok) return false;
+  Lout = terminate(G, c.expPi, b.prior, ltab, q, nu1, rng);
+  if (!__all_sync(0xffffffffu, (rng < kRangeBound) & !bad)) return false;
 
   // nu_1 (beta|sigma) -> nuT (sigma = g | gamma = 2q+e)
   tile_store(xch, g, q, nu1);
@@ -532,12 +556,12 @@ bool lattice_supported(const BaseView &B, const CentreView &C, int T, bool need_
 int launch_lattice_bwd(const BaseView &B, const CentreView &C, int T, double *L_elbo, Fallback fb,
                        cudaStream_t st) {
   const int rs = C.rec_stride;
-  int kc = (int)((64 * 1024) / (sizeof(double) * rs));
+  int kc = (int)((VB_KC_BYTES) / (sizeof(double) * rs));
   if (kc > C.K) kc = C.K;
   const size_t smem = sizeof(double) * ((size_t)kc * rs + kTabDoubles);
   const int ny = (C.K + kc - 1) / kc;
   int nx = (B.N + kBwdWarps - 1) / kBwdWarps;
-  const int cap = 2 * sm_count();
+  const int cap = VB_BWD_MINB * sm_count();
   if (nx > cap) nx = cap;
   return dispatch(B.d, B.covmode, [&](auto Dc, auto Fc) {
     auto kern = k_lattice_bwd<decltype(Dc)::value, decltype(Fc)::value>;

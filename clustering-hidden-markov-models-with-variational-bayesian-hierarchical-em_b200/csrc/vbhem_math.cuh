@@ -24,16 +24,15 @@ namespace vbhem {
 
 // Polynomial / reduction constants.  On the device they live in constant memory so that DFMA reads
 // them as c[bank][offset] operands; as literals ptxas re-materialises each one with two moves per use.
-#define VB_MATH_CONSTS { 1.0 / 720, 1.0 / 120, 1.0 / 24, 1.0 / 6, /*4*/ VBHEM_32_LN2, -VBHEM_LN2_32_HI, \
-                         -VBHEM_LN2_32_LO, 6755399441055744.0, /*8*/ -1.0 / 6, 0.2, 1.0 / 3, VBHEM_LN2_HI, \
-                         VBHEM_LN2_LO }
+#define VB_MATH_CONSTS { 1.0 / 120, 1.0 / 24, 1.0 / 6, /*3*/ VBHEM_EXP_SCALE, -VBHEM_EXP_STEP_HI, \
+                         -VBHEM_EXP_STEP_LO, 6755399441055744.0, /*7*/ 0.2, 1.0 / 3, /*9*/ 0.69314718055994530942 }
 #ifdef __CUDACC__
-__constant__ double g_mc[13] = VB_MATH_CONSTS;
+__constant__ double g_mc[10] = VB_MATH_CONSTS;
 #endif
 #ifdef __CUDA_ARCH__
 #define VB_MC(i) g_mc[i]
 #else
-static const double h_mc[13] = VB_MATH_CONSTS;
+static const double h_mc[10] = VB_MATH_CONSTS;
 #define VB_MC(i) h_mc[i]
 #endif
 
@@ -59,47 +58,45 @@ VB_HD double make_double(int hi, int lo) {
 #endif
 }
 
-// e^x for x <= ~0.  Returns 0 below -708 (the reference's exp would return a denormal < 2.3e-308
-// there; it only ever enters sums whose largest term is 1).
-VB_HD double exp_nonpos(double x) {
-  constexpr double c[VBHEM_EXP_NCOEF] = VBHEM_EXP_COEF;
-  constexpr double kMagic = 6755399441055744.0;            // 1.5 * 2^52
-  const double t = fma(x, VBHEM_LOG2E, kMagic);
-  const int k = lo_word(t);                                // rint(x / ln2)
-  const double kf = t - kMagic;
-  double r = fma(kf, -VBHEM_LN2_HI, x);
-  r = fma(kf, -VBHEM_LN2_LO, r);
-  double p = c[VBHEM_EXP_NCOEF - 1];
-#pragma unroll
-  for (int i = VBHEM_EXP_NCOEF - 2; i >= 0; i--) p = fma(p, r, c[i]);
-  const double e = fma(p, r, 1.0);
-  const double s = make_double(hi_word(e) + (k << 20), lo_word(e));
-  return x < -708.0 ? 0.0 : s;
-}
-
-// Same function with a 32-entry table of 2^(j/32) (etab): 11 fp64 instructions instead of 16.
-VB_HD double exp_nonpos_tab(double x, const double *etab) {
-  const double t = fma(x, VB_MC(4), VB_MC(7));             // 32 x / ln2 + 1.5 * 2^52
-  const int k = lo_word(t);                                // rint(32 x / ln2)
-  const double kf = t - VB_MC(7);
-  double r = fma(kf, VB_MC(5), x);
-  r = fma(kf, VB_MC(6), r);
+// e^x for x <~ 0 (or -inf) with a VBHEM_EXP_BINS-entry table of 2^(j/BINS) (etab): 10 fp64
+// instructions.  x = k (ln2/BINS) + r;  e^x = 2^(k >> SHIFT) * T[k & (BINS-1)] * (1 + r + ... + r^5/120).
+// Below -708.5 it returns ~1e-308 instead of the reference's denormal / zero: the value only ever
+// enters sums whose largest term is ~1.  NaN inputs are the caller's business (see pair_inputs_bad).
+VB_HD double exp_nonpos_tab(double xin, const double *etab) {
+#if defined(VB_EXPERIMENT) && (VB_EXPERIMENT == 2 || VB_EXPERIMENT == 3 || VB_EXPERIMENT == 5)   // timing experiment only
+  return fma(xin, 1e-9, 1.0) + etab[0];
+#endif
+  // clamp at about -708.5 with one unsigned min on the high word (negative doubles order by magnitude
+  // there; -inf and anything below the clamp become ~1e-308, i.e. nothing next to a row maximum of 1)
+  const unsigned hx = (unsigned)hi_word(xin);
+  const double x = make_double((int)(hx < 0xC0862400u ? hx : 0xC0862400u), lo_word(xin));
+  const double t = fma(x, VB_MC(3), VB_MC(6));             // BINS x / ln2 + 1.5 * 2^52
+  const int k = lo_word(t);                                // rint(BINS x / ln2)
+  const double kf = t - VB_MC(6);
+  double r = fma(kf, VB_MC(4), x);
+  r = fma(kf, VB_MC(5), r);
   const double T = etab[k & (VBHEM_EXP_BINS - 1)];
   double q = fma(r, VB_MC(0), VB_MC(1));
   q = fma(q, r, VB_MC(2));
-  q = fma(q, r, VB_MC(3));
   q = fma(q, r, 0.5);
   q = fma(q, r, 1.0);
   const double e = fma(T * r, q, T);                       // T * e^r
-  const double s = make_double(hi_word(e) + ((k >> 5) << 20), lo_word(e));
-  // x < -708  <=>  its high word, read as unsigned, exceeds that of -708.0 (x <= 0 here; -inf too)
-  return (unsigned)hi_word(x) > 0xC0862000u ? 0.0 : s;
+  return make_double(hi_word(e) + ((k >> VBHEM_EXP_SHIFT) << 20), lo_word(e));
 }
 
-// tiny <= s < inf, with tiny = 2^-930 ~ 1.1e-280, on the integer pipe (false for NaN, Inf, negatives).
-VB_HD bool sum_is_safe(double s) {
-  return (unsigned)(hi_word(s) - 0x05D00000) < (unsigned)(0x7FF00000 - 0x05D00000);
+// Range tracking on the integer pipe: a lattice sum s is trusted iff 2^-930 <= s < inf.
+// range_excess(s) is < kRangeBound exactly then (NaN, Inf, negatives, zero and tiny values all map to
+// large unsigned numbers), so one running unsigned max per pair replaces per-step fp64 compares.
+constexpr unsigned kRangeBound = 0x7FF00000u - 0x05D00000u;
+VB_HD unsigned range_excess(double s) { return (unsigned)(hi_word(s) - 0x05D00000); }
+
+// true for NaN and +Inf (-Inf is a legitimate "impossible state" value of an emission term)
+VB_HD bool nan_or_posinf(double x) {
+  const int h = hi_word(x);
+  return (h >= 0x7ff00000) | ((unsigned)h > 0xfff00000u) | (((unsigned)h == 0xfff00000u) & (lo_word(x) != 0));
 }
+// true for NaN and +-Inf
+VB_HD bool nonfinite(double x) { return ((unsigned)hi_word(x) & 0x7ff00000u) == 0x7ff00000u; }
 
 // Order-preserving map double -> int32 that looks at the high word only, and its inverse.
 VB_HD int order_key(double x) {
@@ -108,22 +105,27 @@ VB_HD int order_key(double x) {
 }
 VB_HD double key_to_double(int key) { return make_double(key ^ ((key >> 31) & 0x7fffffff), 0); }
 
-// log(s) for normal positive s.  tab = VBHEM_LOG_TABLE as (invc, logc) pairs.
-VB_HD double log_pos(double s, const double *tab) {
+// add + log(s) for normal positive s, 8 fp64 instructions.  tab = VBHEM_LOG_TABLE as (invc, logc)
+// pairs: s = 2^e m, r = m invc - 1 (|r| < 2^-8.9), log s = e ln2 + logc + (r - r^2/2 + ... + r^5/5).
+// Absolute error <= ~4e-16 + |e| 2.4e-17 (ln2 is a single double: the result is always added to a
+// lattice shift of magnitude >> 1, so absolute accuracy is what matters).
+VB_HD double log_pos_plus(double s, const double *tab, double add) {
+#if defined(VB_EXPERIMENT) && (VB_EXPERIMENT == 2 || VB_EXPERIMENT == 4 || VB_EXPERIMENT == 5)   // timing experiment only
+  return fma(s, 1e-9, add) + tab[0];
+#endif
   const int hi = hi_word(s);
   const int e = (hi >> 20) - 1023;
-  const int i = (hi >> 13) & (VBHEM_LOG_BINS - 1);
+  const int i = (hi >> VBHEM_LOG_SHIFT) & (VBHEM_LOG_BINS - 1);
   const double m = make_double((hi & 0x000fffff) | 0x3ff00000, lo_word(s));
   const double invc = tab[2 * i], logc = tab[2 * i + 1];
   const double r = fma(m, invc, -1.0);
   const double r2 = r * r;
-  double q = fma(r, VB_MC(8), VB_MC(9));
-  q = fma(q, r, -0.25);
-  q = fma(q, r, VB_MC(10));
+  double q = fma(r, VB_MC(7), -0.25);
+  q = fma(q, r, VB_MC(8));
   q = fma(q, r, -0.5);
   const double p = fma(r2, q, r);
-  const double ed = (double)e;
-  return fma(ed, VB_MC(11), logc) + fma(ed, VB_MC(12), p);
+  return fma((double)e, VB_MC(9), add) + (logc + p);
 }
+VB_HD double log_pos(double s, const double *tab) { return log_pos_plus(s, tab, 0.0); }
 
 }  // namespace vbhem
