@@ -95,6 +95,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.armed = False      # only samples taken while armed (the timed region) are kept
 
     def run(self):
         try:
@@ -107,12 +108,14 @@ class ClockSampler(threading.Thread):
                      nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
                      nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
             while not self.stop_flag:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for bit, name in names.items():
-                    if r & bit:
-                        self.reasons.add(name)
-                time.sleep(0.02)
+                if self.armed:
+                    self.samples.append(mhz)
+                    for bit, name in names.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                time.sleep(0.005)
         except Exception as e:  # noqa: BLE001
             self.reasons.add(f"sampler_error:{type(e).__name__}")
 
@@ -227,13 +230,14 @@ def main():
         check(L.vbhem_finalize_stats_dev(bs._h, K, Sr.ctypes.data_as(ip), S, 1, C.c_void_p(stats.data_ptr())))
 
     def timed_run(bs, steps, warm):
+        sampler = ClockSampler(local)
+        sampler.start()
         for _ in range(warm):
             step(bs)
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
-        sampler = ClockSampler(local)
-        sampler.start()
+        sampler.armed = True
         tot, phases, launches = 0.0, np.zeros(8), 0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for _ in range(steps):
@@ -254,6 +258,7 @@ def main():
             tt = torch.tensor([tot], dtype=torch.float64, device="cuda")
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             tot = float(tt.item())
+        sampler.armed = False
         sampler.stop_flag = True
         sampler.join()
         return tot, phases / steps, launches, sampler.summary(), bs.counters()
@@ -305,11 +310,13 @@ def main():
         h2d = sum(v.nbytes for v in pb.values() if isinstance(v, np.ndarray)) + sum(v.nbytes for v in H.values())
         d2h = Lh.nbytes + zh.nbytes + sh.nbytes + pre.nbytes
 
+        b2 = BaseSet(pbp, device=local, packed=True)
+
         def e2e_step():
-            with BaseSet(pbp, device=local, packed=True) as b2:
-                check(L.vbhem_estep_hyp(b2._h, K, Sr.ctypes.data_as(ip), S, None, 1, tau, P(H["alpha"]), P(H["eta"]),
-                                        P(H["eps"]), P(H["m"]), P(H["W"]), P(H["v"]), P(H["lam"]), P(Lh), P(zh),
-                                        P(sh), P(pre)))
+            b2.repack(pbp, packed=True)                                   # base set: host -> device
+            check(L.vbhem_estep_hyp(b2._h, K, Sr.ctypes.data_as(ip), S, None, 1, tau, P(H["alpha"]), P(H["eta"]),
+                                    P(H["eps"]), P(H["m"]), P(H["W"]), P(H["v"]), P(H["lam"]), P(Lh), P(zh),
+                                    P(sh), P(pre)))                       # centres H2D; L_elbo, z_hat, stats D2H
             return float(sh[0])
 
         for _ in range(2):
@@ -329,8 +336,10 @@ def main():
             dt = float(tt.item())
         e2e = dict(value=pairs_step * ne / dt, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
                    ms_per_step=1e3 * dt / ne, steps=ne,
-                   note="every step: vbhem_pack_base (base set H2D from pinned memory) + vbhem_estep_hyp + "
-                        "L_elbo, z_hat, statistics D2H; shards are not all-reduced on this path")
+                   note="every step: vbhem_repack_base (whole base set H2D from pinned memory) + vbhem_estep_hyp "
+                        "(centres H2D; L_elbo, z_hat, statistics D2H into pinned memory); wall clock, "
+                        "synchronised both sides; shards are not all-reduced on this path")
+        b2.close()
 
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=W,

@@ -24,6 +24,7 @@ SIGNATURES = {
     "vbhem_pack_base": (C.c_int, [C.c_int, C.c_int, ip, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, dp,
                                   C.POINTER(vp)]),
     "vbhem_free_base": (C.c_int, [vp]),
+    "vbhem_repack_base": (C.c_int, [vp, ip, dp, dp, dp, dp, dp]),
     "vbhem_set_stream": (C.c_int, [vp, vp]),
     "vbhem_synchronize": (C.c_int, [vp]),
     "vbhem_set_kernel": (C.c_int, [vp, C.c_int]),

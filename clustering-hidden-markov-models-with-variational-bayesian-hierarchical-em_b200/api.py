@@ -44,6 +44,13 @@ class BaseSet:
                                     _d(pb["prior"]), _d(pb["A"]), _d(pb["mu"]), _d(pb["cov"]), _d(pb["Ntilde"]),
                                     C.byref(self._h)))
 
+    def repack(self, base: dict, packed: bool = False):
+        """Re-upload a base set of the same shape into this handle (``vbhem_repack_base``)."""
+        pb = base if packed else pack.pack_base(base)
+        assert (pb["N"], pb["maxSb"], pb["d"], pb["covmode"]) == (self.N, self.maxSb, self.d, self.covmode)
+        check(lib().vbhem_repack_base(self._h, _i(pb["Sb"]), _d(pb["prior"]), _d(pb["A"]), _d(pb["mu"]),
+                                      _d(pb["cov"]), _d(pb["Ntilde"])))
+
     # -- lifetime -----------------------------------------------------------
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:

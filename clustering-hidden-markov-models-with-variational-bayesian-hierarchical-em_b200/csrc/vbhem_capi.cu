@@ -440,6 +440,28 @@ int vbhem_pack_base(int device, int N, const int32_t *Sb, int maxSb, int d, int 
   return VBHEM_OK;
 }
 
+int vbhem_repack_base(vbhem_base_t *h, const int32_t *Sb, const double *prior, const double *A, const double *mu,
+                      const double *cov, const double *Ntilde) {
+  if (!h) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: base handle is NULL");
+  if (!Sb || !prior || !A || !mu || !cov) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: a base array is NULL");
+  const int N = h->B.N, maxSb = h->B.maxSb, d = h->B.d, dd = h->B.dd;
+  for (int i = 0; i < N; i++)
+    if (Sb[i] < 1 || Sb[i] > maxSb)
+      return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: Sb[%d]=%d outside 1..maxSb=%d", i, Sb[i], maxSb);
+  CU(cudaSetDevice(h->device));
+  const size_t nS = (size_t)maxSb * N;
+  CU(cudaMemcpyAsync(h->bSb.p, Sb, sizeof(int) * N, cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(h->bprior.p, prior, sizeof(double) * nS, cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(h->bA.p, A, sizeof(double) * nS * maxSb, cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(h->bmu.p, mu, sizeof(double) * nS * d, cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(h->bcov.p, cov, sizeof(double) * nS * dd, cudaMemcpyHostToDevice, h->st));
+  if (Ntilde) CU(cudaMemcpyAsync(h->bNt.p, Ntilde, sizeof(double) * N, cudaMemcpyHostToDevice, h->st));
+  launch_sanitize_base(h->B, h->bprior.as<double>(), h->bA.as<double>(), h->bmu.as<double>(), h->bcov.as<double>(),
+                       h->st);
+  CU(cudaGetLastError());
+  return VBHEM_OK;
+}
+
 int vbhem_free_base(vbhem_base_t *h) {
   if (!h) return VBHEM_OK;
   cudaSetDevice(h->device);

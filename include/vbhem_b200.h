@@ -72,6 +72,11 @@ int vbhem_pack_base(int device, int N, const int32_t *Sb, int maxSb, int d, int 
                     const double *Ntilde, vbhem_base_t **out);
 int vbhem_free_base(vbhem_base_t *base);
 
+/* Re-upload a base set of the SAME shape (N, maxSb, d, covmode) into an existing handle: the
+ * host-to-device copies of vbhem_pack_base without its allocations.  Ntilde may be NULL (= keep). */
+int vbhem_repack_base(vbhem_base_t *base, const int32_t *Sb, const double *prior, const double *A,
+                      const double *mu, const double *cov, const double *Ntilde);
+
 /* Run subsequent work of this handle on an existing CUDA stream (a cudaStream_t
  * passed as void*), e.g. torch's current stream.  NULL = the handle's own stream. */
 int vbhem_set_stream(vbhem_base_t *base, void *cuda_stream);

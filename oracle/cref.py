@@ -25,6 +25,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(HERE, "_ref", "libvbhem_ref.so")
 PORT_SO = os.path.join(HERE, "_build", "libvbhem_oracle.so")
+GATEWAY_SO = os.path.join(HERE, "_build", "libvbhem_gateway.so")   # this repo's MEX gateway behind the same shim
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -48,7 +49,7 @@ _libs = {}
 
 def _lib(which: str):
     if which not in _libs:
-        path = REF_SO if which == "ref" else PORT_SO
+        path = {"ref": REF_SO, "gateway": GATEWAY_SO}.get(which, PORT_SO)
         if not os.path.exists(path):
             build()
         _libs[which] = C.CDLL(path)
@@ -79,9 +80,10 @@ def alloc_pair_outputs(N, K, maxSr, d, covmode, fill=0.0):
                 mu=mk(K, N, d, maxSr), Mu=mk(K, N, dd, maxSr))
 
 
-def ref_estep_pairs(base: dict, cen: dict, T: int) -> dict:
-    """Reference C through the MEX gateway signature.  cen needs W and v (not vW)."""
-    lib = _lib("ref")
+def ref_estep_pairs(base: dict, cen: dict, T: int, which: str = "ref") -> dict:
+    """The MEX gateway signature through the mx shim: the reference's C (`ref`) or this repo's CUDA-backed
+    gateway (`gateway`).  cen needs W and v (not vW)."""
+    lib = _lib(which)
     N, maxSb = base["prior"].shape
     K, maxSr = cen["logPi"].shape
     d, covmode = base["d"], base["covmode"]
@@ -101,8 +103,8 @@ def ref_estep_pairs(base: dict, cen: dict, T: int) -> dict:
     return o
 
 
-def ref_call_malformed(mode: int):
-    lib = _lib("ref")
+def ref_call_malformed(mode: int, which: str = "ref"):
+    lib = _lib(which)
     lib.shim_last_error_id.restype = C.c_char_p
     rc = lib.shim_call_malformed(C.c_int(mode))
     return rc, lib.shim_last_error_id().decode()

@@ -1,0 +1,47 @@
+"""The MEX gateway of this repo (mex/vbhem_hmm_bwd_fwd_mex.cpp) behind the same mx shim and flat driver as
+the reference's gateway: identical call, identical cell/struct arguments, outputs compared with the reference
+golden vectors.  The error-id checks need no GPU (they fire before any CUDA call)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import cref
+from vbhem_b200 import pack
+from test_oracle import load_golden
+from util import assert_pairs_close
+
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+needs_gateway = pytest.mark.skipif(not os.path.exists(cref.GATEWAY_SO), reason="gateway not built")
+
+
+@needs_gateway
+def test_gateway_error_ids_match_reference():
+    """/root/reference/src/vbhem/vbhem_hmm_bwd_fwd_mex.c:335-366."""
+    assert cref.ref_call_malformed(0, "gateway") == (1, "MyToolbox:arrayProduct:nrhs")
+    assert cref.ref_call_malformed(1, "gateway") == (1, "MyToolbox:arrayProduct:nlhs")
+    assert cref.ref_call_malformed(2, "gateway") == (1, "vbhem_mex:invalidinput")
+    assert cref.ref_call_malformed(3, "gateway") == (1, "vbhem_mex:invalidinput")
+
+
+@needs_gateway
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+def test_gateway_matches_reference_golden(path):
+    base, hyp, cen, want, tau, covmode = load_golden(path)
+    pb, pc = pack.pack_base(base), pack.pack_centres(cen)
+    got = pack.pairs_to_natural(cref.ref_estep_pairs(pb, pc, tau, which="gateway"), pb["d"], pb["covmode"])
+    assert_pairs_close(got, want, rtol=1e-9, what="MEX gateway (CUDA) vs reference golden")
+
+
+@needs_gateway
+@pytest.mark.gpu
+def test_gateway_handle_reuse_and_reshape():
+    """Consecutive calls: same shape re-uploads into the cached handle, a new shape re-packs."""
+    from util import make_case, oracle_pairs
+    for seed, N, Sb in ((1, 6, 3), (2, 6, 3), (3, 9, 4)):
+        base, hyp, cen = make_case(N=N, K=3, Sb=Sb, Sr=3, d=2, covmode="full", ragged=True, seed=seed)
+        pb, pc = pack.pack_base(base), pack.pack_centres(cen)
+        got = pack.pairs_to_natural(cref.ref_estep_pairs(pb, pc, 4, which="gateway"), 2, 1)
+        assert_pairs_close(got, oracle_pairs(base, cen, 4), rtol=1e-9)

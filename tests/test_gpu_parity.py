@@ -254,3 +254,30 @@ def test_north_star_shape_properties():
     sub = {k: v[idx] for k, v in base.items()}
     want = oracle_pairs(sub, cen, 10)
     np.testing.assert_allclose(got["L_elbo"][idx], want["L_elbo"], rtol=RTOL)
+
+
+def test_sharded_matches_single():
+    """Two shards on one GPU, raw buffers summed on the host (what NCCL does across GPUs), then normalised:
+    equal to the un-sharded E-step up to fp64 summation order."""
+    from vbhem_b200.dist import shard_base
+    base, hyp, cen = make_case(N=401, K=6, Sb=5, Sr=4, d=2, covmode="full", ragged=True, seed=83, Nv=9.0)
+    with BaseSet(base) as bs:
+        one = bs.estep(cen, 6)
+        fin_one = bs.finalize(one["buf"], cen["Sr"], 4)
+        bufs = []
+        for r in range(2):
+            with BaseSet(shard_base(base, 2, r)) as sh:
+                bufs.append(sh.estep(cen, 6, want_pairs=False)["buf"])
+        fin_two = bs.finalize(bufs[0] + bufs[1], cen["Sr"], 4)
+    for k in fin_one:
+        np.testing.assert_allclose(fin_two[k], fin_one[k], rtol=1e-11, atol=1e-11 * np.abs(fin_one[k]).max(), err_msg=k)
+
+
+def test_repack_same_shape():
+    base, hyp, cen = make_case(N=50, K=3, Sb=4, Sr=3, d=2, covmode="full", ragged=True, seed=85)
+    base2, _, _ = make_case(N=50, K=3, Sb=4, Sr=3, d=2, covmode="full", ragged=True, seed=86)
+    with BaseSet(base) as bs:
+        bs.estep_pairs(cen, 4)
+        bs.repack(base2)
+        got = bs.estep_pairs(cen, 4)
+    assert_pairs_close(got, oracle_pairs(base2, cen, 4), rtol=RTOL)
