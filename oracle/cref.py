@@ -26,6 +26,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(HERE, "_ref", "libvbhem_ref.so")
 PORT_SO = os.path.join(HERE, "_build", "libvbhem_oracle.so")
 GATEWAY_SO = os.path.join(HERE, "_build", "libvbhem_gateway.so")   # this repo's MEX gateway behind the same shim
+FUSED_SO = os.path.join(HERE, "_build", "libvbhem_gateway_fused.so")   # ... and its fused-E-step gateway
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -49,7 +50,7 @@ _libs = {}
 
 def _lib(which: str):
     if which not in _libs:
-        path = {"ref": REF_SO, "gateway": GATEWAY_SO}.get(which, PORT_SO)
+        path = {"ref": REF_SO, "gateway": GATEWAY_SO, "fused": FUSED_SO}.get(which, PORT_SO)
         if not os.path.exists(path):
             build()
         _libs[which] = C.CDLL(path)
@@ -108,6 +109,31 @@ def ref_call_malformed(mode: int, which: str = "ref"):
     lib.shim_last_error_id.restype = C.c_char_p
     rc = lib.shim_call_malformed(C.c_int(mode))
     return rc, lib.shim_last_error_id().decode()
+
+
+def gateway_estep_fused(base: dict, cen: dict, T: int) -> dict:
+    """mex/vbhem_estep_fused_mex.cpp through the mx shim (nine plain-array outputs, already normalised)."""
+    lib = _lib("fused")
+    N, maxSb = base["prior"].shape
+    K, r = cen["logPi"].shape
+    d, covmode = base["d"], base["covmode"]
+    dd = d * d if covmode else d
+    o = dict(L_elbo=np.zeros((K, N)), zhat=np.zeros((K, N)), Nj=np.zeros(K), Nj_rho1=np.zeros((K, r)),
+             Nj_rho2rho=np.zeros((K, r, r)), Nj_rho=np.zeros((K, r)), y_bar=np.zeros((K, d, r)),
+             S_plus_C=np.zeros((K, dd, r)), lb=np.zeros(2))
+    fn = lib.shim_estep_fused
+    fn.restype = C.c_int
+    rc = fn(C.c_int(N), _i(_i32(base["Sb"])), C.c_int(maxSb), C.c_int(d), C.c_int(covmode),
+            _d(_f64(base["prior"])), _d(_f64(base["A"])), _d(_f64(base["mu"])), _d(_f64(base["cov"])),
+            _d(_f64(base["Ntilde"])), C.c_int(K), _i(_i32(cen["Sr"])), C.c_int(r),
+            _d(_f64(cen["logPi"])), _d(_f64(cen["logA"])), _d(_f64(cen["m"])), _d(_f64(cen["W"])),
+            _d(_f64(cen["v"])), _d(_f64(cen["cterm"])), _d(_f64(cen["logOmega"])), C.c_int(T),
+            *[_d(o[k]) for k in ("L_elbo", "zhat", "Nj", "Nj_rho1", "Nj_rho2rho", "Nj_rho", "y_bar", "S_plus_C", "lb")])
+    if rc != 0:
+        lib.shim_last_error_id.restype = C.c_char_p
+        lib.shim_last_error_msg.restype = C.c_char_p
+        raise RuntimeError(f"{lib.shim_last_error_id().decode()}: {lib.shim_last_error_msg().decode()}")
+    return o
 
 
 def port_estep_pairs(base: dict, cen: dict, T: int, lonly: bool = False) -> dict:

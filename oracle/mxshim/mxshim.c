@@ -168,33 +168,19 @@ static mxArray *dbl_scalar(double v) {
   return a;
 }
 
-/* shim_estep_pairs
- *
+/* ---- cell/struct trees of the two HMM lists ---------------------------------
  * Packed inputs (all column-major, fp64):
  *   base set  : Sb[Kb]; prior[maxSb,Kb]; A[maxSb,maxSb,Kb] (A[from,to]);
  *               mu[d,maxSb,Kb]; cov[d,d,maxSb,Kb] (full) or [d,maxSb,Kb] (diag)
  *   centres   : Sr[Kr]; logPi[maxSr,Kr]; logA[maxSr,maxSr,Kr] (row = from);
  *               m[d,maxSr,Kr]; W[d,d,maxSr,Kr] or [d,maxSr,Kr]; v[maxSr,Kr];
  *               cterm[maxSr,Kr]  (= -logLambdaTilde + d/lambda)
- *   covmode   : 0 diag, 1 full;  what: 5-arg or 7-arg gateway call.
- * Packed outputs (pair index p = i + Kb*j):
- *   L_elbo[Kb,Kr]; nu1[maxSr,p]; xi[maxSr,maxSr,p]; pr[maxSr,p];
- *   mu_out[maxSr,d,p]; Mu_out[maxSr,d,d,p] (full) or [maxSr,d,p] (diag).
- *   Entries beyond a pair's own (Sr_j) extent are left untouched.
- * Returns 0, or 1 if the gateway raised mexErrMsgIdAndTxt (see shim_last_error_*).
- */
-int shim_estep_pairs(int Kb, const int *Sb, int maxSb, int d, int covmode,
-                     const double *prior, const double *A, const double *mu, const double *cov,
-                     int Kr, const int *Sr, int maxSr,
-                     const double *logPi, const double *logA, const double *m, const double *W,
-                     const double *v, const double *cterm, int T,
-                     double *L_elbo, double *nu1, double *xi, double *pr, double *mu_out, double *Mu_out) {
-  const int dd = covmode ? d * d : d;
-  int rc = 0;
-  g_jmp_armed = 1;
-  if (setjmp(g_jmp)) { g_jmp_armed = 0; arena_reset(); return 1; }
+ *   covmode   : 0 diag, 1 full. */
 
-  /* h3m_b.hmm : {1 x Kb} of struct(A, prior, emit{1 x Sb} of struct(centres, covars, nin)) */
+/* h3m_b.hmm : {1 x Kb} of struct(A, prior, emit{1 x Sb} of struct(centres, covars, nin)) */
+static mxArray *make_base_tree(int Kb, const int *Sb, int maxSb, int d, int covmode, const double *prior,
+                               const double *A, const double *mu, const double *cov) {
+  const int dd = covmode ? d * d : d;
   mxArray *hb = mxCreateCellMatrix(1, (mwSize)Kb);
   for (int i = 0; i < Kb; i++) {
     const int S = Sb[i];
@@ -215,7 +201,16 @@ int shim_estep_pairs(int Kb, const int *Sb, int maxSb, int d, int covmode,
     set_field(h, "emit", em);
     mxSetCell(hb, i, h);
   }
-  /* h3m_r.hmm : {1 x Kr} of struct(logATilde, logPiTilde, emit{1 x Sr} of struct(m, W, v, logLambdaTildePlusDdivlamda)) */
+  return hb;
+}
+
+/* h3m_r.hmm : {1 x Kr} of struct(logATilde, logPiTilde, emit{1 x Sr} of struct(m, W, v,
+ * logLambdaTildePlusDdivlamda)); *c5 = logdetCovPlusDdivlamR {1 x Kr}, *c6 = invCovR {1 x Kr}
+ * (invCovR{j}(:,:,n) = v .* W, vbhem_h3m_c_step_fc.m:189). */
+static mxArray *make_centre_tree(int Kr, const int *Sr, int maxSr, int d, int covmode, const double *logPi,
+                                 const double *logA, const double *m, const double *W, const double *v,
+                                 const double *cterm, mxArray **c5out, mxArray **c6out) {
+  const int dd = covmode ? d * d : d;
   mxArray *hr = mxCreateCellMatrix(1, (mwSize)Kr);
   mxArray *c5 = mxCreateCellMatrix(1, (mwSize)Kr);
   mxArray *c6 = mxCreateCellMatrix(1, (mwSize)Kr);
@@ -238,7 +233,7 @@ int shim_estep_pairs(int Kb, const int *Sb, int maxSb, int d, int covmode,
       set_field(e, "logLambdaTildePlusDdivlamda", dbl_scalar(cterm[s]));
       mxSetCell(em, k, e);
       ld->pr[k] = cterm[s];
-      if (covmode)   /* invCovR{j}(:,:,n) = v .* W   (vbhem_h3m_c_step_fc.m:189) */
+      if (covmode)
         for (int q = 0; q < dd; q++) ic->pr[q + (size_t)dd * k] = v[s] * W[(size_t)dd * s + q];
     }
     set_field(h, "emit", em);
@@ -246,7 +241,30 @@ int shim_estep_pairs(int Kb, const int *Sb, int maxSb, int d, int covmode,
     mxSetCell(c5, j, ld);
     mxSetCell(c6, j, ic);
   }
+  *c5out = c5;
+  *c6out = c6;
+  return hr;
+}
 
+/* shim_estep_pairs: the six-output signature of vbhem_hmm_bwd_fwd_mex.
+ * Packed outputs (pair index p = i + Kb*j):
+ *   L_elbo[Kb,Kr]; nu1[maxSr,p]; xi[maxSr,maxSr,p]; pr[maxSr,p];
+ *   mu_out[maxSr,d,p]; Mu_out[maxSr,d,d,p] (full) or [maxSr,d,p] (diag).
+ *   Entries beyond a pair's own (Sr_j) extent are left untouched.
+ * Returns 0, or 1 if the gateway raised mexErrMsgIdAndTxt (see shim_last_error_*). */
+int shim_estep_pairs(int Kb, const int *Sb, int maxSb, int d, int covmode,
+                     const double *prior, const double *A, const double *mu, const double *cov,
+                     int Kr, const int *Sr, int maxSr,
+                     const double *logPi, const double *logA, const double *m, const double *W,
+                     const double *v, const double *cterm, int T,
+                     double *L_elbo, double *nu1, double *xi, double *pr, double *mu_out, double *Mu_out) {
+  const int dd = covmode ? d * d : d;
+  g_jmp_armed = 1;
+  if (setjmp(g_jmp)) { g_jmp_armed = 0; arena_reset(); return 1; }
+
+  mxArray *c5, *c6;
+  mxArray *hb = make_base_tree(Kb, Sb, maxSb, d, covmode, prior, A, mu, cov);
+  mxArray *hr = make_centre_tree(Kr, Sr, maxSr, d, covmode, logPi, logA, m, W, v, cterm, &c5, &c6);
   const mxArray *prhs[7];
   mxArray *plhs[6] = {0, 0, 0, 0, 0, 0};
   prhs[0] = hb; prhs[1] = hr;
@@ -280,7 +298,41 @@ int shim_estep_pairs(int Kb, const int *Sb, int maxSb, int d, int covmode,
   }
   g_jmp_armed = 0;
   arena_reset();
-  return rc;
+  return 0;
+}
+
+/* shim_estep_fused: the nine-output signature of this repo's vbhem_estep_fused_mex
+ * (mex/vbhem_estep_fused_mex.cpp).  Extra inputs Ntilde[Kb], logOmega[Kr]; outputs are copied
+ * verbatim: L_elbo[Kb,Kr], zhat[Kb,Kr], Nj[Kr], Nj_rho1[maxSr,Kr], Nj_rho2rho[maxSr,maxSr,Kr],
+ * Nj_rho[maxSr,Kr], y_bar[maxSr,d,Kr], S_plus_C[maxSr,dd,Kr], lb[2]. */
+int shim_estep_fused(int Kb, const int *Sb, int maxSb, int d, int covmode,
+                     const double *prior, const double *A, const double *mu, const double *cov,
+                     const double *Ntilde, int Kr, const int *Sr, int maxSr,
+                     const double *logPi, const double *logA, const double *m, const double *W,
+                     const double *v, const double *cterm, const double *logOmega, int T,
+                     double *L_elbo, double *zhat, double *Nj, double *Nj_rho1, double *Nj_rho2rho,
+                     double *Nj_rho, double *y_bar, double *S_plus_C, double *lb) {
+  g_jmp_armed = 1;
+  if (setjmp(g_jmp)) { g_jmp_armed = 0; arena_reset(); return 1; }
+  mxArray *c5, *c6;
+  mxArray *hb = make_base_tree(Kb, Sb, maxSb, d, covmode, prior, A, mu, cov);
+  mxArray *hr = make_centre_tree(Kr, Sr, maxSr, d, covmode, logPi, logA, m, W, v, cterm, &c5, &c6);
+  const mxArray *prhs[9];
+  mxArray *plhs[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  prhs[0] = hb; prhs[1] = hr;
+  prhs[2] = dbl_scalar((double)T);
+  prhs[3] = dbl_scalar((double)maxSb);
+  prhs[4] = dbl_scalar((double)maxSr);
+  prhs[5] = dbl_matrix(Kb, 1, Ntilde, Kb, 0);
+  prhs[6] = dbl_matrix(1, Kr, logOmega, 1, 0);
+  prhs[7] = c5; prhs[8] = c6;
+  mexFunction(9, plhs, covmode ? 9 : 7, prhs);
+  double *outs[9] = {L_elbo, zhat, Nj, Nj_rho1, Nj_rho2rho, Nj_rho, y_bar, S_plus_C, lb};
+  for (int k = 0; k < 9; k++)
+    memcpy(outs[k], mxGetPr(plhs[k]), sizeof(double) * mxGetNumberOfElements(plhs[k]));
+  g_jmp_armed = 0;
+  arena_reset();
+  return 0;
 }
 
 /* Calls the linked gateway with a deliberately malformed argument list so the

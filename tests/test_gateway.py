@@ -45,3 +45,40 @@ def test_gateway_handle_reuse_and_reshape():
         pb, pc = pack.pack_base(base), pack.pack_centres(cen)
         got = pack.pairs_to_natural(cref.ref_estep_pairs(pb, pc, 4, which="gateway"), 2, 1)
         assert_pairs_close(got, oracle_pairs(base, cen, 4), rtol=1e-9)
+
+
+needs_fused = pytest.mark.skipif(not os.path.exists(cref.FUSED_SO), reason="fused gateway not built")
+
+
+@needs_fused
+def test_fused_gateway_argument_count_errors():
+    assert cref.ref_call_malformed(0, "fused") == (1, "MyToolbox:arrayProduct:nrhs")
+    assert cref.ref_call_malformed(1, "fused")[0] == 1
+
+
+@needs_fused
+@pytest.mark.gpu
+@pytest.mark.parametrize("covmode,d", [("full", 2), ("diag", 3)])
+def test_fused_gateway_matches_oracle(covmode, d):
+    """vbhem_estep_fused_mex through the shim vs the oracle's literal path + numpy normalisation."""
+    from oracle import numpy_ref as nr
+    from util import make_case, oracle_fused
+    base, hyp, cen = make_case(N=150, K=4, Sb=4, Sr=3, d=d, covmode=covmode, ragged=True, seed=29, Nv=12.0,
+                               sr_list=[3, 1, 2, 3])
+    pb, pc = pack.pack_base(base), pack.pack_centres(cen)
+    got = cref.gateway_estep_fused(pb, pc, 5)
+    want = oracle_fused(base, cen, 5)
+    np.testing.assert_allclose(got["L_elbo"].T, want["L_elbo"], rtol=1e-9)
+    np.testing.assert_allclose(got["zhat"].T, want["zhat"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(got["Nj"], want["Nj"], rtol=1e-9)
+    np.testing.assert_allclose(got["lb"][0], want["lb"][0], rtol=1e-9)
+    for j in range(4):
+        r = int(cen["Sr"][j])
+        f = nr.finalize_stats(want["nu1"][j, :r], want["xi"][j, :r, :r], want["pr"][j, :r], want["mu"][j, :r],
+                              want["Mu"][j, :r], covmode)
+        np.testing.assert_allclose(got["Nj_rho1"][j, :r], f[0], rtol=1e-9)
+        np.testing.assert_allclose(got["Nj_rho2rho"][j].T[:r, :r], f[1], rtol=1e-9, atol=1e-9 * np.abs(f[1]).max())
+        np.testing.assert_allclose(got["Nj_rho"][j, :r], f[2], rtol=1e-9)
+        np.testing.assert_allclose(got["y_bar"][j].T[:r], f[3], rtol=1e-9)
+        SC = got["S_plus_C"][j].reshape(d, d, 3).transpose(2, 1, 0)[:r] if covmode == "full" else got["S_plus_C"][j].T[:r]
+        np.testing.assert_allclose(SC, f[4], rtol=1e-7, atol=1e-9 * np.abs(f[4]).max())

@@ -1,0 +1,38 @@
+"""CPU tier: the lattice kernels' own fp64 exp / log (csrc/vbhem_math.cuh) compiled for the host and compared
+with libm.  They replace libdevice's exp / log (19 / 47 DFMA-equivalents per call on B200) with 10 / 8 fp64
+instructions; this pins their accuracy so the 1e-9 parity budget is not spent here."""
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "clustering-hidden-markov-models-with-variational-bayesian-hierarchical-em_b200", "csrc")
+
+
+def test_kernel_math_against_libm(tmp_path):
+    exe = str(tmp_path / "math_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-I", CSRC, "-o", exe,
+                    os.path.join(ROOT, "tests", "math_check.cpp")], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split("\n")
+    exp_rel, log_abs_small, log_rel = map(float, out[0].split())
+    assert exp_rel < 4.5e-16              # <= 2 ulp over [-708, 0.7]
+    assert log_abs_small < 8e-15          # log s with |log s| < 32: about one ulp of 32
+    assert log_rel < 4.5e-16              # c + log s, relative to max(|c|, |log s|, 1)
+    assert out[1].split() == ["1"] * 8, out[1]
+    bad, slack = out[2].split()
+    assert int(bad) == 0 and float(slack) < 2e-6   # order key monotone; shift within 2^-20 of the element
+
+
+def test_math_tables_are_current(tmp_path):
+    """vbhem_mathtab.h is generated; regenerate and compare so the committed header cannot drift."""
+    import importlib.util
+    import shutil
+    src = os.path.join(CSRC, "gen_mathtab.py")
+    work = tmp_path / "gen"
+    work.mkdir()
+    shutil.copy(src, work / "gen_mathtab.py")
+    spec = importlib.util.spec_from_file_location("gen_mathtab", str(work / "gen_mathtab.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.HERE = str(work)
+    mod.main()
+    assert open(work / "vbhem_mathtab.h").read() == open(os.path.join(CSRC, "vbhem_mathtab.h")).read()
