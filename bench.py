@@ -285,6 +285,19 @@ def main():
     phases = dict(stage_ms=ph[0], first_pass_ms=ph[1], zhat_list_ms=ph[2], second_pass_ms=ph[3], reduce_ms=ph[4],
                   estep_ms=ph[5], active_pairs=counters["active_pairs"], fallback_pairs=counters["general_pairs"])
 
+    # ---- one full VBHEM iteration (E-step + normalisation D2H + host M-step + lower bound), N = 1 only
+    vbhem_iter = None
+    if world == 1:
+        from vbhem_b200 import h3m
+        opt = dict(synth.DEFAULT_OPT, tau=tau, max_iter=6, minDiff=0.0)
+        check(L.vbhem_set_profile(bs._h, 0))
+        run = h3m.vbhem_h3m_c_step_fc({k: v for k, v in hyp.items()}, bs, opt)
+        check(L.vbhem_set_profile(bs._h, 1))
+        vbhem_iter = dict(ms=run["ms_per_iter"], iters=int(run["iters"]), LL_first=float(run["LogLs"][0]),
+                          LL_last=float(run["LogLs"][-1]),
+                          note="median wall time of one EM iteration of h3m.vbhem_h3m_c_step_fc: fused E-step on the "
+                               "GPU, statistics D2H, M-step and lower bound on the host (numpy)")
+
     # ---- strong scaling of the north-star size (100k bases in total)
     strong = None
     if world > 1:
@@ -350,6 +363,8 @@ def main():
             line["cpu_baseline"] = cpu
         if strong is not None:
             line["strong"] = strong
+        if vbhem_iter is not None:
+            line["vbhem_iter"] = vbhem_iter
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

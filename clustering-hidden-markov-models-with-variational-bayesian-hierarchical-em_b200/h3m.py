@@ -1,0 +1,179 @@
+"""Host mirror of the reference's EM driver around the E-step (Python, numpy for the O(K*S) host parts).
+
+``vbhem_h3m_c_step_fc(h3m_r, base, vbhemopt)`` follows the control flow of
+/root/reference/src/vbhem/vbhem_h3m_c_step_fc.m:115-433 -- E-step, lower bound, relative-change
+convergence test from the third pass on, M-step (also after the breaking pass), NaN guard -- with the same
+option names (``tau``, ``max_iter``, ``minDiff``, ``alpha0``, ``eta0``, ``epsilon0``, ``m0``, ``lambda0``, ``W0``,
+``v0``).  The E-step (pre-pass, L_elbo, responsibilities, statistics reduction and normalisation) runs on the
+GPU through the C ABI; what stays on the host is the part SURVEY.md 8(f) ranks "next": the M-step formulas
+(/root/reference/src/vbhem/vbhem_mstep_component.m:42-70) and the lower bound
+(/root/reference/src/vbhem/vbhemh3m_lb.m:64-186), both O(K*S*d^2).
+
+Centre hyper-parameters travel as one dict of stacked arrays (natural layout):
+    alpha[K], eta[K,S], epsilon[K,S,S] (from,to), m[K,S,d], W[K,S,d,d] | [K,S,d], v[K,S], lam[K,S], Sr[K]
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+from scipy.special import gammaln, psi
+
+
+def hmms_to_h3m_hem(hmms: list, covmode: str = "full", use_post: bool = True, Nv: float = 100.0) -> dict:
+    """List of learned HMMs -> natural base dict (hmms_to_h3m_hem.m:19-140).
+
+    Each HMM is a dict with ``prior[S]``, ``trans[S,S]``, ``mean[S,d]``, ``cov[S,d,d]`` and, for ``use_post``,
+    ``varpar = dict(alpha[S], epsilon[S,S], beta[S])``; ``None`` entries become zero-weight dummies (:113-133).
+    """
+    live = [h for h in hmms if h is not None]
+    d = np.asarray(live[0]["mean"]).shape[1]
+    S = max(len(h["prior"]) for h in live)
+    N = len(hmms)
+    full = covmode == "full"
+    out = dict(Sb=np.ones(N, np.int32), prior=np.zeros((N, S)), A=np.zeros((N, S, S)), mu=np.zeros((N, S, d)),
+               cov=np.zeros((N, S, d, d) if full else (N, S, d)))
+    omega = np.ones(N)
+    for i, h in enumerate(hmms):
+        if h is None:                                   # dummy one-state HMM with weight 0
+            out["prior"][i, 0] = 1.0
+            out["A"][i, 0, 0] = 1.0
+            out["cov"][i, 0] = np.eye(d) if full else np.ones(d)
+            omega[i] = 0.0
+            continue
+        s = len(h["prior"])
+        out["Sb"][i] = s
+        if use_post:
+            al, ep = np.asarray(h["varpar"]["alpha"], float), np.asarray(h["varpar"]["epsilon"], float)
+            out["prior"][i, :s] = np.exp(psi(al) - psi(al.sum()))
+            out["A"][i, :s, :s] = np.exp(psi(ep) - psi(ep.sum(1, keepdims=True)))
+            tb = (np.asarray(h["varpar"]["beta"], float) + 1.0) / np.asarray(h["varpar"]["beta"], float)
+        else:
+            out["prior"][i, :s] = h["prior"]
+            out["A"][i, :s, :s] = h["trans"]
+            tb = np.ones(s)
+        out["mu"][i, :s] = h["mean"]
+        cov = np.asarray(h["cov"], float)
+        out["cov"][i, :s] = tb[:, None, None] * cov if full else tb[:, None] * np.diagonal(cov, axis1=1, axis2=2)
+    omega /= omega.sum()
+    out["Ntilde"] = Nv * N * omega                      # vbhem_h3m_c_step_fc.m:26-30
+    return out
+
+
+def _W0(opt, d):
+    w = np.atleast_1d(np.asarray(opt["W0"], float))
+    return (w[0] * np.eye(d), True) if w.size == 1 else (np.diag(w), False)
+
+
+def vbhem_mstep(fin: dict, opt: dict, covmode: str = "full") -> dict:
+    """vbhem_mstep_component.m:42-70 for all centres at once.  fin: the normalised statistics of
+    BaseSet.finalize (Nj, Nj_rho1[K,S], Nj_rho2rho[K,S,S], Nj_rho[K,S], y_bar[K,S,d], S_plus_C[K,S,d,d]|[K,S,d])."""
+    R = fin["Nj_rho"]
+    K, S = R.shape
+    d = fin["y_bar"].shape[2]
+    W0m, _ = _W0(opt, d)
+    if opt["v0"] <= d - 1:
+        raise ValueError("v0 not large enough")
+    W0inv = np.linalg.inv(W0m)
+    m0 = np.asarray(opt["m0"], float).reshape(d)
+    lam0, v0 = float(opt["lambda0"]), float(opt["v0"])
+    diff = fin["y_bar"] - m0
+    SC = fin["S_plus_C"] if covmode == "full" else np.einsum("ksi,ij->ksij", fin["S_plus_C"], np.eye(d))
+    mult1 = lam0 * R / (lam0 + R)
+    tW = np.linalg.inv(W0inv + R[..., None, None] * SC + mult1[..., None, None] * diff[..., :, None] * diff[..., None, :])
+    Wn = 0.5 * (tW + np.swapaxes(tW, -1, -2))
+    return dict(alpha=opt["alpha0"] + fin["Nj"], eta=opt["eta0"] + fin["Nj_rho1"],
+                epsilon=opt["epsilon0"] + fin["Nj_rho2rho"], lam=lam0 + R, v=v0 + R + 1.0,
+                m=(lam0 * m0 + R[..., None] * fin["y_bar"]) / (lam0 + R)[..., None],
+                W=Wn if covmode == "full" else np.diagonal(Wn, axis1=-2, axis2=-1).copy())
+
+
+def vbhemh3m_lb(Lt1, Lt7, Nj, pre: dict, hyp: dict, opt: dict, covmode: str = "full"):
+    """vbhemh3m_lb.m:64-186.  pre: logOmega[K], logPi[K,S], logA[K,S,S], logLambdaTilde[K,S] (device pre-pass)."""
+    K, S = hyp["eta"].shape
+    d = hyp["m"].shape[2]
+    a0, e0, p0 = float(opt["alpha0"]), float(opt["eta0"]), float(opt["epsilon0"])
+    lam0, v0 = float(opt["lambda0"]), float(opt["v0"])
+    m0 = np.asarray(opt["m0"], float).reshape(d)
+    W0m, iid = _W0(opt, d)
+    W0inv = np.linalg.inv(W0m)
+    logdetW0inv = d * np.log(W0inv[0, 0]) if iid else np.sum(np.log(np.diag(W0inv)))
+    ii = np.arange(1, d + 1, dtype=float)
+    logB0 = (v0 / 2) * logdetW0inv - (v0 * d / 2) * np.log(2) - (d * (d - 1) / 4) * np.log(np.pi) \
+        - np.sum(gammaln(0.5 * (v0 + 1 - ii)))
+    lO, lP, lA, lL = pre["logOmega"], pre["logPi"], pre["logA"], pre["logLambdaTilde"]
+    al, eta, eps, lam, v = hyp["alpha"], hyp["eta"], hyp["epsilon"], hyp["lam"], hyp["v"]
+    W = hyp["W"] if covmode == "full" else np.einsum("ksi,ij->ksij", hyp["W"], np.eye(d))
+    Lt2 = float(np.dot(Nj, lO))
+    Lt3 = K * (gammaln(S * e0) - S * gammaln(e0)) + (e0 - 1) * lP.sum()
+    Lt4 = K * S * (gammaln(S * p0) - S * gammaln(p0)) + (p0 - 1) * lA.sum()
+    Lt6 = gammaln(K * a0) - K * gammaln(a0) + (a0 - 1) * lO.sum()
+    Lt8 = gammaln(al.sum()) - gammaln(al).sum() + float(np.dot(al - 1, lO))
+    df = hyp["m"] - m0
+    mWm = np.einsum("ksi,ksij,ksj->ks", df, W, df)
+    trW = np.einsum("ij,ksji->ks", W0inv, W)
+    logdetW = np.log(np.linalg.det(W))
+    logB = -(v / 2) * logdetW - (v * d / 2) * np.log(2) - (d * (d - 1) / 4) * np.log(np.pi) \
+        - gammaln(0.5 * (v[..., None] + 1 - ii)).sum(-1)
+    H = (-logB - 0.5 * (v - d - 1) * lL + 0.5 * v * d).sum(1)
+    Lt5 = (0.5 * (d * np.log(lam0 / (2 * np.pi)) + lL - d * lam0 / lam - lam0 * v * mWm).sum()
+           + K * S * logB0 + 0.5 * (v0 - d - 1) * lL.sum() - 0.5 * (v * trW).sum())
+    Lt9 = (gammaln(eta.sum(1)) - gammaln(eta).sum(1) + ((eta - 1) * lP).sum(1)).sum() \
+        + (gammaln(eps.sum(2)) - gammaln(eps).sum(2) + ((eps - 1) * lA).sum(2)).sum()
+    Lt10 = (0.5 * (lL + d * np.log(lam / (2 * np.pi))).sum(1) - 0.5 * d * S - H).sum()
+    LB = Lt1 + Lt2 + Lt3 + Lt4 + Lt5 + Lt6 - Lt7 - Lt8 - Lt9 - Lt10
+    return float(LB), dict(Lt1=Lt1, Lt2=Lt2, Lt3=Lt3, Lt4=Lt4, Lt5=Lt5, Lt6=Lt6, Lt7=Lt7, Lt8=Lt8, Lt9=Lt9, Lt10=Lt10)
+
+
+def vbhem_h3m_c_step_fc(h3m_r: dict, base, vbhemopt: dict, covmode: str = "full", estep=None, verbose: int = 0):
+    """One EM run from the centre hyper-parameters ``h3m_r`` (vbhem_h3m_c_step_fc.m:115-433).
+
+    ``base``: a ``BaseSet`` (device-resident base mixture).  ``estep(hyp, tau)`` may be supplied to run the
+    E-step elsewhere (e.g. ``dist.ShardedEStep.estep_hyp`` on several GPUs); it must return the normalised
+    statistics plus ``pre`` / ``lb`` as ``BaseSet`` does.
+    Returns dict(hyp=final hyper-parameters, LogLs, LL, iters, ms_per_iter, Nj, unstable).
+    """
+    opt = vbhemopt
+    tau, max_iter, min_diff = int(opt["tau"]), int(opt.get("max_iter", 200)), float(opt.get("minDiff", 1e-5))
+    hyp = {k: np.array(v, dtype=np.int32 if k == "Sr" else np.float64) for k, v in h3m_r.items()}
+    K, S = hyp["eta"].shape
+    hyp.setdefault("Sr", np.full(K, S, np.int32))
+
+    def default_estep(h, t):
+        out = base.estep_hyp(h, t, want_pairs=False)
+        fin = base.finalize(out["buf"], h["Sr"], S)
+        fin["pre"] = dict(logOmega=out["logOmega"], logPi=out["logPi"], logA=out["logA"],
+                          logLambdaTilde=out["logLambdaTilde"])
+        return fin
+
+    run = estep or default_estep
+    LogLs, lastL, it, unstable, times = [], -np.finfo(float).max, 0, False, []
+    fin = None
+    while True:
+        t0 = time.perf_counter()
+        fin = run(hyp, tau)                                               # E-step (GPU)
+        L, _ = vbhemh3m_lb(fin["lb"][0], fin["lb"][1], fin["Nj"], fin["pre"], hyp, opt, covmode)
+        do_break = False
+        if it > 1:
+            if abs((L - lastL) / lastL) <= min_diff:
+                do_break = True
+        if it == max_iter:
+            do_break = True
+        if np.isnan(L):                                                   # :338-354
+            do_break, unstable, L = True, True, -np.inf
+        if do_break and unstable:
+            LogLs.append(L)
+            break
+        new = vbhem_mstep(fin, opt, covmode)                              # M-step (host, O(K*S*d^2))
+        new["Sr"] = hyp["Sr"]
+        hyp = new
+        it += 1
+        LogLs.append(L)
+        lastL = L
+        times.append(time.perf_counter() - t0)
+        if verbose:
+            print(f"iter {it}: L={L:.10g}")
+        if do_break:
+            break
+    return dict(hyp=hyp, LogLs=np.array(LogLs), LL=LogLs[-1], iters=it, unstable=unstable, Nj=fin["Nj"],
+                ms_per_iter=1e3 * float(np.median(times)) if times else float("nan"))

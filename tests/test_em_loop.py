@@ -1,0 +1,103 @@
+"""EM driver (host mirror of vbhem_h3m_c_step_fc) on the GPU against the same loop built from the oracle:
+lower-bound trace, iteration count and final hyper-parameters.  The M-step / lower-bound host code in the
+package (h3m.py) is checked against oracle/numpy_ref.py on CPU as well."""
+import numpy as np
+import pytest
+
+from oracle import cref, numpy_ref as nr
+from vbhem_b200 import h3m, pack, synth
+from util import make_case, prepass_natural
+
+OPT = dict(alpha0=1.0, eta0=1.0, epsilon0=1.0, lambda0=1.0, v0=5.0, W0=0.005, m0=(256.0, 192.0), tau=5,
+           max_iter=30, minDiff=1e-6, Nv=20.0)
+
+
+def oracle_em(base, hyp, opt, covmode="full"):
+    """The same control flow with every piece taken from the oracle."""
+    pb = pack.pack_base(base)
+    K, S = hyp["eta"].shape
+    hyp = {k: np.array(v) for k, v in hyp.items()}
+    LogLs, lastL, it = [], -np.finfo(float).max, 0
+    while True:
+        cen = prepass_natural(hyp, covmode)
+        St = pack.stats_to_natural(cref.port_estep_fused(pb, pack.pack_centres(cen), opt["tau"], want_pairs=False), 2, 1)
+        centres = [dict(eta=hyp["eta"][j], epsilon=hyp["epsilon"][j], m=hyp["m"][j], W=hyp["W"][j], v=hyp["v"][j],
+                        lam=hyp["lam"][j]) for j in range(K)]
+        pre = [nr.prepass(c, covmode) for c in centres]
+        L, _ = nr.lower_bound(St["lb"][0], St["lb"][1], St["Nj"], cen["logOmega"], hyp["alpha"], centres, pre, opt, covmode)
+        do_break = it > 1 and abs((L - lastL) / lastL) <= opt["minDiff"]
+        do_break = do_break or it == opt["max_iter"]
+        new = dict(alpha=opt["alpha0"] + St["Nj"], Sr=hyp["Sr"])
+        parts = [nr.mstep_component(*nr.finalize_stats(St["nu1"][j], St["xi"][j], St["pr"][j], St["mu"][j], St["Mu"][j],
+                                                       covmode), opt, covmode) for j in range(K)]
+        for k in ("eta", "epsilon", "lam", "v", "m", "W"):
+            new[k] = np.stack([p[k] for p in parts])
+        hyp = new
+        it += 1
+        LogLs.append(L)
+        lastL = L
+        if do_break:
+            break
+    return hyp, np.array(LogLs)
+
+
+def test_host_mstep_and_lb_match_numpy_ref():
+    """CPU: h3m.vbhem_mstep / vbhemh3m_lb (vectorised) against the per-centre numpy_ref restatement."""
+    base, hyp, cen = make_case(N=25, K=3, Sb=3, Sr=3, d=2, covmode="full", ragged=False, seed=12, Nv=10.0)
+    St = pack.stats_to_natural(cref.port_estep_fused(pack.pack_base(base), pack.pack_centres(cen), 4), 2, 1)
+    fins = [nr.finalize_stats(St["nu1"][j], St["xi"][j], St["pr"][j], St["mu"][j], St["Mu"][j]) for j in range(3)]
+    fin = dict(Nj=St["Nj"], Nj_rho1=np.stack([f[0] for f in fins]), Nj_rho2rho=np.stack([f[1] for f in fins]),
+               Nj_rho=np.stack([f[2] for f in fins]), y_bar=np.stack([f[3] for f in fins]),
+               S_plus_C=np.stack([f[4] for f in fins]))
+    got = h3m.vbhem_mstep(fin, OPT)
+    for j in range(3):
+        want = nr.mstep_component(*fins[j], OPT)
+        for k in ("eta", "epsilon", "lam", "v", "m", "W"):
+            np.testing.assert_allclose(got[k][j], want[k], rtol=1e-12, atol=1e-300, err_msg=k)
+    centres = [dict(eta=hyp["eta"][j], epsilon=hyp["epsilon"][j], m=hyp["m"][j], W=hyp["W"][j], v=hyp["v"][j],
+                    lam=hyp["lam"][j]) for j in range(3)]
+    pre = [nr.prepass(c) for c in centres]
+    want_L, want_t = nr.lower_bound(St["lb"][0], St["lb"][1], St["Nj"], cen["logOmega"], hyp["alpha"], centres, pre, OPT)
+    pre_s = dict(logOmega=cen["logOmega"], logPi=cen["logPi"], logA=cen["logA"], logLambdaTilde=cen["logLambdaTilde"])
+    got_L, got_t = h3m.vbhemh3m_lb(St["lb"][0], St["lb"][1], St["Nj"], pre_s, hyp, OPT)
+    for k in want_t:
+        np.testing.assert_allclose(got_t[k], want_t[k], rtol=1e-12, atol=1e-9, err_msg=k)
+    np.testing.assert_allclose(got_L, want_L, rtol=1e-12)
+
+
+def test_hmms_to_h3m_hem_layout():
+    rng = np.random.default_rng(0)
+    hm = []
+    for s in (2, 3, None, 1):
+        if s is None:
+            hm.append(None)
+            continue
+        cov = np.stack([np.eye(2) * (k + 1) for k in range(s)])
+        hm.append(dict(prior=np.full(s, 1 / s), trans=np.full((s, s), 1 / s), mean=rng.normal(size=(s, 2)), cov=cov,
+                       varpar=dict(alpha=1 + rng.uniform(size=s), epsilon=1 + rng.uniform(size=(s, s)),
+                                   beta=1 + rng.uniform(size=s))))
+    b = h3m.hmms_to_h3m_hem(hm, "full", True, Nv=10.0)
+    assert list(b["Sb"]) == [2, 3, 1, 1] and b["prior"].shape == (4, 3)
+    assert b["Ntilde"][2] == 0.0 and np.isclose(b["Ntilde"].sum(), 40.0)       # dummy HMM has weight 0
+    a = hm[0]["varpar"]["alpha"]
+    from scipy.special import psi
+    np.testing.assert_allclose(b["prior"][0, :2], np.exp(psi(a) - psi(a.sum())))
+    assert (b["A"][0, :2, :2].sum(1) < 1).all()                                  # sub-stochastic on purpose
+    tb = (hm[1]["varpar"]["beta"] + 1) / hm[1]["varpar"]["beta"]
+    np.testing.assert_allclose(b["cov"][1, :3], tb[:, None, None] * hm[1]["cov"])
+
+
+@pytest.mark.gpu
+def test_em_run_matches_oracle_em():
+    from vbhem_b200.api import BaseSet
+    base, _ = synth.make_base_set(120, S=3, d=2, C=3, covmode="full", seed=77, Nv=OPT["Nv"])
+    hyp = synth.init_centres_baseem(base, 3, 3, seed=77, opt=dict(synth.DEFAULT_OPT, Nv=OPT["Nv"]))
+    want_hyp, want_L = oracle_em(base, hyp, OPT)
+    with BaseSet(base) as bs:
+        got = h3m.vbhem_h3m_c_step_fc(hyp, bs, OPT)
+    assert got["iters"] == len(want_L) and not got["unstable"]
+    np.testing.assert_allclose(got["LogLs"], want_L, rtol=1e-9)
+    assert np.all(np.diff(got["LogLs"]) > -1e-6 * np.abs(got["LogLs"][:-1]))     # EM: the bound does not decrease
+    for k in ("alpha", "eta", "epsilon", "lam", "v", "m", "W"):
+        np.testing.assert_allclose(got["hyp"][k], want_hyp[k], rtol=1e-7, atol=1e-9 * np.abs(want_hyp[k]).max(),
+                                   err_msg=k)
