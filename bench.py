@@ -146,6 +146,15 @@ def main():
     if a.cpu_worker:
         return cpu_worker(a.cpu_worker, K, S, d, tau, a.seed)
 
+    # The contract is ONE JSON line on stdout: keep the real stdout aside and send everything else that
+    # libraries print there (NCCL prints its version banner to stdout) to stderr.
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+    def emit(obj):
+        real_stdout.write(json.dumps(obj) + "\n")
+        real_stdout.flush()
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -175,7 +184,7 @@ def main():
                     cpu_baseline=dict(value=v, unit=UNIT, cores=vals[0]["cores"], kind=vals[0]["kind"],
                                       sample=vals[0]["sample"]),
                     e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-        print(json.dumps(line))
+        emit(line)
         return
 
     # ---- CPU baseline first (before CUDA is initialised in this process), rank 0, N = 1 only
@@ -365,8 +374,9 @@ def main():
             line["strong"] = strong
         if vbhem_iter is not None:
             line["vbhem_iter"] = vbhem_iter
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
 
 
