@@ -247,33 +247,43 @@ __global__ void k_zhat_reduce(int nblocks, int K, int ngroups, const double *Nj_
   }
 }
 
-// offs[blk][j]: exclusive prefix over blocks of cnt[.][j]; seg_start[j], chunk_start[j]
-// (K+1 entries each): exclusive prefix over centres; totals = {#active, #chunks}.
-__global__ void k_list_scan(int nblocks, int K, int chunk_len, const int *cnt, int *offs, int *seg_start,
-                            int *chunk_start, int *totals) {
-  extern __shared__ int segcnt[];
-  for (int j = threadIdx.x; j < K; j += blockDim.x) {
-    int run = 0;
-    for (int b = 0; b < nblocks; b++) {
-      offs[(size_t)b * K + j] = run;
-      run += cnt[(size_t)b * K + j];
+// offs[blk][j]: exclusive prefix over blocks of cnt[.][j] -- one warp per centre, 32 blocks per step;
+// segcnt[j]: the centre's total.
+__global__ void k_list_scan_blocks(int nblocks, int K, const int *cnt, int *offs, int *segcnt) {
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= K) return;
+  int run = 0;
+  for (int b0 = 0; b0 < nblocks; b0 += 32) {
+    const int b = b0 + lane;
+    const int v = b < nblocks ? cnt[(size_t)b * K + j] : 0;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
     }
-    segcnt[j] = run;
+    if (b < nblocks) offs[(size_t)b * K + j] = run + inc - v;
+    run += __shfl_sync(0xffffffffu, inc, 31);
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int a = 0, c = 0;
-    for (int j = 0; j < K; j++) {
-      seg_start[j] = a;
-      chunk_start[j] = c;
-      a += segcnt[j];
-      c += (segcnt[j] + chunk_len - 1) / chunk_len;
-    }
-    seg_start[K] = a;
-    chunk_start[K] = c;
-    totals[0] = a;
-    totals[1] = c;
+  if (lane == 0) segcnt[j] = run;
+}
+
+// seg_start[j], chunk_start[j] (K+1 entries each): exclusive prefix over centres; totals = {#active, #chunks}.
+__global__ void k_list_scan_centres(int K, int chunk_len, const int *segcnt, int *seg_start, int *chunk_start,
+                                    int *totals) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int a = 0, c = 0;
+  for (int j = 0; j < K; j++) {
+    seg_start[j] = a;
+    chunk_start[j] = c;
+    a += segcnt[j];
+    c += (segcnt[j] + chunk_len - 1) / chunk_len;
   }
+  seg_start[K] = a;
+  chunk_start[K] = c;
+  totals[0] = a;
+  totals[1] = c;
 }
 
 __global__ void __launch_bounds__(kZThreads)
@@ -459,11 +469,11 @@ int launch_zhat(int N, int K, int ngroups, const int *gstart, const double *L_el
   return 2;
 }
 
-int launch_list_scan(int N, int K, int chunk_len, const int *cnt, int *offs, int *seg_start, int *chunk_start,
-                     int *totals, cudaStream_t st) {
-  k_list_scan<<<1, 1024, sizeof(int) * K, st>>>(zhat_blocks(N), K, chunk_len, cnt, offs, seg_start, chunk_start,
-                                                totals);
-  return 1;
+int launch_list_scan(int N, int K, int chunk_len, const int *cnt, int *offs, int *segcnt, int *seg_start,
+                     int *chunk_start, int *totals, cudaStream_t st) {
+  k_list_scan_blocks<<<(K + 3) / 4, 128, 0, st>>>(zhat_blocks(N), K, cnt, offs, segcnt);
+  k_list_scan_centres<<<1, 32, 0, st>>>(K, chunk_len, segcnt, seg_start, chunk_start, totals);
+  return 2;
 }
 
 int launch_list_fill(int N, int K, int chunk_len, int nchunks, const double *zhat, const double *Ntilde,

@@ -280,14 +280,15 @@ int estep_device(vbhem_base *h, const CentreArgs &a, double *stats_dev, double *
   CU(h->lbp.ensure(sizeof(double) * (size_t)nb * 2 * a.ngroups));
   CU(h->cnt.ensure(sizeof(int) * (size_t)nb * K));
   CU(h->offs.ensure(sizeof(int) * (size_t)nb * K));
-  CU(h->segs.ensure(sizeof(int) * (size_t)(2 * (K + 1) + 2)));
+  CU(h->segs.ensure(sizeof(int) * (size_t)(3 * (K + 1) + 2)));
   StatsPtr S = carve_stats(stats_dev, K, r, d, dd, a.ngroups);
   launches += launch_zhat(N, K, a.ngroups, cd.gstart, h->L.as<double>(), cd.C.logOmega, h->B.Ntilde,
                           h->z.as<double>(), h->Njp.as<double>(), h->cnt.as<int>(), h->lbp.as<double>(), S.Nj, S.lb,
                           h->st);
   int *seg_start = h->segs.as<int>(), *chunk_start = seg_start + (K + 1), *totals = chunk_start + (K + 1);
-  launches += launch_list_scan(N, K, kChunkLen, h->cnt.as<int>(), h->offs.as<int>(), seg_start, chunk_start, totals,
-                               h->st);
+  int *segcnt = totals + 2;
+  launches += launch_list_scan(N, K, kChunkLen, h->cnt.as<int>(), h->offs.as<int>(), segcnt, seg_start, chunk_start,
+                               totals, h->st);
   CU(cudaMemcpyAsync(h->h_totals, totals, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
   CU(cudaStreamSynchronize(h->st));
   const int nact = h->h_totals[0], nch = h->h_totals[1];

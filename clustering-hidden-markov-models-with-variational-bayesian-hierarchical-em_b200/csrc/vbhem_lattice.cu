@@ -244,10 +244,10 @@ __device__ __forceinline__ double terminate(const Frag &G, const Frag &expPi, do
 // is a single dependent chain (shift -> exp -> DMMA -> log -> DMMA), so independent pairs are the
 // only instruction-level parallelism there is; every phase below is written across the NP pairs.
 #ifndef VB_BWD_WARPS
-#define VB_BWD_WARPS 8      // warps per CTA
+#define VB_BWD_WARPS 16     // warps per CTA (one 16-warp CTA per SM measured best: profiles/r01_sweep_occupancy.log)
 #endif
 #ifndef VB_BWD_MINB
-#define VB_BWD_MINB 2       // CTAs per SM the register budget is set for
+#define VB_BWD_MINB 1       // CTAs per SM the register budget is set for
 #endif
 #ifndef VB_NP
 #define VB_NP 2             // pairs in flight per warp
