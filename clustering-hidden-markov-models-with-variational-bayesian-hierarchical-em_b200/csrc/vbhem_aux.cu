@@ -122,9 +122,21 @@ __global__ void k_build_records(CentreView C, int d, int dd, double *rec) {
     else val = exp(logA[rho + ld * sg]);
     o[x] = val;
   }
+  for (int k = threadIdx.x; k < 8; k += blockDim.x) o[64 + k] = k < r ? exp(C.logPi[k + (size_t)ld * j]) : 0.0;
+  __syncthreads();
+  // The lattice kernel's sums are bounded below by these weights (vbhem_lattice.cu): a centre with a
+  // weight under 2^-900 (log weight < -623) gets a NaN emission constant, which sends its pairs to the
+  // general log-space kernel.
+  __shared__ int weak;
+  if (threadIdx.x == 0) weak = 0;
+  __syncthreads();
+  for (int x = threadIdx.x; x < 64 + 8; x += blockDim.x) {
+    const bool live = x < 64 ? (x / 8 < r && x % 8 < r) : (x - 64 < r);
+    if (live && !(o[x] >= 0x1p-900)) weak = 1;
+  }
+  __syncthreads();
   for (int k = threadIdx.x; k < 8; k += blockDim.x) {
-    o[64 + k] = k < r ? exp(C.logPi[k + (size_t)ld * j]) : 0.0;
-    o[72 + k] = k < r ? d * log(kTwoPi) + C.cterm[k + (size_t)ld * j] : INFINITY;
+    o[72 + k] = k < r ? (weak ? NAN : d * log(kTwoPi) + C.cterm[k + (size_t)ld * j]) : INFINITY;
     for (int q = 0; q < d; q++) o[80 + k * d + q] = k < r ? C.m[q + d * (k + (size_t)ld * j)] : 0.0;
     for (int q = 0; q < dd; q++) o[80 + 8 * d + k * dd + q] = k < r ? C.vW[q + dd * (k + (size_t)ld * j)] : 0.0;
   }

@@ -21,9 +21,12 @@
 //     lse[beta,rho] = c[beta] + log S[beta,rho]
 //     Theta[rho,sigma,beta] = expA[rho,sigma] * Bm[beta,sigma] / S[beta,rho]
 // which needs Sb*Sr exp + Sb*Sr log per step and is the same number up to
-// rounding whenever S does not underflow.  When it does (S < 1e-280, or
-// NaN/Inf in the data) the pair is flagged and redone by the general log-space
-// kernel, so every result the caller sees keeps the reference's semantics.
+// rounding whenever S does not underflow.  The shift never exists as a double:
+// exp_split() returns e^G as mantissa x 2^e and c[beta] is the integer maximum
+// of e over the row (vbhem_math.cuh), so S >= min expA > 0 by construction.
+// Pairs with NaN/Inf in the data, centre weights below 2^-900, or a row shift
+// outside +-1.5e9 binary orders are flagged and redone by the general
+// log-space kernel, so every result keeps the reference's semantics.
 // The forward pass (vbhem_hmm_bwd_fwd_mex.c:1100-1298) needs only Bm and 1/S of
 // each step (2 x 64 doubles instead of the 512-double Theta slice), kept in
 // shared memory and read back transposed.
@@ -32,8 +35,8 @@
 
 #include <type_traits>
 
-#ifndef VB_EXPERIMENT
-#define VB_EXPERIMENT 0
+#ifndef VB_SPLIT_ACC
+#define VB_SPLIT_ACC 0
 #endif
 
 namespace vbhem {
@@ -45,17 +48,33 @@ constexpr int kTile = 8 * kLd;    // doubles per tile
 
 struct Frag { double x0, x1; };
 
-// (invc, logc) pairs of log_pos(); copied to shared memory by every CTA (random per-lane index)
-// and the 2^(j/32) table of exp_nonpos_tab() behind it
+// (invc, logc) pairs of log_shift() and the 2^(j/BINS) table of exp_split().  Every CTA copies them to
+// shared memory: the per-lane index is random, so a plain table costs ~3 bank-conflict replays per
+// lookup.  The first-pass kernel therefore keeps one copy per bank group -- 16 interleaved copies of
+// the 8-byte exp table, 8 of the 16-byte log table -- and lane l reads copy l % 16 (l % 8): every
+// lookup is conflict-free (LDS.64 is served per half-warp, LDS.128 per quarter-warp).  The second-pass
+// kernel needs its shared memory for the stored lattice and keeps single copies.
 __device__ const double g_log_table[2 * VBHEM_LOG_BINS] = VBHEM_LOG_TABLE;
 __device__ const double g_exp_table[VBHEM_EXP_BINS] = VBHEM_EXP_TABLE;
-constexpr int kLogDoubles = 2 * VBHEM_LOG_BINS;
-constexpr int kTabDoubles = kLogDoubles + VBHEM_EXP_BINS;
-
-__device__ __forceinline__ void load_log_table(double *dst) {
-  for (int x = threadIdx.x; x < kLogDoubles; x += blockDim.x) dst[x] = g_log_table[x];
-  for (int x = threadIdx.x; x < VBHEM_EXP_BINS; x += blockDim.x) dst[kLogDoubles + x] = g_exp_table[x];
-}
+template <int LS, int ES>
+struct Tables {
+  static constexpr int kLogDoubles = 2 * VBHEM_LOG_BINS * LS;
+  static constexpr int kDoubles = kLogDoubles + VBHEM_EXP_BINS * ES;
+  static __device__ __forceinline__ void load(double *dst) {
+    for (int x = threadIdx.x; x < kLogDoubles; x += blockDim.x) {
+      const int e = x & 1, i = (x >> 1) / LS;                               // dst[(i * LS + copy) * 2 + e]
+      dst[x] = g_log_table[2 * i + e];
+    }
+    for (int x = threadIdx.x; x < VBHEM_EXP_BINS * ES; x += blockDim.x) dst[kLogDoubles + x] = g_exp_table[x / ES];
+  }
+  // the calling lane's views of the two tables
+  static __device__ __forceinline__ const double *log_view(const double *base, int lane) { return base + 2 * (lane % LS); }
+  static __device__ __forceinline__ const double *exp_view(const double *base, int lane) {
+    return base + kLogDoubles + (lane % ES);
+  }
+};
+using TabFirst = Tables<8, 16>;   // first pass: bank-replicated
+using TabFull = Tables<1, 1>;     // second pass: compact
 
 __device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -63,8 +82,11 @@ __device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b)
 }
 // D(m|n) = sum_c A[m][c] * X[n][c], all three in accumulator layout.
 __device__ __forceinline__ void mma_nt_acc(Frag &D, const Frag &A, const Frag &X) {
-#if VB_EXPERIMENT == 1 || VB_EXPERIMENT == 5 // timing experiment only: no tensor-core work
-  D.x0 = fma(A.x0, X.x0, D.x0) + 1.0; D.x1 = fma(A.x1, X.x1, D.x1) + 1.0;
+#if VB_SPLIT_ACC
+  Frag D2{0.0, 0.0};
+  dmma(D.x0, D.x1, A.x0, X.x0);
+  dmma(D2.x0, D2.x1, A.x1, X.x1);
+  D.x0 += D2.x0; D.x1 += D2.x1;
 #else
   dmma(D.x0, D.x1, A.x0, X.x0);
   dmma(D.x0, D.x1, A.x1, X.x1);
@@ -102,6 +124,7 @@ struct BaseConst {
   Frag Ab;        // Ab(beta' = g | beta = 2q+e)  = A[from g, to 2q+e]
   Frag AbT;       // [g][2q+e] = A[from 2q+e, to g]
   double prior;   // prior[g]
+  Frag priorT;    // prior[2q+e], the same in every row g
   double mu[D];   // centres of state g
   double cov[DD]; // covars of state g
   int Sb;
@@ -119,6 +142,8 @@ __device__ __forceinline__ void load_base(BaseConst<D, FULL> &b, const BaseView 
   b.AbT.x0 = (g < ld && c0 < ld) ? A[c0 + ld * g] : 0.0;
   b.AbT.x1 = (g < ld && c1 < ld) ? A[c1 + ld * g] : 0.0;
   b.prior = g < ld ? B.prior[g + (size_t)ld * i] : 0.0;
+  b.priorT.x0 = c0 < ld ? B.prior[c0 + (size_t)ld * i] : 0.0;
+  b.priorT.x1 = c1 < ld ? B.prior[c1 + (size_t)ld * i] : 0.0;
 #pragma unroll
   for (int k = 0; k < D; k++) b.mu[k] = g < ld ? B.mu[k + D * (g + (size_t)ld * i)] : 0.0;
 #pragma unroll
@@ -142,7 +167,7 @@ __device__ __forceinline__ void load_centre(CentreConst<D, FULL> &c, const doubl
   c.expPi = Frag{rec[64 + 2 * q], rec[64 + 2 * q + 1]};
 }
 
-// E(beta = g | sigma = 2q+e), vbhem_hmm_bwd_fwd_mex.c:796-843 (full) / :744-759 (diag).
+// E(beta = g | sigma = 2q+e) / u, vbhem_hmm_bwd_fwd_mex.c:796-843 (full) / :744-759 (diag).
 template <int D, bool FULL>
 __device__ __forceinline__ Frag emission(const BaseConst<D, FULL> &b, const double *rec, int g, int q) {
   constexpr int DD = BaseConst<D, FULL>::DD;
@@ -171,50 +196,58 @@ __device__ __forceinline__ Frag emission(const BaseConst<D, FULL> &b, const doub
         acc += P[k] * (df * df);
       }
     }
-    // padded base states: any finite row works (their weights are zero); 0 keeps S = rowsum(expA)
-    out[e] = (g < b.Sb) ? -0.5 * acc : (isinf(rec[72 + sg]) ? -INFINITY : 0.0);
+    // In lattice units (vbhem_math.cuh), clamped below at kUnitsFloor, which is also the value of an
+    // impossible (padded) centre state; NaN and +Inf pass through for pair_inputs_bad.  Padded base
+    // states: any finite row works (their weights are zero); 0 keeps S = rowsum(expA).
+    const double v = (-0.5 * kPerUnit) * acc;
+    out[e] = (g < b.Sb) ? (v < kUnitsFloor ? kUnitsFloor : v) : (isinf(rec[72 + sg]) ? kUnitsFloor : 0.0);
   }
   return Frag{out[0], out[1]};
 }
 
-// Shift of one lattice row: any number within a few hundred of the row maximum works, because the
-// same c enters exp(G - c) and c + log(sum).  The maximum is taken over an order-preserving int32
-// key of the high words (integer pipe, 32-bit shuffles); the shift differs from the true maximum by
-// at most 2^-20 of its magnitude.
-__device__ __forceinline__ int row_shift_key(const Frag &G) {
-  int m = max(order_key(G.x0), order_key(G.x1));
+// Shift of one lattice row = the largest binary exponent of e^G over the row (integer pipe, 32-bit
+// shuffles over the four lanes that hold the row).
+__device__ __forceinline__ int row_shift(int e0, int e1) {
+  int m = max(e0, e1);
   m = max(m, __shfl_xor_sync(0xffffffffu, m, 1));
   m = max(m, __shfl_xor_sync(0xffffffffu, m, 2));
   return m;
 }
 
 // The linear-domain recursion cannot create a NaN out of clean inputs (sums of non-negative
-// products, logs of range-checked sums), so NaN / Inf are screened once per pair, not per step:
-// the pair is bad if any transition / prior / centre weight is non-finite or an emission term is
-// NaN or +Inf.  Such pairs go to the general log-space kernel, which reproduces the reference.
+// products, logs of sums that are bounded below by a centre weight), so the inputs are screened once
+// per pair, not per step: the pair is bad if a transition / prior / centre weight is non-finite, the
+// base transition rows sum (in magnitude) to more than 1.001 (growth bound of the recursion), or an
+// emission term is NaN, +Inf or above 2^35 units (9e7).  k_build_records poisons the emission constant of a
+// centre whose weights are below 2^-900, which lands here as a NaN.  Such pairs go to the general
+// log-space kernel, which reproduces the reference.
+__device__ __forceinline__ double base_check(const Frag &Ab, double prior) {
+  const double rs = quad_sum(fabs(Ab.x0) + fabs(Ab.x1));
+  return (rs <= 1.001 ? 0.0 : INFINITY) + prior;          // NaN / Inf anywhere => non-finite
+}
 __device__ __forceinline__ bool pair_inputs_bad(double base_chk, const Frag &expA, const Frag &expPi,
                                                 const Frag &E) {
   const double chk = base_chk + ((expA.x0 + expA.x1) + (expPi.x0 + expPi.x1));
-  return nonfinite(chk) | nan_or_posinf(E.x0) | nan_or_posinf(E.x1);
+  return nonfinite(chk) | nan_or_large(E.x0) | nan_or_large(E.x1);
 }
 
 // One backward step (t = T-1 .. 1).  In: G(beta|sigma) = E + L of this step.  Out: G of the
 // previous time step, G(beta'|rho) = E + sum_beta Ab[beta',beta] lse[beta,rho].  With STORE the
 // step's Bm(beta|sigma) and 1/S^T(rho|beta) go to shared memory for the forward pass.  `rng`
-// accumulates the range excess of the step's sums (see range_excess).
+// accumulates the excess of the step's row shifts (see shift_excess).
 template <bool STORE>
 __device__ __forceinline__ void bwd_step(const Frag &E, Frag &G, const Frag &expA, const Frag &Ab,
-                                         const double *ltab, double *sBm, double *sInvS, unsigned &rng, int g,
-                                         int q) {
-  const double *etab = ltab + kLogDoubles;
-  const int key = row_shift_key(G);
-  const double c = key_to_double(key);                         // c[beta = g]
-  const Frag Bm{exp_nonpos_tab(G.x0 - c, etab), exp_nonpos_tab(G.x1 - c, etab)};
+                                         const double *ltab, const double *etab, double *sBm, double *sInvS,
+                                         unsigned &rng, int g, int q) {
+  int e0, e1;
+  const double m0 = exp_split(G.x0, etab, e0), m1 = exp_split(G.x1, etab, e1);
+  const int c = row_shift(e0, e1);                             // shift of row beta = g
+  rng = max(rng, shift_excess(c));
+  const Frag Bm{exp_scale(m0, e0 - c), exp_scale(m1, e1 - c)};
   const Frag ST = mma_nt(expA, Bm);                            // S^T(rho = g | beta = 2q+e)
-  rng = max(rng, max(range_excess(ST.x0), range_excess(ST.x1)));
-  const double cb0 = key_to_double(__shfl_sync(0xffffffffu, key, (2 * q) * 4));
-  const double cb1 = key_to_double(__shfl_sync(0xffffffffu, key, (2 * q + 1) * 4));
-  const Frag ell{log_pos_plus(ST.x0, ltab, cb0), log_pos_plus(ST.x1, ltab, cb1)};   // lse^T(rho | beta)
+  const int cb0 = __shfl_sync(0xffffffffu, c - 1023, (2 * q) * 4);
+  const int cb1 = __shfl_sync(0xffffffffu, c - 1023, (2 * q + 1) * 4);
+  const Frag ell{log_shift_biased(ST.x0, ltab, cb0), log_shift_biased(ST.x1, ltab, cb1)};   // lse^T(rho | beta)
   G = E;
   mma_nt_acc(G, Ab, ell);                                      // G(beta' = g | rho = 2q+e)
   if (STORE) {
@@ -225,15 +258,17 @@ __device__ __forceinline__ void bwd_step(const Frag &E, Frag &G, const Frag &exp
 
 // Termination (vbhem_hmm_bwd_fwd_mex.c:1029-1080).  Returns L_elbo (all lanes) and
 // nu_1(beta = g | sigma = 2q+e) = prior * Theta_1.
+template <int LS, int ES>
 __device__ __forceinline__ double terminate(const Frag &G, const Frag &expPi, double prior, const double *ltab,
-                                            int q, Frag &nu1, unsigned &rng) {
-  const double *etab = ltab + kLogDoubles;
-  const double c = key_to_double(row_shift_key(G));
-  const Frag Bm{exp_nonpos_tab(G.x0 - c, etab), exp_nonpos_tab(G.x1 - c, etab)};
+                                            const double *etab, int q, Frag &nu1, unsigned &rng) {
+  int e0, e1;
+  const double m0 = exp_split<ES>(G.x0, etab, e0), m1 = exp_split<ES>(G.x1, etab, e1);
+  const int c = row_shift(e0, e1);
+  rng = max(rng, shift_excess(c));
+  const Frag Bm{exp_scale(m0, e0 - c), exp_scale(m1, e1 - c)};
   const double s = quad_sum(expPi.x0 * Bm.x0 + expPi.x1 * Bm.x1);
-  rng = max(rng, range_excess(s));
-  const double ell = log_pos_plus(s, ltab, c);
-  const double Lq = across_sum(q == 0 ? prior * ell : 0.0);    // valid in lanes with q == 0
+  const double ell = log_shift<LS>(s, ltab, c);
+  const double Lq = across_sum(q == 0 ? (prior * kUnit) * ell : 0.0);    // valid in lanes with q == 0
   const double w = prior / s;
   nu1 = Frag{w * expPi.x0 * Bm.x0, w * expPi.x1 * Bm.x1};
   return __shfl_sync(0xffffffffu, Lq, 0);
@@ -252,38 +287,78 @@ __device__ __forceinline__ double terminate(const Frag &G, const Frag &expPi, do
 #ifndef VB_NP
 #define VB_NP 2             // pairs in flight per warp
 #endif
+#ifndef VB_TERM_STEP
+#define VB_TERM_STEP 0
+#endif
 #ifndef VB_KC_BYTES
 #define VB_KC_BYTES (64 * 1024)   // shared-memory budget for centre records per CTA
 #endif
 constexpr int kBwdWarps = VB_BWD_WARPS;
 constexpr int kNP = VB_NP;
 
-template <int NP>
+template <int NP, int LS, int ES>
 __device__ __forceinline__ void bwd_step_n(const Frag (&E)[NP], Frag (&G)[NP], const Frag (&expA)[NP],
-                                           const Frag &Ab, const double *ltab, unsigned (&rng)[NP], int q) {
-  const double *etab = ltab + kLogDoubles;
-  int key[NP];
+                                           const Frag &Ab, const double *ltab, const double *etab,
+                                           unsigned (&rng)[NP], int q) {
+  int e0[NP], e1[NP], c[NP];
   Frag Bm[NP], ST[NP], ell[NP];
 #pragma unroll
-  for (int p = 0; p < NP; p++) key[p] = row_shift_key(G[p]);
+  for (int p = 0; p < NP; p++) {
+    Bm[p].x0 = exp_split<ES>(G[p].x0, etab, e0[p]);
+    Bm[p].x1 = exp_split<ES>(G[p].x1, etab, e1[p]);
+  }
+#pragma unroll
+  for (int p = 0; p < NP; p++) c[p] = row_shift(e0[p], e1[p]);
 #pragma unroll
   for (int p = 0; p < NP; p++) {
-    const double c = key_to_double(key[p]);
-    Bm[p] = Frag{exp_nonpos_tab(G[p].x0 - c, etab), exp_nonpos_tab(G[p].x1 - c, etab)};
+    rng[p] = max(rng[p], shift_excess(c[p]));
+    Bm[p] = Frag{exp_scale(Bm[p].x0, e0[p] - c[p]), exp_scale(Bm[p].x1, e1[p] - c[p])};
   }
 #pragma unroll
   for (int p = 0; p < NP; p++) ST[p] = mma_nt(expA[p], Bm[p]);
 #pragma unroll
   for (int p = 0; p < NP; p++) {
-    rng[p] = max(rng[p], max(range_excess(ST[p].x0), range_excess(ST[p].x1)));
-    const double cb0 = key_to_double(__shfl_sync(0xffffffffu, key[p], (2 * q) * 4));
-    const double cb1 = key_to_double(__shfl_sync(0xffffffffu, key[p], (2 * q + 1) * 4));
-    ell[p] = Frag{log_pos_plus(ST[p].x0, ltab, cb0), log_pos_plus(ST[p].x1, ltab, cb1)};
+    const int cb0 = __shfl_sync(0xffffffffu, c[p] - 1023, (2 * q) * 4);
+    const int cb1 = __shfl_sync(0xffffffffu, c[p] - 1023, (2 * q + 1) * 4);
+    ell[p] = Frag{log_shift_biased<LS>(ST[p].x0, ltab, cb0), log_shift_biased<LS>(ST[p].x1, ltab, cb1)};
   }
 #pragma unroll
   for (int p = 0; p < NP; p++) {
     G[p] = E[p];
     mma_nt_acc(G[p], Ab, ell[p]);
+  }
+}
+
+// Termination of NP pairs side by side (first pass: L_elbo only, valid in lane 0).
+template <int NP, int LS, int ES>
+__device__ __forceinline__ void terminate_n(const Frag (&G)[NP], const Frag (&expPi)[NP], double prior,
+                                            const double *ltab, const double *etab, int q, unsigned (&rng)[NP],
+                                            double (&L)[NP]) {
+  int e0[NP], e1[NP], c[NP];
+  double m0[NP], m1[NP], s[NP];
+#pragma unroll
+  for (int p = 0; p < NP; p++) {
+    m0[p] = exp_split<ES>(G[p].x0, etab, e0[p]);
+    m1[p] = exp_split<ES>(G[p].x1, etab, e1[p]);
+  }
+#pragma unroll
+  for (int p = 0; p < NP; p++) c[p] = row_shift(e0[p], e1[p]);
+#pragma unroll
+  for (int p = 0; p < NP; p++) {
+    rng[p] = max(rng[p], shift_excess(c[p]));
+    s[p] = expPi[p].x0 * exp_scale(m0[p], e0[p] - c[p]) + expPi[p].x1 * exp_scale(m1[p], e1[p] - c[p]);
+  }
+#pragma unroll
+  for (int p = 0; p < NP; p++) s[p] += __shfl_xor_sync(0xffffffffu, s[p], 1);
+#pragma unroll
+  for (int p = 0; p < NP; p++) s[p] += __shfl_xor_sync(0xffffffffu, s[p], 2);
+  const double pu = prior * kUnit;
+#pragma unroll
+  for (int p = 0; p < NP; p++) L[p] = q == 0 ? pu * log_shift<LS>(s[p], ltab, c[p]) : 0.0;
+#pragma unroll
+  for (int o = 4; o < 32; o <<= 1) {
+#pragma unroll
+    for (int p = 0; p < NP; p++) L[p] += __shfl_xor_sync(0xffffffffu, L[p], o);
   }
 }
 
@@ -296,18 +371,18 @@ k_lattice_bwd(BaseView B, CentreView C, int T, int kc, double *L_elbo, Fallback 
   const int j0 = blockIdx.y * kc;
   const int nj = min(kc, C.K - j0);
   const int rs = C.rec_stride;
-  const double *ltab = smem;
-  double *recs = smem + kTabDoubles;
-  load_log_table(smem);
+  const double *ltab = TabFirst::log_view(smem, lane), *etab = TabFirst::exp_view(smem, lane);
+  double *recs = smem + TabFirst::kDoubles;
+  TabFirst::load(smem);
   for (int x = threadIdx.x; x < nj * rs; x += blockDim.x) recs[x] = C.rec[(size_t)j0 * rs + x];
   __syncthreads();
 
   for (int i = blockIdx.x * kBwdWarps + warp; i < B.N; i += gridDim.x * kBwdWarps) {
     BaseConst<D, FULL> b;
     load_base(b, B, i, g, q);
-    const double base_chk = (b.Ab.x0 + b.Ab.x1) + b.prior;
+    const double base_chk = base_check(b.Ab, b.prior);
     for (int jj = 0; jj < nj; jj += kNP) {
-      Frag E[kNP], G[kNP], expA[kNP], expPi[kNP];
+      Frag E[kNP], G[kNP], expA[kNP], expPi[kNP], Z[kNP];
       unsigned rng[kNP];
       bool bad[kNP];
 #pragma unroll
@@ -319,15 +394,29 @@ k_lattice_bwd(BaseView B, CentreView C, int T, int kc, double *L_elbo, Fallback 
         expPi[p] = c.expPi;
         E[p] = emission(b, rec, g, q);
         G[p] = E[p];
+        Z[p] = Frag{0.0, 0.0};
         rng[p] = 0u;
         bad[p] = pair_inputs_bad(base_chk, expA[p], expPi[p], E[p]);
       }
-      for (int t = T - 1; t >= 1; t--) bwd_step_n<kNP>(E, G, expA, b.Ab, ltab, rng, q);
+      for (int t = T - 1; t >= 1; t--) bwd_step_n<kNP, 8, 16>(E, G, expA, b.Ab, ltab, etab, rng, q);
+      // Termination (vbhem_hmm_bwd_fwd_mex.c:1029-1080) is one more step of the same shape with
+      // logPi in place of every row of logA and the prior in place of every row of A_b:
+      //   S(rho|beta) = sum_sigma expPi[sigma] Bm[beta,sigma]   (the same for every rho)
+      //   G(beta'|rho) = sum_beta prior[beta] lse[beta]          = L_elbo in every element
+#if VB_TERM_STEP
+      bwd_step_n<kNP, 8, 16>(Z, G, expPi, b.priorT, ltab, etab, rng, q);
+#else
+      double Lt[kNP];
+      terminate_n<kNP, 8, 16>(G, expPi, b.prior, ltab, etab, q, rng, Lt);
+#endif
 #pragma unroll
       for (int p = 0; p < kNP; p++) {
-        Frag nu1;
-        const double Le = terminate(G[p], expPi[p], b.prior, ltab, q, nu1, rng[p]);
-        const bool good = __all_sync(0xffffffffu, (rng[p] < kRangeBound) & !bad[p]);
+#if VB_TERM_STEP
+        const double Le = G[p].x0 * kUnit;
+#else
+        const double Le = Lt[p];
+#endif
+        const bool good = __all_sync(0xffffffffu, (rng[p] <= kShiftBound) & !bad[p]);
         if (lane == 0 && jj + p < nj) {
           const size_t pi = (size_t)i + (size_t)B.N * (j0 + jj + p);
           L_elbo[pi] = Le;
@@ -350,21 +439,21 @@ struct PairStats {
 template <int D, bool FULL>
 __device__ __forceinline__ bool pair_full(const BaseView &B, int i, const BaseConst<D, FULL> &b,
                                           const CentreConst<D, FULL> &c, const double *rec, int T,
-                                          const double *ltab, double *sm, int g, int q, double &Lout,
+                                          const double *ltab, const double *etab, double *sm, int g, int q, double &Lout,
                                           PairStats<D, FULL> &st) {
   constexpr int DD = BaseConst<D, FULL>::DD;
   double *xch = sm + (size_t)2 * kTile * (T - 1);
   const Frag E = emission(b, rec, g, q);
   Frag G = E;
   unsigned rng = 0u;
-  const bool bad = pair_inputs_bad((b.Ab.x0 + b.Ab.x1) + b.prior, c.expA, c.expPi, E);
+  const bool bad = pair_inputs_bad(base_check(b.Ab, b.prior), c.expA, c.expPi, E);
   for (int t = T - 1; t >= 1; t--) {
     double *s = sm + (size_t)2 * kTile * (t - 1);
-    bwd_step<true>(E, G, c.expA, b.Ab, ltab, s, s + kTile, rng, g, q);
+    bwd_step<true>(E, G, c.expA, b.Ab, ltab, etab, s, s + kTile, rng, g, q);
   }
   Frag nu1;
-  Lout = terminate(G, c.expPi, b.prior, ltab, q, nu1, rng);
-  if (!__all_sync(0xffffffffu, (rng < kRangeBound) & !bad)) return false;
+  Lout = terminate<1, 1>(G, c.expPi, b.prior, ltab, etab, q, nu1, rng);
+  if (!__all_sync(0xffffffffu, (rng <= kShiftBound) & !bad)) return false;
 
   // nu_1 (beta|sigma) -> nuT (sigma = g | gamma = 2q+e)
   tile_store(xch, g, q, nu1);
@@ -423,10 +512,10 @@ k_lattice_full(BaseView B, CentreView C, int T, PairWork W, PairOut O, Fallback 
   constexpr int DD = BaseConst<D, FULL>::DD;
   const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
   const int warp = threadIdx.x >> 5;
-  const double *ltab = smem;
-  load_log_table(smem);
+  const double *ltab = smem, *etab = smem + TabFull::kLogDoubles;
+  TabFull::load(smem);
   __syncthreads();
-  double *sm = smem + kTabDoubles + (size_t)warp * ((size_t)2 * kTile * (T - 1) + kTile);
+  double *sm = smem + TabFull::kDoubles + (size_t)warp * ((size_t)2 * kTile * (T - 1) + kTile);
   const long long gw = (long long)blockIdx.x * warps_per_block + warp;
   const long long nw = (long long)gridDim.x * warps_per_block;
   const int ro = C.maxSr;
@@ -442,7 +531,7 @@ k_lattice_full(BaseView B, CentreView C, int T, PairWork W, PairOut O, Fallback 
       load_centre(c, rec, g, q);
       PairStats<D, FULL> st;
       double Le;
-      const bool ok = pair_full(B, i, b, c, rec, T, ltab, sm, g, q, Le, st);
+      const bool ok = pair_full(B, i, b, c, rec, T, ltab, etab, sm, g, q, Le, st);
       if (!ok) {
         if (lane == 0) { fb.flags[p] = 1; atomicAdd(fb.count, 1); }
         continue;
@@ -484,7 +573,7 @@ k_lattice_full(BaseView B, CentreView C, int T, PairWork W, PairOut O, Fallback 
       load_base(b, B, it.i, g, q);
       PairStats<D, FULL> st;
       double Le;
-      const bool ok = pair_full(B, it.i, b, c, rec, T, ltab, sm, g, q, Le, st);
+      const bool ok = pair_full(B, it.i, b, c, rec, T, ltab, etab, sm, g, q, Le, st);
       if (!ok) {
         if (lane == 0) { fb.flags[cr.x + e] = 1; atomicAdd(fb.count, 1); }
         continue;
@@ -558,7 +647,7 @@ int launch_lattice_bwd(const BaseView &B, const CentreView &C, int T, double *L_
   const int rs = C.rec_stride;
   int kc = (int)((VB_KC_BYTES) / (sizeof(double) * rs));
   if (kc > C.K) kc = C.K;
-  const size_t smem = sizeof(double) * ((size_t)kc * rs + kTabDoubles);
+  const size_t smem = sizeof(double) * ((size_t)kc * rs + TabFirst::kDoubles);
   const int ny = (C.K + kc - 1) / kc;
   int nx = (B.N + kBwdWarps - 1) / kBwdWarps;
   const int cap = VB_BWD_MINB * sm_count();
@@ -582,7 +671,7 @@ int launch_lattice_full(const BaseView &B, const CentreView &C, int T, const Pai
   long long blocks = (units + wpb - 1) / wpb;
   const long long cap = sm_count();
   if (blocks > cap) blocks = cap;
-  const size_t smem = pw * wpb + sizeof(double) * kTabDoubles;
+  const size_t smem = pw * wpb + sizeof(double) * TabFull::kDoubles;
   return dispatch(B.d, B.covmode, [&](auto Dc, auto Fc) {
     auto kern = k_lattice_full<decltype(Dc)::value, decltype(Fc)::value>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -1,15 +1,34 @@
-// vbhem_math.cuh -- lean fp64 exp / log / reciprocal for the lattice kernels.
+// vbhem_math.cuh -- lean fp64 exp / log for the lattice kernels.
 //
-// The E-step is bound by the fp64 pipe and libdevice's exp / log cost 19 / 47 DFMA-equivalents
-// per call on B200 (profiles/r01_fp64_peaks.json), most of it argument-range and special-case
-// handling these call sites never need:
-//   exp_nonpos(x): x = G - max(G) is <= 0 (up to the float rounding of the shift) or -inf
-//   log_pos(s)   : s is a sum of non-negative products, already checked >= 1e-280
-// NaN / +Inf never reach them un-flagged: the caller tests every step's inputs and sends such
-// pairs to the general log-space kernel.  Constants: csrc/gen_mathtab.py -> vbhem_mathtab.h.
-// The same code compiles for the host (g++) so tests/test_math.py can check it against libm.
+// The E-step is bound by the fp64 pipe AND by register-file read bandwidth (a DFMA with three
+// distinct register operands issues every 3 cycles, not 2: profiles/r02_pipe_overlap.json), and
+// libdevice's exp / log cost 19 / 47 DFMA-equivalents per call on B200
+// (profiles/r01_fp64_peaks.json), most of it range and special-case handling these call sites never
+// need.  Two ideas remove nearly all of that:
+//
+//  1. UNITS.  Every log-domain quantity of the lattice (emission terms, lse, L, G) is kept in units
+//     of u = ln2 / BINS:  y = x / u.  Then the argument reduction of e^x is exact and free of
+//     constants: k = rint(y), r = y - k, e^x = 2^(k / BINS) e^(r u).  The tables and polynomial
+//     coefficients absorb u (csrc/gen_mathtab.py); the kernels convert once on the way in (the
+//     emission term) and once on the way out (L_elbo).
+//  2. INTEGER SHIFT.  A lattice row needs lse_sigma(G) = c + log sum_sigma w exp(G - c) for ANY c
+//     near the row maximum, so no floating-point maximum is ever taken:
+//       exp_split(y)    -> (mant, e) with e^(y u) = mant 2^e, mant in [1, 2)     8 fp64 instructions
+//       row shift       =  integer max of e over the row (32-bit shuffles)
+//       exp_scale()     -> mant 2^(e - c): two integer instructions on the high word
+//       log_shift(s, c) =  ((c + exponent(s)) ln2 + log(mantissa(s))) / u         7 fp64 instructions + I2F
+//
+// Domain: exp_split takes |y| < 2^39 (no clamp inside: the kernels clamp the emission terms
+// once per pair and the recursion cannot leave the range while its row shifts stay in
+// [-2^27, 1.5e9] binary orders, which shift_excess() tracks; pairs outside go to the general
+// log-space kernel).  NaN / +Inf never reach these functions un-flagged (pair_inputs_bad in
+// vbhem_lattice.cu).  The same code compiles for the host (g++) so that tests/test_math.py can check
+// it against libm.
 #pragma once
-#include "vbhem_mathtab.h"
+#ifndef VBHEM_MATHTAB
+#define VBHEM_MATHTAB "vbhem_mathtab.h"
+#endif
+#include VBHEM_MATHTAB
 
 #ifdef __CUDACC__
 #define VB_HD __host__ __device__ __forceinline__
@@ -22,17 +41,24 @@
 
 namespace vbhem {
 
-// Polynomial / reduction constants.  On the device they live in constant memory so that DFMA reads
-// them as c[bank][offset] operands; as literals ptxas re-materialises each one with two moves per use.
-#define VB_MATH_CONSTS { 1.0 / 120, 1.0 / 24, 1.0 / 6, /*3*/ VBHEM_EXP_SCALE, -VBHEM_EXP_STEP_HI, \
-                         -VBHEM_EXP_STEP_LO, 6755399441055744.0, /*7*/ 0.2, 1.0 / 3, /*9*/ 0.69314718055994530942 }
+constexpr double kUnit = VBHEM_UNIT;          // u: natural-log value of one lattice unit
+constexpr double kPerUnit = VBHEM_PER_UNIT;   // 1 / u
+// Emission terms are clamped to >= kUnitsFloor once per pair (also the value of padded / impossible
+// states); rows whose shift falls below -2^27 orders (= -2^35 units) are not trusted.
+constexpr double kUnitsFloor = -68719476736.0;          // -2^36 units (~ -1.9e8 natural)
+constexpr double kUnitsCeil = 34359738368.0;            //  2^35 units (~  9.3e7 natural)
+
+// Polynomial constants.  On the device they live in constant memory so that DFMA reads them as
+// c[bank][offset] operands (no register-file bandwidth); as literals ptxas re-materialises each one
+// with two moves per use.   [0..4] exp: u^n/n!;  [5..9] log: (-1)^(n+1)/(n u);  [10] 1.5 * 2^52
+#define VB_MATH_CONSTS { VBHEM_EXP_COEF, VBHEM_LOG_COEF, 6755399441055744.0 }
 #ifdef __CUDACC__
-__constant__ double g_mc[10] = VB_MATH_CONSTS;
+__constant__ double g_mc[11] = VB_MATH_CONSTS;
 #endif
 #ifdef __CUDA_ARCH__
 #define VB_MC(i) g_mc[i]
 #else
-static const double h_mc[10] = VB_MATH_CONSTS;
+static const double h_mc[11] = VB_MATH_CONSTS;
 #define VB_MC(i) h_mc[i]
 #endif
 
@@ -57,75 +83,85 @@ VB_HD double make_double(int hi, int lo) {
   uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo; double x; memcpy(&x, &u, 8); return x;
 #endif
 }
-
-// e^x for x <~ 0 (or -inf) with a VBHEM_EXP_BINS-entry table of 2^(j/BINS) (etab): 10 fp64
-// instructions.  x = k (ln2/BINS) + r;  e^x = 2^(k >> SHIFT) * T[k & (BINS-1)] * (1 + r + ... + r^5/120).
-// Below -708.5 it returns ~1e-308 instead of the reference's denormal / zero: the value only ever
-// enters sums whose largest term is ~1.  NaN inputs are the caller's business (see pair_inputs_bad).
-VB_HD double exp_nonpos_tab(double xin, const double *etab) {
-#if defined(VB_EXPERIMENT) && (VB_EXPERIMENT == 2 || VB_EXPERIMENT == 3 || VB_EXPERIMENT == 5)   // timing experiment only
-  return fma(xin, 1e-9, 1.0) + etab[0];
+// low 32 bits of (hi:lo) >> s, 0 < s < 32
+VB_HD int funnel_right(int lo, int hi, int s) {
+#ifdef __CUDA_ARCH__
+  return (int)__funnelshift_r((unsigned)lo, (unsigned)hi, s);
+#else
+  return (int)((((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo) >> s);
 #endif
-  // clamp at about -708.5 with one unsigned min on the high word (negative doubles order by magnitude
-  // there; -inf and anything below the clamp become ~1e-308, i.e. nothing next to a row maximum of 1)
-  const unsigned hx = (unsigned)hi_word(xin);
-  const double x = make_double((int)(hx < 0xC0862400u ? hx : 0xC0862400u), lo_word(xin));
-  const double t = fma(x, VB_MC(3), VB_MC(6));             // BINS x / ln2 + 1.5 * 2^52
-  const int k = lo_word(t);                                // rint(BINS x / ln2)
-  const double kf = t - VB_MC(6);
-  double r = fma(kf, VB_MC(4), x);
-  r = fma(kf, VB_MC(5), r);
-  const double T = etab[k & (VBHEM_EXP_BINS - 1)];
-  double q = fma(r, VB_MC(0), VB_MC(1));
-  q = fma(q, r, VB_MC(2));
-  q = fma(q, r, 0.5);
-  q = fma(q, r, 1.0);
-  const double e = fma(T * r, q, T);                       // T * e^r
-  return make_double(hi_word(e) + ((k >> VBHEM_EXP_SHIFT) << 20), lo_word(e));
 }
 
-// Range tracking on the integer pipe: a lattice sum s is trusted iff 2^-930 <= s < inf.
-// range_excess(s) is < kRangeBound exactly then (NaN, Inf, negatives, zero and tiny values all map to
-// large unsigned numbers), so one running unsigned max per pair replaces per-step fp64 compares.
-constexpr unsigned kRangeBound = 0x7FF00000u - 0x05D00000u;
-VB_HD unsigned range_excess(double s) { return (unsigned)(hi_word(s) - 0x05D00000); }
+// e^(y u) = mant * 2^e with mant in [1 - 2^-9, 2).  k = rint(y) is read off the low bits of
+// y + 1.5 2^52 (k may have up to 42 bits: e is taken from both words), r = y - k exactly, e^(r u) by
+// its Taylor polynomial.  ES = stride of the table in doubles (the first-pass kernel keeps one copy
+// per shared-memory bank pair).
+template <int ES = 1>
+VB_HD double exp_split(double y, const double *etab, int &e) {
+  const double t = y + VB_MC(10);
+  const double r = y - (t - VB_MC(10));
+  e = funnel_right(lo_word(t), hi_word(t), VBHEM_EXP_SHIFT);   // k >> SHIFT
+  const double T = etab[(lo_word(t) & (VBHEM_EXP_BINS - 1)) * ES];
+#if VBHEM_EXP_DEG == 3
+  double q = fma(r, VB_MC(2), VB_MC(1));
+#elif VBHEM_EXP_DEG == 4
+  double q = fma(r, VB_MC(3), VB_MC(2));
+  q = fma(q, r, VB_MC(1));
+#else
+  double q = fma(r, VB_MC(4), VB_MC(3));
+  q = fma(q, r, VB_MC(2));
+  q = fma(q, r, VB_MC(1));
+#endif
+  q = fma(q, r, VB_MC(0));
+  return fma(T * r, q, T);                                 // T * e^(r u)
+}
 
-// true for NaN and +Inf (-Inf is a legitimate "impossible state" value of an emission term)
-VB_HD bool nan_or_posinf(double x) {
-  const int h = hi_word(x);
-  return (h >= 0x7ff00000) | ((unsigned)h > 0xfff00000u) | (((unsigned)h == 0xfff00000u) & (lo_word(x) != 0));
+// mant * 2^de for de <= 0 (clamped at -1000: ~1e-301, nothing next to the row maximum's [1, 2)).
+VB_HD double exp_scale(double mant, int de) {
+  const int d = de > -1000 ? de : -1000;
+  return make_double(hi_word(mant) + (int)((unsigned)d << 20), lo_word(mant));
+}
+
+// Validity of a row shift c (binary orders): trusted iff -2^27 <= c <= 1.5e9.  shift_excess(c) is
+// <= kShiftBound exactly then, so one running unsigned max per pair covers every row of every step.
+constexpr unsigned kShiftBound = 1500000000u + 134217728u;
+VB_HD unsigned shift_excess(int c) { return (unsigned)c + 134217728u; }
+
+// true for NaN, +Inf and anything above kUnitsCeil = 2^35 (-Inf is a legitimate "impossible state" term)
+VB_HD bool nan_or_large(double y) {
+  const int h = hi_word(y);
+  return (h >= 0x42200000) | ((unsigned)h > 0xfff00000u) | (((unsigned)h == 0xfff00000u) & (lo_word(y) != 0));
 }
 // true for NaN and +-Inf
 VB_HD bool nonfinite(double x) { return ((unsigned)hi_word(x) & 0x7ff00000u) == 0x7ff00000u; }
 
-// Order-preserving map double -> int32 that looks at the high word only, and its inverse.
-VB_HD int order_key(double x) {
-  const int h = hi_word(x);
-  return h ^ ((h >> 31) & 0x7fffffff);
-}
-VB_HD double key_to_double(int key) { return make_double(key ^ ((key >> 31) & 0x7fffffff), 0); }
-
-// add + log(s) for normal positive s, 8 fp64 instructions.  tab = VBHEM_LOG_TABLE as (invc, logc)
-// pairs: s = 2^e m, r = m invc - 1 (|r| < 2^-8.9), log s = e ln2 + logc + (r - r^2/2 + ... + r^5/5).
-// Absolute error <= ~4e-16 + |e| 2.4e-17 (ln2 is a single double: the result is always added to a
-// lattice shift of magnitude >> 1, so absolute accuracy is what matters).
-VB_HD double log_pos_plus(double s, const double *tab, double add) {
-#if defined(VB_EXPERIMENT) && (VB_EXPERIMENT == 2 || VB_EXPERIMENT == 4 || VB_EXPERIMENT == 5)   // timing experiment only
-  return fma(s, 1e-9, add) + tab[0];
-#endif
+// (c ln2 + log s) / u for normal positive s; cb = c - 1023.  tab = VBHEM_LOG_TABLE as (invc, logc/u)
+// pairs: s = 2^e m, r = m invc - 1, log s = e ln2 + logc + log1p(r); in units, e ln2 / u = e BINS
+// exactly.  LS = stride of the table in pairs.  Error <= ~1e-13 units = 3e-16 natural.
+template <int LS = 1>
+VB_HD double log_shift_biased(double s, const double *tab, int cb) {
   const int hi = hi_word(s);
-  const int e = (hi >> 20) - 1023;
-  const int i = (hi >> VBHEM_LOG_SHIFT) & (VBHEM_LOG_BINS - 1);
+  const int e = (hi >> 20) + cb;
+  const int i = (hi >> (20 - VBHEM_LOG_BITS)) & (VBHEM_LOG_BINS - 1);
   const double m = make_double((hi & 0x000fffff) | 0x3ff00000, lo_word(s));
-  const double invc = tab[2 * i], logc = tab[2 * i + 1];
+#ifdef __CUDA_ARCH__
+  const double2 tl = *reinterpret_cast<const double2 *>(tab + 2 * LS * i);   // 16-byte aligned by construction
+  const double invc = tl.x, logc = tl.y;
+#else
+  const double invc = tab[2 * LS * i], logc = tab[2 * LS * i + 1];
+#endif
   const double r = fma(m, invc, -1.0);
-  const double r2 = r * r;
-  double q = fma(r, VB_MC(7), -0.25);
-  q = fma(q, r, VB_MC(8));
-  q = fma(q, r, -0.5);
-  const double p = fma(r2, q, r);
-  return fma((double)e, VB_MC(9), add) + (logc + p);
+#if VBHEM_LOG_DEG == 4
+  double q = fma(r, VB_MC(8), VB_MC(7));
+#else
+  double q = fma(r, VB_MC(9), VB_MC(8));
+  q = fma(q, r, VB_MC(7));
+#endif
+  q = fma(q, r, VB_MC(6));
+  q = fma(q, r, VB_MC(5));
+  return fma((double)e, (double)VBHEM_EXP_BINS, fma(q, r, logc));
 }
-VB_HD double log_pos(double s, const double *tab) { return log_pos_plus(s, tab, 0.0); }
+template <int LS = 1>
+VB_HD double log_shift(double s, const double *tab, int c) { return log_shift_biased<LS>(s, tab, c - 1023); }
 
 }  // namespace vbhem
