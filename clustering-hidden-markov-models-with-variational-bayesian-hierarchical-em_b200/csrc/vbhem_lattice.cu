@@ -67,10 +67,12 @@ struct Tables {
     }
     for (int x = threadIdx.x; x < VBHEM_EXP_BINS * ES; x += blockDim.x) dst[kLogDoubles + x] = g_exp_table[x / ES];
   }
-  // the calling lane's views of the two tables
-  static __device__ __forceinline__ const double *log_view(const double *base, int lane) { return base + 2 * (lane % LS); }
-  static __device__ __forceinline__ const double *exp_view(const double *base, int lane) {
-    return base + kLogDoubles + (lane % ES);
+  // the calling lane's views of the two tables (shared-space byte addresses)
+  static __device__ __forceinline__ tab_t log_view(const double *base, int lane) {
+    return (tab_t)__cvta_generic_to_shared(base + 2 * (lane % LS));
+  }
+  static __device__ __forceinline__ tab_t exp_view(const double *base, int lane) {
+    return (tab_t)__cvta_generic_to_shared(base + kLogDoubles + (lane % ES));
   }
 };
 using TabFirst = Tables<8, 16>;   // first pass: bank-replicated
@@ -237,7 +239,7 @@ __device__ __forceinline__ bool pair_inputs_bad(double base_chk, const Frag &exp
 // accumulates the excess of the step's row shifts (see shift_excess).
 template <bool STORE>
 __device__ __forceinline__ void bwd_step(const Frag &E, Frag &G, const Frag &expA, const Frag &Ab,
-                                         const double *ltab, const double *etab, double *sBm, double *sInvS,
+                                         tab_t ltab, tab_t etab, double *sBm, double *sInvS,
                                          unsigned &rng, int g, int q) {
   int e0, e1;
   const double m0 = exp_split(G.x0, etab, e0), m1 = exp_split(G.x1, etab, e1);
@@ -259,8 +261,8 @@ __device__ __forceinline__ void bwd_step(const Frag &E, Frag &G, const Frag &exp
 // Termination (vbhem_hmm_bwd_fwd_mex.c:1029-1080).  Returns L_elbo (all lanes) and
 // nu_1(beta = g | sigma = 2q+e) = prior * Theta_1.
 template <int LS, int ES>
-__device__ __forceinline__ double terminate(const Frag &G, const Frag &expPi, double prior, const double *ltab,
-                                            const double *etab, int q, Frag &nu1, unsigned &rng) {
+__device__ __forceinline__ double terminate(const Frag &G, const Frag &expPi, double prior, tab_t ltab,
+                                            tab_t etab, int q, Frag &nu1, unsigned &rng) {
   int e0, e1;
   const double m0 = exp_split<ES>(G.x0, etab, e0), m1 = exp_split<ES>(G.x1, etab, e1);
   const int c = row_shift(e0, e1);
@@ -298,8 +300,8 @@ constexpr int kNP = VB_NP;
 
 template <int NP, int LS, int ES>
 __device__ __forceinline__ void bwd_step_n(const Frag (&E)[NP], Frag (&G)[NP], const Frag (&expA)[NP],
-                                           const Frag &Ab, const double *ltab, const double *etab,
-                                           unsigned (&rng)[NP], int q) {
+                                           const Frag &Ab, tab_t ltab, tab_t etab,
+                                           unsigned (&rng)[NP], int q, int one) {
   int e0[NP], e1[NP], c[NP];
   Frag Bm[NP], ST[NP], ell[NP];
 #pragma unroll
@@ -320,7 +322,7 @@ __device__ __forceinline__ void bwd_step_n(const Frag (&E)[NP], Frag (&G)[NP], c
   for (int p = 0; p < NP; p++) {
     const int cb0 = __shfl_sync(0xffffffffu, c[p] - 1023, (2 * q) * 4);
     const int cb1 = __shfl_sync(0xffffffffu, c[p] - 1023, (2 * q + 1) * 4);
-    ell[p] = Frag{log_shift_biased<LS>(ST[p].x0, ltab, cb0), log_shift_biased<LS>(ST[p].x1, ltab, cb1)};
+    ell[p] = Frag{log_shift_biased<LS>(ST[p].x0, ltab, cb0, one), log_shift_biased<LS>(ST[p].x1, ltab, cb1, one)};
   }
 #pragma unroll
   for (int p = 0; p < NP; p++) {
@@ -332,7 +334,7 @@ __device__ __forceinline__ void bwd_step_n(const Frag (&E)[NP], Frag (&G)[NP], c
 // Termination of NP pairs side by side (first pass: L_elbo only, valid in lane 0).
 template <int NP, int LS, int ES>
 __device__ __forceinline__ void terminate_n(const Frag (&G)[NP], const Frag (&expPi)[NP], double prior,
-                                            const double *ltab, const double *etab, int q, unsigned (&rng)[NP],
+                                            tab_t ltab, tab_t etab, int q, unsigned (&rng)[NP],
                                             double (&L)[NP]) {
   int e0[NP], e1[NP], c[NP];
   double m0[NP], m1[NP], s[NP];
@@ -371,7 +373,9 @@ k_lattice_bwd(BaseView B, CentreView C, int T, int kc, double *L_elbo, Fallback 
   const int j0 = blockIdx.y * kc;
   const int nj = min(kc, C.K - j0);
   const int rs = C.rec_stride;
-  const double *ltab = TabFirst::log_view(smem, lane), *etab = TabFirst::exp_view(smem, lane);
+  const tab_t ltab = TabFirst::log_view(smem, lane), etab = TabFirst::exp_view(smem, lane);
+  int one;   // 0x3ff00000 pinned in a register (see mant_hi)
+  asm volatile("mov.b32 %0, 0x3ff00000;" : "=r"(one));
   double *recs = smem + TabFirst::kDoubles;
   TabFirst::load(smem);
   for (int x = threadIdx.x; x < nj * rs; x += blockDim.x) recs[x] = C.rec[(size_t)j0 * rs + x];
@@ -398,13 +402,13 @@ k_lattice_bwd(BaseView B, CentreView C, int T, int kc, double *L_elbo, Fallback 
         rng[p] = 0u;
         bad[p] = pair_inputs_bad(base_chk, expA[p], expPi[p], E[p]);
       }
-      for (int t = T - 1; t >= 1; t--) bwd_step_n<kNP, 8, 16>(E, G, expA, b.Ab, ltab, etab, rng, q);
+      for (int t = T - 1; t >= 1; t--) bwd_step_n<kNP, 8, 16>(E, G, expA, b.Ab, ltab, etab, rng, q, one);
       // Termination (vbhem_hmm_bwd_fwd_mex.c:1029-1080) is one more step of the same shape with
       // logPi in place of every row of logA and the prior in place of every row of A_b:
       //   S(rho|beta) = sum_sigma expPi[sigma] Bm[beta,sigma]   (the same for every rho)
       //   G(beta'|rho) = sum_beta prior[beta] lse[beta]          = L_elbo in every element
 #if VB_TERM_STEP
-      bwd_step_n<kNP, 8, 16>(Z, G, expPi, b.priorT, ltab, etab, rng, q);
+      bwd_step_n<kNP, 8, 16>(Z, G, expPi, b.priorT, ltab, etab, rng, q, one);
 #else
       double Lt[kNP];
       terminate_n<kNP, 8, 16>(G, expPi, b.prior, ltab, etab, q, rng, Lt);
@@ -439,7 +443,7 @@ struct PairStats {
 template <int D, bool FULL>
 __device__ __forceinline__ bool pair_full(const BaseView &B, int i, const BaseConst<D, FULL> &b,
                                           const CentreConst<D, FULL> &c, const double *rec, int T,
-                                          const double *ltab, const double *etab, double *sm, int g, int q, double &Lout,
+                                          tab_t ltab, tab_t etab, double *sm, int g, int q, double &Lout,
                                           PairStats<D, FULL> &st) {
   constexpr int DD = BaseConst<D, FULL>::DD;
   double *xch = sm + (size_t)2 * kTile * (T - 1);
@@ -512,7 +516,7 @@ k_lattice_full(BaseView B, CentreView C, int T, PairWork W, PairOut O, Fallback 
   constexpr int DD = BaseConst<D, FULL>::DD;
   const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
   const int warp = threadIdx.x >> 5;
-  const double *ltab = smem, *etab = smem + TabFull::kLogDoubles;
+  const tab_t ltab = TabFull::log_view(smem, 0), etab = TabFull::exp_view(smem, 0);
   TabFull::load(smem);
   __syncthreads();
   double *sm = smem + TabFull::kDoubles + (size_t)warp * ((size_t)2 * kTile * (T - 1) + kTile);

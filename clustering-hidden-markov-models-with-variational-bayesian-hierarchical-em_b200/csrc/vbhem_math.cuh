@@ -83,6 +83,51 @@ VB_HD double make_double(int hi, int lo) {
   uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo; double x; memcpy(&x, &u, 8); return x;
 #endif
 }
+// A lane's view of a lookup table.  Under nvcc it is the 32-bit shared-space byte address and the
+// loads are explicit ld.shared (address arithmetic stays in 32 bits: mask, shift-add, load); for the
+// host build (tests) it is a plain pointer.
+#ifdef __CUDACC__
+typedef unsigned tab_t;
+__host__ __device__ __forceinline__ double tab_ld(tab_t base, unsigned byte_off) {
+  double v = 0.0;
+#ifdef __CUDA_ARCH__
+  asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(base + byte_off));
+#endif
+  return v;
+}
+__host__ __device__ __forceinline__ void tab_ld2(tab_t base, unsigned byte_off, double &a, double &b) {
+  a = b = 0.0;
+#ifdef __CUDA_ARCH__
+  asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(base + byte_off));
+#endif
+}
+// a & mask as an opaque instruction, so that the compiler keeps "mask, then scale-and-add" (LOP3 + IMAD/LEA)
+// instead of re-associating table addresses into shift, mask, add
+template <unsigned MASK>
+__host__ __device__ __forceinline__ unsigned and_opaque(unsigned a) {
+  unsigned d = a & MASK;
+#ifdef __CUDA_ARCH__
+  asm("and.b32 %0, %1, %2;" : "=r"(d) : "r"(a), "n"(MASK));
+#endif
+  return d;
+}
+// high word of the mantissa-only double: (hi & 0x000fffff) | one, one = 0x3ff00000 held in a register (one LOP3)
+__host__ __device__ __forceinline__ int mant_hi(int hi, int one) {
+  int d = (hi & 0x000fffff) | one;
+#ifdef __CUDA_ARCH__
+  asm("lop3.b32 %0, %1, 0x000fffff, %2, 0xEA;" : "=r"(d) : "r"(hi), "r"(one));
+#endif
+  return d;
+}
+#else
+inline int mant_hi(int hi, int one) { return (hi & 0x000fffff) | one; }
+template <unsigned MASK>
+inline unsigned and_opaque(unsigned a) { return a & MASK; }
+typedef const double *tab_t;
+inline double tab_ld(tab_t base, unsigned byte_off) { return base[byte_off / 8]; }
+inline void tab_ld2(tab_t base, unsigned byte_off, double &a, double &b) { a = base[byte_off / 8]; b = base[byte_off / 8 + 1]; }
+#endif
+
 // low 32 bits of (hi:lo) >> s, 0 < s < 32
 VB_HD int funnel_right(int lo, int hi, int s) {
 #ifdef __CUDA_ARCH__
@@ -97,11 +142,11 @@ VB_HD int funnel_right(int lo, int hi, int s) {
 // its Taylor polynomial.  ES = stride of the table in doubles (the first-pass kernel keeps one copy
 // per shared-memory bank pair).
 template <int ES = 1>
-VB_HD double exp_split(double y, const double *etab, int &e) {
+VB_HD double exp_split(double y, tab_t etab, int &e) {
   const double t = y + VB_MC(10);
   const double r = y - (t - VB_MC(10));
   e = funnel_right(lo_word(t), hi_word(t), VBHEM_EXP_SHIFT);   // k >> SHIFT
-  const double T = etab[(lo_word(t) & (VBHEM_EXP_BINS - 1)) * ES];
+  const double T = tab_ld(etab, and_opaque<VBHEM_EXP_BINS - 1>((unsigned)lo_word(t)) * (8u * ES));
 #if VBHEM_EXP_DEG == 3
   double q = fma(r, VB_MC(2), VB_MC(1));
 #elif VBHEM_EXP_DEG == 4
@@ -138,18 +183,18 @@ VB_HD bool nonfinite(double x) { return ((unsigned)hi_word(x) & 0x7ff00000u) == 
 // (c ln2 + log s) / u for normal positive s; cb = c - 1023.  tab = VBHEM_LOG_TABLE as (invc, logc/u)
 // pairs: s = 2^e m, r = m invc - 1, log s = e ln2 + logc + log1p(r); in units, e ln2 / u = e BINS
 // exactly.  LS = stride of the table in pairs.  Error <= ~1e-13 units = 3e-16 natural.
+VB_HD constexpr int ilog2(int x) { return x <= 1 ? 0 : 1 + ilog2(x >> 1); }
 template <int LS = 1>
-VB_HD double log_shift_biased(double s, const double *tab, int cb) {
+VB_HD double log_shift_biased(double s, tab_t tab, int cb, int one = 0x3ff00000) {
   const int hi = hi_word(s);
   const int e = (hi >> 20) + cb;
-  const int i = (hi >> (20 - VBHEM_LOG_BITS)) & (VBHEM_LOG_BINS - 1);
-  const double m = make_double((hi & 0x000fffff) | 0x3ff00000, lo_word(s));
-#ifdef __CUDA_ARCH__
-  const double2 tl = *reinterpret_cast<const double2 *>(tab + 2 * LS * i);   // 16-byte aligned by construction
-  const double invc = tl.x, logc = tl.y;
-#else
-  const double invc = tab[2 * LS * i], logc = tab[2 * LS * i + 1];
-#endif
+  // byte offset of pair i = top LOG_BITS mantissa bits: i * 16 * LS, as one mask and one shift
+  constexpr int sh = 20 - VBHEM_LOG_BITS - 4 - ilog2(LS);
+  static_assert(sh >= 0 && (1 << ilog2(LS)) == LS, "table stride");
+  const unsigned off = and_opaque<(VBHEM_LOG_BINS - 1u) << (20 - VBHEM_LOG_BITS)>((unsigned)hi) >> sh;
+  const double m = make_double(mant_hi(hi, one), lo_word(s));
+  double invc, logc;
+  tab_ld2(tab, off, invc, logc);
   const double r = fma(m, invc, -1.0);
 #if VBHEM_LOG_DEG == 4
   double q = fma(r, VB_MC(8), VB_MC(7));
@@ -162,6 +207,6 @@ VB_HD double log_shift_biased(double s, const double *tab, int cb) {
   return fma((double)e, (double)VBHEM_EXP_BINS, fma(q, r, logc));
 }
 template <int LS = 1>
-VB_HD double log_shift(double s, const double *tab, int c) { return log_shift_biased<LS>(s, tab, c - 1023); }
+VB_HD double log_shift(double s, tab_t tab, int c) { return log_shift_biased<LS>(s, tab, c - 1023); }
 
 }  // namespace vbhem
