@@ -125,14 +125,14 @@ __global__ void k_build_records(CentreView C, int d, int dd, double *rec) {
   for (int k = threadIdx.x; k < 8; k += blockDim.x) o[64 + k] = k < r ? exp(C.logPi[k + (size_t)ld * j]) : 0.0;
   __syncthreads();
   // The lattice kernel's sums are bounded below by these weights (vbhem_lattice.cu): a centre with a
-  // weight under 2^-900 (log weight < -623) gets a NaN emission constant, which sends its pairs to the
+  // weight that is non-finite or under 2^-900 (log weight < -623) gets a NaN emission constant, which sends its pairs to the
   // general log-space kernel.
   __shared__ int weak;
   if (threadIdx.x == 0) weak = 0;
   __syncthreads();
   for (int x = threadIdx.x; x < 64 + 8; x += blockDim.x) {
     const bool live = x < 64 ? (x / 8 < r && x % 8 < r) : (x - 64 < r);
-    if (live && !(o[x] >= 0x1p-900)) weak = 1;
+    if (live && !(o[x] >= 0x1p-900 && o[x] <= 1e300)) weak = 1;   // also NaN / Inf
   }
   __syncthreads();
   for (int k = threadIdx.x; k < 8; k += blockDim.x) {

@@ -221,16 +221,14 @@ __device__ __forceinline__ int row_shift(int e0, int e1) {
 // per pair, not per step: the pair is bad if a transition / prior / centre weight is non-finite, the
 // base transition rows sum (in magnitude) to more than 1.001 (growth bound of the recursion), or an
 // emission term is NaN, +Inf or above 2^35 units (9e7).  k_build_records poisons the emission constant of a
-// centre whose weights are below 2^-900, which lands here as a NaN.  Such pairs go to the general
+// centre whose weights are non-finite or below 2^-900, which lands here as a NaN.  Such pairs go to the general
 // log-space kernel, which reproduces the reference.
-__device__ __forceinline__ double base_check(const Frag &Ab, double prior) {
+__device__ __forceinline__ bool base_bad(const Frag &Ab, double prior) {
   const double rs = quad_sum(fabs(Ab.x0) + fabs(Ab.x1));
-  return (rs <= 1.001 ? 0.0 : INFINITY) + prior;          // NaN / Inf anywhere => non-finite
+  return nonfinite((rs <= 1.001 ? 0.0 : INFINITY) + prior);   // NaN / Inf anywhere => non-finite
 }
-__device__ __forceinline__ bool pair_inputs_bad(double base_chk, const Frag &expA, const Frag &expPi,
-                                                const Frag &E) {
-  const double chk = base_chk + ((expA.x0 + expA.x1) + (expPi.x0 + expPi.x1));
-  return nonfinite(chk) | nan_or_large(E.x0) | nan_or_large(E.x1);
+__device__ __forceinline__ bool pair_inputs_bad(bool base_is_bad, const Frag &E) {
+  return base_is_bad | nan_or_large(E.x0) | nan_or_large(E.x1);
 }
 
 // One backward step (t = T-1 .. 1).  In: G(beta|sigma) = E + L of this step.  Out: G of the
@@ -331,7 +329,8 @@ __device__ __forceinline__ void bwd_step_n(const Frag (&E)[NP], Frag (&G)[NP], c
   }
 }
 
-// Termination of NP pairs side by side (first pass: L_elbo only, valid in lane 0).
+// Termination of NP pairs side by side (first pass: L_elbo only; L[p] is valid in lane p when NP == 2,
+// in lane 0 otherwise).
 template <int NP, int LS, int ES>
 __device__ __forceinline__ void terminate_n(const Frag (&G)[NP], const Frag (&expPi)[NP], double prior,
                                             tab_t ltab, tab_t etab, int q, unsigned (&rng)[NP],
@@ -350,17 +349,31 @@ __device__ __forceinline__ void terminate_n(const Frag (&G)[NP], const Frag (&ex
     rng[p] = max(rng[p], shift_excess(c[p]));
     s[p] = expPi[p].x0 * exp_scale(m0[p], e0[p] - c[p]) + expPi[p].x1 * exp_scale(m1[p], e1[p] - c[p]);
   }
-#pragma unroll
-  for (int p = 0; p < NP; p++) s[p] += __shfl_xor_sync(0xffffffffu, s[p], 1);
-#pragma unroll
-  for (int p = 0; p < NP; p++) s[p] += __shfl_xor_sync(0xffffffffu, s[p], 2);
   const double pu = prior * kUnit;
+  if constexpr (NP == 2) {
+    // Transposing reduction over the quad: lanes with even q end up with pair 0's sum, odd q with pair
+    // 1's, so each lane takes ONE logarithm and the sum over base states runs once for both pairs.
+    // L[0] is valid in lane 0, L[1] in lane 1.
+    const bool odd = q & 1;
+    double v = (odd ? s[1] : s[0]) + __shfl_xor_sync(0xffffffffu, odd ? s[0] : s[1], 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    double w = q < 2 ? pu * log_shift<LS>(v, ltab, odd ? c[1] : c[0]) : 0.0;
 #pragma unroll
-  for (int p = 0; p < NP; p++) L[p] = q == 0 ? pu * log_shift<LS>(s[p], ltab, c[p]) : 0.0;
+    for (int o = 4; o < 32; o <<= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+    L[0] = w;
+    L[NP - 1] = w;
+  } else {
 #pragma unroll
-  for (int o = 4; o < 32; o <<= 1) {
+    for (int p = 0; p < NP; p++) s[p] += __shfl_xor_sync(0xffffffffu, s[p], 1);
 #pragma unroll
-    for (int p = 0; p < NP; p++) L[p] += __shfl_xor_sync(0xffffffffu, L[p], o);
+    for (int p = 0; p < NP; p++) s[p] += __shfl_xor_sync(0xffffffffu, s[p], 2);
+#pragma unroll
+    for (int p = 0; p < NP; p++) L[p] = q == 0 ? pu * log_shift<LS>(s[p], ltab, c[p]) : 0.0;
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+#pragma unroll
+      for (int p = 0; p < NP; p++) L[p] += __shfl_xor_sync(0xffffffffu, L[p], o);
+    }
   }
 }
 
@@ -384,7 +397,7 @@ k_lattice_bwd(BaseView B, CentreView C, int T, int kc, double *L_elbo, Fallback 
   for (int i = blockIdx.x * kBwdWarps + warp; i < B.N; i += gridDim.x * kBwdWarps) {
     BaseConst<D, FULL> b;
     load_base(b, B, i, g, q);
-    const double base_chk = base_check(b.Ab, b.prior);
+    const bool base_chk = base_bad(b.Ab, b.prior);
     for (int jj = 0; jj < nj; jj += kNP) {
       Frag E[kNP], G[kNP], expA[kNP], expPi[kNP], Z[kNP];
       unsigned rng[kNP];
@@ -400,7 +413,7 @@ k_lattice_bwd(BaseView B, CentreView C, int T, int kc, double *L_elbo, Fallback 
         G[p] = E[p];
         Z[p] = Frag{0.0, 0.0};
         rng[p] = 0u;
-        bad[p] = pair_inputs_bad(base_chk, expA[p], expPi[p], E[p]);
+        bad[p] = pair_inputs_bad(base_chk, E[p]);
       }
       for (int t = T - 1; t >= 1; t--) bwd_step_n<kNP, 8, 16>(E, G, expA, b.Ab, ltab, etab, rng, q, one);
       // Termination (vbhem_hmm_bwd_fwd_mex.c:1029-1080) is one more step of the same shape with
@@ -421,7 +434,7 @@ k_lattice_bwd(BaseView B, CentreView C, int T, int kc, double *L_elbo, Fallback 
         const double Le = Lt[p];
 #endif
         const bool good = __all_sync(0xffffffffu, (rng[p] <= kShiftBound) & !bad[p]);
-        if (lane == 0 && jj + p < nj) {
+        if (lane == (kNP == 2 && !VB_TERM_STEP ? p : 0) && jj + p < nj) {
           const size_t pi = (size_t)i + (size_t)B.N * (j0 + jj + p);
           L_elbo[pi] = Le;
           if (!good) { fb.flags[pi] = 1; atomicAdd(fb.count, 1); }
@@ -450,7 +463,7 @@ __device__ __forceinline__ bool pair_full(const BaseView &B, int i, const BaseCo
   const Frag E = emission(b, rec, g, q);
   Frag G = E;
   unsigned rng = 0u;
-  const bool bad = pair_inputs_bad(base_check(b.Ab, b.prior), c.expA, c.expPi, E);
+  const bool bad = pair_inputs_bad(base_bad(b.Ab, b.prior), E);
   for (int t = T - 1; t >= 1; t--) {
     double *s = sm + (size_t)2 * kTile * (t - 1);
     bwd_step<true>(E, G, c.expA, b.Ab, ltab, etab, s, s + kTile, rng, g, q);
