@@ -36,6 +36,10 @@ SIGNATURES = {
                               dp, dp, dp]),
     "vbhem_estep_hyp": (C.c_int, [vp, C.c_int, ip, C.c_int, ip, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, dp,
                                   dp, dp, dp, dp]),
+    "vbhem_estep_stream": (C.c_int, [vp, ip, dp, dp, dp, dp, dp, C.c_int, C.c_int, ip, C.c_int, ip, C.c_int, C.c_int,
+                                     dp, dp, dp, dp, dp, dp, dp, dp, dp]),
+    "vbhem_estep_hyp_stream": (C.c_int, [vp, ip, dp, dp, dp, dp, dp, C.c_int, C.c_int, ip, C.c_int, ip, C.c_int,
+                                         C.c_int, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp]),
     "vbhem_estep_dev": (C.c_int, [vp, C.c_int, ip, C.c_int, ip, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, vp]),
     "vbhem_estep_hyp_dev": (C.c_int, [vp, C.c_int, ip, C.c_int, ip, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, dp,
                                       vp, dp]),

@@ -136,8 +136,12 @@ class BaseSet:
         out["buf"] = buf
         return out
 
-    def estep_hyp(self, hyp: dict, tau: int, want_pairs: bool = True, group=None) -> dict:
+    def estep_hyp(self, hyp: dict, tau: int, want_pairs: bool = True, group=None, stream_base: dict | None = None,
+                  nslices: int = 8) -> dict:
         """Fused E-step from centre hyper-parameters; the pre-pass runs on the device.
+
+        With ``stream_base`` (a base set of this handle's shape, natural or packed) the base set is streamed
+        in from host memory slice by slice while earlier slices compute (``vbhem_estep_hyp_stream``).
 
         hyp (natural): Sr[K], alpha[K], eta[K,S], epsilon[K,S,S], m[K,S,d], W[K,S,d,d]|[K,S,d], v[K,S], lam[K,S].
         Also returns the pre-pass results the host-side lower bound needs
@@ -157,8 +161,16 @@ class BaseSet:
         z = np.zeros((K, self.N)) if want_pairs else None
         f64 = lambda a: c(a, dtype=np.float64)
         al, et, m, v, lam = f64(hyp["alpha"]), f64(hyp["eta"]), f64(hyp["m"]), f64(hyp["v"]), f64(hyp["lam"])
-        check(lib().vbhem_estep_hyp(self._h, K, _i(Sr), r, _i(grp), ng, tau, _d(al), _d(et), _d(eps), _d(m),
-                                    _d(Wp), _d(v), _d(lam), _d(L), _d(z), _d(buf), _d(pre)))
+        if stream_base is not None:
+            pb = stream_base if "Sb" in stream_base and "maxSb" in stream_base else pack.pack_base(stream_base)
+            assert (pb["N"], pb["maxSb"], pb["d"], pb["covmode"]) == (self.N, self.maxSb, self.d, self.covmode)
+            check(lib().vbhem_estep_hyp_stream(self._h, _i(pb["Sb"]), _d(pb["prior"]), _d(pb["A"]), _d(pb["mu"]),
+                                               _d(pb["cov"]), _d(pb["Ntilde"]), nslices, K, _i(Sr), r, _i(grp), ng,
+                                               tau, _d(al), _d(et), _d(eps), _d(m), _d(Wp), _d(v), _d(lam), _d(L),
+                                               _d(z), _d(buf), _d(pre)))
+        else:
+            check(lib().vbhem_estep_hyp(self._h, K, _i(Sr), r, _i(grp), ng, tau, _d(al), _d(et), _d(eps), _d(m),
+                                        _d(Wp), _d(v), _d(lam), _d(L), _d(z), _d(buf), _d(pre)))
         S = self._split_stats(buf, K, r, ng)
         S["L_elbo"], S["zhat"] = L, z
         out = pack.stats_to_natural(S, self.d, self.covmode)

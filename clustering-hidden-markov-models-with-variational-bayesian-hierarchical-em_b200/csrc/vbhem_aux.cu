@@ -143,9 +143,9 @@ __global__ void k_build_records(CentreView C, int d, int dd, double *rec) {
 }
 
 // Zero everything beyond each base HMM's own state count (the kernels rely on it).
-__global__ void k_sanitize_base(BaseView B, double *prior, double *A, double *mu, double *cov) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B.N) return;
+__global__ void k_sanitize_base(BaseView B, double *prior, double *A, double *mu, double *cov, int i0, int i1) {
+  const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= i1) return;
   const int b = B.Sb[i], ld = B.maxSb;
   for (int k = 0; k < ld; k++) {
     if (k >= b) {
@@ -173,11 +173,12 @@ __device__ __forceinline__ double warp_sum(double v) {
 // lb_part[blk][2*ngroups] (Lt1, Lt7 partial sums).
 __global__ void __launch_bounds__(kZThreads)
 k_zhat(int N, int K, int ngroups, const int *gstart, const double *L_elbo, const double *logOmega,
-       const double *Ntilde, double *zhat, double *Nj_part, int *cnt, double *lb_part) {
+       const double *Ntilde, double *zhat, double *Nj_part, int *cnt, double *lb_part, int blk0) {
   __shared__ double red[kZWarps][kJT];
   __shared__ int redc[kZWarps][kJT];
   __shared__ double redl[kZWarps][2];
-  const int i = blockIdx.x * kZThreads + threadIdx.x;
+  const int blk = blk0 + blockIdx.x;
+  const int i = blk * kZThreads + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool live = i < N;
   const double Nt = live ? Ntilde[i] : 0.0;
@@ -224,8 +225,8 @@ k_zhat(int N, int K, int ngroups, const int *gstart, const double *L_elbo, const
         double s = 0.0;
         int c = 0;
         for (int w = 0; w < kZWarps; w++) { s += red[w][lane]; c += redc[w][lane]; }
-        Nj_part[(size_t)blockIdx.x * K + j0 + lane] = s;
-        cnt[(size_t)blockIdx.x * K + j0 + lane] = c;
+        Nj_part[(size_t)blk * K + j0 + lane] = s;
+        cnt[(size_t)blk * K + j0 + lane] = c;
       }
       __syncthreads();
     }
@@ -236,8 +237,8 @@ k_zhat(int N, int K, int ngroups, const int *gstart, const double *L_elbo, const
     if (threadIdx.x == 0) {
       double a = 0.0, b = 0.0;
       for (int w = 0; w < kZWarps; w++) { a += redl[w][0]; b += redl[w][1]; }
-      lb_part[(size_t)blockIdx.x * 2 * ngroups + 2 * g] = a;
-      lb_part[(size_t)blockIdx.x * 2 * ngroups + 2 * g + 1] = b;
+      lb_part[(size_t)blk * 2 * ngroups + 2 * g] = a;
+      lb_part[(size_t)blk * 2 * ngroups + 2 * g + 1] = b;
     }
     __syncthreads();
   }
@@ -464,8 +465,11 @@ int launch_build_records(const CentreView &C, int d, int dd, double *rec, cudaSt
   return 1;
 }
 
-int launch_sanitize_base(BaseView B, double *prior, double *A, double *mu, double *cov, cudaStream_t st) {
-  k_sanitize_base<<<(B.N + 127) / 128, 128, 0, st>>>(B, prior, A, mu, cov);
+int launch_sanitize_base(BaseView B, double *prior, double *A, double *mu, double *cov, cudaStream_t st, int i0,
+                         int n) {
+  if (n < 0) n = B.N - i0;
+  if (n <= 0) return 0;
+  k_sanitize_base<<<(n + 127) / 128, 128, 0, st>>>(B, prior, A, mu, cov, i0, i0 + n);
   return 1;
 }
 
@@ -473,13 +477,24 @@ int zhat_blocks(int N) { return (N + kZThreads - 1) / kZThreads; }
 
 int launch_zhat(int N, int K, int ngroups, const int *gstart, const double *L_elbo, const double *logOmega,
                 const double *Ntilde, double *zhat, double *Nj_part, int *cnt, double *lb_part, double *Nj, double *lb,
-                cudaStream_t st) {
+                cudaStream_t st, int blk0, int nblk, bool reduce) {
   const int nb = zhat_blocks(N);
-  k_zhat<<<nb, kZThreads, 0, st>>>(N, K, ngroups, gstart, L_elbo, logOmega, Ntilde, zhat, Nj_part, cnt, lb_part);
-  const int tot = K + 2 * ngroups;
-  k_zhat_reduce<<<(tot + 127) / 128, 128, 0, st>>>(nb, K, ngroups, Nj_part, lb_part, Nj, lb);
-  return 2;
+  if (nblk < 0) nblk = nb - blk0;
+  int launched = 0;
+  if (nblk > 0) {
+    k_zhat<<<nblk, kZThreads, 0, st>>>(N, K, ngroups, gstart, L_elbo, logOmega, Ntilde, zhat, Nj_part, cnt, lb_part,
+                                       blk0);
+    launched++;
+  }
+  if (reduce) {
+    const int tot = K + 2 * ngroups;
+    k_zhat_reduce<<<(tot + 127) / 128, 128, 0, st>>>(nb, K, ngroups, Nj_part, lb_part, Nj, lb);
+    launched++;
+  }
+  return launched;
 }
+
+int zhat_block_size() { return kZThreads; }
 
 int launch_list_scan(int N, int K, int chunk_len, const int *cnt, int *offs, int *segcnt, int *seg_start,
                      int *chunk_start, int *totals, cudaStream_t st) {

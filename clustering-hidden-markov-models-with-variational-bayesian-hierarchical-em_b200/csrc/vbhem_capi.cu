@@ -70,6 +70,9 @@ struct vbhem_base {
   // results and work lists
   DevBuf L, z, flags, fbcount, Njp, lbp, cnt, offs, segs, items, chunks, partial, itemflags, scratch, pairs_out,
       stats;
+  // streamed E-step (base set in host memory): copy-in / copy-out streams and per-slice events
+  cudaStream_t cin = nullptr, cout = nullptr;
+  std::vector<cudaEvent_t> slice_ev;
   int *h_totals = nullptr;   // pinned
   bool profile = false;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -89,6 +92,14 @@ struct CentreArgs {
   // ... or hyper-parameters (vbhem_estep_hyp)
   const double *alpha, *eta, *epsilon, *W, *v, *lambda;
   bool hyp;
+};
+
+// Host-resident base set and host result buffers of a streamed E-step (vbhem_estep*_stream).
+struct StreamIO {
+  const int32_t *Sb;
+  const double *prior, *A, *mu, *cov, *Ntilde;
+  double *L_host, *z_host;
+  int nslices;
 };
 
 int check_common(vbhem_base *h, const CentreArgs &a, bool need_omega) {
@@ -208,6 +219,21 @@ int ensure_scratch(vbhem_base *h, int maxSr, int T, long long want_warps, size_t
   return VBHEM_OK;
 }
 
+struct StatsPtr { double *Nj, *nu1, *xi, *pr, *mu, *Mu, *lb; };
+
+StatsPtr carve_stats(double *s, int K, int r, int d, int dd, int ng) {
+  (void)ng;
+  StatsPtr p;
+  p.Nj = s; s += K;
+  p.nu1 = s; s += (size_t)r * K;
+  p.xi = s; s += (size_t)r * r * K;
+  p.pr = s; s += (size_t)r * K;
+  p.mu = s; s += (size_t)r * d * K;
+  p.Mu = s; s += (size_t)r * dd * K;
+  p.lb = s;
+  return p;
+}
+
 // L_elbo for every pair into h->L (first pass).
 int first_pass(vbhem_base *h, const CentreDev &cd, int T, long long &launches) {
   const long long np = (long long)h->B.N * cd.C.K;
@@ -242,23 +268,93 @@ int first_pass(vbhem_base *h, const CentreDev &cd, int T, long long &launches) {
   return VBHEM_OK;
 }
 
-struct StatsPtr { double *Nj, *nu1, *xi, *pr, *mu, *Mu, *lb; };
-
-StatsPtr carve_stats(double *s, int K, int r, int d, int dd, int ng) {
-  (void)ng;
-  StatsPtr p;
-  p.Nj = s; s += K;
-  p.nu1 = s; s += (size_t)r * K;
-  p.xi = s; s += (size_t)r * r * K;
-  p.pr = s; s += (size_t)r * K;
-  p.mu = s; s += (size_t)r * d * K;
-  p.Mu = s; s += (size_t)r * dd * K;
-  p.lb = s;
-  return p;
+// Front half of a streamed E-step: the base set arrives from host memory in slices (multiples of the
+// zhat block, so every fixed-order sum is the one the resident path takes) on the copy-in stream while
+// earlier slices run first pass + responsibilities on the handle's stream and their L_elbo / zhat rows
+// leave on the copy-out stream.  Afterwards the handle holds the whole set, as after vbhem_repack_base.
+int streamed_front(vbhem_base *h, const CentreDev &cd, const CentreArgs &a, const StreamIO &io, const StatsPtr &S,
+                   long long &launches) {
+  const int N = h->B.N, K = a.K, T = a.tau, maxSb = h->B.maxSb, d = h->B.d, dd = h->B.dd;
+  const long long np = (long long)N * K;
+  if (!h->cin) CU(cudaStreamCreateWithFlags(&h->cin, cudaStreamNonBlocking));
+  if (!h->cout) CU(cudaStreamCreateWithFlags(&h->cout, cudaStreamNonBlocking));
+  const int zb = zhat_block_size();
+  int ns = io.nslices < 1 ? 1 : (io.nslices > 64 ? 64 : io.nslices);
+  // slice length: a multiple of the responsibility block, and of one full wave of the first-pass grid when the
+  // set is large enough, so that slicing adds no partially filled wave
+  long long unit = zb;
+  {
+    const long long wave = lattice_bwd_wave();
+    long long a = unit, b = wave;
+    while (b) { const long long t = a % b; a = b; b = t; }
+    const long long l = unit / a * wave;
+    if (l * 2 <= N) unit = l;
+  }
+  long long per64 = (((long long)N + ns - 1) / ns + unit - 1) / unit * unit;
+  const int per = (int)(per64 < N ? per64 : ((N + zb - 1) / zb * zb));
+  ns = (N + per - 1) / per;
+  while ((int)h->slice_ev.size() < 2 * ns + 1) {
+    cudaEvent_t e;
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->slice_ev.push_back(e);
+  }
+  CU(h->flags.ensure(np));
+  CU(h->fbcount.ensure(2 * sizeof(int)));
+  CU(cudaMemsetAsync(h->flags.p, 0, np, h->st));
+  CU(cudaMemsetAsync(h->fbcount.p, 0, 2 * sizeof(int), h->st));
+  Fallback fb{h->flags.as<unsigned char>(), h->fbcount.as<int>()};
+  size_t sd;
+  int rc = ensure_scratch(h, cd.C.maxSr, T, 296, sd);
+  if (rc) return rc;
+  // earlier work on the handle's stream may still read the base buffers
+  CU(cudaEventRecord(h->slice_ev[2 * ns], h->st));
+  CU(cudaStreamWaitEvent(h->cin, h->slice_ev[2 * ns], 0));
+  PairWork W{nullptr, nullptr, 0, np};
+  PairOut O{};
+  O.mode = 0;
+  O.L_elbo = h->L.as<double>();
+  for (int c = 0; c < ns; c++) {
+    const int i0 = c * per, n = (N - i0 < per) ? N - i0 : per;
+    const size_t o1 = (size_t)maxSb * i0, n1 = (size_t)maxSb * n;
+    CU(cudaMemcpyAsync(h->bSb.as<int>() + i0, io.Sb + i0, sizeof(int) * n, cudaMemcpyHostToDevice, h->cin));
+    CU(cudaMemcpyAsync(h->bprior.as<double>() + o1, io.prior + o1, sizeof(double) * n1, cudaMemcpyHostToDevice, h->cin));
+    CU(cudaMemcpyAsync(h->bA.as<double>() + o1 * maxSb, io.A + o1 * maxSb, sizeof(double) * n1 * maxSb,
+                       cudaMemcpyHostToDevice, h->cin));
+    CU(cudaMemcpyAsync(h->bmu.as<double>() + o1 * d, io.mu + o1 * d, sizeof(double) * n1 * d, cudaMemcpyHostToDevice,
+                       h->cin));
+    CU(cudaMemcpyAsync(h->bcov.as<double>() + o1 * dd, io.cov + o1 * dd, sizeof(double) * n1 * dd,
+                       cudaMemcpyHostToDevice, h->cin));
+    if (io.Ntilde)
+      CU(cudaMemcpyAsync(h->bNt.as<double>() + i0, io.Ntilde + i0, sizeof(double) * n, cudaMemcpyHostToDevice, h->cin));
+    CU(cudaEventRecord(h->slice_ev[2 * c], h->cin));
+    CU(cudaStreamWaitEvent(h->st, h->slice_ev[2 * c], 0));
+    launches += launch_sanitize_base(h->B, h->bprior.as<double>(), h->bA.as<double>(), h->bmu.as<double>(),
+                                     h->bcov.as<double>(), h->st, i0, n);
+    launches += launch_lattice_bwd(h->B, cd.C, T, O.L_elbo, fb, h->st, i0, n);
+    const int ng = launch_general(h->B, cd.C, T, W, O, fb.flags, fb.count, h->scratch.as<double>(), sd, h->st);
+    if (ng < 0) return fail(VBHEM_ENOMEM, "general kernel scratch too small");
+    launches += ng;
+    launches += launch_zhat(N, K, a.ngroups, cd.gstart, h->L.as<double>(), cd.C.logOmega, h->B.Ntilde,
+                            h->z.as<double>(), h->Njp.as<double>(), h->cnt.as<int>(), h->lbp.as<double>(), S.Nj, S.lb,
+                            h->st, i0 / zb, (n + zb - 1) / zb, c == ns - 1);
+    CU(cudaEventRecord(h->slice_ev[2 * c + 1], h->st));
+    CU(cudaStreamWaitEvent(h->cout, h->slice_ev[2 * c + 1], 0));
+    const size_t pitch = sizeof(double) * (size_t)N;
+    if (io.L_host)
+      CU(cudaMemcpy2DAsync(io.L_host + i0, pitch, h->L.as<double>() + i0, pitch, sizeof(double) * n, K,
+                           cudaMemcpyDeviceToHost, h->cout));
+    if (io.z_host)
+      CU(cudaMemcpy2DAsync(io.z_host + i0, pitch, h->z.as<double>() + i0, pitch, sizeof(double) * n, K,
+                           cudaMemcpyDeviceToHost, h->cout));
+  }
+  h->counters[1] += np;
+  return VBHEM_OK;
 }
 
-// The fused E-step on device buffers; stats_dev receives the raw sums.
-int estep_device(vbhem_base *h, const CentreArgs &a, double *stats_dev, double *pre_host) {
+// The fused E-step on device buffers; stats_dev receives the raw sums.  With `io` the base set is
+// streamed in from host memory (streamed_front) instead of being resident.
+int estep_device(vbhem_base *h, const CentreArgs &a, double *stats_dev, double *pre_host,
+                 const StreamIO *io = nullptr) {
   const int N = h->B.N, K = a.K, r = a.maxSr, d = h->B.d, dd = h->B.dd, T = a.tau;
   long long launches = 0;
   memset(h->counters, 0, sizeof h->counters);
@@ -268,13 +364,9 @@ int estep_device(vbhem_base *h, const CentreArgs &a, double *stats_dev, double *
   int rc = stage_centres(h, a, cd, pre_host, launches);
   if (rc) return rc;
   mark(1);
-  rc = first_pass(h, cd, T, launches);
-  if (rc) return rc;
-  mark(2);
-
-  // responsibilities + deterministic active list
   const long long np = (long long)N * K;
   const int nb = zhat_blocks(N);
+  CU(h->L.ensure(sizeof(double) * np));
   CU(h->z.ensure(sizeof(double) * np));
   CU(h->Njp.ensure(sizeof(double) * (size_t)nb * K));
   CU(h->lbp.ensure(sizeof(double) * (size_t)nb * 2 * a.ngroups));
@@ -282,9 +374,27 @@ int estep_device(vbhem_base *h, const CentreArgs &a, double *stats_dev, double *
   CU(h->offs.ensure(sizeof(int) * (size_t)nb * K));
   CU(h->segs.ensure(sizeof(int) * (size_t)(3 * (K + 1) + 2)));
   StatsPtr S = carve_stats(stats_dev, K, r, d, dd, a.ngroups);
-  launches += launch_zhat(N, K, a.ngroups, cd.gstart, h->L.as<double>(), cd.C.logOmega, h->B.Ntilde,
-                          h->z.as<double>(), h->Njp.as<double>(), h->cnt.as<int>(), h->lbp.as<double>(), S.Nj, S.lb,
-                          h->st);
+  if (io && cd.C.rec && lattice_supported(h->B, cd.C, T, false)) {
+    rc = streamed_front(h, cd, a, *io, S, launches);
+    if (rc) return rc;
+    mark(2);
+  } else {
+    if (io) {   // shapes the lattice kernel does not take: upload everything, then the resident path
+      rc = vbhem_repack_base(h, io->Sb, io->prior, io->A, io->mu, io->cov, io->Ntilde);
+      if (rc) return rc;
+    }
+    rc = first_pass(h, cd, T, launches);
+    if (rc) return rc;
+    mark(2);
+    // responsibilities + deterministic active list
+    launches += launch_zhat(N, K, a.ngroups, cd.gstart, h->L.as<double>(), cd.C.logOmega, h->B.Ntilde,
+                            h->z.as<double>(), h->Njp.as<double>(), h->cnt.as<int>(), h->lbp.as<double>(), S.Nj, S.lb,
+                            h->st);
+    if (io) {
+      if (io->L_host) CU(cudaMemcpyAsync(io->L_host, h->L.p, sizeof(double) * np, cudaMemcpyDeviceToHost, h->st));
+      if (io->z_host) CU(cudaMemcpyAsync(io->z_host, h->z.p, sizeof(double) * np, cudaMemcpyDeviceToHost, h->st));
+    }
+  }
   int *seg_start = h->segs.as<int>(), *chunk_start = seg_start + (K + 1), *totals = chunk_start + (K + 1);
   int *segcnt = totals + 2;
   launches += launch_list_scan(N, K, kChunkLen, h->cnt.as<int>(), h->offs.as<int>(), segcnt, seg_start, chunk_start,
@@ -342,23 +452,38 @@ int estep_device(vbhem_base *h, const CentreArgs &a, double *stats_dev, double *
   return VBHEM_OK;
 }
 
-int estep_host(vbhem_base *h, const CentreArgs &a, double *L_elbo, double *zhat, double *stats, double *pre) {
+int estep_host(vbhem_base *h, const CentreArgs &a, double *L_elbo, double *zhat, double *stats, double *pre,
+               StreamIO *io = nullptr) {
   if (!stats) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: stats is NULL");
   const size_t ns = vbhem_stats_size(a.K, a.maxSr, h->B.d, h->B.covmode, a.ngroups);
   CU(cudaSetDevice(h->device));
   CU(h->stats.ensure(sizeof(double) * ns));
-  int rc = estep_device(h, a, h->stats.as<double>(), pre);
+  if (io) { io->L_host = L_elbo; io->z_host = zhat; }
+  int rc = estep_device(h, a, h->stats.as<double>(), pre, io);
   if (rc) return rc;
   const size_t np = (size_t)h->B.N * a.K;
   CU(cudaMemcpyAsync(stats, h->stats.p, sizeof(double) * ns, cudaMemcpyDeviceToHost, h->st));
-  if (L_elbo) CU(cudaMemcpyAsync(L_elbo, h->L.p, sizeof(double) * np, cudaMemcpyDeviceToHost, h->st));
-  if (zhat) CU(cudaMemcpyAsync(zhat, h->z.p, sizeof(double) * np, cudaMemcpyDeviceToHost, h->st));
+  if (!io) {
+    if (L_elbo) CU(cudaMemcpyAsync(L_elbo, h->L.p, sizeof(double) * np, cudaMemcpyDeviceToHost, h->st));
+    if (zhat) CU(cudaMemcpyAsync(zhat, h->z.p, sizeof(double) * np, cudaMemcpyDeviceToHost, h->st));
+  }
   CU(cudaStreamSynchronize(h->st));
+  if (io && h->cout) CU(cudaStreamSynchronize(h->cout));
   if (h->fbcount.p) {
     int fb[2] = {0, 0};
     CU(cudaMemcpy(fb, h->fbcount.p, sizeof fb, cudaMemcpyDeviceToHost));
     h->counters[2] += fb[0] + fb[1];
   }
+  return VBHEM_OK;
+}
+
+int check_stream_base(vbhem_base *h, const StreamIO &io) {
+  if (!h) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: base handle is NULL");
+  if (!io.Sb || !io.prior || !io.A || !io.mu || !io.cov)
+    return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: a base array is NULL");
+  for (int i = 0; i < h->B.N; i++)
+    if (io.Sb[i] < 1 || io.Sb[i] > h->B.maxSb)
+      return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: Sb[%d]=%d outside 1..maxSb=%d", i, io.Sb[i], h->B.maxSb);
   return VBHEM_OK;
 }
 
@@ -467,6 +592,9 @@ int vbhem_free_base(vbhem_base_t *h) {
   if (!h) return VBHEM_OK;
   cudaSetDevice(h->device);
   if (h->own) cudaStreamSynchronize(h->own);
+  if (h->cin) { cudaStreamSynchronize(h->cin); cudaStreamDestroy(h->cin); }
+  if (h->cout) { cudaStreamSynchronize(h->cout); cudaStreamDestroy(h->cout); }
+  for (cudaEvent_t e : h->slice_ev) cudaEventDestroy(e);
   DevBuf *all[] = {&h->bSb, &h->bprior, &h->bA, &h->bmu, &h->bcov, &h->bNt, &h->cen_i, &h->cen_d, &h->hyp_d, &h->rec,
                    &h->L, &h->z, &h->flags, &h->fbcount, &h->Njp, &h->lbp, &h->cnt, &h->offs, &h->segs, &h->items,
                    &h->chunks, &h->partial, &h->itemflags, &h->scratch, &h->pairs_out, &h->stats};
@@ -621,6 +749,38 @@ int vbhem_estep_hyp(vbhem_base_t *h, int K, const int32_t *Sr, int maxSr, const 
   int rc = check_common(h, a, true);
   if (rc) return rc;
   return estep_host(h, a, L_elbo, zhat, stats, pre);
+}
+
+int vbhem_estep_stream(vbhem_base_t *h, const int32_t *Sb, const double *prior, const double *A, const double *mu,
+                       const double *cov, const double *Ntilde, int nslices, int K, const int32_t *Sr, int maxSr,
+                       const int32_t *group, int ngroups, int tau, const double *logPi, const double *logA,
+                       const double *m, const double *vW, const double *cterm, const double *logOmega, double *L_elbo,
+                       double *zhat, double *stats) {
+  CentreArgs a{};
+  a.K = K; a.maxSr = maxSr; a.ngroups = ngroups; a.tau = tau; a.Sr = Sr; a.group = group;
+  a.logPi = logPi; a.logA = logA; a.m = m; a.vW = vW; a.cterm = cterm; a.logOmega = logOmega; a.hyp = false;
+  int rc = check_common(h, a, true);
+  if (rc) return rc;
+  StreamIO io{Sb, prior, A, mu, cov, Ntilde, nullptr, nullptr, nslices};
+  rc = check_stream_base(h, io);
+  if (rc) return rc;
+  return estep_host(h, a, L_elbo, zhat, stats, nullptr, &io);
+}
+
+int vbhem_estep_hyp_stream(vbhem_base_t *h, const int32_t *Sb, const double *prior, const double *A, const double *mu,
+                           const double *cov, const double *Ntilde, int nslices, int K, const int32_t *Sr, int maxSr,
+                           const int32_t *group, int ngroups, int tau, const double *alpha, const double *eta,
+                           const double *epsilon, const double *m, const double *W, const double *v,
+                           const double *lambda, double *L_elbo, double *zhat, double *stats, double *pre) {
+  CentreArgs a{};
+  a.K = K; a.maxSr = maxSr; a.ngroups = ngroups; a.tau = tau; a.Sr = Sr; a.group = group;
+  a.alpha = alpha; a.eta = eta; a.epsilon = epsilon; a.m = m; a.W = W; a.v = v; a.lambda = lambda; a.hyp = true;
+  int rc = check_common(h, a, true);
+  if (rc) return rc;
+  StreamIO io{Sb, prior, A, mu, cov, Ntilde, nullptr, nullptr, nslices};
+  rc = check_stream_base(h, io);
+  if (rc) return rc;
+  return estep_host(h, a, L_elbo, zhat, stats, pre, &io);
 }
 
 int vbhem_estep_dev(vbhem_base_t *h, int K, const int32_t *Sr, int maxSr, const int32_t *group, int ngroups, int tau,

@@ -78,11 +78,13 @@ int launch_general(const BaseView &B, const CentreView &C, int T, const PairWork
 size_t general_scratch_per_warp(int maxSb, int maxSr, int d, int dd, int T);
 
 bool lattice_supported(const BaseView &B, const CentreView &C, int T, bool need_forward);
+// bases [i0, i0 + n) only (n < 0: to the end); L_elbo keeps its leading dimension B.N
 int launch_lattice_bwd(const BaseView &B, const CentreView &C, int T, double *L_elbo, Fallback fb,
-                       cudaStream_t st);
+                       cudaStream_t st, int i0 = 0, int n = -1);
 int launch_lattice_full(const BaseView &B, const CentreView &C, int T, const PairWork &W, const PairOut &O,
                         Fallback fb, cudaStream_t st);
 int lattice_rec_stride(int d, int dd);
+int lattice_bwd_wave();   // bases one full wave of the first-pass grid takes
 
 // aux kernels (vbhem_aux.cu)
 int zhat_blocks(int N);
@@ -91,11 +93,15 @@ int launch_prepass(int K, int maxSr, int d, int covmode, const int *Sr, const in
                    const double *lambda, double *logOmega, double *logPi, double *logA, double *logLam, double *cterm,
                    double *vW, cudaStream_t st);
 int launch_build_records(const CentreView &C, int d, int dd, double *rec, cudaStream_t st);
-int launch_sanitize_base(BaseView B, double *prior, double *A, double *mu, double *cov, cudaStream_t st);
+int launch_sanitize_base(BaseView B, double *prior, double *A, double *mu, double *cov, cudaStream_t st, int i0 = 0,
+                         int n = -1);
 // zhat, Nj, lb (fixed-order sums) and the per-block counts of pairs with Z > 1e-8
+// blocks [blk0, blk0 + nblk) of zhat_blocks(N) (nblk < 0: all); the fixed-order sums over all blocks run when
+// `reduce` is set (the last slice of a streamed E-step)
 int launch_zhat(int N, int K, int ngroups, const int *gstart, const double *L_elbo, const double *logOmega,
                 const double *Ntilde, double *zhat, double *Nj_part, int *cnt, double *lb_part, double *Nj, double *lb,
-                cudaStream_t st);
+                cudaStream_t st, int blk0 = 0, int nblk = -1, bool reduce = true);
+int zhat_block_size();
 // deterministic (centre-major, base-ascending) list of those pairs, cut in chunks of chunk_len
 int launch_list_scan(int N, int K, int chunk_len, const int *cnt, int *offs, int *segcnt, int *seg_start,
                      int *chunk_start, int *totals, cudaStream_t st);

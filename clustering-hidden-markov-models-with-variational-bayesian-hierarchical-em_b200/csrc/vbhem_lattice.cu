@@ -379,7 +379,7 @@ __device__ __forceinline__ void terminate_n(const Frag (&G)[NP], const Frag (&ex
 
 template <int D, bool FULL>
 __global__ void __launch_bounds__(kBwdWarps * 32, VB_BWD_MINB)
-k_lattice_bwd(BaseView B, CentreView C, int T, int kc, double *L_elbo, Fallback fb) {
+k_lattice_bwd(BaseView B, CentreView C, int T, int kc, double *L_elbo, Fallback fb, int i0, int i1) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
   const int warp = threadIdx.x >> 5;
@@ -394,7 +394,7 @@ k_lattice_bwd(BaseView B, CentreView C, int T, int kc, double *L_elbo, Fallback 
   for (int x = threadIdx.x; x < nj * rs; x += blockDim.x) recs[x] = C.rec[(size_t)j0 * rs + x];
   __syncthreads();
 
-  for (int i = blockIdx.x * kBwdWarps + warp; i < B.N; i += gridDim.x * kBwdWarps) {
+  for (int i = i0 + blockIdx.x * kBwdWarps + warp; i < i1; i += gridDim.x * kBwdWarps) {
     BaseConst<D, FULL> b;
     load_base(b, B, i, g, q);
     const bool base_chk = base_bad(b.Ab, b.prior);
@@ -653,6 +653,8 @@ int sm_count() {
 
 int lattice_rec_stride(int d, int dd) { return 80 + 8 * d + 8 * dd; }
 
+int lattice_bwd_wave() { return VB_BWD_MINB * sm_count() * kBwdWarps; }
+
 bool lattice_supported(const BaseView &B, const CentreView &C, int T, bool need_forward) {
   if (B.maxSb > kS8 || C.maxSr > kS8 || B.d < 1 || B.d > 3 || T < 1) return false;
   if (need_forward && full_smem_per_warp(T) > kSmemBudget) return false;
@@ -660,19 +662,21 @@ bool lattice_supported(const BaseView &B, const CentreView &C, int T, bool need_
 }
 
 int launch_lattice_bwd(const BaseView &B, const CentreView &C, int T, double *L_elbo, Fallback fb,
-                       cudaStream_t st) {
+                       cudaStream_t st, int i0, int n) {
+  if (n < 0) n = B.N - i0;
+  if (n <= 0) return 0;
   const int rs = C.rec_stride;
   int kc = (int)((VB_KC_BYTES) / (sizeof(double) * rs));
   if (kc > C.K) kc = C.K;
   const size_t smem = sizeof(double) * ((size_t)kc * rs + TabFirst::kDoubles);
   const int ny = (C.K + kc - 1) / kc;
-  int nx = (B.N + kBwdWarps - 1) / kBwdWarps;
+  int nx = (n + kBwdWarps - 1) / kBwdWarps;
   const int cap = VB_BWD_MINB * sm_count();
   if (nx > cap) nx = cap;
   return dispatch(B.d, B.covmode, [&](auto Dc, auto Fc) {
     auto kern = k_lattice_bwd<decltype(Dc)::value, decltype(Fc)::value>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<dim3(nx, ny), kBwdWarps * 32, smem, st>>>(B, C, T, kc, L_elbo, fb);
+    kern<<<dim3(nx, ny), kBwdWarps * 32, smem, st>>>(B, C, T, kc, L_elbo, fb, i0, i0 + n);
     return 1;
   });
 }

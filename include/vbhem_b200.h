@@ -135,6 +135,25 @@ int vbhem_estep_hyp(vbhem_base_t *base, int K, const int32_t *Sr, int maxSr, con
                     const double *W, const double *v, const double *lambda,
                     double *L_elbo, double *zhat, double *stats, double *pre);
 
+/* Streamed variants for a base set that lives in HOST memory (a MEX call that has no resident handle
+ * yet, or a base set that changes every call): the base arrays of vbhem_pack_base are uploaded in
+ * `nslices` slices on a copy stream while earlier slices already run, and the L_elbo / zhat rows of
+ * finished slices are copied back on a third stream, so host<->device transfers hide behind the
+ * kernels.  Results are bit-identical to vbhem_repack_base + vbhem_estep[_hyp]; afterwards the handle
+ * holds the new base set.  The shape (N, maxSb, d, covmode) is the handle's.  Pinned host buffers are
+ * needed for the copies to overlap (pageable memory works, serialised).  Ntilde may be NULL (= keep). */
+int vbhem_estep_stream(vbhem_base_t *base, const int32_t *Sb, const double *prior, const double *A, const double *mu,
+                       const double *cov, const double *Ntilde, int nslices, int K, const int32_t *Sr, int maxSr,
+                       const int32_t *group, int ngroups, int tau, const double *logPi, const double *logA,
+                       const double *m, const double *vW, const double *cterm, const double *logOmega, double *L_elbo,
+                       double *zhat, double *stats);
+int vbhem_estep_hyp_stream(vbhem_base_t *base, const int32_t *Sb, const double *prior, const double *A,
+                           const double *mu, const double *cov, const double *Ntilde, int nslices, int K,
+                           const int32_t *Sr, int maxSr, const int32_t *group, int ngroups, int tau,
+                           const double *alpha, const double *eta, const double *epsilon, const double *m,
+                           const double *W, const double *v, const double *lambda, double *L_elbo, double *zhat,
+                           double *stats, double *pre);
+
 /* Device-resident variants for multi-GPU hosts: identical to vbhem_estep /
  * vbhem_estep_hyp, but `stats_dev` is a DEVICE pointer (e.g. a torch tensor the
  * caller then all-reduces with NCCL) and nothing is copied back; the work is

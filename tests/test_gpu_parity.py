@@ -281,3 +281,32 @@ def test_repack_same_shape():
         bs.repack(base2)
         got = bs.estep_pairs(cen, 4)
     assert_pairs_close(got, oracle_pairs(base2, cen, 4), rtol=RTOL)
+
+
+@pytest.mark.parametrize("nslices", [1, 3, 8])
+def test_streamed_estep_is_bit_identical_to_resident(nslices):
+    """vbhem_estep_hyp_stream: the base set arrives from host memory in slices (multiples of the
+    256-base responsibility block) while earlier slices compute; every result must be bit-identical
+    to vbhem_repack_base + vbhem_estep_hyp, and match the oracle."""
+    base, hyp, cen = make_case(N=1500, K=5, Sb=4, Sr=4, d=2, covmode="full", ragged=True, seed=91, Nv=30.0)
+    other, _, _ = make_case(N=1500, K=5, Sb=4, Sr=4, d=2, covmode="full", ragged=True, seed=92, Nv=30.0)
+    with BaseSet(other) as bs:                      # the handle starts with a DIFFERENT base set of the same shape
+        bs.estep_hyp(hyp, 5)
+        got = bs.estep_hyp(hyp, 5, stream_base=base, nslices=nslices)
+        again = bs.estep_hyp(hyp, 5)                # the streamed set is now resident
+    with BaseSet(base) as bs:
+        ref = bs.estep_hyp(hyp, 5)
+    for k in ("L_elbo", "zhat", "buf"):
+        assert np.array_equal(got[k], ref[k]), k
+        assert np.array_equal(again[k], ref[k]), k
+    check_fused(got, oracle_fused(base, cen, 5), 1500)
+
+
+def test_streamed_estep_general_kernel_shapes():
+    """Shapes the lattice kernel does not take (here 10 base states) go through upload + resident path."""
+    base, hyp, cen = make_case(N=40, K=3, Sb=10, Sr=3, d=2, covmode="full", ragged=True, seed=93, Nv=20.0)
+    with BaseSet(base) as bs:
+        ref = bs.estep_hyp(hyp, 4)
+        got = bs.estep_hyp(hyp, 4, stream_base=base, nslices=4)
+    for k in ("L_elbo", "zhat", "buf"):
+        assert np.array_equal(got[k], ref[k]), k
