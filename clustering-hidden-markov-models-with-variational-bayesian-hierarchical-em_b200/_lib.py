@@ -44,6 +44,13 @@ SIGNATURES = {
     "vbhem_estep_hyp_dev": (C.c_int, [vp, C.c_int, ip, C.c_int, ip, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, dp,
                                       vp, dp]),
     "vbhem_fetch": (C.c_int, [vp, dp, dp]),
+    "vbhem_em_begin": (C.c_int, [vp, C.c_int, ip, C.c_int, ip, C.c_int, C.c_double, C.c_double, C.c_double,
+                                 C.c_double, C.c_double, dp, dp, C.c_int, dp, dp, dp, dp, dp, dp, dp]),
+    "vbhem_em_estep": (C.c_int, [vp, C.c_int, vp]),
+    "vbhem_em_lower_bound": (C.c_int, [vp, vp, dp]),
+    "vbhem_em_mstep": (C.c_int, [vp, vp]),
+    "vbhem_em_fetch": (C.c_int, [vp, dp, dp, dp, dp, dp, dp, dp]),
+    "vbhem_em_run": (C.c_int, [vp, C.c_int, C.c_int, C.c_double, dp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "vbhem_finalize_stats": (C.c_int, [vp, C.c_int, ip, C.c_int, C.c_int, dp]),
     "vbhem_finalize_stats_dev": (C.c_int, [vp, C.c_int, ip, C.c_int, C.c_int, vp]),
     "vbhem_set_profile": (C.c_int, [vp, C.c_int]),

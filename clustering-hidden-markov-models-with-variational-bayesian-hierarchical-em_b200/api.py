@@ -182,6 +182,60 @@ class BaseSet:
         out["logLambdaTilde"] = pre[o:o + r * K].reshape(K, r).copy()
         return out
 
+    # -- device-resident EM run (vbhem_em_*) ---------------------------------
+    def em_begin(self, hyp: dict, opt: dict, group=None):
+        """Upload the prior (opt: alpha0, eta0, epsilon0, lambda0, v0, m0, W0) and the initial centre
+        hyper-parameters (natural layout, as for ``estep_hyp``); they then stay in HBM between iterations."""
+        c = np.ascontiguousarray
+        f64 = lambda a: c(a, dtype=np.float64)
+        K, r = hyp["eta"].shape
+        self._em = dict(K=K, r=r, Sr=c(hyp.get("Sr", np.full(K, r)), dtype=np.int32),
+                        grp=None if group is None else c(group, dtype=np.int32))
+        ng = int(self._em["grp"].max()) + 1 if group is not None else 1
+        self._em["ng"] = ng
+        full = self.covmode == 1
+        W = np.asarray(hyp["W"], dtype=np.float64)
+        Wp = c(np.transpose(W, (0, 1, 3, 2))) if full else c(W)
+        eps = c(np.transpose(hyp["epsilon"], (0, 2, 1)), dtype=np.float64)
+        m0 = f64(np.asarray(opt["m0"], float).reshape(self.d))
+        W0 = f64(np.atleast_1d(np.asarray(opt["W0"], float)))
+        al, et, m, v, lam = f64(hyp["alpha"]), f64(hyp["eta"]), f64(hyp["m"]), f64(hyp["v"]), f64(hyp["lam"])
+        check(lib().vbhem_em_begin(self._h, K, _i(self._em["Sr"]), r, _i(self._em["grp"]), ng,
+                                   float(opt["alpha0"]), float(opt["eta0"]), float(opt["epsilon0"]),
+                                   float(opt["lambda0"]), float(opt["v0"]), _d(m0), _d(W0), int(W0.size),
+                                   _d(al), _d(et), _d(eps), _d(m), _d(Wp), _d(v), _d(lam)))
+
+    def em_estep(self, tau: int, stats_dev: int | None = None):
+        check(lib().vbhem_em_estep(self._h, tau, C.c_void_p(stats_dev or 0)))
+
+    def em_lower_bound(self, stats_dev: int | None = None) -> np.ndarray:
+        """[ngroups, 12]: Lt1..Lt10, LB, sum Nj."""
+        out = np.zeros((self._em["ng"], 12))
+        check(lib().vbhem_em_lower_bound(self._h, C.c_void_p(stats_dev or 0), _d(out)))
+        return out
+
+    def em_mstep(self, stats_dev: int | None = None):
+        check(lib().vbhem_em_mstep(self._h, C.c_void_p(stats_dev or 0)))
+
+    def em_fetch(self) -> dict:
+        """The resident hyper-parameters, natural layout."""
+        K, r, d, dd = self._em["K"], self._em["r"], self.d, self.dd
+        o = dict(alpha=np.zeros(K), eta=np.zeros((K, r)), eps=np.zeros((K, r, r)), m=np.zeros((K, r, d)),
+                 W=np.zeros((K, r, d, d) if self.covmode else (K, r, d)), v=np.zeros((K, r)), lam=np.zeros((K, r)))
+        check(lib().vbhem_em_fetch(self._h, _d(o["alpha"]), _d(o["eta"]), _d(o["eps"]), _d(o["m"]), _d(o["W"]),
+                                   _d(o["v"]), _d(o["lam"])))
+        return dict(alpha=o["alpha"], eta=o["eta"], epsilon=np.transpose(o["eps"], (0, 2, 1)).copy(), m=o["m"],
+                    W=np.transpose(o["W"], (0, 1, 3, 2)).copy() if self.covmode else o["W"], v=o["v"], lam=o["lam"],
+                    Sr=self._em["Sr"].copy())
+
+    def em_run(self, tau: int, max_iter: int = 200, min_diff: float = 1e-5) -> dict:
+        """vbhem_h3m_c_step_fc.m:115-433 entirely through the C ABI (one H3M, one GPU)."""
+        LogLs = np.zeros(max_iter + 2)
+        it, bad = C.c_int(), C.c_int()
+        check(lib().vbhem_em_run(self._h, tau, max_iter, min_diff, _d(LogLs), C.byref(it), C.byref(bad)))
+        n = it.value + (1 if bad.value else 0)
+        return dict(LogLs=LogLs[:n].copy(), iters=it.value, unstable=bool(bad.value), hyp=self.em_fetch())
+
     def finalize(self, buf: np.ndarray, Sr, r: int, ng: int = 1) -> dict:
         """vbhem_compute_Statistics.m:57-82 on a raw stats buffer (e.g. after an all-reduce)."""
         Sr = np.ascontiguousarray(Sr, dtype=np.int32)

@@ -6,6 +6,7 @@
 #include "../../include/vbhem_b200.h"
 #include "vbhem_internal.cuh"
 
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -73,6 +74,16 @@ struct vbhem_base {
   // streamed E-step (base set in host memory): copy-in / copy-out streams and per-slice events
   cudaStream_t cin = nullptr, cout = nullptr;
   std::vector<cudaEvent_t> slice_ev;
+  // device-resident EM run (vbhem_em_*): the hyper-parameters live in hyp_d (layout of stage_centres)
+  // and em_m; em_prior = m0[d] | W0inv[d]; em_lb = [12 * ngroups] lower-bound terms
+  struct Em {
+    bool active = false;
+    int K = 0, maxSr = 0, ngroups = 1;
+    std::vector<int32_t> Sr, group;
+    double alpha0 = 0, eta0 = 0, epsilon0 = 0, lambda0 = 0, v0 = 0;
+    DevBuf m, prior, lb, stats;
+    double *h_lb = nullptr;   // pinned
+  } em;
   int *h_totals = nullptr;   // pinned
   bool profile = false;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -92,6 +103,7 @@ struct CentreArgs {
   // ... or hyper-parameters (vbhem_estep_hyp)
   const double *alpha, *eta, *epsilon, *W, *v, *lambda;
   bool hyp;
+  bool resident = false;   // hyp: the arrays are already in the handle (device-resident EM run)
 };
 
 // Host-resident base set and host result buffers of a streamed E-step (vbhem_estep*_stream).
@@ -112,7 +124,7 @@ int check_common(vbhem_base *h, const CentreArgs &a, bool need_omega) {
     if (a.Sr[j] < 1 || a.Sr[j] > a.maxSr)
       return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: Sr[%d]=%d outside 1..maxSr=%d", j, a.Sr[j], a.maxSr);
   if (a.hyp) {
-    if (!a.alpha || !a.eta || !a.epsilon || !a.m || !a.W || !a.v || !a.lambda)
+    if (!a.resident && (!a.alpha || !a.eta || !a.epsilon || !a.m || !a.W || !a.v || !a.lambda))
       return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: a centre hyper-parameter array is NULL");
     if (h->B.d > 8) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: device pre-pass supports d <= 8");
   } else {
@@ -168,7 +180,10 @@ int stage_centres(vbhem_base *h, const CentreArgs &a, CentreDev &cd, double *pre
   double *dCt = p; p += nr;
   double *dm = p; p += d * nr;
   double *dvW = p;
-  CU(cudaMemcpyAsync(dm, a.m, sizeof(double) * d * nr, cudaMemcpyHostToDevice, h->st));
+  if (a.hyp && a.resident)
+    CU(cudaMemcpyAsync(dm, h->em.m.p, sizeof(double) * d * nr, cudaMemcpyDeviceToDevice, h->st));
+  else
+    CU(cudaMemcpyAsync(dm, a.m, sizeof(double) * d * nr, cudaMemcpyHostToDevice, h->st));
   if (a.hyp) {
     const size_t th = nK + nr + nrr + dd * nr + nr + nr;
     CU(h->hyp_d.ensure(sizeof(double) * th));
@@ -179,12 +194,14 @@ int stage_centres(vbhem_base *h, const CentreArgs &a, CentreDev &cd, double *pre
     double *hW = q; q += dd * nr;
     double *hv = q; q += nr;
     double *hl = q;
-    CU(cudaMemcpyAsync(hal, a.alpha, sizeof(double) * nK, cudaMemcpyHostToDevice, h->st));
-    CU(cudaMemcpyAsync(het, a.eta, sizeof(double) * nr, cudaMemcpyHostToDevice, h->st));
-    CU(cudaMemcpyAsync(hep, a.epsilon, sizeof(double) * nrr, cudaMemcpyHostToDevice, h->st));
-    CU(cudaMemcpyAsync(hW, a.W, sizeof(double) * dd * nr, cudaMemcpyHostToDevice, h->st));
-    CU(cudaMemcpyAsync(hv, a.v, sizeof(double) * nr, cudaMemcpyHostToDevice, h->st));
-    CU(cudaMemcpyAsync(hl, a.lambda, sizeof(double) * nr, cudaMemcpyHostToDevice, h->st));
+    if (!a.resident) {
+      CU(cudaMemcpyAsync(hal, a.alpha, sizeof(double) * nK, cudaMemcpyHostToDevice, h->st));
+      CU(cudaMemcpyAsync(het, a.eta, sizeof(double) * nr, cudaMemcpyHostToDevice, h->st));
+      CU(cudaMemcpyAsync(hep, a.epsilon, sizeof(double) * nrr, cudaMemcpyHostToDevice, h->st));
+      CU(cudaMemcpyAsync(hW, a.W, sizeof(double) * dd * nr, cudaMemcpyHostToDevice, h->st));
+      CU(cudaMemcpyAsync(hv, a.v, sizeof(double) * nr, cudaMemcpyHostToDevice, h->st));
+      CU(cudaMemcpyAsync(hl, a.lambda, sizeof(double) * nr, cudaMemcpyHostToDevice, h->st));
+    }
     launches += launch_prepass(K, r, d, h->B.covmode, dSr, dgs, a.ngroups, hal, het, hep, hW, hv, hl, dOm, dPi, dA,
                                dLam, dCt, dvW, h->st);
     if (pre_host)   // logOmega | logPi | logA | logLambdaTilde are contiguous by construction
@@ -595,6 +612,8 @@ int vbhem_free_base(vbhem_base_t *h) {
   if (h->cin) { cudaStreamSynchronize(h->cin); cudaStreamDestroy(h->cin); }
   if (h->cout) { cudaStreamSynchronize(h->cout); cudaStreamDestroy(h->cout); }
   for (cudaEvent_t e : h->slice_ev) cudaEventDestroy(e);
+  h->em.m.release(); h->em.prior.release(); h->em.lb.release(); h->em.stats.release();
+  if (h->em.h_lb) cudaFreeHost(h->em.h_lb);
   DevBuf *all[] = {&h->bSb, &h->bprior, &h->bA, &h->bmu, &h->bcov, &h->bNt, &h->cen_i, &h->cen_d, &h->hyp_d, &h->rec,
                    &h->L, &h->z, &h->flags, &h->fbcount, &h->Njp, &h->lbp, &h->cnt, &h->offs, &h->segs, &h->items,
                    &h->chunks, &h->partial, &h->itemflags, &h->scratch, &h->pairs_out, &h->stats};
@@ -807,6 +826,181 @@ int vbhem_estep_hyp_dev(vbhem_base_t *h, int K, const int32_t *Sr, int maxSr, co
   if (!stats_dev) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: stats_dev is NULL");
   CU(cudaSetDevice(h->device));
   return estep_device(h, a, stats_dev, pre);
+}
+
+// ---- device-resident EM run -------------------------------------------------
+namespace {
+struct HypPtrs { double *alpha, *eta, *epsilon, *W, *v, *lambda; };
+HypPtrs carve_hyp(vbhem_base *h, int K, int r) {
+  const size_t nK = K, nr = (size_t)r * K, nrr = (size_t)r * r * K, dd = h->B.dd;
+  double *q = h->hyp_d.as<double>();
+  HypPtrs p;
+  p.alpha = q; q += nK;
+  p.eta = q; q += nr;
+  p.epsilon = q; q += nrr;
+  p.W = q; q += dd * nr;
+  p.v = q; q += nr;
+  p.lambda = q;
+  return p;
+}
+CentreArgs em_args(vbhem_base *h, int tau) {
+  CentreArgs a{};
+  a.K = h->em.K; a.maxSr = h->em.maxSr; a.ngroups = h->em.ngroups; a.tau = tau;
+  a.Sr = h->em.Sr.data(); a.group = h->em.group.empty() ? nullptr : h->em.group.data();
+  a.hyp = true; a.resident = true;
+  return a;
+}
+}  // namespace
+
+int vbhem_em_begin(vbhem_base_t *h, int K, const int32_t *Sr, int maxSr, const int32_t *group, int ngroups,
+                   double alpha0, double eta0, double epsilon0, double lambda0, double v0, const double *m0,
+                   const double *W0, int nW0, const double *alpha, const double *eta, const double *epsilon,
+                   const double *m, const double *W, const double *v, const double *lambda) {
+  CentreArgs a{};
+  a.K = K; a.maxSr = maxSr; a.ngroups = ngroups; a.tau = 1; a.Sr = Sr; a.group = group;
+  a.alpha = alpha; a.eta = eta; a.epsilon = epsilon; a.m = m; a.W = W; a.v = v; a.lambda = lambda; a.hyp = true;
+  int rc = check_common(h, a, true);
+  if (rc) return rc;
+  const int d = h->B.d, dd = h->B.dd;
+  if (!m0 || !W0 || (nW0 != 1 && nW0 != d))
+    return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: m0[d] and W0[1 or d] are required");
+  if (!(v0 > d - 1)) return fail(VBHEM_EINVAL, "v0 not large enough");   // vbhem_mstep_component.m:24-26
+  CU(cudaSetDevice(h->device));
+  auto &em = h->em;
+  em.K = K; em.maxSr = maxSr; em.ngroups = ngroups;
+  em.Sr.assign(Sr, Sr + K);
+  if (group) em.group.assign(group, group + K); else em.group.clear();
+  em.alpha0 = alpha0; em.eta0 = eta0; em.epsilon0 = epsilon0; em.lambda0 = lambda0; em.v0 = v0;
+  const size_t nK = K, nr = (size_t)maxSr * K, nrr = (size_t)maxSr * maxSr * K;
+  CU(h->hyp_d.ensure(sizeof(double) * (nK + nr + nrr + dd * nr + nr + nr)));
+  CU(em.m.ensure(sizeof(double) * d * nr));
+  CU(em.prior.ensure(sizeof(double) * 2 * d));
+  CU(em.lb.ensure(sizeof(double) * 12 * ngroups));
+  CU(em.stats.ensure(sizeof(double) * vbhem_stats_size(K, maxSr, d, h->B.covmode, ngroups)));
+  if (!em.h_lb) CU(cudaMallocHost(&em.h_lb, sizeof(double) * 12 * 4096));
+  if (ngroups > 4096) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: at most 4096 groups in a device EM run");
+  HypPtrs p = carve_hyp(h, K, maxSr);
+  CU(cudaMemcpyAsync(p.alpha, alpha, sizeof(double) * nK, cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(p.eta, eta, sizeof(double) * nr, cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(p.epsilon, epsilon, sizeof(double) * nrr, cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(p.W, W, sizeof(double) * dd * nr, cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(p.v, v, sizeof(double) * nr, cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(p.lambda, lambda, sizeof(double) * nr, cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(em.m.p, m, sizeof(double) * d * nr, cudaMemcpyHostToDevice, h->st));
+  std::vector<double> pr(2 * d);
+  for (int q = 0; q < d; q++) { pr[q] = m0[q]; pr[d + q] = 1.0 / W0[nW0 == 1 ? 0 : q]; }
+  CU(cudaMemcpyAsync(em.prior.p, pr.data(), sizeof(double) * 2 * d, cudaMemcpyHostToDevice, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  em.active = true;
+  return VBHEM_OK;
+}
+
+int vbhem_em_estep(vbhem_base_t *h, int tau, double *stats_dev) {
+  if (!h || !h->em.active) return fail(VBHEM_EINVAL, "vbhem_em_begin has not been called on this handle");
+  CentreArgs a = em_args(h, tau);
+  int rc = check_common(h, a, true);
+  if (rc) return rc;
+  CU(cudaSetDevice(h->device));
+  return estep_device(h, a, stats_dev ? stats_dev : h->em.stats.as<double>(), nullptr);
+}
+
+namespace {
+// Views of the EM state and of a statistics buffer, shared by the lower bound and the M-step.
+struct EmCtx { EmView E; StatsPtr S; HypPtrs p; const double *dOm, *dPi, *dA, *dLam; };
+EmCtx em_ctx(vbhem_base *h, double *st) {
+  auto &em = h->em;
+  const int K = em.K, r = em.maxSr, d = h->B.d, dd = h->B.dd, ng = em.ngroups;
+  EmCtx c;
+  c.S = carve_stats(st, K, r, d, dd, ng);
+  const int *dSr = h->cen_i.as<int>(), *dgs = dSr + K;           // staged by the E-step
+  c.p = carve_hyp(h, K, r);
+  EmView &E = c.E;
+  E = EmView{};
+  E.K = K; E.maxSr = r; E.d = d; E.covmode = h->B.covmode; E.ngroups = ng; E.Sr = dSr; E.gstart = dgs;
+  E.alpha0 = em.alpha0; E.eta0 = em.eta0; E.epsilon0 = em.epsilon0; E.lambda0 = em.lambda0; E.v0 = em.v0;
+  E.m0 = em.prior.as<double>(); E.W0inv = E.m0 + d;
+  E.alpha = c.p.alpha; E.eta = c.p.eta; E.epsilon = c.p.epsilon; E.m = em.m.as<double>(); E.W = c.p.W;
+  E.v = c.p.v; E.lambda = c.p.lambda;
+  // pre-pass results of the E-step that produced these statistics (layout of stage_centres)
+  const size_t nK = K, nr = (size_t)r * K, nrr = (size_t)r * r * K;
+  c.dOm = h->cen_d.as<double>(); c.dPi = c.dOm + nK; c.dA = c.dPi + nr; c.dLam = c.dA + nrr;
+  return c;
+}
+}  // namespace
+
+int vbhem_em_lower_bound(vbhem_base_t *h, double *stats_dev, double *lb_out) {
+  if (!h || !h->em.active) return fail(VBHEM_EINVAL, "vbhem_em_begin has not been called on this handle");
+  CU(cudaSetDevice(h->device));
+  auto &em = h->em;
+  EmCtx c = em_ctx(h, stats_dev ? stats_dev : em.stats.as<double>());
+  launch_finalize(em.K, em.maxSr, h->B.d, h->B.covmode, c.E.Sr, c.S.Nj, c.S.xi, c.S.pr, c.S.mu, c.S.Mu, h->st);
+  launch_lower_bound(c.E, c.S.Nj, c.S.lb, c.dOm, c.dPi, c.dA, c.dLam, em.lb.as<double>(), h->st);
+  CU(cudaMemcpyAsync(em.h_lb, em.lb.p, sizeof(double) * 12 * em.ngroups, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  CU(cudaGetLastError());
+  if (lb_out) memcpy(lb_out, em.h_lb, sizeof(double) * 12 * em.ngroups);
+  return VBHEM_OK;
+}
+
+int vbhem_em_mstep(vbhem_base_t *h, double *stats_dev) {
+  if (!h || !h->em.active) return fail(VBHEM_EINVAL, "vbhem_em_begin has not been called on this handle");
+  CU(cudaSetDevice(h->device));
+  auto &em = h->em;
+  EmCtx c = em_ctx(h, stats_dev ? stats_dev : em.stats.as<double>());
+  launch_mstep(c.E, c.S.Nj, c.S.nu1, c.S.xi, c.S.pr, c.S.mu, c.S.Mu, c.p.alpha, c.p.eta, c.p.epsilon,
+               em.m.as<double>(), c.p.W, c.p.v, c.p.lambda, h->st);
+  CU(cudaGetLastError());
+  return VBHEM_OK;
+}
+
+int vbhem_em_fetch(vbhem_base_t *h, double *alpha, double *eta, double *epsilon, double *m, double *W, double *v,
+                   double *lambda) {
+  if (!h || !h->em.active) return fail(VBHEM_EINVAL, "vbhem_em_begin has not been called on this handle");
+  CU(cudaSetDevice(h->device));
+  const int K = h->em.K, r = h->em.maxSr, d = h->B.d, dd = h->B.dd;
+  const size_t nK = K, nr = (size_t)r * K, nrr = (size_t)r * r * K;
+  HypPtrs p = carve_hyp(h, K, r);
+  if (alpha) CU(cudaMemcpyAsync(alpha, p.alpha, sizeof(double) * nK, cudaMemcpyDeviceToHost, h->st));
+  if (eta) CU(cudaMemcpyAsync(eta, p.eta, sizeof(double) * nr, cudaMemcpyDeviceToHost, h->st));
+  if (epsilon) CU(cudaMemcpyAsync(epsilon, p.epsilon, sizeof(double) * nrr, cudaMemcpyDeviceToHost, h->st));
+  if (m) CU(cudaMemcpyAsync(m, h->em.m.p, sizeof(double) * d * nr, cudaMemcpyDeviceToHost, h->st));
+  if (W) CU(cudaMemcpyAsync(W, p.W, sizeof(double) * dd * nr, cudaMemcpyDeviceToHost, h->st));
+  if (v) CU(cudaMemcpyAsync(v, p.v, sizeof(double) * nr, cudaMemcpyDeviceToHost, h->st));
+  if (lambda) CU(cudaMemcpyAsync(lambda, p.lambda, sizeof(double) * nr, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  return VBHEM_OK;
+}
+
+// vbhem_h3m_c_step_fc.m:115-433 on one GPU, one H3M: E-step, lower bound, relative-change test from the
+// third pass on, M-step (also after the breaking pass), NaN guard.
+int vbhem_em_run(vbhem_base_t *h, int tau, int max_iter, double min_diff, double *LogLs, int *iters, int *unstable) {
+  if (!h || !h->em.active) return fail(VBHEM_EINVAL, "vbhem_em_begin has not been called on this handle");
+  if (h->em.ngroups != 1) return fail(VBHEM_EINVAL, "vbhem_em_run drives one H3M; batch several with em_estep/em_mstep");
+  if (!LogLs || !iters) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: LogLs / iters is NULL");
+  double lastL = -1.79769313486231570e308, lb[12];
+  int it = 0, n = 0, bad = 0;
+  while (true) {
+    int rc = vbhem_em_estep(h, tau, nullptr);
+    if (rc) return rc;
+    rc = vbhem_em_lower_bound(h, nullptr, lb);      // of the hyper-parameters this E-step used
+    if (rc) return rc;
+    double L = lb[10];
+    bool do_break = false;
+    if (it > 1 && fabs((L - lastL) / lastL) <= min_diff) do_break = true;
+    if (it == max_iter) do_break = true;
+    if (L != L) { do_break = true; bad = 1; L = -INFINITY; }     // vbhem_h3m_c_step_fc.m:338-354
+    LogLs[n++] = L;
+    if (do_break && bad) break;                                  // keep the last stable hyper-parameters
+    rc = vbhem_em_mstep(h, nullptr);
+    if (rc) return rc;
+    it++;
+    lastL = L;
+    if (do_break) break;
+  }
+  CU(cudaStreamSynchronize(h->st));
+  *iters = it;
+  if (unstable) *unstable = bad;
+  return VBHEM_OK;
 }
 
 int vbhem_fetch(vbhem_base_t *h, double *L_elbo, double *zhat) {

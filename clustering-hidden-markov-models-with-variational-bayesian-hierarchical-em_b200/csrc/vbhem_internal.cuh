@@ -113,6 +113,24 @@ int launch_partial_reduce(int K, int per, const int *chunk_start, const double *
 int launch_finalize(int K, int maxSr, int d, int covmode, const int *Sr, double *Nj, double *S_xi, double *S_pr,
                     double *S_mu, double *S_Mu, cudaStream_t st);
 
+// Device-resident EM state (vbhem_em.cu): prior hyper-parameters, current centre hyper-parameters
+// (C-ABI layouts of vbhem_estep_hyp) and the softmax groups.
+struct EmView {
+  int K, maxSr, d, covmode, ngroups;
+  const int *Sr, *gstart;
+  double alpha0, eta0, epsilon0, lambda0, v0;
+  const double *m0;       // [d]
+  const double *W0inv;    // [d] diagonal of inv(W0)
+  const double *alpha, *eta, *epsilon, *m, *W, *v, *lambda;
+};
+// out[g][12]: Lt1..Lt10, LB, sum_j Nj of softmax group g (vbhemh3m_lb.m:64-186)
+int launch_lower_bound(const EmView &E, const double *Nj, const double *lbsum, const double *logOmega,
+                       const double *logPi, const double *logA, const double *logLam, double *out, cudaStream_t st);
+// vbhem_mstep_component.m:42-70 in place on the hyper-parameter arrays, from the normalised statistics
+int launch_mstep(const EmView &E, const double *Nj, const double *nu1, const double *xi, const double *pr,
+                 const double *ybar, const double *SC, double *alpha, double *eta, double *epsilon, double *m,
+                 double *W, double *v, double *lambda, cudaStream_t st);
+
 // fp64 peak micro-benchmark (vbhem_aux.cu): out[0] DMMA, out[1] DFMA TFLOP/s; returns 0 on success
 int measure_fp64_peak(double out[2]);
 

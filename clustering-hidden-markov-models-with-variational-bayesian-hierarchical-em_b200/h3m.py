@@ -125,8 +125,13 @@ def vbhemh3m_lb(Lt1, Lt7, Nj, pre: dict, hyp: dict, opt: dict, covmode: str = "f
     return float(LB), dict(Lt1=Lt1, Lt2=Lt2, Lt3=Lt3, Lt4=Lt4, Lt5=Lt5, Lt6=Lt6, Lt7=Lt7, Lt8=Lt8, Lt9=Lt9, Lt10=Lt10)
 
 
-def vbhem_h3m_c_step_fc(h3m_r: dict, base, vbhemopt: dict, covmode: str = "full", estep=None, verbose: int = 0):
+def vbhem_h3m_c_step_fc(h3m_r: dict, base, vbhemopt: dict, covmode: str = "full", estep=None, verbose: int = 0,
+                        device_loop: bool = False):
     """One EM run from the centre hyper-parameters ``h3m_r`` (vbhem_h3m_c_step_fc.m:115-433).
+
+    ``device_loop=True`` runs the whole loop through the C ABI (``vbhem_em_run``): lower bound and M-step on
+    the device, hyper-parameters resident in HBM; the default keeps them on the host (numpy), which is also
+    what a multi-GPU ``estep`` callback uses.
 
     ``base``: a ``BaseSet`` (device-resident base mixture).  ``estep(hyp, tau)`` may be supplied to run the
     E-step elsewhere (e.g. ``dist.ShardedEStep.estep_hyp`` on several GPUs); it must return the normalised
@@ -138,6 +143,15 @@ def vbhem_h3m_c_step_fc(h3m_r: dict, base, vbhemopt: dict, covmode: str = "full"
     hyp = {k: np.array(v, dtype=np.int32 if k == "Sr" else np.float64) for k, v in h3m_r.items()}
     K, S = hyp["eta"].shape
     hyp.setdefault("Sr", np.full(K, S, np.int32))
+    if device_loop:
+        assert estep is None, "device_loop drives the handle's own E-step"
+        t0 = time.perf_counter()
+        base.em_begin(hyp, opt)
+        out = base.em_run(tau, max_iter, min_diff)
+        dt = time.perf_counter() - t0
+        return dict(hyp=out["hyp"], LogLs=out["LogLs"], LL=out["LogLs"][-1], iters=out["iters"],
+                    unstable=out["unstable"], Nj=out["hyp"]["alpha"] - float(opt["alpha0"]),
+                    ms_per_iter=1e3 * dt / max(1, len(out["LogLs"])))
 
     def default_estep(h, t):
         out = base.estep_hyp(h, t, want_pairs=False)

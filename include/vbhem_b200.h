@@ -178,6 +178,34 @@ int vbhem_finalize_stats(vbhem_base_t *base, int K, const int32_t *Sr, int maxSr
 /* As vbhem_finalize_stats, on a DEVICE stats buffer, enqueued on the handle's stream. */
 int vbhem_finalize_stats_dev(vbhem_base_t *base, int K, const int32_t *Sr, int maxSr, int ngroups, double *stats_dev);
 
+/* ---- Device-resident EM run --------------------------------
+ * The rest of one VBHEM iteration -- lower bound (/root/reference/src/vbhem/vbhemh3m_lb.m:64-186) and M-step
+ * (/root/reference/src/vbhem/vbhem_mstep_component.m:42-70; alpha: vbhem_h3m_c_step_fc.m:396) -- on the
+ * device, with the centre hyper-parameters resident in the handle between iterations.
+ *   vbhem_em_begin       uploads the prior (alpha0, eta0, epsilon0, lambda0, v0, m0[d], W0[nW0 = 1 or d]) and
+ *                        the initial hyper-parameters (layouts of vbhem_estep_hyp); several H3Ms may be
+ *                        batched through group[] as in vbhem_estep.
+ *   vbhem_em_estep       fused E-step from the resident hyper-parameters; raw sums into stats_dev (DEVICE
+ *                        pointer, NULL = a buffer of the handle); returns without synchronising, so a
+ *                        multi-GPU caller can all-reduce stats_dev next.
+ *   vbhem_em_lower_bound normalises the statistics (vbhem_compute_Statistics.m:57-82) and evaluates, per
+ *                        group g, lb_out[12 g + 0..9] = Lt1..Lt10, [10] = LB, [11] = sum_j Nj (HOST).
+ *   vbhem_em_mstep       replaces the resident hyper-parameters by the M-step of those statistics.
+ *   vbhem_em_fetch       copies the resident hyper-parameters to HOST arrays (any may be NULL).
+ *   vbhem_em_run         the loop of vbhem_h3m_c_step_fc.m:115-433 for one H3M on one GPU: LogLs[] (room
+ *                        for max_iter + 2 values), *iters = M-steps taken, *unstable = NaN guard fired. */
+int vbhem_em_begin(vbhem_base_t *base, int K, const int32_t *Sr, int maxSr, const int32_t *group, int ngroups,
+                   double alpha0, double eta0, double epsilon0, double lambda0, double v0, const double *m0,
+                   const double *W0, int nW0, const double *alpha, const double *eta, const double *epsilon,
+                   const double *m, const double *W, const double *v, const double *lambda);
+int vbhem_em_estep(vbhem_base_t *base, int tau, double *stats_dev);
+int vbhem_em_lower_bound(vbhem_base_t *base, double *stats_dev, double *lb_out);
+int vbhem_em_mstep(vbhem_base_t *base, double *stats_dev);
+int vbhem_em_fetch(vbhem_base_t *base, double *alpha, double *eta, double *epsilon, double *m, double *W, double *v,
+                   double *lambda);
+int vbhem_em_run(vbhem_base_t *base, int tau, int max_iter, double min_diff, double *LogLs, int *iters,
+                 int *unstable);
+
 /* Phase timing of the handle's E-steps, for bench.py: when enabled, CUDA events are
  * recorded on the handle's stream around each phase and vbhem_last_timings() returns the
  * milliseconds of the last E-step:

@@ -101,3 +101,69 @@ def test_em_run_matches_oracle_em():
     for k in ("alpha", "eta", "epsilon", "lam", "v", "m", "W"):
         np.testing.assert_allclose(got["hyp"][k], want_hyp[k], rtol=1e-7, atol=1e-9 * np.abs(want_hyp[k]).max(),
                                    err_msg=k)
+
+
+@pytest.mark.gpu
+def test_device_em_run_matches_oracle_em():
+    """vbhem_em_run: E-step, lower bound, M-step and the convergence test through the C ABI with the
+    hyper-parameters resident in HBM, against the same loop built from the oracle."""
+    from vbhem_b200.api import BaseSet
+    base, _ = synth.make_base_set(120, S=3, d=2, C=3, covmode="full", seed=77, Nv=OPT["Nv"])
+    hyp = synth.init_centres_baseem(base, 3, 3, seed=77, opt=dict(synth.DEFAULT_OPT, Nv=OPT["Nv"]))
+    want_hyp, want_L = oracle_em(base, hyp, OPT)
+    with BaseSet(base) as bs:
+        bs.em_begin(hyp, OPT)
+        got = bs.em_run(OPT["tau"], OPT["max_iter"], OPT["minDiff"])
+    assert got["iters"] == len(want_L) and not got["unstable"]
+    np.testing.assert_allclose(got["LogLs"], want_L, rtol=1e-9)
+    for k in ("alpha", "eta", "epsilon", "lam", "v", "m", "W"):
+        np.testing.assert_allclose(got["hyp"][k], want_hyp[k], rtol=1e-7, atol=1e-9 * np.abs(want_hyp[k]).max(),
+                                   err_msg=k)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("covmode,d", [("full", 2), ("diag", 3), ("full", 3)])
+def test_device_lower_bound_and_mstep_match_host(covmode, d):
+    """One iteration, term by term: vbhem_em_lower_bound / vbhem_em_mstep against h3m.vbhemh3m_lb /
+    vbhem_mstep (numpy) fed with the same E-step, on ragged centres."""
+    from vbhem_b200.api import BaseSet
+    base, hyp, cen = make_case(N=90, K=4, Sb=4, Sr=4, d=d, covmode=covmode, ragged=True, seed=31, Nv=15.0)
+    opt = dict(OPT, m0=tuple([256.0, 192.0, 128.0][:d]), W0=0.005 if covmode == "full" else [0.005, 0.01, 0.02][:d])
+    with BaseSet(base) as bs:
+        out = bs.estep_hyp(hyp, 4, want_pairs=False)
+        fin = bs.finalize(out["buf"], hyp["Sr"], 4)
+        pre = dict(logOmega=out["logOmega"], logPi=out["logPi"], logA=out["logA"], logLambdaTilde=out["logLambdaTilde"])
+        bs.em_begin(hyp, opt)
+        bs.em_estep(4)
+        lb = bs.em_lower_bound()[0]
+        bs.em_mstep()
+        got = bs.em_fetch()
+    # the host formulas assume one state count per H3M; evaluate them centre by centre on the ragged set
+    want_terms = np.zeros(10)
+    K = len(hyp["Sr"])
+    for j in range(K):
+        s = int(hyp["Sr"][j])
+        hj = {k: np.asarray(hyp[k])[j:j + 1, :s] for k in ("eta", "v", "lam")}
+        hj.update(alpha=hyp["alpha"][j:j + 1], epsilon=hyp["epsilon"][j:j + 1, :s, :s], m=hyp["m"][j:j + 1, :s],
+                  W=hyp["W"][j:j + 1, :s])
+        pj = dict(logOmega=pre["logOmega"][j:j + 1], logPi=pre["logPi"][j:j + 1, :s], logA=pre["logA"][j:j + 1, :s, :s],
+                  logLambdaTilde=pre["logLambdaTilde"][j:j + 1, :s])
+        _, t = h3m.vbhemh3m_lb(0.0, 0.0, fin["Nj"][j:j + 1], pj, hj, opt, covmode)
+        want_terms += np.array([t[f"Lt{i}"] for i in range(1, 11)])
+    # terms that couple the centres of one H3M (Dirichlet over omega) are not additive: take them from the whole set
+    from scipy.special import gammaln
+    a0 = opt["alpha0"]
+    want_terms[5] = gammaln(K * a0) - K * gammaln(a0) + (a0 - 1) * pre["logOmega"].sum()
+    want_terms[7] = gammaln(hyp["alpha"].sum()) - gammaln(hyp["alpha"]).sum() + np.dot(hyp["alpha"] - 1, pre["logOmega"])
+    want_terms[0], want_terms[6] = fin["lb"][0], fin["lb"][1]
+    np.testing.assert_allclose(lb[:10], want_terms, rtol=1e-10, atol=1e-9)
+    want_LB = want_terms[:6].sum() - want_terms[6:].sum()
+    np.testing.assert_allclose(lb[10], want_LB, rtol=1e-11)
+    np.testing.assert_allclose(lb[11], fin["Nj"].sum(), rtol=1e-12)
+    new = h3m.vbhem_mstep(fin, opt, covmode)
+    for j in range(K):
+        s = int(hyp["Sr"][j])
+        np.testing.assert_allclose(got["alpha"][j], new["alpha"][j], rtol=1e-12)
+        for k in ("eta", "lam", "v", "m", "W"):
+            np.testing.assert_allclose(got[k][j, :s], new[k][j, :s], rtol=1e-10, atol=1e-14, err_msg=k)
+        np.testing.assert_allclose(got["epsilon"][j, :s, :s], new["epsilon"][j, :s, :s], rtol=1e-10, err_msg="epsilon")
