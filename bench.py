@@ -331,7 +331,7 @@ def main():
                                "host_mirror_ms = median iteration of h3m.vbhem_h3m_c_step_fc (statistics D2H, numpy "
                                "M-step and lower bound)")
 
-    # ---- strong scaling of the north-star size (100k bases in total)
+    # ---- strong scaling of the north-star size (100k bases in total): E-step and whole EM iterations
     strong = None
     if world > 1:
         nbs = a.bases // world
@@ -343,6 +343,23 @@ def main():
         s_ms, _, _, _, _ = timed_run(bs, a.steps, W)
         strong = dict(bases_total=nbs * world, ms_per_estep=s_ms / a.steps,
                       pairs_per_s=nbs * world * K * a.steps / (s_ms * 1e-3))
+        # device-resident EM iterations over the sharded set: E-step, NCCL all-reduce, lower bound + M-step on
+        # every rank (dist.ShardedEStep.em_run drives the same vbhem_em_* calls)
+        from vbhem_b200.dist import ShardedEStep
+        opt = dict(synth.DEFAULT_OPT, tau=tau, max_iter=6, minDiff=0.0)
+        check(L.vbhem_set_profile(bs._h, 0))
+        sh = ShardedEStep.__new__(ShardedEStep)
+        sh.dist, sh.group, sh.world, sh.torch, sh.device, sh.bs = dist, None, world, torch, local, bs
+        sh._compute = sh._finalize = None
+        sh.em_run({k: v for k, v in hyp.items()}, dict(opt, max_iter=1))      # warm-up
+        torch.cuda.synchronize()
+        dist.barrier()
+        emr = sh.em_run({k: v for k, v in hyp.items()}, opt)
+        tt = torch.tensor([emr["ms_per_iter"]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        strong["vbhem_iter_ms"] = float(tt.item())
+        strong["LL_last"] = float(emr["LogLs"][-1])
+        strong["iters"] = int(emr["iters"])
     bs.close()
 
     # ---- e2e through the host-buffer C ABI: pack (H2D) + E-step + results (D2H), every step

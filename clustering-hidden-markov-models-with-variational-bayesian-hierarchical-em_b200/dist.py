@@ -103,3 +103,41 @@ class ShardedEStep:
         if self.world > 1:
             self.dist.all_reduce(buf, op=self.dist.ReduceOp.SUM, group=self.group)
         return finalize(buf, extra)
+
+    # -- a whole EM run, hyper-parameters resident on every rank -------------
+    def em_run(self, hyp: dict, opt: dict, covmode: str = "full") -> dict:
+        """vbhem_h3m_c_step_fc.m:115-433 over the sharded base set: every rank keeps the centre hyper-parameters
+        in HBM (``vbhem_em_begin``), runs the fused E-step on its shard, all-reduces the raw statistics (the one
+        collective), and applies the identical lower bound + M-step on the device, so no parameters travel
+        between iterations.  CUDA path only."""
+        assert self.bs is not None, "em_run needs the CUDA library"
+        import time
+        torch, bs = self.torch, self.bs
+        tau, max_iter, min_diff = int(opt["tau"]), int(opt.get("max_iter", 200)), float(opt.get("minDiff", 1e-5))
+        K, r = hyp["eta"].shape
+        bs.em_begin(hyp, opt)
+        ns = bs.stats_size(K, r)
+        stats = torch.zeros(ns, dtype=torch.float64, device=f"cuda:{self.device}")
+        LogLs, lastL, it, unstable, times = [], -np.finfo(float).max, 0, False, []
+        while True:
+            t0 = time.perf_counter()
+            bs.em_estep(tau, stats.data_ptr())
+            if self.world > 1:
+                self.dist.all_reduce(stats, op=self.dist.ReduceOp.SUM, group=self.group)
+            L = float(bs.em_lower_bound(stats.data_ptr())[0, 10])
+            do_break = it > 1 and abs((L - lastL) / lastL) <= min_diff
+            do_break = do_break or it == max_iter
+            if np.isnan(L):
+                do_break, unstable, L = True, True, -np.inf
+            LogLs.append(L)
+            if do_break and unstable:
+                break
+            bs.em_mstep(stats.data_ptr())
+            it += 1
+            lastL = L
+            times.append(time.perf_counter() - t0)
+            if do_break:
+                break
+        bs.synchronize()
+        return dict(hyp=bs.em_fetch(), LogLs=np.array(LogLs), LL=LogLs[-1], iters=it, unstable=unstable,
+                    ms_per_iter=1e3 * float(np.median(times)) if times else float("nan"))

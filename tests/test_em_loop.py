@@ -167,3 +167,23 @@ def test_device_lower_bound_and_mstep_match_host(covmode, d):
         for k in ("eta", "lam", "v", "m", "W"):
             np.testing.assert_allclose(got[k][j, :s], new[k][j, :s], rtol=1e-10, atol=1e-14, err_msg=k)
         np.testing.assert_allclose(got["epsilon"][j, :s, :s], new["epsilon"][j, :s, :s], rtol=1e-10, err_msg="epsilon")
+
+
+@pytest.mark.gpu
+def test_sharded_device_em_run_world_1():
+    """dist.ShardedEStep.em_run (the multi-GPU loop: E-step on the shard, all-reduce, device lower bound and
+    M-step) on one rank equals vbhem_em_run."""
+    from vbhem_b200.api import BaseSet
+    from vbhem_b200.dist import ShardedEStep
+    base, _ = synth.make_base_set(120, S=3, d=2, C=3, covmode="full", seed=77, Nv=OPT["Nv"])
+    hyp = synth.init_centres_baseem(base, 3, 3, seed=77, opt=dict(synth.DEFAULT_OPT, Nv=OPT["Nv"]))
+    with BaseSet(base) as bs:
+        bs.em_begin(hyp, OPT)
+        want = bs.em_run(OPT["tau"], OPT["max_iter"], OPT["minDiff"])
+    sh = ShardedEStep(base, device=0)
+    got = sh.em_run(hyp, OPT)
+    sh.close()
+    assert got["iters"] == want["iters"]
+    assert np.array_equal(got["LogLs"], want["LogLs"])
+    for k in ("alpha", "eta", "epsilon", "lam", "v", "m", "W"):
+        assert np.array_equal(got["hyp"][k], want["hyp"][k]), k
