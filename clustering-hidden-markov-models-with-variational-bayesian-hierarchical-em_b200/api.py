@@ -74,7 +74,14 @@ class BaseSet:
         check(lib().vbhem_set_kernel(self._h, {"auto": 0, "general": 1}[which]))
 
     def set_stream(self, cuda_stream: int | None):
-        check(lib().vbhem_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+        """Run this handle's work on an existing CUDA stream (``torch.cuda.current_stream().cuda_stream``).
+        ``None`` = the handle's own stream.  ``0`` is torch's default stream, i.e. the legacy default stream,
+        which the C ABI takes as ``cudaStreamLegacy`` (NULL there means "own stream")."""
+        if cuda_stream is None:
+            handle = 0
+        else:
+            handle = cuda_stream if cuda_stream else 1          # (cudaStream_t)0x1 == cudaStreamLegacy
+        check(lib().vbhem_set_stream(self._h, C.c_void_p(handle)))
 
     def synchronize(self):
         check(lib().vbhem_synchronize(self._h))

@@ -78,7 +78,8 @@ int vbhem_repack_base(vbhem_base_t *base, const int32_t *Sb, const double *prior
                       const double *mu, const double *cov, const double *Ntilde);
 
 /* Run subsequent work of this handle on an existing CUDA stream (a cudaStream_t
- * passed as void*), e.g. torch's current stream.  NULL = the handle's own stream. */
+ * passed as void*), e.g. torch's current stream.  NULL = the handle's own (non-blocking)
+ * stream; to name the legacy default stream pass cudaStreamLegacy, not 0. */
 int vbhem_set_stream(vbhem_base_t *base, void *cuda_stream);
 int vbhem_synchronize(vbhem_base_t *base);
 

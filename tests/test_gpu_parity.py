@@ -310,3 +310,26 @@ def test_streamed_estep_general_kernel_shapes():
         got = bs.estep_hyp(hyp, 4, stream_base=base, nslices=4)
     for k in ("L_elbo", "zhat", "buf"):
         assert np.array_equal(got[k], ref[k]), k
+
+
+def test_set_stream_orders_with_torch_default_stream():
+    """A handle bound to torch's current (default) stream must be ordered with torch work on that stream:
+    the statistics buffer is consumed by a torch op right after vbhem_estep_hyp_dev without a synchronise."""
+    import ctypes as C
+    import torch
+    from vbhem_b200._lib import check, dp, ip, lib
+    base, hyp, cen = make_case(N=4000, K=6, Sb=4, Sr=4, d=2, covmode="full", ragged=False, seed=19, Nv=30.0)
+    with BaseSet(base) as bs:
+        want = bs.estep_hyp(hyp, 6, want_pairs=False)["buf"]
+        bs.set_stream(torch.cuda.current_stream().cuda_stream)
+        K, r = hyp["eta"].shape
+        c = np.ascontiguousarray
+        Sr = c(hyp["Sr"], dtype=np.int32)
+        H = [c(hyp["alpha"]), c(hyp["eta"]), c(np.transpose(hyp["epsilon"], (0, 2, 1))), c(hyp["m"]),
+             c(np.transpose(hyp["W"], (0, 1, 3, 2))), c(hyp["v"]), c(hyp["lam"])]
+        for _ in range(5):
+            stats = torch.full((bs.stats_size(K, r),), float("nan"), dtype=torch.float64, device="cuda")
+            check(lib().vbhem_estep_hyp_dev(bs._h, K, Sr.ctypes.data_as(ip), r, None, 1, 6,
+                                            *[h.ctypes.data_as(dp) for h in H], C.c_void_p(stats.data_ptr()), None))
+            got = (stats * 1.0).cpu().numpy()          # torch op on the same stream, no explicit synchronise
+            assert np.array_equal(got, want)
