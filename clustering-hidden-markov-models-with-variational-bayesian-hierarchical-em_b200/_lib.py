@@ -53,6 +53,14 @@ SIGNATURES = {
     "vbhem_em_run": (C.c_int, [vp, C.c_int, C.c_int, C.c_double, dp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "vbhem_finalize_stats": (C.c_int, [vp, C.c_int, ip, C.c_int, C.c_int, dp]),
     "vbhem_finalize_stats_dev": (C.c_int, [vp, C.c_int, ip, C.c_int, C.c_int, vp]),
+    "vbhmm_pack_data": (C.c_int, [C.c_int, C.c_int, C.c_int, ip, C.POINTER(C.c_longlong), dp, C.POINTER(vp)]),
+    "vbhmm_free_data": (C.c_int, [vp]),
+    "vbhmm_data_shape": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                   C.POINTER(C.c_longlong)]),
+    "vbhmm_fb": (C.c_int, [vp, C.c_int, dp, dp, dp, dp, dp, C.c_double, dp, dp, dp, dp, dp, dp]),
+    "vbhmm_fb_dev": (C.c_int, [vp, C.c_int, dp, dp, dp, dp, dp, C.c_double, dp, dp]),
+    "vbhmm_fb_fetch": (C.c_int, [vp, dp, dp, dp, dp]),
+    "vbhmm_fb_last_ms": (C.c_int, [vp, dp]),
     "vbhem_set_profile": (C.c_int, [vp, C.c_int]),
     "vbhem_last_timings": (C.c_int, [vp, dp]),
     "vbhem_measure_fp64_peak": (C.c_int, [C.c_int, dp]),

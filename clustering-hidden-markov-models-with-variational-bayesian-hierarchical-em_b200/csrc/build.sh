@@ -3,4 +3,4 @@
 set -e
 cd "$(dirname "$0")"
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -shared \
-     "$@" -o ../libvbhem_b200.so vbhem_capi.cu vbhem_general.cu vbhem_lattice.cu vbhem_aux.cu vbhem_em.cu
+     "$@" -o ../libvbhem_b200.so vbhem_capi.cu vbhem_general.cu vbhem_lattice.cu vbhem_aux.cu vbhem_em.cu vbhmm_fb.cu

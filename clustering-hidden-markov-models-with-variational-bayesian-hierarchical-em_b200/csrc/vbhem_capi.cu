@@ -31,6 +31,23 @@ int fail(int code, const char *fmt, ...) {
   return code;
 }
 
+}  // namespace
+
+// error sink shared with vbhmm_fb.cu (same thread-local message behind vbhem_last_error())
+namespace vbhem {
+int fail_fb(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+}  // namespace vbhem
+
+namespace {
+
 #define CU(x)                                                                                  \
   do {                                                                                         \
     cudaError_t e_ = (x);                                                                      \

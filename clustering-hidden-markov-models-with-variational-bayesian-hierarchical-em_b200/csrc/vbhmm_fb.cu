@@ -1,0 +1,565 @@
+// vbhmm_fb.cu -- the VB-HMM forward-backward pass of the toolbox's HMM learning (SURVEY.md 8f #3,
+// BASELINE.json configs[4]) on the device.
+//
+// Reference: /root/reference/src/hmm/vbhmm_fb.m:264-380 and its native twin
+// /root/reference/src/hmm/vbhmm_fb_mex.c:314-950, selected by vbhmm_fb.m:99-145:
+//   [logrho_Saved, gamma_all, xi_sum, phi_norm] =
+//       vbhmm_fb_mex(data, K, N, dim, maxT, m, W, v, beta, logLambdaTilde, const_denominator, t_pz1, t_tpztzt1)
+// Per sequence: Normal-Wishart expected emission log-densities (Bishop 10.64 / 10.46), max-shifted
+// emissions, scaled forward recursion, backward recursion, responsibilities gamma and summed pair
+// marginals xi, and phi_norm = sum_t log c_t + sum_t max_k logrho.
+//
+// This path is HBM-bound (about 3 flop per byte), unlike the VBHEM E-step.  Design:
+//   * one thread per sequence; the observations are repacked once into X[dim, N, maxT], so that every
+//     load and every store of a warp at time step t is one contiguous run of 32 x (dim or K) doubles;
+//   * the model (m, W, v, dim/beta, logLambdaTilde, p(z1), p(z_t | z_t-1)) travels as a by-value kernel
+//     parameter: it sits in the constant bank and every use is a DFMA operand, never a load;
+//   * the forward pass writes logrho and parks alpha_hat in the gamma output; the backward pass reads
+//     it back in place, recomputes the emissions of step t+1 from X (cheaper than reading logrho back)
+//     and the scale c_{t+1} from alpha_t (bit-identical to the forward value, so no scale array);
+//   * outputs beyond a sequence's own length are written as zeros by the same thread (no memset pass).
+#include "../../include/vbhem_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace vbhem {
+int fail_fb(int code, const char *fmt, ...);
+}
+
+namespace {
+
+using vbhem::fail_fb;
+
+#define CU(x)                                                                                                 \
+  do {                                                                                                        \
+    cudaError_t e_ = (x);                                                                                     \
+    if (e_ != cudaSuccess)                                                                                    \
+      return fail_fb(e_ == cudaErrorMemoryAllocation ? VBHEM_ENOMEM : VBHEM_ECUDA, "%s: %s (%s:%d)", #x,      \
+                     cudaGetErrorString(e_), __FILE__, __LINE__);                                             \
+  } while (0)
+
+constexpr int kFbThreads = 128;
+#ifndef VB_FB_MINB
+#define VB_FB_MINB 4
+#endif
+#ifndef VB_FB_BLOCKS
+#define VB_FB_BLOCKS 0     // > 0: cap the resident blocks per SM (L2 residency of the parked alpha_hat)
+#endif
+constexpr int kFbMaxK = 8, kFbMaxDim = 3;         // template instantiations; beyond: the generic kernel
+constexpr int kFbGenK = 32, kFbGenDim = 8;
+
+template <int K, int DIM>
+struct FbPar {
+  double m[K][DIM];          // m(:,k)
+  double W[K][DIM][DIM];     // W[k][i][j] = W(j,i,k): the MEX walks W sequentially (vbhmm_fb_mex.c:378-391)
+  double v[K], dob[K];       // v(k), dim / beta(k)
+  double lLT[K];             // logLambdaTilde(k)
+  double pz1[K];             // exp(logPiTilde)
+  double A[K][K];            // exp(logATilde)(from, to)
+  double cden;
+};
+
+// logrho(k) of one observation, in the reference's order of operations (vbhmm_fb_mex.c:334-458).
+template <int K, int DIM>
+__device__ __forceinline__ void emissions(const FbPar<K, DIM> &P, const double (&x)[DIM], double (&lr)[K]) {
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    double diff[DIM];
+#pragma unroll
+    for (int i = 0; i < DIM; i++) diff[i] = x[i] - P.m[k][i];
+    double mterm = 0.0;
+#pragma unroll
+    for (int i = 0; i < DIM; i++) {
+      double tmp = 0.0;
+#pragma unroll
+      for (int j = 0; j < DIM; j++) tmp += P.W[k][i][j] * diff[j];
+      mterm += tmp * diff[i];
+    }
+    const double delta = P.dob[k] + P.v[k] * mterm;
+    lr[k] = 0.5 * (P.lLT[k] - delta) - P.cden;
+  }
+}
+
+template <int K>
+__device__ __forceinline__ double shifted_exp(const double (&lr)[K], double (&p)[K]) {
+  double mx = lr[0];
+#pragma unroll
+  for (int k = 1; k < K; k++) mx = lr[k] > mx ? lr[k] : mx;
+#pragma unroll
+  for (int k = 0; k < K; k++) p[k] = exp(lr[k] - mx);
+  return mx;
+}
+
+// Delta(k) = (alpha A)(k) p(k) and its sum c: the forward step, also the backward pass's way of
+// getting c_{t+1} back (same inputs, same order => same bits).
+template <int K, int DIM>
+__device__ __forceinline__ double forward_step(const FbPar<K, DIM> &P, const double (&alpha)[K], const double (&p)[K],
+                                               double (&delta)[K]) {
+  double c = 0.0;
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    double tmp = 0.0;
+#pragma unroll
+    for (int j = 0; j < K; j++) tmp += alpha[j] * P.A[j][k];
+    delta[k] = tmp * p[k];
+    c += delta[k];
+  }
+  return c;
+}
+
+template <int K, int DIM>
+__global__ void __launch_bounds__(kFbThreads, VB_FB_MINB)
+k_fb(const __grid_constant__ FbPar<K, DIM> P, int N, int maxT, const int *__restrict__ Tn,
+     const double *__restrict__ X, double *__restrict__ logrho, double *__restrict__ gamma,
+     double *__restrict__ xi_sum, double *__restrict__ phi) {
+  const int n = blockIdx.x * kFbThreads + threadIdx.x;
+  if (n >= N) return;
+  const int T = Tn[n];
+  const size_t NK = (size_t)N * K, ND = (size_t)N * DIM;
+  const double *xp = X + (size_t)DIM * n;
+  double *lp = logrho + (size_t)K * n, *gp = gamma + (size_t)K * n;
+  double alpha[K], p[K], lr[K], x[DIM], xn[DIM];
+  double sumlogc = 0.0, summax = 0.0;
+
+  // ---- forward (vbhmm_fb.m:316-347).  The next observation is requested one step ahead; logrho is a
+  // streaming store (never read again here), alpha_hat a normal one (read back below, ideally from L2).
+#pragma unroll
+  for (int i = 0; i < DIM; i++) xn[i] = T > 0 ? xp[i] : 0.0;
+  for (int t = 0; t < T; t++) {
+#pragma unroll
+    for (int i = 0; i < DIM; i++) x[i] = xn[i];
+    if (t + 1 < T) {
+#pragma unroll
+      for (int i = 0; i < DIM; i++) xn[i] = xp[ND * (t + 1) + i];
+    }
+    emissions<K, DIM>(P, x, lr);
+#pragma unroll
+    for (int k = 0; k < K; k++) __stcs(lp + NK * t + k, lr[k]);
+    summax += shifted_exp<K>(lr, p);
+    double delta[K], c;
+    if (t == 0) {
+      c = 0.0;
+#pragma unroll
+      for (int k = 0; k < K; k++) { delta[k] = P.pz1[k] * p[k]; c += delta[k]; }
+    } else {
+      c = forward_step<K, DIM>(P, alpha, p, delta);
+    }
+    const double rc = 1.0 / c;
+#pragma unroll
+    for (int k = 0; k < K; k++) { alpha[k] = delta[k] * rc; gp[NK * t + k] = alpha[k]; }
+    sumlogc += log(c);
+  }
+  phi[n] = sumlogc + summax;
+  // zeros beyond the sequence's own length (the reference's outputs start as zeros)
+  for (int t = T; t < maxT; t++) {
+#pragma unroll
+    for (int k = 0; k < K; k++) { __stcs(lp + NK * t + k, 0.0); __stcs(gp + NK * t + k, 0.0); }
+  }
+
+  // ---- backward, responsibilities, summed pair marginals (vbhmm_fb.m:349-377).  The K x K accumulator of
+  // each thread lives in shared memory ([j][k][thread]: conflict-free), which keeps the register count low
+  // enough for three to four resident blocks per SM.
+  extern __shared__ double xis[];
+  double *xi = xis + threadIdx.x;
+  double beta[K], an[K];
+#pragma unroll
+  for (int j = 0; j < K; j++) {
+    beta[j] = 1.0;
+#pragma unroll
+    for (int k = 0; k < K; k++) xi[(j * K + k) * kFbThreads] = 0.0;
+  }
+  // gamma(:, T) = alpha(:, T) is already in place; x holds the last observation
+  if (T >= 2) {
+#pragma unroll
+    for (int k = 0; k < K; k++) an[k] = gp[NK * (T - 2) + k];
+  }
+  for (int t = T - 2; t >= 0; t--) {
+    // x = observation t+1 (from the previous iteration / the forward pass), alpha = alpha_hat(t)
+#pragma unroll
+    for (int k = 0; k < K; k++) alpha[k] = an[k];
+#pragma unroll
+    for (int i = 0; i < DIM; i++) xn[i] = xp[ND * t + i];             // observation t, used next iteration
+    if (t > 0) {
+#pragma unroll
+      for (int k = 0; k < K; k++) an[k] = gp[NK * (t - 1) + k];      // alpha_hat(t-1), parked by the forward pass
+    }
+    emissions<K, DIM>(P, x, lr);
+    shifted_exp<K>(lr, p);                                            // p(x_{t+1} | z) / max
+    double delta[K];
+    const double rc = 1.0 / forward_step<K, DIM>(P, alpha, p, delta);   // 1 / c(t+1)
+    double bpi[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) bpi[k] = beta[k] * p[k];
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+      double eta = 0.0;
+#pragma unroll
+      for (int k = 0; k < K; k++) eta += bpi[k] * P.A[j][k];
+      beta[j] = eta * rc;
+    }
+#pragma unroll
+    for (int k = 0; k < K; k++) __stcs(gp + NK * t + k, alpha[k] * beta[k]);
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+      const double aj = alpha[j] * rc;
+#pragma unroll
+      for (int k = 0; k < K; k++) xi[(j * K + k) * kFbThreads] += P.A[j][k] * (aj * bpi[k]);
+    }
+#pragma unroll
+    for (int i = 0; i < DIM; i++) x[i] = xn[i];
+  }
+  double *xo = xi_sum + (size_t)K * K * n;
+#pragma unroll
+  for (int k = 0; k < K; k++)
+#pragma unroll
+    for (int j = 0; j < K; j++) __stcs(xo + j + K * k, xi[(j * K + k) * kFbThreads]);
+}
+
+// Any K <= 32, dim <= 8: the same recursion with the model in global memory and local arrays.
+struct FbParGen { const double *m, *W, *v, *dob, *lLT, *pz1, *A; double cden; int K, dim; };
+
+__device__ double gen_emit(const FbParGen &P, const double *x, double *lr, double *p) {
+  const int K = P.K, dim = P.dim;
+  double mx = 0.0;
+  for (int k = 0; k < K; k++) {
+    double diff[kFbGenDim];
+    for (int i = 0; i < dim; i++) diff[i] = x[i] - P.m[i + dim * k];
+    double mterm = 0.0;
+    for (int i = 0; i < dim; i++) {
+      double tmp = 0.0;
+      for (int j = 0; j < dim; j++) tmp += P.W[j + dim * (i + dim * k)] * diff[j];
+      mterm += tmp * diff[i];
+    }
+    lr[k] = 0.5 * (P.lLT[k] - (P.dob[k] + P.v[k] * mterm)) - P.cden;
+    if (k == 0 || lr[k] > mx) mx = lr[k];
+  }
+  for (int k = 0; k < K; k++) p[k] = exp(lr[k] - mx);
+  return mx;
+}
+__device__ double gen_forward(const FbParGen &P, const double *alpha, const double *p, double *delta) {
+  double c = 0.0;
+  for (int k = 0; k < P.K; k++) {
+    double tmp = 0.0;
+    for (int j = 0; j < P.K; j++) tmp += alpha[j] * P.A[j + P.K * k];
+    delta[k] = tmp * p[k];
+    c += delta[k];
+  }
+  return c;
+}
+
+__global__ void __launch_bounds__(kFbThreads)
+k_fb_generic(FbParGen P, int N, int maxT, const int *__restrict__ Tn, const double *__restrict__ X,
+             double *__restrict__ logrho, double *__restrict__ gamma, double *__restrict__ xi_sum,
+             double *__restrict__ phi) {
+  const int n = blockIdx.x * kFbThreads + threadIdx.x;
+  if (n >= N) return;
+  const int K = P.K, dim = P.dim, T = Tn[n];
+  const size_t NK = (size_t)N * K, ND = (size_t)N * dim;
+  const double *xp = X + (size_t)dim * n;
+  double *lp = logrho + (size_t)K * n, *gp = gamma + (size_t)K * n, *xo = xi_sum + (size_t)K * K * n;
+  double alpha[kFbGenK], p[kFbGenK], lr[kFbGenK], delta[kFbGenK], beta[kFbGenK], bpi[kFbGenK], x[kFbGenDim];
+  double sumlogc = 0.0, summax = 0.0;
+  for (int t = 0; t < T; t++) {
+    for (int i = 0; i < dim; i++) x[i] = xp[ND * t + i];
+    summax += gen_emit(P, x, lr, p);
+    for (int k = 0; k < K; k++) lp[NK * t + k] = lr[k];
+    double c;
+    if (t == 0) { c = 0.0; for (int k = 0; k < K; k++) { delta[k] = P.pz1[k] * p[k]; c += delta[k]; } }
+    else c = gen_forward(P, alpha, p, delta);
+    const double rc = 1.0 / c;
+    for (int k = 0; k < K; k++) { alpha[k] = delta[k] * rc; gp[NK * t + k] = alpha[k]; }
+    sumlogc += log(c);
+  }
+  phi[n] = sumlogc + summax;
+  for (int t = T; t < maxT; t++)
+    for (int k = 0; k < K; k++) { lp[NK * t + k] = 0.0; gp[NK * t + k] = 0.0; }
+  for (int q = 0; q < K * K; q++) xo[q] = 0.0;
+  for (int k = 0; k < K; k++) beta[k] = 1.0;
+  for (int t = T - 2; t >= 0; t--) {
+    for (int i = 0; i < dim; i++) x[i] = xp[ND * (t + 1) + i];
+    gen_emit(P, x, lr, p);
+    for (int k = 0; k < K; k++) alpha[k] = gp[NK * t + k];
+    const double rc = 1.0 / gen_forward(P, alpha, p, delta);
+    for (int k = 0; k < K; k++) bpi[k] = beta[k] * p[k];
+    for (int j = 0; j < K; j++) {
+      double eta = 0.0;
+      for (int k = 0; k < K; k++) eta += bpi[k] * P.A[j + K * k];
+      delta[j] = eta * rc;
+    }
+    for (int k = 0; k < K; k++) { beta[k] = delta[k]; gp[NK * t + k] = alpha[k] * beta[k]; }
+    for (int k = 0; k < K; k++)
+      for (int j = 0; j < K; j++) xo[j + K * k] += P.A[j + K * k] * ((alpha[j] * rc) * bpi[k]);
+  }
+}
+
+// flat[offs[n] + t + d * T_n]  ->  X[d + dim * (n + N * t)]
+__global__ void k_repack(int N, int dim, int maxT, const int *Tn, const long long *offs, const double *flat,
+                         double *X) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int T = Tn[n];
+  const double *src = flat + offs[n];
+  for (int t = 0; t < maxT; t++)
+    for (int d = 0; d < dim; d++) X[d + (size_t)dim * (n + (size_t)N * t)] = t < T ? src[t + (size_t)d * T] : 0.0;
+}
+
+struct Buf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 8);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+
+}  // namespace
+
+struct vbhmm_data {
+  int device = 0, N = 0, dim = 0, maxT = 0;
+  long long total = 0;         // sum_n T_n
+  cudaStream_t st = nullptr;
+  Buf Tn, X, par, logrho, gamma, xi, phi;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  double last_ms = 0.0;
+  int lastK = 0;
+};
+
+namespace {
+
+template <int K, int DIM>
+int launch_fb_t(vbhmm_data *h, const double *m, const double *W, const double *v, const double *beta,
+                const double *lLT, double cden, const double *pz1, const double *A) {
+  FbPar<K, DIM> P;
+  for (int k = 0; k < K; k++) {
+    for (int i = 0; i < DIM; i++) {
+      P.m[k][i] = m[i + DIM * k];
+      for (int j = 0; j < DIM; j++) P.W[k][i][j] = W[j + DIM * (i + DIM * k)];
+    }
+    P.v[k] = v[k]; P.dob[k] = DIM / beta[k]; P.lLT[k] = lLT[k]; P.pz1[k] = pz1[k];
+    for (int j = 0; j < K; j++) P.A[k][j] = A[k + K * j];
+  }
+  P.cden = cden;
+  const int blocks = (h->N + kFbThreads - 1) / kFbThreads;
+  size_t smem = sizeof(double) * K * K * kFbThreads;
+#if VB_FB_BLOCKS > 0
+  if (smem < (size_t)(220 * 1024) / VB_FB_BLOCKS - 1024) smem = (size_t)(220 * 1024) / VB_FB_BLOCKS - 1024;
+#endif
+  cudaFuncSetAttribute(k_fb<K, DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_fb<K, DIM><<<blocks, kFbThreads, smem, h->st>>>(P, h->N, h->maxT, h->Tn.as<int>(), h->X.as<double>(),
+                                                 h->logrho.as<double>(), h->gamma.as<double>(), h->xi.as<double>(),
+                                                 h->phi.as<double>());
+  return 1;
+}
+
+template <int K>
+int launch_fb_k(vbhmm_data *h, const double *m, const double *W, const double *v, const double *beta,
+                const double *lLT, double cden, const double *pz1, const double *A) {
+  switch (h->dim) {
+    case 1: return launch_fb_t<K, 1>(h, m, W, v, beta, lLT, cden, pz1, A);
+    case 2: return launch_fb_t<K, 2>(h, m, W, v, beta, lLT, cden, pz1, A);
+    case 3: return launch_fb_t<K, 3>(h, m, W, v, beta, lLT, cden, pz1, A);
+  }
+  return 0;
+}
+
+int run_fb(vbhmm_data *h, int K, const double *m, const double *W, const double *v, const double *beta,
+           const double *lLT, double cden, const double *pz1, const double *A) {
+  const int N = h->N, dim = h->dim;
+  const size_t nkt = (size_t)K * N * (h->maxT > 0 ? h->maxT : 1);
+  CU(h->logrho.ensure(sizeof(double) * nkt));
+  CU(h->gamma.ensure(sizeof(double) * nkt));
+  CU(h->xi.ensure(sizeof(double) * (size_t)K * K * N));
+  CU(h->phi.ensure(sizeof(double) * (size_t)N));
+  CU(cudaEventRecord(h->ev[0], h->st));
+  int launched = 0;
+  if (K <= kFbMaxK && dim <= kFbMaxDim) {
+    switch (K) {
+      case 1: launched = launch_fb_k<1>(h, m, W, v, beta, lLT, cden, pz1, A); break;
+      case 2: launched = launch_fb_k<2>(h, m, W, v, beta, lLT, cden, pz1, A); break;
+      case 3: launched = launch_fb_k<3>(h, m, W, v, beta, lLT, cden, pz1, A); break;
+      case 4: launched = launch_fb_k<4>(h, m, W, v, beta, lLT, cden, pz1, A); break;
+      case 5: launched = launch_fb_k<5>(h, m, W, v, beta, lLT, cden, pz1, A); break;
+      case 6: launched = launch_fb_k<6>(h, m, W, v, beta, lLT, cden, pz1, A); break;
+      case 7: launched = launch_fb_k<7>(h, m, W, v, beta, lLT, cden, pz1, A); break;
+      case 8: launched = launch_fb_k<8>(h, m, W, v, beta, lLT, cden, pz1, A); break;
+    }
+  }
+  if (!launched) {
+    // model to HBM: m | W | v | dob | lLT | pz1 | A
+    const size_t nd = (size_t)dim * K + (size_t)dim * dim * K + 4 * (size_t)K + (size_t)K * K;
+    std::vector<double> hp(nd);
+    double *q = hp.data();
+    memcpy(q, m, sizeof(double) * dim * K); q += (size_t)dim * K;
+    memcpy(q, W, sizeof(double) * dim * dim * K); q += (size_t)dim * dim * K;
+    memcpy(q, v, sizeof(double) * K); q += K;
+    for (int k = 0; k < K; k++) q[k] = dim / beta[k];
+    q += K;
+    memcpy(q, lLT, sizeof(double) * K); q += K;
+    memcpy(q, pz1, sizeof(double) * K); q += K;
+    memcpy(q, A, sizeof(double) * K * K);
+    CU(h->par.ensure(sizeof(double) * nd));
+    CU(cudaMemcpyAsync(h->par.p, hp.data(), sizeof(double) * nd, cudaMemcpyHostToDevice, h->st));
+    CU(cudaStreamSynchronize(h->st));     // hp goes out of scope
+    FbParGen P;
+    const double *d = h->par.as<double>();
+    P.m = d; d += (size_t)dim * K;
+    P.W = d; d += (size_t)dim * dim * K;
+    P.v = d; d += K;
+    P.dob = d; d += K;
+    P.lLT = d; d += K;
+    P.pz1 = d; d += K;
+    P.A = d;
+    P.cden = cden; P.K = K; P.dim = dim;
+    k_fb_generic<<<(N + kFbThreads - 1) / kFbThreads, kFbThreads, 0, h->st>>>(
+        P, N, h->maxT, h->Tn.as<int>(), h->X.as<double>(), h->logrho.as<double>(), h->gamma.as<double>(),
+        h->xi.as<double>(), h->phi.as<double>());
+  }
+  CU(cudaEventRecord(h->ev[1], h->st));
+  CU(cudaGetLastError());
+  h->lastK = K;
+  return VBHEM_OK;
+}
+
+int check_model(vbhmm_data *h, int K, const double *m, const double *W, const double *v, const double *beta,
+                const double *lLT, const double *pz1, const double *A) {
+  if (!h) return fail_fb(VBHEM_EINVAL, "vbhmm_fb_mex:invalidinput: data handle is NULL");
+  if (K < 1 || K > kFbGenK) return fail_fb(VBHEM_EINVAL, "vbhmm_fb_mex:invalidinput: K must be 1..%d", kFbGenK);
+  if (!m || !W || !v || !beta || !lLT || !pz1 || !A)
+    return fail_fb(VBHEM_EINVAL, "vbhmm_fb_mex:invalidinput: a model array is NULL");
+  return VBHEM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vbhmm_pack_data(int device, int N, int dim, const int32_t *T, const long long *offs, const double *flat,
+                    vbhmm_data_t **out) {
+  if (!out) return fail_fb(VBHEM_EINVAL, "vbhmm_fb_mex:invalidinput: out is NULL");
+  *out = nullptr;
+  if (N < 1 || dim < 1 || dim > kFbGenDim)
+    return fail_fb(VBHEM_EINVAL, "vbhmm_fb_mex:invalidinput: N >= 1 and dim in 1..%d required", kFbGenDim);
+  if (!T || !offs || !flat) return fail_fb(VBHEM_EINVAL, "vbhmm_fb_mex:invalidinput: data is not a cell array");
+  int maxT = 0;
+  long long total = 0, span = 0;
+  for (int n = 0; n < N; n++) {
+    if (T[n] < 0) return fail_fb(VBHEM_EINVAL, "vbhmm_fb_mex:invalidinput: T[%d] < 0", n);
+    if (T[n] > maxT) maxT = T[n];
+    total += T[n];
+    const long long end = offs[n] + (long long)T[n] * dim;
+    if (offs[n] < 0) return fail_fb(VBHEM_EINVAL, "vbhmm_fb_mex:invalidinput: offs[%d] < 0", n);
+    if (end > span) span = end;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+    return fail_fb(VBHEM_ENODEVICE, "no CUDA device (this library has no CPU path)");
+  if (device < 0 || device >= ndev) return fail_fb(VBHEM_EINVAL, "device %d out of range (have %d)", device, ndev);
+  CU(cudaSetDevice(device));
+  vbhmm_data *h = new (std::nothrow) vbhmm_data;
+  if (!h) return fail_fb(VBHEM_ENOMEM, "out of host memory");
+  h->device = device; h->N = N; h->dim = dim; h->maxT = maxT; h->total = total;
+  Buf dflat, doffs;
+  auto bail = [&](int code) { dflat.release(); doffs.release(); vbhmm_free_data(h); return code; };
+#define CUB(x)                                                                                               \
+  do {                                                                                                       \
+    cudaError_t e_ = (x);                                                                                    \
+    if (e_ != cudaSuccess)                                                                                   \
+      return bail(fail_fb(e_ == cudaErrorMemoryAllocation ? VBHEM_ENOMEM : VBHEM_ECUDA, "%s: %s", #x,        \
+                          cudaGetErrorString(e_)));                                                          \
+  } while (0)
+  CUB(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+  CUB(cudaEventCreate(&h->ev[0]));
+  CUB(cudaEventCreate(&h->ev[1]));
+  CUB(h->Tn.ensure(sizeof(int) * (size_t)N));
+  CUB(h->X.ensure(sizeof(double) * (size_t)dim * N * (maxT > 0 ? maxT : 1)));
+  CUB(dflat.ensure(sizeof(double) * (size_t)(span > 0 ? span : 1)));
+  CUB(doffs.ensure(sizeof(long long) * (size_t)N));
+  CUB(cudaMemcpyAsync(h->Tn.p, T, sizeof(int) * (size_t)N, cudaMemcpyHostToDevice, h->st));
+  CUB(cudaMemcpyAsync(doffs.p, offs, sizeof(long long) * (size_t)N, cudaMemcpyHostToDevice, h->st));
+  if (span > 0) CUB(cudaMemcpyAsync(dflat.p, flat, sizeof(double) * (size_t)span, cudaMemcpyHostToDevice, h->st));
+  k_repack<<<(N + 127) / 128, 128, 0, h->st>>>(N, dim, maxT, h->Tn.as<int>(), doffs.as<long long>(),
+                                               dflat.as<double>(), h->X.as<double>());
+  CUB(cudaStreamSynchronize(h->st));
+  CUB(cudaGetLastError());
+#undef CUB
+  dflat.release();
+  doffs.release();
+  *out = h;
+  return VBHEM_OK;
+}
+
+int vbhmm_free_data(vbhmm_data_t *h) {
+  if (!h) return VBHEM_OK;
+  cudaSetDevice(h->device);
+  if (h->st) { cudaStreamSynchronize(h->st); cudaStreamDestroy(h->st); }
+  for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+  Buf *all[] = {&h->Tn, &h->X, &h->par, &h->logrho, &h->gamma, &h->xi, &h->phi};
+  for (Buf *b : all) b->release();
+  delete h;
+  return VBHEM_OK;
+}
+
+int vbhmm_data_shape(vbhmm_data_t *h, int *N, int *dim, int *maxT, long long *total) {
+  if (!h) return fail_fb(VBHEM_EINVAL, "vbhmm_fb_mex:invalidinput: data handle is NULL");
+  if (N) *N = h->N;
+  if (dim) *dim = h->dim;
+  if (maxT) *maxT = h->maxT;
+  if (total) *total = h->total;
+  return VBHEM_OK;
+}
+
+int vbhmm_fb_dev(vbhmm_data_t *h, int K, const double *m, const double *W, const double *v, const double *beta,
+                 const double *logLambdaTilde, double const_denominator, const double *pz1, const double *tpztzt1) {
+  int rc = check_model(h, K, m, W, v, beta, logLambdaTilde, pz1, tpztzt1);
+  if (rc) return rc;
+  CU(cudaSetDevice(h->device));
+  return run_fb(h, K, m, W, v, beta, logLambdaTilde, const_denominator, pz1, tpztzt1);
+}
+
+int vbhmm_fb_fetch(vbhmm_data_t *h, double *logrho_Saved, double *gamma_all, double *xi_sum, double *phi_norm) {
+  if (!h) return fail_fb(VBHEM_EINVAL, "vbhmm_fb_mex:invalidinput: data handle is NULL");
+  if (h->lastK < 1) return fail_fb(VBHEM_EINVAL, "no forward-backward pass has run on this handle");
+  CU(cudaSetDevice(h->device));
+  const int K = h->lastK;
+  const size_t nkt = (size_t)K * h->N * h->maxT;
+  if (logrho_Saved && nkt) CU(cudaMemcpyAsync(logrho_Saved, h->logrho.p, sizeof(double) * nkt, cudaMemcpyDeviceToHost, h->st));
+  if (gamma_all && nkt) CU(cudaMemcpyAsync(gamma_all, h->gamma.p, sizeof(double) * nkt, cudaMemcpyDeviceToHost, h->st));
+  if (xi_sum) CU(cudaMemcpyAsync(xi_sum, h->xi.p, sizeof(double) * (size_t)K * K * h->N, cudaMemcpyDeviceToHost, h->st));
+  if (phi_norm) CU(cudaMemcpyAsync(phi_norm, h->phi.p, sizeof(double) * (size_t)h->N, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  return VBHEM_OK;
+}
+
+int vbhmm_fb(vbhmm_data_t *h, int K, const double *m, const double *W, const double *v, const double *beta,
+             const double *logLambdaTilde, double const_denominator, const double *pz1, const double *tpztzt1,
+             double *logrho_Saved, double *gamma_all, double *xi_sum, double *phi_norm) {
+  int rc = vbhmm_fb_dev(h, K, m, W, v, beta, logLambdaTilde, const_denominator, pz1, tpztzt1);
+  if (rc) return rc;
+  return vbhmm_fb_fetch(h, logrho_Saved, gamma_all, xi_sum, phi_norm);
+}
+
+int vbhmm_fb_last_ms(vbhmm_data_t *h, double *ms) {
+  if (!h || !ms) return fail_fb(VBHEM_EINVAL, "vbhmm_fb_mex:invalidinput: NULL argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaEventSynchronize(h->ev[1]));
+  float f = 0.f;
+  CU(cudaEventElapsedTime(&f, h->ev[0], h->ev[1]));
+  *ms = f;
+  return VBHEM_OK;
+}
+
+}  // extern "C"

@@ -207,6 +207,34 @@ int vbhem_em_fetch(vbhem_base_t *base, double *alpha, double *eta, double *epsil
 int vbhem_em_run(vbhem_base_t *base, int tau, int max_iter, double min_diff, double *LogLs, int *iters,
                  int *unstable);
 
+/* ---- VB-HMM forward-backward (the toolbox's HMM learning) ----
+ * Replaces the MEX plug-in of /root/reference/src/hmm/vbhmm_fb.m:99-145,
+ *   [logrho_Saved, gamma_all, xi_sum, phi_norm] =
+ *       vbhmm_fb_mex(data, K, N, dim, maxT, m, W, v, beta, logLambdaTilde, const_denominator, t_pz1, t_tpztzt1)
+ * (gateway /root/reference/src/hmm/vbhmm_fb_mex.c:185-186; body :314-950).  The observation sequences do
+ * not change during vbhmm_em, so they are packed once into HBM and every EM iteration passes only the model.
+ *   vbhmm_pack_data: N sequences, sequence n = [T_n x dim] COLUMN-MAJOR (time fastest: mxGetPr(data{n})) at
+ *     flat[offs[n]] (offs in doubles; the gateway may point offs into separately allocated cells as long as all
+ *     lie in one address range, or copy them into one buffer); T_n = 0 is allowed.
+ *   vbhmm_fb: model in the MEX layouts -- m[dim,K], W[dim,dim,K], v[K], beta[K], logLambdaTilde[K],
+ *     const_denominator = dim*log(2*pi)/2, pz1[K] = exp(logPiTilde), tpztzt1[K,K] = exp(logATilde)(from,to) --
+ *     outputs (HOST, any may be NULL): logrho_Saved[K,N,maxT], gamma_all[K,N,maxT], xi_sum[K,K,N], phi_norm[N],
+ *     zero beyond a sequence's own length.  K <= 32, dim <= 8 (K <= 8, dim <= 3 take the fast kernel).
+ *   vbhmm_fb_dev / vbhmm_fb_fetch: the same split into compute (results stay in the handle, no
+ *     synchronisation) and copy-out.  vbhmm_fb_last_ms: device time of the last pass (CUDA events). */
+typedef struct vbhmm_data vbhmm_data_t;
+int vbhmm_pack_data(int device, int N, int dim, const int32_t *T, const long long *offs, const double *flat,
+                    vbhmm_data_t **out);
+int vbhmm_free_data(vbhmm_data_t *data);
+int vbhmm_data_shape(vbhmm_data_t *data, int *N, int *dim, int *maxT, long long *total);
+int vbhmm_fb(vbhmm_data_t *data, int K, const double *m, const double *W, const double *v, const double *beta,
+             const double *logLambdaTilde, double const_denominator, const double *pz1, const double *tpztzt1,
+             double *logrho_Saved, double *gamma_all, double *xi_sum, double *phi_norm);
+int vbhmm_fb_dev(vbhmm_data_t *data, int K, const double *m, const double *W, const double *v, const double *beta,
+                 const double *logLambdaTilde, double const_denominator, const double *pz1, const double *tpztzt1);
+int vbhmm_fb_fetch(vbhmm_data_t *data, double *logrho_Saved, double *gamma_all, double *xi_sum, double *phi_norm);
+int vbhmm_fb_last_ms(vbhmm_data_t *data, double *ms);
+
 /* Phase timing of the handle's E-steps, for bench.py: when enabled, CUDA events are
  * recorded on the handle's stream around each phase and vbhem_last_timings() returns the
  * milliseconds of the last E-step:

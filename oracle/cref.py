@@ -25,6 +25,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(HERE, "_ref", "libvbhem_ref.so")
 PORT_SO = os.path.join(HERE, "_build", "libvbhem_oracle.so")
+FB_REF_SO = os.path.join(HERE, "_ref", "libvbhmm_fb_ref.so")        # reference's src/hmm/vbhmm_fb_mex.c in place
+FB_PORT_SO = os.path.join(HERE, "_build", "libvbhmm_fb_oracle.so")  # oracle/fb_oracle.c
 GATEWAY_SO = os.path.join(HERE, "_build", "libvbhem_gateway.so")   # this repo's MEX gateway behind the same shim
 FUSED_SO = os.path.join(HERE, "_build", "libvbhem_gateway_fused.so")   # ... and its fused-E-step gateway
 
@@ -50,7 +52,8 @@ _libs = {}
 
 def _lib(which: str):
     if which not in _libs:
-        path = {"ref": REF_SO, "gateway": GATEWAY_SO, "fused": FUSED_SO}.get(which, PORT_SO)
+        path = {"ref": REF_SO, "gateway": GATEWAY_SO, "fused": FUSED_SO, "fb_ref": FB_REF_SO,
+                "fb_port": FB_PORT_SO}.get(which, PORT_SO)
         if not os.path.exists(path):
             build()
         _libs[which] = C.CDLL(path)
@@ -197,3 +200,55 @@ def port_estep_fused(base: dict, cen: dict, T: int, want_pairs: bool = True) -> 
         _d(S["nu1"]), _d(S["xi"]), _d(S["pr"]), _d(S["mu"]), _d(S["Mu"]))
     S["L_elbo"], S["zhat"] = L, z
     return S
+
+
+# ----------------------------------------------------------------------------- VB-HMM forward-backward
+def have_fb_ref() -> bool:
+    return os.path.exists(FB_REF_SO)
+
+
+def pack_sequences(data: list) -> dict:
+    """data[n]: array [T_n, dim] (time, coordinate) -> flat buffer with sequence n stored [T_n x dim] column-major
+    (exactly mxGetPr(data{n}) of the reference), offsets in doubles."""
+    dim = int(np.asarray(data[0]).reshape(len(data[0]), -1).shape[1]) if len(data) else 1
+    T = np.array([len(x) for x in data], np.int32)
+    offs = np.zeros(len(data) + 1, np.int64)
+    offs[1:] = np.cumsum(T.astype(np.int64) * dim)
+    flat = np.zeros(max(1, int(offs[-1])))
+    for n, x in enumerate(data):
+        x = np.asarray(x, float).reshape(len(x), dim)
+        flat[offs[n]:offs[n + 1]] = x.T.ravel()          # column-major [T x dim]
+    return dict(N=len(data), dim=dim, T=T, offs=offs, flat=flat, maxT=int(T.max()) if len(T) else 0)
+
+
+def _fb(which: str, ps: dict, par: dict) -> dict:
+    """par: m[K,dim], W[K,dim,dim], v[K], beta[K], logLambdaTilde[K], const_denominator, pz1[K], A[K(from),K(to)]."""
+    L = _lib(which)
+    fn = L.shim_vbhmm_fb if which == "fb_ref" else L.fb_oracle
+    N, dim, maxT = ps["N"], ps["dim"], ps["maxT"]
+    K = len(par["v"])
+    c = np.ascontiguousarray
+    m = c(par["m"], dtype=np.float64)                                     # [K, dim]  == column-major [dim, K]
+    W = c(np.transpose(par["W"], (0, 2, 1)), dtype=np.float64)            # [K, j, i] == column-major [i, j, K]
+    A = c(np.asarray(par["A"], float).T)                                  # [to, from] == column-major [from, to]
+    out = dict(logrho=np.zeros((maxT, N, K)), gamma=np.zeros((maxT, N, K)), xi=np.zeros((N, K, K)), phi=np.zeros(N))
+    fn.restype = C.c_int
+    rc = fn(N, dim, K, maxT, ps["T"].ctypes.data_as(_ip), ps["offs"].ctypes.data_as(C.POINTER(C.c_longlong)),
+            _d(ps["flat"]), _d(m), _d(W), _d(c(par["v"], dtype=np.float64)), _d(c(par["beta"], dtype=np.float64)),
+            _d(c(par["logLambdaTilde"], dtype=np.float64)), C.c_double(par["const_denominator"]),
+            _d(c(par["pz1"], dtype=np.float64)), _d(A), _d(out["logrho"]), _d(out["gamma"]), _d(out["xi"]),
+            _d(out["phi"]))
+    if rc != 0:
+        raise RuntimeError(f"{which} vbhmm_fb failed ({rc})")
+    # natural views: logrho / gamma [N, maxT, K]; xi [N, from, to]
+    return dict(logrho_Saved=np.transpose(out["logrho"], (1, 0, 2)).copy(),
+                gamma_all=np.transpose(out["gamma"], (1, 0, 2)).copy(),
+                xi_sum=np.transpose(out["xi"], (0, 2, 1)).copy(), phi_norm=out["phi"])
+
+
+def ref_vbhmm_fb(ps: dict, par: dict) -> dict:
+    return _fb("fb_ref", ps, par)
+
+
+def port_vbhmm_fb(ps: dict, par: dict) -> dict:
+    return _fb("fb_port", ps, par)

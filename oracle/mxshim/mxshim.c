@@ -353,3 +353,40 @@ int shim_call_malformed(int mode) {
   arena_reset();
   return 0;
 }
+
+/* ------------------------------------------------------------------ vbhmm_fb
+ * Driver for the reference's VB-HMM forward-backward MEX
+ * (/root/reference/src/hmm/vbhmm_fb_mex.c:185-186; call site vbhmm_fb.m:144-145), linked into
+ * oracle/_ref/libvbhmm_fb_ref.so only:
+ *   [logrho_Saved, gamma_all, xi_sum, phi_norm] =
+ *       vbhmm_fb_mex(data, K, N, dim, maxT, m, W, v, beta, logLambdaTilde, const_denominator, t_pz1, t_tpztzt1)
+ * seq = concatenated sequences, sequence n = [T_n x dim] column-major at offs[n]. */
+int shim_vbhmm_fb(int N, int dim, int K, int maxT, const int *T, const long long *offs, const double *seq,
+                  const double *m, const double *W, const double *v, const double *beta,
+                  const double *logLambdaTilde, double const_denominator, const double *pz1, const double *A,
+                  double *logrho, double *gamma, double *xi, double *phi) {
+  g_jmp_armed = 1;
+  if (setjmp(g_jmp)) { g_jmp_armed = 0; arena_reset(); return -1; }
+  mxArray *data = mxCreateCellMatrix((mwSize)N, 1);
+  for (int n = 0; n < N; n++) mxSetCell(data, (mwIndex)n, dbl_matrix((mwSize)T[n], (mwSize)dim, seq + offs[n], (size_t)T[n], 0));
+  mwSize wd[3] = {(mwSize)dim, (mwSize)dim, (mwSize)K};
+  /* MATLAB drops trailing singleton dimensions: W(:,:,1) alone is 2-D (vbhmm_fb_mex.c:137-139 relies on it) */
+  mxArray *Wm = K > 1 ? mxCreateNumericArray(3, wd, mxDOUBLE_CLASS, mxREAL)
+                      : mxCreateDoubleMatrix((mwSize)dim, (mwSize)dim, mxREAL);
+  memcpy(mxGetPr(Wm), W, sizeof(double) * (size_t)dim * dim * K);
+  const mxArray *prhs[13] = {data, dbl_scalar(K), dbl_scalar(N), dbl_scalar(dim), dbl_scalar(maxT),
+                             dbl_matrix((mwSize)dim, (mwSize)K, m, (size_t)dim, 0), Wm, dbl_matrix((mwSize)K, 1, v, (size_t)K, 0),
+                             dbl_matrix((mwSize)K, 1, beta, (size_t)K, 0), dbl_matrix(1, (mwSize)K, logLambdaTilde, 1, 0),
+                             dbl_scalar(const_denominator), dbl_matrix(1, (mwSize)K, pz1, 1, 0),
+                             dbl_matrix((mwSize)K, (mwSize)K, A, (size_t)K, 0)};
+  mxArray *plhs[4] = {NULL, NULL, NULL, NULL};
+  mexFunction(4, plhs, 13, prhs);
+  const size_t nkt = (size_t)K * N * maxT;
+  memcpy(logrho, mxGetPr(plhs[0]), sizeof(double) * nkt);
+  memcpy(gamma, mxGetPr(plhs[1]), sizeof(double) * nkt);
+  memcpy(xi, mxGetPr(plhs[2]), sizeof(double) * (size_t)K * K * N);
+  memcpy(phi, mxGetPr(plhs[3]), sizeof(double) * (size_t)N);
+  g_jmp_armed = 0;
+  arena_reset();
+  return 0;
+}

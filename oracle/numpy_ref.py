@@ -266,3 +266,61 @@ def lower_bound(Lt1, Lt7, Nj, logOmega, alpha, centres, pre, opt, covmode="full"
     terms = dict(Lt1=Lt1, Lt2=Lt2, Lt3=Lt3, Lt4=Lt4, Lt5=Lt5, Lt6=Lt6, Lt7=Lt7, Lt8=Lt8, Lt9=Lt9, Lt10=Lt10)
     LB = Lt1 + Lt2 + Lt3 + Lt4 + Lt5 + Lt6 - Lt7 - Lt8 - Lt9 - Lt10
     return float(LB), terms
+
+
+# ----------------------------------------------------------------------------- VB-HMM forward-backward
+def vbhmm_fb_prepass(varpar: dict) -> dict:
+    """vbhmm_fb.m:28-80: logLambdaTilde, logATilde, logPiTilde and the MEX arguments derived from them.
+    varpar (natural): v[K], W[K,dim,dim], epsilon[K(from),K(to)], alpha[K], m[K,dim], beta[K]."""
+    from scipy.special import psi
+    v, W, eps, al = (np.asarray(varpar[k], float) for k in ("v", "W", "epsilon", "alpha"))
+    K, dim = np.asarray(varpar["m"]).shape
+    ii = np.arange(1, dim + 1)
+    lLT = np.array([psi(0.5 * (v[k] + 1) - 0.5 * ii).sum() + dim * np.log(2) + np.log(np.linalg.det(W[k]))
+                    for k in range(K)])
+    logA = psi(eps) - psi(eps.sum(1, keepdims=True))
+    logPi = psi(al) - psi(al.sum())
+    return dict(m=np.asarray(varpar["m"], float), W=W, v=v, beta=np.asarray(varpar["beta"], float),
+                logLambdaTilde=lLT, const_denominator=dim * np.log(2 * np.pi) / 2, pz1=np.exp(logPi), A=np.exp(logA),
+                logPiTilde=logPi, logATilde=logA)
+
+
+def vbhmm_fb(data: list, par: dict) -> dict:
+    """vbhmm_fb.m:264-380 (the MATLAB branch), sequence by sequence.  data[n]: [T_n, dim]; par: vbhmm_fb_prepass.
+    Returns natural arrays: logrho_Saved / gamma_all [N, maxT, K], xi_sum [N, from, to], phi_norm [N]."""
+    N = len(data)
+    K, dim = par["m"].shape
+    maxT = max((len(x) for x in data), default=0)
+    out = dict(logrho_Saved=np.zeros((N, maxT, K)), gamma_all=np.zeros((N, maxT, K)), xi_sum=np.zeros((N, K, K)),
+               phi_norm=np.zeros(N))
+    A, pz1 = par["A"], par["pz1"]
+    for n, x in enumerate(data):
+        x = np.asarray(x, float).reshape(len(x), dim)
+        T = len(x)
+        if T == 0:
+            continue
+        diff = x[:, None, :] - par["m"][None]                                       # [T, K, dim]
+        mterm = np.einsum("tki,kij,tkj->tk", diff, par["W"], diff)
+        delta = dim / par["beta"][None] + par["v"][None] * mterm
+        logrho = 0.5 * par["logLambdaTilde"][None] - 0.5 * delta - par["const_denominator"]
+        out["logrho_Saved"][n, :T] = logrho
+        mx = logrho.max(1)
+        p = np.exp(logrho - mx[:, None])
+        alpha, c = np.zeros((T, K)), np.zeros(T)
+        for t in range(T):
+            d = pz1 * p[0] if t == 0 else (alpha[t - 1] @ A) * p[t]
+            c[t] = d.sum()
+            alpha[t] = d / c[t]
+        beta = np.ones(K)
+        gam = np.zeros((T, K))
+        gam[T - 1] = alpha[T - 1]
+        xi = np.zeros((K, K))
+        for t in range(T - 2, -1, -1):
+            bpi = beta * p[t + 1]
+            beta = (bpi @ A.T) / c[t + 1]
+            gam[t] = alpha[t] * beta
+            xi += (A * np.outer(alpha[t], bpi)) / c[t + 1]
+        out["gamma_all"][n, :T] = gam
+        out["xi_sum"][n] = xi
+        out["phi_norm"][n] = np.log(c).sum() + mx.sum()
+    return out

@@ -45,3 +45,16 @@ if __name__ == "__main__":
         blob["covmode"] = np.array(kw["covmode"])
         np.savez_compressed(os.path.join(here, name + ".npz"), **blob)
         print(name, "L_elbo[0,:]=", out["L_elbo"][0])
+
+    # VB-HMM forward-backward (src/hmm/vbhmm_fb_mex.c compiled in place): ragged sequences incl. T = 1 and T = 0
+    assert os.path.exists("/root/reference/src/hmm/vbhmm_fb_mex.c")
+    from oracle import numpy_ref as nr
+    from test_fb import make_fb_case
+    data, vp = make_fb_case(N=12, K=4, dim=2, maxT=15, seed=3)
+    out = cref.ref_vbhmm_fb(cref.pack_sequences(data), nr.vbhmm_fb_prepass(vp))
+    blob = {f"seq{n}": x for n, x in enumerate(data)}
+    blob.update(vp)
+    blob.update(out)
+    blob["N"] = np.int64(len(data))
+    np.savez_compressed(os.path.join(here, "vbhmm_fb_ragged_d2_k4.npz"), **blob)
+    print("vbhmm_fb_ragged_d2_k4 phi_norm[:3]=", out["phi_norm"][:3])

@@ -16,7 +16,7 @@ HEADER = os.path.join(ROOT, "include", "vbhem_b200.h")
 def declared_symbols():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(vbhem_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(vbh[em]m_[a-z0-9_]+)\s*\(", src)))
 
 
 def test_library_is_built():

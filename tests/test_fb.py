@@ -1,0 +1,129 @@
+"""VB-HMM forward-backward: the reference's src/hmm/vbhmm_fb_mex.c compiled in place, the
+plain-C restatement (oracle/fb_oracle.c) and the numpy restatement of vbhmm_fb.m on CPU; the CUDA path
+(vbhmm_fb through the C ABI) against them on the GPU.  Tolerance 1e-9, the authors' own cross-check bound
+(vbhmm_fb.m:186-190)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import cref, numpy_ref as nr
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "vbhmm_fb_ragged_d2_k4.npz")
+
+
+def make_fb_case(N=12, K=4, dim=2, maxT=15, seed=3, ragged=True, with_empty=True):
+    rng = np.random.default_rng(seed)
+    centre = np.resize(np.array([256.0, 192.0, 128.0]), dim)
+    lens = rng.integers(1, maxT + 1, size=N) if ragged else np.full(N, maxT)
+    lens[0] = maxT
+    if ragged and N > 2:
+        lens[1] = 1
+        if with_empty:
+            lens[2] = 0
+    means = rng.normal(size=(K, dim)) * 60 + centre
+    data = []
+    for T in lens:
+        z = rng.integers(0, K, size=T)
+        data.append(means[z] + rng.normal(size=(T, dim)) * 15)
+    W = np.stack([np.linalg.inv(np.cov(rng.normal(size=(dim, 30)) * 20).reshape(dim, dim)) / 8 for _ in range(K)])
+    vp = dict(v=5 + rng.uniform(size=K) * 10, W=W, epsilon=1 + rng.uniform(size=(K, K)) * 5,
+              alpha=1 + rng.uniform(size=K) * 3, m=means + rng.normal(size=(K, dim)) * 5, beta=1 + rng.uniform(size=K) * 5)
+    return data, vp
+
+
+def assert_fb_close(got, want, rtol=1e-9):
+    np.testing.assert_allclose(got["logrho_Saved"], want["logrho_Saved"], rtol=rtol, atol=1e-12)
+    np.testing.assert_allclose(got["gamma_all"], want["gamma_all"], rtol=rtol, atol=1e-13)
+    np.testing.assert_allclose(got["xi_sum"], want["xi_sum"], rtol=rtol, atol=1e-13)
+    np.testing.assert_allclose(got["phi_norm"], want["phi_norm"], rtol=rtol, atol=1e-12)
+
+
+@pytest.mark.parametrize("K,dim", [(4, 2), (1, 1), (3, 3), (8, 2)])
+def test_port_and_numpy_match_reference_build(K, dim):
+    if not cref.have_fb_ref():
+        pytest.skip("reference build not present")
+    data, vp = make_fb_case(N=9, K=K, dim=dim, seed=10 + K)
+    par = nr.vbhmm_fb_prepass(vp)
+    ps = cref.pack_sequences(data)
+    ref, port, npy = cref.ref_vbhmm_fb(ps, par), cref.port_vbhmm_fb(ps, par), nr.vbhmm_fb(data, par)
+    assert np.array_equal(port["logrho_Saved"], ref["logrho_Saved"])
+    assert np.array_equal(port["gamma_all"], ref["gamma_all"])
+    assert_fb_close(port, ref, rtol=1e-13)
+    assert_fb_close(npy, ref, rtol=1e-11)
+    # forward-backward invariants: responsibilities sum to one, pair marginals to T - 1
+    T = np.array([len(x) for x in data])
+    for n in range(len(data)):
+        np.testing.assert_allclose(ref["gamma_all"][n, :T[n]].sum(1), 1.0, rtol=1e-12)
+        np.testing.assert_allclose(ref["xi_sum"][n].sum(), max(T[n] - 1, 0), rtol=1e-12, atol=1e-13)
+        assert not ref["gamma_all"][n, T[n]:].any() and not ref["logrho_Saved"][n, T[n]:].any()
+
+
+def test_golden_fixture_pins_the_port():
+    """tests/golden/vbhmm_fb_*.npz was generated from the reference build (tests/golden/make_golden.py)."""
+    g = np.load(GOLD)
+    data = [g[f"seq{n}"] for n in range(int(g["N"]))]
+    vp = {k: g[k] for k in ("v", "W", "epsilon", "alpha", "m", "beta")}
+    par = nr.vbhmm_fb_prepass(vp)
+    port = cref.port_vbhmm_fb(cref.pack_sequences(data), par)
+    assert_fb_close(port, {k: g[k] for k in ("logrho_Saved", "gamma_all", "xi_sum", "phi_norm")}, rtol=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("K,dim,N,maxT", [(4, 2, 40, 15), (1, 1, 7, 5), (5, 2, 300, 50), (8, 3, 33, 9), (3, 2, 5, 1),
+                                           (11, 2, 21, 8), (4, 5, 19, 6)])
+def test_cuda_fb_matches_oracle(K, dim, N, maxT):
+    from vbhem_b200 import fb
+    data, vp = make_fb_case(N=N, K=K, dim=dim, maxT=maxT, seed=100 + K + dim)
+    par = nr.vbhmm_fb_prepass(vp)
+    want = cref.port_vbhmm_fb(cref.pack_sequences(data), par)
+    got = fb.vbhmm_fb(data, vp)
+    assert_fb_close(got, want)
+    np.testing.assert_allclose(got["logLambdaTilde"], par["logLambdaTilde"], rtol=1e-13)
+    np.testing.assert_allclose(got["logATilde"], par["logATilde"], rtol=1e-13)
+
+
+@pytest.mark.gpu
+def test_cuda_fb_golden_and_resident_handle():
+    from vbhem_b200 import fb
+    g = np.load(GOLD)
+    data = [g[f"seq{n}"] for n in range(int(g["N"]))]
+    vp = {k: g[k] for k in ("v", "W", "epsilon", "alpha", "m", "beta")}
+    with fb.SequenceSet(data) as seqs:
+        a = fb.vbhmm_fb(seqs, vp)
+        vp2 = dict(vp, m=vp["m"] + 3.0)
+        fb.vbhmm_fb(seqs, vp2)                      # another model on the resident data
+        b = fb.vbhmm_fb(seqs, vp)
+    assert_fb_close(a, {k: g[k] for k in ("logrho_Saved", "gamma_all", "xi_sum", "phi_norm")})
+    for k in ("logrho_Saved", "gamma_all", "xi_sum", "phi_norm"):
+        assert np.array_equal(a[k], b[k]), k       # bit-identical run to run
+
+
+@pytest.mark.gpu
+def test_cuda_fb_long_sequences_stay_normalised():
+    """Size-independent properties at a length where an unscaled recursion would underflow."""
+    from vbhem_b200 import fb
+    data, vp = make_fb_case(N=64, K=5, dim=2, maxT=4000, seed=7, ragged=False)
+    out = fb.vbhmm_fb(data, vp)
+    assert np.isfinite(out["phi_norm"]).all()
+    np.testing.assert_allclose(out["gamma_all"].sum(2), 1.0, rtol=1e-10)
+    np.testing.assert_allclose(out["xi_sum"].sum((1, 2)), 3999.0, rtol=1e-10)
+    # xi marginals agree with gamma: sum_to xi(from, to) = sum_{t < T} gamma(t, from)
+    np.testing.assert_allclose(out["xi_sum"].sum(2), out["gamma_all"][:, :-1].sum(1), rtol=1e-9)
+
+
+@pytest.mark.gpu
+def test_cuda_fb_error_codes():
+    import ctypes as C
+    from vbhem_b200 import fb
+    from vbhem_b200._lib import VbhemError, lib
+    data, vp = make_fb_case(N=4, K=2, dim=2, maxT=4, seed=1)
+    with fb.SequenceSet(data) as seqs:
+        par = fb.prepass(vp)
+        par_bad = dict(par, v=np.zeros(40), beta=np.ones(40), logLambdaTilde=np.zeros(40), pz1=np.ones(40),
+                       m=np.zeros((40, 2)), W=np.zeros((40, 2, 2)), A=np.zeros((40, 40)))
+        with pytest.raises(VbhemError) as ei:
+            fb.fb_call(seqs, par_bad)
+        assert ei.value.code == -1 and "vbhmm_fb_mex:invalidinput" in ei.value.msg
+    h = C.c_void_p()
+    assert lib().vbhmm_pack_data(0, 0, 2, None, None, None, C.byref(h)) == -1
