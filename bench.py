@@ -142,10 +142,22 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--slices", type=int, default=6, help="slices of the streamed (e2e) E-step")
+    ap.add_argument("--workload", default="estep", choices=["estep", "grid", "fb"],
+                    help="estep = BASELINE configs[2] (the metric's workload, default); grid = configs[3], the (K,S) "
+                         "model-selection grid K=1..16 x S=1..8 over 20k bases in one batched call; fb = configs[4], "
+                         "the VB-HMM forward-backward pass over 1M sequences of length 50")
     a = ap.parse_args()
     K, S, d, tau = a.centres, a.states, a.dim, a.tau
+    if a.workload == "fb":
+        from bench_fb import main_fb
+        return main_fb(a)
     if a.cpu_worker:
         return cpu_worker(a.cpu_worker, K, S, d, tau, a.seed)
+    grid = a.workload == "grid"
+    if grid:
+        if a.bases == 100_000:
+            a.bases = 20_000
+        a.no_cpu, a.no_e2e = True, True
 
     # The contract is ONE JSON line on stdout: keep the real stdout aside and send everything else that
     # libraries print there (NCCL prints its version banner to stdout) to stderr.
@@ -161,7 +173,9 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     W = max(a.warmup, 3) if a.impl == "b200" else a.warmup
     cores = os.cpu_count() or 1
-    config = dict(workload="configs[2]: synthetic base HMMs x centre HMMs, full-covariance Gaussian emissions, "
+    config = dict(workload=("configs[3]: (K,S) model-selection grid K=1..16 x S=1..8, every candidate's centres in ONE "
+                            "batched fused E-step (128 soft-max groups, ragged state counts)") if grid else
+                           "configs[2]: synthetic base HMMs x centre HMMs, full-covariance Gaussian emissions, "
                            "baseem-initialised centres, one fused E-step per step",
                   bases_per_gpu=a.bases, centres=K, states=S, dim=d, tau=tau, Nv=100,
                   pairs_per_step=a.bases * K * world, parallelism=f"bases sharded x{world}, centres replicated",
@@ -209,7 +223,13 @@ def main():
 
     # ---- workload: centres come from the seed-1001 base set on every rank; shard r uses seed 1001 + r
     base0, _ = synth.make_base_set(a.bases, S=S, d=d, C=K, seed=a.seed)
-    hyp = synth.init_centres_baseem(base0, K, S, seed=a.seed)
+    grp, ngroups = None, 1
+    if grid:
+        hyp, grp, models = synth.model_selection_grid(base0, seed=a.seed)
+        K, ngroups = int(hyp["Sr"].shape[0]), len(models)
+        config.update(centres=K, models=ngroups, pairs_per_step=a.bases * K * world)
+    else:
+        hyp = synth.init_centres_baseem(base0, K, S, seed=a.seed)
     base = base0 if rank == 0 else synth.make_base_set(a.bases, S=S, d=d, C=K, seed=a.seed + rank)[0]
     pb = pack.pack_base(base)
     c = np.ascontiguousarray
@@ -217,7 +237,8 @@ def main():
     H = dict(alpha=c(hyp["alpha"]), eta=c(hyp["eta"]), eps=c(np.transpose(hyp["epsilon"], (0, 2, 1))),
              m=c(hyp["m"]), W=c(np.transpose(hyp["W"], (0, 1, 3, 2))), v=c(hyp["v"]), lam=c(hyp["lam"]))
     P = lambda x: x.ctypes.data_as(dp)
-    ns = int(L.vbhem_stats_size(K, S, d, 1, 1))
+    ns = int(L.vbhem_stats_size(K, S, d, 1, ngroups))
+    gp = None if grp is None else grp.ctypes.data_as(ip)
     stats = torch.zeros(ns, dtype=torch.float64, device="cuda")
     pre = np.zeros(K + S * K * (2 + S))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -232,12 +253,12 @@ def main():
         return bs
 
     def step(bs):
-        check(L.vbhem_estep_hyp_dev(bs._h, K, Sr.ctypes.data_as(ip), S, None, 1, tau, P(H["alpha"]), P(H["eta"]),
+        check(L.vbhem_estep_hyp_dev(bs._h, K, Sr.ctypes.data_as(ip), S, gp, ngroups, tau, P(H["alpha"]), P(H["eta"]),
                                     P(H["eps"]), P(H["m"]), P(H["W"]), P(H["v"]), P(H["lam"]),
                                     C.c_void_p(stats.data_ptr()), P(pre)))
         if dist is not None:
             dist.all_reduce(stats)
-        check(L.vbhem_finalize_stats_dev(bs._h, K, Sr.ctypes.data_as(ip), S, 1, C.c_void_p(stats.data_ptr())))
+        check(L.vbhem_finalize_stats_dev(bs._h, K, Sr.ctypes.data_as(ip), S, ngroups, C.c_void_p(stats.data_ptr())))
 
     def timed_run(bs, steps, warm):
         sampler = ClockSampler(local)
@@ -277,7 +298,11 @@ def main():
     tot_ms, ph, launches, clocks, counters = timed_run(bs, a.steps, W)
     pairs_step = a.bases * K * world
     value = pairs_step * a.steps / (tot_ms * 1e-3)
-    fl = flops_per_pair(S, S, d, tau)
+    if grid:   # algorithmic flops of the reference per pair depend on the centre's own state count
+        per = [flops_per_pair(S, int(r), d, tau) for r in Sr]
+        fl = dict(first_pass=sum(f["first_pass"] for f in per) / K, total=sum(f["total"] for f in per) / K)
+    else:
+        fl = flops_per_pair(S, S, d, tau)
     first_ms = ph[1]
     ach = a.bases * K * fl["first_pass"] / (first_ms * 1e-3) / 1e12
     alg_bytes = a.bases * (S + S * S + S * d + S * d * d) * 8 + a.bases * K * 8
@@ -308,7 +333,7 @@ def main():
 
     # ---- full VBHEM iterations (E-step + lower bound + M-step + convergence test), N = 1 only
     vbhem_iter = None
-    if world == 1:
+    if world == 1 and not grid:
         from vbhem_b200 import h3m
         opt = dict(synth.DEFAULT_OPT, tau=tau, max_iter=6, minDiff=0.0)
         check(L.vbhem_set_profile(bs._h, 0))
@@ -333,7 +358,7 @@ def main():
 
     # ---- strong scaling of the north-star size (100k bases in total): E-step and whole EM iterations
     strong = None
-    if world > 1:
+    if world > 1 and not grid:
         nbs = a.bases // world
         sub = {k: (v[rank * nbs:(rank + 1) * nbs] if isinstance(v, np.ndarray) and v.shape[:1] == (a.bases,) else v)
                for k, v in pack.pack_base(base0).items()}

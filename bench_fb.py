@@ -1,0 +1,196 @@
+"""bench.py --workload fb: the VB-HMM forward-backward pass (BASELINE.json configs[4]) on one GPU.
+
+Workload: N = 1 000 000 synthetic 2-D sequences of length 50, S = 5 states (``--bases`` overrides N).  One
+"step" is one pass of ``vbhmm_fb`` over every sequence: emission log-densities, scaled forward-backward,
+responsibilities, summed pair marginals, phi_norm -- what ``vbhmm_em`` runs once per EM iteration through
+the MEX plug-in ``vbhmm_fb_mex`` (/root/reference/src/hmm/vbhmm_fb.m:99-145).
+
+Same JSON contract as bench.py: ``value`` = sequences/s with the packed sequences resident in HBM (CUDA
+events around the kernel on its own stream); ``e2e`` = pack (H2D) + pass + every output back to pinned host
+memory; ``roofline`` = HBM (this path moves ~3 flop per byte); ``cpu_baseline`` = the reference's own C
+(oracle/_ref/libvbhmm_fb_ref.so) on the host cores, bounded sample.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+METRIC = "VB-HMM forward-backward sequences/sec"
+UNIT = "sequences/s"
+
+
+def make_workload(N, T, K, dim, seed):
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    means = rng.uniform([0] * dim, [512, 384, 256][:dim], size=(K, dim))
+    z = rng.integers(0, K, size=(N, T))
+    X = means[z] + rng.normal(size=(N, T, dim)) * 15
+    flat = np.ascontiguousarray(np.transpose(X, (0, 2, 1))).ravel()      # each sequence [T x dim] column-major
+    Tn = np.full(N, T, np.int32)
+    offs = np.arange(N + 1, dtype=np.int64) * T * dim
+    vp = dict(v=5 + rng.uniform(size=K) * 10, W=np.stack([np.eye(dim) / (15.0 ** 2 * 8)] * K),
+              epsilon=1 + rng.uniform(size=(K, K)) * 5, alpha=1 + rng.uniform(size=K) * 3, m=means,
+              beta=np.full(K, 50.0))
+    return Tn, offs, flat, vp
+
+
+def cpu_worker(n, T, K, dim, seed):
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    from oracle import cref, numpy_ref as nr
+    Tn, offs, flat, vp = make_workload(n, T, K, dim, seed)
+    par = nr.vbhmm_fb_prepass(vp)
+    ps = dict(N=n, dim=dim, T=Tn, offs=offs, flat=flat, maxT=T)
+    kind = "reference" if cref.have_fb_ref() else "port"
+    fn = cref.ref_vbhmm_fb if kind == "reference" else cref.port_vbhmm_fb
+    t0 = time.perf_counter()
+    out = fn(ps, par)
+    dt = time.perf_counter() - t0
+    assert np.isfinite(out["phi_norm"]).all()
+    print(json.dumps(dict(seconds=dt, sequences=n, kind=kind)))
+
+
+def run_cpu_baseline(n, T, K, dim, cores):
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "fb", "--cpu-worker", str(n), "--tau", str(T),
+           "--states", str(K), "--dim", str(dim)]
+    t0 = time.perf_counter()
+    procs = [subprocess.Popen(cmd + ["--seed", str(3000 + w)], stdout=subprocess.PIPE, text=True,
+                              env=dict(os.environ, OMP_NUM_THREADS="1", CUDA_VISIBLE_DEVICES=""))
+             for w in range(cores)]
+    outs = [json.loads(p.communicate()[0].strip().splitlines()[-1]) for p in procs]
+    wall = time.perf_counter() - t0
+    worst = max(o["seconds"] for o in outs)
+    tot = sum(o["sequences"] for o in outs)
+    return dict(value=tot / worst, unit=UNIT, cores=cores, kind=outs[0]["kind"],
+                per_core=statistics.median(o["sequences"] / o["seconds"] for o in outs),
+                sample=f"{cores} processes x {n} sequences (T={T}, dim={dim}, S={K}) through the reference MEX gateway "
+                       f"vbhmm_fb_mex compiled in place; slowest worker {worst:.2f} s, wall {wall:.1f} s")
+
+
+def main_fb(a):
+    K, dim, T = (a.states if a.states != 8 else 5), a.dim, (a.tau if a.tau != 10 else 50)
+    if a.cpu_worker:
+        return cpu_worker(a.cpu_worker, T, K, dim, a.seed)
+    N = a.bases if a.bases != 100_000 else 1_000_000
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    rank = int(os.environ.get("RANK", "0"))
+    cores = os.cpu_count() or 1
+    config = dict(workload="configs[4] (forward-backward part): synthetic 2-D sequences, one vbhmm_fb pass per step",
+                  sequences=N, length=T, states=K, dim=dim,
+                  l2="working set 5.8 GB >> L2; no flush needed between steps")
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        vals = [run_cpu_baseline(a.cpu_bases or 20000, T, K, dim, cores) for _ in range(a.warmup + a.steps)][a.warmup:]
+        v = statistics.median(x["value"] for x in vals)
+        line = dict(metric=METRIC, value=v, unit=UNIT, n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
+                    ms_per_step=1e3 * cores * (a.cpu_bases or 20000) / v, higher_is_better=True, scaling="weak",
+                    vs_baseline=None, dtype="f64", data="synthetic", impl="reference",
+                    config=dict(config, note="each step = a bounded sample of the workload"),
+                    cpu_baseline=dict(value=v, unit=UNIT, cores=cores, kind=vals[0]["kind"], sample=vals[0]["sample"]),
+                    e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+        real_stdout.write(json.dumps(line) + "\n")
+        return
+    cpu = None if a.no_cpu else run_cpu_baseline(a.cpu_bases or 20000, T, K, dim, cores)
+
+    import numpy as np
+    import torch
+    sys.path.insert(0, ROOT)
+    import vbhem_b200  # noqa: F401
+    from vbhem_b200 import fb
+    from vbhem_b200._lib import check, dp, ip, lib
+    from bench import ClockSampler
+    L = lib()
+    W = max(a.warmup, 3)
+    Tn, offs, flat, vp = make_workload(N, T, K, dim, a.seed)
+    par = fb.prepass(vp)
+    c = np.ascontiguousarray
+    m, Wm, A = c(par["m"]), c(np.transpose(par["W"], (0, 2, 1))), c(par["A"].T)
+    P = lambda x: x.ctypes.data_as(dp)
+    model = (K, P(m), P(Wm), P(c(par["v"])), P(c(par["beta"])), P(c(par["logLambdaTilde"])),
+             C.c_double(par["const_denominator"]), P(c(par["pz1"])), P(A))
+    keep = (m, Wm, A)   # noqa: F841  (the ctypes pointers above borrow these)
+    seqs = fb.SequenceSet.from_packed(Tn, offs, flat, dim)
+    sampler = ClockSampler(0)
+    sampler.start()
+    ms = C.c_double()
+    for _ in range(W):
+        check(L.vbhmm_fb_dev(seqs._h, *model))
+    check(L.vbhmm_fb_last_ms(seqs._h, C.byref(ms)))
+    sampler.armed = True
+    tot = 0.0
+    for _ in range(a.steps):
+        check(L.vbhmm_fb_dev(seqs._h, *model))
+        check(L.vbhmm_fb_last_ms(seqs._h, C.byref(ms)))           # CUDA events on the kernel's own stream
+        tot += ms.value
+    sampler.armed = False
+    sampler.stop_flag = True
+    sampler.join()
+    value = N * a.steps / (tot * 1e-3)
+    alg = N * T * dim * 8 + 2 * N * T * K * 8 + N * K * K * 8 + N * 8
+    peak, src = 6552.0, "fallback 6552 GB/s"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak, src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (copy bandwidth, burst)"
+    except Exception:  # noqa: BLE001
+        pass
+    traffic = None
+    try:
+        if (N, T, K, dim) == (1_000_000, 50, 5, 2):
+            with open(os.path.join(ROOT, "profiles", "r02_k_fb_ncu.json")) as f:
+                nc = json.load(f)
+            traffic = (float(nc["dram__bytes_read.sum"]["value"]) + float(nc["dram__bytes_write.sum"]["value"])) * 1e9
+    except Exception:  # noqa: BLE001
+        pass
+    ach = alg / (tot / a.steps * 1e-3) / 1e9
+    roofline = dict(bound="hbm", kernel="k_fb<5,2> (emissions + scaled forward + backward + gamma + xi, one thread per "
+                                        "sequence)", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak,
+                    peak_source=src, traffic=traffic, algorithmic_bytes=alg,
+                    bytes_per_sequence=alg / N,
+                    note="algorithmic bytes = observations in + logrho_Saved, gamma_all, xi_sum, phi_norm out; the "
+                         "kernel also parks alpha_hat in the gamma output and reads it back (traffic)")
+    # e2e: pack (H2D of the observations) + pass + all four outputs to pinned host memory, every step
+    e2e = None
+    if not a.no_e2e:
+        pin = lambda x: torch.from_numpy(x).pin_memory().numpy()
+        flat_p = pin(flat)
+        lr = torch.empty((T, N, K), dtype=torch.float64).pin_memory().numpy()
+        gm = torch.empty((T, N, K), dtype=torch.float64).pin_memory().numpy()
+        xi = torch.empty((N, K, K), dtype=torch.float64).pin_memory().numpy()
+        ph = torch.empty(N, dtype=torch.float64).pin_memory().numpy()
+        seqs.close()
+
+        def e2e_step():
+            h = C.c_void_p()
+            check(L.vbhmm_pack_data(0, N, dim, Tn.ctypes.data_as(ip), offs.ctypes.data_as(C.POINTER(C.c_longlong)),
+                                    P(flat_p), C.byref(h)))
+            check(L.vbhmm_fb(h, *model, P(lr), P(gm), P(xi), P(ph)))
+            L.vbhmm_free_data(h)
+            return float(ph[0])
+
+        e2e_step()
+        ne = max(2, min(a.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(ne):
+            e2e_step()
+        dt = time.perf_counter() - t0
+        e2e = dict(value=N * ne / dt, unit=UNIT, h2d_bytes_per_step=int(flat.nbytes + Tn.nbytes + offs.nbytes),
+                   d2h_bytes_per_step=int(lr.nbytes + gm.nbytes + xi.nbytes + ph.nbytes), ms_per_step=1e3 * dt / ne,
+                   steps=ne, note="every step: vbhmm_pack_data (observations H2D + repack) + vbhmm_fb (all four outputs "
+                                  "D2H into pinned memory) + free; wall clock")
+    else:
+        seqs.close()
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=1, steps=a.steps, warmup=W, ms_per_step=tot / a.steps,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic", config=config,
+                clocks=sampler.summary(), e2e=e2e, gpu_launches=a.steps, roofline=roofline)
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    real_stdout.write(json.dumps(line) + "\n")
+    real_stdout.flush()

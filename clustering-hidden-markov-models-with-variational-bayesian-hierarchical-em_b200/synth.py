@@ -125,3 +125,25 @@ def north_star(N=100_000, K=64, S=8, d=2, seed=1001, covmode="full"):
     base, lab = make_base_set(N, S=S, d=d, C=K, covmode=covmode, seed=seed)
     cen = init_centres_baseem(base, K, S, seed=seed)
     return base, cen, lab
+
+
+def model_selection_grid(base, Ks=range(1, 17), Ss=range(1, 9), seed=1001, opt=DEFAULT_OPT):
+    """BASELINE.json configs[3]: the centres of every (K, S) candidate of the posterior model selection
+    (vbhem_h3m_cluster.m:261-355 runs them one after the other) stacked for ONE batched E-step call:
+    hyper-parameter dict padded to max(Ss) states, plus ``group`` (one soft-max segment per (K, S) model)
+    and ``models`` = [(K, S), ...] in group order."""
+    parts, group, models = [], [], []
+    maxS = max(Ss)
+    for S in Ss:
+        for K in Ks:
+            h = init_centres_baseem(base, K, S, seed=seed + 131 * K + S, opt=opt)
+            pad = maxS - S
+            parts.append(dict(Sr=h["Sr"], alpha=h["alpha"], eta=np.pad(h["eta"], ((0, 0), (0, pad))),
+                              epsilon=np.pad(h["epsilon"], ((0, 0), (0, pad), (0, pad))),
+                              m=np.pad(h["m"], ((0, 0), (0, pad), (0, 0))),
+                              W=np.pad(h["W"], ((0, 0), (0, pad)) + ((0, 0),) * (h["W"].ndim - 2)),
+                              v=np.pad(h["v"], ((0, 0), (0, pad))), lam=np.pad(h["lam"], ((0, 0), (0, pad)))))
+            group += [len(models)] * K
+            models.append((K, S))
+    hyp = {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
+    return hyp, np.array(group, np.int32), models

@@ -27,6 +27,7 @@ REF_SO = os.path.join(HERE, "_ref", "libvbhem_ref.so")
 PORT_SO = os.path.join(HERE, "_build", "libvbhem_oracle.so")
 FB_REF_SO = os.path.join(HERE, "_ref", "libvbhmm_fb_ref.so")        # reference's src/hmm/vbhmm_fb_mex.c in place
 FB_PORT_SO = os.path.join(HERE, "_build", "libvbhmm_fb_oracle.so")  # oracle/fb_oracle.c
+FB_GATEWAY_SO = os.path.join(HERE, "_build", "libvbhmm_fb_gateway.so")  # this repo's mex/vbhmm_fb_mex.cpp behind the shim
 GATEWAY_SO = os.path.join(HERE, "_build", "libvbhem_gateway.so")   # this repo's MEX gateway behind the same shim
 FUSED_SO = os.path.join(HERE, "_build", "libvbhem_gateway_fused.so")   # ... and its fused-E-step gateway
 
@@ -53,7 +54,7 @@ _libs = {}
 def _lib(which: str):
     if which not in _libs:
         path = {"ref": REF_SO, "gateway": GATEWAY_SO, "fused": FUSED_SO, "fb_ref": FB_REF_SO,
-                "fb_port": FB_PORT_SO}.get(which, PORT_SO)
+                "fb_port": FB_PORT_SO, "fb_gateway": FB_GATEWAY_SO}.get(which, PORT_SO)
         if not os.path.exists(path):
             build()
         _libs[which] = C.CDLL(path)
@@ -224,7 +225,7 @@ def pack_sequences(data: list) -> dict:
 def _fb(which: str, ps: dict, par: dict) -> dict:
     """par: m[K,dim], W[K,dim,dim], v[K], beta[K], logLambdaTilde[K], const_denominator, pz1[K], A[K(from),K(to)]."""
     L = _lib(which)
-    fn = L.shim_vbhmm_fb if which == "fb_ref" else L.fb_oracle
+    fn = L.fb_oracle if which == "fb_port" else L.shim_vbhmm_fb
     N, dim, maxT = ps["N"], ps["dim"], ps["maxT"]
     K = len(par["v"])
     c = np.ascontiguousarray
@@ -252,3 +253,8 @@ def ref_vbhmm_fb(ps: dict, par: dict) -> dict:
 
 def port_vbhmm_fb(ps: dict, par: dict) -> dict:
     return _fb("fb_port", ps, par)
+
+
+def gateway_vbhmm_fb(ps: dict, par: dict) -> dict:
+    """mex/vbhmm_fb_mex.cpp (CUDA library behind it) through the same mx shim and driver as the reference's MEX."""
+    return _fb("fb_gateway", ps, par)

@@ -127,3 +127,35 @@ def test_cuda_fb_error_codes():
         assert ei.value.code == -1 and "vbhmm_fb_mex:invalidinput" in ei.value.msg
     h = C.c_void_p()
     assert lib().vbhmm_pack_data(0, 0, 2, None, None, None, C.byref(h)) == -1
+
+
+needs_fb_gateway = pytest.mark.skipif(not os.path.exists(cref.FB_GATEWAY_SO), reason="fb gateway not built")
+
+
+@needs_fb_gateway
+def test_fb_gateway_argument_checks_need_no_gpu():
+    """Checks fire before any CUDA call: a sequence longer than the caller's maxT is refused with the
+    reference's error id family (the reference itself would write out of bounds there)."""
+    data, vp = make_fb_case(N=4, K=3, dim=2, maxT=5, seed=2)
+    par = nr.vbhmm_fb_prepass(vp)
+    ps = cref.pack_sequences(data)
+    with pytest.raises(RuntimeError):
+        cref._fb("fb_gateway", dict(ps, maxT=ps["maxT"] - 1), par)
+
+
+@needs_fb_gateway
+@pytest.mark.gpu
+def test_fb_gateway_matches_reference_golden_and_caches_data():
+    g = np.load(GOLD)
+    data = [g[f"seq{n}"] for n in range(int(g["N"]))]
+    vp = {k: g[k] for k in ("v", "W", "epsilon", "alpha", "m", "beta")}
+    par = nr.vbhmm_fb_prepass(vp)
+    ps = cref.pack_sequences(data)
+    want = {k: g[k] for k in ("logrho_Saved", "gamma_all", "xi_sum", "phi_norm")}
+    assert_fb_close(cref.gateway_vbhmm_fb(ps, par), want)
+    # a second model on the same data, then other data of another shape
+    par2 = nr.vbhmm_fb_prepass(dict(vp, m=vp["m"] - 2.0))
+    assert_fb_close(cref.gateway_vbhmm_fb(ps, par2), cref.port_vbhmm_fb(ps, par2))
+    data3, vp3 = make_fb_case(N=20, K=2, dim=3, maxT=7, seed=44)
+    ps3, par3 = cref.pack_sequences(data3), nr.vbhmm_fb_prepass(vp3)
+    assert_fb_close(cref.gateway_vbhmm_fb(ps3, par3), cref.port_vbhmm_fb(ps3, par3))

@@ -334,3 +334,23 @@ def test_set_stream_orders_with_torch_default_stream():
                                             *[h.ctypes.data_as(dp) for h in H], C.c_void_p(stats.data_ptr()), None))
             got = (stats * 1.0).cpu().numpy()          # torch op on the same stream, no explicit synchronise
             assert np.array_equal(got, want)
+
+
+def test_model_selection_grid_batched_equals_one_model_at_a_time():
+    """BASELINE configs[3]: every (K,S) candidate's centres stacked in ONE fused E-step (one soft-max group per
+    model, ragged state counts) must give each model what a call of its own gives."""
+    from vbhem_b200 import synth
+    base, _ = synth.make_base_set(300, S=4, d=2, C=3, covmode="full", seed=23, Nv=20.0)
+    hyp, grp, models = synth.model_selection_grid(base, Ks=range(1, 4), Ss=range(1, 5), seed=23,
+                                                  opt=dict(synth.DEFAULT_OPT, Nv=20.0))
+    with BaseSet(base) as bs:
+        allg = bs.estep_hyp(hyp, 5, group=grp)
+        for g, (K, S) in enumerate(models):
+            sel = np.where(grp == g)[0]
+            one = bs.estep_hyp({k: v[sel] for k, v in hyp.items()}, 5)
+            np.testing.assert_array_equal(allg["L_elbo"][:, sel], one["L_elbo"])
+            np.testing.assert_array_equal(allg["zhat"][:, sel], one["zhat"])
+            np.testing.assert_allclose(allg["Nj"][sel], one["Nj"], rtol=1e-13)
+            np.testing.assert_allclose(allg["lb"][2 * g:2 * g + 2], one["lb"], rtol=1e-12)
+            for k in ("nu1", "xi", "pr", "mu", "Mu"):
+                np.testing.assert_allclose(allg[k][sel], one[k], rtol=1e-12, atol=1e-12 * np.abs(one[k]).max(), err_msg=k)
