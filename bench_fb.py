@@ -142,13 +142,9 @@ def main_fb(a):
     except Exception:  # noqa: BLE001
         pass
     traffic = None
-    try:
-        if (N, T, K, dim) == (1_000_000, 50, 5, 2):
-            with open(os.path.join(ROOT, "profiles", "r02_k_fb_ncu.json")) as f:
-                nc = json.load(f)
-            traffic = (float(nc["dram__bytes_read.sum"]["value"]) + float(nc["dram__bytes_write.sum"]["value"])) * 1e9
-    except Exception:  # noqa: BLE001
-        pass
+    if (N, T, K, dim) == (1_000_000, 50, 5, 2):
+        from bench import ncu_dram_bytes
+        traffic = ncu_dram_bytes(os.path.join(ROOT, "profiles", "r01b_k_fb_ncu.json"))
     ach = alg / (tot / a.steps * 1e-3) / 1e9
     roofline = dict(bound="hbm", kernel="k_fb<5,2> (emissions + scaled forward + backward + gamma + xi, one thread per "
                                         "sequence)", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak,

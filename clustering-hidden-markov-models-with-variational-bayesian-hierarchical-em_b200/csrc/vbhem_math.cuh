@@ -1,7 +1,7 @@
 // vbhem_math.cuh -- lean fp64 exp / log for the lattice kernels.
 //
 // The E-step is bound by the fp64 pipe AND by register-file read bandwidth (a DFMA with three
-// distinct register operands issues every 3 cycles, not 2: profiles/r02_pipe_overlap.json), and
+// distinct register operands issues every 3 cycles, not 2: profiles/r01b_pipe_overlap.json), and
 // libdevice's exp / log cost 19 / 47 DFMA-equivalents per call on B200
 // (profiles/r01_fp64_peaks.json), most of it range and special-case handling these call sites never
 // need.  Two ideas remove nearly all of that:
