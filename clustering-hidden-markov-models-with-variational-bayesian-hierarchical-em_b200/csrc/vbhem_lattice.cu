@@ -35,9 +35,6 @@
 
 #include <type_traits>
 
-#ifndef VB_SPLIT_ACC
-#define VB_SPLIT_ACC 0
-#endif
 
 namespace vbhem {
 
@@ -84,15 +81,9 @@ __device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b)
 }
 // D(m|n) = sum_c A[m][c] * X[n][c], all three in accumulator layout.
 __device__ __forceinline__ void mma_nt_acc(Frag &D, const Frag &A, const Frag &X) {
-#if VB_SPLIT_ACC
-  Frag D2{0.0, 0.0};
-  dmma(D.x0, D.x1, A.x0, X.x0);
-  dmma(D2.x0, D2.x1, A.x1, X.x1);
-  D.x0 += D2.x0; D.x1 += D2.x1;
-#else
+  // one accumulator chain: splitting it costs two DADDs and is slower (profiles/r01b_sweep_occupancy.log)
   dmma(D.x0, D.x1, A.x0, X.x0);
   dmma(D.x0, D.x1, A.x1, X.x1);
-#endif
 }
 __device__ __forceinline__ Frag mma_nt(const Frag &A, const Frag &X) {
   Frag D{0.0, 0.0};
@@ -126,7 +117,6 @@ struct BaseConst {
   Frag Ab;        // Ab(beta' = g | beta = 2q+e)  = A[from g, to 2q+e]
   Frag AbT;       // [g][2q+e] = A[from 2q+e, to g]
   double prior;   // prior[g]
-  Frag priorT;    // prior[2q+e], the same in every row g
   double mu[D];   // centres of state g
   double cov[DD]; // covars of state g
   int Sb;
@@ -144,8 +134,6 @@ __device__ __forceinline__ void load_base(BaseConst<D, FULL> &b, const BaseView 
   b.AbT.x0 = (g < ld && c0 < ld) ? A[c0 + ld * g] : 0.0;
   b.AbT.x1 = (g < ld && c1 < ld) ? A[c1 + ld * g] : 0.0;
   b.prior = g < ld ? B.prior[g + (size_t)ld * i] : 0.0;
-  b.priorT.x0 = c0 < ld ? B.prior[c0 + (size_t)ld * i] : 0.0;
-  b.priorT.x1 = c1 < ld ? B.prior[c1 + (size_t)ld * i] : 0.0;
 #pragma unroll
   for (int k = 0; k < D; k++) b.mu[k] = g < ld ? B.mu[k + D * (g + (size_t)ld * i)] : 0.0;
 #pragma unroll
@@ -203,6 +191,59 @@ __device__ __forceinline__ Frag emission(const BaseConst<D, FULL> &b, const doub
     // states: any finite row works (their weights are zero); 0 keeps S = rowsum(expA).
     const double v = (-0.5 * kPerUnit) * acc;
     out[e] = (g < b.Sb) ? (v < kUnitsFloor ? kUnitsFloor : v) : (isinf(rec[72 + sg]) ? kUnitsFloor : 0.0);
+  }
+  return Frag{out[0], out[1]};
+}
+
+// First-pass versions on a centre record staged in shared memory (32-bit shared address `rec`): the two
+// elements of a lane (sigma = 2q, 2q+1) sit next to each other in every block of the record, so every
+// quantity arrives in 16-byte loads.
+__device__ __forceinline__ Frag lds_frag(unsigned saddr) {
+  Frag f;
+  asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(f.x0), "=d"(f.x1) : "r"(saddr));
+  return f;
+}
+template <int D, bool FULL>
+__device__ __forceinline__ Frag emission_smem(const BaseConst<D, FULL> &b, unsigned rec, int g, int q) {
+  constexpr int DD = BaseConst<D, FULL>::DD;
+  const Frag c0 = lds_frag(rec + 8u * (72 + 2 * q));
+  double m[2 * D], P[2 * DD];
+#pragma unroll
+  for (int k = 0; k < D; k++) {
+    const Frag f = lds_frag(rec + 8u * (80 + 2 * D * q + 2 * k));
+    m[2 * k] = f.x0; m[2 * k + 1] = f.x1;
+  }
+#pragma unroll
+  for (int k = 0; k < DD; k++) {
+    const Frag f = lds_frag(rec + 8u * (80 + 8 * D + 2 * DD * q + 2 * k));
+    P[2 * k] = f.x0; P[2 * k + 1] = f.x1;
+  }
+  double out[2];
+#pragma unroll
+  for (int e = 0; e < 2; e++) {
+    const double *me = m + e * D, *Pe = P + e * DD;
+    double acc = e ? c0.x1 : c0.x0;
+    if (FULL) {
+#pragma unroll
+      for (int k = 0; k < DD; k++) acc += Pe[k] * b.cov[k];
+#pragma unroll
+      for (int tj = 0; tj < D; tj++) {
+        double t = 0.0;
+#pragma unroll
+        for (int ti = 0; ti < D; ti++) t += (b.mu[ti] - me[ti]) * Pe[ti + D * tj];
+        acc += t * (b.mu[tj] - me[tj]);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < D; k++) {
+        const double df = b.mu[k] - me[k];
+        acc += Pe[k] * b.cov[k];
+        acc += Pe[k] * (df * df);
+      }
+    }
+    // see emission(); a padded base row takes 0 everywhere (its weights are zero, any finite row works)
+    const double v = (-0.5 * kPerUnit) * acc;
+    out[e] = (g < b.Sb) ? (v < kUnitsFloor ? kUnitsFloor : v) : 0.0;
   }
   return Frag{out[0], out[1]};
 }
@@ -286,9 +327,6 @@ __device__ __forceinline__ double terminate(const Frag &G, const Frag &expPi, do
 #endif
 #ifndef VB_NP
 #define VB_NP 2             // pairs in flight per warp
-#endif
-#ifndef VB_TERM_STEP
-#define VB_TERM_STEP 0
 #endif
 #ifndef VB_KC_BYTES
 #define VB_KC_BYTES (64 * 1024)   // shared-memory budget for centre records per CTA
@@ -390,6 +428,8 @@ k_lattice_bwd(BaseView B, CentreView C, int T, int kc, double *L_elbo, Fallback 
   int one;   // 0x3ff00000 pinned in a register (see mant_hi)
   asm volatile("mov.b32 %0, 0x3ff00000;" : "=r"(one));
   double *recs = smem + TabFirst::kDoubles;
+  constexpr int RS = 80 + 8 * D + 8 * BaseConst<D, FULL>::DD;              // lattice_rec_stride(d, dd)
+  const unsigned recs_s = (unsigned)__cvta_generic_to_shared(recs);
   TabFirst::load(smem);
   for (int x = threadIdx.x; x < nj * rs; x += blockDim.x) recs[x] = C.rec[(size_t)j0 * rs + x];
   __syncthreads();
@@ -399,45 +439,48 @@ k_lattice_bwd(BaseView B, CentreView C, int T, int kc, double *L_elbo, Fallback 
     load_base(b, B, i, g, q);
     const bool base_chk = base_bad(b.Ab, b.prior);
     for (int jj = 0; jj < nj; jj += kNP) {
-      Frag E[kNP], G[kNP], expA[kNP], expPi[kNP], Z[kNP];
+      Frag E[kNP], G[kNP], expA[kNP], expPi[kNP];
       unsigned rng[kNP];
       bool bad[kNP];
 #pragma unroll
       for (int p = 0; p < kNP; p++) {
-        const double *rec = recs + min(jj + p, nj - 1) * rs;   // odd tail: redo the last centre, not stored
-        CentreConst<D, FULL> c;
-        load_centre(c, rec, g, q);
-        expA[p] = c.expA;
-        expPi[p] = c.expPi;
-        E[p] = emission(b, rec, g, q);
+        const unsigned rec = recs_s + 8u * RS * (unsigned)min(jj + p, nj - 1);   // odd tail: redo the last centre, not stored
+        expA[p] = lds_frag(rec + 8u * (g * 8 + 2 * q));
+        expPi[p] = lds_frag(rec + 8u * (64 + 2 * q));
+        E[p] = emission_smem<D, FULL>(b, rec, g, q);
         G[p] = E[p];
-        Z[p] = Frag{0.0, 0.0};
         rng[p] = 0u;
         bad[p] = pair_inputs_bad(base_chk, E[p]);
       }
       for (int t = T - 1; t >= 1; t--) bwd_step_n<kNP, 8, 16>(E, G, expA, b.Ab, ltab, etab, rng, q, one);
-      // Termination (vbhem_hmm_bwd_fwd_mex.c:1029-1080) is one more step of the same shape with
-      // logPi in place of every row of logA and the prior in place of every row of A_b:
-      //   S(rho|beta) = sum_sigma expPi[sigma] Bm[beta,sigma]   (the same for every rho)
-      //   G(beta'|rho) = sum_beta prior[beta] lse[beta]          = L_elbo in every element
-#if VB_TERM_STEP
-      bwd_step_n<kNP, 8, 16>(Z, G, expPi, b.priorT, ltab, etab, rng, q, one);
-#else
+      // termination (vbhem_hmm_bwd_fwd_mex.c:1029-1080); running it as one more lattice step (logPi for every
+      // row of logA, the prior for every row of A_b) needs no special code but twice the fp64 work: slower
       double Lt[kNP];
       terminate_n<kNP, 8, 16>(G, expPi, b.prior, ltab, etab, q, rng, Lt);
-#endif
+      if constexpr (kNP == 2) {
+        // Lt[0] == Lt[1] holds pair 0's value in lane 0 and pair 1's in lane 1: one store for both; the
+        // (rare) flagged pairs take the slow path
+        const bool ok = (max(rng[0], rng[1]) <= kShiftBound) & !(bad[0] | bad[1]);
+        const bool all_ok = __all_sync(0xffffffffu, ok);
+        const size_t pi = (size_t)i + (size_t)B.N * (j0 + jj + lane);
+        if (lane < 2 && jj + lane < nj) L_elbo[pi] = Lt[0];
+        if (!all_ok) {
 #pragma unroll
-      for (int p = 0; p < kNP; p++) {
-#if VB_TERM_STEP
-        const double Le = G[p].x0 * kUnit;
-#else
-        const double Le = Lt[p];
-#endif
-        const bool good = __all_sync(0xffffffffu, (rng[p] <= kShiftBound) & !bad[p]);
-        if (lane == (kNP == 2 && !VB_TERM_STEP ? p : 0) && jj + p < nj) {
-          const size_t pi = (size_t)i + (size_t)B.N * (j0 + jj + p);
-          L_elbo[pi] = Le;
-          if (!good) { fb.flags[pi] = 1; atomicAdd(fb.count, 1); }
+          for (int p = 0; p < 2; p++) {
+            const bool good = __all_sync(0xffffffffu, (rng[p] <= kShiftBound) & !bad[p]);
+            if (!good && lane == p && jj + p < nj) { fb.flags[pi] = 1; atomicAdd(fb.count, 1); }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int p = 0; p < kNP; p++) {
+          const double Le = Lt[p];
+          const bool good = __all_sync(0xffffffffu, (rng[p] <= kShiftBound) & !bad[p]);
+          if (lane == 0 && jj + p < nj) {
+            const size_t pi = (size_t)i + (size_t)B.N * (j0 + jj + p);
+            L_elbo[pi] = Le;
+            if (!good) { fb.flags[pi] = 1; atomicAdd(fb.count, 1); }
+          }
         }
       }
     }
