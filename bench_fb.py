@@ -130,6 +130,18 @@ def main_fb(a):
         check(L.vbhmm_fb_dev(seqs._h, *model))
         check(L.vbhmm_fb_last_ms(seqs._h, C.byref(ms)))           # CUDA events on the kernel's own stream
         tot += ms.value
+    # the EM-iteration form: the same pass fused with the sums vbhmm_em takes from it (vbhmm_fb_stats); only
+    # 2K + K^2 + K dim + K dim^2 + 2 doubles come back, so this is also its end-to-end time per EM iteration
+    st = [np.zeros(K), np.zeros(K), np.zeros((K, K)), np.zeros((dim, K)), np.zeros((K, dim, dim)), np.zeros(2)]
+    stats_ms, stats_wall = [], []
+    for i in range(W + a.steps):
+        t0 = time.perf_counter()
+        check(L.vbhmm_fb_stats(seqs._h, *model, *[P(x) for x in st]))
+        dtw = time.perf_counter() - t0
+        check(L.vbhmm_fb_last_ms(seqs._h, C.byref(ms)))
+        if i >= W:
+            stats_ms.append(ms.value)
+            stats_wall.append(1e3 * dtw)
     sampler.armed = False
     sampler.stop_flag = True
     sampler.join()
@@ -185,7 +197,13 @@ def main_fb(a):
         seqs.close()
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=1, steps=a.steps, warmup=W, ms_per_step=tot / a.steps,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic", config=config,
-                clocks=sampler.summary(), e2e=e2e, gpu_launches=a.steps, roofline=roofline)
+                clocks=sampler.summary(), e2e=e2e, gpu_launches=a.steps + 3 * a.steps, roofline=roofline,
+                em_iteration=dict(device_ms=statistics.median(stats_ms), wall_ms=statistics.median(stats_wall),
+                                  sequences_per_s=N / (statistics.median(stats_wall) * 1e-3),
+                                  d2h_bytes=int(sum(x.nbytes for x in st)),
+                                  note="vbhmm_fb_stats: forward-backward + the M-step sums of vbhmm_em.m:158-246 + Lt63 / "
+                                       "Lt64 on the device, observations resident (packed once per vbhmm_em run); wall_ms "
+                                       "is host wall clock of the C-ABI call including the result copy"))
     if cpu is not None:
         line["cpu_baseline"] = cpu
     real_stdout.write(json.dumps(line) + "\n")

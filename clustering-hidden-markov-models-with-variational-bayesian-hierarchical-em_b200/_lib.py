@@ -60,6 +60,7 @@ SIGNATURES = {
     "vbhmm_fb": (C.c_int, [vp, C.c_int, dp, dp, dp, dp, dp, C.c_double, dp, dp, dp, dp, dp, dp]),
     "vbhmm_fb_dev": (C.c_int, [vp, C.c_int, dp, dp, dp, dp, dp, C.c_double, dp, dp]),
     "vbhmm_fb_fetch": (C.c_int, [vp, dp, dp, dp, dp]),
+    "vbhmm_fb_stats": (C.c_int, [vp, C.c_int, dp, dp, dp, dp, dp, C.c_double, dp, dp, dp, dp, dp, dp, dp, dp]),
     "vbhmm_fb_last_ms": (C.c_int, [vp, dp]),
     "vbhem_set_profile": (C.c_int, [vp, C.c_int]),
     "vbhem_last_timings": (C.c_int, [vp, dp]),

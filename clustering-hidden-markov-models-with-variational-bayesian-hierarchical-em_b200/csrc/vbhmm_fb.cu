@@ -125,7 +125,7 @@ k_fb(const __grid_constant__ FbPar<K, DIM> P, int N, int maxT, const int *__rest
   const int T = Tn[n];
   const size_t NK = (size_t)N * K, ND = (size_t)N * DIM;
   const double *xp = X + (size_t)DIM * n;
-  double *lp = logrho + (size_t)K * n, *gp = gamma + (size_t)K * n;
+  double *lp = logrho ? logrho + (size_t)K * n : nullptr, *gp = gamma + (size_t)K * n;
   double alpha[K], p[K], lr[K], x[DIM], xn[DIM];
   double sumlogc = 0.0, summax = 0.0;
 
@@ -141,8 +141,10 @@ k_fb(const __grid_constant__ FbPar<K, DIM> P, int N, int maxT, const int *__rest
       for (int i = 0; i < DIM; i++) xn[i] = xp[ND * (t + 1) + i];
     }
     emissions<K, DIM>(P, x, lr);
+    if (logrho) {
 #pragma unroll
-    for (int k = 0; k < K; k++) __stcs(lp + NK * t + k, lr[k]);
+      for (int k = 0; k < K; k++) __stcs(lp + NK * t + k, lr[k]);
+    }
     summax += shifted_exp<K>(lr, p);
     double delta[K], c;
     if (t == 0) {
@@ -161,7 +163,7 @@ k_fb(const __grid_constant__ FbPar<K, DIM> P, int N, int maxT, const int *__rest
   // zeros beyond the sequence's own length (the reference's outputs start as zeros)
   for (int t = T; t < maxT; t++) {
 #pragma unroll
-    for (int k = 0; k < K; k++) { __stcs(lp + NK * t + k, 0.0); __stcs(gp + NK * t + k, 0.0); }
+    for (int k = 0; k < K; k++) { if (logrho) __stcs(lp + NK * t + k, 0.0); __stcs(gp + NK * t + k, 0.0); }
   }
 
   // ---- backward, responsibilities, summed pair marginals (vbhmm_fb.m:349-377).  The K x K accumulator of
@@ -221,6 +223,121 @@ k_fb(const __grid_constant__ FbPar<K, DIM> P, int N, int maxT, const int *__rest
   for (int k = 0; k < K; k++)
 #pragma unroll
     for (int j = 0; j < K; j++) __stcs(xo + j + K * k, xi[(j * K + k) * kFbThreads]);
+}
+
+// ---- M-step statistics of vbhmm_em.m:158-246 and the fb-dependent lower-bound terms (vbhmm_em_lb.m:214,217)
+// straight from the responsibilities in HBM, so that gamma_all / logrho_Saved never cross PCIe:
+//   Nk1(k) = sum_n gamma(k,n,1), Nk(k) = sum_{n,t} gamma, M = sum_n xi_sum,
+//   first / second moments of the observations about the CURRENT means m_k (no cancellation),
+//   Lt63 = sum gamma .* logrho (logrho recomputed from X), Lt64 = sum phi_norm.
+// One thread per (n, t) element, grid-stride; fixed grid => fixed-order (deterministic) sums.
+constexpr int kMomThreads = 256;
+template <int K, int DIM>
+struct MomLayout {
+  static constexpr int DD = DIM * DIM;
+  static constexpr int nk1 = 0, nk = K, sx = 2 * K, sxx = 2 * K + K * DIM, M = 2 * K + K * DIM + K * DD,
+                       lt63 = M + K * K, lt64 = lt63 + 1, total = lt64 + 1;
+};
+
+template <int NV>
+__device__ __forceinline__ void block_reduce_store(double (&acc)[NV], double *out) {
+  __shared__ double sh[kMomThreads / 32][NV];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int v = 0; v < NV; v++) {
+    double a = acc[v];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) sh[warp][v] = a;
+  }
+  __syncthreads();
+  for (int v = threadIdx.x; v < NV; v += kMomThreads) {
+    double a = 0.0;
+    for (int w = 0; w < kMomThreads / 32; w++) a += sh[w][v];
+    out[v] = a;
+  }
+}
+
+template <int K, int DIM>
+__global__ void __launch_bounds__(kMomThreads)
+k_fb_moments(const __grid_constant__ FbPar<K, DIM> P, int N, int maxT, const double *__restrict__ X,
+             const double *__restrict__ gamma, const double *__restrict__ xi_sum, const double *__restrict__ phi,
+             double *__restrict__ partial) {
+  using L = MomLayout<K, DIM>;
+  double acc[L::total];
+#pragma unroll
+  for (int v = 0; v < L::total; v++) acc[v] = 0.0;
+  const long long tot = (long long)N * maxT, stride = (long long)gridDim.x * kMomThreads;
+  for (long long e = (long long)blockIdx.x * kMomThreads + threadIdx.x; e < tot; e += stride) {
+    double g[K], x[DIM], lr[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) g[k] = __ldcs(gamma + (size_t)K * e + k);
+#pragma unroll
+    for (int i = 0; i < DIM; i++) x[i] = X[(size_t)DIM * e + i];
+    emissions<K, DIM>(P, x, lr);
+    const bool first = e < N;                                   // t == 0
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      if (first) acc[L::nk1 + k] += g[k];
+      acc[L::nk + k] += g[k];
+      acc[L::lt63] += g[k] * lr[k];
+      double diff[DIM];
+#pragma unroll
+      for (int i = 0; i < DIM; i++) diff[i] = x[i] - P.m[k][i];
+#pragma unroll
+      for (int i = 0; i < DIM; i++) {
+        const double gd = g[k] * diff[i];
+        acc[L::sx + k * DIM + i] += gd;
+#pragma unroll
+        for (int j = 0; j < DIM; j++) acc[L::sxx + (k * DIM + i) * DIM + j] += gd * diff[j];
+      }
+    }
+  }
+  for (long long n = (long long)blockIdx.x * kMomThreads + threadIdx.x; n < N; n += stride) {
+    acc[L::lt64] += phi[n];
+#pragma unroll
+    for (int q = 0; q < K * K; q++) acc[L::M + q] += __ldcs(xi_sum + (size_t)K * K * n + q);   // [from + K * to]
+  }
+  block_reduce_store<L::total>(acc, partial + (size_t)L::total * blockIdx.x);
+}
+
+// Fixed-order sum over the blocks, then the normalisation of vbhmm_em.m:161-246.
+// out: Nk1[K] | Nk[K] | M[K,K] | xbar[K,dim] (row k) | S[dim,dim,K] | Lt63 | Lt64
+template <int K, int DIM>
+__global__ void k_fb_moments_finish(const __grid_constant__ FbPar<K, DIM> P, int nblocks,
+                                    const double *__restrict__ partial, double *__restrict__ out) {
+  using L = MomLayout<K, DIM>;
+  __shared__ double s[L::total];
+  for (int v = threadIdx.x; v < L::total; v += blockDim.x) {
+    double a = 0.0;
+    for (int b = 0; b < nblocks; b++) a += partial[(size_t)L::total * b + v];
+    s[v] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  double *o = out;
+  for (int k = 0; k < K; k++) o[k] = s[L::nk1 + k] + 1e-50;                       // vbhmm_em.m:163
+  o += K;
+  for (int k = 0; k < K; k++) o[k] = s[L::nk + k] + 1e-50;                        // :171-172
+  o += K;
+  for (int q = 0; q < K * K; q++) o[q] = s[L::M + q];                             // :178
+  o += K * K;
+  double *xb = o, *S = o + K * DIM;
+  for (int k = 0; k < K; k++) {
+    const double nk = s[L::nk + k], Nk = nk + 1e-50;
+    double del[DIM];                                                              // xbar - m_k
+    for (int i = 0; i < DIM; i++) {
+      xb[k + K * i] = (P.m[k][i] * nk + s[L::sx + k * DIM + i]) / Nk;             // :216-219, [K x dim] column-major
+      del[i] = xb[k + K * i] - P.m[k][i];
+    }
+    for (int i = 0; i < DIM; i++)
+      for (int j = 0; j < DIM; j++)                                               // :240-245 about xbar
+        S[i + DIM * (j + DIM * k)] = (s[L::sxx + (k * DIM + i) * DIM + j] - s[L::sx + k * DIM + i] * del[j] -
+                                      del[i] * s[L::sx + k * DIM + j] + nk * del[i] * del[j]) / Nk;
+  }
+  o = S + DIM * DIM * K;
+  o[0] = s[L::lt63];
+  o[1] = s[L::lt64];
 }
 
 // Any K <= 32, dim <= 8: the same recursion with the model in global memory and local arrays.
@@ -332,7 +449,7 @@ struct vbhmm_data {
   int device = 0, N = 0, dim = 0, maxT = 0;
   long long total = 0;         // sum_n T_n
   cudaStream_t st = nullptr;
-  Buf Tn, X, par, logrho, gamma, xi, phi;
+  Buf Tn, X, par, logrho, gamma, xi, phi, mom_partial, mom_out;
   cudaEvent_t ev[2] = {nullptr, nullptr};
   double last_ms = 0.0;
   int lastK = 0;
@@ -340,9 +457,11 @@ struct vbhmm_data {
 
 namespace {
 
+// stats == false: the literal pass (all four outputs).  stats == true: no logrho store, then the moment kernels
+// (results in h->mom_out, layout of k_fb_moments_finish).
 template <int K, int DIM>
 int launch_fb_t(vbhmm_data *h, const double *m, const double *W, const double *v, const double *beta,
-                const double *lLT, double cden, const double *pz1, const double *A) {
+                const double *lLT, double cden, const double *pz1, const double *A, bool stats) {
   FbPar<K, DIM> P;
   for (int k = 0; k < K; k++) {
     for (int i = 0; i < DIM; i++) {
@@ -360,27 +479,44 @@ int launch_fb_t(vbhmm_data *h, const double *m, const double *W, const double *v
 #endif
   cudaFuncSetAttribute(k_fb<K, DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k_fb<K, DIM><<<blocks, kFbThreads, smem, h->st>>>(P, h->N, h->maxT, h->Tn.as<int>(), h->X.as<double>(),
-                                                 h->logrho.as<double>(), h->gamma.as<double>(), h->xi.as<double>(),
-                                                 h->phi.as<double>());
-  return 1;
+                                                 stats ? nullptr : h->logrho.as<double>(), h->gamma.as<double>(),
+                                                 h->xi.as<double>(), h->phi.as<double>());
+  if (!stats) return 1;
+  using L = MomLayout<K, DIM>;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+  const long long tot = (long long)h->N * h->maxT;
+  long long want = (tot + kMomThreads - 1) / kMomThreads;
+  const int mb = (int)(want < 1 ? 1 : (want > 8LL * sms ? 8LL * sms : want));
+  if (h->mom_partial.ensure(sizeof(double) * (size_t)L::total * mb) != cudaSuccess ||
+      h->mom_out.ensure(sizeof(double) * L::total) != cudaSuccess)
+    return -1;
+  k_fb_moments<K, DIM><<<mb, kMomThreads, 0, h->st>>>(P, h->N, h->maxT, h->X.as<double>(), h->gamma.as<double>(),
+                                                      h->xi.as<double>(), h->phi.as<double>(),
+                                                      h->mom_partial.as<double>());
+  k_fb_moments_finish<K, DIM><<<1, 128, 0, h->st>>>(P, mb, h->mom_partial.as<double>(), h->mom_out.as<double>());
+  return 3;
 }
 
 template <int K>
 int launch_fb_k(vbhmm_data *h, const double *m, const double *W, const double *v, const double *beta,
-                const double *lLT, double cden, const double *pz1, const double *A) {
+                const double *lLT, double cden, const double *pz1, const double *A, bool stats) {
   switch (h->dim) {
-    case 1: return launch_fb_t<K, 1>(h, m, W, v, beta, lLT, cden, pz1, A);
-    case 2: return launch_fb_t<K, 2>(h, m, W, v, beta, lLT, cden, pz1, A);
-    case 3: return launch_fb_t<K, 3>(h, m, W, v, beta, lLT, cden, pz1, A);
+    case 1: return launch_fb_t<K, 1>(h, m, W, v, beta, lLT, cden, pz1, A, stats);
+    case 2: return launch_fb_t<K, 2>(h, m, W, v, beta, lLT, cden, pz1, A, stats);
+    case 3: return launch_fb_t<K, 3>(h, m, W, v, beta, lLT, cden, pz1, A, stats);
   }
   return 0;
 }
 
 int run_fb(vbhmm_data *h, int K, const double *m, const double *W, const double *v, const double *beta,
-           const double *lLT, double cden, const double *pz1, const double *A) {
+           const double *lLT, double cden, const double *pz1, const double *A, bool stats = false) {
   const int N = h->N, dim = h->dim;
   const size_t nkt = (size_t)K * N * (h->maxT > 0 ? h->maxT : 1);
-  CU(h->logrho.ensure(sizeof(double) * nkt));
+  if (stats && !(K <= kFbMaxK && dim <= kFbMaxDim))
+    return fail_fb(VBHEM_EINVAL, "vbhmm_fb_mex:invalidinput: vbhmm_fb_stats takes K <= %d, dim <= %d (use vbhmm_fb)",
+                   kFbMaxK, kFbMaxDim);
+  if (!stats) CU(h->logrho.ensure(sizeof(double) * nkt));
   CU(h->gamma.ensure(sizeof(double) * nkt));
   CU(h->xi.ensure(sizeof(double) * (size_t)K * K * N));
   CU(h->phi.ensure(sizeof(double) * (size_t)N));
@@ -388,16 +524,17 @@ int run_fb(vbhmm_data *h, int K, const double *m, const double *W, const double 
   int launched = 0;
   if (K <= kFbMaxK && dim <= kFbMaxDim) {
     switch (K) {
-      case 1: launched = launch_fb_k<1>(h, m, W, v, beta, lLT, cden, pz1, A); break;
-      case 2: launched = launch_fb_k<2>(h, m, W, v, beta, lLT, cden, pz1, A); break;
-      case 3: launched = launch_fb_k<3>(h, m, W, v, beta, lLT, cden, pz1, A); break;
-      case 4: launched = launch_fb_k<4>(h, m, W, v, beta, lLT, cden, pz1, A); break;
-      case 5: launched = launch_fb_k<5>(h, m, W, v, beta, lLT, cden, pz1, A); break;
-      case 6: launched = launch_fb_k<6>(h, m, W, v, beta, lLT, cden, pz1, A); break;
-      case 7: launched = launch_fb_k<7>(h, m, W, v, beta, lLT, cden, pz1, A); break;
-      case 8: launched = launch_fb_k<8>(h, m, W, v, beta, lLT, cden, pz1, A); break;
+      case 1: launched = launch_fb_k<1>(h, m, W, v, beta, lLT, cden, pz1, A, stats); break;
+      case 2: launched = launch_fb_k<2>(h, m, W, v, beta, lLT, cden, pz1, A, stats); break;
+      case 3: launched = launch_fb_k<3>(h, m, W, v, beta, lLT, cden, pz1, A, stats); break;
+      case 4: launched = launch_fb_k<4>(h, m, W, v, beta, lLT, cden, pz1, A, stats); break;
+      case 5: launched = launch_fb_k<5>(h, m, W, v, beta, lLT, cden, pz1, A, stats); break;
+      case 6: launched = launch_fb_k<6>(h, m, W, v, beta, lLT, cden, pz1, A, stats); break;
+      case 7: launched = launch_fb_k<7>(h, m, W, v, beta, lLT, cden, pz1, A, stats); break;
+      case 8: launched = launch_fb_k<8>(h, m, W, v, beta, lLT, cden, pz1, A, stats); break;
     }
   }
+  if (launched < 0) return fail_fb(VBHEM_ENOMEM, "out of device memory for the moment partials");
   if (!launched) {
     // model to HBM: m | W | v | dob | lLT | pz1 | A
     const size_t nd = (size_t)dim * K + (size_t)dim * dim * K + 4 * (size_t)K + (size_t)K * K;
@@ -430,7 +567,7 @@ int run_fb(vbhmm_data *h, int K, const double *m, const double *W, const double 
   }
   CU(cudaEventRecord(h->ev[1], h->st));
   CU(cudaGetLastError());
-  h->lastK = K;
+  h->lastK = stats ? -K : K;   // after a statistics pass logrho is not available for vbhmm_fb_fetch
   return VBHEM_OK;
 }
 
@@ -507,7 +644,7 @@ int vbhmm_free_data(vbhmm_data_t *h) {
   cudaSetDevice(h->device);
   if (h->st) { cudaStreamSynchronize(h->st); cudaStreamDestroy(h->st); }
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
-  Buf *all[] = {&h->Tn, &h->X, &h->par, &h->logrho, &h->gamma, &h->xi, &h->phi};
+  Buf *all[] = {&h->Tn, &h->X, &h->par, &h->logrho, &h->gamma, &h->xi, &h->phi, &h->mom_partial, &h->mom_out};
   for (Buf *b : all) b->release();
   delete h;
   return VBHEM_OK;
@@ -532,7 +669,7 @@ int vbhmm_fb_dev(vbhmm_data_t *h, int K, const double *m, const double *W, const
 
 int vbhmm_fb_fetch(vbhmm_data_t *h, double *logrho_Saved, double *gamma_all, double *xi_sum, double *phi_norm) {
   if (!h) return fail_fb(VBHEM_EINVAL, "vbhmm_fb_mex:invalidinput: data handle is NULL");
-  if (h->lastK < 1) return fail_fb(VBHEM_EINVAL, "no forward-backward pass has run on this handle");
+  if (h->lastK < 1) return fail_fb(VBHEM_EINVAL, "no literal forward-backward pass (vbhmm_fb / vbhmm_fb_dev) has run last");
   CU(cudaSetDevice(h->device));
   const int K = h->lastK;
   const size_t nkt = (size_t)K * h->N * h->maxT;
@@ -550,6 +687,34 @@ int vbhmm_fb(vbhmm_data_t *h, int K, const double *m, const double *W, const dou
   int rc = vbhmm_fb_dev(h, K, m, W, v, beta, logLambdaTilde, const_denominator, pz1, tpztzt1);
   if (rc) return rc;
   return vbhmm_fb_fetch(h, logrho_Saved, gamma_all, xi_sum, phi_norm);
+}
+
+int vbhmm_fb_stats(vbhmm_data_t *h, int K, const double *m, const double *W, const double *v, const double *beta,
+                   const double *logLambdaTilde, double const_denominator, const double *pz1, const double *tpztzt1,
+                   double *Nk1, double *Nk, double *M, double *xbar, double *S, double *lb2) {
+  int rc = check_model(h, K, m, W, v, beta, logLambdaTilde, pz1, tpztzt1);
+  if (rc) return rc;
+  CU(cudaSetDevice(h->device));
+  rc = run_fb(h, K, m, W, v, beta, logLambdaTilde, const_denominator, pz1, tpztzt1, true);
+  if (rc) return rc;
+  const int d = h->dim;
+  const size_t tot = 2 * (size_t)K + (size_t)K * K + (size_t)K * d + (size_t)d * d * K + 2;
+  std::vector<double> host(tot);
+  CU(cudaMemcpyAsync(host.data(), h->mom_out.p, sizeof(double) * tot, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  const double *q = host.data();
+  if (Nk1) memcpy(Nk1, q, sizeof(double) * K);
+  q += K;
+  if (Nk) memcpy(Nk, q, sizeof(double) * K);
+  q += K;
+  if (M) memcpy(M, q, sizeof(double) * K * K);
+  q += (size_t)K * K;
+  if (xbar) memcpy(xbar, q, sizeof(double) * K * d);
+  q += (size_t)K * d;
+  if (S) memcpy(S, q, sizeof(double) * d * d * K);
+  q += (size_t)d * d * K;
+  if (lb2) { lb2[0] = q[0]; lb2[1] = q[1]; }
+  return VBHEM_OK;
 }
 
 int vbhmm_fb_last_ms(vbhmm_data_t *h, double *ms) {

@@ -119,6 +119,27 @@ def fb_call(seqs: SequenceSet, par: dict, want=("logrho_Saved", "gamma_all", "xi
     return out
 
 
+def fb_stats(seqs: SequenceSet, hmm_varpar: dict) -> dict:
+    """One forward-backward pass fused with the sums ``vbhmm_em`` takes from it (vbhmm_em.m:158-246,
+    vbhmm_em_lb.m:214,217) -- ``vbhmm_fb_stats``: nothing of size N leaves the device.
+    Returns Nk1[K], Nk[K], M[K(from),K(to)], xbar[K,dim], S[K,dim,dim], Lt63, Lt64 and the pre-pass results."""
+    c = np.ascontiguousarray
+    par = prepass(hmm_varpar)
+    K, dim = par["m"].shape
+    m = c(par["m"], dtype=np.float64)
+    W = c(np.transpose(par["W"], (0, 2, 1)), dtype=np.float64)
+    A = c(np.asarray(par["A"], float).T)
+    Nk1, Nk, M, xb, S, lb = np.zeros(K), np.zeros(K), np.zeros((K, K)), np.zeros((dim, K)), np.zeros((K, dim, dim)), np.zeros(2)
+    P = lambda a: a.ctypes.data_as(dp)
+    check(lib().vbhmm_fb_stats(seqs._h, K, P(m), P(W), P(c(par["v"], dtype=np.float64)),
+                               P(c(par["beta"], dtype=np.float64)), P(c(par["logLambdaTilde"], dtype=np.float64)),
+                               C.c_double(float(par["const_denominator"])), P(c(par["pz1"], dtype=np.float64)), P(A),
+                               P(Nk1), P(Nk), P(M), P(xb), P(S), P(lb)))
+    return dict(Nk1=Nk1, Nk=Nk, M=M.T.copy(), xbar=xb.T.copy(), S=np.transpose(S, (0, 2, 1)).copy(), Lt63=lb[0],
+                Lt64=lb[1], logLambdaTilde=par["logLambdaTilde"], logPiTilde=par["logPiTilde"],
+                logATilde=par["logATilde"])
+
+
 def vbhmm_fb(data, hmm_varpar: dict, opt: dict | None = None) -> dict:
     """[fbstats] = vbhmm_fb(data, hmm_varpar, opt)  (vbhmm_fb.m:1).
 

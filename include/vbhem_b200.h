@@ -233,6 +233,16 @@ int vbhmm_fb(vbhmm_data_t *data, int K, const double *m, const double *W, const 
 int vbhmm_fb_dev(vbhmm_data_t *data, int K, const double *m, const double *W, const double *v, const double *beta,
                  const double *logLambdaTilde, double const_denominator, const double *pz1, const double *tpztzt1);
 int vbhmm_fb_fetch(vbhmm_data_t *data, double *logrho_Saved, double *gamma_all, double *xi_sum, double *phi_norm);
+/* The same pass fused with what vbhmm_em consumes (/root/reference/src/hmm/vbhmm_em.m:158-246 and the
+ * fb-dependent lower-bound terms of vbhmm_em_lb.m:214,217), so that gamma_all / logrho_Saved never leave the device
+ * during EM (fetch them once at the end with vbhmm_fb):
+ *   Nk1[K] = sum_n gamma(:,n,1) + 1e-50;  Nk[K] = sum_{n,t} gamma + 1e-50;  M[K,K] = sum_n xi_sum (from,to);
+ *   xbar[K,dim] = sum gamma x / Nk;  S[dim,dim,K] = sum gamma (x - xbar)(x - xbar)' / Nk;
+ *   lb2[0] = Lt63 = sum gamma .* logrho_Saved,  lb2[1] = Lt64 = sum phi_norm.
+ * All HOST, column-major, any may be NULL.  K <= 8, dim <= 3. */
+int vbhmm_fb_stats(vbhmm_data_t *data, int K, const double *m, const double *W, const double *v, const double *beta,
+                   const double *logLambdaTilde, double const_denominator, const double *pz1, const double *tpztzt1,
+                   double *Nk1, double *Nk, double *M, double *xbar, double *S, double *lb2);
 int vbhmm_fb_last_ms(vbhmm_data_t *data, double *ms);
 
 /* Phase timing of the handle's E-steps, for bench.py: when enabled, CUDA events are

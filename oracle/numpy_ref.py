@@ -324,3 +324,25 @@ def vbhmm_fb(data: list, par: dict) -> dict:
         out["xi_sum"][n] = xi
         out["phi_norm"][n] = np.log(c).sum() + mx.sum()
     return out
+
+
+def vbhmm_em_stats(data: list, fbstats: dict) -> dict:
+    """vbhmm_em.m:158-246 (responsibility sums, transition counts, ROI means and scatter matrices) and the
+    fb-dependent lower-bound terms vbhmm_em_lb.m:214,217, from the outputs of vbhmm_fb (natural layout)."""
+    gam, xi = fbstats["gamma_all"], fbstats["xi_sum"]                    # [N, maxT, K], [N, from, to]
+    N, maxT, K = gam.shape
+    dim = np.asarray(data[0]).reshape(len(data[0]), -1).shape[1] if len(data[0]) else 1
+    X = np.zeros((N, maxT, dim))
+    for n, x in enumerate(data):
+        if len(x):
+            X[n, :len(x)] = np.asarray(x, float).reshape(len(x), -1)
+    Nk1 = gam[:, 0].sum(0) + 1e-50
+    Nk = gam.sum((0, 1)) + 1e-50
+    M = xi.sum(0)
+    xbar = np.einsum("ntk,ntd->kd", gam, X) / Nk[:, None]
+    S = np.zeros((K, dim, dim))
+    for k in range(K):
+        d1 = X - xbar[k]
+        S[k] = np.einsum("nt,nti,ntj->ij", gam[:, :, k], d1, d1) / Nk[k]
+    return dict(Nk1=Nk1, Nk=Nk, M=M, xbar=xbar, S=S, Lt63=float((gam * fbstats["logrho_Saved"]).sum()),
+                Lt64=float(fbstats["phi_norm"].sum()))

@@ -159,3 +159,32 @@ def test_fb_gateway_matches_reference_golden_and_caches_data():
     data3, vp3 = make_fb_case(N=20, K=2, dim=3, maxT=7, seed=44)
     ps3, par3 = cref.pack_sequences(data3), nr.vbhmm_fb_prepass(vp3)
     assert_fb_close(cref.gateway_vbhmm_fb(ps3, par3), cref.port_vbhmm_fb(ps3, par3))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("K,dim,N,maxT", [(5, 2, 400, 50), (1, 1, 9, 4), (8, 3, 70, 12), (3, 2, 6, 1)])
+def test_cuda_fb_stats_match_vbhmm_em_sums(K, dim, N, maxT):
+    """vbhmm_fb_stats (forward-backward fused with the sums of vbhmm_em.m:158-246) against those sums taken
+    from the oracle's per-step outputs."""
+    from vbhem_b200 import fb
+    data, vp = make_fb_case(N=N, K=K, dim=dim, maxT=maxT, seed=200 + K + dim)
+    want = nr.vbhmm_em_stats(data, cref.port_vbhmm_fb(cref.pack_sequences(data), nr.vbhmm_fb_prepass(vp)))
+    with fb.SequenceSet(data) as seqs:
+        got = fb.fb_stats(seqs, vp)
+        again = fb.fb_stats(seqs, vp)
+        lit = fb.vbhmm_fb(seqs, vp)                       # the literal pass still works on the same handle afterwards
+    for k in ("Nk1", "Nk", "M", "xbar", "Lt63", "Lt64"):
+        np.testing.assert_allclose(got[k], want[k], rtol=1e-9, atol=1e-12, err_msg=k)
+        assert np.array_equal(got[k], again[k]), k         # fixed-order sums
+    np.testing.assert_allclose(got["S"], want["S"], rtol=1e-9, atol=1e-9 * np.abs(want["S"]).max())
+    np.testing.assert_allclose(lit["gamma_all"].sum((0, 1)) + 1e-50, got["Nk"], rtol=1e-12)
+
+
+@pytest.mark.gpu
+def test_cuda_fb_stats_rejects_generic_shapes():
+    from vbhem_b200 import fb
+    from vbhem_b200._lib import VbhemError
+    data, vp = make_fb_case(N=5, K=11, dim=2, maxT=4, seed=5)
+    with fb.SequenceSet(data) as seqs, pytest.raises(VbhemError) as ei:
+        fb.fb_stats(seqs, vp)
+    assert ei.value.code == -1
