@@ -332,6 +332,10 @@ __device__ __forceinline__ double terminate(const Frag &G, const Frag &expPi, do
 #define VB_KC_BYTES (64 * 1024)   // shared-memory budget for centre records per CTA
 #endif
 constexpr int kBwdWarps = VB_BWD_WARPS;
+#ifndef VB_UNIT_CENTRES
+#define VB_UNIT_CENTRES 16
+#endif
+constexpr int kUnitCentres = VB_UNIT_CENTRES;   // centres per work unit of the first pass (multiple of VB_NP)
 constexpr int kNP = VB_NP;
 
 template <int NP, int LS, int ES>
@@ -434,11 +438,17 @@ k_lattice_bwd(BaseView B, CentreView C, int T, int kc, double *L_elbo, Fallback 
   for (int x = threadIdx.x; x < nj * rs; x += blockDim.x) recs[x] = C.rec[(size_t)j0 * rs + x];
   __syncthreads();
 
-  for (int i = i0 + blockIdx.x * kBwdWarps + warp; i < i1; i += gridDim.x * kBwdWarps) {
+  // Work unit = one base x kUnitCentres centres: fine enough that the last wave of warps is nearly full even
+  // for a 12 500-base shard (8-GPU strong scaling), coarse enough that re-reading the base costs < 1 %.
+  const int nuc = (nj + kUnitCentres - 1) / kUnitCentres;
+  const long long nunits = (long long)(i1 - i0) * nuc, nw = (long long)gridDim.x * kBwdWarps;
+  for (long long u = (long long)blockIdx.x * kBwdWarps + warp; u < nunits; u += nw) {
+    const int i = i0 + (int)(u / nuc), jc = (int)(u % nuc) * kUnitCentres;
+    const int je = min(jc + kUnitCentres, nj);
     BaseConst<D, FULL> b;
     load_base(b, B, i, g, q);
     const bool base_chk = base_bad(b.Ab, b.prior);
-    for (int jj = 0; jj < nj; jj += kNP) {
+    for (int jj = jc; jj < je; jj += kNP) {
       Frag E[kNP], G[kNP], expA[kNP], expPi[kNP];
       unsigned rng[kNP];
       bool bad[kNP];
@@ -713,7 +723,9 @@ int launch_lattice_bwd(const BaseView &B, const CentreView &C, int T, double *L_
   if (kc > C.K) kc = C.K;
   const size_t smem = sizeof(double) * ((size_t)kc * rs + TabFirst::kDoubles);
   const int ny = (C.K + kc - 1) / kc;
-  int nx = (n + kBwdWarps - 1) / kBwdWarps;
+  const int kcu = (kc + kUnitCentres - 1) / kUnitCentres;
+  long long nxl = ((long long)n * kcu + kBwdWarps - 1) / kBwdWarps;
+  int nx = nxl > (1 << 30) ? (1 << 30) : (int)nxl;
   const int cap = VB_BWD_MINB * sm_count();
   if (nx > cap) nx = cap;
   return dispatch(B.d, B.covmode, [&](auto Dc, auto Fc) {
