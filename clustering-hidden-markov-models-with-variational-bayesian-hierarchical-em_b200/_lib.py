@@ -49,6 +49,9 @@ SIGNATURES = {
     "vbhem_em_estep": (C.c_int, [vp, C.c_int, vp]),
     "vbhem_em_lower_bound": (C.c_int, [vp, vp, dp]),
     "vbhem_em_mstep": (C.c_int, [vp, vp]),
+    "vbhem_em_mstep_masked": (C.c_int, [vp, vp, C.POINTER(C.c_ubyte)]),
+    "vbhem_em_run_groups": (C.c_int, [vp, C.c_int, C.c_int, C.c_double, dp, C.c_int, C.POINTER(C.c_int),
+                                      C.POINTER(C.c_int)]),
     "vbhem_em_fetch": (C.c_int, [vp, dp, dp, dp, dp, dp, dp, dp]),
     "vbhem_em_run": (C.c_int, [vp, C.c_int, C.c_int, C.c_double, dp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "vbhem_finalize_stats": (C.c_int, [vp, C.c_int, ip, C.c_int, C.c_int, dp]),

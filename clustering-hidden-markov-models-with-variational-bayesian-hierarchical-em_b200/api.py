@@ -243,6 +243,17 @@ class BaseSet:
         n = it.value + (1 if bad.value else 0)
         return dict(LogLs=LogLs[:n].copy(), iters=it.value, unstable=bool(bad.value), hyp=self.em_fetch())
 
+    def em_run_groups(self, tau: int, max_iter: int = 200, min_diff: float = 1e-5) -> dict:
+        """Every batched H3M of ``em_begin(..., group=...)`` run to its own convergence in one loop
+        (``vbhem_em_run_groups``): LogLs is a list of per-group traces."""
+        G, ld = self._em["ng"], max_iter + 2
+        LogLs = np.zeros((G, ld))
+        it, bad = np.zeros(G, np.int32), np.zeros(G, np.int32)
+        check(lib().vbhem_em_run_groups(self._h, tau, max_iter, min_diff, _d(LogLs), ld,
+                                        it.ctypes.data_as(C.POINTER(C.c_int)), bad.ctypes.data_as(C.POINTER(C.c_int))))
+        return dict(LogLs=[LogLs[g, :it[g] + (1 if bad[g] else 0)].copy() for g in range(G)], iters=it,
+                    unstable=bad.astype(bool), hyp=self.em_fetch())
+
     def finalize(self, buf: np.ndarray, Sr, r: int, ng: int = 1) -> dict:
         """vbhem_compute_Statistics.m:57-82 on a raw stats buffer (e.g. after an all-reduce)."""
         Sr = np.ascontiguousarray(Sr, dtype=np.int32)

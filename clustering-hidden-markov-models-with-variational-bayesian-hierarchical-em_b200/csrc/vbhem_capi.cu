@@ -98,7 +98,7 @@ struct vbhem_base {
     int K = 0, maxSr = 0, ngroups = 1;
     std::vector<int32_t> Sr, group;
     double alpha0 = 0, eta0 = 0, epsilon0 = 0, lambda0 = 0, v0 = 0;
-    DevBuf m, prior, lb, stats;
+    DevBuf m, prior, lb, stats, frozen;
     double *h_lb = nullptr;   // pinned
   } em;
   int *h_totals = nullptr;   // pinned
@@ -629,7 +629,7 @@ int vbhem_free_base(vbhem_base_t *h) {
   if (h->cin) { cudaStreamSynchronize(h->cin); cudaStreamDestroy(h->cin); }
   if (h->cout) { cudaStreamSynchronize(h->cout); cudaStreamDestroy(h->cout); }
   for (cudaEvent_t e : h->slice_ev) cudaEventDestroy(e);
-  h->em.m.release(); h->em.prior.release(); h->em.lb.release(); h->em.stats.release();
+  h->em.m.release(); h->em.prior.release(); h->em.lb.release(); h->em.stats.release(); h->em.frozen.release();
   if (h->em.h_lb) cudaFreeHost(h->em.h_lb);
   DevBuf *all[] = {&h->bSb, &h->bprior, &h->bA, &h->bmu, &h->bcov, &h->bNt, &h->cen_i, &h->cen_d, &h->hyp_d, &h->rec,
                    &h->L, &h->z, &h->flags, &h->fbcount, &h->Njp, &h->lbp, &h->cnt, &h->offs, &h->segs, &h->items,
@@ -959,6 +959,29 @@ int vbhem_em_lower_bound(vbhem_base_t *h, double *stats_dev, double *lb_out) {
   return VBHEM_OK;
 }
 
+namespace {
+int em_mstep_masked(vbhem_base *h, double *stats_dev, const unsigned char *frozen_host) {
+  if (!h || !h->em.active) return fail(VBHEM_EINVAL, "vbhem_em_begin has not been called on this handle");
+  CU(cudaSetDevice(h->device));
+  auto &em = h->em;
+  EmCtx c = em_ctx(h, stats_dev ? stats_dev : em.stats.as<double>());
+  if (frozen_host) {
+    CU(em.frozen.ensure((size_t)em.ngroups));
+    CU(cudaMemcpyAsync(em.frozen.p, frozen_host, (size_t)em.ngroups, cudaMemcpyHostToDevice, h->st));
+    c.E.frozen = em.frozen.as<unsigned char>();
+  }
+  launch_mstep(c.E, c.S.Nj, c.S.nu1, c.S.xi, c.S.pr, c.S.mu, c.S.Mu, c.p.alpha, c.p.eta, c.p.epsilon,
+               em.m.as<double>(), c.p.W, c.p.v, c.p.lambda, h->st);
+  if (frozen_host) CU(cudaStreamSynchronize(h->st));     // the caller's mask buffer may change next
+  CU(cudaGetLastError());
+  return VBHEM_OK;
+}
+}  // namespace
+
+int vbhem_em_mstep_masked(vbhem_base_t *h, double *stats_dev, const unsigned char *frozen) {
+  return em_mstep_masked(h, stats_dev, frozen);
+}
+
 int vbhem_em_mstep(vbhem_base_t *h, double *stats_dev) {
   if (!h || !h->em.active) return fail(VBHEM_EINVAL, "vbhem_em_begin has not been called on this handle");
   CU(cudaSetDevice(h->device));
@@ -1017,6 +1040,50 @@ int vbhem_em_run(vbhem_base_t *h, int tau, int max_iter, double min_diff, double
   CU(cudaStreamSynchronize(h->st));
   *iters = it;
   if (unstable) *unstable = bad;
+  return VBHEM_OK;
+}
+
+// The same loop for several H3Ms batched in one handle (soft-max groups of vbhem_em_begin): every group
+// follows the control flow of vbhem_h3m_c_step_fc.m:311-354 on its own; a group that has stopped keeps its
+// hyper-parameters (masked M-step) while the others go on.  LogLs is [ngroups][ld], iters / unstable [ngroups].
+int vbhem_em_run_groups(vbhem_base_t *h, int tau, int max_iter, double min_diff, double *LogLs, int ld, int *iters,
+                        int *unstable) {
+  if (!h || !h->em.active) return fail(VBHEM_EINVAL, "vbhem_em_begin has not been called on this handle");
+  if (!LogLs || !iters || ld < max_iter + 2) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: LogLs[ngroups][>= max_iter + 2], iters required");
+  const int G = h->em.ngroups;
+  std::vector<double> lb(12 * (size_t)G), lastL(G, -1.79769313486231570e308);
+  std::vector<int> it(G, 0), n(G, 0), bad(G, 0);
+  std::vector<unsigned char> done(G, 0), skip(G, 0);
+  int left = G;
+  while (left > 0) {
+    int rc = vbhem_em_estep(h, tau, nullptr);
+    if (rc) return rc;
+    rc = vbhem_em_lower_bound(h, nullptr, lb.data());
+    if (rc) return rc;
+    std::vector<unsigned char> stop(G, 0);
+    for (int g = 0; g < G; g++) {
+      skip[g] = done[g];
+      if (done[g]) continue;
+      double L = lb[12 * (size_t)g + 10];
+      bool do_break = false;
+      if (it[g] > 1 && fabs((L - lastL[g]) / lastL[g]) <= min_diff) do_break = true;
+      if (it[g] == max_iter) do_break = true;
+      if (L != L) { do_break = true; bad[g] = 1; L = -INFINITY; }
+      LogLs[(size_t)ld * g + n[g]++] = L;
+      if (do_break && bad[g]) { skip[g] = 1; stop[g] = 1; continue; }   // keep the last stable hyper-parameters
+      it[g]++;
+      lastL[g] = L;
+      if (do_break) stop[g] = 1;                                          // the M-step still runs once more
+    }
+    rc = em_mstep_masked(h, nullptr, skip.data());
+    if (rc) return rc;
+    for (int g = 0; g < G; g++)
+      if (stop[g] && !done[g]) { done[g] = 1; left--; }
+  }
+  for (int g = 0; g < G; g++) {
+    iters[g] = it[g];
+    if (unstable) unstable[g] = bad[g];
+  }
   return VBHEM_OK;
 }
 

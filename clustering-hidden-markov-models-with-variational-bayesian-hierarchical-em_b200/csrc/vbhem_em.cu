@@ -186,6 +186,11 @@ __global__ void k_mstep(EmView E, const double *Nj, const double *nu1, const dou
   const int r = E.maxSr, d = E.d, dd = E.covmode ? d * d : d;
   if (x >= E.K * r) return;
   const int k = x % r, j = x / r;
+  if (E.frozen) {          // batched EM runs: H3Ms that have converged keep their hyper-parameters
+    int g = 0;
+    while (g + 1 < E.ngroups && E.gstart[g + 1] <= j) g++;
+    if (E.frozen[g]) return;
+  }
   if (k == 0) alpha[j] = E.alpha0 + Nj[j];
   if (k >= E.Sr[j]) return;
   const size_t s = x;

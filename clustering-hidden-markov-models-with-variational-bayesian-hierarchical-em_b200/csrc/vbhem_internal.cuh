@@ -118,6 +118,7 @@ int launch_finalize(int K, int maxSr, int d, int covmode, const int *Sr, double 
 struct EmView {
   int K, maxSr, d, covmode, ngroups;
   const int *Sr, *gstart;
+  const unsigned char *frozen;   // per soft-max group: 1 = leave this H3M's hyper-parameters alone (may be null)
   double alpha0, eta0, epsilon0, lambda0, v0;
   const double *m0;       // [d]
   const double *W0inv;    // [d] diagonal of inv(W0)

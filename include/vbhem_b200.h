@@ -193,8 +193,13 @@ int vbhem_finalize_stats_dev(vbhem_base_t *base, int K, const int32_t *Sr, int m
  *                        group g, lb_out[12 g + 0..9] = Lt1..Lt10, [10] = LB, [11] = sum_j Nj (HOST).
  *   vbhem_em_mstep       replaces the resident hyper-parameters by the M-step of those statistics.
  *   vbhem_em_fetch       copies the resident hyper-parameters to HOST arrays (any may be NULL).
+ *   vbhem_em_mstep_masked  the same, leaving the groups with frozen[g] != 0 (HOST bytes, one per group) untouched.
  *   vbhem_em_run         the loop of vbhem_h3m_c_step_fc.m:115-433 for one H3M on one GPU: LogLs[] (room
- *                        for max_iter + 2 values), *iters = M-steps taken, *unstable = NaN guard fired. */
+ *                        for max_iter + 2 values), *iters = M-steps taken, *unstable = NaN guard fired.
+ *   vbhem_em_run_groups  that loop for every batched H3M at once (trials, initialisations or (K,S) candidates
+ *                        that share the base set: vbhem_h3m_c.m:28-76, vbhem_h3m_cluster.m:261-355): each group
+ *                        stops by its own convergence test and keeps its hyper-parameters while the others go
+ *                        on.  LogLs is [ngroups][ld] (ld >= max_iter + 2), iters / unstable are [ngroups]. */
 int vbhem_em_begin(vbhem_base_t *base, int K, const int32_t *Sr, int maxSr, const int32_t *group, int ngroups,
                    double alpha0, double eta0, double epsilon0, double lambda0, double v0, const double *m0,
                    const double *W0, int nW0, const double *alpha, const double *eta, const double *epsilon,
@@ -202,10 +207,13 @@ int vbhem_em_begin(vbhem_base_t *base, int K, const int32_t *Sr, int maxSr, cons
 int vbhem_em_estep(vbhem_base_t *base, int tau, double *stats_dev);
 int vbhem_em_lower_bound(vbhem_base_t *base, double *stats_dev, double *lb_out);
 int vbhem_em_mstep(vbhem_base_t *base, double *stats_dev);
+int vbhem_em_mstep_masked(vbhem_base_t *base, double *stats_dev, const unsigned char *frozen);
 int vbhem_em_fetch(vbhem_base_t *base, double *alpha, double *eta, double *epsilon, double *m, double *W, double *v,
                    double *lambda);
 int vbhem_em_run(vbhem_base_t *base, int tau, int max_iter, double min_diff, double *LogLs, int *iters,
                  int *unstable);
+int vbhem_em_run_groups(vbhem_base_t *base, int tau, int max_iter, double min_diff, double *LogLs, int ld, int *iters,
+                        int *unstable);
 
 /* ---- VB-HMM forward-backward (the toolbox's HMM learning) ----
  * Replaces the MEX plug-in of /root/reference/src/hmm/vbhmm_fb.m:99-145,

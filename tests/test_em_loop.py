@@ -187,3 +187,26 @@ def test_sharded_device_em_run_world_1():
     assert np.array_equal(got["LogLs"], want["LogLs"])
     for k in ("alpha", "eta", "epsilon", "lam", "v", "m", "W"):
         assert np.array_equal(got["hyp"][k], want["hyp"][k]), k
+
+
+@pytest.mark.gpu
+def test_batched_em_runs_equal_separate_runs():
+    """vbhem_em_run_groups: several (K,S) candidates over one base set, each run to its own convergence in one
+    batched loop, must reproduce every candidate's own vbhem_em_run (trace, iteration count, hyper-parameters)."""
+    from vbhem_b200.api import BaseSet
+    opt = dict(OPT, max_iter=25, minDiff=1e-4)
+    base, _ = synth.make_base_set(150, S=3, d=2, C=3, covmode="full", seed=61, Nv=opt["Nv"])
+    hyp, grp, models = synth.model_selection_grid(base, Ks=range(1, 4), Ss=range(2, 4), seed=61,
+                                                  opt=dict(synth.DEFAULT_OPT, Nv=opt["Nv"]))
+    with BaseSet(base) as bs:
+        bs.em_begin(hyp, opt, group=grp)
+        got = bs.em_run_groups(opt["tau"], opt["max_iter"], opt["minDiff"])
+        assert len(set(int(i) for i in got["iters"])) > 1          # the candidates stop at different iterations
+        for g, (K, S) in enumerate(models):
+            sel = np.where(grp == g)[0]
+            bs.em_begin({k: v[sel] for k, v in hyp.items()}, opt)
+            one = bs.em_run(opt["tau"], opt["max_iter"], opt["minDiff"])
+            assert one["iters"] == got["iters"][g], (K, S)
+            np.testing.assert_allclose(got["LogLs"][g], one["LogLs"], rtol=1e-12)
+            for k in ("alpha", "eta", "epsilon", "lam", "v", "m", "W"):
+                np.testing.assert_allclose(got["hyp"][k][sel], one["hyp"][k], rtol=1e-11, atol=1e-300, err_msg=f"{k} {K},{S}")
