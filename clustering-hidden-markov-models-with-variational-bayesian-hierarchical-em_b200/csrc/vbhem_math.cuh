@@ -53,7 +53,7 @@ constexpr double kUnitsCeil = 34359738368.0;            //  2^35 units (~  9.3e7
 // with two moves per use.   [0..4] exp: u^n/n!;  [5..9] log: (-1)^(n+1)/(n u);  [10] 1.5 * 2^52
 #define VB_MATH_CONSTS { VBHEM_EXP_COEF, VBHEM_LOG_COEF, 6755399441055744.0 }
 #ifdef __CUDACC__
-__constant__ double g_mc[11] = VB_MATH_CONSTS;
+static __constant__ double g_mc[11] = VB_MATH_CONSTS;   // one copy per translation unit
 #endif
 #ifdef __CUDA_ARCH__
 #define VB_MC(i) g_mc[i]

@@ -19,6 +19,7 @@
 //     and the scale c_{t+1} from alpha_t (bit-identical to the forward value, so no scale array);
 //   * outputs beyond a sequence's own length are written as zeros by the same thread (no memset pass).
 #include "../../include/vbhem_b200.h"
+#include "vbhem_math.cuh"
 
 #include <cuda_runtime.h>
 
@@ -88,13 +89,25 @@ __device__ __forceinline__ void emissions(const FbPar<K, DIM> &P, const double (
   }
 }
 
+// 2^(j/256) table of the lattice kernels' exp (vbhem_math.cuh), staged per block
+__device__ const double g_fb_exp_table[VBHEM_EXP_BINS] = VBHEM_EXP_TABLE;
+
+// p(k) = exp(logrho(k) - max_k logrho): arguments are <= 0, so the lean exp of the lattice kernels applies
+// (8 fp64 instructions against libdevice's ~19): y = x / u, e^x = mant 2^e, e <= 0; below 2^-1000 it returns
+// ~1e-301 where libdevice returns 0 -- both nothing next to the state that holds the maximum (p = 1).
 template <int K>
-__device__ __forceinline__ double shifted_exp(const double (&lr)[K], double (&p)[K]) {
+__device__ __forceinline__ double shifted_exp(const double (&lr)[K], double (&p)[K], vbhem::tab_t etab) {
   double mx = lr[0];
 #pragma unroll
   for (int k = 1; k < K; k++) mx = lr[k] > mx ? lr[k] : mx;
 #pragma unroll
-  for (int k = 0; k < K; k++) p[k] = exp(lr[k] - mx);
+  for (int k = 0; k < K; k++) {
+    double y = (lr[k] - mx) * vbhem::kPerUnit;
+    y = y > -4.0e8 ? y : -4.0e8;                  // exp_split's domain; far below the 2^-1000 clamp anyway
+    int e;
+    const double mant = vbhem::exp_split<1>(y, etab, e);
+    p[k] = vbhem::exp_scale(mant, e);
+  }
   return mx;
 }
 
@@ -120,6 +133,10 @@ __global__ void __launch_bounds__(kFbThreads, VB_FB_MINB)
 k_fb(const __grid_constant__ FbPar<K, DIM> P, int N, int maxT, const int *__restrict__ Tn,
      const double *__restrict__ X, double *__restrict__ logrho, double *__restrict__ gamma,
      double *__restrict__ xi_sum, double *__restrict__ phi) {
+  __shared__ __align__(16) double s_etab[VBHEM_EXP_BINS];
+  for (int j = threadIdx.x; j < VBHEM_EXP_BINS; j += kFbThreads) s_etab[j] = g_fb_exp_table[j];
+  __syncthreads();
+  const vbhem::tab_t etab = (vbhem::tab_t)__cvta_generic_to_shared(s_etab);
   const int n = blockIdx.x * kFbThreads + threadIdx.x;
   if (n >= N) return;
   const int T = Tn[n];
@@ -145,7 +162,7 @@ k_fb(const __grid_constant__ FbPar<K, DIM> P, int N, int maxT, const int *__rest
 #pragma unroll
       for (int k = 0; k < K; k++) __stcs(lp + NK * t + k, lr[k]);
     }
-    summax += shifted_exp<K>(lr, p);
+    summax += shifted_exp<K>(lr, p, etab);
     double delta[K], c;
     if (t == 0) {
       c = 0.0;
@@ -194,7 +211,7 @@ k_fb(const __grid_constant__ FbPar<K, DIM> P, int N, int maxT, const int *__rest
       for (int k = 0; k < K; k++) an[k] = gp[NK * (t - 1) + k];      // alpha_hat(t-1), parked by the forward pass
     }
     emissions<K, DIM>(P, x, lr);
-    shifted_exp<K>(lr, p);                                            // p(x_{t+1} | z) / max
+    shifted_exp<K>(lr, p, etab);                                      // p(x_{t+1} | z) / max
     double delta[K];
     const double rc = 1.0 / forward_step<K, DIM>(P, alpha, p, delta);   // 1 / c(t+1)
     double bpi[K];
