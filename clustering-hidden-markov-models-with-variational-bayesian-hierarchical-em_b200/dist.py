@@ -105,26 +105,38 @@ class ShardedEStep:
         return finalize(buf, extra)
 
     # -- a whole EM run, hyper-parameters resident on every rank -------------
-    def em_run(self, hyp: dict, opt: dict, covmode: str = "full") -> dict:
-        """vbhem_h3m_c_step_fc.m:115-433 over the sharded base set: every rank keeps the centre hyper-parameters
-        in HBM (``vbhem_em_begin``), runs the fused E-step on its shard, all-reduces the raw statistics (the one
-        collective), and applies the identical lower bound + M-step on the device, so no parameters travel
-        between iterations.  CUDA path only."""
-        assert self.bs is not None, "em_run needs the CUDA library"
-        import time
+    def _cuda_em_ops(self, hyp, opt):
+        """The device-resident EM state as five callables (vbhem_em_*); the statistics buffer is a CUDA tensor."""
         torch, bs = self.torch, self.bs
-        tau, max_iter, min_diff = int(opt["tau"]), int(opt.get("max_iter", 200)), float(opt.get("minDiff", 1e-5))
         K, r = hyp["eta"].shape
         bs.em_begin(hyp, opt)
-        ns = bs.stats_size(K, r)
-        stats = torch.zeros(ns, dtype=torch.float64, device=f"cuda:{self.device}")
+        stats = torch.zeros(bs.stats_size(K, r), dtype=torch.float64, device=f"cuda:{self.device}")
+
+        def estep(tau):
+            bs.em_estep(tau, stats.data_ptr())
+            return stats
+
+        return dict(estep=estep, lower_bound=lambda buf: float(bs.em_lower_bound(buf.data_ptr())[0, 10]),
+                    mstep=lambda buf: bs.em_mstep(buf.data_ptr()), fetch=bs.em_fetch, sync=bs.synchronize)
+
+    def em_run(self, hyp: dict, opt: dict, covmode: str = "full", ops=None) -> dict:
+        """vbhem_h3m_c_step_fc.m:115-433 over the sharded base set: every rank keeps the centre hyper-parameters
+        (``vbhem_em_begin``: in HBM), runs the fused E-step on its shard, all-reduces the raw statistics (the one
+        collective), and applies the identical lower bound + M-step, so no parameters travel between iterations.
+
+        ``ops`` (estep(tau) -> raw statistics tensor, lower_bound(buf) -> L after normalising buf in place,
+        mstep(buf), fetch() -> hyper-parameters, sync()) defaults to the CUDA library; the gloo test injects the
+        oracle so that the loop and the exchange are exercised on CPU-only machines."""
+        import time
+        ops = ops or self._cuda_em_ops(hyp, opt)
+        tau, max_iter, min_diff = int(opt["tau"]), int(opt.get("max_iter", 200)), float(opt.get("minDiff", 1e-5))
         LogLs, lastL, it, unstable, times = [], -np.finfo(float).max, 0, False, []
         while True:
             t0 = time.perf_counter()
-            bs.em_estep(tau, stats.data_ptr())
+            stats = ops["estep"](tau)
             if self.world > 1:
                 self.dist.all_reduce(stats, op=self.dist.ReduceOp.SUM, group=self.group)
-            L = float(bs.em_lower_bound(stats.data_ptr())[0, 10])
+            L = ops["lower_bound"](stats)
             do_break = it > 1 and abs((L - lastL) / lastL) <= min_diff
             do_break = do_break or it == max_iter
             if np.isnan(L):
@@ -132,12 +144,12 @@ class ShardedEStep:
             LogLs.append(L)
             if do_break and unstable:
                 break
-            bs.em_mstep(stats.data_ptr())
+            ops["mstep"](stats)
             it += 1
             lastL = L
             times.append(time.perf_counter() - t0)
             if do_break:
                 break
-        bs.synchronize()
-        return dict(hyp=bs.em_fetch(), LogLs=np.array(LogLs), LL=LogLs[-1], iters=it, unstable=unstable,
+        ops["sync"]()
+        return dict(hyp=ops["fetch"](), LogLs=np.array(LogLs), LL=LogLs[-1], iters=it, unstable=unstable,
                     ms_per_iter=1e3 * float(np.median(times)) if times else float("nan"))

@@ -79,3 +79,77 @@ def test_shard_bounds_cover_everything():
             assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
             sizes = [hi - lo for lo, hi in b]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _em_worker(rank, world, port, out_dir):
+    """Sharded EM loop (dist.ShardedEStep.em_run) with every device op replaced by the oracle / numpy formulas."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import vbhem_b200  # noqa: F401
+    from vbhem_b200 import h3m, pack, synth
+    from vbhem_b200.dist import ShardedEStep, shard_base
+    from oracle import cref, numpy_ref as nr
+    from util import prepass_natural
+    from test_em_loop import OPT
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    base, _ = synth.make_base_set(60, S=3, d=2, C=3, covmode="full", seed=77, Nv=OPT["Nv"])
+    hyp0 = synth.init_centres_baseem(base, 3, 3, seed=77, opt=dict(synth.DEFAULT_OPT, Nv=OPT["Nv"]))
+    shard = pack.pack_base(shard_base(base, world, rank))
+    state = dict(hyp={k: np.array(v) for k, v in hyp0.items()}, pre=None, fin=None)
+    keys = ("Nj", "nu1", "xi", "pr", "mu", "Mu", "lb")
+
+    def estep(tau):
+        cen = prepass_natural(state["hyp"], "full")
+        state["pre"] = dict(logOmega=cen["logOmega"], logPi=cen["logPi"], logA=cen["logA"],
+                            logLambdaTilde=cen["logLambdaTilde"])
+        S = cref.port_estep_fused(shard, pack.pack_centres(cen), tau, want_pairs=False)
+        S["Nj"] = S["Nj"] - 1e-50                     # raw sums travel
+        state["shapes"] = [S[k].shape for k in keys]
+        return torch.from_numpy(np.concatenate([S[k].ravel() for k in keys]))
+
+    def lower_bound(buf):
+        parts, o = {}, 0
+        for k, sh in zip(keys, state["shapes"]):
+            n = int(np.prod(sh))
+            parts[k] = buf.numpy()[o:o + n].reshape(sh)
+            o += n
+        St = pack.stats_to_natural(parts, 2, 1)
+        K = St["Nj"].shape[0]
+        fins = [nr.finalize_stats(St["nu1"][j], St["xi"][j], St["pr"][j], St["mu"][j], St["Mu"][j]) for j in range(K)]
+        state["fin"] = dict(Nj=St["Nj"] + 1e-50, Nj_rho1=np.stack([f[0] for f in fins]),
+                            Nj_rho2rho=np.stack([f[1] for f in fins]), Nj_rho=np.stack([f[2] for f in fins]),
+                            y_bar=np.stack([f[3] for f in fins]), S_plus_C=np.stack([f[4] for f in fins]))
+        L, _ = h3m.vbhemh3m_lb(St["lb"][0], St["lb"][1], state["fin"]["Nj"], state["pre"], state["hyp"], OPT)
+        return L
+
+    def mstep(buf):
+        new = h3m.vbhem_mstep(state["fin"], OPT)
+        new["Sr"] = state["hyp"]["Sr"]
+        state["hyp"] = new
+
+    ops = dict(estep=estep, lower_bound=lower_bound, mstep=mstep, fetch=lambda: state["hyp"], sync=lambda: None)
+    got = ShardedEStep(None, compute=lambda *a: None).em_run(hyp0, OPT, ops=ops)
+    if rank == 0:
+        np.savez(os.path.join(out_dir, "em.npz"), LogLs=got["LogLs"], iters=got["iters"],
+                 **{f"hyp_{k}": v for k, v in got["hyp"].items()})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_em_loop_equals_single_process_oracle_em(tmp_path):
+    """The multi-GPU EM loop (E-step per shard, ONE all-reduce, identical lower bound / M-step on every rank,
+    convergence rule of vbhem_h3m_c_step_fc.m:311-354) on two gloo ranks against the un-sharded oracle loop."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from vbhem_b200 import synth
+    from test_em_loop import OPT, oracle_em
+    port = _free_port()
+    mp.spawn(_em_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    got = np.load(os.path.join(tmp_path, "em.npz"))
+    base, _ = synth.make_base_set(60, S=3, d=2, C=3, covmode="full", seed=77, Nv=OPT["Nv"])
+    hyp0 = synth.init_centres_baseem(base, 3, 3, seed=77, opt=dict(synth.DEFAULT_OPT, Nv=OPT["Nv"]))
+    want_hyp, want_L = oracle_em(base, hyp0, OPT)
+    assert int(got["iters"]) == len(want_L)
+    np.testing.assert_allclose(got["LogLs"], want_L, rtol=1e-10)
+    for k in ("alpha", "eta", "epsilon", "lam", "v", "m", "W"):
+        np.testing.assert_allclose(got[f"hyp_{k}"], want_hyp[k], rtol=1e-8, atol=1e-10 * np.abs(want_hyp[k]).max(), err_msg=k)

@@ -210,3 +210,16 @@ def test_batched_em_runs_equal_separate_runs():
             np.testing.assert_allclose(got["LogLs"][g], one["LogLs"], rtol=1e-12)
             for k in ("alpha", "eta", "epsilon", "lam", "v", "m", "W"):
                 np.testing.assert_allclose(got["hyp"][k][sel], one["hyp"][k], rtol=1e-11, atol=1e-300, err_msg=f"{k} {K},{S}")
+
+
+def test_model_selection_grid_layout():
+    """CPU: synth.model_selection_grid stacks every (K,S) candidate, padded to the largest S, one group per model."""
+    base, _ = synth.make_base_set(30, S=3, d=2, C=2, covmode="full", seed=4, Nv=10.0)
+    hyp, grp, models = synth.model_selection_grid(base, Ks=range(1, 4), Ss=range(1, 4), seed=4)
+    assert len(models) == 9 and hyp["Sr"].shape[0] == 3 * (1 + 2 + 3) == grp.shape[0]
+    assert hyp["eta"].shape == (18, 3) and hyp["W"].shape == (18, 3, 2, 2)
+    for g, (K, S) in enumerate(models):
+        sel = np.where(grp == g)[0]
+        assert len(sel) == K and (hyp["Sr"][sel] == S).all()
+        assert (hyp["eta"][sel, :S] > 0).all() and not hyp["eta"][sel, S:].any()
+    assert (np.diff(grp) >= 0).all() and grp[0] == 0 and grp[-1] == 8

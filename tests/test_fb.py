@@ -188,3 +188,30 @@ def test_cuda_fb_stats_rejects_generic_shapes():
     with fb.SequenceSet(data) as seqs, pytest.raises(VbhemError) as ei:
         fb.fb_stats(seqs, vp)
     assert ei.value.code == -1
+
+
+@pytest.mark.gpu
+def test_cuda_fb_full_size_properties():
+    """BASELINE configs[4] scale (200 k of the 1 M sequences, T = 50, S = 5, d = 2): size-independent properties
+    of the literal outputs, and the fused statistics against sums of those outputs."""
+    from vbhem_b200 import fb
+    import bench_fb
+    N, T, K, dim = 200_000, 50, 5, 2
+    Tn, offs, flat, vp = bench_fb.make_workload(N, T, K, dim, seed=5)
+    with fb.SequenceSet.from_packed(Tn, offs, flat, dim) as seqs:
+        par = fb.prepass(vp)
+        out = fb.fb_call(seqs, par, want=("gamma_all", "xi_sum", "phi_norm"))
+        st = fb.fb_stats(seqs, vp)
+    g = out["gamma_all"]
+    assert np.isfinite(out["phi_norm"]).all()
+    np.testing.assert_allclose(g.sum(2), 1.0, rtol=1e-11)
+    np.testing.assert_allclose(out["xi_sum"].sum((1, 2)), T - 1.0, rtol=1e-11)
+    np.testing.assert_allclose(out["xi_sum"].sum(2), g[:, :-1].sum(1), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(st["Nk"], g.sum((0, 1)) + 1e-50, rtol=1e-11)
+    np.testing.assert_allclose(st["Nk1"], g[:, 0].sum(0) + 1e-50, rtol=1e-11)
+    np.testing.assert_allclose(st["M"], out["xi_sum"].sum(0), rtol=1e-11)
+    np.testing.assert_allclose(st["Lt64"], out["phi_norm"].sum(), rtol=1e-12)
+    np.testing.assert_allclose(st["Nk"].sum(), N * T, rtol=1e-12)
+    X = np.transpose(flat.reshape(N, dim, T), (0, 2, 1))
+    xbar = np.einsum("ntk,ntd->kd", g, X) / st["Nk"][:, None]
+    np.testing.assert_allclose(st["xbar"], xbar, rtol=1e-10)
