@@ -71,7 +71,7 @@ class BaseSet:
 
     # -- knobs --------------------------------------------------------------
     def set_kernel(self, which: str = "auto"):
-        check(lib().vbhem_set_kernel(self._h, {"auto": 0, "general": 1}[which]))
+        check(lib().vbhem_set_kernel(self._h, {"auto": 0, "general": 1, "unpaired": 2}[which]))
 
     def set_stream(self, cuda_stream: int | None):
         """Run this handle's work on an existing CUDA stream (``torch.cuda.current_stream().cuda_stream``).

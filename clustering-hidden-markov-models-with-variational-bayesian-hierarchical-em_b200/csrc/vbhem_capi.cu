@@ -6,6 +6,7 @@
 #include "../../include/vbhem_b200.h"
 #include "vbhem_internal.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -84,7 +85,7 @@ struct vbhem_base {
   BaseView B{};
   DevBuf bSb, bprior, bA, bmu, bcov, bNt;
   // centre set (per call)
-  DevBuf cen_i, cen_d, hyp_d, rec;
+  DevBuf cen_i, cen_d, hyp_d, rec, tile_i, pair_rec;
   // results and work lists
   DevBuf L, z, flags, fbcount, Njp, lbp, cnt, offs, segs, items, chunks, partial, itemflags, scratch, pairs_out,
       stats;
@@ -106,6 +107,7 @@ struct vbhem_base {
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   double timings[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int kernel_choice = 0;
+  bool pair_centres = true;   // first pass: two centres of <= 4 states per tile (vbhem_set_kernel bit 1 disables)
   long long counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int lastK = 0;
 };
@@ -239,6 +241,26 @@ int stage_centres(vbhem_base *h, const CentreArgs &a, CentreDev &cd, double *pre
     CU(h->rec.ensure(sizeof(double) * (size_t)cd.C.rec_stride * K));
     cd.C.rec = h->rec.as<double>();
     launches += launch_build_records(cd.C, d, dd, h->rec.as<double>(), h->st);
+    // first-pass tiling: centres with <= 4 states share a tile, two by two (pairing needs >= 2 of them)
+    std::vector<int> big, small;
+    for (int j = 0; j < K; j++) (a.Sr[j] <= 4 && h->pair_centres ? small : big).push_back(j);
+    if (small.size() < 2) { big.insert(big.end(), small.begin(), small.end()); small.clear(); std::sort(big.begin(), big.end()); }
+    if (small.size() % 2) small.push_back(-1);
+    std::vector<int> lists(big);
+    lists.insert(lists.end(), small.begin(), small.end());
+    CU(h->tile_i.ensure(sizeof(int) * (lists.size() + 1)));
+    CU(cudaMemcpyAsync(h->tile_i.p, lists.data(), sizeof(int) * lists.size(), cudaMemcpyHostToDevice, h->st));
+    CU(cudaStreamSynchronize(h->st));                      // `lists` goes out of scope
+    cd.C.big_list = h->tile_i.as<int>();
+    cd.C.nbig = (int)big.size();
+    cd.C.pair_list = cd.C.big_list + big.size();
+    cd.C.npairs = (int)small.size() / 2;
+    cd.C.pair_rec = nullptr;
+    if (cd.C.npairs > 0) {
+      CU(h->pair_rec.ensure(sizeof(double) * (size_t)cd.C.rec_stride * cd.C.npairs));
+      cd.C.pair_rec = h->pair_rec.as<double>();
+      launches += launch_pair_records(cd.C, d, dd, h->pair_rec.as<double>(), h->st);
+    }
   }
   return VBHEM_OK;
 }
@@ -657,8 +679,9 @@ int vbhem_synchronize(vbhem_base_t *h) {
 
 int vbhem_set_kernel(vbhem_base_t *h, int which) {
   if (!h) return fail(VBHEM_EINVAL, "base handle is NULL");
-  if (which != 0 && which != 1) return fail(VBHEM_EINVAL, "kernel must be 0 (auto) or 1 (general)");
-  h->kernel_choice = which;
+  if (which < 0 || which > 2) return fail(VBHEM_EINVAL, "kernel must be 0 (auto), 1 (general) or 2 (auto, one centre per tile)");
+  h->kernel_choice = which == 1 ? 1 : 0;
+  h->pair_centres = which != 2;
   return VBHEM_OK;
 }
 

@@ -38,6 +38,11 @@ struct CentreView {
   //   expA[8][8] (row rho, col sigma) | expPi[8] | c0[8] | m[8][d] | vW[8][dd]
   const double *rec;
   int rec_stride;         // doubles per record
+  // First-pass tiling: centres with more than four states take a tile each (big_list[nbig]); centres with at
+  // most four are paired, two per tile (pair_list[2 * npairs], -1 = no partner; tile records in pair_rec).
+  const int *big_list, *pair_list;
+  const double *pair_rec;
+  int nbig, npairs;
 };
 
 // One unit of second-pass work.
@@ -84,6 +89,7 @@ int launch_lattice_bwd(const BaseView &B, const CentreView &C, int T, double *L_
 int launch_lattice_full(const BaseView &B, const CentreView &C, int T, const PairWork &W, const PairOut &O,
                         Fallback fb, cudaStream_t st);
 int lattice_rec_stride(int d, int dd);
+int launch_pair_records(const CentreView &C, int d, int dd, double *out, cudaStream_t st);
 int lattice_bwd_wave();   // bases one full wave of the first-pass grid takes
 
 // aux kernels (vbhem_aux.cu)

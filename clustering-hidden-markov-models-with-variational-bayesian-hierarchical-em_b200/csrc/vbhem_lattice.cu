@@ -250,10 +250,13 @@ __device__ __forceinline__ Frag emission_smem(const BaseConst<D, FULL> &b, unsig
 
 // Shift of one lattice row = the largest binary exponent of e^G over the row (integer pipe, 32-bit
 // shuffles over the four lanes that hold the row).
+// CP ("centre pairing"): the tile holds TWO centres of at most four states each -- columns 0-3 and 4-7, a
+// block-diagonal expA -- so a row has one shift per half, shared by the two lanes that hold that half.
+template <bool CP = false>
 __device__ __forceinline__ int row_shift(int e0, int e1) {
   int m = max(e0, e1);
   m = max(m, __shfl_xor_sync(0xffffffffu, m, 1));
-  m = max(m, __shfl_xor_sync(0xffffffffu, m, 2));
+  if (!CP) m = max(m, __shfl_xor_sync(0xffffffffu, m, 2));
   return m;
 }
 
@@ -338,10 +341,10 @@ constexpr int kBwdWarps = VB_BWD_WARPS;
 constexpr int kUnitCentres = VB_UNIT_CENTRES;   // centres per work unit of the first pass (multiple of VB_NP)
 constexpr int kNP = VB_NP;
 
-template <int NP, int LS, int ES>
+template <int NP, int LS, int ES, bool CP>
 __device__ __forceinline__ void bwd_step_n(const Frag (&E)[NP], Frag (&G)[NP], const Frag (&expA)[NP],
                                            const Frag &Ab, tab_t ltab, tab_t etab,
-                                           unsigned (&rng)[NP], int q, int one) {
+                                           unsigned (&rng)[NP], int q, int one, int src0, int src1) {
   int e0[NP], e1[NP], c[NP];
   Frag Bm[NP], ST[NP], ell[NP];
 #pragma unroll
@@ -350,7 +353,7 @@ __device__ __forceinline__ void bwd_step_n(const Frag (&E)[NP], Frag (&G)[NP], c
     Bm[p].x1 = exp_split<ES>(G[p].x1, etab, e1[p]);
   }
 #pragma unroll
-  for (int p = 0; p < NP; p++) c[p] = row_shift(e0[p], e1[p]);
+  for (int p = 0; p < NP; p++) c[p] = row_shift<CP>(e0[p], e1[p]);
 #pragma unroll
   for (int p = 0; p < NP; p++) {
     rng[p] = max(rng[p], shift_excess(c[p]));
@@ -360,8 +363,9 @@ __device__ __forceinline__ void bwd_step_n(const Frag (&E)[NP], Frag (&G)[NP], c
   for (int p = 0; p < NP; p++) ST[p] = mma_nt(expA[p], Bm[p]);
 #pragma unroll
   for (int p = 0; p < NP; p++) {
-    const int cb0 = __shfl_sync(0xffffffffu, c[p] - 1023, (2 * q) * 4);
-    const int cb1 = __shfl_sync(0xffffffffu, c[p] - 1023, (2 * q + 1) * 4);
+    // shift of row beta = 2q+e (and, with CP, of the half that this lane's rho = g belongs to)
+    const int cb0 = __shfl_sync(0xffffffffu, c[p] - 1023, src0);
+    const int cb1 = __shfl_sync(0xffffffffu, c[p] - 1023, src1);
     ell[p] = Frag{log_shift_biased<LS>(ST[p].x0, ltab, cb0, one), log_shift_biased<LS>(ST[p].x1, ltab, cb1, one)};
   }
 #pragma unroll
@@ -373,7 +377,7 @@ __device__ __forceinline__ void bwd_step_n(const Frag (&E)[NP], Frag (&G)[NP], c
 
 // Termination of NP pairs side by side (first pass: L_elbo only; L[p] is valid in lane p when NP == 2,
 // in lane 0 otherwise).
-template <int NP, int LS, int ES>
+template <int NP, int LS, int ES, bool CP>
 __device__ __forceinline__ void terminate_n(const Frag (&G)[NP], const Frag (&expPi)[NP], double prior,
                                             tab_t ltab, tab_t etab, int q, unsigned (&rng)[NP],
                                             double (&L)[NP]) {
@@ -385,14 +389,26 @@ __device__ __forceinline__ void terminate_n(const Frag (&G)[NP], const Frag (&ex
     m1[p] = exp_split<ES>(G[p].x1, etab, e1[p]);
   }
 #pragma unroll
-  for (int p = 0; p < NP; p++) c[p] = row_shift(e0[p], e1[p]);
+  for (int p = 0; p < NP; p++) c[p] = row_shift<CP>(e0[p], e1[p]);
 #pragma unroll
   for (int p = 0; p < NP; p++) {
     rng[p] = max(rng[p], shift_excess(c[p]));
     s[p] = expPi[p].x0 * exp_scale(m0[p], e0[p] - c[p]) + expPi[p].x1 * exp_scale(m1[p], e1[p] - c[p]);
   }
   const double pu = prior * kUnit;
-  if constexpr (NP == 2) {
+  if constexpr (CP) {
+    // two centres per tile, two tiles in flight: the half-row sums of both tiles, then lane q takes the
+    // logarithm for (tile q & 1, half q >> 1); after the sum over base states lane q of row 0 holds that L_elbo
+    static_assert(NP == 2, "centre pairing is written for two tiles in flight");
+    const double v0 = s[0] + __shfl_xor_sync(0xffffffffu, s[0], 1);
+    const double v1 = s[1] + __shfl_xor_sync(0xffffffffu, s[1], 1);
+    const bool odd = q & 1;
+    double w = pu * log_shift<LS>(odd ? v1 : v0, ltab, odd ? c[1] : c[0]);
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+    L[0] = w;
+    L[1] = w;
+  } else if constexpr (NP == 2) {
     // Transposing reduction over the quad: lanes with even q end up with pair 0's sum, odd q with pair
     // 1's, so each lane takes ONE logarithm and the sum over base states runs once for both pairs.
     // L[0] is valid in lane 0, L[1] in lane 1.
@@ -419,26 +435,36 @@ __device__ __forceinline__ void terminate_n(const Frag (&G)[NP], const Frag (&ex
   }
 }
 
-template <int D, bool FULL>
+// rec_src / list: without CP, tile r of this launch is centre list[r] and its record is rec_src + RS * list[r];
+// with CP, tile r is the pair (list[2r], list[2r+1]) (-1 = no partner) and its record is rec_src + RS * r.
+template <int D, bool FULL, bool CP>
 __global__ void __launch_bounds__(kBwdWarps * 32, VB_BWD_MINB)
-k_lattice_bwd(BaseView B, CentreView C, int T, int kc, double *L_elbo, Fallback fb, int i0, int i1) {
+k_lattice_bwd(BaseView B, const double *__restrict__ rec_src, const int *__restrict__ list, int ntiles, int T, int kc,
+              double *L_elbo, Fallback fb, int i0, int i1) {
   extern __shared__ __align__(16) double smem[];
+  constexpr int CPT = CP ? 2 : 1;                                           // centres per tile
   const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
   const int warp = threadIdx.x >> 5;
   const int j0 = blockIdx.y * kc;
-  const int nj = min(kc, C.K - j0);
-  const int rs = C.rec_stride;
+  const int nj = min(kc, ntiles - j0);
   const tab_t ltab = TabFirst::log_view(smem, lane), etab = TabFirst::exp_view(smem, lane);
   int one;   // 0x3ff00000 pinned in a register (see mant_hi)
   asm volatile("mov.b32 %0, 0x3ff00000;" : "=r"(one));
   double *recs = smem + TabFirst::kDoubles;
   constexpr int RS = 80 + 8 * D + 8 * BaseConst<D, FULL>::DD;              // lattice_rec_stride(d, dd)
+  int *sidx = reinterpret_cast<int *>(recs + (size_t)kc * RS);             // centre index of every tile slot
   const unsigned recs_s = (unsigned)__cvta_generic_to_shared(recs);
   TabFirst::load(smem);
-  for (int x = threadIdx.x; x < nj * rs; x += blockDim.x) recs[x] = C.rec[(size_t)j0 * rs + x];
+  for (int x = threadIdx.x; x < nj * CPT; x += blockDim.x) sidx[x] = list[(size_t)j0 * CPT + x];
+  for (int x = threadIdx.x; x < nj * RS; x += blockDim.x) {
+    const int r = x / RS, o = x - r * RS;
+    recs[x] = rec_src[(size_t)RS * (CP ? j0 + r : list[j0 + r]) + o];
+  }
   __syncthreads();
+  // lanes that hold the shift of row beta = 2q+e (with CP: of the half this lane's rho = g lies in)
+  const int src0 = (2 * q) * 4 + (CP ? (g >> 2) * 2 : 0), src1 = src0 + 4;
 
-  // Work unit = one base x kUnitCentres centres: fine enough that the last wave of warps is nearly full even
+  // Work unit = one base x kUnitCentres tiles: fine enough that the last wave of warps is nearly full even
   // for a 12 500-base shard (8-GPU strong scaling), coarse enough that re-reading the base costs < 1 %.
   const int nuc = (nj + kUnitCentres - 1) / kUnitCentres;
   const long long nunits = (long long)(i1 - i0) * nuc, nw = (long long)gridDim.x * kBwdWarps;
@@ -454,7 +480,7 @@ k_lattice_bwd(BaseView B, CentreView C, int T, int kc, double *L_elbo, Fallback 
       bool bad[kNP];
 #pragma unroll
       for (int p = 0; p < kNP; p++) {
-        const unsigned rec = recs_s + 8u * RS * (unsigned)min(jj + p, nj - 1);   // odd tail: redo the last centre, not stored
+        const unsigned rec = recs_s + 8u * RS * (unsigned)min(jj + p, nj - 1);   // odd tail: redo the last tile, not stored
         expA[p] = lds_frag(rec + 8u * (g * 8 + 2 * q));
         expPi[p] = lds_frag(rec + 8u * (64 + 2 * q));
         E[p] = emission_smem<D, FULL>(b, rec, g, q);
@@ -462,38 +488,70 @@ k_lattice_bwd(BaseView B, CentreView C, int T, int kc, double *L_elbo, Fallback 
         rng[p] = 0u;
         bad[p] = pair_inputs_bad(base_chk, E[p]);
       }
-      for (int t = T - 1; t >= 1; t--) bwd_step_n<kNP, 8, 16>(E, G, expA, b.Ab, ltab, etab, rng, q, one);
+      for (int t = T - 1; t >= 1; t--)
+        bwd_step_n<kNP, 8, 16, CP>(E, G, expA, b.Ab, ltab, etab, rng, q, one, src0, src1);
       // termination (vbhem_hmm_bwd_fwd_mex.c:1029-1080); running it as one more lattice step (logPi for every
       // row of logA, the prior for every row of A_b) needs no special code but twice the fp64 work: slower
       double Lt[kNP];
-      terminate_n<kNP, 8, 16>(G, expPi, b.prior, ltab, etab, q, rng, Lt);
+      terminate_n<kNP, 8, 16, CP>(G, expPi, b.prior, ltab, etab, q, rng, Lt);
       if constexpr (kNP == 2) {
-        // Lt[0] == Lt[1] holds pair 0's value in lane 0 and pair 1's in lane 1: one store for both; the
-        // (rare) flagged pairs take the slow path
+        // Lt[0] == Lt[1] holds, in lane l of row 0, the value of tile l (without CP) or of (tile l & 1, half
+        // l >> 1) (with CP): one store for all; the (rare) flagged pairs take the slow path
         const bool ok = (max(rng[0], rng[1]) <= kShiftBound) & !(bad[0] | bad[1]);
         const bool all_ok = __all_sync(0xffffffffu, ok);
-        const size_t pi = (size_t)i + (size_t)B.N * (j0 + jj + lane);
-        if (lane < 2 && jj + lane < nj) L_elbo[pi] = Lt[0];
+        const int tile = jj + (lane & 1), slot = CP ? 2 * tile + ((lane >> 1) & 1) : tile;
+        const int j = (lane < 2 * CPT && tile < nj) ? sidx[slot] : -1;
+        const size_t pi = (size_t)i + (size_t)B.N * (j < 0 ? 0 : j);
+        if (j >= 0) L_elbo[pi] = Lt[0];
         if (!all_ok) {
 #pragma unroll
           for (int p = 0; p < 2; p++) {
             const bool good = __all_sync(0xffffffffu, (rng[p] <= kShiftBound) & !bad[p]);
-            if (!good && lane == p && jj + p < nj) { fb.flags[pi] = 1; atomicAdd(fb.count, 1); }
+            if (!good && j >= 0 && (lane & 1) == p) { fb.flags[pi] = 1; atomicAdd(fb.count, 1); }
           }
         }
       } else {
+        static_assert(!CP || kNP == 2, "centre pairing needs two tiles in flight");
 #pragma unroll
         for (int p = 0; p < kNP; p++) {
           const double Le = Lt[p];
           const bool good = __all_sync(0xffffffffu, (rng[p] <= kShiftBound) & !bad[p]);
           if (lane == 0 && jj + p < nj) {
-            const size_t pi = (size_t)i + (size_t)B.N * (j0 + jj + p);
+            const size_t pi = (size_t)i + (size_t)B.N * sidx[jj + p];
             L_elbo[pi] = Le;
             if (!good) { fb.flags[pi] = 1; atomicAdd(fb.count, 1); }
           }
         }
       }
     }
+  }
+}
+
+// One block per pair of small centres: the tile record of the pair out of the two centres' own records
+// (k_build_records): slots 0-3 <- centre a's states 0-3, slots 4-7 <- centre b's, expA block-diagonal.
+__global__ void k_pair_records(const double *rec, const int *pairs, int rs, int d, int dd, double *out) {
+  const int a = pairs[2 * blockIdx.x], b = pairs[2 * blockIdx.x + 1];
+  double *o = out + (size_t)rs * blockIdx.x;
+  for (int x = threadIdx.x; x < rs; x += blockDim.x) {
+    // (block, slot, k): which per-state block of the record, which of the 8 tile slots, which entry
+    int base, width, slot, k;
+    if (x < 64) { base = 0; width = 8; slot = x / 8; k = x % 8; }          // expA[rho = slot][sigma = k]
+    else if (x < 72) { base = 64; width = 1; slot = x - 64; k = 0; }       // expPi
+    else if (x < 80) { base = 72; width = 1; slot = x - 72; k = 0; }       // c0
+    else if (x < 80 + 8 * d) { base = 80; width = d; slot = (x - 80) / d; k = (x - 80) % d; }
+    else { base = 80 + 8 * d; width = dd; slot = (x - base) / dd; k = (x - base) % dd; }
+    const int src = slot < 4 ? a : b, s4 = slot & 3;
+    double v;
+    if (base == 0) {
+      if ((k < 4) != (slot < 4)) v = 0.0;                                  // off-diagonal block
+      else if (src >= 0) v = rec[(size_t)rs * src + s4 * 8 + (k & 3)];
+      else v = (k & 3) == 0 ? 1.0 : 0.0;                                   // no partner: a harmless one-state centre
+    } else if (src >= 0) {
+      v = rec[(size_t)rs * src + base + s4 * width + k];
+    } else {
+      v = base == 64 ? (s4 == 0 ? 1.0 : 0.0) : (base == 72 ? (s4 == 0 ? 0.0 : INFINITY) : 0.0);
+    }
+    o[x] = v;
   }
 }
 
@@ -714,26 +772,44 @@ bool lattice_supported(const BaseView &B, const CentreView &C, int T, bool need_
   return true;
 }
 
-int launch_lattice_bwd(const BaseView &B, const CentreView &C, int T, double *L_elbo, Fallback fb,
-                       cudaStream_t st, int i0, int n) {
-  if (n < 0) n = B.N - i0;
-  if (n <= 0) return 0;
-  const int rs = C.rec_stride;
+namespace {
+template <bool CP>
+int launch_bwd_list(const BaseView &B, const double *rec_src, const int *list, int ntiles, int rs, int T,
+                    double *L_elbo, Fallback fb, cudaStream_t st, int i0, int n) {
+  if (ntiles <= 0) return 0;
   int kc = (int)((VB_KC_BYTES) / (sizeof(double) * rs));
-  if (kc > C.K) kc = C.K;
-  const size_t smem = sizeof(double) * ((size_t)kc * rs + TabFirst::kDoubles);
-  const int ny = (C.K + kc - 1) / kc;
+  if (kc > ntiles) kc = ntiles;
+  const size_t smem = sizeof(double) * ((size_t)kc * rs + TabFirst::kDoubles) + sizeof(int) * 2 * (size_t)kc + 16;
+  const int ny = (ntiles + kc - 1) / kc;
   const int kcu = (kc + kUnitCentres - 1) / kUnitCentres;
   long long nxl = ((long long)n * kcu + kBwdWarps - 1) / kBwdWarps;
   int nx = nxl > (1 << 30) ? (1 << 30) : (int)nxl;
   const int cap = VB_BWD_MINB * sm_count();
   if (nx > cap) nx = cap;
   return dispatch(B.d, B.covmode, [&](auto Dc, auto Fc) {
-    auto kern = k_lattice_bwd<decltype(Dc)::value, decltype(Fc)::value>;
+    auto kern = k_lattice_bwd<decltype(Dc)::value, decltype(Fc)::value, CP>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<dim3(nx, ny), kBwdWarps * 32, smem, st>>>(B, C, T, kc, L_elbo, fb, i0, i0 + n);
+    kern<<<dim3(nx, ny), kBwdWarps * 32, smem, st>>>(B, rec_src, list, ntiles, T, kc, L_elbo, fb, i0, i0 + n);
     return 1;
   });
+}
+}  // namespace
+
+// First pass over bases [i0, i0 + n): the centres of C.big_list one per tile, the pairs of C.pair_list two per tile.
+int launch_lattice_bwd(const BaseView &B, const CentreView &C, int T, double *L_elbo, Fallback fb,
+                       cudaStream_t st, int i0, int n) {
+  if (n < 0) n = B.N - i0;
+  if (n <= 0) return 0;
+  int launched = 0;
+  launched += launch_bwd_list<false>(B, C.rec, C.big_list, C.nbig, C.rec_stride, T, L_elbo, fb, st, i0, n);
+  launched += launch_bwd_list<true>(B, C.pair_rec, C.pair_list, C.npairs, C.rec_stride, T, L_elbo, fb, st, i0, n);
+  return launched;
+}
+
+int launch_pair_records(const CentreView &C, int d, int dd, double *out, cudaStream_t st) {
+  if (C.npairs <= 0) return 0;
+  k_pair_records<<<C.npairs, 128, 0, st>>>(C.rec, C.pair_list, C.rec_stride, d, dd, out);
+  return 1;
 }
 
 int launch_lattice_full(const BaseView &B, const CentreView &C, int T, const PairWork &W, const PairOut &O,

@@ -85,7 +85,8 @@ int vbhem_synchronize(vbhem_base_t *base);
 
 /* Kernel selection, for tests and benchmarks: 0 = automatic (tensor-core
  * lattice kernel when maxSb,maxSr <= 8 and d <= 3, else the general kernel),
- * 1 = force the general (any-size, literal log-space) kernel. */
+ * 1 = force the general (any-size, literal log-space) kernel,
+ * 2 = automatic, but without packing two centres of <= 4 states into one 8-state tile. */
 int vbhem_set_kernel(vbhem_base_t *base, int which);
 
 /* ---- Boundary-1: the literal per-pair outputs of the MEX gateway ------------

@@ -354,3 +354,23 @@ def test_model_selection_grid_batched_equals_one_model_at_a_time():
             np.testing.assert_allclose(allg["lb"][2 * g:2 * g + 2], one["lb"], rtol=1e-12)
             for k in ("nu1", "xi", "pr", "mu", "Mu"):
                 np.testing.assert_allclose(allg[k][sel], one[k], rtol=1e-12, atol=1e-12 * np.abs(one[k]).max(), err_msg=k)
+
+
+@pytest.mark.parametrize("sr_list", [[2, 8, 3, 1, 4, 6, 4], [3, 3], [1, 2, 3], [4, 5, 8]])
+def test_centre_pairing_is_bit_identical_to_one_centre_per_tile(sr_list):
+    """First pass: centres of <= 4 states are packed two per 8-state tile (block-diagonal transition weights,
+    one row shift per half).  The packing adds exact zeros only, so L_elbo -- and with it everything
+    downstream -- must be bit-identical to the one-centre-per-tile kernel, and both must match the oracle.
+    Odd numbers of small centres exercise the partner-less tile."""
+    K = len(sr_list)
+    base, hyp, cen = make_case(N=200, K=K, Sb=8, Sr=8, d=2, covmode="full", ragged=True, seed=57, Nv=25.0,
+                               sr_list=np.array(sr_list))
+    with BaseSet(base) as bs:
+        got = bs.estep(cen, 6)
+        cp = bs.counters()
+        bs.set_kernel("unpaired")
+        ref = bs.estep(cen, 6)
+    for k in ("L_elbo", "zhat", "buf"):
+        assert np.array_equal(got[k], ref[k]), k
+    assert cp["general_pairs"] == 0
+    check_fused(got, oracle_fused(base, cen, 6), 200)
