@@ -71,7 +71,7 @@ class BaseSet:
 
     # -- knobs --------------------------------------------------------------
     def set_kernel(self, which: str = "auto"):
-        check(lib().vbhem_set_kernel(self._h, {"auto": 0, "general": 1, "unpaired": 2}[which]))
+        check(lib().vbhem_set_kernel(self._h, {"auto": 0, "general": 1, "unpaired": 2, "halves": 3}[which]))
 
     def set_stream(self, cuda_stream: int | None):
         """Run this handle's work on an existing CUDA stream (``torch.cuda.current_stream().cuda_stream``).
@@ -89,7 +89,8 @@ class BaseSet:
     def counters(self) -> dict:
         out = (C.c_longlong * 8)()
         check(lib().vbhem_last_counters(self._h, out))
-        return dict(launches=out[0], lattice_pairs=out[1], general_pairs=out[2], active_pairs=out[3])
+        return dict(launches=out[0], lattice_pairs=out[1], general_pairs=out[2], active_pairs=out[3], tiles=out[4],
+                    split_tiles=out[5])
 
     # -- Boundary-1 ---------------------------------------------------------
     def estep_pairs(self, cen: dict, tau: int, L_only: bool = False, packed: bool = False) -> dict:

@@ -107,7 +107,8 @@ struct vbhem_base {
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   double timings[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int kernel_choice = 0;
-  bool pair_centres = true;   // first pass: two centres of <= 4 states per tile (vbhem_set_kernel bit 1 disables)
+  bool pair_centres = true;   // first pass: two centres per 8-state tile when they fit (vbhem_set_kernel 2 disables)
+  bool split_tiles = true;    // ... including 5..7 states next to 3..1 (vbhem_set_kernel 3: halves only)
   long long counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int lastK = 0;
 };
@@ -241,23 +242,54 @@ int stage_centres(vbhem_base *h, const CentreArgs &a, CentreDev &cd, double *pre
     CU(h->rec.ensure(sizeof(double) * (size_t)cd.C.rec_stride * K));
     cd.C.rec = h->rec.as<double>();
     launches += launch_build_records(cd.C, d, dd, h->rec.as<double>(), h->st);
-    // first-pass tiling: centres with <= 4 states share a tile, two by two (pairing needs >= 2 of them)
-    std::vector<int> big, small;
-    for (int j = 0; j < K; j++) (a.Sr[j] <= 4 && h->pair_centres ? small : big).push_back(j);
-    if (small.size() < 2) { big.insert(big.end(), small.begin(), small.end()); small.clear(); std::sort(big.begin(), big.end()); }
-    if (small.size() % 2) small.push_back(-1);
+    // First-pass tiling.  A centre of 5..7 states takes, largest first, the largest centre that still fits beside
+    // it (split tile, class = the smaller one's column count 1..3); the remaining centres of <= 4 states pair up
+    // two by two (halves, class 0; pairing needs >= 2 of them); everything else has a tile of its own.
+    std::vector<int> big, small[5], cls[kTileClasses];
+    for (int j = 0; j < K; j++) {
+      if (a.Sr[j] <= 4 && h->pair_centres) small[a.Sr[j]].push_back(j);
+      else big.push_back(j);
+    }
+    if (h->pair_centres && h->split_tiles) {
+      std::vector<int> order(big);
+      std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return a.Sr[x] > a.Sr[y]; });
+      std::vector<int> alone;
+      for (int j : order) {
+        int s = 8 - a.Sr[j];
+        if (s > 3) s = 3;
+        while (s >= 1 && small[s].empty()) s--;
+        if (s >= 1) {
+          cls[s].push_back(small[s].back());
+          cls[s].push_back(j);
+          small[s].pop_back();
+        } else {
+          alone.push_back(j);
+        }
+      }
+      big.swap(alone);
+      std::sort(big.begin(), big.end());
+    }
+    for (int s = 4; s >= 1; s--) cls[0].insert(cls[0].end(), small[s].begin(), small[s].end());
+    if (cls[0].size() < 2) { big.insert(big.end(), cls[0].begin(), cls[0].end()); cls[0].clear(); std::sort(big.begin(), big.end()); }
+    if (cls[0].size() % 2) cls[0].push_back(-1);
     std::vector<int> lists(big);
-    lists.insert(lists.end(), small.begin(), small.end());
+    int ntile_pairs = 0;
+    for (int c = 0; c < kTileClasses; c++) {
+      lists.insert(lists.end(), cls[c].begin(), cls[c].end());
+      cd.C.npairs[c] = (int)cls[c].size() / 2;
+      ntile_pairs += cd.C.npairs[c];
+    }
     CU(h->tile_i.ensure(sizeof(int) * (lists.size() + 1)));
     CU(cudaMemcpyAsync(h->tile_i.p, lists.data(), sizeof(int) * lists.size(), cudaMemcpyHostToDevice, h->st));
     CU(cudaStreamSynchronize(h->st));                      // `lists` goes out of scope
     cd.C.big_list = h->tile_i.as<int>();
     cd.C.nbig = (int)big.size();
     cd.C.pair_list = cd.C.big_list + big.size();
-    cd.C.npairs = (int)small.size() / 2;
     cd.C.pair_rec = nullptr;
-    if (cd.C.npairs > 0) {
-      CU(h->pair_rec.ensure(sizeof(double) * (size_t)cd.C.rec_stride * cd.C.npairs));
+    h->counters[4] = cd.C.nbig + ntile_pairs;
+    h->counters[5] = ntile_pairs - cd.C.npairs[0];
+    if (ntile_pairs > 0) {
+      CU(h->pair_rec.ensure(sizeof(double) * (size_t)cd.C.rec_stride * ntile_pairs));
       cd.C.pair_rec = h->pair_rec.as<double>();
       launches += launch_pair_records(cd.C, d, dd, h->pair_rec.as<double>(), h->st);
     }
@@ -679,9 +711,11 @@ int vbhem_synchronize(vbhem_base_t *h) {
 
 int vbhem_set_kernel(vbhem_base_t *h, int which) {
   if (!h) return fail(VBHEM_EINVAL, "base handle is NULL");
-  if (which < 0 || which > 2) return fail(VBHEM_EINVAL, "kernel must be 0 (auto), 1 (general) or 2 (auto, one centre per tile)");
+  if (which < 0 || which > 3)
+    return fail(VBHEM_EINVAL, "kernel must be 0 (auto), 1 (general), 2 (auto, one centre per tile) or 3 (auto, halves only)");
   h->kernel_choice = which == 1 ? 1 : 0;
   h->pair_centres = which != 2;
+  h->split_tiles = which != 3;
   return VBHEM_OK;
 }
 

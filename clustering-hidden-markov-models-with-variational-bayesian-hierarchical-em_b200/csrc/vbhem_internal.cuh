@@ -38,12 +38,15 @@ struct CentreView {
   //   expA[8][8] (row rho, col sigma) | expPi[8] | c0[8] | m[8][d] | vW[8][dd]
   const double *rec;
   int rec_stride;         // doubles per record
-  // First-pass tiling: centres with more than four states take a tile each (big_list[nbig]); centres with at
-  // most four are paired, two per tile (pair_list[2 * npairs], -1 = no partner; tile records in pair_rec).
+  // First-pass tiling: a centre alone in its tile (big_list[nbig]) or two centres per tile, in kTileClasses
+  // classes laid out one after the other in pair_list (two entries per tile, -1 = no partner) and pair_rec (one
+  // tile record each): class 0 = two centres of at most four states, columns 0-3 / 4-7; class k = 1..3 = a centre
+  // of at most k states in columns [0, k) and one of at most 8 - k states in columns [k, 8).
   const int *big_list, *pair_list;
   const double *pair_rec;
-  int nbig, npairs;
+  int nbig, npairs[4];
 };
+constexpr int kTileClasses = 4;
 
 // One unit of second-pass work.
 struct PairItem { int i, j; double w; };

@@ -250,14 +250,28 @@ __device__ __forceinline__ Frag emission_smem(const BaseConst<D, FULL> &b, unsig
 
 // Shift of one lattice row = the largest binary exponent of e^G over the row (integer pipe, 32-bit
 // shuffles over the four lanes that hold the row).
-// CP ("centre pairing"): the tile holds TWO centres of at most four states each -- columns 0-3 and 4-7, a
-// block-diagonal expA -- so a row has one shift per half, shared by the two lanes that hold that half.
-template <bool CP = false>
+// SP ("centre pairing"): 0 = one centre per tile.  1 = the tile holds TWO centres of at most four states each --
+// columns 0-3 and 4-7, a block-diagonal expA -- so a row has one shift per half, shared by the two lanes that
+// hold that half.  2 = two centres split at any column k (1 <= k <= 7; columns [0,k) and [k,8)): a row has a
+// left and a right shift, every lane ends up with both (row_shift_split).
+template <int SP = 0>
 __device__ __forceinline__ int row_shift(int e0, int e1) {
   int m = max(e0, e1);
   m = max(m, __shfl_xor_sync(0xffffffffu, m, 1));
-  if (!CP) m = max(m, __shfl_xor_sync(0xffffffffu, m, 2));
+  if (SP == 0) m = max(m, __shfl_xor_sync(0xffffffffu, m, 2));
   return m;
+}
+// Which of a lane's two columns (2q, 2q+1) lie in the left segment of a split tile; lane q = 0 always holds a
+// left column and publishes the left shift to the transposed read, the others publish the right one.
+struct Split { bool l0, l1, pubL; };
+__device__ __forceinline__ void row_shift_split(const Split &sp, int e0, int e1, int &cL, int &cR) {
+  constexpr int kNone = -2147483647 - 1;
+  cL = max(sp.l0 ? e0 : kNone, sp.l1 ? e1 : kNone);
+  cR = max(sp.l0 ? kNone : e0, sp.l1 ? kNone : e1);
+  cL = max(cL, __shfl_xor_sync(0xffffffffu, cL, 1));
+  cR = max(cR, __shfl_xor_sync(0xffffffffu, cR, 1));
+  cL = max(cL, __shfl_xor_sync(0xffffffffu, cL, 2));
+  cR = max(cR, __shfl_xor_sync(0xffffffffu, cR, 2));
 }
 
 // The linear-domain recursion cannot create a NaN out of clean inputs (sums of non-negative
@@ -341,10 +355,10 @@ constexpr int kBwdWarps = VB_BWD_WARPS;
 constexpr int kUnitCentres = VB_UNIT_CENTRES;   // centres per work unit of the first pass (multiple of VB_NP)
 constexpr int kNP = VB_NP;
 
-template <int NP, int LS, int ES, bool CP>
+template <int NP, int LS, int ES, int SP>
 __device__ __forceinline__ void bwd_step_n(const Frag (&E)[NP], Frag (&G)[NP], const Frag (&expA)[NP],
                                            const Frag &Ab, tab_t ltab, tab_t etab,
-                                           unsigned (&rng)[NP], int q, int one, int src0, int src1) {
+                                           unsigned (&rng)[NP], int q, int one, int src0, int src1, const Split &sp) {
   int e0[NP], e1[NP], c[NP];
   Frag Bm[NP], ST[NP], ell[NP];
 #pragma unroll
@@ -352,18 +366,30 @@ __device__ __forceinline__ void bwd_step_n(const Frag (&E)[NP], Frag (&G)[NP], c
     Bm[p].x0 = exp_split<ES>(G[p].x0, etab, e0[p]);
     Bm[p].x1 = exp_split<ES>(G[p].x1, etab, e1[p]);
   }
+  if constexpr (SP == 2) {
+    int cL[NP], cR[NP];
 #pragma unroll
-  for (int p = 0; p < NP; p++) c[p] = row_shift<CP>(e0[p], e1[p]);
+    for (int p = 0; p < NP; p++) row_shift_split(sp, e0[p], e1[p], cL[p], cR[p]);
 #pragma unroll
-  for (int p = 0; p < NP; p++) {
-    rng[p] = max(rng[p], shift_excess(c[p]));
-    Bm[p] = Frag{exp_scale(Bm[p].x0, e0[p] - c[p]), exp_scale(Bm[p].x1, e1[p] - c[p])};
+    for (int p = 0; p < NP; p++) {
+      rng[p] = max(rng[p], max(shift_excess(cL[p]), shift_excess(cR[p])));
+      Bm[p] = Frag{exp_scale(Bm[p].x0, e0[p] - (sp.l0 ? cL[p] : cR[p])), exp_scale(Bm[p].x1, e1[p] - (sp.l1 ? cL[p] : cR[p]))};
+      c[p] = sp.pubL ? cL[p] : cR[p];
+    }
+  } else {
+#pragma unroll
+    for (int p = 0; p < NP; p++) c[p] = row_shift<SP>(e0[p], e1[p]);
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+      rng[p] = max(rng[p], shift_excess(c[p]));
+      Bm[p] = Frag{exp_scale(Bm[p].x0, e0[p] - c[p]), exp_scale(Bm[p].x1, e1[p] - c[p])};
+    }
   }
 #pragma unroll
   for (int p = 0; p < NP; p++) ST[p] = mma_nt(expA[p], Bm[p]);
 #pragma unroll
   for (int p = 0; p < NP; p++) {
-    // shift of row beta = 2q+e (and, with CP, of the half that this lane's rho = g belongs to)
+    // shift of row beta = 2q+e (and, with SP, of the segment that this lane's rho = g belongs to)
     const int cb0 = __shfl_sync(0xffffffffu, c[p] - 1023, src0);
     const int cb1 = __shfl_sync(0xffffffffu, c[p] - 1023, src1);
     ell[p] = Frag{log_shift_biased<LS>(ST[p].x0, ltab, cb0, one), log_shift_biased<LS>(ST[p].x1, ltab, cb1, one)};
@@ -377,10 +403,10 @@ __device__ __forceinline__ void bwd_step_n(const Frag (&E)[NP], Frag (&G)[NP], c
 
 // Termination of NP pairs side by side (first pass: L_elbo only; L[p] is valid in lane p when NP == 2,
 // in lane 0 otherwise).
-template <int NP, int LS, int ES, bool CP>
+template <int NP, int LS, int ES, int SP>
 __device__ __forceinline__ void terminate_n(const Frag (&G)[NP], const Frag (&expPi)[NP], double prior,
                                             tab_t ltab, tab_t etab, int q, unsigned (&rng)[NP],
-                                            double (&L)[NP]) {
+                                            double (&L)[NP], const Split &sp) {
   int e0[NP], e1[NP], c[NP];
   double m0[NP], m1[NP], s[NP];
 #pragma unroll
@@ -388,15 +414,44 @@ __device__ __forceinline__ void terminate_n(const Frag (&G)[NP], const Frag (&ex
     m0[p] = exp_split<ES>(G[p].x0, etab, e0[p]);
     m1[p] = exp_split<ES>(G[p].x1, etab, e1[p]);
   }
+  const double pu = prior * kUnit;
+  if constexpr (SP == 2) {
+    // two centres per tile split at any column, two tiles in flight: four segment sums per row; a transposing
+    // reduction over the quad leaves lane q with the sum of (tile q & 1, segment q >> 1), one logarithm per lane
+    static_assert(NP == 2, "centre pairing is written for two tiles in flight");
+    int cL[2], cR[2];
+    double tL[2], tR[2];
 #pragma unroll
-  for (int p = 0; p < NP; p++) c[p] = row_shift<CP>(e0[p], e1[p]);
+    for (int p = 0; p < 2; p++) row_shift_split(sp, e0[p], e1[p], cL[p], cR[p]);
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+      rng[p] = max(rng[p], max(shift_excess(cL[p]), shift_excess(cR[p])));
+      const double a0 = expPi[p].x0 * exp_scale(m0[p], e0[p] - (sp.l0 ? cL[p] : cR[p]));
+      const double a1 = expPi[p].x1 * exp_scale(m1[p], e1[p] - (sp.l1 ? cL[p] : cR[p]));
+      tL[p] = (sp.l0 ? a0 : 0.0) + (sp.l1 ? a1 : 0.0);
+      tR[p] = (sp.l0 ? 0.0 : a0) + (sp.l1 ? 0.0 : a1);
+    }
+    const bool odd = q & 1, hi = q & 2;
+    // xor 1: even lanes keep tile 0's sums, odd lanes tile 1's
+    const double kL = (odd ? tL[1] : tL[0]) + __shfl_xor_sync(0xffffffffu, odd ? tL[0] : tL[1], 1);
+    const double kR = (odd ? tR[1] : tR[0]) + __shfl_xor_sync(0xffffffffu, odd ? tR[0] : tR[1], 1);
+    // xor 2: lanes q < 2 keep the left segment, q >= 2 the right one
+    const double v = (hi ? kR : kL) + __shfl_xor_sync(0xffffffffu, hi ? kL : kR, 2);
+    const int cs = odd ? (hi ? cR[1] : cL[1]) : (hi ? cR[0] : cL[0]);
+    double w = pu * log_shift<LS>(v, ltab, cs);
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+    L[0] = w;
+    L[1] = w;
+  } else {
+#pragma unroll
+  for (int p = 0; p < NP; p++) c[p] = row_shift<SP>(e0[p], e1[p]);
 #pragma unroll
   for (int p = 0; p < NP; p++) {
     rng[p] = max(rng[p], shift_excess(c[p]));
     s[p] = expPi[p].x0 * exp_scale(m0[p], e0[p] - c[p]) + expPi[p].x1 * exp_scale(m1[p], e1[p] - c[p]);
   }
-  const double pu = prior * kUnit;
-  if constexpr (CP) {
+  if constexpr (SP == 1) {
     // two centres per tile, two tiles in flight: the half-row sums of both tiles, then lane q takes the
     // logarithm for (tile q & 1, half q >> 1); after the sum over base states lane q of row 0 holds that L_elbo
     static_assert(NP == 2, "centre pairing is written for two tiles in flight");
@@ -433,16 +488,18 @@ __device__ __forceinline__ void terminate_n(const Frag (&G)[NP], const Frag (&ex
       for (int p = 0; p < NP; p++) L[p] += __shfl_xor_sync(0xffffffffu, L[p], o);
     }
   }
+  }
 }
 
-// rec_src / list: without CP, tile r of this launch is centre list[r] and its record is rec_src + RS * list[r];
-// with CP, tile r is the pair (list[2r], list[2r+1]) (-1 = no partner) and its record is rec_src + RS * r.
-template <int D, bool FULL, bool CP>
+// rec_src / list: without SP, tile r of this launch is centre list[r] and its record is rec_src + RS * list[r];
+// with SP, tile r is the pair (list[2r], list[2r+1]) (-1 = no partner) and its record is rec_src + RS * r.
+// ksplit (SP == 2): the column where the second centre of every tile of this launch starts.
+template <int D, bool FULL, int SP>
 __global__ void __launch_bounds__(kBwdWarps * 32, VB_BWD_MINB)
 k_lattice_bwd(BaseView B, const double *__restrict__ rec_src, const int *__restrict__ list, int ntiles, int T, int kc,
-              double *L_elbo, Fallback fb, int i0, int i1) {
+              double *L_elbo, Fallback fb, int i0, int i1, int ksplit) {
   extern __shared__ __align__(16) double smem[];
-  constexpr int CPT = CP ? 2 : 1;                                           // centres per tile
+  constexpr int CPT = SP ? 2 : 1;                                           // centres per tile
   const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
   const int warp = threadIdx.x >> 5;
   const int j0 = blockIdx.y * kc;
@@ -458,11 +515,12 @@ k_lattice_bwd(BaseView B, const double *__restrict__ rec_src, const int *__restr
   for (int x = threadIdx.x; x < nj * CPT; x += blockDim.x) sidx[x] = list[(size_t)j0 * CPT + x];
   for (int x = threadIdx.x; x < nj * RS; x += blockDim.x) {
     const int r = x / RS, o = x - r * RS;
-    recs[x] = rec_src[(size_t)RS * (CP ? j0 + r : list[j0 + r]) + o];
+    recs[x] = rec_src[(size_t)RS * (SP ? j0 + r : list[j0 + r]) + o];
   }
   __syncthreads();
-  // lanes that hold the shift of row beta = 2q+e (with CP: of the half this lane's rho = g lies in)
-  const int src0 = (2 * q) * 4 + (CP ? (g >> 2) * 2 : 0), src1 = src0 + 4;
+  // lanes that hold the shift of row beta = 2q+e (with SP: of the segment this lane's rho = g lies in)
+  const int src0 = (2 * q) * 4 + (SP == 1 ? (g >> 2) * 2 : (SP == 2 ? (g < ksplit ? 0 : 3) : 0)), src1 = src0 + 4;
+  const Split sp{2 * q < ksplit, 2 * q + 1 < ksplit, q == 0};
 
   // Work unit = one base x kUnitCentres tiles: fine enough that the last wave of warps is nearly full even
   // for a 12 500-base shard (8-GPU strong scaling), coarse enough that re-reading the base costs < 1 %.
@@ -489,17 +547,17 @@ k_lattice_bwd(BaseView B, const double *__restrict__ rec_src, const int *__restr
         bad[p] = pair_inputs_bad(base_chk, E[p]);
       }
       for (int t = T - 1; t >= 1; t--)
-        bwd_step_n<kNP, 8, 16, CP>(E, G, expA, b.Ab, ltab, etab, rng, q, one, src0, src1);
+        bwd_step_n<kNP, 8, 16, SP>(E, G, expA, b.Ab, ltab, etab, rng, q, one, src0, src1, sp);
       // termination (vbhem_hmm_bwd_fwd_mex.c:1029-1080); running it as one more lattice step (logPi for every
       // row of logA, the prior for every row of A_b) needs no special code but twice the fp64 work: slower
       double Lt[kNP];
-      terminate_n<kNP, 8, 16, CP>(G, expPi, b.prior, ltab, etab, q, rng, Lt);
+      terminate_n<kNP, 8, 16, SP>(G, expPi, b.prior, ltab, etab, q, rng, Lt, sp);
       if constexpr (kNP == 2) {
-        // Lt[0] == Lt[1] holds, in lane l of row 0, the value of tile l (without CP) or of (tile l & 1, half
-        // l >> 1) (with CP): one store for all; the (rare) flagged pairs take the slow path
+        // Lt[0] == Lt[1] holds, in lane l of row 0, the value of tile l (without SP) or of (tile l & 1, segment
+        // l >> 1) (with SP): one store for all; the (rare) flagged pairs take the slow path
         const bool ok = (max(rng[0], rng[1]) <= kShiftBound) & !(bad[0] | bad[1]);
         const bool all_ok = __all_sync(0xffffffffu, ok);
-        const int tile = jj + (lane & 1), slot = CP ? 2 * tile + ((lane >> 1) & 1) : tile;
+        const int tile = jj + (lane & 1), slot = SP ? 2 * tile + ((lane >> 1) & 1) : tile;
         const int j = (lane < 2 * CPT && tile < nj) ? sidx[slot] : -1;
         const size_t pi = (size_t)i + (size_t)B.N * (j < 0 ? 0 : j);
         if (j >= 0) L_elbo[pi] = Lt[0];
@@ -511,7 +569,7 @@ k_lattice_bwd(BaseView B, const double *__restrict__ rec_src, const int *__restr
           }
         }
       } else {
-        static_assert(!CP || kNP == 2, "centre pairing needs two tiles in flight");
+        static_assert(!SP || kNP == 2, "centre pairing needs two tiles in flight");
 #pragma unroll
         for (int p = 0; p < kNP; p++) {
           const double Le = Lt[p];
@@ -527,9 +585,9 @@ k_lattice_bwd(BaseView B, const double *__restrict__ rec_src, const int *__restr
   }
 }
 
-// One block per pair of small centres: the tile record of the pair out of the two centres' own records
-// (k_build_records): slots 0-3 <- centre a's states 0-3, slots 4-7 <- centre b's, expA block-diagonal.
-__global__ void k_pair_records(const double *rec, const int *pairs, int rs, int d, int dd, double *out) {
+// One block per pair of centres that share a tile: the tile record out of the two centres' own records
+// (k_build_records): slots [0, ks) <- centre a's states 0.., slots [ks, 8) <- centre b's, expA block-diagonal.
+__global__ void k_pair_records(const double *rec, const int *pairs, int rs, int d, int dd, int ks, double *out) {
   const int a = pairs[2 * blockIdx.x], b = pairs[2 * blockIdx.x + 1];
   double *o = out + (size_t)rs * blockIdx.x;
   for (int x = threadIdx.x; x < rs; x += blockDim.x) {
@@ -540,16 +598,17 @@ __global__ void k_pair_records(const double *rec, const int *pairs, int rs, int 
     else if (x < 80) { base = 72; width = 1; slot = x - 72; k = 0; }       // c0
     else if (x < 80 + 8 * d) { base = 80; width = d; slot = (x - 80) / d; k = (x - 80) % d; }
     else { base = 80 + 8 * d; width = dd; slot = (x - base) / dd; k = (x - base) % dd; }
-    const int src = slot < 4 ? a : b, s4 = slot & 3;
+    const int src = slot < ks ? a : b, sl = slot < ks ? slot : slot - ks;   // the centre's own state index
     double v;
     if (base == 0) {
-      if ((k < 4) != (slot < 4)) v = 0.0;                                  // off-diagonal block
-      else if (src >= 0) v = rec[(size_t)rs * src + s4 * 8 + (k & 3)];
-      else v = (k & 3) == 0 ? 1.0 : 0.0;                                   // no partner: a harmless one-state centre
+      const int kl = k < ks ? k : k - ks;
+      if ((k < ks) != (slot < ks)) v = 0.0;                                // off-diagonal block
+      else if (src >= 0) v = rec[(size_t)rs * src + sl * 8 + kl];
+      else v = kl == 0 ? 1.0 : 0.0;                                        // no partner: a harmless one-state centre
     } else if (src >= 0) {
-      v = rec[(size_t)rs * src + base + s4 * width + k];
+      v = rec[(size_t)rs * src + base + sl * width + k];
     } else {
-      v = base == 64 ? (s4 == 0 ? 1.0 : 0.0) : (base == 72 ? (s4 == 0 ? 0.0 : INFINITY) : 0.0);
+      v = base == 64 ? (sl == 0 ? 1.0 : 0.0) : (base == 72 ? (sl == 0 ? 0.0 : INFINITY) : 0.0);
     }
     o[x] = v;
   }
@@ -773,9 +832,9 @@ bool lattice_supported(const BaseView &B, const CentreView &C, int T, bool need_
 }
 
 namespace {
-template <bool CP>
+template <int SP>
 int launch_bwd_list(const BaseView &B, const double *rec_src, const int *list, int ntiles, int rs, int T,
-                    double *L_elbo, Fallback fb, cudaStream_t st, int i0, int n) {
+                    double *L_elbo, Fallback fb, cudaStream_t st, int i0, int n, int ksplit) {
   if (ntiles <= 0) return 0;
   int kc = (int)((VB_KC_BYTES) / (sizeof(double) * rs));
   if (kc > ntiles) kc = ntiles;
@@ -787,29 +846,43 @@ int launch_bwd_list(const BaseView &B, const double *rec_src, const int *list, i
   const int cap = VB_BWD_MINB * sm_count();
   if (nx > cap) nx = cap;
   return dispatch(B.d, B.covmode, [&](auto Dc, auto Fc) {
-    auto kern = k_lattice_bwd<decltype(Dc)::value, decltype(Fc)::value, CP>;
+    auto kern = k_lattice_bwd<decltype(Dc)::value, decltype(Fc)::value, SP>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<dim3(nx, ny), kBwdWarps * 32, smem, st>>>(B, rec_src, list, ntiles, T, kc, L_elbo, fb, i0, i0 + n);
+    kern<<<dim3(nx, ny), kBwdWarps * 32, smem, st>>>(B, rec_src, list, ntiles, T, kc, L_elbo, fb, i0, i0 + n, ksplit);
     return 1;
   });
 }
 }  // namespace
 
-// First pass over bases [i0, i0 + n): the centres of C.big_list one per tile, the pairs of C.pair_list two per tile.
+// First pass over bases [i0, i0 + n): the centres of C.big_list one per tile, the pairs of the tile classes two per
+// tile (class 0: halves, split at column 4; classes 1-3: split at that column).
 int launch_lattice_bwd(const BaseView &B, const CentreView &C, int T, double *L_elbo, Fallback fb,
                        cudaStream_t st, int i0, int n) {
   if (n < 0) n = B.N - i0;
   if (n <= 0) return 0;
   int launched = 0;
-  launched += launch_bwd_list<false>(B, C.rec, C.big_list, C.nbig, C.rec_stride, T, L_elbo, fb, st, i0, n);
-  launched += launch_bwd_list<true>(B, C.pair_rec, C.pair_list, C.npairs, C.rec_stride, T, L_elbo, fb, st, i0, n);
+  launched += launch_bwd_list<0>(B, C.rec, C.big_list, C.nbig, C.rec_stride, T, L_elbo, fb, st, i0, n, 8);
+  int off = 0;
+  for (int c = 0; c < kTileClasses; c++) {
+    const double *rec = C.pair_rec + (size_t)C.rec_stride * off;
+    const int *list = C.pair_list + 2 * (size_t)off;
+    if (c == 0) launched += launch_bwd_list<1>(B, rec, list, C.npairs[c], C.rec_stride, T, L_elbo, fb, st, i0, n, 4);
+    else launched += launch_bwd_list<2>(B, rec, list, C.npairs[c], C.rec_stride, T, L_elbo, fb, st, i0, n, c);
+    off += C.npairs[c];
+  }
   return launched;
 }
 
 int launch_pair_records(const CentreView &C, int d, int dd, double *out, cudaStream_t st) {
-  if (C.npairs <= 0) return 0;
-  k_pair_records<<<C.npairs, 128, 0, st>>>(C.rec, C.pair_list, C.rec_stride, d, dd, out);
-  return 1;
+  int launched = 0, off = 0;
+  for (int c = 0; c < kTileClasses; c++) {
+    if (C.npairs[c] <= 0) continue;
+    k_pair_records<<<C.npairs[c], 128, 0, st>>>(C.rec, C.pair_list + 2 * (size_t)off, C.rec_stride, d, dd, c == 0 ? 4 : c,
+                                                out + (size_t)C.rec_stride * off);
+    off += C.npairs[c];
+    launched++;
+  }
+  return launched;
 }
 
 int launch_lattice_full(const BaseView &B, const CentreView &C, int T, const PairWork &W, const PairOut &O,

@@ -86,7 +86,8 @@ int vbhem_synchronize(vbhem_base_t *base);
 /* Kernel selection, for tests and benchmarks: 0 = automatic (tensor-core
  * lattice kernel when maxSb,maxSr <= 8 and d <= 3, else the general kernel),
  * 1 = force the general (any-size, literal log-space) kernel,
- * 2 = automatic, but without packing two centres of <= 4 states into one 8-state tile. */
+ * 2 = automatic, but without packing two small centres into one 8-state tile,
+ * 3 = automatic, packing only centres of <= 4 states two by two (no 5+3 / 6+2 / 7+1 tiles). */
 int vbhem_set_kernel(vbhem_base_t *base, int which);
 
 /* ---- Boundary-1: the literal per-pair outputs of the MEX gateway ------------
@@ -270,7 +271,8 @@ int vbhem_measure_fp64_peak(int device, double out[2]);
 /* Counters of the handle's last E-step, for bench.py / tests:
  *   out[0] kernels launched, out[1] pairs through the tensor-core kernel,
  *   out[2] pairs through the general kernel (incl. numerical fall-backs),
- *   out[3] pairs with Z > 1e-8 (second pass), out[4..7] reserved. */
+ *   out[3] pairs with Z > 1e-8 (second pass), out[4] 8-state tiles per base in the first pass,
+ *   out[5] of which split tiles (5..7 + 3..1 states), out[6..7] reserved. */
 int vbhem_last_counters(vbhem_base_t *base, long long out[8]);
 
 #ifdef __cplusplus

@@ -366,11 +366,39 @@ def test_centre_pairing_is_bit_identical_to_one_centre_per_tile(sr_list):
     base, hyp, cen = make_case(N=200, K=K, Sb=8, Sr=8, d=2, covmode="full", ragged=True, seed=57, Nv=25.0,
                                sr_list=np.array(sr_list))
     with BaseSet(base) as bs:
+        bs.set_kernel("halves")
         got = bs.estep(cen, 6)
         cp = bs.counters()
         bs.set_kernel("unpaired")
         ref = bs.estep(cen, 6)
     for k in ("L_elbo", "zhat", "buf"):
         assert np.array_equal(got[k], ref[k]), k
-    assert cp["general_pairs"] == 0
+    assert cp["general_pairs"] == 0 and cp["split_tiles"] == 0
     check_fused(got, oracle_fused(base, cen, 6), 200)
+
+
+@pytest.mark.parametrize("sr_list,tiles,split", [
+    ([2, 8, 3, 1, 4, 6, 4], 4, 1),          # 8 | 6+2 | 4+4 | 3+1
+    ([7, 1, 6, 2, 5, 3], 3, 3),             # every split class once
+    ([5, 1, 5, 2, 7, 3, 6, 1, 1], 5, 4),    # 7+1 | 6+2 | 5+3 | 5+1 | 1+none: slots left empty beside a partner
+    ([8, 8, 5, 7], 4, 0),                   # nothing to pair with
+    ([6, 6, 2, 1], 2, 2)])
+@pytest.mark.parametrize("covmode,d", [("full", 2), ("diag", 3)])
+def test_split_tiles_match_one_centre_per_tile(sr_list, tiles, split, covmode, d):
+    """First pass: a centre of 5..7 states shares its tile with one of <= 3..1 states (columns [0,k) and [k,8),
+    two shifts per row).  The columns move, so sums are re-associated: equal to the one-centre-per-tile kernel
+    to a few ulp (1e-13 here), equal to the oracle at the parity tolerance, and run-to-run identical."""
+    K = len(sr_list)
+    base, hyp, cen = make_case(N=150, K=K, Sb=8, Sr=8, d=d, covmode=covmode, ragged=True, seed=61, Nv=25.0,
+                               sr_list=np.array(sr_list))
+    with BaseSet(base) as bs:
+        got = bs.estep(cen, 7)
+        cp = bs.counters()
+        again = bs.estep(cen, 7)
+        bs.set_kernel("unpaired")
+        ref = bs.estep(cen, 7)
+    assert (cp["tiles"], cp["split_tiles"], cp["general_pairs"]) == (tiles, split, 0)
+    for k in ("L_elbo", "zhat", "buf"):
+        assert np.array_equal(got[k], again[k]), k
+    np.testing.assert_allclose(got["L_elbo"], ref["L_elbo"], rtol=1e-13, atol=0)
+    check_fused(got, oracle_fused(base, cen, 7), 150)
