@@ -182,7 +182,8 @@ k_zhat(int N, int K, int ngroups, const int *gstart, const double *L_elbo, const
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool live = i < N;
   const double Nt = live ? Ntilde[i] : 0.0;
-  for (int g = 0; g < ngroups; g++) {
+  // soft-max groups are independent: blockIdx.y strides over them (a (K,S) grid has few bases and many groups)
+  for (int g = blockIdx.y; g < ngroups; g += gridDim.y) {
     const int ja = gstart[g], jb = gstart[g + 1];
     double mv = -INFINITY, lse = 0.0;
     if (live) {
@@ -285,18 +286,30 @@ __global__ void k_list_scan_blocks(int nblocks, int K, const int *cnt, int *offs
 // seg_start[j], chunk_start[j] (K+1 entries each): exclusive prefix over centres; totals = {#active, #chunks}.
 __global__ void k_list_scan_centres(int K, int chunk_len, const int *segcnt, int *seg_start, int *chunk_start,
                                     int *totals) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  // one warp; lane l owns the contiguous range [l * per, (l + 1) * per) of centres
+  const int lane = threadIdx.x, per = (K + 31) / 32;
+  const int ja = min(K, lane * per), jb = min(K, ja + per);
   int a = 0, c = 0;
-  for (int j = 0; j < K; j++) {
-    seg_start[j] = a;
-    chunk_start[j] = c;
-    a += segcnt[j];
-    c += (segcnt[j] + chunk_len - 1) / chunk_len;
+  for (int j = ja; j < jb; j++) { a += segcnt[j]; c += (segcnt[j] + chunk_len - 1) / chunk_len; }
+  int ia = a, ic = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int ta = __shfl_up_sync(0xffffffffu, ia, o), tc = __shfl_up_sync(0xffffffffu, ic, o);
+    if (lane >= o) { ia += ta; ic += tc; }
   }
-  seg_start[K] = a;
-  chunk_start[K] = c;
-  totals[0] = a;
-  totals[1] = c;
+  int ra = ia - a, rc = ic - c;   // exclusive prefixes
+  for (int j = ja; j < jb; j++) {
+    seg_start[j] = ra;
+    chunk_start[j] = rc;
+    ra += segcnt[j];
+    rc += (segcnt[j] + chunk_len - 1) / chunk_len;
+  }
+  if (lane == 31) {
+    seg_start[K] = ia;
+    chunk_start[K] = ic;
+    totals[0] = ia;
+    totals[1] = ic;
+  }
 }
 
 __global__ void __launch_bounds__(kZThreads)
@@ -307,7 +320,7 @@ k_list_fill(int N, int K, const double *zhat, const double *Ntilde, const int *o
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool live = i < N;
   const double Nt = live ? Ntilde[i] : 0.0;
-  for (int j0 = 0; j0 < K; j0 += kJT) {
+  for (int j0 = blockIdx.y * kJT; j0 < K; j0 += gridDim.y * kJT) {   // centre tiles are independent
     const int nt = min(kJT, K - j0);
     int minec = 0;
     for (int jj = 0; jj < nt; jj++) {
@@ -475,6 +488,14 @@ int launch_sanitize_base(BaseView B, double *prior, double *A, double *mu, doubl
 
 int zhat_blocks(int N) { return (N + kZThreads - 1) / kZThreads; }
 
+// gridDim.y for kernels whose blocks over the bases each loop over `parts` independent parts: enough blocks for
+// eight per SM (B200: 148 SMs) when the base set alone gives too few
+static int spread(int nblk, int parts) {
+  int ny = (8 * 148 + nblk - 1) / (nblk > 0 ? nblk : 1);
+  if (ny > parts) ny = parts;
+  return ny < 1 ? 1 : ny;
+}
+
 int launch_zhat(int N, int K, int ngroups, const int *gstart, const double *L_elbo, const double *logOmega,
                 const double *Ntilde, double *zhat, double *Nj_part, int *cnt, double *lb_part, double *Nj, double *lb,
                 cudaStream_t st, int blk0, int nblk, bool reduce) {
@@ -482,8 +503,8 @@ int launch_zhat(int N, int K, int ngroups, const int *gstart, const double *L_el
   if (nblk < 0) nblk = nb - blk0;
   int launched = 0;
   if (nblk > 0) {
-    k_zhat<<<nblk, kZThreads, 0, st>>>(N, K, ngroups, gstart, L_elbo, logOmega, Ntilde, zhat, Nj_part, cnt, lb_part,
-                                       blk0);
+    k_zhat<<<dim3(nblk, spread(nblk, ngroups)), kZThreads, 0, st>>>(N, K, ngroups, gstart, L_elbo, logOmega, Ntilde, zhat,
+                                                                    Nj_part, cnt, lb_part, blk0);
     launched++;
   }
   if (reduce) {
@@ -506,7 +527,8 @@ int launch_list_scan(int N, int K, int chunk_len, const int *cnt, int *offs, int
 int launch_list_fill(int N, int K, int chunk_len, int nchunks, const double *zhat, const double *Ntilde,
                      const int *offs, const int *seg_start, const int *chunk_start, PairItem *items, int2 *chunks,
                      cudaStream_t st) {
-  k_list_fill<<<zhat_blocks(N), kZThreads, 0, st>>>(N, K, zhat, Ntilde, offs, seg_start, items);
+  const int nb = zhat_blocks(N);
+  k_list_fill<<<dim3(nb, spread(nb, (K + kJT - 1) / kJT)), kZThreads, 0, st>>>(N, K, zhat, Ntilde, offs, seg_start, items);
   if (nchunks > 0) k_chunks<<<(nchunks + 255) / 256, 256, 0, st>>>(K, chunk_len, seg_start, chunk_start, chunks);
   return nchunks > 0 ? 2 : 1;
 }

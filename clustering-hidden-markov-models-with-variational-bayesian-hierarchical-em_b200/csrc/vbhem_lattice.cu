@@ -50,7 +50,7 @@ struct Frag { double x0, x1; };
 // lookup.  The first-pass kernel therefore keeps one copy per bank group -- 16 interleaved copies of
 // the 8-byte exp table, 8 of the 16-byte log table -- and lane l reads copy l % 16 (l % 8): every
 // lookup is conflict-free (LDS.64 is served per half-warp, LDS.128 per quarter-warp).  The second-pass
-// kernel needs its shared memory for the stored lattice and keeps single copies.
+// kernel needs its shared memory for the stored lattice and keeps four copies of each.
 __device__ const double g_log_table[2 * VBHEM_LOG_BINS] = VBHEM_LOG_TABLE;
 __device__ const double g_exp_table[VBHEM_EXP_BINS] = VBHEM_EXP_TABLE;
 template <int LS, int ES>
@@ -73,7 +73,14 @@ struct Tables {
   }
 };
 using TabFirst = Tables<8, 16>;   // first pass: bank-replicated
-using TabFull = Tables<1, 1>;     // second pass: compact
+#ifndef VB_FULL_LS
+#define VB_FULL_LS 4
+#endif
+#ifndef VB_FULL_ES
+#define VB_FULL_ES 4
+#endif
+constexpr int kFullLS = VB_FULL_LS, kFullES = VB_FULL_ES;
+using TabFull = Tables<kFullLS, kFullES>;   // second pass: the stored lattice needs the space, 24 KB of tables
 
 __device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -298,14 +305,14 @@ __device__ __forceinline__ void bwd_step(const Frag &E, Frag &G, const Frag &exp
                                          tab_t ltab, tab_t etab, double *sBm, double *sInvS,
                                          unsigned &rng, int g, int q) {
   int e0, e1;
-  const double m0 = exp_split(G.x0, etab, e0), m1 = exp_split(G.x1, etab, e1);
+  const double m0 = exp_split<kFullES>(G.x0, etab, e0), m1 = exp_split<kFullES>(G.x1, etab, e1);
   const int c = row_shift(e0, e1);                             // shift of row beta = g
   rng = max(rng, shift_excess(c));
   const Frag Bm{exp_scale(m0, e0 - c), exp_scale(m1, e1 - c)};
   const Frag ST = mma_nt(expA, Bm);                            // S^T(rho = g | beta = 2q+e)
   const int cb0 = __shfl_sync(0xffffffffu, c - 1023, (2 * q) * 4);
   const int cb1 = __shfl_sync(0xffffffffu, c - 1023, (2 * q + 1) * 4);
-  const Frag ell{log_shift_biased(ST.x0, ltab, cb0), log_shift_biased(ST.x1, ltab, cb1)};   // lse^T(rho | beta)
+  const Frag ell{log_shift_biased<kFullLS>(ST.x0, ltab, cb0), log_shift_biased<kFullLS>(ST.x1, ltab, cb1)};   // lse^T(rho | beta)
   G = E;
   mma_nt_acc(G, Ab, ell);                                      // G(beta' = g | rho = 2q+e)
   if (STORE) {
@@ -639,7 +646,7 @@ __device__ __forceinline__ bool pair_full(const BaseView &B, int i, const BaseCo
     bwd_step<true>(E, G, c.expA, b.Ab, ltab, etab, s, s + kTile, rng, g, q);
   }
   Frag nu1;
-  Lout = terminate<1, 1>(G, c.expPi, b.prior, ltab, etab, q, nu1, rng);
+  Lout = terminate<kFullLS, kFullES>(G, c.expPi, b.prior, ltab, etab, q, nu1, rng);
   if (!__all_sync(0xffffffffu, (rng <= kShiftBound) & !bad)) return false;
 
   // nu_1 (beta|sigma) -> nuT (sigma = g | gamma = 2q+e)
@@ -699,7 +706,7 @@ k_lattice_full(BaseView B, CentreView C, int T, PairWork W, PairOut O, Fallback 
   constexpr int DD = BaseConst<D, FULL>::DD;
   const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
   const int warp = threadIdx.x >> 5;
-  const tab_t ltab = TabFull::log_view(smem, 0), etab = TabFull::exp_view(smem, 0);
+  const tab_t ltab = TabFull::log_view(smem, lane), etab = TabFull::exp_view(smem, lane);
   TabFull::load(smem);
   __syncthreads();
   double *sm = smem + TabFull::kDoubles + (size_t)warp * ((size_t)2 * kTile * (T - 1) + kTile);
