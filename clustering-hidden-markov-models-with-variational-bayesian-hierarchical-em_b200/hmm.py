@@ -1,0 +1,223 @@
+"""Host mirror of the toolbox's VB-HMM learning entry points around the GPU forward-backward pass.
+
+``vbhmm_em(data, K, ini)`` follows /root/reference/src/hmm/vbhmm_em.m:1-496 and ``vbhmm_learn(data, K, vbopt)``
+the selection logic of /root/reference/src/hmm/vbhmm_learn.m:360-620 (candidate state counts, random restarts,
+best lower bound), with the reference's option names (``alpha0``, ``epsilon0``, ``mu0``, ``beta0``, ``W0``, ``v0``,
+``maxIter``, ``minDiff``, ``initmode``, ``initgmm``, ``inithmm``, ``numTrials``, ``seed``).
+
+Every EM iteration is ONE call of the fused pass ``vbhmm_fb_stats`` (csrc/vbhmm_fb.cu): forward-backward, the sums
+vbhmm_em.m:158-246 takes from it and the two sequence-sized lower-bound terms (vbhmm_em_lb.m:214,217) are reduced on
+the GPU and 536 bytes come back; what stays on the host is O(K * dim^2): the M-step (vbhmm_em.m:353-414) and the
+lower bound (vbhmm_em_lb.m:74-258).  The observations are packed into HBM once per run (``SequenceSet``).
+
+The learned model is a dict with the reference's field names (vbhmm_em.m:426-491), arrays in natural layout:
+``prior[K]``, ``trans[K(from),K(to)]``, ``mean[K,dim]``, ``cov[K,dim,dim]`` (the reference's ``pdf{k}.mean/.cov``
+stacked), ``LL``, ``M``, ``N1``, ``N``, ``varpar = {alpha, epsilon, beta, v, m, W}``, plus ``iter`` and ``LLs``.  It is
+what ``h3m.hmms_to_h3m_hem`` takes, so ``vbhmm_learn`` -> ``hmms_to_h3m_hem`` -> ``vbhem_h3m_c_step_fc`` is the
+toolbox's pipeline (learn one HMM per subject, then cluster the HMMs).
+
+Not mirrored: groups, ``fix_cov`` / ``fix_clusters``, hyper-parameter learning (``learn_hyps``, vbhmm_em_hyp.m) and
+its derivatives; ``gamma`` (the per-sequence responsibilities, vbhmm_em.m:463-466) is not materialised -- the unfused
+pass ``fb.vbhmm_fb(data, hmm['varpar'])`` returns it.  There is no CPU implementation behind this module.
+"""
+from __future__ import annotations
+
+import numpy as np
+from scipy.special import gammaln
+
+from . import fb as _fb
+
+DEFAULT_VBOPT = dict(alpha0=0.1, epsilon0=0.1, mu0=(256.0, 192.0), beta0=1.0, W0=0.005, v0=5.0, maxIter=100,
+                     minDiff=1e-5, initmode="random", numTrials=50, seed=None, verbose=0)   # vbhmm_learn.m:232-300
+
+
+def _W0inv(ini: dict, dim: int) -> tuple[np.ndarray, bool]:
+    w = np.atleast_1d(np.asarray(ini["W0"], float)).ravel()
+    if w.size == 1:
+        return np.eye(dim) / w[0], True                                    # vbhmm_init.m:136-140,152
+    if w.size != dim:
+        raise ValueError(f"vbopt.W0 should have dimension D={dim} for diagonal matrix")
+    return np.diag(1.0 / w), False                                         # :141-148
+
+
+def _fit_gmm(X: np.ndarray, K: int, seed) -> dict:
+    """Stand-in for ``gmdistribution.fit(data, K, 'Options', struct('TolFun', 1e-5), 'Start', 'randSample')``
+    (vbhmm_init.m:60-61; Statistics Toolbox, not reproducible outside MATLAB): scikit-learn's EM from random points."""
+    import warnings
+    from sklearn.exceptions import ConvergenceWarning
+    from sklearn.mixture import GaussianMixture
+    with warnings.catch_warnings():   # warning('off', 'stats:gmdistribution:FailedToConverge'), vbhmm_init.m:47
+        warnings.simplefilter("ignore", ConvergenceWarning)
+        g = GaussianMixture(n_components=K, covariance_type="full", tol=1e-5, init_params="random_from_data",
+                            random_state=seed, reg_covar=1e-10).fit(X)
+    return dict(prior=g.weights_, mean=g.means_, cov=g.covariances_)
+
+
+def vbhmm_init(data, K: int, ini: dict) -> dict:
+    """vbhmm_init.m:1-216 -> initial variational parameters ``alpha, epsilon, beta, v, m[K,dim], W[K,dim,dim]``.
+    initmode ``'initgmm'`` (ini['initgmm'] = dict(prior[K], mean[K,dim], cov[K,dim,dim])), ``'inithmm'``
+    (ini['inithmm']['varpar']) or ``'random'`` (a GMM fitted from random points; K = 1 and N <= K as at :25-41).
+    ``data``: the sequences, or ``(N, dim)`` = number of observations and their dimension when the mode does not
+    look at them ('initgmm', 'inithmm')."""
+    mode = ini.get("initmode", "random")
+    if isinstance(data, tuple):
+        (N, dim), X = data, None
+        if mode == "random":
+            raise ValueError("initmode 'random' needs the observations")
+    else:
+        X = np.concatenate([np.asarray(x, float).reshape(len(x), -1) for x in data if len(x)])
+        N, dim = X.shape
+    if len(np.atleast_1d(ini["mu0"])) != dim:
+        raise ValueError(f"vbopt.mu0 should have dimension D={dim}")
+    if ini["v0"] <= dim - 1:
+        raise ValueError("v0 not large enough")
+    if mode == "inithmm":
+        vp = ini["inithmm"]["varpar"]
+        return {k: np.array(vp[k], float) for k in ("alpha", "epsilon", "beta", "v", "m", "W")}
+    if mode == "initgmm":
+        g = ini["initgmm"]
+        gmm = dict(prior=np.asarray(g["prior"], float).ravel(), mean=np.asarray(g["mean"], float).reshape(-1, dim),
+                   cov=np.asarray(g["cov"], float).reshape(-1, dim, dim))
+        if gmm["mean"].shape[0] != K:
+            raise ValueError("bad initgmm dimensions -- possibly mean is not a row vector")
+    elif mode == "random":
+        if K == 1:
+            gmm = dict(prior=np.ones(1), mean=X.mean(0, keepdims=True), cov=np.atleast_2d(np.cov(X.T))[None])
+        elif N <= K:
+            t = np.r_[np.ones(N), 1e-6 * np.ones(K - N)]
+            gmm = dict(prior=t / t.sum(), mean=np.r_[X, np.zeros((K - N, dim))],
+                       cov=np.tile(np.eye(dim) * X.var(0, ddof=1).mean(), (K, 1, 1)))
+        else:
+            gmm = _fit_gmm(X, K, ini.get("seed"))
+    else:
+        raise ValueError("bad initmode")
+    m0 = np.asarray(ini["mu0"], float).reshape(dim)
+    W0inv, _ = _W0inv(ini, dim)
+    Nk, Nk2 = N * gmm["prior"], np.full(K, N / K)                          # :166-167
+    beta = ini["beta0"] + Nk
+    W = np.zeros((K, dim, dim))
+    for k in range(K):                                                     # :197-201
+        d3 = gmm["mean"][k] - m0
+        W[k] = np.linalg.inv(W0inv + Nk[k] * gmm["cov"][k] + ini["beta0"] * Nk[k] / (ini["beta0"] + Nk[k]) * np.outer(d3, d3))
+    return dict(alpha=ini["alpha0"] + Nk2, epsilon=np.tile(ini["epsilon0"] + Nk2, (K, 1)), beta=beta,
+                v=ini["v0"] + Nk + 1, m=(ini["beta0"] * m0[None] + Nk[:, None] * gmm["mean"]) / beta[:, None], W=W)
+
+
+def vbhmm_mstep(st: dict, ini: dict) -> dict:
+    """vbhmm_em.m:353-389 from the sums of one fused pass (``fb.fb_stats``)."""
+    K, dim = st["xbar"].shape
+    m0 = np.asarray(ini["mu0"], float).reshape(dim)
+    W0inv, _ = _W0inv(ini, dim)
+    Nk, b0 = st["Nk"], float(ini["beta0"])
+    beta = b0 + Nk
+    dx = st["xbar"] - m0[None]
+    Winv = W0inv[None] + Nk[:, None, None] * st["S"] + (b0 * Nk / (b0 + Nk))[:, None, None] * dx[:, :, None] * dx[:, None, :]
+    W = np.linalg.inv(Winv)
+    return dict(alpha=ini["alpha0"] + st["Nk1"], epsilon=ini["epsilon0"] + st["M"], beta=beta, v=ini["v0"] + Nk + 1,
+                m=(b0 * m0[None] + Nk[:, None] * st["xbar"]) / beta[:, None], W=(W + np.transpose(W, (0, 2, 1))) / 2)
+
+
+def vbhmm_em_lb(st: dict, vp: dict, ini: dict) -> tuple[float, dict]:
+    """vbhmm_em_lb.m:74-258 with the sequence-sized terms taken from the fused pass: Lt2a = sum_k Nk1(k) logPiTilde(k)
+    (:143-146), Lt2b = sum M .* logATilde (:162), Lt63, Lt64 (:214,217).  ``vp`` = the parameters the pass ran with."""
+    v, W, eps, al, m, beta = (np.asarray(vp[k], float) for k in ("v", "W", "epsilon", "alpha", "m", "beta"))
+    K, dim = m.shape
+    a0, e0, b0, v0 = (float(ini[k]) for k in ("alpha0", "epsilon0", "beta0", "v0"))
+    m0 = np.asarray(ini["mu0"], float).reshape(dim)
+    W0inv, iid = _W0inv(ini, dim)
+    logdetW0inv = dim * np.log(W0inv[0, 0]) if iid else np.log(np.diag(W0inv)).sum()
+    lLT, logPi, logA = st["logLambdaTilde"], st["logPiTilde"], st["logATilde"]
+    half = 0.5 * (1 - np.arange(1, dim + 1))
+    lnB = lambda vv, logdetW: -(vv / 2) * logdetW - (vv * dim / 2) * np.log(2) - (dim * (dim - 1) / 4) * np.log(np.pi) \
+        - gammaln(0.5 * vv + half).sum()
+    logdetW = np.linalg.slogdet(W)[1]
+    H = sum(-lnB(v[k], logdetW[k]) - 0.5 * (v[k] - dim - 1) * lLT[k] + 0.5 * v[k] * dim for k in range(K))
+    trSW = np.einsum("kij,kji->k", st["S"], W)
+    dx, dm = st["xbar"] - m, m - m0[None]
+    xWx = np.einsum("ki,kij,kj->k", dx, W, dx)
+    mWm = np.einsum("ki,kij,kj->k", dm, W, dm)
+    trW0W = np.einsum("ij,kji->k", W0inv, W)
+    Nk = st["Nk"]
+    T = {}
+    T["Lt1"] = 0.5 * (Nk * (lLT - dim / beta - v * trSW - v * xWx - dim * np.log(2 * np.pi))).sum()
+    Lt2a, Lt2b = (st["Nk1"] * logPi).sum(), (st["M"] * logA).sum()
+    T["Lt2"] = Lt2a + Lt2b
+    T["Lt3"] = gammaln(K * a0) - K * gammaln(a0) + (a0 - 1) * logPi.sum()
+    T["Lt4"] = K * (gammaln(K * e0) - K * gammaln(e0)) + (e0 - 1) * logA.sum()
+    T["Lt5"] = 0.5 * (dim * np.log(b0 / (2 * np.pi)) + lLT - dim * b0 / beta - b0 * v * mWm).sum() \
+        + K * lnB(v0, -logdetW0inv) + 0.5 * (v0 - dim - 1) * lLT.sum() - 0.5 * (v * trW0W).sum()
+    T["Lt6"] = Lt2a + Lt2b + st["Lt63"] - st["Lt64"]
+    T["Lt7"] = ((al - 1) * logPi).sum() + gammaln(al.sum()) - gammaln(al).sum() \
+        + (((eps - 1) * logA).sum(1) + gammaln(eps.sum(1)) - gammaln(eps).sum(1)).sum()
+    T["Lt8"] = 0.5 * (lLT + dim * np.log(beta / (2 * np.pi))).sum() - 0.5 * dim * K - H
+    LB = T["Lt1"] + T["Lt2"] + T["Lt3"] + T["Lt4"] + T["Lt5"] - T["Lt6"] - T["Lt7"] - T["Lt8"]
+    return float(LB), T
+
+
+def vbhmm_em(data, K: int, ini: dict) -> dict:
+    """[hmm, L] = vbhmm_em(data, K, ini)  (vbhmm_em.m:1).  ``data``: list of [T_n, dim] arrays or a ``SequenceSet``
+    (then ``ini['initmode']`` must be 'initgmm' or 'inithmm', which need no look at the observations).
+    The per-sequence responsibilities (``hmm.gamma``, vbhmm_em.m:463-466) are not materialised: call
+    ``fb.vbhmm_fb(data, hmm['varpar'])`` for them."""
+    own = not isinstance(data, _fb.SequenceSet)
+    vp = vbhmm_init(data if own else (int(data.T.sum()), data.dim), K, ini)
+    seqs = _fb.SequenceSet(data) if own else data
+    try:
+        max_iter, min_diff = int(ini.get("maxIter", 100)), float(ini.get("minDiff", 1e-5))
+        L = lastL = -np.finfo(float).max
+        LLs, unstable, it, st = [], False, 0, None
+        for it in range(1, max_iter + 1):
+            st = _fb.fb_stats(seqs, vp)                                    # E-step + sums (GPU)
+            if it > 1:
+                lastL = L
+            L, _ = vbhmm_em_lb(st, vp, ini)
+            do_break = (it > 1 and abs((L - lastL) / lastL) <= min_diff) or it == max_iter       # vbhmm_em.m:293-316
+            if np.isnan(L):                                                # :320-330
+                do_break, unstable, L = True, True, -np.inf
+            LLs.append(L)
+            if do_break and unstable:
+                break
+            vp = vbhmm_mstep(st, ini)                                      # also after the breaking pass (:411-414)
+            if do_break:
+                break
+        dim = vp["m"].shape[1]
+        Ci = np.linalg.inv(vp["W"]) / np.where(vp["v"] > dim + 1, vp["v"] - dim - 1, vp["v"])[:, None, None]   # :391-404
+        rs = vp["epsilon"].sum(1, keepdims=True)
+        hmm = dict(prior=vp["alpha"] / vp["alpha"].sum(), trans=vp["epsilon"] / np.where(rs == 0, 1.0, rs),
+                   mean=vp["m"].copy(), cov=(Ci + np.transpose(Ci, (0, 2, 1))) / 2, LL=L, M=st["M"], N1=st["Nk1"],
+                   N=st["Nk"], varpar=vp, iter=it, LLs=np.array(LLs), unstable=unstable, K=K)
+        return hmm
+    finally:
+        if own:
+            seqs.close()
+
+
+def vbhmm_learn(data: list, K, vbopt: dict | None = None) -> dict:
+    """[hmm, L] = vbhmm_learn(data, K, vbopt)  (vbhmm_learn.m:1): for every candidate K run ``numTrials`` EM runs from
+    random initialisations (seed + trial), keep the best lower bound (:465-557); over the candidates keep the best
+    ``LL + gammaln(K + 1)`` (:387-405).  The sequences are packed into HBM once for all runs."""
+    opt = dict(DEFAULT_VBOPT)
+    opt.update(vbopt or {})
+    Ks = [int(k) for k in np.atleast_1d(K)]
+    X = np.concatenate([np.asarray(x, float).reshape(len(x), -1) for x in data if len(x)])
+    best_all, model_LL, per_k = None, [], []
+    with _fb.SequenceSet(data) as seqs:
+        for k in Ks:
+            best = None
+            trials = 1 if opt["initmode"] != "random" else int(opt["numTrials"])
+            for t in range(trials):
+                ini = dict(opt)
+                if opt["initmode"] == "random":
+                    seed = None if opt.get("seed") is None else int(opt["seed"]) + t
+                    ini.update(initmode="inithmm",
+                               inithmm=dict(varpar=vbhmm_init([X], k, dict(opt, initmode="random", seed=seed))))
+                h = vbhmm_em(seqs, k, ini)
+                if best is None or h["LL"] > best["LL"]:
+                    best = h
+            per_k.append(best)
+            model_LL.append(best["LL"] + gammaln(k + 1))
+            if best_all is None or model_LL[-1] > best_all[0]:
+                best_all = (model_LL[-1], best)
+    out = dict(best_all[1])
+    out.update(model_LL=np.array(model_LL), model_k=np.array(Ks), model_all=per_k, L=best_all[0])
+    return out

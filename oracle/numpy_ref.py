@@ -346,3 +346,148 @@ def vbhmm_em_stats(data: list, fbstats: dict) -> dict:
         S[k] = np.einsum("nt,nti,ntj->ij", gam[:, :, k], d1, d1) / Nk[k]
     return dict(Nk1=Nk1, Nk=Nk, M=M, xbar=xbar, S=S, Lt63=float((gam * fbstats["logrho_Saved"]).sum()),
                 Lt64=float(fbstats["phi_norm"].sum()))
+
+
+# ---------------------------------------------------------------------------- VB-HMM learning loop
+# Restatement of /root/reference/src/hmm/vbhmm_init.m, vbhmm_em.m and vbhmm_em_lb.m (no groups, no
+# derivatives, no fix_cov / fix_clusters).  Parity status: the forward-backward part is pinned on the
+# reference's own C (oracle/_ref/libvbhmm_fb_ref.so); M-step and lower bound exist in MATLAB only, so
+# this restatement is unpinned beyond the MATLAB builtins' stand-ins (scipy psi / gammaln, numpy inv / det).
+
+def vbhmm_init_from_gmm(gmm: dict, Ntot: int, ini: dict) -> dict:
+    """vbhmm_init.m:128-200 for initmode 'initgmm' (or the GMM any other mode produced).
+    gmm: prior[K], mean[K,dim], cov[K,dim,dim]; Ntot = total number of observations (vbhmm_init.m:19-20).
+    Returns the variational parameters alpha, epsilon[from,to], beta, v, m[K,dim], W[K,dim,dim]."""
+    pc = np.asarray(gmm["prior"], float)
+    mu = np.asarray(gmm["mean"], float)
+    Sg = np.asarray(gmm["cov"], float)
+    K, dim = mu.shape
+    m0 = np.asarray(ini["mu0"], float).reshape(dim)
+    W0 = np.asarray(ini["W0"], float).ravel()
+    W0inv = np.linalg.inv(np.eye(dim) * W0[0] if W0.size == 1 else np.diag(W0))        # :136-152
+    Nk = Ntot * pc                                                                      # :166
+    Nk2 = Ntot * np.full(K, 1.0 / K)                                                    # :167
+    alpha = ini["alpha0"] + Nk2                                                         # :189
+    epsilon = np.tile(ini["epsilon0"] + Nk2, (K, 1))                                    # :190-192
+    beta = ini["beta0"] + Nk                                                            # :193
+    v = ini["v0"] + Nk + 1                                                              # :194
+    m = (ini["beta0"] * m0[None] + Nk[:, None] * mu) / beta[:, None]                    # :195
+    W = np.zeros((K, dim, dim))
+    for k in range(K):                                                                  # :197-201
+        mult1 = ini["beta0"] * Nk[k] / (ini["beta0"] + Nk[k])
+        d3 = mu[k] - m0
+        W[k] = np.linalg.inv(W0inv + Nk[k] * Sg[k] + mult1 * np.outer(d3, d3))
+    return dict(alpha=alpha, epsilon=epsilon, beta=beta, v=v, m=m, W=W)
+
+
+def vbhmm_em_lb(st: dict, varpar: dict, fbstats: dict, ini: dict, N: int) -> float:
+    """vbhmm_em_lb.m:74-258 (value only).  st: Nk, M, xbar, S (= t1_S) of vbhmm_em_stats; varpar: the parameters
+    the E-step ran with; fbstats: full outputs of vbhmm_fb plus logLambdaTilde / logPiTilde / logATilde."""
+    from scipy.special import gammaln
+    v, W, eps, al, m, beta = (np.asarray(varpar[k], float) for k in ("v", "W", "epsilon", "alpha", "m", "beta"))
+    K, dim = m.shape
+    a0, e0, b0, v0 = ini["alpha0"], ini["epsilon0"], ini["beta0"], ini["v0"]
+    m0 = np.asarray(ini["mu0"], float).reshape(dim)
+    W0 = np.asarray(ini["W0"], float).ravel()
+    W0inv = np.linalg.inv(np.eye(dim) * W0[0] if W0.size == 1 else np.diag(W0))
+    logdetW0inv = dim * np.log(W0inv[0, 0]) if W0.size == 1 else np.log(np.diag(W0inv)).sum()      # :75-82
+    lLT, logPi, logA = fbstats["logLambdaTilde"], fbstats["logPiTilde"], fbstats["logATilde"]
+    ii = np.arange(1, dim + 1)
+    logCalpha0 = gammaln(K * a0) - K * gammaln(a0)                                                  # :84
+    logCeps0 = np.full(K, gammaln(K * e0) - K * gammaln(e0))                                        # :85-87
+    logB0 = (v0 / 2) * logdetW0inv - (v0 * dim / 2) * np.log(2) - (dim * (dim - 1) / 4) * np.log(np.pi) \
+        - gammaln(0.5 * (v0 + 1 - ii)).sum()                                                        # :88-89
+    logCalpha = gammaln(al.sum()) - gammaln(al).sum()                                               # :92
+    logCeps = np.array([gammaln(eps[k].sum()) - gammaln(eps[k]).sum() for k in range(K)])           # :93-95
+    H = 0.0
+    trSW, xWx, mWm, trW0W = np.zeros(K), np.zeros(K), np.zeros(K), np.zeros(K)
+    for k in range(K):                                                                              # :107-119
+        logBk = -(v[k] / 2) * np.log(np.linalg.det(W[k])) - (v[k] * dim / 2) * np.log(2) \
+            - (dim * (dim - 1) / 4) * np.log(np.pi) - gammaln(0.5 * (v[k] + 1 - ii)).sum()
+        H = H - logBk - 0.5 * (v[k] - dim - 1) * lLT[k] + 0.5 * v[k] * dim
+        trSW[k] = np.trace(st["S"][k] @ W[k])
+        d = st["xbar"][k] - m[k]
+        xWx[k] = d @ W[k] @ d
+        d = m[k] - m0
+        mWm[k] = d @ W[k] @ d
+        trW0W[k] = np.trace(W0inv @ W[k])
+    Nk, M = st["Nk"], st["M"]
+    Lt1 = 0.5 * (Nk * (lLT - dim / beta - v * trSW - v * xWx - dim * np.log(2 * np.pi))).sum()      # :124-125
+    gamma1 = fbstats["gamma_all"][:, 0, :]                                                          # :128  [N, K]
+    Lt2a = (gamma1 * logPi[None]).sum()                                                             # :143-146
+    Lt2b = (M * logA).sum()                                                                         # :162
+    Lt2 = Lt2a + Lt2b
+    Lt3 = logCalpha0 + (a0 - 1) * logPi.sum()                                                       # :176
+    Lt4 = (logCeps0 + (e0 - 1) * logA.sum(1)).sum()                                                 # :186-189
+    Lt51 = 0.5 * (dim * np.log(b0 / (2 * np.pi)) + lLT - dim * b0 / beta - b0 * v * mWm).sum()      # :201
+    Lt52 = K * logB0 + 0.5 * (v0 - dim - 1) * lLT.sum() - 0.5 * (v * trW0W).sum()                   # :202
+    Lt5 = Lt51 + Lt52
+    Lt63 = (fbstats["gamma_all"] * fbstats["logrho_Saved"]).sum()                                   # :214
+    Lt64 = fbstats["phi_norm"].sum()                                                                # :217
+    Lt6 = Lt2a + Lt2b + Lt63 - Lt64                                                                 # :221
+    Lt71 = ((al - 1) * logPi).sum() + logCalpha                                                     # :225
+    Lt72 = (((eps - 1) * logA).sum(1) + logCeps).sum()                                              # :235-238
+    Lt7 = Lt71 + Lt72
+    Lt8 = 0.5 * (lLT + dim * np.log(beta / (2 * np.pi))).sum() - 0.5 * dim * K - H                  # :253
+    return float(Lt1 + Lt2 + Lt3 + Lt4 + Lt5 - Lt6 - Lt7 - Lt8)                                     # :257
+
+
+def vbhmm_em(data: list, varpar0: dict, ini: dict, fb=None) -> dict:
+    """vbhmm_em.m:108-418 from given initial variational parameters (vbhmm_init.m's output): E-step, sums, lower
+    bound, convergence test |dL / L_last| <= minDiff from iteration 2 on, M-step (which still runs once after the
+    test fires, :411-414).  fb(data, par) -> fbstats defaults to the numpy forward-backward above.
+    Returns varpar (final), LL, LLs (per iteration), iter, prior, trans, pdf mean / cov (vbhmm_em.m:429-460)."""
+    fb = fb or vbhmm_fb
+    vp = {k: np.array(varpar0[k], float) for k in ("alpha", "epsilon", "beta", "v", "m", "W")}
+    K, dim = vp["m"].shape
+    N = len(data)
+    m0 = np.asarray(ini["mu0"], float).reshape(dim)
+    W0 = np.asarray(ini["W0"], float).ravel()
+    W0inv = np.linalg.inv(np.eye(dim) * W0[0] if W0.size == 1 else np.diag(W0))
+    L, lastL, LLs = -np.finfo(float).max, -np.finfo(float).max, []
+    it = 0
+    unstable = False
+    for it in range(1, int(ini["maxIter"]) + 1):
+        par = vbhmm_fb_prepass(vp)
+        fbs = fb(data, par)
+        fbs = dict(fbs, logLambdaTilde=par["logLambdaTilde"], logPiTilde=par["logPiTilde"], logATilde=par["logATilde"])
+        st = vbhmm_em_stats(data, fbs)
+        if it > 1:
+            lastL = L
+        L = vbhmm_em_lb(st, vp, fbs, ini, N)
+        LLs.append(L)
+        do_break = False
+        if it > 1 and abs((L - lastL) / lastL) <= ini["minDiff"]:                                   # :293-312
+            do_break = True
+        if it == int(ini["maxIter"]):
+            do_break = True
+        if np.isnan(L):                                                                             # :320-330
+            do_break, unstable, L = True, True, -np.inf
+            LLs[-1] = L
+        if do_break and unstable:
+            break
+        # M-step, vbhmm_em.m:353-400
+        vp["alpha"] = ini["alpha0"] + st["Nk1"]
+        vp["epsilon"] = ini["epsilon0"] + st["M"]
+        Nk = st["Nk"]
+        vp["beta"] = ini["beta0"] + Nk
+        vp["v"] = ini["v0"] + Nk + 1
+        vp["m"] = (ini["beta0"] * m0[None] + Nk[:, None] * st["xbar"]) / vp["beta"][:, None]
+        W = np.zeros((K, dim, dim))
+        for k in range(K):
+            mult1 = ini["beta0"] * Nk[k] / (ini["beta0"] + Nk[k])
+            d3 = st["xbar"][k] - m0
+            Wk = np.linalg.inv(W0inv + Nk[k] * st["S"][k] + mult1 * np.outer(d3, d3))
+            W[k] = (Wk + Wk.T) / 2
+        vp["W"] = W
+        if do_break:
+            break
+    C = np.zeros((K, dim, dim))
+    for k in range(K):                                                                              # :402-414
+        Ck = np.linalg.inv(vp["W"][k]) / (vp["v"][k] - dim - 1 if vp["v"][k] > dim + 1 else vp["v"][k])
+        C[k] = (Ck + Ck.T) / 2
+    prior = vp["alpha"] / vp["alpha"].sum()                                                         # :430-432
+    rs = vp["epsilon"].sum(1, keepdims=True)
+    trans = vp["epsilon"] / np.where(rs == 0, 1.0, rs)                                              # :434-439
+    return dict(varpar=vp, LL=L, LLs=np.array(LLs), iter=it, prior=prior, trans=trans, mean=vp["m"].copy(), cov=C,
+                M=st["M"], N1=st["Nk1"], N=st["Nk"], unstable=unstable)

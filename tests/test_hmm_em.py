@@ -1,0 +1,145 @@
+"""VB-HMM learning loop (vbhmm_em / vbhmm_learn mirrors in vbhem_b200/hmm.py) against the oracle's restatement of
+/root/reference/src/hmm/vbhmm_em.m + vbhmm_em_lb.m + vbhmm_init.m.
+
+CPU part: the host formulas (initialisation from a GMM, M-step, lower bound from the fused sums) against the
+oracle's literal restatement, which evaluates the lower bound from the full forward-backward outputs.
+GPU part: whole EM runs -- same number of iterations, same trace of lower bounds (rtol 1e-9), same final
+variational parameters (1e-7) as the oracle loop, whose forward-backward is the reference's own C when built."""
+import numpy as np
+import pytest
+
+import vbhem_b200  # noqa: F401
+from oracle import cref, numpy_ref as nr
+from vbhem_b200 import hmm as H
+
+INI = dict(alpha0=0.1, epsilon0=0.1, beta0=1.0, v0=5.0, mu0=[256.0, 192.0], W0=0.005, maxIter=60, minDiff=1e-6)
+
+
+def make_sequences(n=14, K=3, seed=4, tmin=4, tmax=18, dim=2):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    mus = rng.uniform([60, 50, 20][:dim], [450, 330, 200][:dim], size=(K, dim))
+    A = rng.dirichlet(np.ones(K), size=K) + 1.5 * np.eye(K)
+    A /= A.sum(1, keepdims=True)
+    data = []
+    for _ in range(n):
+        T = int(rng.integers(tmin, tmax + 1))
+        z = int(rng.integers(K))
+        x = np.zeros((T, dim))
+        for t in range(T):
+            x[t] = mus[z] + rng.normal(0, 14, dim)
+            z = int(rng.choice(K, p=A[z]))
+        data.append(x)
+    gmm = dict(prior=np.full(K, 1.0 / K), mean=mus + rng.normal(0, 8, (K, dim)), cov=np.tile(np.eye(dim) * 300.0, (K, 1, 1)))
+    return data, gmm
+
+
+def oracle_fb(data, par):
+    """The reference's own C forward-backward when built here, else its numpy restatement."""
+    if cref.have_fb_ref():
+        return cref.ref_vbhmm_fb(cref.pack_sequences(data), par)
+    return nr.vbhmm_fb(data, par)
+
+
+@pytest.mark.parametrize("K,dim,W0", [(3, 2, 0.005), (2, 2, [0.004, 0.008]), (4, 3, 0.01)])
+def test_host_formulas_match_oracle(K, dim, W0):
+    ini = dict(INI, W0=W0, mu0=[256.0, 192.0, 100.0][:dim])
+    data, gmm = make_sequences(K=K, dim=dim, seed=11 + K)
+    ntot = sum(len(x) for x in data)
+    vp_o = nr.vbhmm_init_from_gmm(gmm, ntot, ini)
+    vp_h = H.vbhmm_init(data, K, dict(ini, initmode="initgmm", initgmm=gmm))
+    vp_t = H.vbhmm_init((ntot, dim), K, dict(ini, initmode="initgmm", initgmm=gmm))
+    for k in vp_o:
+        np.testing.assert_allclose(vp_h[k], vp_o[k], rtol=1e-12, err_msg=k)
+        np.testing.assert_array_equal(vp_t[k], vp_h[k])
+    # one E-step by the oracle, then lower bound and M-step both ways
+    par = nr.vbhmm_fb_prepass(vp_o)
+    fbs = dict(nr.vbhmm_fb(data, par), logLambdaTilde=par["logLambdaTilde"], logPiTilde=par["logPiTilde"],
+               logATilde=par["logATilde"])
+    st = nr.vbhmm_em_stats(data, fbs)
+    want = nr.vbhmm_em_lb(st, vp_o, fbs, ini, len(data))
+    fused = dict(st, logLambdaTilde=par["logLambdaTilde"], logPiTilde=par["logPiTilde"], logATilde=par["logATilde"])
+    got, terms = H.vbhmm_em_lb(fused, vp_o, ini)
+    assert abs(got - want) <= 1e-10 * abs(want)
+    assert set(terms) == {f"Lt{i}" for i in range(1, 9)}
+    new = H.vbhmm_mstep(st, ini)
+    one = nr.vbhmm_em(data, vp_o, dict(ini, maxIter=1))["varpar"]      # maxIter = 1: E-step, break, M-step
+    for k in one:
+        np.testing.assert_allclose(new[k], one[k], rtol=1e-11, err_msg=k)
+
+
+def test_oracle_loop_lower_bound_increases():
+    """The bound rises from pass to pass; it is not strictly monotone at convergence because the reference's
+    Wishart update takes v = v0 + Nk + 1 (vbhmm_em.m:369, "BUG FIX (add 1)" at vbhmm_init.m:194), one more than the
+    maximiser of its own bound -- it prints "[LL decreased]" for that case (vbhmm_em.m:299-309).  Parity is with that."""
+    data, gmm = make_sequences(K=3, seed=21)
+    vp0 = nr.vbhmm_init_from_gmm(gmm, sum(len(x) for x in data), INI)
+    out = nr.vbhmm_em(data, vp0, INI)
+    assert out["iter"] >= 3 and not out["unstable"]
+    assert out["LLs"][1] > out["LLs"][0]
+    assert np.all(np.diff(out["LLs"]) > -1e-6 * np.abs(out["LLs"][:-1]))
+    np.testing.assert_allclose(out["trans"].sum(1), 1.0, rtol=1e-12)
+    np.testing.assert_allclose(out["prior"].sum(), 1.0, rtol=1e-12)
+
+
+def test_init_errors():
+    data, gmm = make_sequences(K=2)
+    with pytest.raises(ValueError, match="mu0"):
+        H.vbhmm_init(data, 2, dict(INI, mu0=[1.0], initmode="initgmm", initgmm=gmm))
+    with pytest.raises(ValueError, match="v0"):
+        H.vbhmm_init(data, 2, dict(INI, v0=1.0, initmode="initgmm", initgmm=gmm))
+    with pytest.raises(ValueError, match="initgmm"):
+        H.vbhmm_init(data, 3, dict(INI, initmode="initgmm", initgmm=gmm))
+    with pytest.raises(ValueError, match="initmode"):
+        H.vbhmm_init(data, 2, dict(INI, initmode="nope"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("K,dim,seed", [(3, 2, 4), (2, 2, 9), (4, 3, 5), (1, 2, 6)])
+def test_em_run_matches_oracle_loop(K, dim, seed):
+    ini = dict(INI, mu0=[256.0, 192.0, 100.0][:dim])
+    data, gmm = make_sequences(n=20, K=K, dim=dim, seed=seed)
+    vp0 = nr.vbhmm_init_from_gmm(gmm, sum(len(x) for x in data), ini)
+    want = nr.vbhmm_em(data, vp0, ini, fb=oracle_fb)
+    got = H.vbhmm_em(data, K, dict(ini, initmode="initgmm", initgmm=gmm))
+    assert got["iter"] == want["iter"] and got["unstable"] == want["unstable"]
+    np.testing.assert_allclose(got["LLs"], want["LLs"], rtol=1e-9)
+    for k in want["varpar"]:
+        np.testing.assert_allclose(got["varpar"][k], want["varpar"][k], rtol=1e-7, atol=1e-12, err_msg=k)
+    for k in ("prior", "trans", "mean", "cov", "M", "N1", "N"):
+        np.testing.assert_allclose(got[k], want[k], rtol=1e-7, atol=1e-12, err_msg=k)
+
+
+@pytest.mark.gpu
+def test_learn_then_cluster_recovers_the_two_groups():
+    """The toolbox's pipeline at the size of its synthetic experiment (Synthetic_experiment/exprmt1_demo.m: two
+    ground-truth HMMs, 20 subjects each): learn one HMM per subject on the GPU (vbhmm_learn), convert
+    (hmms_to_h3m_hem), cluster with VBHEM (K = 2) -- the known answer is the subjects' group (syn_evluate.m:19-22)."""
+    from vbhem_b200 import BaseSet, h3m, synth
+    rng = np.random.Generator(np.random.PCG64(1001))
+    truth = [dict(mu=np.array([[120.0, 100.0], [380.0, 280.0]]), A=np.array([[0.8, 0.2], [0.3, 0.7]])),
+             dict(mu=np.array([[130.0, 290.0], [370.0, 90.0]]), A=np.array([[0.3, 0.7], [0.7, 0.3]]))]
+    hmms, label = [], []
+    for s in range(16):
+        g = s % 2
+        data = []
+        for _ in range(12):
+            z, x = int(rng.integers(2)), np.zeros((10, 2))
+            for t in range(10):
+                x[t] = truth[g]["mu"][z] + rng.normal(0, 12, 2)
+                z = int(rng.choice(2, p=truth[g]["A"][z]))
+            data.append(x)
+        hmms.append(H.vbhmm_learn(data, [1, 2, 3], dict(numTrials=3, seed=100 + s)))
+        label.append(g)
+    assert all(h["K"] == 2 for h in hmms), [h["K"] for h in hmms]
+    base = h3m.hmms_to_h3m_hem(hmms)
+    opt = dict(synth.DEFAULT_OPT)
+    runs = []
+    with BaseSet(base) as bs:
+        for trial in range(8):                      # vbhem_h3m_c.m:28-76: several initialisations, best bound wins
+            hyp = synth.init_centres_baseem(base, 2, 2, seed=1001 + trial, opt=opt)
+            runs.append(h3m.vbhem_h3m_c_step_fc(hyp, bs, opt))
+        best = max(runs, key=lambda r: r["LL"])
+        z = bs.estep_hyp(best["hyp"], opt["tau"])["zhat"]
+    assign = z.argmax(1)
+    label = np.array(label)
+    assert (assign == label).all() or (assign == 1 - label).all(), (assign, [r["LL"] for r in runs])
