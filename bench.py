@@ -216,7 +216,7 @@ def main():
     # ---- CPU baseline first (before CUDA is initialised in this process), rank 0, N = 1 only
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu:
-        cpu = run_cpu_baseline(a.cpu_bases or 1024, K, S, d, tau, cores)
+        cpu = run_cpu_baseline(a.cpu_bases or 3072, K, S, d, tau, cores)   # ~12 s of CPU work per core
 
     import numpy as np
     import torch

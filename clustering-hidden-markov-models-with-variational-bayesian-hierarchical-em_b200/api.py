@@ -90,7 +90,7 @@ class BaseSet:
         out = (C.c_longlong * 8)()
         check(lib().vbhem_last_counters(self._h, out))
         return dict(launches=out[0], lattice_pairs=out[1], general_pairs=out[2], active_pairs=out[3], tiles=out[4],
-                    split_tiles=out[5])
+                    split_tiles=out[5], compactions=out[6])
 
     # -- Boundary-1 ---------------------------------------------------------
     def estep_pairs(self, cen: dict, tau: int, L_only: bool = False, packed: bool = False) -> dict:

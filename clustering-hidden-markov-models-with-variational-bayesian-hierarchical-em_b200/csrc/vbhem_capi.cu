@@ -917,6 +917,50 @@ HypPtrs carve_hyp(vbhem_base *h, int K, int r) {
   p.lambda = q;
   return p;
 }
+// The centre set of a device-resident EM run: shapes into h->em, hyper-parameters into HBM.  The prior stays.
+int em_upload_state(vbhem_base *h, int K, const int32_t *Sr, int maxSr, const int32_t *group, int ngroups,
+                    const double *alpha, const double *eta, const double *epsilon, const double *m, const double *W,
+                    const double *v, const double *lambda) {
+  auto &em = h->em;
+  const int d = h->B.d, dd = h->B.dd;
+  em.K = K; em.maxSr = maxSr; em.ngroups = ngroups;
+  if (Sr != em.Sr.data()) em.Sr.assign(Sr, Sr + K);
+  if (!group) em.group.clear();
+  else if (group != em.group.data()) em.group.assign(group, group + K);
+  const size_t nK = K, nr = (size_t)maxSr * K, nrr = (size_t)maxSr * maxSr * K;
+  CU(h->hyp_d.ensure(sizeof(double) * (nK + nr + nrr + dd * nr + nr + nr)));
+  CU(em.m.ensure(sizeof(double) * d * nr));
+  CU(em.lb.ensure(sizeof(double) * 12 * ngroups));
+  CU(em.stats.ensure(sizeof(double) * vbhem_stats_size(K, maxSr, d, h->B.covmode, ngroups)));
+  HypPtrs p = carve_hyp(h, K, maxSr);
+  CU(cudaMemcpyAsync(p.alpha, alpha, sizeof(double) * nK, cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(p.eta, eta, sizeof(double) * nr, cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(p.epsilon, epsilon, sizeof(double) * nrr, cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(p.W, W, sizeof(double) * dd * nr, cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(p.v, v, sizeof(double) * nr, cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(p.lambda, lambda, sizeof(double) * nr, cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(em.m.p, m, sizeof(double) * d * nr, cudaMemcpyHostToDevice, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  return VBHEM_OK;
+}
+
+// Host copy of a centre set's hyper-parameters, C-ABI layouts (one contiguous block per centre in every array).
+struct HypHost {
+  std::vector<double> alpha, eta, eps, m, W, v, lam;
+  void resize(int K, int r, int d, int dd) {
+    alpha.resize(K); eta.resize((size_t)r * K); eps.resize((size_t)r * r * K); m.resize((size_t)d * r * K);
+    W.resize((size_t)dd * r * K); v.resize((size_t)r * K); lam.resize((size_t)r * K);
+  }
+  // centre jd of this <- centre js of src
+  void copy_centre(int jd, const HypHost &src, int js, int r, int d, int dd) {
+    auto cp = [&](std::vector<double> &a, const std::vector<double> &b, size_t w) {
+      memcpy(a.data() + w * jd, b.data() + w * js, sizeof(double) * w);
+    };
+    cp(alpha, src.alpha, 1); cp(eta, src.eta, r); cp(eps, src.eps, (size_t)r * r); cp(m, src.m, (size_t)d * r);
+    cp(W, src.W, (size_t)dd * r); cp(v, src.v, r); cp(lam, src.lam, r);
+  }
+};
+
 CentreArgs em_args(vbhem_base *h, int tau) {
   CentreArgs a{};
   a.K = h->em.K; a.maxSr = h->em.maxSr; a.ngroups = h->em.ngroups; a.tau = tau;
@@ -935,36 +979,21 @@ int vbhem_em_begin(vbhem_base_t *h, int K, const int32_t *Sr, int maxSr, const i
   a.alpha = alpha; a.eta = eta; a.epsilon = epsilon; a.m = m; a.W = W; a.v = v; a.lambda = lambda; a.hyp = true;
   int rc = check_common(h, a, true);
   if (rc) return rc;
-  const int d = h->B.d, dd = h->B.dd;
+  const int d = h->B.d;
   if (!m0 || !W0 || (nW0 != 1 && nW0 != d))
     return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: m0[d] and W0[1 or d] are required");
   if (!(v0 > d - 1)) return fail(VBHEM_EINVAL, "v0 not large enough");   // vbhem_mstep_component.m:24-26
   CU(cudaSetDevice(h->device));
   auto &em = h->em;
-  em.K = K; em.maxSr = maxSr; em.ngroups = ngroups;
-  em.Sr.assign(Sr, Sr + K);
-  if (group) em.group.assign(group, group + K); else em.group.clear();
   em.alpha0 = alpha0; em.eta0 = eta0; em.epsilon0 = epsilon0; em.lambda0 = lambda0; em.v0 = v0;
-  const size_t nK = K, nr = (size_t)maxSr * K, nrr = (size_t)maxSr * maxSr * K;
-  CU(h->hyp_d.ensure(sizeof(double) * (nK + nr + nrr + dd * nr + nr + nr)));
-  CU(em.m.ensure(sizeof(double) * d * nr));
   CU(em.prior.ensure(sizeof(double) * 2 * d));
-  CU(em.lb.ensure(sizeof(double) * 12 * ngroups));
-  CU(em.stats.ensure(sizeof(double) * vbhem_stats_size(K, maxSr, d, h->B.covmode, ngroups)));
   if (!em.h_lb) CU(cudaMallocHost(&em.h_lb, sizeof(double) * 12 * 4096));
   if (ngroups > 4096) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: at most 4096 groups in a device EM run");
-  HypPtrs p = carve_hyp(h, K, maxSr);
-  CU(cudaMemcpyAsync(p.alpha, alpha, sizeof(double) * nK, cudaMemcpyHostToDevice, h->st));
-  CU(cudaMemcpyAsync(p.eta, eta, sizeof(double) * nr, cudaMemcpyHostToDevice, h->st));
-  CU(cudaMemcpyAsync(p.epsilon, epsilon, sizeof(double) * nrr, cudaMemcpyHostToDevice, h->st));
-  CU(cudaMemcpyAsync(p.W, W, sizeof(double) * dd * nr, cudaMemcpyHostToDevice, h->st));
-  CU(cudaMemcpyAsync(p.v, v, sizeof(double) * nr, cudaMemcpyHostToDevice, h->st));
-  CU(cudaMemcpyAsync(p.lambda, lambda, sizeof(double) * nr, cudaMemcpyHostToDevice, h->st));
-  CU(cudaMemcpyAsync(em.m.p, m, sizeof(double) * d * nr, cudaMemcpyHostToDevice, h->st));
   std::vector<double> pr(2 * d);
   for (int q = 0; q < d; q++) { pr[q] = m0[q]; pr[d + q] = 1.0 / W0[nW0 == 1 ? 0 : q]; }
   CU(cudaMemcpyAsync(em.prior.p, pr.data(), sizeof(double) * 2 * d, cudaMemcpyHostToDevice, h->st));
-  CU(cudaStreamSynchronize(h->st));
+  rc = em_upload_state(h, K, Sr, maxSr, group, ngroups, alpha, eta, epsilon, m, W, v, lambda);   // synchronises
+  if (rc) return rc;
   em.active = true;
   return VBHEM_OK;
 }
@@ -1102,41 +1131,105 @@ int vbhem_em_run(vbhem_base_t *h, int tau, int max_iter, double min_diff, double
 
 // The same loop for several H3Ms batched in one handle (soft-max groups of vbhem_em_begin): every group
 // follows the control flow of vbhem_h3m_c_step_fc.m:311-354 on its own; a group that has stopped keeps its
-// hyper-parameters (masked M-step) while the others go on.  LogLs is [ngroups][ld], iters / unstable [ngroups].
+// hyper-parameters (masked M-step) while the others go on.  Once a quarter of the centres in the handle belong
+// to stopped groups the centre set is compacted to the running groups (the stopped ones wait in a host copy), so
+// the E-step's cost follows the work that is left; at the end the handle holds all groups again, in their
+// original order.  LogLs is [ngroups][ld], iters / unstable [ngroups].
 int vbhem_em_run_groups(vbhem_base_t *h, int tau, int max_iter, double min_diff, double *LogLs, int ld, int *iters,
                         int *unstable) {
   if (!h || !h->em.active) return fail(VBHEM_EINVAL, "vbhem_em_begin has not been called on this handle");
   if (!LogLs || !iters || ld < max_iter + 2) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: LogLs[ngroups][>= max_iter + 2], iters required");
-  const int G = h->em.ngroups;
+  auto &em = h->em;
+  const int G = em.ngroups, K0 = em.K, r = em.maxSr, d = h->B.d, dd = h->B.dd;
+  const std::vector<int32_t> Sr0 = em.Sr;
+  std::vector<int32_t> grp0 = em.group;
+  if (grp0.empty()) grp0.assign(K0, 0);
   std::vector<double> lb(12 * (size_t)G), lastL(G, -1.79769313486231570e308);
   std::vector<int> it(G, 0), n(G, 0), bad(G, 0);
-  std::vector<unsigned char> done(G, 0), skip(G, 0);
+  std::vector<unsigned char> done(G, 0), skip(G, 0), stop(G, 0);
+  std::vector<int> cur_groups(G), cmap(K0);          // original group / centre of every current one
+  for (int g = 0; g < G; g++) cur_groups[g] = g;
+  for (int j = 0; j < K0; j++) cmap[j] = j;
+  HypHost full, cur;
+  bool compacted = false;
+  int ncompact = 0;
+  // current (possibly compacted) device state -> `full`, at the centres' original positions
+  auto save_current = [&]() -> int {
+    const int Kc = (int)cmap.size();
+    cur.resize(Kc, r, d, dd);
+    int rc = vbhem_em_fetch(h, cur.alpha.data(), cur.eta.data(), cur.eps.data(), cur.m.data(), cur.W.data(),
+                            cur.v.data(), cur.lam.data());
+    if (rc) return rc;
+    if (full.alpha.empty()) full.resize(K0, r, d, dd);
+    for (int jc = 0; jc < Kc; jc++) full.copy_centre(cmap[jc], cur, jc, r, d, dd);
+    return VBHEM_OK;
+  };
   int left = G;
   while (left > 0) {
+    const int Gc = (int)cur_groups.size();
     int rc = vbhem_em_estep(h, tau, nullptr);
     if (rc) return rc;
     rc = vbhem_em_lower_bound(h, nullptr, lb.data());
     if (rc) return rc;
-    std::vector<unsigned char> stop(G, 0);
-    for (int g = 0; g < G; g++) {
-      skip[g] = done[g];
+    for (int gc = 0; gc < Gc; gc++) {
+      const int g = cur_groups[gc];
+      stop[gc] = 0;
+      skip[gc] = done[g];
       if (done[g]) continue;
-      double L = lb[12 * (size_t)g + 10];
+      double L = lb[12 * (size_t)gc + 10];
       bool do_break = false;
       if (it[g] > 1 && fabs((L - lastL[g]) / lastL[g]) <= min_diff) do_break = true;
       if (it[g] == max_iter) do_break = true;
       if (L != L) { do_break = true; bad[g] = 1; L = -INFINITY; }
       LogLs[(size_t)ld * g + n[g]++] = L;
-      if (do_break && bad[g]) { skip[g] = 1; stop[g] = 1; continue; }   // keep the last stable hyper-parameters
+      if (do_break && bad[g]) { skip[gc] = 1; stop[gc] = 1; continue; }   // keep the last stable hyper-parameters
       it[g]++;
       lastL[g] = L;
-      if (do_break) stop[g] = 1;                                          // the M-step still runs once more
+      if (do_break) stop[gc] = 1;                                          // the M-step still runs once more
     }
     rc = em_mstep_masked(h, nullptr, skip.data());
     if (rc) return rc;
-    for (int g = 0; g < G; g++)
-      if (stop[g] && !done[g]) { done[g] = 1; left--; }
+    for (int gc = 0; gc < Gc; gc++)
+      if (stop[gc] && !done[cur_groups[gc]]) { done[cur_groups[gc]] = 1; left--; }
+    if (left == 0) break;
+    // compact when at least a quarter of the current centres belong to stopped groups
+    int stopped = 0;
+    for (int jc = 0; jc < (int)cmap.size(); jc++) stopped += done[grp0[cmap[jc]]];
+    if (4 * stopped < (int)cmap.size()) continue;
+    rc = save_current();
+    if (rc) return rc;
+    std::vector<int> ngroups_list, ncmap;
+    std::vector<int32_t> nSr, ngrp;
+    for (int gc = 0; gc < Gc; gc++)
+      if (!done[cur_groups[gc]]) ngroups_list.push_back(cur_groups[gc]);
+    for (int jc = 0; jc < (int)cmap.size(); jc++) {
+      const int j = cmap[jc], g = grp0[j];
+      if (done[g]) continue;
+      const int gi = (int)(std::lower_bound(ngroups_list.begin(), ngroups_list.end(), g) - ngroups_list.begin());
+      ncmap.push_back(j);
+      nSr.push_back(Sr0[j]);
+      ngrp.push_back(gi);
+    }
+    const int Kc = (int)ncmap.size();
+    cur.resize(Kc, r, d, dd);
+    for (int jc = 0; jc < Kc; jc++) cur.copy_centre(jc, full, ncmap[jc], r, d, dd);
+    rc = em_upload_state(h, Kc, nSr.data(), r, ngrp.data(), (int)ngroups_list.size(), cur.alpha.data(), cur.eta.data(),
+                         cur.eps.data(), cur.m.data(), cur.W.data(), cur.v.data(), cur.lam.data());
+    if (rc) return rc;
+    cur_groups.swap(ngroups_list);
+    cmap.swap(ncmap);
+    compacted = true;
+    ncompact++;
   }
+  if (compacted) {
+    int rc = save_current();
+    if (rc) return rc;
+    rc = em_upload_state(h, K0, Sr0.data(), r, G > 1 || !h->em.group.empty() ? grp0.data() : nullptr, G, full.alpha.data(),
+                         full.eta.data(), full.eps.data(), full.m.data(), full.W.data(), full.v.data(), full.lam.data());
+    if (rc) return rc;
+    h->lastK = 0;   // the pair results in the handle belong to the last compacted E-step: not fetchable
+  }
+  h->counters[6] = ncompact;
   for (int g = 0; g < G; g++) {
     iters[g] = it[g];
     if (unstable) unstable[g] = bad[g];

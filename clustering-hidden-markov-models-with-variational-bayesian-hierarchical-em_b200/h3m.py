@@ -191,3 +191,130 @@ def vbhem_h3m_c_step_fc(h3m_r: dict, base, vbhemopt: dict, covmode: str = "full"
             break
     return dict(hyp=hyp, LogLs=np.array(LogLs), LL=LogLs[-1], iters=it, unstable=unstable, Nj=fin["Nj"],
                 ms_per_iter=1e3 * float(np.median(times)) if times else float("nan"))
+
+
+# ----------------------------------------------------------------------------- user entry: (K, S) model selection
+CLUSTER_DEFAULTS = dict(alpha0=1.0, eta0=1.0, epsilon0=1.0, m0=(256.0, 192.0), W0=0.005, lambda0=1.0, v0=5.0,
+                        trials=100, max_iter=200, minDiff=1e-5, Nv=100.0, tau=10, use_post=True, seed=None,
+                        initmode="baseem")
+"""vbhem_h3m_cluster.m:141-179 (``initmode`` 'auto' of the reference tries 'baseem', 'gmmNew' and 'wtkmeans';
+only 'baseem' is mirrored, the other two need the Statistics Toolbox)."""
+
+
+def stack_h3ms(models: list) -> tuple[dict, np.ndarray]:
+    """Several H3Ms' centre hyper-parameter dicts -> one dict padded to the largest state count, plus ``group``
+    (model index of every centre): the argument of ``BaseSet.em_begin(..., group=...)`` / ``estep_hyp``."""
+    maxS = max(h["eta"].shape[1] for h in models)
+    parts, group = [], []
+    for g, h in enumerate(models):
+        K, S = h["eta"].shape
+        pad = maxS - S
+        parts.append(dict(Sr=np.asarray(h.get("Sr", np.full(K, S)), np.int32), alpha=np.asarray(h["alpha"], float),
+                          eta=np.pad(h["eta"], ((0, 0), (0, pad))),
+                          epsilon=np.pad(h["epsilon"], ((0, 0), (0, pad), (0, pad))),
+                          m=np.pad(h["m"], ((0, 0), (0, pad), (0, 0))),
+                          W=np.pad(h["W"], ((0, 0), (0, pad)) + ((0, 0),) * (np.ndim(h["W"]) - 2)),
+                          v=np.pad(h["v"], ((0, 0), (0, pad))), lam=np.pad(h["lam"], ((0, 0), (0, pad)))))
+        group += [g] * K
+    return {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}, np.array(group, np.int32)
+
+
+def _slice_h3m(hyp: dict, sel: np.ndarray, S: int) -> dict:
+    out = {k: np.asarray(v)[sel] for k, v in hyp.items()}
+    out.update(eta=out["eta"][:, :S], epsilon=out["epsilon"][:, :S, :S], m=out["m"][:, :S], W=out["W"][:, :S],
+               v=out["v"][:, :S], lam=out["lam"][:, :S])
+    return out
+
+
+def h3m_parameters(hyp: dict, covmode: str = "full") -> dict:
+    """convert_h3mrtoh3mb.m:1-79: point estimates of a centre set from its hyper-parameters -- omega[K],
+    prior[K,S], trans[K,S,S], mean[K,S,d], cov[K,S,d,d] | [K,S,d] (zero beyond each centre's own state count)."""
+    Sr = np.asarray(hyp["Sr"])
+    K, S = hyp["eta"].shape
+    d = hyp["m"].shape[2]
+    full = covmode == "full"
+    out = dict(omega=hyp["alpha"] / hyp["alpha"].sum(), prior=np.zeros((K, S)), trans=np.zeros((K, S, S)),
+               mean=np.zeros((K, S, d)), cov=np.zeros((K, S, d, d) if full else (K, S, d)))
+    for j in range(K):
+        s = int(Sr[j])
+        out["prior"][j, :s] = hyp["eta"][j, :s] / hyp["eta"][j, :s].sum()
+        rs = hyp["epsilon"][j, :s, :s].sum(1, keepdims=True)
+        out["trans"][j, :s, :s] = hyp["epsilon"][j, :s, :s] / np.where(rs == 0, 1.0, rs)
+        out["mean"][j, :s] = hyp["m"][j, :s]
+        for k in range(s):
+            v = hyp["v"][j, k]
+            den = v - d - 1 if v > d + 1 else v
+            if full:
+                tC = np.linalg.inv(hyp["W"][j, k]) / den
+                out["cov"][j, k] = (tC + tC.T) / 2
+            else:
+                out["cov"][j, k] = (1.0 / hyp["W"][j, k]) / den
+    return out
+
+
+def vbhem_h3m_cluster(hmms, K, S, vbhemopt: dict | None = None, covmode: str = "full", device: int = 0) -> dict:
+    """[group_hmms] = vbhem_h3m_cluster(hmms, K, S, vbhemopt)  (vbhem_h3m_cluster.m:1): cluster HMMs into K groups
+    with S states per group HMM; vectors of K and / or S select the model by the lower bound.
+
+    The reference recurses -- for each K, for each S, ``trials`` EM runs from seeded random initialisations one
+    after the other (vbhem_h3m_cluster.m:261-355, vbhem_h3m_c.m:28-76).  Here every candidate (K, S, trial) is a
+    soft-max group of ONE batched device-resident EM loop over the shared base set (``vbhem_em_run_groups``), each
+    run to its own convergence.  Selection is the reference's: best trial by LL; over S the largest
+    ``LL + gammaln(S + 1)`` (:327-331); over K the largest ``LL(best S) + gammaln(K + 1)`` (:279-283).
+
+    ``hmms``: list of learned HMMs (see ``hmms_to_h3m_hem``) or an already converted natural base dict.
+    Returns the chosen model with the reference's field names where they exist (form_outputH3M.m:1-61):
+    ``K, S, LL, hyp`` (hyper-parameters after the last M-step), ``omega, prior, trans, mean, cov``
+    (convert_h3mrtoh3mb.m), ``Z [N,K]``, ``L_elbo [N,K]``, ``label`` (0-based), ``groups``, ``group_size``,
+    ``model_LL [nK]``, ``model_k``, ``model_bestK``, ``model_LL_S [nK][nS]``, ``model_S``, ``model_bestS``,
+    ``trials_LL [nK,nS,trials]``, ``iters``.  ``Z`` / ``L_elbo`` are evaluated under the returned hyper-parameters --
+    one E-step later than the reference's hat_Z (vbhem_h3m_c_step_fc.m:446), equal to it within ``minDiff``."""
+    from . import synth
+    from .api import BaseSet
+    opt = dict(CLUSTER_DEFAULTS)
+    opt.update(vbhemopt or {})
+    if opt.get("seed") is None:
+        raise ValueError("vbhemopt.seed has not been set. This is required to obtain reproducible results.")
+    if opt["initmode"] != "baseem":
+        raise NotImplementedError(f"initmode {opt['initmode']!r}: only 'baseem' is mirrored")
+    base = hmms if isinstance(hmms, dict) else hmms_to_h3m_hem(hmms, covmode, bool(opt["use_post"]), float(opt["Nv"]))
+    d = base["mu"].shape[2]
+    if opt["v0"] <= d - 1:
+        raise ValueError("v0 not large enough...should be > D-1")
+    if len(np.atleast_1d(opt["m0"])) != d:
+        raise ValueError(f"vbhemopt.m0 should have dimension D={d}")
+    Ks, Ss = [int(k) for k in np.atleast_1d(K)], [int(s) for s in np.atleast_1d(S)]
+    trials = int(opt["trials"])
+    cand, models = [], []
+    for ki, k in enumerate(Ks):
+        for si, s in enumerate(Ss):
+            for t in range(trials):
+                cand.append((ki, si, t))
+                models.append(synth.init_centres_baseem(base, k, s, seed=int(opt["seed"]) + t + 1, opt=opt))
+    hyp, group = stack_h3ms(models)
+    with BaseSet(base, device=device) as bs:
+        bs.em_begin(hyp, opt, group=group)
+        run = bs.em_run_groups(int(opt["tau"]), int(opt["max_iter"]), float(opt["minDiff"]))
+        LL = np.full((len(Ks), len(Ss), trials), -np.inf)
+        for g, (ki, si, t) in enumerate(cand):
+            if len(run["LogLs"][g]) and not run["unstable"][g]:
+                LL[ki, si, t] = run["LogLs"][g][-1]
+        best_t = LL.argmax(2)                                                # vbhem_h3m_c.m: best trial
+        LL_ks = np.take_along_axis(LL, best_t[:, :, None], 2)[:, :, 0]
+        LL_S = LL_ks + gammaln(np.array(Ss) + 1.0)[None]                     # vbhem_h3m_cluster.m:327-331
+        best_s = LL_S.argmax(1)
+        LL_K = LL_ks[np.arange(len(Ks)), best_s] + gammaln(np.array(Ks) + 1.0)   # :279-283 (the run's own LL)
+        bk = int(LL_K.argmax())
+        bs_i = int(best_s[bk])
+        g = cand.index((bk, bs_i, int(best_t[bk, bs_i])))
+        chosen = _slice_h3m(run["hyp"], group == g, Ss[bs_i])
+        last = bs.estep_hyp(chosen, int(opt["tau"]))
+    out = dict(K=Ks[bk], S=Ss[bs_i], LL=float(LL_ks[bk, bs_i]), hyp=chosen, Z=last["zhat"], L_elbo=last["L_elbo"],
+               Nj=chosen["alpha"] - float(opt["alpha0"]), iters=int(run["iters"][g]), model_LL=LL_K,
+               model_k=np.array(Ks), model_bestK=Ks[bk], model_LL_S=LL_S, model_S=np.array(Ss), model_bestS=Ss[bs_i],
+               trials_LL=LL, vbhemopt=opt)
+    out.update(h3m_parameters(chosen, covmode))
+    out["label"] = out["Z"].argmax(1)
+    out["groups"] = [np.flatnonzero(out["label"] == j) for j in range(out["K"])]
+    out["group_size"] = np.array([len(x) for x in out["groups"]])
+    return out

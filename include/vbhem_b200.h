@@ -201,7 +201,11 @@ int vbhem_finalize_stats_dev(vbhem_base_t *base, int K, const int32_t *Sr, int m
  *   vbhem_em_run_groups  that loop for every batched H3M at once (trials, initialisations or (K,S) candidates
  *                        that share the base set: vbhem_h3m_c.m:28-76, vbhem_h3m_cluster.m:261-355): each group
  *                        stops by its own convergence test and keeps its hyper-parameters while the others go
- *                        on.  LogLs is [ngroups][ld] (ld >= max_iter + 2), iters / unstable are [ngroups]. */
+ *                        on; once a quarter of the centres belong to stopped groups the E-step continues on
+ *                        the running groups only.  LogLs is [ngroups][ld] (ld >= max_iter + 2), iters /
+ *                        unstable are [ngroups].  Afterwards vbhem_em_fetch returns every group in its
+ *                        original place; the per-pair results of the last E-step are not fetchable
+ *                        (vbhem_fetch) when the set was compacted on the way. */
 int vbhem_em_begin(vbhem_base_t *base, int K, const int32_t *Sr, int maxSr, const int32_t *group, int ngroups,
                    double alpha0, double eta0, double epsilon0, double lambda0, double v0, const double *m0,
                    const double *W0, int nW0, const double *alpha, const double *eta, const double *epsilon,
@@ -272,7 +276,8 @@ int vbhem_measure_fp64_peak(int device, double out[2]);
  *   out[0] kernels launched, out[1] pairs through the tensor-core kernel,
  *   out[2] pairs through the general kernel (incl. numerical fall-backs),
  *   out[3] pairs with Z > 1e-8 (second pass), out[4] 8-state tiles per base in the first pass,
- *   out[5] of which split tiles (5..7 + 3..1 states), out[6..7] reserved. */
+ *   out[5] of which split tiles (5..7 + 3..1 states), out[6] compactions of the last vbhem_em_run_groups,
+ *   out[7] reserved. */
 int vbhem_last_counters(vbhem_base_t *base, long long out[8]);
 
 #ifdef __cplusplus

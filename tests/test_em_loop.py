@@ -202,6 +202,7 @@ def test_batched_em_runs_equal_separate_runs():
         bs.em_begin(hyp, opt, group=grp)
         got = bs.em_run_groups(opt["tau"], opt["max_iter"], opt["minDiff"])
         assert len(set(int(i) for i in got["iters"])) > 1          # the candidates stop at different iterations
+        assert bs.counters()["compactions"] >= 1                   # ... and the stopped ones left the E-step
         for g, (K, S) in enumerate(models):
             sel = np.where(grp == g)[0]
             bs.em_begin({k: v[sel] for k, v in hyp.items()}, opt)

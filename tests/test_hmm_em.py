@@ -131,15 +131,26 @@ def test_learn_then_cluster_recovers_the_two_groups():
         hmms.append(H.vbhmm_learn(data, [1, 2, 3], dict(numTrials=3, seed=100 + s)))
         label.append(g)
     assert all(h["K"] == 2 for h in hmms), [h["K"] for h in hmms]
-    base = h3m.hmms_to_h3m_hem(hmms)
-    opt = dict(synth.DEFAULT_OPT)
-    runs = []
-    with BaseSet(base) as bs:
-        for trial in range(8):                      # vbhem_h3m_c.m:28-76: several initialisations, best bound wins
-            hyp = synth.init_centres_baseem(base, 2, 2, seed=1001 + trial, opt=opt)
-            runs.append(h3m.vbhem_h3m_c_step_fc(hyp, bs, opt))
-        best = max(runs, key=lambda r: r["LL"])
-        z = bs.estep_hyp(best["hyp"], opt["tau"])["zhat"]
-    assign = z.argmax(1)
+    out = h3m.vbhem_h3m_cluster(hmms, [1, 2, 3], [1, 2, 3], dict(trials=4, seed=1001))
     label = np.array(label)
-    assert (assign == label).all() or (assign == 1 - label).all(), (assign, [r["LL"] for r in runs])
+    assert out["model_bestK"] == 2 and out["K"] == 2, (out["model_LL"], out["model_LL_S"])
+    assert (out["label"] == label).all() or (out["label"] == 1 - label).all(), out["label"]
+    assert out["group_size"].tolist() == [8, 8]
+    np.testing.assert_allclose(out["Z"].sum(1), 1.0, rtol=1e-12)
+    np.testing.assert_allclose(out["trans"][:, :out["S"], :out["S"]].sum(2), 1.0, rtol=1e-12)
+    # the same selection by hand: every (K, S, trial) as a separate device EM run from the same initialisation
+    base = h3m.hmms_to_h3m_hem(hmms)
+    opt = out["vbhemopt"]
+    with BaseSet(base) as bs:
+        for ki, k in enumerate([1, 2, 3]):
+            for si, sn in enumerate([1, 2, 3]):
+                for t in range(4):
+                    hyp = synth.init_centres_baseem(base, k, sn, seed=1001 + t + 1, opt=opt)
+                    one = h3m.vbhem_h3m_c_step_fc(hyp, bs, opt, device_loop=True)
+                    np.testing.assert_allclose(out["trials_LL"][ki, si, t], one["LL"], rtol=1e-12, err_msg=str((k, sn, t)))
+
+
+def test_cluster_needs_a_seed():
+    from vbhem_b200 import h3m
+    with pytest.raises(ValueError, match="seed"):
+        h3m.vbhem_h3m_cluster(dict(mu=np.zeros((2, 1, 2))), 2, 2, {})
