@@ -148,6 +148,8 @@ def main():
     ap.add_argument("--dim", type=int, default=2)
     ap.add_argument("--tau", type=int, default=10)
     ap.add_argument("--seed", type=int, default=1001)
+    ap.add_argument("--grid-em", type=int, default=0, metavar="MAX_ITER",
+                    help="--workload grid: also run every candidate's EM to convergence (at most MAX_ITER passes)")
     ap.add_argument("--cpu-worker", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--cpu-bases", type=int, default=0, help="bases per CPU worker (0 = default sample)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -362,6 +364,28 @@ def main():
                                "host_mirror_ms = median iteration of h3m.vbhem_h3m_c_step_fc (statistics D2H, numpy "
                                "M-step and lower bound)")
 
+    # ---- (K,S) grid: every candidate's whole EM run, batched (vbhem_em_run_groups), N = 1 only
+    grid_em = None
+    if world == 1 and grid and a.grid_em:
+        opt = dict(synth.DEFAULT_OPT, tau=tau, max_iter=a.grid_em, minDiff=1e-5)
+        check(L.vbhem_set_profile(bs._h, 0))
+        bs.em_begin({k: v for k, v in hyp.items()}, opt, group=grp)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = bs.em_run_groups(tau, opt["max_iter"], opt["minDiff"])
+        t_run = time.perf_counter() - t0
+        check(L.vbhem_set_profile(bs._h, 1))
+        passes = [len(x) for x in out["LogLs"]]
+        centre_passes = int(sum(p * k for p, (k, _) in zip(passes, models)))
+        grid_em = dict(seconds=t_run, models=len(models), max_iter=opt["max_iter"], minDiff=opt["minDiff"],
+                       e_steps=int(max(passes)), centre_passes=centre_passes,
+                       centre_passes_uncompacted=int(max(passes)) * K, compactions=int(bs.counters()["compactions"]),
+                       pairs_per_s=centre_passes * a.bases / t_run,
+                       note="vbhem_em_run_groups: all (K,S) candidates to their own convergence in one loop; "
+                            "centre_passes = sum over candidates of K x E-steps it needed (the useful work); the loop "
+                            "compacts the centre set to the running candidates, so its cost follows that sum "
+                            "instead of e_steps x all centres")
+
     # ---- strong scaling of the north-star size (100k bases in total): E-step and whole EM iterations
     strong = None
     if world > 1 and not grid:
@@ -462,6 +486,8 @@ def main():
             line["strong"] = strong
         if vbhem_iter is not None:
             line["vbhem_iter"] = vbhem_iter
+        if grid_em is not None:
+            line["grid_em"] = grid_em
         emit(line)
     if dist is not None:
         dist.barrier()
