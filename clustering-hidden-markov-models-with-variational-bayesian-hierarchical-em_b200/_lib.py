@@ -65,6 +65,12 @@ SIGNATURES = {
     "vbhmm_fb_fetch": (C.c_int, [vp, dp, dp, dp, dp]),
     "vbhmm_fb_stats": (C.c_int, [vp, C.c_int, dp, dp, dp, dp, dp, C.c_double, dp, dp, dp, dp, dp, dp, dp, dp]),
     "vbhmm_fb_last_ms": (C.c_int, [vp, dp]),
+    "vbhmm_batch_begin": (C.c_int, [vp, C.c_int, ip, ip, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, dp,
+                                    dp, C.c_int, dp, dp, dp, dp, dp, dp, C.c_int, C.POINTER(vp)]),
+    "vbhmm_batch_run": (C.c_int, [vp, C.c_double, C.POINTER(C.c_int)]),
+    "vbhmm_batch_fetch": (C.c_int, [vp, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp, ip, ip]),
+    "vbhmm_batch_last_ms": (C.c_int, [vp, dp]),
+    "vbhmm_batch_free": (C.c_int, [vp]),
     "vbhem_set_profile": (C.c_int, [vp, C.c_int]),
     "vbhem_last_timings": (C.c_int, [vp, dp]),
     "vbhem_measure_fp64_peak": (C.c_int, [C.c_int, dp]),

@@ -29,6 +29,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 namespace vbhem {
@@ -745,3 +746,5 @@ int vbhmm_fb_last_ms(vbhmm_data_t *h, double *ms) {
 }
 
 }  // extern "C"
+
+#include "vbhmm_batch.inl"

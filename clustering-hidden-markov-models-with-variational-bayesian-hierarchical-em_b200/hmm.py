@@ -25,7 +25,10 @@ from __future__ import annotations
 import numpy as np
 from scipy.special import gammaln
 
+import ctypes as C
+
 from . import fb as _fb
+from ._lib import check, dp, ip, lib
 
 DEFAULT_VBOPT = dict(alpha0=0.1, epsilon0=0.1, mu0=(256.0, 192.0), beta0=1.0, W0=0.005, v0=5.0, maxIter=100,
                      minDiff=1e-5, initmode="random", numTrials=50, seed=None, verbose=0)   # vbhmm_learn.m:232-300
@@ -220,4 +223,103 @@ def vbhmm_learn(data: list, K, vbopt: dict | None = None) -> dict:
                 best_all = (model_LL[-1], best)
     out = dict(best_all[1])
     out.update(model_LL=np.array(model_LL), model_k=np.array(Ks), model_all=per_k, L=best_all[0])
+    return out
+
+
+# ----------------------------------------------------------------------------- many runs at once, on the device
+def _hmm_from_varpar(vp: dict, K: int) -> dict:
+    """vbhmm_em.m:391-460: point estimates from the final variational parameters."""
+    dim = vp["m"].shape[1]
+    Ci = np.linalg.inv(vp["W"]) / np.where(vp["v"] > dim + 1, vp["v"] - dim - 1, vp["v"])[:, None, None]
+    rs = vp["epsilon"].sum(1, keepdims=True)
+    return dict(prior=vp["alpha"] / vp["alpha"].sum(), trans=vp["epsilon"] / np.where(rs == 0, 1.0, rs),
+                mean=vp["m"].copy(), cov=(Ci + np.transpose(Ci, (0, 2, 1))) / 2, varpar=vp, K=K)
+
+
+def vbhmm_em_batch(seqs: _fb.SequenceSet, runs, K: int, ini: dict, inits: list) -> tuple[list, dict]:
+    """Many ``vbhmm_em`` runs over one packed ``SequenceSet`` in a single device-resident loop (``vbhmm_batch_*``).
+
+    ``runs[r] = (lo, hi)``: run r learns from sequences lo..hi-1 (the reference's per-subject loop,
+    vbhmm_learn_batch.m, and per-initialisation loop, vbhmm_learn.m:465-557, flattened; runs may share sequences);
+    ``inits[r]``: its initial variational parameters (``vbhmm_init``).  All runs have K states.
+    Returns (list of hmm dicts as ``vbhmm_em``, info = dict(passes, device_ms))."""
+    R = len(runs)
+    dim = seqs.dim
+    c = np.ascontiguousarray
+    lo = c([a for a, _ in runs], dtype=np.int32)
+    hi = c([b for _, b in runs], dtype=np.int32)
+    stack = lambda k: np.stack([np.asarray(v[k], float) for v in inits])
+    al, be, vv = c(stack("alpha")), c(stack("beta")), c(stack("v"))                    # [R, K]     == col-major [K, R]
+    ep = c(np.transpose(stack("epsilon"), (0, 2, 1)))                                  # [R, to, from] == [from, to, R]
+    mm = c(stack("m"))                                                                 # [R, K, dim]  == [dim, K, R]
+    WW = c(np.transpose(stack("W"), (0, 1, 3, 2)))                                     # [R, K, j, i] == [i, j, K, R]
+    m0 = c(np.asarray(ini["mu0"], float).reshape(dim))
+    W0 = c(np.atleast_1d(np.asarray(ini["W0"], float)).ravel())
+    max_iter, min_diff = int(ini.get("maxIter", 100)), float(ini.get("minDiff", 1e-5))
+    P = lambda a: a.ctypes.data_as(dp)
+    h = C.c_void_p()
+    check(lib().vbhmm_batch_begin(seqs._h, R, lo.ctypes.data_as(ip), hi.ctypes.data_as(ip), K, float(ini["alpha0"]),
+                                  float(ini["epsilon0"]), float(ini["beta0"]), float(ini["v0"]), P(m0), P(W0),
+                                  int(W0.size), P(al), P(ep), P(be), P(vv), P(mm), P(WW), max_iter, C.byref(h)))
+    try:
+        passes = C.c_int()
+        check(lib().vbhmm_batch_run(h, min_diff, C.byref(passes)))
+        o = dict(alpha=np.zeros((R, K)), eps=np.zeros((R, K, K)), beta=np.zeros((R, K)), v=np.zeros((R, K)),
+                 m=np.zeros((R, K, dim)), W=np.zeros((R, K, dim, dim)), Nk1=np.zeros((R, K)), Nk=np.zeros((R, K)),
+                 M=np.zeros((R, K, K)), LLs=np.zeros((R, max_iter)), it=np.zeros(R, np.int32), bad=np.zeros(R, np.int32))
+        check(lib().vbhmm_batch_fetch(h, P(o["alpha"]), P(o["eps"]), P(o["beta"]), P(o["v"]), P(o["m"]), P(o["W"]),
+                                      P(o["Nk1"]), P(o["Nk"]), P(o["M"]), P(o["LLs"]), o["it"].ctypes.data_as(ip),
+                                      o["bad"].ctypes.data_as(ip)))
+        ms = C.c_double()
+        check(lib().vbhmm_batch_last_ms(h, C.byref(ms)))
+    finally:
+        check(lib().vbhmm_batch_free(h))
+    out = []
+    for r in range(R):
+        vp = dict(alpha=o["alpha"][r], epsilon=o["eps"][r].T.copy(), beta=o["beta"][r], v=o["v"][r], m=o["m"][r],
+                  W=np.transpose(o["W"][r], (0, 2, 1)).copy())
+        hm = _hmm_from_varpar(vp, K)
+        n = int(o["it"][r])
+        hm.update(LL=float(o["LLs"][r, n - 1]), LLs=o["LLs"][r, :n].copy(), iter=n, unstable=bool(o["bad"][r]),
+                  M=o["M"][r].copy(), N1=o["Nk1"][r].copy(), N=o["Nk"][r].copy())
+        out.append(hm)
+    return out, dict(passes=passes.value, device_ms=ms.value)
+
+
+def vbhmm_learn_batch(subjects: list, K, vbopt: dict | None = None) -> list:
+    """vbhmm_learn_batch.m: one HMM per subject (``subjects[s]`` = that subject's list of [T, dim] sequences), every
+    subject x candidate K x random initialisation as one run of a device-resident batch per K; per subject the best
+    trial by LL, then the best K by ``LL + gammaln(K + 1)`` (vbhmm_learn.m:387-405,555)."""
+    opt = dict(DEFAULT_VBOPT)
+    opt.update(vbopt or {})
+    Ks = [int(k) for k in np.atleast_1d(K)]
+    flat = [x for sub in subjects for x in sub]
+    start = np.concatenate([[0], np.cumsum([len(sub) for sub in subjects])]).astype(int)
+    trials = 1 if opt["initmode"] != "random" else int(opt["numTrials"])
+    best = [None] * len(subjects)
+    score = [-np.inf] * len(subjects)
+    per_k = [[None] * len(Ks) for _ in subjects]
+    with _fb.SequenceSet(flat) as seqs:
+        for ki, k in enumerate(Ks):
+            runs, inits, owner = [], [], []
+            for s, sub in enumerate(subjects):
+                for t in range(trials):
+                    seed = None if opt.get("seed") is None else int(opt["seed"]) + t
+                    inits.append(vbhmm_init(sub, k, dict(opt, seed=seed)))
+                    runs.append((int(start[s]), int(start[s + 1])))
+                    owner.append(s)
+            hmms, _ = vbhmm_em_batch(seqs, runs, k, opt, inits)
+            for s in range(len(subjects)):
+                mine = [h for h, o in zip(hmms, owner) if o == s]
+                top = max(mine, key=lambda h: h["LL"])
+                per_k[s][ki] = top
+                sc = top["LL"] + gammaln(k + 1)
+                if sc > score[s]:
+                    score[s], best[s] = sc, top
+    out = []
+    for s in range(len(subjects)):
+        h = dict(best[s])
+        h.update(model_LL=np.array([per_k[s][ki]["LL"] + gammaln(k + 1) for ki, k in enumerate(Ks)]),
+                 model_k=np.array(Ks), L=score[s])
+        out.append(h)
     return out

@@ -259,6 +259,34 @@ int vbhmm_fb_stats(vbhmm_data_t *data, int K, const double *m, const double *W, 
                    double *Nk1, double *Nk, double *M, double *xbar, double *S, double *lb2);
 int vbhmm_fb_last_ms(vbhmm_data_t *data, double *ms);
 
+/* ---- Batched VB-HMM learning: many independent vbhmm_em runs on the device -------------------------------
+ * The toolbox learns one HMM per subject by looping vbhmm_learn over the subjects
+ * (/root/reference/src/hmm/vbhmm_learn_batch.m), and inside it vbhmm_em over random initialisations and candidate
+ * state counts (/root/reference/src/hmm/vbhmm_learn.m:465-557).  Here a RUN is a range [seq_lo, seq_hi) of the packed
+ * sequences plus its own K-state model; all R runs of a batch execute the loop of
+ * /root/reference/src/hmm/vbhmm_em.m:108-418 on the device -- pre-pass (vbhmm_fb.m:62-80), forward-backward, the sums
+ * of vbhmm_em.m:158-246, the lower bound (vbhmm_em_lb.m:74-258), the convergence test |dL / L_last| <= min_diff from
+ * the second pass on or max_iter passes (vbhmm_em.m:293-330), the M-step (:353-389, also after the breaking pass) --
+ * and the host reads one integer per pass.  Runs may share sequences (several initialisations of one subject).
+ *   vbhmm_batch_begin: priors alpha0, epsilon0, beta0, v0, m0[dim], W0[nW0 = 1 | dim] (vbhmm_init.m:128-152) and the
+ *     initial variational parameters of every run, MATLAB layouts with the run as the last index:
+ *     alpha[K,R], epsilon[K(from),K(to),R], beta[K,R], v[K,R], m[dim,K,R], W[dim,dim,K,R].  K <= 8, dim <= 3.
+ *   vbhmm_batch_run: runs every run to its own end; *passes = passes of the slowest run.
+ *   vbhmm_batch_fetch (any pointer may be NULL): final parameters (same layouts), the last E-step's Nk1[K,R]
+ *     (+1e-50), Nk[K,R] (+1e-50), M[K(to)... stored [K(from) x K(to)] ROW-major per run], LLs[R][max_iter] (0 beyond
+ *     a run's own passes), iters[R] = passes made, unstable[R] = the NaN guard of vbhmm_em.m:320-330 fired (then the
+ *     parameters are those before that pass and the last LL is -Inf). */
+typedef struct vbhmm_batch vbhmm_batch_t;
+int vbhmm_batch_begin(vbhmm_data_t *data, int R, const int32_t *seq_lo, const int32_t *seq_hi, int K, double alpha0,
+                      double epsilon0, double beta0, double v0, const double *m0, const double *W0, int nW0,
+                      const double *alpha, const double *epsilon, const double *beta, const double *v, const double *m,
+                      const double *W, int max_iter, vbhmm_batch_t **out);
+int vbhmm_batch_run(vbhmm_batch_t *batch, double min_diff, int *passes);
+int vbhmm_batch_fetch(vbhmm_batch_t *batch, double *alpha, double *epsilon, double *beta, double *v, double *m,
+                      double *W, double *Nk1, double *Nk, double *M, double *LLs, int32_t *iters, int32_t *unstable);
+int vbhmm_batch_last_ms(vbhmm_batch_t *batch, double *ms);
+int vbhmm_batch_free(vbhmm_batch_t *batch);
+
 /* Phase timing of the handle's E-steps, for bench.py: when enabled, CUDA events are
  * recorded on the handle's stream around each phase and vbhem_last_timings() returns the
  * milliseconds of the last E-step:

@@ -154,3 +154,56 @@ def test_cluster_needs_a_seed():
     from vbhem_b200 import h3m
     with pytest.raises(ValueError, match="seed"):
         h3m.vbhem_h3m_cluster(dict(mu=np.zeros((2, 1, 2))), 2, 2, {})
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("K,dim", [(3, 2), (2, 3), (5, 2), (1, 1)])
+def test_batched_em_runs_match_oracle_loops(K, dim):
+    """vbhmm_em_batch: several subjects x several initialisations as runs of ONE device-resident loop (pre-pass,
+    forward-backward, sums, lower bound, convergence test and M-step all on the GPU) -- every run must reproduce the
+    oracle's vbhmm_em from the same initialisation: passes, trace of lower bounds (1e-9), parameters (1e-7)."""
+    from vbhem_b200 import fb
+    ini = dict(INI, mu0=[256.0, 192.0, 100.0][:dim], maxIter=40)
+    subjects, gmms = [], []
+    for s in range(5):
+        data, gmm = make_sequences(n=6 + 3 * s, K=K, dim=dim, seed=40 + s, tmin=1 if s == 1 else 4)
+        subjects.append(data)
+        gmms.append(gmm)
+    flat = [x for sub in subjects for x in sub]
+    start = np.concatenate([[0], np.cumsum([len(sub) for sub in subjects])])
+    rng = np.random.Generator(np.random.PCG64(77))
+    runs, inits, datas = [], [], []
+    for s, sub in enumerate(subjects):
+        for trial in range(2):                                     # two initialisations share the subject's sequences
+            g = dict(gmms[s], mean=gmms[s]["mean"] + (rng.normal(0, 10, gmms[s]["mean"].shape) if trial else 0.0))
+            inits.append(nr.vbhmm_init_from_gmm(g, sum(len(x) for x in sub), ini))
+            runs.append((int(start[s]), int(start[s + 1])))
+            datas.append(sub)
+    with fb.SequenceSet(flat) as seqs:
+        got, info = H.vbhmm_em_batch(seqs, runs, K, ini, inits)
+    assert info["passes"] == max(h["iter"] for h in got)
+    assert len(set(h["iter"] for h in got)) > 1 or K == 1        # the runs stop at different passes
+    for r, (h, vp0, data) in enumerate(zip(got, inits, datas)):
+        want = nr.vbhmm_em(data, vp0, ini, fb=oracle_fb)
+        assert h["iter"] == want["iter"] and h["unstable"] == want["unstable"], r
+        np.testing.assert_allclose(h["LLs"], want["LLs"], rtol=1e-9, err_msg=f"run {r}")
+        for k in want["varpar"]:
+            np.testing.assert_allclose(h["varpar"][k], want["varpar"][k], rtol=1e-7, atol=1e-12, err_msg=f"{k} run {r}")
+        for k in ("prior", "trans", "mean", "cov", "M", "N1", "N"):
+            np.testing.assert_allclose(h[k], want[k], rtol=1e-7, atol=1e-12, err_msg=f"{k} run {r}")
+
+
+@pytest.mark.gpu
+def test_learn_batch_equals_learning_subject_by_subject():
+    """vbhmm_learn_batch (all subjects x K x trials in one device loop per K) picks the same models as vbhmm_learn
+    subject by subject (same seeds => same initial GMMs)."""
+    subjects = [make_sequences(n=10, K=2, seed=60 + s)[0] for s in range(4)]
+    opt = dict(numTrials=3, seed=5, maxIter=50)
+    got = H.vbhmm_learn_batch(subjects, [1, 2, 3], opt)
+    for s, sub in enumerate(subjects):
+        one = H.vbhmm_learn(sub, [1, 2, 3], opt)
+        assert got[s]["K"] == one["K"]
+        np.testing.assert_allclose(got[s]["model_LL"], one["model_LL"], rtol=1e-9)
+        # trials that reach the same optimum tie to the last bits, so the winner's states may be permuted
+        order = lambda m: m[np.lexsort(m.T[::-1])]
+        np.testing.assert_allclose(order(got[s]["mean"]), order(one["mean"]), rtol=1e-6)
