@@ -142,6 +142,30 @@ def main_fb(a):
         if i >= W:
             stats_ms.append(ms.value)
             stats_wall.append(1e3 * dtw)
+    # the toolbox's actual use: one HMM per subject (vbhmm_learn_batch.m).  20 000 subjects share the N sequences;
+    # every subject's whole EM run (vbhmm_em.m) executes in ONE device-resident loop (vbhmm_batch_*)
+    learn = None
+    nsub = min(20000, N // 8)
+    if nsub >= 1 and K <= 8 and dim <= 3:
+        from vbhem_b200 import hmm as Hm
+        per = N // nsub
+        rng = np.random.default_rng(a.seed + 1)
+        runs = [(s * per, (s + 1) * per) for s in range(nsub)]
+        inits = [dict(vp, m=vp["m"] + rng.normal(0, 6, vp["m"].shape)) for _ in range(nsub)]
+        ini = dict(alpha0=0.1, epsilon0=0.1, beta0=1.0, v0=5.0, mu0=[256.0, 192.0, 128.0][:dim], W0=0.005, maxIter=30,
+                   minDiff=1e-5)
+        t0 = time.perf_counter()
+        hm, info = Hm.vbhmm_em_batch(seqs, runs, K, ini, inits)
+        wall = time.perf_counter() - t0
+        run_passes = sum(h["iter"] for h in hm)
+        learn = dict(subjects=nsub, sequences_per_subject=per, passes=info["passes"], run_passes=run_passes,
+                     device_ms=info["device_ms"], wall_ms=1e3 * wall,
+                     sequence_passes_per_s=run_passes * per / (info["device_ms"] * 1e-3),
+                     unstable=int(sum(h["unstable"] for h in hm)),
+                     note="hmm.vbhmm_em_batch: every subject's vbhmm_em run (pre-pass, forward-backward, sums, lower "
+                          "bound, convergence test |dL/L| <= 1e-5, M-step) in one device-resident loop; device_ms = the "
+                          "loop (CUDA events), wall_ms includes stacking the initialisations and fetching 20k models; "
+                          "sequence_passes_per_s = (sum over subjects of the passes each needed x its sequences) / device time")
     sampler.armed = False
     sampler.stop_flag = True
     sampler.join()
@@ -204,6 +228,8 @@ def main_fb(a):
                                   note="vbhmm_fb_stats: forward-backward + the M-step sums of vbhmm_em.m:158-246 + Lt63 / "
                                        "Lt64 on the device, observations resident (packed once per vbhmm_em run); wall_ms "
                                        "is host wall clock of the C-ABI call including the result copy"))
+    if learn is not None:
+        line["learn_batch"] = learn
     if cpu is not None:
         line["cpu_baseline"] = cpu
     real_stdout.write(json.dumps(line) + "\n")
