@@ -322,14 +322,14 @@ def main():
     # DRAM traffic of the same kernel from the committed `ncu --set full` capture (same workload, per launch)
     traffic = None
     if (a.bases, K, S, d, tau) == (100_000, 64, 8, 2, 10) and not grid:
-        traffic = ncu_dram_bytes(os.path.join(ROOT, "profiles", "r01b_k_lattice_bwd_ncu.json"))
+        traffic = ncu_dram_bytes(os.path.join(ROOT, "profiles", "r01c_k_lattice_bwd_ncu.json"))
     roofline = dict(bound="tensor", kernel="k_lattice_bwd (first pass: emission expectation + backward lattice + "
                                            "termination for every pair; fp64 DMMA m8n8k4)",
                     achieved=ach, peak=float(peak[0]), unit="TFLOP/s", frac=ach / float(peak[0]),
                     peak_source="fp64 DMMA chain measured in this process (vbhem_measure_fp64_peak); "
                                 "MEASURED_PEAKS.json has no fp64 entry; DFMA chain: %.2f TFLOP/s" % float(peak[1]),
                     flops_per_pair=fl["first_pass"], kernel_ms=first_ms, traffic=traffic,
-                    traffic_source="profiles/r01b_k_lattice_bwd_ncu.json (dram__bytes_read.sum + dram__bytes_write.sum, "
+                    traffic_source="profiles/r01c_k_lattice_bwd_ncu.json (dram__bytes_read.sum + dram__bytes_write.sum, "
                                    "bytes per launch; null when the workload differs from the captured one)",
                     hbm=dict(algorithmic_bytes=alg_bytes, achieved_gbs=alg_bytes / (first_ms * 1e-3) / 1e9),
                     whole_step=dict(flops_per_pair=fl["total"],
