@@ -7,8 +7,9 @@
 // every run of a batch executes the loop of /root/reference/src/hmm/vbhmm_em.m:108-418 on the device:
 //   k_batch_prepass   thread per run: logLambdaTilde, logATilde, logPiTilde (vbhmm_fb.m:62-80) -> the run's FbPar
 //   k_fb_batch        thread per (run, sequence): the forward-backward pass of k_fb, model read through L1
-//   k_batch_update    block per run: the sums of vbhmm_em.m:158-246 in a fixed order, the lower bound
-//                     (vbhmm_em_lb.m:74-258), the convergence test (vbhmm_em.m:293-330) and the M-step (:353-389)
+//   k_batch_sums      block per run: the sums of vbhmm_em.m:158-246 in a fixed order
+//   k_batch_update    thread per run: the lower bound (vbhmm_em_lb.m:74-258), the convergence test
+//                     (vbhmm_em.m:293-330) and the M-step (:353-389)
 // and the host only reads back how many runs are still going.  Runs that have stopped cost nothing further.
 
 namespace {
@@ -119,7 +120,7 @@ __global__ void k_batch_prepass(int R, const unsigned char *__restrict__ done, c
 // k_fb for work item w = (run, sequence): the model of the item's run comes from HBM through L1 (the items of a
 // run are neighbours, so a warp reads one or two models), gamma / xi / phi are indexed by the work item.
 template <int K, int DIM>
-__global__ void __launch_bounds__(kFbThreads, 2)   // the K x K pair-marginal accumulator stays in registers
+__global__ void __launch_bounds__(kFbThreads, 3)
 k_fb_batch(const FbPar<K, DIM> *__restrict__ pars, const unsigned char *__restrict__ done, int Wn, int N, int maxT,
            const int *__restrict__ run_of, const int *__restrict__ seq_of, const int *__restrict__ Tn,
            const double *__restrict__ X, double *__restrict__ gamma, double *__restrict__ xi_sum,
@@ -158,12 +159,15 @@ k_fb_batch(const FbPar<K, DIM> *__restrict__ pars, const unsigned char *__restri
     sumlogc += log(c);
   }
   phi[w] = sumlogc + summax;
-  double beta[K], xi[K][K];
+  // the K x K pair-marginal accumulator of each thread lives in shared memory ([j][k][thread]: conflict-free), as in k_fb
+  extern __shared__ double xis[];
+  double *xi = xis + threadIdx.x;
+  double beta[K];
 #pragma unroll
   for (int j = 0; j < K; j++) {
     beta[j] = 1.0;
 #pragma unroll
-    for (int k = 0; k < K; k++) xi[j][k] = 0.0;
+    for (int k = 0; k < K; k++) xi[(j * K + k) * kFbThreads] = 0.0;
   }
   for (int t = T - 2; t >= 0; t--) {
 #pragma unroll
@@ -190,14 +194,14 @@ k_fb_batch(const FbPar<K, DIM> *__restrict__ pars, const unsigned char *__restri
     for (int j = 0; j < K; j++) {
       const double aj = alpha[j] * rc;
 #pragma unroll
-      for (int k = 0; k < K; k++) xi[j][k] += P.A[j][k] * (aj * bpi[k]);
+      for (int k = 0; k < K; k++) xi[(j * K + k) * kFbThreads] += P.A[j][k] * (aj * bpi[k]);
     }
   }
   double *xo = xi_sum + (size_t)K * K * w;
 #pragma unroll
   for (int j = 0; j < K; j++)
 #pragma unroll
-    for (int k = 0; k < K; k++) xo[j * K + k] = xi[j][k];               // [from][to]
+    for (int k = 0; k < K; k++) xo[j * K + k] = xi[(j * K + k) * kFbThreads];   // [from][to]
 }
 
 // Per-run state of the EM loop (vbhmm_em.m:108-418).
@@ -206,15 +210,14 @@ struct RunState { double L, lastL; int it, done, unstable, pad; };
 template <int K, int DIM>
 struct BatchStats { double Nk1[K], Nk[K], M[K][K] /* [from][to] */, xbar[K][DIM], S[K][DIM][DIM]; };
 
+// Block per run: the raw sums of vbhmm_em.m:158-246 (moments about the current means, as k_fb_moments) in a fixed order.
 template <int K, int DIM>
 __global__ void __launch_bounds__(kBatchThreads)
-k_batch_update(int R, int Wn, int N, int maxT, const int *__restrict__ wstart, const int *__restrict__ seq_of,
-               const int *__restrict__ Tn, const double *__restrict__ X, const double *__restrict__ gamma,
-               const double *__restrict__ xi_sum, const double *__restrict__ phi,
-               const FbPar<K, DIM> *__restrict__ pars, const PreOut<K> *__restrict__ pre, BatchPrior pr,
-               VarPar<K, DIM> *__restrict__ vp, BatchStats<K, DIM> *__restrict__ stats, RunState *__restrict__ state,
-               unsigned char *__restrict__ done, double *__restrict__ LLs, int ld, int max_iter, double min_diff,
-               int *__restrict__ n_left) {
+k_batch_sums(int Wn, int N, int maxT, const int *__restrict__ wstart, const int *__restrict__ seq_of,
+             const int *__restrict__ Tn, const double *__restrict__ X, const double *__restrict__ gamma,
+             const double *__restrict__ xi_sum, const double *__restrict__ phi,
+             const FbPar<K, DIM> *__restrict__ pars, const unsigned char *__restrict__ done,
+             double *__restrict__ sums) {
   using L = MomLayout<K, DIM>;
   const int r = blockIdx.x;
   if (done[r]) return;
@@ -260,7 +263,6 @@ k_batch_update(int R, int Wn, int N, int maxT, const int *__restrict__ wstart, c
   }
   // block reduction in a fixed order
   __shared__ double sh[kBatchThreads / 32][L::total];
-  __shared__ double s[L::total];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int v = 0; v < L::total; v++) {
@@ -273,10 +275,22 @@ k_batch_update(int R, int Wn, int N, int maxT, const int *__restrict__ wstart, c
   for (int v = threadIdx.x; v < L::total; v += kBatchThreads) {
     double a = 0.0;
     for (int q = 0; q < kBatchThreads / 32; q++) a += sh[q][v];
-    s[v] = a;
+    sums[(size_t)L::total * r + v] = a;
   }
-  __syncthreads();
-  if (threadIdx.x != 0) return;
+}
+
+// Thread per run: normalisation, lower bound, convergence test, M-step.
+template <int K, int DIM>
+__global__ void __launch_bounds__(kBatchThreads)
+k_batch_update(int R, const double *__restrict__ sums, const FbPar<K, DIM> *__restrict__ pars,
+               const PreOut<K> *__restrict__ pre, BatchPrior pr, VarPar<K, DIM> *__restrict__ vp,
+               BatchStats<K, DIM> *__restrict__ stats, RunState *__restrict__ state, unsigned char *__restrict__ done,
+               double *__restrict__ LLs, int ld, int max_iter, double min_diff, int *__restrict__ n_left) {
+  using L = MomLayout<K, DIM>;
+  const int r = blockIdx.x * kBatchThreads + threadIdx.x;
+  if (r >= R || done[r]) return;
+  const FbPar<K, DIM> &P = pars[r];
+  const double *s = sums + (size_t)L::total * r;
 
   // ---- normalisation (vbhmm_em.m:161-246), as k_fb_moments_finish
   BatchStats<K, DIM> &B = stats[r];
@@ -400,7 +414,7 @@ struct vbhmm_batch {
   vbhmm_data *data = nullptr;
   int R = 0, K = 0, Wn = 0;
   BatchPrior prior{};
-  Buf run_of, seq_of, wstart, vp, par, pre, stats, state, done, LLs, gamma, xi, phi, nleft;
+  Buf run_of, seq_of, wstart, vp, par, pre, stats, sums, state, done, LLs, gamma, xi, phi, nleft;
   int ld = 0;
   int *h_left = nullptr;   // pinned
   size_t vp_bytes = 0, stats_bytes = 0;
@@ -416,6 +430,7 @@ int batch_alloc(vbhmm_batch *b) {
   CU(b->par.ensure(sizeof(FbPar<K, DIM>) * (size_t)b->R));
   CU(b->pre.ensure(sizeof(PreOut<K>) * (size_t)b->R));
   CU(b->stats.ensure(sizeof(BatchStats<K, DIM>) * (size_t)b->R));
+  CU(b->sums.ensure(sizeof(double) * MomLayout<K, DIM>::total * (size_t)b->R));
   b->vp_bytes = sizeof(VarPar<K, DIM>);
   b->stats_bytes = sizeof(BatchStats<K, DIM>);
   return VBHEM_OK;
@@ -427,14 +442,19 @@ int batch_pass(vbhmm_batch *b, int max_iter, double min_diff) {
   const int R = b->R, Wn = b->Wn;
   k_batch_prepass<K, DIM><<<(R + 127) / 128, 128, 0, h->st>>>(R, b->done.as<unsigned char>(), b->vp.as<VarPar<K, DIM>>(),
                                                            b->par.as<FbPar<K, DIM>>(), b->pre.as<PreOut<K>>());
-  k_fb_batch<K, DIM><<<(Wn + kFbThreads - 1) / kFbThreads, kFbThreads, 0, h->st>>>(
+  const size_t smem = sizeof(double) * K * K * kFbThreads;
+  cudaFuncSetAttribute(k_fb_batch<K, DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_fb_batch<K, DIM><<<(Wn + kFbThreads - 1) / kFbThreads, kFbThreads, smem, h->st>>>(
       b->par.as<FbPar<K, DIM>>(), b->done.as<unsigned char>(), Wn, h->N, h->maxT, b->run_of.as<int>(),
       b->seq_of.as<int>(), h->Tn.as<int>(), h->X.as<double>(), b->gamma.as<double>(), b->xi.as<double>(),
       b->phi.as<double>());
-  k_batch_update<K, DIM><<<R, kBatchThreads, 0, h->st>>>(
-      R, Wn, h->N, h->maxT, b->wstart.as<int>(), b->seq_of.as<int>(), h->Tn.as<int>(), h->X.as<double>(),
-      b->gamma.as<double>(), b->xi.as<double>(), b->phi.as<double>(), b->par.as<FbPar<K, DIM>>(), b->pre.as<PreOut<K>>(),
-      b->prior, b->vp.as<VarPar<K, DIM>>(), b->stats.as<BatchStats<K, DIM>>(), b->state.as<RunState>(),
+  k_batch_sums<K, DIM><<<R, kBatchThreads, 0, h->st>>>(
+      Wn, h->N, h->maxT, b->wstart.as<int>(), b->seq_of.as<int>(), h->Tn.as<int>(), h->X.as<double>(),
+      b->gamma.as<double>(), b->xi.as<double>(), b->phi.as<double>(), b->par.as<FbPar<K, DIM>>(),
+      b->done.as<unsigned char>(), b->sums.as<double>());
+  k_batch_update<K, DIM><<<(R + kBatchThreads - 1) / kBatchThreads, kBatchThreads, 0, h->st>>>(
+      R, b->sums.as<double>(), b->par.as<FbPar<K, DIM>>(), b->pre.as<PreOut<K>>(), b->prior,
+      b->vp.as<VarPar<K, DIM>>(), b->stats.as<BatchStats<K, DIM>>(), b->state.as<RunState>(),
       b->done.as<unsigned char>(), b->LLs.as<double>(), b->ld, max_iter, min_diff, b->nleft.as<int>());
   return VBHEM_OK;
 }
@@ -461,7 +481,7 @@ extern "C" {
 int vbhmm_batch_free(vbhmm_batch_t *b) {
   if (!b) return VBHEM_OK;
   if (b->data) cudaSetDevice(b->data->device);
-  Buf *all[] = {&b->run_of, &b->seq_of, &b->wstart, &b->vp, &b->par, &b->pre, &b->stats, &b->state, &b->done, &b->LLs,
+  Buf *all[] = {&b->run_of, &b->seq_of, &b->wstart, &b->vp, &b->par, &b->pre, &b->stats, &b->sums, &b->state, &b->done, &b->LLs,
                 &b->gamma, &b->xi, &b->phi, &b->nleft};
   for (Buf *x : all) x->release();
   if (b->h_left) cudaFreeHost(b->h_left);
