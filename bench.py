@@ -356,9 +356,26 @@ def main():
         # (b) host mirror: statistics D2H, M-step and lower bound in numpy (h3m.vbhem_h3m_c_step_fc)
         run = h3m.vbhem_h3m_c_step_fc({k: v for k, v in hyp.items()}, bs, opt)
         check(L.vbhem_set_profile(bs._h, 1))
+        # (c) SURVEY 8(d): the E-step again with the centres after 5 EM iterations (sharper responsibilities)
+        bs.em_begin({k: v for k, v in hyp.items()}, opt)
+        bs.em_run(tau, 5, 0.0)
+        late = []
+        for _ in range(4):
+            flush.fill_(1)
+            bs.em_estep(tau)
+            bs.synchronize()
+            t = (C.c_double * 8)()
+            check(L.vbhem_last_timings(bs._h, t))
+            late.append(list(t))
+        late = np.median(np.array(late[1:]), axis=0)
+        late_counters = bs.counters()
         vbhem_iter = dict(ms=1e3 * t_dev, iters=int(dev["iters"]), LL_first=float(dev["LogLs"][0]),
                           LL_last=float(dev["LogLs"][-1]), host_mirror_ms=run["ms_per_iter"],
                           LL_last_host_mirror=float(run["LogLs"][-1]),
+                          estep_after_5_iters=dict(estep_ms=float(late[5]), first_pass_ms=float(late[1]),
+                                                   second_pass_ms=float(late[3]),
+                                                   active_pairs=int(late_counters["active_pairs"]),
+                                                   fallback_pairs=int(late_counters["general_pairs"])),
                           note="ms = wall time of vbhem_em_run / E-steps taken: fused E-step, lower bound, M-step and "
                                "convergence test through the C ABI with the centre hyper-parameters resident in HBM; "
                                "host_mirror_ms = median iteration of h3m.vbhem_h3m_c_step_fc (statistics D2H, numpy "

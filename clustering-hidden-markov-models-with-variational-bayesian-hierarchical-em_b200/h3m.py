@@ -125,6 +125,77 @@ def vbhemh3m_lb(Lt1, Lt7, Nj, pre: dict, hyp: dict, opt: dict, covmode: str = "f
     return float(LB), dict(Lt1=Lt1, Lt2=Lt2, Lt3=Lt3, Lt4=Lt4, Lt5=Lt5, Lt6=Lt6, Lt7=Lt7, Lt8=Lt8, Lt9=Lt9, Lt10=Lt10)
 
 
+HYPS_MAX = dict(alpha0=1.0686e+13, eta0=1.0686e+13, epsilon0=1.0686e+13, v0=1e4, lambda0=1.0686e+13, W0=1.0686e+13)
+HYPS_MIN = dict(alpha0=1.0686e-13, eta0=1.0686e-13, epsilon0=1.0686e-13, v0=None, lambda0=1.0686e-13, W0=1.0686e-13)
+"""vbhem_h3m_cluster.m:182-200 (``v0``'s minimum is exp(-20) + D - 1)."""
+
+
+def vbhem_clip_hyps(opt: dict) -> tuple[dict, dict]:
+    """vbhem_clip_hyps.m:1-86: hyper-parameters clipped to [hyps_min, hyps_max]; clipped[name][i] = +1 / -1 / 0."""
+    d = len(np.atleast_1d(opt["m0"]))
+    hmax = dict(HYPS_MAX, **opt.get("hyps_max", {}))
+    hmin = dict(HYPS_MIN, **opt.get("hyps_min", {}))
+    if hmin.get("v0") is None:
+        hmin["v0"] = 2.0612e-09 + d - 1
+    out, clipped = dict(opt), {}
+    for name in hmax:
+        val = np.atleast_1d(np.asarray(opt[name], float)).copy()
+        c = np.zeros(val.size, int)
+        hi, lo = val >= hmax[name], val <= hmin[name]
+        val[hi], c[hi] = hmax[name], +1
+        val[lo], c[lo] = hmin[name], -1
+        out[name] = float(val[0]) if np.ndim(opt[name]) == 0 else val
+        clipped[name] = c
+    return out, clipped
+
+
+def vbhemh3m_lb_deriv(pre: dict, hyp: dict, opt: dict, covmode: str = "full", clipped: dict | None = None) -> dict:
+    """vbhemh3m_lb.m:202-343: derivatives of the lower bound with respect to the prior hyper-parameters at fixed
+    variational posteriors (``hyp`` / ``pre`` = the centre hyper-parameters and pre-pass results of the E-step the
+    bound belongs to), then with respect to their transformed versions (the optimiser's coordinates):
+    d_logalpha0, d_logeta0, d_logepsilon0, d_logv0D1, d_sqrtv0D1, d_loglambda0, d_sqrtlambda0, d_sqrtW0inv, d_logW0, d_m0."""
+    K, S = hyp["eta"].shape
+    d = hyp["m"].shape[2]
+    a0, e0, p0 = float(opt["alpha0"]), float(opt["eta0"]), float(opt["epsilon0"])
+    lam0, v0 = float(opt["lambda0"]), float(opt["v0"])
+    m0 = np.asarray(opt["m0"], float).reshape(d)
+    W0m, iid = _W0(opt, d)
+    W0inv = np.diag(1.0 / np.diag(W0m))
+    logdetW0inv = np.log(np.diag(W0inv)).sum()
+    ii = np.arange(1, d + 1, dtype=float)
+    lam, v = hyp["lam"], hyp["v"]
+    W = hyp["W"] if covmode == "full" else np.einsum("ksi,ij->ksij", hyp["W"], np.eye(d))
+    df = hyp["m"] - m0
+    mWm = np.einsum("ksi,ksij,ksj->ks", df, W, df)
+    D = {}
+    D["alpha0"] = np.atleast_1d(K * psi(K * a0) - K * psi(a0) + pre["logOmega"].sum())                        # :205-209
+    D["eta0"] = np.atleast_1d(K * (S * psi(S * e0) - S * psi(e0)) + pre["logPi"].sum())                        # :213-217
+    D["epsilon0"] = np.atleast_1d(K * S * (S * psi(S * p0) - S * psi(p0)) + pre["logA"].sum())                 # :221-225
+    d_logB0_v0 = 0.5 * logdetW0inv - (d / 2) * np.log(2) - 0.5 * psi(0.5 * (v0 + 1 - ii)).sum()
+    D["v0"] = np.atleast_1d(K * S * d_logB0_v0 + 0.5 * pre["logLambdaTilde"].sum())                           # :229-230
+    D["lambda0"] = np.atleast_1d(0.5 * (d / lam0 - d / lam - v * mWm).sum())                                   # :233-241
+    diagW = np.diagonal(W, axis1=-2, axis2=-1)                                                                 # [K,S,d]
+    if iid:                                                                                                    # :244-267
+        w0inv = W0inv[0, 0]
+        D["W0"] = np.atleast_1d(K * S * (-0.5 * v0 * d * w0inv) - 0.5 * (-v * w0inv ** 2 * diagW.sum(-1)).sum())
+        myW0 = np.atleast_1d(1.0 / w0inv)
+    else:                                                                                                      # :270-293
+        w0inv = np.diag(W0inv)
+        D["W0"] = K * S * (-0.5 * v0 * w0inv) - 0.5 * (-(v[..., None]) * w0inv ** 2 * diagW).sum((0, 1))
+        myW0 = 1.0 / w0inv
+    D["m0"] = lam0 * np.einsum("ks,ksij,ksj->i", v, W, df)                                                     # :300-309
+    for name, c in (clipped or {}).items():                                                                    # :312-327
+        if name in D:
+            g = D[name]
+            for i in range(min(len(c), len(g))):
+                if (c[i] == +1 and g[i] > 0) or (c[i] == -1 and g[i] < 0):
+                    g[i] = 0.0
+    return dict(d_logalpha0=D["alpha0"] * a0, d_logeta0=D["eta0"] * e0, d_logepsilon0=D["epsilon0"] * p0,      # :330-339
+                d_logv0D1=D["v0"] * (v0 - d + 1), d_sqrtv0D1=D["v0"] * 2 * np.sqrt(v0 - d + 1),
+                d_loglambda0=D["lambda0"] * lam0, d_sqrtlambda0=D["lambda0"] * 2 * np.sqrt(lam0),
+                d_sqrtW0inv=D["W0"] * myW0 ** 1.5 * (-2), d_logW0=D["W0"] * myW0, d_m0=D["m0"], raw=D)
+
+
 def vbhem_h3m_c_step_fc(h3m_r: dict, base, vbhemopt: dict, covmode: str = "full", estep=None, verbose: int = 0,
                         device_loop: bool = False):
     """One EM run from the centre hyper-parameters ``h3m_r`` (vbhem_h3m_c_step_fc.m:115-433).
@@ -162,7 +233,7 @@ def vbhem_h3m_c_step_fc(h3m_r: dict, base, vbhemopt: dict, covmode: str = "full"
 
     run = estep or default_estep
     LogLs, lastL, it, unstable, times = [], -np.finfo(float).max, 0, False, []
-    fin = None
+    fin, dLL = None, None
     while True:
         t0 = time.perf_counter()
         fin = run(hyp, tau)                                               # E-step (GPU)
@@ -175,6 +246,10 @@ def vbhem_h3m_c_step_fc(h3m_r: dict, base, vbhemopt: dict, covmode: str = "full"
             do_break = True
         if np.isnan(L):                                                   # :338-354
             do_break, unstable, L = True, True, -np.inf
+        if do_break and opt.get("calc_LLderiv"):                          # before the last M-step (:356-369)
+            dLL = vbhemh3m_lb_deriv(fin["pre"], hyp, opt, covmode, opt.get("hyp_clipped"))
+            if unstable:
+                dLL = {k: (np.full_like(np.asarray(v, float), np.nan) if k != "raw" else v) for k, v in dLL.items()}
         if do_break and unstable:
             LogLs.append(L)
             break
@@ -189,7 +264,7 @@ def vbhem_h3m_c_step_fc(h3m_r: dict, base, vbhemopt: dict, covmode: str = "full"
             print(f"iter {it}: L={L:.10g}")
         if do_break:
             break
-    return dict(hyp=hyp, LogLs=np.array(LogLs), LL=LogLs[-1], iters=it, unstable=unstable, Nj=fin["Nj"],
+    return dict(hyp=hyp, LogLs=np.array(LogLs), LL=LogLs[-1], iters=it, unstable=unstable, Nj=fin["Nj"], dLL=dLL,
                 ms_per_iter=1e3 * float(np.median(times)) if times else float("nan"))
 
 
@@ -318,3 +393,74 @@ def vbhem_h3m_cluster(hmms, K, S, vbhemopt: dict | None = None, covmode: str = "
     out["groups"] = [np.flatnonzero(out["label"] == j) for j in range(out["K"])]
     out["group_size"] = np.array([len(x) for x in out["groups"]])
     return out
+
+
+# ----------------------------------------------------------------------------- hyper-parameter learning
+def vbhem_get_hypinfo(learn_hyps, opt: dict) -> list:
+    """vbhem_get_hypinfo.m:1-89: for every learnable hyper-parameter its option name, the name of its derivative in
+    ``vbhemh3m_lb_deriv`` and the transform between the optimiser's coordinate and the hyper-parameter."""
+    d = len(np.atleast_1d(opt["m0"]))
+    nW = np.atleast_1d(opt["W0"]).size
+    table = {
+        "alpha0": ("alpha0", "d_logalpha0", np.exp, np.log, 1),
+        "eta0": ("eta0", "d_logeta0", np.exp, np.log, 1),
+        "epsilon0": ("epsilon0", "d_logepsilon0", np.exp, np.log, 1),
+        "v0": ("v0", "d_logv0D1", lambda x: np.exp(x) + d - 1, lambda x: np.log(x - d + 1), 1),
+        "lambda0": ("lambda0", "d_loglambda0", np.exp, np.log, 1),
+        "W0": ("W0", "d_sqrtW0inv", lambda x: x ** -2.0, lambda x: 1.0 / np.sqrt(x), nW),
+        "W0isqrt": ("W0", "d_sqrtW0inv", lambda x: x ** -2.0, lambda x: 1.0 / np.sqrt(x), nW),
+        "W0log": ("W0", "d_logW0", np.exp, np.log, nW),
+        "m0": ("m0", "d_m0", lambda x: x, lambda x: x, d),
+    }
+    out = []
+    for name in learn_hyps:
+        if name not in table:
+            raise ValueError("bad value of learn_hyp")
+        o, dn, tr, inv, dims = table[name]
+        out.append(dict(optname=o, derivname=dn, hyptrans=tr, hypinvtrans=inv, hypdims=dims))
+    return out
+
+
+def vbhem_h3m_c_hyp(h3m_init: dict, base, vbhemopt: dict, covmode: str = "full", max_evals: int = 100) -> dict:
+    """[h3m, L] = vbhem_h3m_c_hyp(h3m_b, vbopt)  (vbhem_h3m_c_hyp.m:1-210): learn the prior hyper-parameters by
+    maximising the converged lower bound.  Every evaluation of the objective is one EM run (``vbhem_h3m_c_step_fc``,
+    E-steps on the GPU) from the SAME initial centres ``h3m_init`` (initmode 'inith3m', vbhemhmm_init.m:428-455) under
+    the candidate hyper-parameters, its value -LL and its gradient the derivatives of the bound at the breaking pass
+    (``vbhemh3m_lb_deriv``) in the transformed coordinates of ``vbhem_get_hypinfo``.
+
+    ``learn_hyps`` = 1 selects {alpha0, eta0, epsilon0, v0, lambda0, W0, m0} (:10-12).  The reference minimises with
+    ``minimize_new`` (L-BFGS, 100 function evaluations, :38-53), which is not part of its repository's numerics that
+    can be pinned here; scipy's L-BFGS-B with the same budget stands in.  Returns the final run under the optimal
+    hyper-parameters plus ``learn_hyps = dict(opt_transhyp, opt_L, vbopt, evals)``."""
+    from scipy.optimize import minimize
+    opt = dict(vbhemopt)
+    lh = opt.get("learn_hyps", 1)
+    names = ["alpha0", "eta0", "epsilon0", "v0", "lambda0", "W0", "m0"] if not isinstance(lh, (list, tuple)) else list(lh)
+    info = vbhem_get_hypinfo(names, opt)
+
+    def set_vbopt(X):
+        o, i = dict(opt), 0
+        for h in info:
+            val = h["hyptrans"](np.asarray(X[i:i + h["hypdims"]], float))
+            o[h["optname"]] = float(val[0]) if h["hypdims"] == 1 and h["optname"] not in ("m0", "W0") else val
+            i += h["hypdims"]
+        return o
+
+    X0 = np.concatenate([np.atleast_1d(h["hypinvtrans"](np.asarray(opt[h["optname"]], float))).ravel() for h in info])
+    evals = []
+
+    def objective(X):
+        o, clipped = vbhem_clip_hyps(set_vbopt(X))
+        run = vbhem_h3m_c_step_fc(h3m_init, base, dict(o, calc_LLderiv=1, hyp_clipped=clipped), covmode)
+        g = -np.concatenate([np.atleast_1d(run["dLL"][h["derivname"]]).ravel() for h in info])
+        evals.append(run["LL"])
+        if not np.isfinite(run["LL"]):
+            return 1e300, np.zeros_like(g)
+        return -run["LL"], np.where(np.isfinite(g), g, 0.0)
+
+    res = minimize(objective, X0, jac=True, method="L-BFGS-B", options=dict(maxfun=int(max_evals), maxiter=int(max_evals)))
+    opt2, _ = vbhem_clip_hyps(set_vbopt(res.x))
+    final = vbhem_h3m_c_step_fc(h3m_init, base, opt2, covmode)
+    final["learn_hyps"] = dict(opt_transhyp=res.x, opt_L=float(-res.fun), vbopt=opt2, evals=np.array(evals),
+                               hypnames=[h["optname"] for h in info])
+    return final
