@@ -271,9 +271,11 @@ def vbhem_h3m_c_step_fc(h3m_r: dict, base, vbhemopt: dict, covmode: str = "full"
 # ----------------------------------------------------------------------------- user entry: (K, S) model selection
 CLUSTER_DEFAULTS = dict(alpha0=1.0, eta0=1.0, epsilon0=1.0, m0=(256.0, 192.0), W0=0.005, lambda0=1.0, v0=5.0,
                         trials=100, max_iter=200, minDiff=1e-5, Nv=100.0, tau=10, use_post=True, seed=None,
-                        initmode="baseem")
+                        initmode="baseem", learn_hyps=0)
 """vbhem_h3m_cluster.m:141-179 (``initmode`` 'auto' of the reference tries 'baseem', 'gmmNew' and 'wtkmeans';
-only 'baseem' is mirrored, the other two need the Statistics Toolbox)."""
+only 'baseem' is mirrored, the other two need the Statistics Toolbox).  ``learn_hyps`` defaults to 1 in the
+reference (:179); here it is opt-in: 1 or a list of names runs ``vbhem_h3m_c_hyp`` on the best trial of every
+(K, S) candidate (the reference optimises every distinct trial solution, vbhem_h3m_c.m:105-150)."""
 
 
 def stack_h3ms(models: list) -> tuple[dict, np.ndarray]:
@@ -376,6 +378,16 @@ def vbhem_h3m_cluster(hmms, K, S, vbhemopt: dict | None = None, covmode: str = "
                 LL[ki, si, t] = run["LogLs"][g][-1]
         best_t = LL.argmax(2)                                                # vbhem_h3m_c.m: best trial
         LL_ks = np.take_along_axis(LL, best_t[:, :, None], 2)[:, :, 0]
+        learnt = {}
+        if opt["learn_hyps"]:                                                # vbhem_h3m_c.m:105-150
+            for ki in range(len(Ks)):
+                for si in range(len(Ss)):
+                    gi = cand.index((ki, si, int(best_t[ki, si])))
+                    start = _slice_h3m(run["hyp"], group == gi, Ss[si])
+                    res = vbhem_h3m_c_hyp(start, bs, opt, covmode)
+                    if np.isfinite(res["LL"]) and res["LL"] > LL_ks[ki, si]:
+                        learnt[(ki, si)] = res
+                        LL_ks[ki, si] = res["LL"]
         LL_S = LL_ks + gammaln(np.array(Ss) + 1.0)[None]                     # vbhem_h3m_cluster.m:327-331
         best_s = LL_S.argmax(1)
         LL_K = LL_ks[np.arange(len(Ks)), best_s] + gammaln(np.array(Ks) + 1.0)   # :279-283 (the run's own LL)
@@ -383,11 +395,16 @@ def vbhem_h3m_cluster(hmms, K, S, vbhemopt: dict | None = None, covmode: str = "
         bs_i = int(best_s[bk])
         g = cand.index((bk, bs_i, int(best_t[bk, bs_i])))
         chosen = _slice_h3m(run["hyp"], group == g, Ss[bs_i])
+        if (bk, bs_i) in learnt:
+            chosen = learnt[(bk, bs_i)]["hyp"]
+            opt = dict(learnt[(bk, bs_i)]["learn_hyps"]["vbopt"])
         last = bs.estep_hyp(chosen, int(opt["tau"]))
     out = dict(K=Ks[bk], S=Ss[bs_i], LL=float(LL_ks[bk, bs_i]), hyp=chosen, Z=last["zhat"], L_elbo=last["L_elbo"],
                Nj=chosen["alpha"] - float(opt["alpha0"]), iters=int(run["iters"][g]), model_LL=LL_K,
                model_k=np.array(Ks), model_bestK=Ks[bk], model_LL_S=LL_S, model_S=np.array(Ss), model_bestS=Ss[bs_i],
                trials_LL=LL, vbhemopt=opt)
+    if (bk, bs_i) in learnt:
+        out["learn_hyps"] = learnt[(bk, bs_i)]["learn_hyps"]
     out.update(h3m_parameters(chosen, covmode))
     out["label"] = out["Z"].argmax(1)
     out["groups"] = [np.flatnonzero(out["label"] == j) for j in range(out["K"])]

@@ -89,3 +89,17 @@ def test_hyper_parameter_learning_raises_the_bound():
     assert abs(info["evals"][0] - plain["LL"]) <= 1e-9 * abs(plain["LL"])      # first evaluation = the given hyps
     assert info["hypnames"] == ["alpha0", "eta0", "epsilon0", "v0", "lambda0", "W0", "m0"]
     assert info["vbopt"]["v0"] > 1.0 and np.all(np.asarray(info["vbopt"]["W0"]) > 0)
+
+
+@pytest.mark.gpu
+def test_cluster_with_learn_hyps():
+    """vbhem_h3m_cluster(..., learn_hyps=[...]): the chosen model's bound is at least the fixed-hyps one and the
+    learnt hyper-parameters come back in vbhemopt."""
+    base, lab = synth.make_base_set(60, S=2, d=2, C=2, seed=21, Nv=20.0)
+    common = dict(trials=3, seed=7, Nv=20.0, max_iter=50)
+    fixed = h3m.vbhem_h3m_cluster(base, [1, 2], 2, common)
+    learnt = h3m.vbhem_h3m_cluster(base, [1, 2], 2, dict(common, learn_hyps=["alpha0", "v0", "lambda0"]))
+    assert learnt["LL"] >= fixed["LL"] and "learn_hyps" in learnt
+    assert learnt["learn_hyps"]["hypnames"] == ["alpha0", "v0", "lambda0"]
+    assert learnt["vbhemopt"]["v0"] != fixed["vbhemopt"]["v0"]
+    assert learnt["Z"].shape == (60, learnt["K"])
