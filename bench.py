@@ -155,15 +155,20 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--slices", type=int, default=6, help="slices of the streamed (e2e) E-step")
-    ap.add_argument("--workload", default="estep", choices=["estep", "grid", "fb"],
+    ap.add_argument("--workload", default="estep", choices=["estep", "grid", "fb", "exprmt1"],
                     help="estep = BASELINE configs[2] (the metric's workload, default); grid = configs[3], the (K,S) "
                          "model-selection grid K=1..16 x S=1..8 over 20k bases in one batched call; fb = configs[4], "
-                         "the VB-HMM forward-backward pass over 1M sequences of length 50")
+                         "the VB-HMM forward-backward pass over 1M sequences of length 50; exprmt1 = configs[0], the "
+                         "reference's synthetic experiment end to end (learn 40 HMMs, cluster over K=1..6 x S=1..5)")
+    ap.add_argument("--trials", type=int, default=20, help="--workload exprmt1: initialisations per (K,S) candidate")
     a = ap.parse_args()
     K, S, d, tau = a.centres, a.states, a.dim, a.tau
     if a.workload == "fb":
         from bench_fb import main_fb
         return main_fb(a)
+    if a.workload == "exprmt1":
+        from bench_exprmt1 import main_exprmt1
+        return main_exprmt1(a)
     if a.cpu_worker:
         return cpu_worker(a.cpu_worker, K, S, d, tau, a.seed)
     grid = a.workload == "grid"

@@ -282,18 +282,27 @@ def stack_h3ms(models: list) -> tuple[dict, np.ndarray]:
     """Several H3Ms' centre hyper-parameter dicts -> one dict padded to the largest state count, plus ``group``
     (model index of every centre): the argument of ``BaseSet.em_begin(..., group=...)`` / ``estep_hyp``."""
     maxS = max(h["eta"].shape[1] for h in models)
-    parts, group = [], []
+    Kt = sum(h["eta"].shape[0] for h in models)
+    first = models[0]
+    out = dict(Sr=np.zeros(Kt, np.int32), alpha=np.zeros(Kt), eta=np.zeros((Kt, maxS)), epsilon=np.zeros((Kt, maxS, maxS)),
+               m=np.zeros((Kt, maxS) + np.shape(first["m"])[2:]), W=np.zeros((Kt, maxS) + np.shape(first["W"])[2:]),
+               v=np.zeros((Kt, maxS)), lam=np.zeros((Kt, maxS)))
+    group = np.zeros(Kt, np.int32)
+    j = 0
     for g, h in enumerate(models):
         K, S = h["eta"].shape
-        pad = maxS - S
-        parts.append(dict(Sr=np.asarray(h.get("Sr", np.full(K, S)), np.int32), alpha=np.asarray(h["alpha"], float),
-                          eta=np.pad(h["eta"], ((0, 0), (0, pad))),
-                          epsilon=np.pad(h["epsilon"], ((0, 0), (0, pad), (0, pad))),
-                          m=np.pad(h["m"], ((0, 0), (0, pad), (0, 0))),
-                          W=np.pad(h["W"], ((0, 0), (0, pad)) + ((0, 0),) * (np.ndim(h["W"]) - 2)),
-                          v=np.pad(h["v"], ((0, 0), (0, pad))), lam=np.pad(h["lam"], ((0, 0), (0, pad)))))
-        group += [g] * K
-    return {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}, np.array(group, np.int32)
+        sl = slice(j, j + K)
+        out["Sr"][sl] = h.get("Sr", S)
+        out["alpha"][sl] = h["alpha"]
+        out["eta"][sl, :S] = h["eta"]
+        out["epsilon"][sl, :S, :S] = h["epsilon"]
+        out["m"][sl, :S] = h["m"]
+        out["W"][sl, :S] = h["W"]
+        out["v"][sl, :S] = h["v"]
+        out["lam"][sl, :S] = h["lam"]
+        group[sl] = g
+        j += K
+    return out, group
 
 
 def _slice_h3m(hyp: dict, sel: np.ndarray, S: int) -> dict:
@@ -363,15 +372,18 @@ def vbhem_h3m_cluster(hmms, K, S, vbhemopt: dict | None = None, covmode: str = "
     Ks, Ss = [int(k) for k in np.atleast_1d(K)], [int(s) for s in np.atleast_1d(S)]
     trials = int(opt["trials"])
     cand, models = [], []
+    clock = [time.perf_counter()]
     for ki, k in enumerate(Ks):
         for si, s in enumerate(Ss):
             for t in range(trials):
                 cand.append((ki, si, t))
                 models.append(synth.init_centres_baseem(base, k, s, seed=int(opt["seed"]) + t + 1, opt=opt))
     hyp, group = stack_h3ms(models)
+    clock.append(time.perf_counter())
     with BaseSet(base, device=device) as bs:
         bs.em_begin(hyp, opt, group=group)
         run = bs.em_run_groups(int(opt["tau"]), int(opt["max_iter"]), float(opt["minDiff"]))
+        clock.append(time.perf_counter())
         LL = np.full((len(Ks), len(Ss), trials), -np.inf)
         for g, (ki, si, t) in enumerate(cand):
             if len(run["LogLs"][g]) and not run["unstable"][g]:
@@ -402,7 +414,8 @@ def vbhem_h3m_cluster(hmms, K, S, vbhemopt: dict | None = None, covmode: str = "
     out = dict(K=Ks[bk], S=Ss[bs_i], LL=float(LL_ks[bk, bs_i]), hyp=chosen, Z=last["zhat"], L_elbo=last["L_elbo"],
                Nj=chosen["alpha"] - float(opt["alpha0"]), iters=int(run["iters"][g]), model_LL=LL_K,
                model_k=np.array(Ks), model_bestK=Ks[bk], model_LL_S=LL_S, model_S=np.array(Ss), model_bestS=Ss[bs_i],
-               trials_LL=LL, vbhemopt=opt)
+               trials_LL=LL, vbhemopt=opt,
+               seconds=dict(init=clock[1] - clock[0], em_loop=clock[2] - clock[1], passes=int(max(run["iters"])) + 1))
     if (bk, bs_i) in learnt:
         out["learn_hyps"] = learnt[(bk, bs_i)]["learn_hyps"]
     out.update(h3m_parameters(chosen, covmode))
