@@ -378,25 +378,36 @@ def vbhem_h3m_cluster(hmms, K, S, vbhemopt: dict | None = None, covmode: str = "
             for t in range(trials):
                 cand.append((ki, si, t))
                 models.append(synth.init_centres_baseem(base, k, s, seed=int(opt["seed"]) + t + 1, opt=opt))
-    hyp, group = stack_h3ms(models)
     clock.append(time.perf_counter())
+    N = base["mu"].shape[0]
     with BaseSet(base, device=device) as bs:
-        bs.em_begin(hyp, opt, group=group)
-        run = bs.em_run_groups(int(opt["tau"]), int(opt["max_iter"]), float(opt["minDiff"]))
-        clock.append(time.perf_counter())
+        # batches of at most 4096 H3Ms (vbhem_em_begin's limit) and 2e8 (base, centre) pairs (3.2 GB of L_elbo + z_hat)
+        finals, iters_all = [None] * len(models), np.zeros(len(models), int)
         LL = np.full((len(Ks), len(Ss), trials), -np.inf)
-        for g, (ki, si, t) in enumerate(cand):
-            if len(run["LogLs"][g]) and not run["unstable"][g]:
-                LL[ki, si, t] = run["LogLs"][g][-1]
+        lo = 0
+        while lo < len(models):
+            hi, ncen = lo, 0
+            while hi < len(models) and hi - lo < 4096 and (hi == lo or (ncen + models[hi]["eta"].shape[0]) * N <= 2e8):
+                ncen += models[hi]["eta"].shape[0]
+                hi += 1
+            hyp, group = stack_h3ms(models[lo:hi])
+            bs.em_begin(hyp, opt, group=group)
+            run = bs.em_run_groups(int(opt["tau"]), int(opt["max_iter"]), float(opt["minDiff"]))
+            for g in range(hi - lo):
+                ki, si, t = cand[lo + g]
+                if len(run["LogLs"][g]) and not run["unstable"][g]:
+                    LL[ki, si, t] = run["LogLs"][g][-1]
+                finals[lo + g] = _slice_h3m(run["hyp"], group == g, models[lo + g]["eta"].shape[1])
+                iters_all[lo + g] = run["iters"][g]
+            lo = hi
+        clock.append(time.perf_counter())
         best_t = LL.argmax(2)                                                # vbhem_h3m_c.m: best trial
         LL_ks = np.take_along_axis(LL, best_t[:, :, None], 2)[:, :, 0]
         learnt = {}
         if opt["learn_hyps"]:                                                # vbhem_h3m_c.m:105-150
             for ki in range(len(Ks)):
                 for si in range(len(Ss)):
-                    gi = cand.index((ki, si, int(best_t[ki, si])))
-                    start = _slice_h3m(run["hyp"], group == gi, Ss[si])
-                    res = vbhem_h3m_c_hyp(start, bs, opt, covmode)
+                    res = vbhem_h3m_c_hyp(finals[cand.index((ki, si, int(best_t[ki, si])))], bs, opt, covmode)
                     if np.isfinite(res["LL"]) and res["LL"] > LL_ks[ki, si]:
                         learnt[(ki, si)] = res
                         LL_ks[ki, si] = res["LL"]
@@ -406,16 +417,16 @@ def vbhem_h3m_cluster(hmms, K, S, vbhemopt: dict | None = None, covmode: str = "
         bk = int(LL_K.argmax())
         bs_i = int(best_s[bk])
         g = cand.index((bk, bs_i, int(best_t[bk, bs_i])))
-        chosen = _slice_h3m(run["hyp"], group == g, Ss[bs_i])
+        chosen = finals[g]
         if (bk, bs_i) in learnt:
             chosen = learnt[(bk, bs_i)]["hyp"]
             opt = dict(learnt[(bk, bs_i)]["learn_hyps"]["vbopt"])
         last = bs.estep_hyp(chosen, int(opt["tau"]))
     out = dict(K=Ks[bk], S=Ss[bs_i], LL=float(LL_ks[bk, bs_i]), hyp=chosen, Z=last["zhat"], L_elbo=last["L_elbo"],
-               Nj=chosen["alpha"] - float(opt["alpha0"]), iters=int(run["iters"][g]), model_LL=LL_K,
+               Nj=chosen["alpha"] - float(opt["alpha0"]), iters=int(iters_all[g]), model_LL=LL_K,
                model_k=np.array(Ks), model_bestK=Ks[bk], model_LL_S=LL_S, model_S=np.array(Ss), model_bestS=Ss[bs_i],
                trials_LL=LL, vbhemopt=opt,
-               seconds=dict(init=clock[1] - clock[0], em_loop=clock[2] - clock[1], passes=int(max(run["iters"])) + 1))
+               seconds=dict(init=clock[1] - clock[0], em_loop=clock[2] - clock[1], passes=int(iters_all.max()) + 1))
     if (bk, bs_i) in learnt:
         out["learn_hyps"] = learnt[(bk, bs_i)]["learn_hyps"]
     out.update(h3m_parameters(chosen, covmode))

@@ -30,6 +30,7 @@ FB_PORT_SO = os.path.join(HERE, "_build", "libvbhmm_fb_oracle.so")  # oracle/fb_
 FB_GATEWAY_SO = os.path.join(HERE, "_build", "libvbhmm_fb_gateway.so")  # this repo's mex/vbhmm_fb_mex.cpp behind the shim
 GATEWAY_SO = os.path.join(HERE, "_build", "libvbhem_gateway.so")   # this repo's MEX gateway behind the same shim
 FUSED_SO = os.path.join(HERE, "_build", "libvbhem_gateway_fused.so")   # ... and its fused-E-step gateway
+EM_SO = os.path.join(HERE, "_build", "libvbhem_gateway_em.so")         # ... and its whole-EM-run gateway
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -53,7 +54,7 @@ _libs = {}
 
 def _lib(which: str):
     if which not in _libs:
-        path = {"ref": REF_SO, "gateway": GATEWAY_SO, "fused": FUSED_SO, "fb_ref": FB_REF_SO,
+        path = {"ref": REF_SO, "gateway": GATEWAY_SO, "fused": FUSED_SO, "em": EM_SO, "fb_ref": FB_REF_SO,
                 "fb_port": FB_PORT_SO, "fb_gateway": FB_GATEWAY_SO}.get(which, PORT_SO)
         if not os.path.exists(path):
             build()
@@ -138,6 +139,40 @@ def gateway_estep_fused(base: dict, cen: dict, T: int) -> dict:
         lib.shim_last_error_msg.restype = C.c_char_p
         raise RuntimeError(f"{lib.shim_last_error_id().decode()}: {lib.shim_last_error_msg().decode()}")
     return o
+
+
+def gateway_em_run(base: dict, hyp: dict, opt: dict) -> dict:
+    """mex/vbhem_em_run_mex.cpp through the mx shim.  base: packed base dict; hyp: natural centre hyper-parameters
+    (alpha[K], eta[K,S], epsilon[K,S,S] (from,to), m[K,S,d], W[K,S,d,d] | [K,S,d], v, lam, Sr); opt: alpha0, eta0,
+    epsilon0, lambda0, v0, m0, W0, tau, max_iter, minDiff.  Returns the hyper-parameters after the run (natural),
+    LogLs, iters, unstable."""
+    lib = _lib("em")
+    N, maxSb = base["prior"].shape
+    K, r = hyp["eta"].shape
+    d, covmode = base["d"], base["covmode"]
+    al, et, v, lam = (_f64(np.array(hyp[k], float)) for k in ("alpha", "eta", "v", "lam"))
+    eps = _f64(np.transpose(hyp["epsilon"], (0, 2, 1)))                     # [K, to, from] == column-major [from, to, K]
+    m = _f64(np.array(hyp["m"], float))                                      # [K, S, d]     == [d, S, K]
+    W = _f64(np.transpose(hyp["W"], (0, 1, 3, 2))) if covmode else _f64(np.array(hyp["W"], float))
+    hyp0 = _f64(np.array([opt["alpha0"], opt["eta0"], opt["epsilon0"], opt["lambda0"], opt["v0"]], float))
+    m0 = _f64(np.asarray(opt["m0"], float).reshape(d))
+    W0 = _f64(np.atleast_1d(np.asarray(opt["W0"], float)))
+    max_iter = int(opt.get("max_iter", 200))
+    LogLs, info = np.zeros(max_iter + 2), np.zeros(3)
+    fn = lib.shim_em_run
+    fn.restype = C.c_int
+    rc = fn(C.c_int(N), _i(_i32(base["Sb"])), C.c_int(maxSb), C.c_int(d), C.c_int(covmode),
+            _d(_f64(base["prior"])), _d(_f64(base["A"])), _d(_f64(base["mu"])), _d(_f64(base["cov"])),
+            _d(_f64(base["Ntilde"])), C.c_int(K), _i(_i32(hyp["Sr"])), C.c_int(r), _d(al), _d(et), _d(eps), _d(m), _d(W),
+            _d(v), _d(lam), _d(hyp0), _d(m0), _d(W0), C.c_int(W0.size), C.c_int(int(opt["tau"])), C.c_int(max_iter),
+            C.c_double(float(opt.get("minDiff", 1e-5))), _d(LogLs), _d(info))
+    if rc != 0:
+        lib.shim_last_error_id.restype = C.c_char_p
+        lib.shim_last_error_msg.restype = C.c_char_p
+        raise RuntimeError(f"{lib.shim_last_error_id().decode()}: {lib.shim_last_error_msg().decode()}")
+    out = dict(alpha=al, eta=et, epsilon=np.transpose(eps, (0, 2, 1)).copy(), m=m,
+               W=np.transpose(W, (0, 1, 3, 2)).copy() if covmode else W, v=v, lam=lam, Sr=np.array(hyp["Sr"]))
+    return dict(hyp=out, LogLs=LogLs[:int(info[2])].copy(), iters=int(info[0]), unstable=bool(info[1]))
 
 
 def port_estep_pairs(base: dict, cen: dict, T: int, lonly: bool = False) -> dict:

@@ -335,6 +335,51 @@ int shim_estep_fused(int Kb, const int *Sb, int maxSb, int d, int covmode,
   return 0;
 }
 
+/* shim_em_run: the signature of this repo's vbhem_em_run_mex (mex/vbhem_em_run_mex.cpp): base tree + flat
+ * hyper-parameter arrays in, the hyper-parameters after the EM run, LogLs[max_iter + 2] and info[2] out. */
+int shim_em_run(int Kb, const int *Sb, int maxSb, int d, int covmode,
+                const double *prior, const double *A, const double *mu, const double *cov, const double *Ntilde,
+                int Kr, const int *Sr, int maxSr, double *alpha, double *eta, double *eps, double *m, double *W,
+                double *v, double *lam, const double *hyp0 /* alpha0 eta0 epsilon0 lambda0 v0 */, const double *m0,
+                const double *W0, int nW0, int T, int max_iter, double min_diff, double *LogLs, double *info) {
+  const int dd = covmode ? d * d : d;
+  g_jmp_armed = 1;
+  if (setjmp(g_jmp)) { g_jmp_armed = 0; arena_reset(); return 1; }
+  mxArray *hb = make_base_tree(Kb, Sb, maxSb, d, covmode, prior, A, mu, cov);
+  mxArray *sr = mxCreateDoubleMatrix(1, (mwSize)Kr, mxREAL);
+  for (int j = 0; j < Kr; j++) sr->pr[j] = Sr[j];
+  const mxArray *prhs[17];
+  mxArray *plhs[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  prhs[0] = hb;
+  prhs[1] = dbl_scalar((double)maxSb);
+  prhs[2] = dbl_matrix(Kb, 1, Ntilde, Kb, 0);
+  prhs[3] = dbl_matrix(1, Kr, alpha, 1, 0);
+  prhs[4] = dbl_matrix(maxSr, Kr, eta, maxSr, 0);
+  prhs[5] = dbl_matrix((mwSize)maxSr * maxSr, Kr, eps, (size_t)maxSr * maxSr, 0);
+  prhs[6] = dbl_matrix((mwSize)d * maxSr, Kr, m, (size_t)d * maxSr, 0);
+  prhs[7] = dbl_matrix((mwSize)dd * maxSr, Kr, W, (size_t)dd * maxSr, 0);
+  prhs[8] = dbl_matrix(maxSr, Kr, v, maxSr, 0);
+  prhs[9] = dbl_matrix(maxSr, Kr, lam, maxSr, 0);
+  prhs[10] = sr;
+  prhs[11] = dbl_matrix(1, 5, hyp0, 1, 0);
+  prhs[12] = dbl_matrix(d, 1, m0, d, 0);
+  prhs[13] = dbl_matrix(nW0, 1, W0, nW0, 0);
+  prhs[14] = dbl_scalar((double)T);
+  prhs[15] = dbl_scalar((double)max_iter);
+  prhs[16] = dbl_scalar(min_diff);
+  mexFunction(9, plhs, 17, prhs);
+  double *outs[7] = {alpha, eta, eps, m, W, v, lam};
+  for (int k = 0; k < 7; k++) memcpy(outs[k], mxGetPr(plhs[k]), sizeof(double) * mxGetNumberOfElements(plhs[k]));
+  const size_t n = mxGetNumberOfElements(plhs[7]);
+  memcpy(LogLs, mxGetPr(plhs[7]), sizeof(double) * n);
+  info[0] = mxGetPr(plhs[8])[0];
+  info[1] = mxGetPr(plhs[8])[1];
+  info[2] = (double)n;
+  g_jmp_armed = 0;
+  arena_reset();
+  return 0;
+}
+
 /* Calls the linked gateway with a deliberately malformed argument list so the
  * tests can check the error ids the boundary raises
  * (vbhem_hmm_bwd_fwd_mex.c:335-366).  mode 0: wrong nrhs; 1: wrong nlhs;

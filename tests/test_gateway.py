@@ -83,3 +83,38 @@ def test_fused_gateway_matches_oracle(covmode, d):
         np.testing.assert_allclose(got["y_bar"][j].T[:r], f[3], rtol=1e-9)
         SC = got["S_plus_C"][j].reshape(d, d, 3).transpose(2, 1, 0)[:r] if covmode == "full" else got["S_plus_C"][j].T[:r]
         np.testing.assert_allclose(SC, f[4], rtol=1e-7, atol=1e-9 * np.abs(f[4]).max())
+
+
+needs_em = pytest.mark.skipif(not os.path.exists(cref.EM_SO), reason="EM-run gateway not built")
+
+
+@needs_em
+@pytest.mark.gpu
+@pytest.mark.parametrize("covmode,d", [("full", 2), ("diag", 3)])
+def test_em_run_gateway_equals_direct_em_run(covmode, d):
+    """vbhem_em_run_mex through the shim (cell tree of base HMMs + flat hyper-parameter arrays in, hyper-parameters
+    and LogLs out) must be the C ABI's vbhem_em_begin + vbhem_em_run + vbhem_em_fetch bit for bit, and its trace that
+    of the oracle's EM loop."""
+    from util import make_case
+    from vbhem_b200 import synth
+    from vbhem_b200.api import BaseSet
+    base, hyp, cen = make_case(N=80, K=3, Sb=3, Sr=3, d=d, covmode=covmode, ragged=False, seed=33, Nv=15.0)
+    opt = dict(synth.DEFAULT_OPT, Nv=15.0, tau=5, max_iter=12, minDiff=1e-6, m0=(256.0, 192.0, 128.0)[:d])
+    got = cref.gateway_em_run(pack.pack_base(base), hyp, opt)
+    with BaseSet(base) as bs:
+        bs.em_begin(hyp, opt)
+        want = bs.em_run(opt["tau"], opt["max_iter"], opt["minDiff"])
+    assert got["iters"] == want["iters"] and got["unstable"] == want["unstable"]
+    assert np.array_equal(got["LogLs"], want["LogLs"])
+    for k in ("alpha", "eta", "epsilon", "m", "W", "v", "lam"):
+        assert np.array_equal(got["hyp"][k], want["hyp"][k]), k
+    if covmode == "full" and d == 2:
+        from test_em_loop import oracle_em
+        _, LL = oracle_em(base, hyp, opt)
+        np.testing.assert_allclose(got["LogLs"], LL, rtol=1e-9)
+
+
+@needs_em
+def test_em_run_gateway_argument_errors():
+    lib = cref._lib("em")
+    assert cref.ref_call_malformed(0, "em") == (1, "MyToolbox:arrayProduct:nrhs")
