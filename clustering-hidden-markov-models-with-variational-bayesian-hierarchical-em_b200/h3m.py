@@ -273,9 +273,121 @@ CLUSTER_DEFAULTS = dict(alpha0=1.0, eta0=1.0, epsilon0=1.0, m0=(256.0, 192.0), W
                         trials=100, max_iter=200, minDiff=1e-5, Nv=100.0, tau=10, use_post=True, seed=None,
                         initmode="baseem", learn_hyps=0)
 """vbhem_h3m_cluster.m:141-179 (``initmode`` 'auto' of the reference tries 'baseem', 'gmmNew' and 'wtkmeans';
-only 'baseem' is mirrored, the other two need the Statistics Toolbox).  ``learn_hyps`` defaults to 1 in the
+'baseem' and 'wtkmeans' are mirrored -- the latter with scikit-learn's k-means in place of the Statistics Toolbox's
+-- and 'auto' means those two; 'gmmNew' needs ``gmdistribution.fit``).  ``learn_hyps`` defaults to 1 in the
 reference (:179); here it is opt-in: 1 or a list of names runs ``vbhem_h3m_c_hyp`` on the best trial of every
 (K, S) candidate (the reference optimises every distinct trial solution, vbhem_h3m_c.m:105-150)."""
+
+
+def my_weighted_kmeans(cluster_num: int, it_max: int, point: np.ndarray, weight: np.ndarray, cluster_center: np.ndarray):
+    """my_weighted_kmeans.m:1-100, restated: weighted k-means with the leave-one-out energy adjustment.
+    point [dim, n], weight [n], cluster_center [dim, k] (initial).  Returns (cluster[n] 0-based, centres [dim, k],
+    energy per iteration)."""
+    point, weight = np.asarray(point, float), np.asarray(weight, float)
+    k = cluster_num
+
+    def centroids(cluster):
+        cw = np.array([weight[cluster == j].sum() for j in range(k)])
+        cen = np.stack([(point[:, cluster == j] * weight[cluster == j]).sum(1) for j in range(k)], 1)
+        return np.where(cw > 0, cen / np.where(cw > 0, cw, 1.0), cen), cw
+
+    def energy(cluster, cen, cw):
+        f = ((point - cen[:, cluster]) ** 2).sum(0)
+        ce = np.array([(weight[cluster == j] * f[cluster == j]).sum() for j in range(k)])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            f = f * cw[cluster] / (cw[cluster] - weight)
+        return f, ce
+
+    d2 = ((point[:, None, :] - np.asarray(cluster_center, float)[:, :, None]) ** 2).sum(0)      # [k, n]
+    cluster = d2.argmin(0)
+    cen, cw = centroids(cluster)
+    f, ce = energy(cluster, cen, cw)
+    old = ce.sum()
+    energies, it = [old], 0
+    while it < it_max:
+        # energy of moving point i into cluster j (non-members) / of keeping it where it is (members)
+        fmat = ((point[:, None, :] - cen[:, :, None]) ** 2).sum(0) * (cw[:, None] / (cw[:, None] + weight[None, :]))
+        fmat[cluster, np.arange(point.shape[1])] = f
+        fmat = np.where(np.isnan(fmat), np.inf, fmat)          # MATLAB's min skips NaN (a singleton's own 0/0)
+        cluster = fmat.argmin(0)
+        cen, cw = centroids(cluster)
+        f, ce = energy(cluster, cen, cw)
+        new = ce.sum()
+        if abs(new - old) < 1e-6:
+            break
+        old = new
+        it += 1
+        energies.append(new)
+    return cluster, cen, np.array(energies)
+
+
+def init_centres_wtkmeans(base: dict, K: int, S: int, seed: int, opt: dict, mode: str = "r0") -> dict:
+    """``wtkmeans`` initialisation (vbhemhmm_init.m:294-425): all base emission means, weighted by their states'
+    occupancy (``makeGMMweights``: p A^50 for mode '0', uniform for 'x'), are clustered into K groups by weighted
+    k-means started from a plain k-means; each group's means are clustered again into the S state means of a centre.
+    Transition / prior pseudo-counts from ``makeAprior`` ('u' uniform, 'r' random).  The reference's plain k-means is
+    the Statistics Toolbox's (:331,360; seeds wtseed, wtseed + 1); scikit-learn's stands in.  Full or diagonal."""
+    from sklearn.cluster import KMeans
+    N, Sb_max, d = base["mu"].shape
+    full = base["cov"].ndim == 4
+    rng = np.random.Generator(np.random.PCG64(seed + 11))
+    pts, wts = [], []
+    for i in range(N):
+        s = int(base["Sb"][i])
+        p, A = base["prior"][i, :s], base["A"][i, :s, :s]
+        if "0" in mode:
+            for _ in range(50):
+                p = p @ A
+        elif "x" in mode:
+            p = np.full(s, 1.0 / s)
+        else:
+            raise ValueError("unknown mode")
+        pts.append(base["mu"][i, :s])
+        wts.append(p)
+    pts, wts = np.concatenate(pts).T, np.concatenate(wts)                               # [d, n], [n]
+    wts = wts / wts.sum()
+
+    def kmeans(x, k, rs):   # x [n, d] -> centres [<= k, d]
+        k = min(k, len(np.unique(x, axis=0)))
+        return KMeans(n_clusters=k, n_init=1, random_state=rs).fit(x).cluster_centers_
+
+    init = kmeans(pts.T, K, seed)
+    if init.shape[0] < K:
+        init = np.concatenate([init, np.repeat(init[:1], K - init.shape[0], 0)])
+    idx, _, _ = my_weighted_kmeans(K, 100, pts, wts, init.T)
+    centres, empty = [], []
+    for j in range(K):
+        mean_j = pts[:, idx == j]
+        if mean_j.shape[1] == 0:
+            centres.append(None)
+            empty.append(j)
+        elif mean_j.shape[1] <= S:
+            centres.append(np.concatenate([mean_j, np.repeat(mean_j[:, :1], S - mean_j.shape[1], 1)], 1))
+        else:
+            c = kmeans(mean_j.T, S, seed + 1).T
+            centres.append(np.concatenate([c, np.repeat(c[:, :1], S - c.shape[1], 1)], 1))
+    first = next(c for c in centres if c is not None)
+    centres = [first if c is None else c for c in centres]
+    NJ = opt["Nv"] * N / K
+    Ns = NJ / S
+    v = np.full((K, S), opt["v0"] + Ns + 1.0)
+    c0 = base["cov"][0, 0]                                                              # h3m_b.hmm{1}.emit{1}.covars
+    W1 = np.linalg.inv((v[0, 0] - d - 1.0) * c0) if full else 1.0 / ((v[0, 0] - d - 1.0) * c0)
+    eta, eps = np.zeros((K, S)), np.zeros((K, S, S))
+    for j in range(K):
+        if "u" in mode:
+            pr, A = np.full(S, 1.0 / S), np.full((S, S), 1.0 / S)
+        elif "r" in mode:
+            pr = rng.uniform(size=S)
+            pr /= pr.sum()
+            A = rng.uniform(size=(S, S))
+            A /= A.sum(1, keepdims=True)
+        else:
+            raise ValueError("unknown mode")
+        eta[j], eps[j] = pr * NJ + opt["eta0"], A * NJ + opt["epsilon0"]
+    return dict(Sr=np.full(K, S, np.int32), alpha=np.full(K, opt["alpha0"] + NJ), eta=eta, epsilon=eps,
+                m=np.stack([c.T for c in centres]), W=np.broadcast_to(W1, (K, S) + W1.shape).copy(), v=v,
+                lam=np.full((K, S), opt["lambda0"] + Ns))
 
 
 def stack_h3ms(models: list) -> tuple[dict, np.ndarray]:
@@ -361,8 +473,8 @@ def vbhem_h3m_cluster(hmms, K, S, vbhemopt: dict | None = None, covmode: str = "
     opt.update(vbhemopt or {})
     if opt.get("seed") is None:
         raise ValueError("vbhemopt.seed has not been set. This is required to obtain reproducible results.")
-    if opt["initmode"] != "baseem":
-        raise NotImplementedError(f"initmode {opt['initmode']!r}: only 'baseem' is mirrored")
+    if opt["initmode"] not in ("baseem", "wtkmeans", "auto"):
+        raise NotImplementedError(f"initmode {opt['initmode']!r}: 'baseem', 'wtkmeans' and 'auto' (both) are mirrored")
     base = hmms if isinstance(hmms, dict) else hmms_to_h3m_hem(hmms, covmode, bool(opt["use_post"]), float(opt["Nv"]))
     d = base["mu"].shape[2]
     if opt["v0"] <= d - 1:
@@ -376,8 +488,14 @@ def vbhem_h3m_cluster(hmms, K, S, vbhemopt: dict | None = None, covmode: str = "
     for ki, k in enumerate(Ks):
         for si, s in enumerate(Ss):
             for t in range(trials):
+                # 'auto' (vbhem_h3m_cluster.m:360-392) tries the modes one after the other and keeps the best bound;
+                # here the trials alternate between them, which the best-trial rule then compares
+                mode = opt["initmode"] if opt["initmode"] != "auto" else ("baseem", "wtkmeans")[t % 2]
                 cand.append((ki, si, t))
-                models.append(synth.init_centres_baseem(base, k, s, seed=int(opt["seed"]) + t + 1, opt=opt))
+                if mode == "baseem":
+                    models.append(synth.init_centres_baseem(base, k, s, seed=int(opt["seed"]) + t + 1, opt=opt))
+                else:   # wtseed = seed + it (vbhem_h3m_c.m:50-52)
+                    models.append(init_centres_wtkmeans(base, k, s, int(opt["seed"]) + t + 1, opt))
     clock.append(time.perf_counter())
     N = base["mu"].shape[0]
     with BaseSet(base, device=device) as bs:

@@ -207,3 +207,40 @@ def test_learn_batch_equals_learning_subject_by_subject():
         # trials that reach the same optimum tie to the last bits, so the winner's states may be permuted
         order = lambda m: m[np.lexsort(m.T[::-1])]
         np.testing.assert_allclose(order(got[s]["mean"]), order(one["mean"]), rtol=1e-6)
+
+
+def test_weighted_kmeans_and_wtkmeans_init():
+    """my_weighted_kmeans.m restated: recovers weighted groups, its energy never rises; init_centres_wtkmeans
+    (vbhemhmm_init.m:294-425) returns well-formed centres whose state means lie among the base means' range."""
+    from vbhem_b200 import h3m, synth
+    rng = np.random.default_rng(0)
+    pts = np.concatenate([rng.normal(c, 0.3, (40, 2)) for c in ([0, 0], [3, 3], [0, 4])]).T
+    w = rng.uniform(0.5, 1.5, 120)
+    w /= w.sum()
+    cl, cen, en = h3m.my_weighted_kmeans(3, 100, pts, w, pts[:, [0, 50, 100]] + 0.5)
+    assert np.bincount(cl).tolist() == [40, 40, 40] and np.all(np.diff(en) <= 1e-12)
+    for j in range(3):
+        np.testing.assert_allclose(cen[:, j], (pts[:, cl == j] * w[cl == j]).sum(1) / w[cl == j].sum(), rtol=1e-12)
+    for covmode in ("full", "diag"):
+        base, _ = synth.make_base_set(40, S=3, d=2, C=3, seed=3, covmode=covmode)
+        h = h3m.init_centres_wtkmeans(base, 3, 2, seed=5, opt=dict(h3m.CLUSTER_DEFAULTS))
+        assert h["m"].shape == (3, 2, 2) and h["W"].shape == ((3, 2, 2, 2) if covmode == "full" else (3, 2, 2))
+        assert np.all(h["m"] >= base["mu"].min()) and np.all(h["m"] <= base["mu"].max())
+        assert np.all(h["eta"] > 0) and np.all(h["epsilon"] > 0) and np.all(h["v"] > 3)
+        again = h3m.init_centres_wtkmeans(base, 3, 2, seed=5, opt=dict(h3m.CLUSTER_DEFAULTS))
+        assert all(np.array_equal(h[k], again[k]) for k in h)
+
+
+@pytest.mark.gpu
+def test_cluster_with_wtkmeans_and_auto_init():
+    """initmode 'wtkmeans' and 'auto' (trials alternate between baseem and wtkmeans): every trial of 'auto' is the
+    same EM run as the trial of that number under its own mode, and the selection takes the best of them."""
+    from vbhem_b200 import h3m, synth
+    base, lab = synth.make_base_set(90, S=3, d=2, C=3, seed=31, Nv=20.0)
+    common = dict(trials=4, seed=3, Nv=20.0, max_iter=60)
+    runs = {mode: h3m.vbhem_h3m_cluster(base, [2, 3], 3, dict(common, initmode=mode)) for mode in ("baseem", "wtkmeans", "auto")}
+    for out in runs.values():
+        assert np.isfinite(out["LL"]) and out["Z"].shape == (90, out["K"]) and out["group_size"].sum() == 90
+    np.testing.assert_allclose(runs["auto"]["trials_LL"][:, :, 0::2], runs["baseem"]["trials_LL"][:, :, 0::2], rtol=1e-12)
+    np.testing.assert_allclose(runs["auto"]["trials_LL"][:, :, 1::2], runs["wtkmeans"]["trials_LL"][:, :, 1::2], rtol=1e-12)
+    assert runs["auto"]["LL"] >= min(runs["baseem"]["LL"], runs["wtkmeans"]["LL"]) - 1e-9 * abs(runs["auto"]["LL"])
