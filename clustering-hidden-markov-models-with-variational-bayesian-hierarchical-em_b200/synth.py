@@ -100,20 +100,25 @@ def init_centres_baseem(base, K, S, seed=1001, opt=DEFAULT_OPT, Sr=None):
     lam = np.zeros((K, S)); v = np.zeros((K, S)); m = np.zeros((K, S, d))
     W = np.zeros((K, S, d, d)) if full else np.zeros((K, S, d))
     eta = np.zeros((K, S)); eps = np.zeros((K, S, S))
-    for j in range(K):
+    Sb = base["Sb"]
+    jj, kk, bb, gg = [], [], [], []
+    for j in range(K):                       # the random draws, in the order the per-centre loop always made them
         s = int(Sr[j])
         rb = rng.integers(0, N, size=s)
-        rg = np.array([rng.integers(0, base["Sb"][b]) for b in rb])
-        lam[j, :s] = opt["lambda0"] + NLr / s
-        v[j, :s] = opt["v0"] + NLr / s + 1.0
-        m[j, :s] = base["mu"][rb, rg]
-        c = base["cov"][rb, rg]
-        if full:
-            W[j, :s] = np.linalg.inv((v[j, :s, None, None] - d - 1.0) * c)
-        else:
-            W[j, :s] = 1.0 / ((v[j, :s, None] - d - 1.0) * c)
+        rg = [rng.integers(0, Sb[b]) for b in rb]
+        jj += [j] * s; kk += range(s); bb += rb.tolist(); gg += rg
         eta[j, :s] = (1.0 / s) * NLr + opt["eta0"]
         eps[j, :s, :s] = (1.0 / s) * NLr / s + opt["epsilon0"]
+    jj, kk, bb, gg = (np.asarray(x, int) for x in (jj, kk, bb, gg))
+    per = NLr / Sr[jj]
+    lam[jj, kk] = opt["lambda0"] + per
+    v[jj, kk] = opt["v0"] + per + 1.0
+    m[jj, kk] = base["mu"][bb, gg]
+    c = base["cov"][bb, gg]
+    if full:
+        W[jj, kk] = np.linalg.inv((v[jj, kk, None, None] - d - 1.0) * c)
+    else:
+        W[jj, kk] = 1.0 / ((v[jj, kk, None] - d - 1.0) * c)
     omega = rng.uniform(size=K)
     omega /= omega.sum()
     alpha = opt["alpha0"] + omega * Nv
