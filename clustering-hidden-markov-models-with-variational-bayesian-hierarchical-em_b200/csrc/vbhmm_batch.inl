@@ -125,10 +125,9 @@ k_fb_batch(const FbPar<K, DIM> *__restrict__ pars, const unsigned char *__restri
            const int *__restrict__ run_of, const int *__restrict__ seq_of, const int *__restrict__ Tn,
            const double *__restrict__ X, double *__restrict__ gamma, double *__restrict__ xi_sum,
            double *__restrict__ phi) {
-  __shared__ __align__(16) double s_etab[VBHEM_EXP_BINS];
-  for (int j = threadIdx.x; j < VBHEM_EXP_BINS; j += kFbThreads) s_etab[j] = g_fb_exp_table[j];
-  __syncthreads();
-  const vbhem::tab_t etab = (vbhem::tab_t)__cvta_generic_to_shared(s_etab);
+  __shared__ __align__(16) double s_tab[kFbTabDoubles];
+  vbhem::tab_t etab, ltab;
+  stage_tables<kFbThreads>(s_tab, etab, ltab);
   const int w = blockIdx.x * kFbThreads + threadIdx.x;
   if (w >= Wn) return;
   const int run = run_of[w];
@@ -156,9 +155,9 @@ k_fb_batch(const FbPar<K, DIM> *__restrict__ pars, const unsigned char *__restri
     const double rc = 1.0 / c;
 #pragma unroll
     for (int k = 0; k < K; k++) { alpha[k] = delta[k] * rc; gp[WK * t + k] = alpha[k]; }
-    sumlogc += log(c);
+    sumlogc += vbhem::log_shift<1>(c, ltab, 0);
   }
-  phi[w] = sumlogc + summax;
+  phi[w] = sumlogc * vbhem::kUnit + summax;
   // the K x K pair-marginal accumulator of each thread lives in shared memory ([j][k][thread]: conflict-free), as in k_fb
   extern __shared__ double xis[];
   double *xi = xis + threadIdx.x;
@@ -176,18 +175,21 @@ k_fb_batch(const FbPar<K, DIM> *__restrict__ pars, const unsigned char *__restri
     for (int i = 0; i < DIM; i++) x[i] = xp[ND * (t + 1) + i];
     emissions<K, DIM>(P, x, lr);
     shifted_exp<K>(lr, p, etab);
-    double delta[K];
-    const double rc = 1.0 / forward_step<K, DIM>(P, alpha, p, delta);
     double bpi[K];
 #pragma unroll
     for (int k = 0; k < K; k++) bpi[k] = beta[k] * p[k];
+    double c = 0.0;                                                     // c(t+1) = sum_j alpha_hat_t(j) eta(j), see k_fb
 #pragma unroll
     for (int j = 0; j < K; j++) {
       double eta = 0.0;
 #pragma unroll
       for (int k = 0; k < K; k++) eta += bpi[k] * P.A[j][k];
-      beta[j] = eta * rc;
+      beta[j] = eta;
+      c += alpha[j] * eta;
     }
+    const double rc = 1.0 / c;
+#pragma unroll
+    for (int j = 0; j < K; j++) beta[j] *= rc;
 #pragma unroll
     for (int k = 0; k < K; k++) gp[WK * t + k] = alpha[k] * beta[k];
 #pragma unroll

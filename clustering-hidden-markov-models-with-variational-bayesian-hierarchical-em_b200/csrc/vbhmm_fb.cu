@@ -17,6 +17,9 @@
 //   * the forward pass writes logrho and parks alpha_hat in the gamma output; the backward pass reads
 //     it back in place, recomputes the emissions of step t+1 from X (cheaper than reading logrho back)
 //     and the scale c_{t+1} from alpha_t (bit-identical to the forward value, so no scale array);
+//     (taking c_{t+1} = sum_j alpha_hat_t(j) eta(j) from the backward sums and log c from the lean log saves 70 fp64
+//     instructions per step but costs registers: 2.30 -> 2.36 ms here, while the batched kernel, which is not held
+//     to 128 registers, gains 3 % from it -- vbhmm_batch.inl)
 //   * outputs beyond a sequence's own length are written as zeros by the same thread (no memset pass).
 #include "../../include/vbhem_b200.h"
 #include "vbhem_math.cuh"
@@ -90,8 +93,21 @@ __device__ __forceinline__ void emissions(const FbPar<K, DIM> &P, const double (
   }
 }
 
-// 2^(j/256) table of the lattice kernels' exp (vbhem_math.cuh), staged per block
+// 2^(j/256) table of the lattice kernels' exp and the (1/c, -log(1/c)/u) table of their log (vbhem_math.cuh), staged
+// per block
 __device__ const double g_fb_exp_table[VBHEM_EXP_BINS] = VBHEM_EXP_TABLE;
+__device__ const double g_fb_log_table[2 * VBHEM_LOG_BINS] = VBHEM_LOG_TABLE;
+
+// exp table | log table in shared memory; returns the two views
+template <int THREADS>
+__device__ __forceinline__ void stage_tables(double *s_tab, vbhem::tab_t &etab, vbhem::tab_t &ltab) {
+  for (int j = threadIdx.x; j < VBHEM_EXP_BINS; j += THREADS) s_tab[j] = g_fb_exp_table[j];
+  for (int j = threadIdx.x; j < 2 * VBHEM_LOG_BINS; j += THREADS) s_tab[VBHEM_EXP_BINS + j] = g_fb_log_table[j];
+  __syncthreads();
+  etab = (vbhem::tab_t)__cvta_generic_to_shared(s_tab);
+  ltab = (vbhem::tab_t)__cvta_generic_to_shared(s_tab + VBHEM_EXP_BINS);
+}
+constexpr int kFbTabDoubles = VBHEM_EXP_BINS + 2 * VBHEM_LOG_BINS;
 
 // p(k) = exp(logrho(k) - max_k logrho): arguments are <= 0, so the lean exp of the lattice kernels applies
 // (8 fp64 instructions against libdevice's ~19): y = x / u, e^x = mant 2^e, e <= 0; below 2^-1000 it returns
