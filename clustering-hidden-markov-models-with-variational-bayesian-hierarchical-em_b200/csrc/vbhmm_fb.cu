@@ -55,6 +55,9 @@ constexpr int kFbThreads = 128;
 #ifndef VB_FB_MINB
 #define VB_FB_MINB 4
 #endif
+#ifndef VB_FB_LEAN
+#define VB_FB_LEAN 0       // 1: k_fb takes c(t+1) from the backward sums and log c from the lean log (see the header note)
+#endif
 #ifndef VB_FB_BLOCKS
 #define VB_FB_BLOCKS 0     // > 0: cap the resident blocks per SM (L2 residency of the parked alpha_hat)
 #endif
@@ -150,10 +153,16 @@ __global__ void __launch_bounds__(kFbThreads, VB_FB_MINB)
 k_fb(const __grid_constant__ FbPar<K, DIM> P, int N, int maxT, const int *__restrict__ Tn,
      const double *__restrict__ X, double *__restrict__ logrho, double *__restrict__ gamma,
      double *__restrict__ xi_sum, double *__restrict__ phi) {
+#if VB_FB_LEAN
+  __shared__ __align__(16) double s_tab[kFbTabDoubles];
+  vbhem::tab_t etab, ltab;
+  stage_tables<kFbThreads>(s_tab, etab, ltab);
+#else
   __shared__ __align__(16) double s_etab[VBHEM_EXP_BINS];
   for (int j = threadIdx.x; j < VBHEM_EXP_BINS; j += kFbThreads) s_etab[j] = g_fb_exp_table[j];
   __syncthreads();
   const vbhem::tab_t etab = (vbhem::tab_t)__cvta_generic_to_shared(s_etab);
+#endif
   const int n = blockIdx.x * kFbThreads + threadIdx.x;
   if (n >= N) return;
   const int T = Tn[n];
@@ -191,9 +200,15 @@ k_fb(const __grid_constant__ FbPar<K, DIM> P, int N, int maxT, const int *__rest
     const double rc = 1.0 / c;
 #pragma unroll
     for (int k = 0; k < K; k++) { alpha[k] = delta[k] * rc; gp[NK * t + k] = alpha[k]; }
+#if VB_FB_LEAN
+    sumlogc += vbhem::log_shift<1>(c, ltab, 0);
+  }
+  phi[n] = sumlogc * vbhem::kUnit + summax;
+#else
     sumlogc += log(c);
   }
   phi[n] = sumlogc + summax;
+#endif
   // zeros beyond the sequence's own length (the reference's outputs start as zeros)
   for (int t = T; t < maxT; t++) {
 #pragma unroll
@@ -229,9 +244,25 @@ k_fb(const __grid_constant__ FbPar<K, DIM> P, int N, int maxT, const int *__rest
     }
     emissions<K, DIM>(P, x, lr);
     shifted_exp<K>(lr, p, etab);                                      // p(x_{t+1} | z) / max
+    double bpi[K];
+#if VB_FB_LEAN
+#pragma unroll
+    for (int k = 0; k < K; k++) bpi[k] = beta[k] * p[k];
+    double c = 0.0;   // c(t+1) = sum_j alpha_hat_t(j) eta(j): sum_k alpha_hat(k) beta_hat(k) = 1 at every step
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+      double eta = 0.0;
+#pragma unroll
+      for (int k = 0; k < K; k++) eta += bpi[k] * P.A[j][k];
+      beta[j] = eta;
+      c += alpha[j] * eta;
+    }
+    const double rc = 1.0 / c;
+#pragma unroll
+    for (int j = 0; j < K; j++) beta[j] *= rc;
+#else
     double delta[K];
     const double rc = 1.0 / forward_step<K, DIM>(P, alpha, p, delta);   // 1 / c(t+1)
-    double bpi[K];
 #pragma unroll
     for (int k = 0; k < K; k++) bpi[k] = beta[k] * p[k];
 #pragma unroll
@@ -241,6 +272,7 @@ k_fb(const __grid_constant__ FbPar<K, DIM> P, int N, int maxT, const int *__rest
       for (int k = 0; k < K; k++) eta += bpi[k] * P.A[j][k];
       beta[j] = eta * rc;
     }
+#endif
 #pragma unroll
     for (int k = 0; k < K; k++) __stcs(gp + NK * t + k, alpha[k] * beta[k]);
 #pragma unroll
