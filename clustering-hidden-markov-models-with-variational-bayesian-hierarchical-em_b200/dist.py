@@ -153,3 +153,24 @@ class ShardedEStep:
         ops["sync"]()
         return dict(hyp=ops["fetch"](), LogLs=np.array(LogLs), LL=LogLs[-1], iters=it, unstable=unstable,
                     ms_per_iter=1e3 * float(np.median(times)) if times else float("nan"))
+
+
+def run_sharded(items: list, fn, group=None) -> list:
+    """Independent work units over the ranks of one box, no data-path collective.
+
+    The batched workloads next to the E-step partition instead of sharding: the subjects of ``hmm.vbhmm_learn_batch``
+    (the reference's vbhmm_learn_batch.m loop) and the (K, S, trial) candidates of a model selection are independent
+    runs.  ``items`` is split contiguously (``shard_bounds``); every rank calls ``fn(its slice)`` -- which must return
+    one result per item -- on its own GPU, and the complete list comes back on every rank through one
+    ``all_gather_object`` of the (small) results.  Without an initialised process group it is ``fn(items)``."""
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        return list(fn(items))
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    lo, hi = shard_bounds(len(items), world, rank)
+    mine = list(fn(items[lo:hi])) if hi > lo else []
+    if len(mine) != hi - lo:
+        raise ValueError("fn must return one result per work item")
+    parts = [None] * world
+    dist.all_gather_object(parts, mine, group=group)
+    return [x for p in parts for x in p]

@@ -153,3 +153,36 @@ def test_two_rank_em_loop_equals_single_process_oracle_em(tmp_path):
     np.testing.assert_allclose(got["LogLs"], want_L, rtol=1e-10)
     for k in ("alpha", "eta", "epsilon", "lam", "v", "m", "W"):
         np.testing.assert_allclose(got[f"hyp_{k}"], want_hyp[k], rtol=1e-8, atol=1e-10 * np.abs(want_hyp[k]).max(), err_msg=k)
+
+
+def _worker_runs(rank, world, port, n, out_dir):
+    sys.path.insert(0, ROOT)
+    import vbhem_b200  # noqa: F401
+    from vbhem_b200.dist import run_sharded, shard_bounds
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    items = [dict(subject=i, data=np.arange(i + 1.0)) for i in range(n)]
+    seen = []
+
+    def fn(chunk):                       # stands for hmm.vbhmm_learn_batch on this rank's GPU
+        seen.extend(c["subject"] for c in chunk)
+        return [dict(subject=c["subject"], total=float(c["data"].sum()), rank=rank) for c in chunk]
+
+    out = run_sharded(items, fn)
+    lo, hi = shard_bounds(n, world, rank)
+    assert seen == list(range(lo, hi))
+    if rank == 1:
+        np.save(os.path.join(out_dir, "runs.npy"), np.array([[o["subject"], o["total"], o["rank"]] for o in out]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [7, 1])
+def test_independent_runs_partition_over_two_ranks(tmp_path, n):
+    """dist.run_sharded: the batched workloads (subjects of vbhmm_learn_batch, candidates of a model selection)
+    partition over the ranks with no data-path collective; every rank ends up with every result, in order."""
+    mp.spawn(_worker_runs, args=(2, _free_port(), n, str(tmp_path)), nprocs=2, join=True)
+    got = np.load(os.path.join(str(tmp_path), "runs.npy"))
+    assert got[:, 0].tolist() == list(range(n))
+    assert got[:, 1].tolist() == [i * (i + 1) / 2 for i in range(n)]
+    assert got[:, 2].tolist() == [0] * ((n + 1) // 2) + [1] * (n // 2)
