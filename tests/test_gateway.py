@@ -13,7 +13,7 @@ from test_oracle import load_golden
 from util import assert_pairs_close
 
 GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
-              if not os.path.basename(p).startswith("vbhmm_fb"))   # E-step fixtures (forward-backward ones: test_fb.py)
+              if not os.path.basename(p).startswith(("vbhmm_", "vbhem_em_")))   # E-step fixtures (others: test_fb.py, test_golden_em.py)
 needs_gateway = pytest.mark.skipif(not os.path.exists(cref.GATEWAY_SO), reason="gateway not built")
 
 

@@ -17,7 +17,7 @@ from util import assert_pairs_close, make_case, oracle_fused, oracle_pairs
 pytestmark = pytest.mark.gpu
 
 GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
-              if not os.path.basename(p).startswith("vbhmm_fb"))   # E-step fixtures (forward-backward ones: test_fb.py)
+              if not os.path.basename(p).startswith(("vbhmm_", "vbhem_em_")))   # E-step fixtures (others: test_fb.py, test_golden_em.py)
 RTOL = 1e-9
 
 
