@@ -31,6 +31,7 @@ FB_GATEWAY_SO = os.path.join(HERE, "_build", "libvbhmm_fb_gateway.so")  # this r
 GATEWAY_SO = os.path.join(HERE, "_build", "libvbhem_gateway.so")   # this repo's MEX gateway behind the same shim
 FUSED_SO = os.path.join(HERE, "_build", "libvbhem_gateway_fused.so")   # ... and its fused-E-step gateway
 EM_SO = os.path.join(HERE, "_build", "libvbhem_gateway_em.so")         # ... and its whole-EM-run gateway
+EM_BATCH_SO = os.path.join(HERE, "_build", "libvbhmm_em_batch_gateway.so")   # batched VB-HMM learning gateway
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -54,7 +55,7 @@ _libs = {}
 
 def _lib(which: str):
     if which not in _libs:
-        path = {"ref": REF_SO, "gateway": GATEWAY_SO, "fused": FUSED_SO, "em": EM_SO, "fb_ref": FB_REF_SO,
+        path = {"ref": REF_SO, "gateway": GATEWAY_SO, "fused": FUSED_SO, "em": EM_SO, "em_batch": EM_BATCH_SO, "fb_ref": FB_REF_SO,
                 "fb_port": FB_PORT_SO, "fb_gateway": FB_GATEWAY_SO}.get(which, PORT_SO)
         if not os.path.exists(path):
             build()
@@ -288,6 +289,47 @@ def ref_vbhmm_fb(ps: dict, par: dict) -> dict:
 
 def port_vbhmm_fb(ps: dict, par: dict) -> dict:
     return _fb("fb_port", ps, par)
+
+
+def gateway_em_batch(subjects: list, run_subject, K: int, ini: dict, inits: list) -> list:
+    """mex/vbhmm_em_batch_mex.cpp through the mx shim.  subjects[s]: list of [T, dim] sequences; run_subject[r]: 0-based
+    subject of run r; inits[r]: natural variational parameters (alpha[K], epsilon[K,K] (from,to), beta, v, m[K,dim],
+    W[K,dim,dim]); ini: alpha0, epsilon0, beta0, v0, mu0, W0, maxIter, minDiff.  Returns per run a dict with the
+    learnt varpar (natural), N1, N, M (from,to), LLs, iter, unstable."""
+    lib = _lib("em_batch")
+    flat_seqs = [x for sub in subjects for x in sub]
+    ps = pack_sequences(flat_seqs)
+    start = np.concatenate([[0], np.cumsum([len(sub) for sub in subjects])]).astype(np.int32)
+    R, dim = len(inits), ps["dim"]
+    st = lambda k: np.stack([np.asarray(v[k], float) for v in inits])
+    al, be, vv = _f64(st("alpha")), _f64(st("beta")), _f64(st("v"))
+    ep = _f64(np.transpose(st("epsilon"), (0, 2, 1)))
+    mm = _f64(st("m"))
+    WW = _f64(np.transpose(st("W"), (0, 1, 3, 2)))
+    prior = _f64(np.array([ini["alpha0"], ini["epsilon0"], ini["beta0"], ini["v0"]], float))
+    m0 = _f64(np.asarray(ini["mu0"], float).reshape(dim))
+    W0 = _f64(np.atleast_1d(np.asarray(ini["W0"], float)))
+    max_iter = int(ini["maxIter"])
+    N1, Nk, M = np.zeros((R, K)), np.zeros((R, K)), np.zeros((R, K, K))
+    LLs, info = np.zeros((R, max_iter)), np.zeros((R, 2))
+    rs = _f64(np.asarray(run_subject, float) + 1.0)
+    fn = lib.shim_em_batch
+    fn.restype = C.c_int
+    rc = fn(C.c_int(len(subjects)), _i(start), C.c_int(dim), _i(_i32(ps["T"])), ps["offs"].ctypes.data_as(C.POINTER(C.c_longlong)),
+            _d(ps["flat"]), C.c_int(R), _d(rs), C.c_int(K), _d(prior), _d(m0), _d(W0), C.c_int(W0.size), _d(al), _d(ep),
+            _d(be), _d(vv), _d(mm), _d(WW), C.c_int(max_iter), C.c_double(float(ini["minDiff"])), _d(N1), _d(Nk), _d(M),
+            _d(LLs), _d(info))
+    if rc != 0:
+        lib.shim_last_error_id.restype = C.c_char_p
+        lib.shim_last_error_msg.restype = C.c_char_p
+        raise RuntimeError(f"{lib.shim_last_error_id().decode()}: {lib.shim_last_error_msg().decode()}")
+    out = []
+    for r in range(R):
+        n = int(info[r, 0])
+        out.append(dict(varpar=dict(alpha=al[r], epsilon=ep[r].T.copy(), beta=be[r], v=vv[r], m=mm[r],
+                                    W=np.transpose(WW[r], (0, 2, 1)).copy()),
+                        N1=N1[r], N=Nk[r], M=M[r].T.copy(), LLs=LLs[r, :n].copy(), iter=n, unstable=bool(info[r, 1])))
+    return out
 
 
 def gateway_vbhmm_fb(ps: dict, par: dict) -> dict:

@@ -380,6 +380,47 @@ int shim_em_run(int Kb, const int *Sb, int maxSb, int d, int covmode,
   return 0;
 }
 
+/* shim_em_batch: the signature of this repo's vbhmm_em_batch_mex (mex/vbhmm_em_batch_mex.cpp).  The S subjects'
+ * sequences arrive concatenated (sequence n = [T_n x dim] column-major at offs[n]; subject s = sequences
+ * [sub_start[s], sub_start[s + 1])) and are handed over as the nested cell the toolbox uses. */
+int shim_em_batch(int S, const int *sub_start, int dim, const int *T, const long long *offs, const double *seq, int R,
+                  const double *run_subject, int K, const double *prior4, const double *m0, const double *W0, int nW0,
+                  double *alpha, double *eps, double *beta, double *v, double *m, double *W, int max_iter,
+                  double min_diff, double *N1, double *Nk, double *M, double *LLs, double *info) {
+  g_jmp_armed = 1;
+  if (setjmp(g_jmp)) { g_jmp_armed = 0; arena_reset(); return 1; }
+  mxArray *data = mxCreateCellMatrix((mwSize)S, 1);
+  for (int s = 0; s < S; s++) {
+    const int n0 = sub_start[s], n1 = sub_start[s + 1];
+    mxArray *sub = mxCreateCellMatrix((mwSize)(n1 - n0), 1);
+    for (int n = n0; n < n1; n++)
+      mxSetCell(sub, (mwIndex)(n - n0), dbl_matrix((mwSize)T[n], (mwSize)dim, seq + offs[n], (size_t)T[n], 0));
+    mxSetCell(data, (mwIndex)s, sub);
+  }
+  const mxArray *prhs[14];
+  mxArray *plhs[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  prhs[0] = data;
+  prhs[1] = dbl_matrix(R, 1, run_subject, R, 0);
+  prhs[2] = dbl_scalar((double)K);
+  prhs[3] = dbl_matrix(1, 4, prior4, 1, 0);
+  prhs[4] = dbl_matrix(dim, 1, m0, dim, 0);
+  prhs[5] = dbl_matrix(nW0, 1, W0, nW0, 0);
+  prhs[6] = dbl_matrix(K, R, alpha, K, 0);
+  prhs[7] = dbl_matrix((mwSize)K * K, R, eps, (size_t)K * K, 0);
+  prhs[8] = dbl_matrix(K, R, beta, K, 0);
+  prhs[9] = dbl_matrix(K, R, v, K, 0);
+  prhs[10] = dbl_matrix((mwSize)dim * K, R, m, (size_t)dim * K, 0);
+  prhs[11] = dbl_matrix((mwSize)dim * dim * K, R, W, (size_t)dim * dim * K, 0);
+  prhs[12] = dbl_scalar((double)max_iter);
+  prhs[13] = dbl_scalar(min_diff);
+  mexFunction(11, plhs, 14, prhs);
+  double *outs[11] = {alpha, eps, beta, v, m, W, N1, Nk, M, LLs, info};
+  for (int k = 0; k < 11; k++) memcpy(outs[k], mxGetPr(plhs[k]), sizeof(double) * mxGetNumberOfElements(plhs[k]));
+  g_jmp_armed = 0;
+  arena_reset();
+  return 0;
+}
+
 /* Calls the linked gateway with a deliberately malformed argument list so the
  * tests can check the error ids the boundary raises
  * (vbhem_hmm_bwd_fwd_mex.c:335-366).  mode 0: wrong nrhs; 1: wrong nlhs;

@@ -118,3 +118,41 @@ def test_em_run_gateway_equals_direct_em_run(covmode, d):
 def test_em_run_gateway_argument_errors():
     lib = cref._lib("em")
     assert cref.ref_call_malformed(0, "em") == (1, "MyToolbox:arrayProduct:nrhs")
+
+
+needs_em_batch = pytest.mark.skipif(not os.path.exists(cref.EM_BATCH_SO), reason="batched-learning gateway not built")
+
+
+@needs_em_batch
+@pytest.mark.gpu
+def test_em_batch_gateway_equals_direct_batch():
+    """vbhmm_em_batch_mex through the shim (nested cell of subjects' sequences, stacked initial parameters) must be
+    hmm.vbhmm_em_batch (vbhmm_batch_begin / run / fetch) bit for bit."""
+    from oracle import numpy_ref as nr
+    from test_hmm_em import INI, make_sequences
+    from vbhem_b200 import fb, hmm
+    ini = dict(INI, maxIter=25)
+    subjects, inits, run_subject = [], [], []
+    for s in range(3):
+        data, gmm = make_sequences(n=5 + 2 * s, K=3, seed=80 + s, tmin=1)
+        subjects.append(data)
+        for trial in range(2):
+            g = dict(gmm, mean=gmm["mean"] + 4.0 * trial)
+            inits.append(nr.vbhmm_init_from_gmm(g, sum(len(x) for x in data), ini))
+            run_subject.append(s)
+    got = cref.gateway_em_batch(subjects, run_subject, 3, ini, inits)
+    start = np.concatenate([[0], np.cumsum([len(x) for x in subjects])])
+    with fb.SequenceSet([x for sub in subjects for x in sub]) as seqs:
+        want, _ = hmm.vbhmm_em_batch(seqs, [(int(start[s]), int(start[s + 1])) for s in run_subject], 3, ini, inits)
+    for g, w in zip(got, want):
+        assert g["iter"] == w["iter"] and g["unstable"] == w["unstable"]
+        assert np.array_equal(g["LLs"], w["LLs"])
+        for k in ("alpha", "epsilon", "beta", "v", "m", "W"):
+            assert np.array_equal(g["varpar"][k], w["varpar"][k]), k
+        for k in ("N1", "N", "M"):
+            assert np.array_equal(g[k], w[k]), k
+
+
+@needs_em_batch
+def test_em_batch_gateway_argument_errors():
+    assert cref.ref_call_malformed(0, "em_batch") == (1, "MyToolbox:arrayProduct:nrhs")
