@@ -158,10 +158,24 @@ def main_fb(a):
         hm, info = Hm.vbhmm_em_batch(seqs, runs, K, ini, inits)
         wall = time.perf_counter() - t0
         run_passes = sum(h["iter"] for h in hm)
+        # the random-initialisation GMM fits of the same runs (vbhmm_init.m:43-61) on the device, against scikit-learn
+        # on the host for a sample of them
+        starts = [rng.choice(per * T, size=K, replace=False) for _ in range(nsub)]
+        Hm.gmm_fit_batch(seqs, runs[:64], K, starts[:64])                     # warm-up (module load)
+        t0 = time.perf_counter()
+        gm = Hm.gmm_fit_batch(seqs, runs, K, starts)
+        t_gmm = time.perf_counter() - t0
+        Xs = np.transpose(flat[:per * T * dim].reshape(per, dim, T), (0, 2, 1)).reshape(-1, dim)
+        t0 = time.perf_counter()
+        for q in range(5):
+            Hm._fit_gmm(Xs, K, q)
+        t_sk = (time.perf_counter() - t0) / 5
         learn = dict(subjects=nsub, sequences_per_subject=per, passes=info["passes"], run_passes=run_passes,
                      device_ms=info["device_ms"], wall_ms=1e3 * wall,
                      sequence_passes_per_s=run_passes * per / (info["device_ms"] * 1e-3),
                      unstable=int(sum(h["unstable"] for h in hm)),
+                     gmm_init=dict(device_seconds=t_gmm, runs=nsub, mean_iters=float(np.mean([g["iters"] for g in gm])),
+                                   sklearn_seconds_per_fit=t_sk, sklearn_seconds_extrapolated=t_sk * nsub),
                      note="hmm.vbhmm_em_batch: every subject's vbhmm_em run (pre-pass, forward-backward, sums, lower "
                           "bound, convergence test |dL/L| <= 1e-5, M-step) in one device-resident loop; device_ms = the "
                           "loop (CUDA events), wall_ms includes stacking the initialisations and fetching 20k models; "

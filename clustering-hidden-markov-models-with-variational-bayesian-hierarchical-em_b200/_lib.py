@@ -71,6 +71,8 @@ SIGNATURES = {
     "vbhmm_batch_fetch": (C.c_int, [vp, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp, ip, ip]),
     "vbhmm_batch_last_ms": (C.c_int, [vp, dp]),
     "vbhmm_batch_free": (C.c_int, [vp]),
+    "vbhmm_gmm_fit": (C.c_int, [vp, C.c_int, ip, ip, C.c_int, ip, ip, C.c_int, C.c_double, C.c_double, dp, dp, dp, dp,
+                                ip]),
     "vbhem_set_profile": (C.c_int, [vp, C.c_int]),
     "vbhem_last_timings": (C.c_int, [vp, dp]),
     "vbhem_measure_fp64_peak": (C.c_int, [C.c_int, dp]),

@@ -796,3 +796,4 @@ int vbhmm_fb_last_ms(vbhmm_data_t *h, double *ms) {
 }  // extern "C"
 
 #include "vbhmm_batch.inl"
+#include "vbhmm_gmm.inl"

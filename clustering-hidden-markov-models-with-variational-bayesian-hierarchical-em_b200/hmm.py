@@ -286,10 +286,39 @@ def vbhmm_em_batch(seqs: _fb.SequenceSet, runs, K: int, ini: dict, inits: list) 
     return out, dict(passes=passes.value, device_ms=ms.value)
 
 
+def gmm_fit_batch(seqs: _fb.SequenceSet, runs, K: int, starts, max_iter: int = 100, tol: float = 1e-5,
+                  reg: float = 1e-10) -> list:
+    """K-component full-covariance GMMs of many runs' pooled observations, one device block per run
+    (``vbhmm_gmm_fit``): the random initialisation of vbhmm_init.m:43-61 without the per-run host fit.
+    ``runs[r] = (lo, hi)`` sequences; ``starts[r]`` = K indices into the run's pooled observations (sequence after
+    sequence, time step after time step) that start its components.  Returns a list of dict(prior, mean, cov, loglik,
+    iters) -- the ``initgmm`` argument of ``vbhmm_init``."""
+    R, dim = len(runs), seqs.dim
+    c = np.ascontiguousarray
+    lo = c([a for a, _ in runs], dtype=np.int32)
+    hi = c([b for _, b in runs], dtype=np.int32)
+    ss, st = np.zeros((R, K), np.int32), np.zeros((R, K), np.int32)
+    for r, (a, b) in enumerate(runs):
+        ends = np.cumsum(seqs.T[a:b])
+        idx = np.asarray(starts[r], int)
+        q = np.searchsorted(ends, idx, side="right")
+        ss[r] = a + q
+        st[r] = idx - np.where(q > 0, ends[np.maximum(q - 1, 0)], 0)
+    w, mu, cv = np.zeros((R, K)), np.zeros((R, K, dim)), np.zeros((R, K, dim, dim))
+    ll, it = np.zeros(R), np.zeros(R, np.int32)
+    P = lambda a: a.ctypes.data_as(dp)
+    I = lambda a: a.ctypes.data_as(ip)
+    check(lib().vbhmm_gmm_fit(seqs._h, R, I(lo), I(hi), K, I(ss), I(st), int(max_iter), float(tol), float(reg), P(w), P(mu),
+                              P(cv), P(ll), I(it)))
+    return [dict(prior=w[r], mean=mu[r], cov=cv[r], loglik=float(ll[r]), iters=int(it[r])) for r in range(R)]
+
+
 def vbhmm_learn_batch(subjects: list, K, vbopt: dict | None = None) -> list:
     """vbhmm_learn_batch.m: one HMM per subject (``subjects[s]`` = that subject's list of [T, dim] sequences), every
     subject x candidate K x random initialisation as one run of a device-resident batch per K; per subject the best
-    trial by LL, then the best K by ``LL + gammaln(K + 1)`` (vbhmm_learn.m:387-405,555)."""
+    trial by LL, then the best K by ``LL + gammaln(K + 1)`` (vbhmm_learn.m:387-405,555).
+    ``vbopt['gmm_init'] = 'device'`` fits the random-initialisation GMMs of all runs on the GPU (``gmm_fit_batch``)
+    instead of one scikit-learn fit per run on the host."""
     opt = dict(DEFAULT_VBOPT)
     opt.update(vbopt or {})
     Ks = [int(k) for k in np.atleast_1d(K)]
@@ -299,15 +328,29 @@ def vbhmm_learn_batch(subjects: list, K, vbopt: dict | None = None) -> list:
     best = [None] * len(subjects)
     score = [-np.inf] * len(subjects)
     per_k = [[None] * len(Ks) for _ in subjects]
+    device_gmm = opt["initmode"] == "random" and opt.get("gmm_init", "sklearn") == "device"
     with _fb.SequenceSet(flat) as seqs:
+        npts = [int(seqs.T[start[s]:start[s + 1]].sum()) for s in range(len(subjects))]
         for ki, k in enumerate(Ks):
             runs, inits, owner = [], [], []
             for s, sub in enumerate(subjects):
                 for t in range(trials):
-                    seed = None if opt.get("seed") is None else int(opt["seed"]) + t
-                    inits.append(vbhmm_init(sub, k, dict(opt, seed=seed)))
                     runs.append((int(start[s]), int(start[s + 1])))
                     owner.append(s)
+            if device_gmm and k > 1 and min(npts) > k:
+                # all runs' GMM fits in one launch; the start points are drawn as vbhmm_init's 'randSample' start would
+                starts = []
+                for s in range(len(subjects)):
+                    for t in range(trials):
+                        rng = np.random.Generator(np.random.PCG64((0 if opt.get("seed") is None else int(opt["seed"])) + t + 7919 * s))
+                        starts.append(rng.choice(npts[s], size=k, replace=False))
+                gmms = gmm_fit_batch(seqs, runs, k, starts)
+                inits = [vbhmm_init((npts[o], seqs.dim), k, dict(opt, initmode="initgmm", initgmm=g)) for g, o in zip(gmms, owner)]
+            else:
+                for s, sub in enumerate(subjects):
+                    for t in range(trials):
+                        seed = None if opt.get("seed") is None else int(opt["seed"]) + t
+                        inits.append(vbhmm_init(sub, k, dict(opt, seed=seed)))
             hmms, _ = vbhmm_em_batch(seqs, runs, k, opt, inits)
             for s in range(len(subjects)):
                 mine = [h for h, o in zip(hmms, owner) if o == s]

@@ -287,6 +287,19 @@ int vbhmm_batch_fetch(vbhmm_batch_t *batch, double *alpha, double *epsilon, doub
 int vbhmm_batch_last_ms(vbhmm_batch_t *batch, double *ms);
 int vbhmm_batch_free(vbhmm_batch_t *batch);
 
+/* Batched Gaussian-mixture fits for the random initialisation of the runs above: the K-component full-covariance GMM
+ * that /root/reference/src/hmm/vbhmm_init.m:43-61 fits to a run's pooled observations with
+ * gmdistribution.fit(data, K, 'Options', struct('TolFun', 1e-5), 'Start', 'randSample') -- EM from K randomly chosen
+ * observations -- once per random trial (vbhmm_learn.m:465-557); one block per run on the device.
+ *   start_seq[K,R], start_t[K,R]: the observation (sequence index, time step) that starts component k of run r (the
+ *     caller draws them); every component starts with the diagonal of the pooled covariance and weight 1/K.
+ *   stops when |ll - ll_old| < tol |ll| (TolFun) or after max_iter iterations; reg is added to every covariance diagonal.
+ *   outputs (HOST): weights[K,R], means[dim,K,R], covs[dim,dim,K,R], loglik[R] (may be NULL), iters[R] (may be NULL).
+ * The toolbox's fit is the Statistics Toolbox's (proprietary); this is the textbook EM, pinned on oracle/numpy_ref.gmm_em. */
+int vbhmm_gmm_fit(vbhmm_data_t *data, int R, const int32_t *seq_lo, const int32_t *seq_hi, int K,
+                  const int32_t *start_seq, const int32_t *start_t, int max_iter, double tol, double reg,
+                  double *weights, double *means, double *covs, double *loglik, int32_t *iters);
+
 /* Phase timing of the handle's E-steps, for bench.py: when enabled, CUDA events are
  * recorded on the handle's stream around each phase and vbhem_last_timings() returns the
  * milliseconds of the last E-step:

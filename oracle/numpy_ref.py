@@ -491,3 +491,40 @@ def vbhmm_em(data: list, varpar0: dict, ini: dict, fb=None) -> dict:
     trans = vp["epsilon"] / np.where(rs == 0, 1.0, rs)                                              # :434-439
     return dict(varpar=vp, LL=L, LLs=np.array(LLs), iter=it, prior=prior, trans=trans, mean=vp["m"].copy(), cov=C,
                 M=st["M"], N1=st["Nk1"], N=st["Nk"], unstable=unstable)
+
+
+def gmm_em(points: np.ndarray, start_idx, K: int, max_iter: int = 100, tol: float = 1e-5, reg: float = 1e-10) -> dict:
+    """The textbook GMM EM that csrc/vbhmm_gmm.inl runs per block (stand-in for the Statistics Toolbox's
+    gmdistribution.fit of /root/reference/src/hmm/vbhmm_init.m:60-61): start from the observations ``start_idx`` as
+    means, the diagonal of the pooled covariance, weights 1/K; stop on |dll| < tol |ll| or max_iter."""
+    X = np.asarray(points, float)
+    n, d = X.shape
+    gmean = X.mean(0)
+    gvar = ((X - gmean) ** 2).sum(0) / (n - 1 if n > 1 else 1) + reg
+    mu = X[np.asarray(start_idx)].copy()
+    cov = np.tile(np.diag(gvar), (K, 1, 1))
+    w = np.full(K, 1.0 / K)
+    ll_old, it = 0.0, 0
+    for it in range(1, max_iter + 1):
+        P = np.linalg.inv(cov)
+        logdet = np.linalg.slogdet(cov)[1]
+        df = X[:, None, :] - mu[None]
+        q = np.einsum("nki,kij,nkj->nk", df, P, df)
+        lp = np.log(w)[None] - 0.5 * (d * np.log(2 * np.pi) + logdet[None] + q)
+        mx = lp.max(1, keepdims=True)
+        e = np.exp(lp - mx)
+        s = e.sum(1, keepdims=True)
+        ll = float((mx + np.log(s)).sum())
+        g = e / s
+        Nk = g.sum(0)
+        Xc = X - gmean
+        for k in range(K):
+            if Nk[k] > 1e-300:
+                w[k] = Nk[k] / n
+                dk = (g[:, k, None] * Xc).sum(0) / Nk[k]
+                mu[k] = gmean + dk
+                cov[k] = np.einsum("n,ni,nj->ij", g[:, k], Xc, Xc) / Nk[k] - np.outer(dk, dk) + reg * np.eye(d)
+        if it > 1 and abs(ll - ll_old) < tol * abs(ll):
+            break
+        ll_old = ll
+    return dict(prior=w, mean=mu, cov=(cov + np.transpose(cov, (0, 2, 1))) / 2, loglik=ll, iters=it)

@@ -244,3 +244,64 @@ def test_cluster_with_wtkmeans_and_auto_init():
     np.testing.assert_allclose(runs["auto"]["trials_LL"][:, :, 0::2], runs["baseem"]["trials_LL"][:, :, 0::2], rtol=1e-12)
     np.testing.assert_allclose(runs["auto"]["trials_LL"][:, :, 1::2], runs["wtkmeans"]["trials_LL"][:, :, 1::2], rtol=1e-12)
     assert runs["auto"]["LL"] >= min(runs["baseem"]["LL"], runs["wtkmeans"]["LL"]) - 1e-9 * abs(runs["auto"]["LL"])
+
+
+def test_oracle_gmm_em_recovers_a_mixture():
+    """oracle/numpy_ref.gmm_em (the algorithm of csrc/vbhmm_gmm.inl): likelihood never falls, a well-separated
+    two-component mixture is recovered."""
+    rng = np.random.default_rng(5)
+    X = np.concatenate([rng.normal([0, 0], 1.0, (300, 2)), rng.normal([6, 5], [1.5, 0.5], (200, 2))])
+    lls = [nr.gmm_em(X, [3, 400], 2, max_iter=m)["loglik"] for m in (1, 2, 3, 5, 10)]
+    assert np.all(np.diff(lls) > -1e-9)
+    g = nr.gmm_em(X, [3, 400], 2)
+    order = np.argsort(g["mean"][:, 0])
+    np.testing.assert_allclose(g["mean"][order], [[0, 0], [6, 5]], atol=0.25)
+    np.testing.assert_allclose(g["prior"][order], [0.6, 0.4], atol=0.02)
+    assert g["iters"] < 100
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("K,dim", [(2, 2), (3, 2), (4, 3), (1, 1)])
+def test_device_gmm_fits_match_oracle(K, dim):
+    """vbhmm_gmm_fit (one block per run) against oracle gmm_em from the same start points; runs of different sizes,
+    two starts per subject.  After 5 EM iterations: log-likelihood 1e-10, parameters 1e-9.  Run on (EM amplifies
+    rounding differences where components overlap): iterations equal, log-likelihood 1e-5."""
+    from vbhem_b200 import fb
+    subjects = [make_sequences(n=6 + 4 * s, K=max(K, 2), dim=dim, seed=90 + s, tmin=1)[0] for s in range(4)]
+    flat = [x for sub in subjects for x in sub]
+    start = np.concatenate([[0], np.cumsum([len(sub) for sub in subjects])])
+    rng = np.random.default_rng(1)
+    runs, starts, pts = [], [], []
+    for s, sub in enumerate(subjects):
+        P = np.concatenate(sub)
+        for _ in range(2):
+            runs.append((int(start[s]), int(start[s + 1])))
+            starts.append(rng.choice(len(P), size=K, replace=False))
+            pts.append(P)
+    with fb.SequenceSet(flat) as seqs:
+        short = H.gmm_fit_batch(seqs, runs, K, starts, max_iter=5, tol=0.0)
+        full = H.gmm_fit_batch(seqs, runs, K, starts, max_iter=60, tol=1e-6)
+    for g, f, P, st in zip(short, full, pts, starts):
+        want = nr.gmm_em(P, st, K, max_iter=5, tol=0.0)
+        assert g["iters"] == want["iters"] == 5
+        np.testing.assert_allclose(g["loglik"], want["loglik"], rtol=1e-10)
+        np.testing.assert_allclose(g["prior"], want["prior"], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(g["mean"], want["mean"], rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(g["cov"], want["cov"], rtol=1e-8, atol=1e-9)
+        want = nr.gmm_em(P, st, K, max_iter=60, tol=1e-6)
+        assert f["iters"] == want["iters"]
+        np.testing.assert_allclose(f["loglik"], want["loglik"], rtol=1e-5)
+        np.testing.assert_allclose(f["prior"].sum(), 1.0, rtol=1e-12)
+
+
+@pytest.mark.gpu
+def test_learn_batch_with_device_gmm_init():
+    """vbhmm_learn_batch(gmm_init='device'): the random-initialisation GMMs come from the GPU; the learnt models are
+    as good as with the host fits (same data, same number of trials) and find the generating state count."""
+    subjects = [make_sequences(n=12, K=2, seed=60 + s, tmin=6)[0] for s in range(4)]
+    opt = dict(numTrials=4, seed=5, maxIter=60)
+    host = H.vbhmm_learn_batch(subjects, [1, 2, 3], opt)
+    dev = H.vbhmm_learn_batch(subjects, [1, 2, 3], dict(opt, gmm_init="device"))
+    for h, d in zip(host, dev):
+        assert d["K"] == h["K"] == 2
+        assert d["LL"] >= h["LL"] - 1e-3 * abs(h["LL"])
