@@ -511,11 +511,12 @@ def vbhem_h3m_cluster(hmms, K, S, vbhemopt: dict | None = None, covmode: str = "
             hyp, group = stack_h3ms(models[lo:hi])
             bs.em_begin(hyp, opt, group=group)
             run = bs.em_run_groups(int(opt["tau"]), int(opt["max_iter"]), float(opt["minDiff"]))
+            first = np.concatenate([[0], np.cumsum([m["eta"].shape[0] for m in models[lo:hi]])])
             for g in range(hi - lo):
                 ki, si, t = cand[lo + g]
                 if len(run["LogLs"][g]) and not run["unstable"][g]:
                     LL[ki, si, t] = run["LogLs"][g][-1]
-                finals[lo + g] = _slice_h3m(run["hyp"], group == g, models[lo + g]["eta"].shape[1])
+                finals[lo + g] = _slice_h3m(run["hyp"], slice(int(first[g]), int(first[g + 1])), models[lo + g]["eta"].shape[1])
                 iters_all[lo + g] = run["iters"][g]
             lo = hi
         clock.append(time.perf_counter())
