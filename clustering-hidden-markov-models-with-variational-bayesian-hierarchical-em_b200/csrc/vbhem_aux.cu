@@ -284,31 +284,46 @@ __global__ void k_list_scan_blocks(int nblocks, int K, const int *cnt, int *offs
 }
 
 // seg_start[j], chunk_start[j] (K+1 entries each): exclusive prefix over centres; totals = {#active, #chunks}.
-__global__ void k_list_scan_centres(int K, int chunk_len, const int *segcnt, int *seg_start, int *chunk_start,
-                                    int *totals) {
+__global__ void k_list_scan_centres(int K, int chunk_len, int target_chunks, const int *segcnt, int *seg_start,
+                                    int *chunk_start, int *totals) {
   // one warp; lane l owns the contiguous range [l * per, (l + 1) * per) of centres
   const int lane = threadIdx.x, per = (K + 31) / 32;
   const int ja = min(K, lane * per), jb = min(K, ja + per);
-  int a = 0, c = 0;
-  for (int j = ja; j < jb; j++) { a += segcnt[j]; c += (segcnt[j] + chunk_len - 1) / chunk_len; }
-  int ia = a, ic = c;
+  int a = 0;
+  for (int j = ja; j < jb; j++) a += segcnt[j];
+  int ia = a;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    const int ta = __shfl_up_sync(0xffffffffu, ia, o), tc = __shfl_up_sync(0xffffffffu, ic, o);
-    if (lane >= o) { ia += ta; ic += tc; }
+    const int ta = __shfl_up_sync(0xffffffffu, ia, o);
+    if (lane >= o) ia += ta;
+  }
+  const int total = __shfl_sync(0xffffffffu, ia, 31);
+  // chunk length: chunk_len when there is work for every warp of the second pass, else halved until there are
+  // about target_chunks chunks (a shard of a multi-GPU run, a small base set): the statistic partials of a
+  // chunk are one warp's serial work
+  int len = chunk_len;
+  while (len > 1 && total / len < target_chunks) len >>= 1;
+  int c = 0;
+  for (int j = ja; j < jb; j++) c += (segcnt[j] + len - 1) / len;
+  int ic = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int tc = __shfl_up_sync(0xffffffffu, ic, o);
+    if (lane >= o) ic += tc;
   }
   int ra = ia - a, rc = ic - c;   // exclusive prefixes
   for (int j = ja; j < jb; j++) {
     seg_start[j] = ra;
     chunk_start[j] = rc;
     ra += segcnt[j];
-    rc += (segcnt[j] + chunk_len - 1) / chunk_len;
+    rc += (segcnt[j] + len - 1) / len;
   }
   if (lane == 31) {
     seg_start[K] = ia;
     chunk_start[K] = ic;
     totals[0] = ia;
     totals[1] = ic;
+    totals[2] = len;
   }
 }
 
@@ -517,10 +532,10 @@ int launch_zhat(int N, int K, int ngroups, const int *gstart, const double *L_el
 
 int zhat_block_size() { return kZThreads; }
 
-int launch_list_scan(int N, int K, int chunk_len, const int *cnt, int *offs, int *segcnt, int *seg_start,
-                     int *chunk_start, int *totals, cudaStream_t st) {
+int launch_list_scan(int N, int K, int chunk_len, int target_chunks, const int *cnt, int *offs, int *segcnt,
+                     int *seg_start, int *chunk_start, int *totals, cudaStream_t st) {
   k_list_scan_blocks<<<(K + 3) / 4, 128, 0, st>>>(zhat_blocks(N), K, cnt, offs, segcnt);
-  k_list_scan_centres<<<1, 32, 0, st>>>(K, chunk_len, segcnt, seg_start, chunk_start, totals);
+  k_list_scan_centres<<<1, 32, 0, st>>>(K, chunk_len, target_chunks, segcnt, seg_start, chunk_start, totals);
   return 2;
 }
 

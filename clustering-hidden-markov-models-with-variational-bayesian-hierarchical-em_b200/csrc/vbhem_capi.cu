@@ -75,7 +75,14 @@ struct DevBuf {
   template <typename T> T *as() const { return static_cast<T *>(p); }
 };
 
-constexpr int kChunkLen = 16;
+constexpr int kChunkLen = 16;   // pairs per second-pass chunk (one warp's serial work); shorter when pairs are few
+// chunks wanted before the chunk length is halved: two per warp of the second-pass grid (one 16-warp CTA per SM)
+int second_pass_warps() {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return 2 * 16 * sms;
+}
 
 }  // namespace
 
@@ -460,7 +467,7 @@ int estep_device(vbhem_base *h, const CentreArgs &a, double *stats_dev, double *
   CU(h->lbp.ensure(sizeof(double) * (size_t)nb * 2 * a.ngroups));
   CU(h->cnt.ensure(sizeof(int) * (size_t)nb * K));
   CU(h->offs.ensure(sizeof(int) * (size_t)nb * K));
-  CU(h->segs.ensure(sizeof(int) * (size_t)(3 * (K + 1) + 2)));
+  CU(h->segs.ensure(sizeof(int) * (size_t)(3 * (K + 1) + 3)));
   StatsPtr S = carve_stats(stats_dev, K, r, d, dd, a.ngroups);
   if (io && cd.C.rec && lattice_supported(h->B, cd.C, T, false)) {
     rc = streamed_front(h, cd, a, *io, S, launches);
@@ -484,18 +491,18 @@ int estep_device(vbhem_base *h, const CentreArgs &a, double *stats_dev, double *
     }
   }
   int *seg_start = h->segs.as<int>(), *chunk_start = seg_start + (K + 1), *totals = chunk_start + (K + 1);
-  int *segcnt = totals + 2;
-  launches += launch_list_scan(N, K, kChunkLen, h->cnt.as<int>(), h->offs.as<int>(), segcnt, seg_start, chunk_start,
+  int *segcnt = totals + 3;
+  launches += launch_list_scan(N, K, kChunkLen, second_pass_warps(), h->cnt.as<int>(), h->offs.as<int>(), segcnt, seg_start, chunk_start,
                                totals, h->st);
-  CU(cudaMemcpyAsync(h->h_totals, totals, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  CU(cudaMemcpyAsync(h->h_totals, totals, 3 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
   CU(cudaStreamSynchronize(h->st));
-  const int nact = h->h_totals[0], nch = h->h_totals[1];
+  const int nact = h->h_totals[0], nch = h->h_totals[1], clen = h->h_totals[2];
   h->counters[3] = nact;
   const int per = stat_per(r, d, dd);
   CU(h->items.ensure(sizeof(PairItem) * (size_t)(nact > 0 ? nact : 1)));
   CU(h->chunks.ensure(sizeof(int2) * (size_t)(nch > 0 ? nch : 1)));
   CU(h->partial.ensure(sizeof(double) * (size_t)per * (nch > 0 ? nch : 1)));
-  launches += launch_list_fill(N, K, kChunkLen, nch, h->z.as<double>(), h->B.Ntilde, h->offs.as<int>(), seg_start,
+  launches += launch_list_fill(N, K, clen, nch, h->z.as<double>(), h->B.Ntilde, h->offs.as<int>(), seg_start,
                                chunk_start, h->items.as<PairItem>(), h->chunks.as<int2>(), h->st);
   mark(3);
   if (nch > 0) {

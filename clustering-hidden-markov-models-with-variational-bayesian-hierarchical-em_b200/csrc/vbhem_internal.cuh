@@ -111,9 +111,10 @@ int launch_zhat(int N, int K, int ngroups, const int *gstart, const double *L_el
                 const double *Ntilde, double *zhat, double *Nj_part, int *cnt, double *lb_part, double *Nj, double *lb,
                 cudaStream_t st, int blk0 = 0, int nblk = -1, bool reduce = true);
 int zhat_block_size();
-// deterministic (centre-major, base-ascending) list of those pairs, cut in chunks of chunk_len
-int launch_list_scan(int N, int K, int chunk_len, const int *cnt, int *offs, int *segcnt, int *seg_start,
-                     int *chunk_start, int *totals, cudaStream_t st);
+// deterministic (centre-major, base-ascending) list of those pairs, cut in chunks of at most chunk_len (shorter,
+// totals[2], when there are fewer than target_chunks of them); totals = {#active, #chunks, chunk length}
+int launch_list_scan(int N, int K, int chunk_len, int target_chunks, const int *cnt, int *offs, int *segcnt,
+                     int *seg_start, int *chunk_start, int *totals, cudaStream_t st);
 int launch_list_fill(int N, int K, int chunk_len, int nchunks, const double *zhat, const double *Ntilde,
                      const int *offs, const int *seg_start, const int *chunk_start, PairItem *items, int2 *chunks,
                      cudaStream_t st);
