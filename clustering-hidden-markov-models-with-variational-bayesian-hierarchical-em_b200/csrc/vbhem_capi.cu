@@ -75,6 +75,25 @@ struct DevBuf {
   template <typename T> T *as() const { return static_cast<T *>(p); }
 };
 
+// Pinned host staging area: small uploads copied here first travel as truly asynchronous copies (a cudaMemcpyAsync
+// from pageable memory blocks the host for a staged copy each).  Re-used by the next call, which is safe because every
+// E-step synchronises its stream (the active-pair totals) after the uploads were enqueued.
+struct PinBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    const size_t want = bytes + bytes / 4 + 4096;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
 constexpr int kChunkLen = 16;   // pairs per second-pass chunk (one warp's serial work); shorter when pairs are few
 // chunks wanted before the chunk length is halved: two per warp of the second-pass grid (one 16-warp CTA per SM)
 int second_pass_warps() {
@@ -110,6 +129,7 @@ struct vbhem_base {
     double *h_lb = nullptr;   // pinned
   } em;
   int *h_totals = nullptr;   // pinned
+  PinBuf stage;              // pinned staging of the per-call centre uploads (stage_centres)
   bool profile = false;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   double timings[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -184,19 +204,27 @@ struct CentreDev {
 // hyper-parameters) and build the lattice records.  `launches` is incremented.
 int stage_centres(vbhem_base *h, const CentreArgs &a, CentreDev &cd, double *pre_host, long long &launches) {
   const int K = a.K, r = a.maxSr, d = h->B.d, dd = h->B.dd;
+  const size_t nK = K, nr = (size_t)r * K, nrr = (size_t)r * r * K;
+  // pinned staging: ints [Sr K | gstart ng+1 | tile lists <= 2K+2] then doubles (what this call uploads)
+  const size_t n_int = (size_t)K + a.ngroups + 1 + 2 * (size_t)K + 4;
+  const size_t int_bytes = (n_int * sizeof(int) + 15) / 16 * 16;
+  const size_t n_dbl = d * nr + (a.hyp ? nK + nr + nrr + dd * nr + nr + nr : nK + nr + nrr + nr + dd * nr);
+  CU(h->stage.ensure(int_bytes + sizeof(double) * n_dbl));
+  int *s_int = static_cast<int *>(h->stage.p);
+  double *s_dbl = reinterpret_cast<double *>(static_cast<char *>(h->stage.p) + int_bytes);
   CU(h->cen_i.ensure(sizeof(int) * (size_t)(K + a.ngroups + 1)));
   int *dSr = h->cen_i.as<int>();
   int *dgs = dSr + K;
-  std::vector<int> gs(a.ngroups + 1, 0);
+  memcpy(s_int, a.Sr, sizeof(int) * K);
+  int *gs = s_int + K;
+  for (int g = 0; g <= a.ngroups; g++) gs[g] = 0;
   if (a.group) {
     for (int j = 0; j < K; j++) gs[a.group[j] + 1] = j + 1;
   } else {
     gs[1] = K;
   }
-  CU(cudaMemcpyAsync(dSr, a.Sr, sizeof(int) * K, cudaMemcpyHostToDevice, h->st));
-  CU(cudaMemcpyAsync(dgs, gs.data(), sizeof(int) * (a.ngroups + 1), cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(dSr, s_int, sizeof(int) * (size_t)(K + a.ngroups + 1), cudaMemcpyHostToDevice, h->st));
   // log-domain block: logOmega[K] | logPi[rK] | logA[rrK] | logLam[rK] | cterm[rK] | m[d r K] | vW[dd r K]
-  const size_t nK = K, nr = (size_t)r * K, nrr = (size_t)r * r * K;
   const size_t tot = nK + nr + nrr + nr + nr + d * nr + dd * nr;
   CU(h->cen_d.ensure(sizeof(double) * tot));
   double *p = h->cen_d.as<double>();
@@ -207,10 +235,14 @@ int stage_centres(vbhem_base *h, const CentreArgs &a, CentreDev &cd, double *pre
   double *dCt = p; p += nr;
   double *dm = p; p += d * nr;
   double *dvW = p;
-  if (a.hyp && a.resident)
+  double *sm = s_dbl;            // staged means
+  double *srest = s_dbl + d * nr;
+  if (a.hyp && a.resident) {
     CU(cudaMemcpyAsync(dm, h->em.m.p, sizeof(double) * d * nr, cudaMemcpyDeviceToDevice, h->st));
-  else
-    CU(cudaMemcpyAsync(dm, a.m, sizeof(double) * d * nr, cudaMemcpyHostToDevice, h->st));
+  } else {
+    memcpy(sm, a.m, sizeof(double) * d * nr);
+    CU(cudaMemcpyAsync(dm, sm, sizeof(double) * d * nr, cudaMemcpyHostToDevice, h->st));
+  }
   if (a.hyp) {
     const size_t th = nK + nr + nrr + dd * nr + nr + nr;
     CU(h->hyp_d.ensure(sizeof(double) * th));
@@ -221,24 +253,32 @@ int stage_centres(vbhem_base *h, const CentreArgs &a, CentreDev &cd, double *pre
     double *hW = q; q += dd * nr;
     double *hv = q; q += nr;
     double *hl = q;
-    if (!a.resident) {
-      CU(cudaMemcpyAsync(hal, a.alpha, sizeof(double) * nK, cudaMemcpyHostToDevice, h->st));
-      CU(cudaMemcpyAsync(het, a.eta, sizeof(double) * nr, cudaMemcpyHostToDevice, h->st));
-      CU(cudaMemcpyAsync(hep, a.epsilon, sizeof(double) * nrr, cudaMemcpyHostToDevice, h->st));
-      CU(cudaMemcpyAsync(hW, a.W, sizeof(double) * dd * nr, cudaMemcpyHostToDevice, h->st));
-      CU(cudaMemcpyAsync(hv, a.v, sizeof(double) * nr, cudaMemcpyHostToDevice, h->st));
-      CU(cudaMemcpyAsync(hl, a.lambda, sizeof(double) * nr, cudaMemcpyHostToDevice, h->st));
+    if (!a.resident) {   // alpha | eta | epsilon | W | v | lambda are contiguous on the device: one upload
+      double *w = srest;
+      memcpy(w, a.alpha, sizeof(double) * nK); w += nK;
+      memcpy(w, a.eta, sizeof(double) * nr); w += nr;
+      memcpy(w, a.epsilon, sizeof(double) * nrr); w += nrr;
+      memcpy(w, a.W, sizeof(double) * dd * nr); w += dd * nr;
+      memcpy(w, a.v, sizeof(double) * nr); w += nr;
+      memcpy(w, a.lambda, sizeof(double) * nr);
+      CU(cudaMemcpyAsync(hal, srest, sizeof(double) * th, cudaMemcpyHostToDevice, h->st));
     }
     launches += launch_prepass(K, r, d, h->B.covmode, dSr, dgs, a.ngroups, hal, het, hep, hW, hv, hl, dOm, dPi, dA,
                                dLam, dCt, dvW, h->st);
     if (pre_host)   // logOmega | logPi | logA | logLambdaTilde are contiguous by construction
       CU(cudaMemcpyAsync(pre_host, dOm, sizeof(double) * (nK + nr + nrr + nr), cudaMemcpyDeviceToHost, h->st));
   } else {
-    if (a.logOmega) CU(cudaMemcpyAsync(dOm, a.logOmega, sizeof(double) * nK, cudaMemcpyHostToDevice, h->st));
-    CU(cudaMemcpyAsync(dPi, a.logPi, sizeof(double) * nr, cudaMemcpyHostToDevice, h->st));
-    CU(cudaMemcpyAsync(dA, a.logA, sizeof(double) * nrr, cudaMemcpyHostToDevice, h->st));
-    CU(cudaMemcpyAsync(dCt, a.cterm, sizeof(double) * nr, cudaMemcpyHostToDevice, h->st));
-    CU(cudaMemcpyAsync(dvW, a.vW, sizeof(double) * dd * nr, cudaMemcpyHostToDevice, h->st));
+    // logOmega | logPi | logA are contiguous on the device; cterm and vW follow separately
+    double *w = srest;
+    if (a.logOmega) memcpy(w, a.logOmega, sizeof(double) * nK); else memset(w, 0, sizeof(double) * nK);
+    memcpy(w + nK, a.logPi, sizeof(double) * nr);
+    memcpy(w + nK + nr, a.logA, sizeof(double) * nrr);
+    CU(cudaMemcpyAsync(dOm, w, sizeof(double) * (nK + nr + nrr), cudaMemcpyHostToDevice, h->st));
+    double *w2 = w + nK + nr + nrr;
+    memcpy(w2, a.cterm, sizeof(double) * nr);
+    CU(cudaMemcpyAsync(dCt, w2, sizeof(double) * nr, cudaMemcpyHostToDevice, h->st));
+    memcpy(w2 + nr, a.vW, sizeof(double) * dd * nr);
+    CU(cudaMemcpyAsync(dvW, w2 + nr, sizeof(double) * dd * nr, cudaMemcpyHostToDevice, h->st));
   }
   cd.C.K = K; cd.C.maxSr = r; cd.C.Sr = dSr; cd.C.group = nullptr;
   cd.C.logPi = dPi; cd.C.logA = dA; cd.C.m = dm; cd.C.vW = dvW; cd.C.cterm = dCt; cd.C.logOmega = dOm;
@@ -287,8 +327,9 @@ int stage_centres(vbhem_base *h, const CentreArgs &a, CentreDev &cd, double *pre
       ntile_pairs += cd.C.npairs[c];
     }
     CU(h->tile_i.ensure(sizeof(int) * (lists.size() + 1)));
-    CU(cudaMemcpyAsync(h->tile_i.p, lists.data(), sizeof(int) * lists.size(), cudaMemcpyHostToDevice, h->st));
-    CU(cudaStreamSynchronize(h->st));                      // `lists` goes out of scope
+    int *s_lists = s_int + K + a.ngroups + 1;              // pinned: outlives this scope, no synchronisation needed
+    memcpy(s_lists, lists.data(), sizeof(int) * lists.size());
+    CU(cudaMemcpyAsync(h->tile_i.p, s_lists, sizeof(int) * lists.size(), cudaMemcpyHostToDevice, h->st));
     cd.C.big_list = h->tile_i.as<int>();
     cd.C.nbig = (int)big.size();
     cd.C.pair_list = cd.C.big_list + big.size();
@@ -697,6 +738,7 @@ int vbhem_free_base(vbhem_base_t *h) {
                    &h->chunks, &h->partial, &h->itemflags, &h->scratch, &h->pairs_out, &h->stats};
   for (DevBuf *b : all) b->release();
   if (h->h_totals) cudaFreeHost(h->h_totals);
+  h->stage.release();
   for (int k = 0; k < 6; k++) if (h->ev[k]) cudaEventDestroy(h->ev[k]);
   if (h->own) cudaStreamDestroy(h->own);
   delete h;
