@@ -28,13 +28,18 @@ CASES = {
     "full_s8_d2_tau10": (dict(N=5, K=4, Sb=8, Sr=8, d=2, covmode="full", ragged=False, seed=1001), 10),
     "full_tau1": (dict(N=4, K=2, Sb=2, Sr=2, d=2, covmode="full", ragged=False, seed=3), 1),
     "exprmt1_shape": (dict(N=40, K=2, Sb=2, Sr=2, d=2, covmode="full", ragged=False, seed=7, Nv=100.0), 50),
+    # BASELINE configs[1] (demo/vbdemo_face.m:46-63): tens of subjects' HMMs with <= 3 states, K up to 5, Nv = 10, tau = 5
+    "face_shape": (dict(N=30, K=5, Sb=3, Sr=3, d=2, covmode="full", ragged=True, seed=17, Nv=10.0), 5),
 }
+ONLY = os.environ.get("GOLDEN_ONLY")   # regenerate one fixture without touching the others
 
 if __name__ == "__main__":
     assert os.path.exists("/root/reference/src/vbhem/vbhem_hmm_bwd_fwd_mex.c"), "needs the reference checkout"
     cref.build()
     here = os.path.dirname(os.path.abspath(__file__))
     for name, (kw, tau) in CASES.items():
+        if ONLY and name != ONLY:
+            continue
         base, hyp, cen = make_case(**kw)
         out = oracle_pairs(base, cen, tau, which="ref")
         blob = {f"base_{k}": v for k, v in base.items()}
@@ -46,6 +51,8 @@ if __name__ == "__main__":
         np.savez_compressed(os.path.join(here, name + ".npz"), **blob)
         print(name, "L_elbo[0,:]=", out["L_elbo"][0])
 
+    if ONLY:
+        sys.exit(0)
     # VB-HMM forward-backward (src/hmm/vbhmm_fb_mex.c compiled in place): ragged sequences incl. T = 1 and T = 0
     assert os.path.exists("/root/reference/src/hmm/vbhmm_fb_mex.c")
     from oracle import numpy_ref as nr
