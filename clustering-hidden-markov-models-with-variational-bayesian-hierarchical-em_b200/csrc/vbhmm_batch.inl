@@ -640,7 +640,9 @@ int vbhmm_batch_fetch(vbhmm_batch_t *b, double *alpha, double *epsilon, double *
     const double *s = hs.data() + pers * r;                           // Nk1 | Nk | M[from][to]
     if (Nk1) memcpy(Nk1 + (size_t)K * r, s, sizeof(double) * K);
     if (Nk) memcpy(Nk + (size_t)K * r, s + K, sizeof(double) * K);
-    if (M) memcpy(M + (size_t)K * K * r, s + 2 * K, sizeof(double) * K * K);
+    if (M)   // BatchStats::M is [from][to]; the ABI is column-major [K(from), K(to), R] like epsilon
+      for (int from = 0; from < K; from++)
+        for (int to = 0; to < K; to++) M[from + K * (to + (size_t)K * r)] = s[2 * K + from * K + to];
     if (iters) iters[r] = st[r].it;
     if (unstable) unstable[r] = st[r].unstable;
   }

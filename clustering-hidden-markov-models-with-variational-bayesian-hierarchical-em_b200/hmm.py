@@ -281,7 +281,7 @@ def vbhmm_em_batch(seqs: _fb.SequenceSet, runs, K: int, ini: dict, inits: list) 
         hm = _hmm_from_varpar(vp, K)
         n = int(o["it"][r])
         hm.update(LL=float(o["LLs"][r, n - 1]), LLs=o["LLs"][r, :n].copy(), iter=n, unstable=bool(o["bad"][r]),
-                  M=o["M"][r].copy(), N1=o["Nk1"][r].copy(), N=o["Nk"][r].copy())
+                  M=o["M"][r].T.copy(), N1=o["Nk1"][r].copy(), N=o["Nk"][r].copy())
         out.append(hm)
     return out, dict(passes=passes.value, device_ms=ms.value)
 

@@ -272,10 +272,11 @@ int vbhmm_fb_last_ms(vbhmm_data_t *data, double *ms);
  *     initial variational parameters of every run, MATLAB layouts with the run as the last index:
  *     alpha[K,R], epsilon[K(from),K(to),R], beta[K,R], v[K,R], m[dim,K,R], W[dim,dim,K,R].  K <= 8, dim <= 3.
  *   vbhmm_batch_run: runs every run to its own end; *passes = passes of the slowest run.
- *   vbhmm_batch_fetch (any pointer may be NULL): final parameters (same layouts), the last E-step's Nk1[K,R]
- *     (+1e-50), Nk[K,R] (+1e-50), M[K(to)... stored [K(from) x K(to)] ROW-major per run], LLs[R][max_iter] (0 beyond
- *     a run's own passes), iters[R] = passes made, unstable[R] = the NaN guard of vbhmm_em.m:320-330 fired (then the
- *     parameters are those before that pass and the last LL is -Inf). */
+ *   vbhmm_batch_fetch (any pointer may be NULL): final parameters (same layouts), the last E-step's N1[K,R] and
+ *     N[K,R] (both with the +1e-50 of vbhmm_em.m:163,172) and M[K(from),K(to),R] (vbhmm_em.m:178), LLs[max_iter,R]
+ *     (column r = run r's trace, 0 beyond its own passes), iters[R] = passes made,
+ *     unstable[R] = the NaN guard of vbhmm_em.m:320-330 fired (then the parameters are those before that pass and the
+ *     last LL is -Inf). */
 typedef struct vbhmm_batch vbhmm_batch_t;
 int vbhmm_batch_begin(vbhmm_data_t *data, int R, const int32_t *seq_lo, const int32_t *seq_hi, int K, double alpha0,
                       double epsilon0, double beta0, double v0, const double *m0, const double *W0, int nW0,

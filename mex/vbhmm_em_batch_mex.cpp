@@ -118,15 +118,11 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
     plhs[8] = array3(K, K, R);
     plhs[9] = mxCreateDoubleMatrix(max_iter, R, mxREAL);
     plhs[10] = mxCreateDoubleMatrix(2, R, mxREAL);
-    std::vector<double> Mrow((size_t)K * K * R);
     std::vector<int32_t> it(R), bad(R);
     rc = vbhmm_batch_fetch(b, mxGetPr(plhs[0]), mxGetPr(plhs[1]), mxGetPr(plhs[2]), mxGetPr(plhs[3]), mxGetPr(plhs[4]),
-                           mxGetPr(plhs[5]), mxGetPr(plhs[6]), mxGetPr(plhs[7]), Mrow.data(), mxGetPr(plhs[9]), it.data(),
-                           bad.data());
-    double *Mo = mxGetPr(plhs[8]);
+                           mxGetPr(plhs[5]), mxGetPr(plhs[6]), mxGetPr(plhs[7]), mxGetPr(plhs[8]), mxGetPr(plhs[9]),
+                           it.data(), bad.data());
     for (int r = 0; r < R; r++) {
-      for (int from = 0; from < K; from++)                 // the library returns M row-major per run; MATLAB wants (from, to)
-        for (int to = 0; to < K; to++) Mo[from + K * (to + (size_t)K * r)] = Mrow[(size_t)K * K * r + from * K + to];
       mxGetPr(plhs[10])[2 * r] = it[r];
       mxGetPr(plhs[10])[2 * r + 1] = bad[r];
     }
