@@ -271,7 +271,7 @@ def vbhem_h3m_c_step_fc(h3m_r: dict, base, vbhemopt: dict, covmode: str = "full"
 # ----------------------------------------------------------------------------- user entry: (K, S) model selection
 CLUSTER_DEFAULTS = dict(alpha0=1.0, eta0=1.0, epsilon0=1.0, m0=(256.0, 192.0), W0=0.005, lambda0=1.0, v0=5.0,
                         trials=100, max_iter=200, minDiff=1e-5, Nv=100.0, tau=10, use_post=True, seed=None,
-                        initmode="baseem", learn_hyps=0)
+                        initmode="baseem", learn_hyps=0, remove_empty=1)
 """vbhem_h3m_cluster.m:141-179 (``initmode`` 'auto' of the reference tries 'baseem', 'gmmNew' and 'wtkmeans';
 'baseem' and 'wtkmeans' are mirrored -- the latter with scikit-learn's k-means in place of the Statistics Toolbox's
 -- and 'auto' means those two; 'gmmNew' needs ``gmdistribution.fit``).  ``learn_hyps`` defaults to 1 in the
@@ -450,6 +450,30 @@ def h3m_parameters(hyp: dict, covmode: str = "full") -> dict:
     return out
 
 
+def vbh3m_remove_empty(out: dict, thresh: float = 1.0) -> tuple[dict, np.ndarray]:
+    """[h3mo, emptyinds] = vbh3m_remove_empty(h3m, thresh)  (vbh3m_remove_empty.m:1-60) on the result of
+    ``vbhem_h3m_cluster``: drop the groups whose mass ``Nj`` is below ``thresh``; omega is re-normalised, ``Z``,
+    ``L_elbo``, ``label``, ``groups``, ``group_size``, the group HMMs' parameters and ``hyp`` follow."""
+    Nj = np.asarray(out["Nj"], float)
+    keep = np.flatnonzero(~(Nj < thresh))
+    gone = np.flatnonzero(Nj < thresh)
+    if gone.size == 0:
+        return out, gone
+    o = dict(out)
+    o["omega"] = out["omega"][keep] / out["omega"][keep].sum()
+    for k in ("Z", "L_elbo"):
+        o[k] = out[k][:, keep]
+    for k in ("Nj", "prior", "trans", "mean", "cov", "group_size"):
+        o[k] = np.asarray(out[k])[keep]
+    o["hyp"] = {k: np.asarray(v)[keep] for k, v in out["hyp"].items()}
+    remap = -np.ones(len(Nj), int)
+    remap[keep] = np.arange(keep.size)
+    o["label"] = remap[out["label"]]
+    o["groups"] = [out["groups"][j] for j in keep]
+    o["K"] = int(keep.size)
+    return o, gone
+
+
 def vbhem_h3m_cluster(hmms, K, S, vbhemopt: dict | None = None, covmode: str = "full", device: int = 0) -> dict:
     """[group_hmms] = vbhem_h3m_cluster(hmms, K, S, vbhemopt)  (vbhem_h3m_cluster.m:1): cluster HMMs into K groups
     with S states per group HMM; vectors of K and / or S select the model by the lower bound.
@@ -475,6 +499,9 @@ def vbhem_h3m_cluster(hmms, K, S, vbhemopt: dict | None = None, covmode: str = "
         raise ValueError("vbhemopt.seed has not been set. This is required to obtain reproducible results.")
     if opt["initmode"] not in ("baseem", "wtkmeans", "auto"):
         raise NotImplementedError(f"initmode {opt['initmode']!r}: 'baseem', 'wtkmeans' and 'auto' (both) are mirrored")
+    if not isinstance(hmms, dict) and opt["remove_empty"]:                   # vbhem_h3m_cluster.m:116-131
+        from .hmm import vbhmm_remove_empty
+        hmms = [h if h is None or "N" not in h else vbhmm_remove_empty(h, 1e-3)[0] for h in hmms]
     base = hmms if isinstance(hmms, dict) else hmms_to_h3m_hem(hmms, covmode, bool(opt["use_post"]), float(opt["Nv"]))
     d = base["mu"].shape[2]
     if opt["v0"] <= d - 1:

@@ -226,6 +226,26 @@ def vbhmm_learn(data: list, K, vbopt: dict | None = None) -> dict:
     return out
 
 
+def vbhmm_remove_empty(hmm: dict, thresh: float = 1.0) -> tuple[dict, np.ndarray]:
+    """[hmmo, emptyinds] = vbhmm_remove_empty(hmm, verbose, thresh)  (vbhmm_remove_empty.m:1-105): drop the states whose
+    occupancy ``hmm['N']`` is below ``thresh``; variational parameters, counts, prior / trans (re-normalised from the
+    remaining alpha / epsilon) and emissions follow.  Returns the HMM and the indices that were removed."""
+    N = np.asarray(hmm["N"], float)
+    keep = np.flatnonzero(~(N < thresh))
+    gone = np.flatnonzero(N < thresh)
+    if gone.size == 0:
+        return hmm, gone
+    vp = hmm["varpar"]
+    nv = dict(alpha=np.asarray(vp["alpha"])[keep], epsilon=np.asarray(vp["epsilon"])[np.ix_(keep, keep)],
+              beta=np.asarray(vp["beta"])[keep], v=np.asarray(vp["v"])[keep], m=np.asarray(vp["m"])[keep],
+              W=np.asarray(vp["W"])[keep])
+    out = dict(hmm)
+    out.update(varpar=nv, M=np.asarray(hmm["M"])[np.ix_(keep, keep)], N1=np.asarray(hmm["N1"])[keep], N=N[keep],
+               prior=nv["alpha"] / nv["alpha"].sum(), trans=nv["epsilon"] / nv["epsilon"].sum(1, keepdims=True),
+               mean=np.asarray(hmm["mean"])[keep], cov=np.asarray(hmm["cov"])[keep], K=int(keep.size))
+    return out, gone
+
+
 # ----------------------------------------------------------------------------- many runs at once, on the device
 def _hmm_from_varpar(vp: dict, K: int) -> dict:
     """vbhmm_em.m:391-460: point estimates from the final variational parameters."""

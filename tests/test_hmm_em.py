@@ -305,3 +305,29 @@ def test_learn_batch_with_device_gmm_init():
     for h, d in zip(host, dev):
         assert d["K"] == h["K"] == 2
         assert d["LL"] >= h["LL"] - 1e-3 * abs(h["LL"])
+
+
+def test_remove_empty_states_and_groups():
+    """vbhmm_remove_empty.m / vbh3m_remove_empty.m mirrors (pure host logic)."""
+    from vbhem_b200 import h3m
+    rng = np.random.default_rng(2)
+    vp = dict(alpha=np.array([3.0, 0.1, 5.0]), epsilon=rng.uniform(1, 4, (3, 3)), beta=np.array([4.0, 1.0, 6.0]),
+              v=np.array([8.0, 6.0, 9.0]), m=rng.normal(size=(3, 2)), W=np.stack([np.eye(2)] * 3))
+    hm = dict(varpar=vp, M=rng.uniform(size=(3, 3)), N1=np.array([2.0, 1e-9, 4.0]), N=np.array([30.0, 1e-8, 50.0]),
+              prior=vp["alpha"] / vp["alpha"].sum(), trans=vp["epsilon"] / vp["epsilon"].sum(1, keepdims=True),
+              mean=vp["m"].copy(), cov=np.stack([np.eye(2)] * 3), K=3)
+    out, gone = H.vbhmm_remove_empty(hm, 1e-3)
+    assert gone.tolist() == [1] and out["K"] == 2 and out["varpar"]["epsilon"].shape == (2, 2)
+    np.testing.assert_allclose(out["prior"], [3 / 8, 5 / 8])
+    np.testing.assert_allclose(out["trans"].sum(1), 1.0)
+    np.testing.assert_array_equal(out["mean"], hm["mean"][[0, 2]])
+    same, none = H.vbhmm_remove_empty(out, 1e-3)
+    assert same is out and none.size == 0
+    res = dict(K=3, Nj=np.array([12.0, 1e-40, 8.0]), omega=np.array([0.6, 0.0, 0.4]), Z=rng.uniform(size=(5, 3)),
+               L_elbo=rng.normal(size=(5, 3)), label=np.array([0, 2, 2, 0, 2]), groups=[np.array([0, 3]), np.array([], int),
+               np.array([1, 2, 4])], group_size=np.array([2, 0, 3]), prior=np.zeros((3, 2)), trans=np.zeros((3, 2, 2)),
+               mean=np.zeros((3, 2, 2)), cov=np.zeros((3, 2, 2, 2)), hyp=dict(alpha=np.ones(3), eta=np.ones((3, 2))))
+    o, gone = h3m.vbh3m_remove_empty(res)
+    assert gone.tolist() == [1] and o["K"] == 2 and o["Z"].shape == (5, 2) and o["label"].tolist() == [0, 1, 1, 0, 1]
+    assert o["group_size"].tolist() == [2, 3] and o["hyp"]["eta"].shape == (2, 2)
+    np.testing.assert_allclose(o["omega"], [0.6, 0.4])
