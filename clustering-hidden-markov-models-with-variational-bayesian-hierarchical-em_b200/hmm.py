@@ -317,13 +317,15 @@ def gmm_fit_batch(seqs: _fb.SequenceSet, runs, K: int, starts, max_iter: int = 1
     c = np.ascontiguousarray
     lo = c([a for a, _ in runs], dtype=np.int32)
     hi = c([b for _, b in runs], dtype=np.int32)
-    ss, st = np.zeros((R, K), np.int32), np.zeros((R, K), np.int32)
-    for r, (a, b) in enumerate(runs):
-        ends = np.cumsum(seqs.T[a:b])
-        idx = np.asarray(starts[r], int)
-        q = np.searchsorted(ends, idx, side="right")
-        ss[r] = a + q
-        st[r] = idx - np.where(q > 0, ends[np.maximum(q - 1, 0)], 0)
+    # pooled observation index of a run -> (sequence, time step): offset by the observations before the run's first
+    # sequence, then one search in the cumulative lengths of all sequences (vectorised over runs x components)
+    cum = np.concatenate([[0], np.cumsum(seqs.T.astype(np.int64))])
+    glob_idx = cum[lo.astype(np.int64)][:, None] + np.asarray(starts, np.int64).reshape(R, K)
+    if np.any(glob_idx < cum[lo][:, None]) or np.any(glob_idx >= cum[hi][:, None]):
+        raise ValueError("a start index lies outside its run's pooled observations")
+    seq_idx = np.searchsorted(cum, glob_idx, side="right") - 1
+    ss = c(seq_idx, dtype=np.int32)
+    st = c(glob_idx - cum[seq_idx], dtype=np.int32)
     w, mu, cv = np.zeros((R, K)), np.zeros((R, K, dim)), np.zeros((R, K, dim, dim))
     ll, it = np.zeros(R), np.zeros(R, np.int32)
     P = lambda a: a.ctypes.data_as(dp)
