@@ -375,11 +375,10 @@ def vbhmm_learn_batch(subjects: list, K, vbopt: dict | None = None) -> list:
                         inits.append(vbhmm_init(sub, k, dict(opt, seed=seed)))
             hmms, _ = vbhmm_em_batch(seqs, runs, k, opt, inits)
             for s in range(len(subjects)):
-                mine = [h for h, o in zip(hmms, owner) if o == s]
-                top = max(mine, key=lambda h: h["LL"])
+                top = max(hmms[s * trials:(s + 1) * trials], key=lambda h: h["LL"])    # runs are subject-major
                 per_k[s][ki] = top
                 sc = top["LL"] + gammaln(k + 1)
-                if sc > score[s]:
+                if best[s] is None or sc > score[s]:
                     score[s], best[s] = sc, top
     out = []
     for s in range(len(subjects)):
