@@ -106,6 +106,29 @@ def vbhmm_init(data, K: int, ini: dict) -> dict:
                 v=ini["v0"] + Nk + 1, m=(ini["beta0"] * m0[None] + Nk[:, None] * gmm["mean"]) / beta[:, None], W=W)
 
 
+def vbhmm_init_from_gmms(gmms: list, npts, K: int, ini: dict) -> list:
+    """``vbhmm_init`` (initmode 'initgmm', vbhmm_init.m:166-201) for many runs at once: ``gmms[r]`` = dict(prior, mean,
+    cov), ``npts[r]`` = the run's number of observations.  Same numbers as one ``vbhmm_init`` call per run."""
+    R = len(gmms)
+    pr = np.stack([np.asarray(g["prior"], float) for g in gmms])                        # [R, K]
+    mu = np.stack([np.asarray(g["mean"], float) for g in gmms])                         # [R, K, dim]
+    cv = np.stack([np.asarray(g["cov"], float) for g in gmms])                          # [R, K, dim, dim]
+    dim = mu.shape[2]
+    n = np.asarray(npts, float).reshape(R, 1)
+    m0 = np.asarray(ini["mu0"], float).reshape(dim)
+    W0inv, _ = _W0inv(ini, dim)
+    b0 = float(ini["beta0"])
+    Nk, Nk2 = n * pr, n / K
+    beta = b0 + Nk
+    d3 = mu - m0
+    W = np.linalg.inv(W0inv + Nk[..., None, None] * cv + (b0 * Nk / (b0 + Nk))[..., None, None] * d3[..., :, None] * d3[..., None, :])
+    alpha = ini["alpha0"] + np.broadcast_to(Nk2, (R, K))
+    eps = ini["epsilon0"] + np.broadcast_to(Nk2[:, :, None], (R, K, K))
+    m = (b0 * m0 + Nk[..., None] * mu) / beta[..., None]
+    v = ini["v0"] + Nk + 1
+    return [dict(alpha=alpha[r].copy(), epsilon=eps[r].copy(), beta=beta[r], v=v[r], m=m[r], W=W[r]) for r in range(R)]
+
+
 def vbhmm_mstep(st: dict, ini: dict) -> dict:
     """vbhmm_em.m:353-389 from the sums of one fused pass (``fb.fb_stats``)."""
     K, dim = st["xbar"].shape
@@ -367,7 +390,7 @@ def vbhmm_learn_batch(subjects: list, K, vbopt: dict | None = None) -> list:
                         rng = np.random.Generator(np.random.PCG64((0 if opt.get("seed") is None else int(opt["seed"])) + t + 7919 * s))
                         starts.append(rng.choice(npts[s], size=k, replace=False))
                 gmms = gmm_fit_batch(seqs, runs, k, starts)
-                inits = [vbhmm_init((npts[o], seqs.dim), k, dict(opt, initmode="initgmm", initgmm=g)) for g, o in zip(gmms, owner)]
+                inits = vbhmm_init_from_gmms(gmms, [npts[o] for o in owner], k, opt)
             else:
                 for s, sub in enumerate(subjects):
                     for t in range(trials):

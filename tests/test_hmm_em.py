@@ -331,3 +331,21 @@ def test_remove_empty_states_and_groups():
     assert gone.tolist() == [1] and o["K"] == 2 and o["Z"].shape == (5, 2) and o["label"].tolist() == [0, 1, 1, 0, 1]
     assert o["group_size"].tolist() == [2, 3] and o["hyp"]["eta"].shape == (2, 2)
     np.testing.assert_allclose(o["omega"], [0.6, 0.4])
+
+
+def test_batched_init_equals_single_init():
+    """hmm.vbhmm_init_from_gmms (all runs at once) gives exactly what one vbhmm_init('initgmm') call per run gives."""
+    rng = np.random.default_rng(9)
+    gmms, npts = [], []
+    for r in range(6):
+        A = rng.normal(size=(3, 2, 2))
+        gmms.append(dict(prior=rng.dirichlet(np.ones(3)), mean=rng.uniform(0, 400, (3, 2)),
+                         cov=A @ np.transpose(A, (0, 2, 1)) * 50 + 20 * np.eye(2)))
+        npts.append(int(rng.integers(50, 400)))
+    for W0 in (0.005, [0.004, 0.008]):
+        ini = dict(INI, W0=W0)
+        got = H.vbhmm_init_from_gmms(gmms, npts, 3, ini)
+        for g, n, vp in zip(gmms, npts, got):
+            want = H.vbhmm_init((n, 2), 3, dict(ini, initmode="initgmm", initgmm=g))
+            for k in want:
+                np.testing.assert_allclose(vp[k], want[k], rtol=1e-13, err_msg=k)
