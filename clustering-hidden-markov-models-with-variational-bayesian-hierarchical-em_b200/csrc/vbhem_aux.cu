@@ -4,8 +4,8 @@
 //   * linear-domain centre records for the lattice kernel
 //   * responsibilities z_hat, Nj, Lt1, Lt7      vbhem_h3m_c_step_fc.m:271-283, vbhemh3m_lb.m:90,107
 //   * deterministic list of the pairs with Z > 1e-8 (vbhem_compute_Statistics.m:35),
-//     centre-major and base-ascending, cut in fixed-length chunks
-//   * fixed-order reduction of the per-chunk partial sums, and the normalisation of
+//     centre-major and base-ascending; its length stays on the device (no host read-back)
+//   * fixed-order reduction of the per-range partial sums, and the normalisation of
 //     vbhem_compute_Statistics.m:57-82.
 // Every sum over bases uses a fixed tree (thread -> warp -> block -> sequential over
 // blocks), so results are bit-identical from run to run.
@@ -283,9 +283,8 @@ __global__ void k_list_scan_blocks(int nblocks, int K, const int *cnt, int *offs
   if (lane == 0) segcnt[j] = run;
 }
 
-// seg_start[j], chunk_start[j] (K+1 entries each): exclusive prefix over centres; totals = {#active, #chunks}.
-__global__ void k_list_scan_centres(int K, int chunk_len, int target_chunks, const int *segcnt, int *seg_start,
-                                    int *chunk_start, int *totals) {
+// seg_start[j] (K + 1 entries): exclusive prefix over centres; totals = {#active, items per range}.
+__global__ void k_list_scan_centres(int K, int nranges, const int *segcnt, int *seg_start, int *totals) {
   // one warp; lane l owns the contiguous range [l * per, (l + 1) * per) of centres
   const int lane = threadIdx.x, per = (K + 31) / 32;
   const int ja = min(K, lane * per), jb = min(K, ja + per);
@@ -297,33 +296,17 @@ __global__ void k_list_scan_centres(int K, int chunk_len, int target_chunks, con
     const int ta = __shfl_up_sync(0xffffffffu, ia, o);
     if (lane >= o) ia += ta;
   }
-  const int total = __shfl_sync(0xffffffffu, ia, 31);
-  // chunk length: chunk_len when there is work for every warp of the second pass, else halved until there are
-  // about target_chunks chunks (a shard of a multi-GPU run, a small base set): the statistic partials of a
-  // chunk are one warp's serial work
-  int len = chunk_len;
-  while (len > 1 && total / len < target_chunks) len >>= 1;
-  int c = 0;
-  for (int j = ja; j < jb; j++) c += (segcnt[j] + len - 1) / len;
-  int ic = c;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int tc = __shfl_up_sync(0xffffffffu, ic, o);
-    if (lane >= o) ic += tc;
-  }
-  int ra = ia - a, rc = ic - c;   // exclusive prefixes
+  int ra = ia - a;   // exclusive prefix
   for (int j = ja; j < jb; j++) {
     seg_start[j] = ra;
-    chunk_start[j] = rc;
     ra += segcnt[j];
-    rc += (segcnt[j] + len - 1) / len;
   }
   if (lane == 31) {
     seg_start[K] = ia;
-    chunk_start[K] = ic;
     totals[0] = ia;
-    totals[1] = ic;
-    totals[2] = len;
+    // the second pass cuts the list in nranges equal ranges, one warp's serial work each
+    const int ipr = (ia + nranges - 1) / nranges;
+    totals[1] = ipr > 0 ? ipr : 1;
   }
 }
 
@@ -353,35 +336,27 @@ k_list_fill(int N, int K, const double *zhat, const double *Ntilde, const int *o
       if (act) {
         int pos = seg_start[j] + offs[(size_t)blockIdx.x * K + j] + __popc(bal & ((1u << lane) - 1u));
         for (int w = 0; w < warp; w++) pos += wcnt[w][jj];
-        items[pos] = PairItem{i, j, Z};
+        items[pos] = PairItem{i, j};
       }
     }
     __syncthreads();
   }
 }
 
-__global__ void k_chunks(int K, int chunk_len, const int *seg_start, const int *chunk_start, int2 *chunks) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= chunk_start[K]) return;
-  int lo = 0, hi = K;                      // largest j with chunk_start[j] <= c
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (chunk_start[mid] <= c) lo = mid; else hi = mid;
-  }
-  const int k = c - chunk_start[lo];
-  const int start = seg_start[lo] + k * chunk_len;
-  const int len = min(chunk_len, seg_start[lo + 1] - start);
-  chunks[c] = make_int2(start, len);
-}
-
-// S_*[., j] = sum over the centre's chunks, in chunk order.
-__global__ void k_partial_reduce(int K, int per, const int *chunk_start, const double *partial, double *S_nu1,
-                                 double *S_xi, double *S_pr, double *S_mu, double *S_Mu, int r, int d, int dd) {
+// S_*[., j] = sum over the partial slots of centre j, in range order: the ranges that overlap the centre's
+// items [seg_start[j], seg_start[j + 1]) are w_lo .. w_hi and range w left its sum in slot w + j (PairWork).
+__global__ void k_partial_reduce(int K, int per, const int *seg_start, const int *totals, const double *partial,
+                                 double *S_nu1, double *S_xi, double *S_pr, double *S_mu, double *S_Mu, int r, int d,
+                                 int dd) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= K * per) return;
   const int j = x / per, q = x % per;
+  const int a = seg_start[j], b = seg_start[j + 1], ipr = totals[1];
   double s = 0.0;
-  for (int c = chunk_start[j]; c < chunk_start[j + 1]; c++) s += partial[(size_t)c * per + q];
+  if (b > a) {
+    const int w_hi = (b - 1) / ipr;
+    for (int w = a / ipr; w <= w_hi; w++) s += partial[(size_t)(w + j) * per + q];
+  }
   if (q < r) S_nu1[q + (size_t)r * j] = s;
   else if (q < r + r * r) S_xi[(q - r) + (size_t)r * r * j] = s;
   else if (q < 2 * r + r * r) S_pr[(q - r - r * r) + (size_t)r * j] = s;
@@ -532,27 +507,26 @@ int launch_zhat(int N, int K, int ngroups, const int *gstart, const double *L_el
 
 int zhat_block_size() { return kZThreads; }
 
-int launch_list_scan(int N, int K, int chunk_len, int target_chunks, const int *cnt, int *offs, int *segcnt,
-                     int *seg_start, int *chunk_start, int *totals, cudaStream_t st) {
+int launch_list_scan(int N, int K, int nranges, const int *cnt, int *offs, int *segcnt, int *seg_start, int *totals,
+                     cudaStream_t st) {
   k_list_scan_blocks<<<(K + 3) / 4, 128, 0, st>>>(zhat_blocks(N), K, cnt, offs, segcnt);
-  k_list_scan_centres<<<1, 32, 0, st>>>(K, chunk_len, target_chunks, segcnt, seg_start, chunk_start, totals);
+  k_list_scan_centres<<<1, 32, 0, st>>>(K, nranges, segcnt, seg_start, totals);
   return 2;
 }
 
-int launch_list_fill(int N, int K, int chunk_len, int nchunks, const double *zhat, const double *Ntilde,
-                     const int *offs, const int *seg_start, const int *chunk_start, PairItem *items, int2 *chunks,
-                     cudaStream_t st) {
+int launch_list_fill(int N, int K, const double *zhat, const double *Ntilde, const int *offs, const int *seg_start,
+                     PairItem *items, cudaStream_t st) {
   const int nb = zhat_blocks(N);
   k_list_fill<<<dim3(nb, spread(nb, (K + kJT - 1) / kJT)), kZThreads, 0, st>>>(N, K, zhat, Ntilde, offs, seg_start, items);
-  if (nchunks > 0) k_chunks<<<(nchunks + 255) / 256, 256, 0, st>>>(K, chunk_len, seg_start, chunk_start, chunks);
-  return nchunks > 0 ? 2 : 1;
+  return 1;
 }
 
-int launch_partial_reduce(int K, int per, const int *chunk_start, const double *partial, double *S_nu1, double *S_xi,
-                          double *S_pr, double *S_mu, double *S_Mu, int r, int d, int dd, cudaStream_t st) {
+int launch_partial_reduce(int K, int per, const int *seg_start, const int *totals, const double *partial,
+                          double *S_nu1, double *S_xi, double *S_pr, double *S_mu, double *S_Mu, int r, int d, int dd,
+                          cudaStream_t st) {
   const int tot = K * per;
-  k_partial_reduce<<<(tot + 127) / 128, 128, 0, st>>>(K, per, chunk_start, partial, S_nu1, S_xi, S_pr, S_mu, S_Mu, r,
-                                                      d, dd);
+  k_partial_reduce<<<(tot + 127) / 128, 128, 0, st>>>(K, per, seg_start, totals, partial, S_nu1, S_xi, S_pr, S_mu, S_Mu,
+                                                      r, d, dd);
   return 1;
 }
 

@@ -76,8 +76,8 @@ struct DevBuf {
 };
 
 // Pinned host staging area: small uploads copied here first travel as truly asynchronous copies (a cudaMemcpyAsync
-// from pageable memory blocks the host for a staged copy each).  Re-used by the next call, which is safe because every
-// E-step synchronises its stream (the active-pair totals) after the uploads were enqueued.
+// from pageable memory blocks the host for a staged copy each).  The E-step never synchronises its stream, so the
+// handle keeps a ring of these (StageRing) and an event per slot says when the slot's copies have left.
 struct PinBuf {
   void *p = nullptr;
   size_t cap = 0;
@@ -94,13 +94,44 @@ struct PinBuf {
   void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
-constexpr int kChunkLen = 16;   // pairs per second-pass chunk (one warp's serial work); shorter when pairs are few
-// chunks wanted before the chunk length is halved: two per warp of the second-pass grid (one 16-warp CTA per SM)
-int second_pass_warps() {
+constexpr int kStageSlots = 4;
+struct StageRing {
+  PinBuf buf[kStageSlots];
+  cudaEvent_t ev[kStageSlots] = {nullptr, nullptr, nullptr, nullptr};
+  bool busy[kStageSlots] = {false, false, false, false};
+  int next = 0, cur = 0;
+  // a slot whose earlier copies have completed, at least `bytes` large
+  cudaError_t acquire(size_t bytes, void **out) {
+    cur = next;
+    next = (next + 1) % kStageSlots;
+    cudaError_t e;
+    if (!ev[cur] && (e = cudaEventCreateWithFlags(&ev[cur], cudaEventDisableTiming)) != cudaSuccess) return e;
+    if (busy[cur] && (e = cudaEventSynchronize(ev[cur])) != cudaSuccess) return e;
+    busy[cur] = false;
+    if ((e = buf[cur].ensure(bytes)) != cudaSuccess) return e;
+    *out = buf[cur].p;
+    return cudaSuccess;
+  }
+  // call after the copies out of the current slot were enqueued on `st`
+  cudaError_t commit(cudaStream_t st) {
+    busy[cur] = true;
+    return cudaEventRecord(ev[cur], st);
+  }
+  void release() {
+    for (int k = 0; k < kStageSlots; k++) {
+      if (ev[k]) { cudaEventSynchronize(ev[k]); cudaEventDestroy(ev[k]); ev[k] = nullptr; }
+      buf[k].release();
+    }
+  }
+};
+
+// Ranges of the second-pass list = warps of its grid (one 16-warp CTA per SM): fixed by the device, not by the
+// number of active pairs, so nothing about the second pass has to be read back by the host.
+int second_pass_ranges() {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  return 2 * 16 * sms;
+  return 16 * sms;
 }
 
 }  // namespace
@@ -113,8 +144,7 @@ struct vbhem_base {
   // centre set (per call)
   DevBuf cen_i, cen_d, hyp_d, rec, tile_i, pair_rec;
   // results and work lists
-  DevBuf L, z, flags, fbcount, Njp, lbp, cnt, offs, segs, items, chunks, partial, itemflags, scratch, pairs_out,
-      stats;
+  DevBuf L, z, flags, fbcount, Njp, lbp, cnt, offs, segs, items, partial, itemflags, scratch, pairs_out, stats;
   // streamed E-step (base set in host memory): copy-in / copy-out streams and per-slice events
   cudaStream_t cin = nullptr, cout = nullptr;
   std::vector<cudaEvent_t> slice_ev;
@@ -125,11 +155,21 @@ struct vbhem_base {
     int K = 0, maxSr = 0, ngroups = 1;
     std::vector<int32_t> Sr, group;
     double alpha0 = 0, eta0 = 0, epsilon0 = 0, lambda0 = 0, v0 = 0;
-    DevBuf m, prior, lb, stats, frozen;
+    // The run's own copies of everything it keeps between calls -- hyper-parameters (layout of stage_centres'
+    // hyp block), means, state counts | group starts -- so that ordinary E-steps on the same handle (which
+    // overwrite cen_i / hyp_d) cannot corrupt it.  `staged`: cen_d holds the pre-pass of THIS run's last E-step
+    // (what vbhem_em_lower_bound reads); any other E-step on the handle clears it.
+    DevBuf hyp, ints, m, prior, lb, stats, frozen;
+    bool staged = false;
     double *h_lb = nullptr;   // pinned
   } em;
-  int *h_totals = nullptr;   // pinned
-  PinBuf stage;              // pinned staging of the per-call centre uploads (stage_centres)
+  std::vector<int> last_lists;   // tile lists as last uploaded to tile_i (skip the copy when unchanged)
+  DevBuf fin_i;                  // state counts of vbhem_finalize_stats*
+  int *h_totals = nullptr;   // pinned: {#active pairs, items per range, fall-backs first pass, second pass}
+  bool lattice_second = false;
+  bool totals_pending = false;   // the last E-step's list totals / fall-back counts are still on the device
+  const int *d_totals = nullptr;
+  StageRing stage;           // pinned staging of the per-call centre uploads (stage_centres)
   bool profile = false;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   double timings[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -209,21 +249,28 @@ int stage_centres(vbhem_base *h, const CentreArgs &a, CentreDev &cd, double *pre
   const size_t n_int = (size_t)K + a.ngroups + 1 + 2 * (size_t)K + 4;
   const size_t int_bytes = (n_int * sizeof(int) + 15) / 16 * 16;
   const size_t n_dbl = d * nr + (a.hyp ? nK + nr + nrr + dd * nr + nr + nr : nK + nr + nrr + nr + dd * nr);
-  CU(h->stage.ensure(int_bytes + sizeof(double) * n_dbl));
-  int *s_int = static_cast<int *>(h->stage.p);
-  double *s_dbl = reinterpret_cast<double *>(static_cast<char *>(h->stage.p) + int_bytes);
-  CU(h->cen_i.ensure(sizeof(int) * (size_t)(K + a.ngroups + 1)));
-  int *dSr = h->cen_i.as<int>();
-  int *dgs = dSr + K;
-  memcpy(s_int, a.Sr, sizeof(int) * K);
-  int *gs = s_int + K;
-  for (int g = 0; g <= a.ngroups; g++) gs[g] = 0;
-  if (a.group) {
-    for (int j = 0; j < K; j++) gs[a.group[j] + 1] = j + 1;
+  void *stage_p = nullptr;
+  CU(h->stage.acquire(int_bytes + sizeof(double) * n_dbl, &stage_p));
+  int *s_int = static_cast<int *>(stage_p);
+  double *s_dbl = reinterpret_cast<double *>(static_cast<char *>(stage_p) + int_bytes);
+  int *dSr, *dgs;
+  if (a.hyp && a.resident) {          // device-resident EM run: state counts and group starts are already there
+    dSr = h->em.ints.as<int>();
   } else {
-    gs[1] = K;
+    h->em.staged = false;             // cen_d is about to hold another centre set's pre-pass
+    CU(h->cen_i.ensure(sizeof(int) * (size_t)(K + a.ngroups + 1)));
+    dSr = h->cen_i.as<int>();
+    memcpy(s_int, a.Sr, sizeof(int) * K);
+    int *gs = s_int + K;
+    for (int g = 0; g <= a.ngroups; g++) gs[g] = 0;
+    if (a.group) {
+      for (int j = 0; j < K; j++) gs[a.group[j] + 1] = j + 1;
+    } else {
+      gs[1] = K;
+    }
+    CU(cudaMemcpyAsync(dSr, s_int, sizeof(int) * (size_t)(K + a.ngroups + 1), cudaMemcpyHostToDevice, h->st));
   }
-  CU(cudaMemcpyAsync(dSr, s_int, sizeof(int) * (size_t)(K + a.ngroups + 1), cudaMemcpyHostToDevice, h->st));
+  dgs = dSr + K;
   // log-domain block: logOmega[K] | logPi[rK] | logA[rrK] | logLam[rK] | cterm[rK] | m[d r K] | vW[dd r K]
   const size_t tot = nK + nr + nrr + nr + nr + d * nr + dd * nr;
   CU(h->cen_d.ensure(sizeof(double) * tot));
@@ -238,15 +285,15 @@ int stage_centres(vbhem_base *h, const CentreArgs &a, CentreDev &cd, double *pre
   double *sm = s_dbl;            // staged means
   double *srest = s_dbl + d * nr;
   if (a.hyp && a.resident) {
-    CU(cudaMemcpyAsync(dm, h->em.m.p, sizeof(double) * d * nr, cudaMemcpyDeviceToDevice, h->st));
+    dm = h->em.m.as<double>();        // read in place
   } else {
     memcpy(sm, a.m, sizeof(double) * d * nr);
     CU(cudaMemcpyAsync(dm, sm, sizeof(double) * d * nr, cudaMemcpyHostToDevice, h->st));
   }
   if (a.hyp) {
     const size_t th = nK + nr + nrr + dd * nr + nr + nr;
-    CU(h->hyp_d.ensure(sizeof(double) * th));
-    double *q = h->hyp_d.as<double>();
+    if (!a.resident) CU(h->hyp_d.ensure(sizeof(double) * th));
+    double *q = (a.resident ? h->em.hyp : h->hyp_d).as<double>();
     double *hal = q; q += nK;
     double *het = q; q += nr;
     double *hep = q; q += nrr;
@@ -326,10 +373,13 @@ int stage_centres(vbhem_base *h, const CentreArgs &a, CentreDev &cd, double *pre
       cd.C.npairs[c] = (int)cls[c].size() / 2;
       ntile_pairs += cd.C.npairs[c];
     }
-    CU(h->tile_i.ensure(sizeof(int) * (lists.size() + 1)));
-    int *s_lists = s_int + K + a.ngroups + 1;              // pinned: outlives this scope, no synchronisation needed
-    memcpy(s_lists, lists.data(), sizeof(int) * lists.size());
-    CU(cudaMemcpyAsync(h->tile_i.p, s_lists, sizeof(int) * lists.size(), cudaMemcpyHostToDevice, h->st));
+    if (!(h->tile_i.p && lists == h->last_lists)) {        // an EM run stages the same lists every iteration
+      CU(h->tile_i.ensure(sizeof(int) * (lists.size() + 1)));
+      int *s_lists = s_int + K + a.ngroups + 1;            // same pinned slot: outlives this scope
+      memcpy(s_lists, lists.data(), sizeof(int) * lists.size());
+      CU(cudaMemcpyAsync(h->tile_i.p, s_lists, sizeof(int) * lists.size(), cudaMemcpyHostToDevice, h->st));
+      h->last_lists = lists;
+    }
     cd.C.big_list = h->tile_i.as<int>();
     cd.C.nbig = (int)big.size();
     cd.C.pair_list = cd.C.big_list + big.size();
@@ -342,6 +392,7 @@ int stage_centres(vbhem_base *h, const CentreArgs &a, CentreDev &cd, double *pre
       launches += launch_pair_records(cd.C, d, dd, h->pair_rec.as<double>(), h->st);
     }
   }
+  CU(h->stage.commit(h->st));   // the slot is free again once everything enqueued so far has run
   return VBHEM_OK;
 }
 
@@ -374,7 +425,7 @@ StatsPtr carve_stats(double *s, int K, int r, int d, int dd, int ng) {
 int first_pass(vbhem_base *h, const CentreDev &cd, int T, long long &launches) {
   const long long np = (long long)h->B.N * cd.C.K;
   CU(h->L.ensure(sizeof(double) * np));
-  PairWork W{nullptr, nullptr, 0, np};
+  PairWork W{nullptr, nullptr, nullptr, nullptr, 0, np};
   PairOut O{};
   O.mode = 0;
   O.L_elbo = h->L.as<double>();
@@ -445,7 +496,7 @@ int streamed_front(vbhem_base *h, const CentreDev &cd, const CentreArgs &a, cons
   // earlier work on the handle's stream may still read the base buffers
   CU(cudaEventRecord(h->slice_ev[2 * ns], h->st));
   CU(cudaStreamWaitEvent(h->cin, h->slice_ev[2 * ns], 0));
-  PairWork W{nullptr, nullptr, 0, np};
+  PairWork W{nullptr, nullptr, nullptr, nullptr, 0, np};
   PairOut O{};
   O.mode = 0;
   O.L_elbo = h->L.as<double>();
@@ -494,6 +545,7 @@ int estep_device(vbhem_base *h, const CentreArgs &a, double *stats_dev, double *
   const int N = h->B.N, K = a.K, r = a.maxSr, d = h->B.d, dd = h->B.dd, T = a.tau;
   long long launches = 0;
   memset(h->counters, 0, sizeof h->counters);
+  h->totals_pending = false;
   auto mark = [&](int k) { if (h->profile) cudaEventRecord(h->ev[k], h->st); };
   mark(0);
   CentreDev cd;
@@ -508,7 +560,10 @@ int estep_device(vbhem_base *h, const CentreArgs &a, double *stats_dev, double *
   CU(h->lbp.ensure(sizeof(double) * (size_t)nb * 2 * a.ngroups));
   CU(h->cnt.ensure(sizeof(int) * (size_t)nb * K));
   CU(h->offs.ensure(sizeof(int) * (size_t)nb * K));
-  CU(h->segs.ensure(sizeof(int) * (size_t)(3 * (K + 1) + 3)));
+  CU(h->segs.ensure(sizeof(int) * (size_t)(2 * (K + 1) + 4)));
+  CU(h->fbcount.ensure(2 * sizeof(int)));
+  if (!(cd.C.rec && lattice_supported(h->B, cd.C, T, false)))       // else the first pass clears both counters
+    CU(cudaMemsetAsync(h->fbcount.p, 0, 2 * sizeof(int), h->st));
   StatsPtr S = carve_stats(stats_dev, K, r, d, dd, a.ngroups);
   if (io && cd.C.rec && lattice_supported(h->B, cd.C, T, false)) {
     rc = streamed_front(h, cd, a, *io, S, launches);
@@ -531,32 +586,28 @@ int estep_device(vbhem_base *h, const CentreArgs &a, double *stats_dev, double *
       if (io->z_host) CU(cudaMemcpyAsync(io->z_host, h->z.p, sizeof(double) * np, cudaMemcpyDeviceToHost, h->st));
     }
   }
-  int *seg_start = h->segs.as<int>(), *chunk_start = seg_start + (K + 1), *totals = chunk_start + (K + 1);
-  int *segcnt = totals + 3;
-  launches += launch_list_scan(N, K, kChunkLen, second_pass_warps(), h->cnt.as<int>(), h->offs.as<int>(), segcnt, seg_start, chunk_start,
-                               totals, h->st);
-  CU(cudaMemcpyAsync(h->h_totals, totals, 3 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
-  CU(cudaStreamSynchronize(h->st));
-  const int nact = h->h_totals[0], nch = h->h_totals[1], clen = h->h_totals[2];
-  h->counters[3] = nact;
+  // Deterministic list of the pairs with Z > 1e-8 and the second pass over it.  The list's length stays on the
+  // device (totals): buffers are sized by their upper bounds and every grid by N, K and the device alone, so the
+  // host enqueues the whole E-step without waiting for anything.
+  int *seg_start = h->segs.as<int>(), *totals = seg_start + (K + 1), *segcnt = totals + 4;
+  const int nranges = second_pass_ranges();
   const int per = stat_per(r, d, dd);
-  CU(h->items.ensure(sizeof(PairItem) * (size_t)(nact > 0 ? nact : 1)));
-  CU(h->chunks.ensure(sizeof(int2) * (size_t)(nch > 0 ? nch : 1)));
-  CU(h->partial.ensure(sizeof(double) * (size_t)per * (nch > 0 ? nch : 1)));
-  launches += launch_list_fill(N, K, clen, nch, h->z.as<double>(), h->B.Ntilde, h->offs.as<int>(), seg_start,
-                               chunk_start, h->items.as<PairItem>(), h->chunks.as<int2>(), h->st);
+  if (np >= ((long long)1 << 31)) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: N * K must be below 2^31");
+  CU(h->items.ensure(sizeof(PairItem) * (size_t)np));
+  CU(h->partial.ensure(sizeof(double) * (size_t)per * ((size_t)nranges + K)));
+  launches += launch_list_scan(N, K, nranges, h->cnt.as<int>(), h->offs.as<int>(), segcnt, seg_start, totals, h->st);
+  launches += launch_list_fill(N, K, h->z.as<double>(), h->B.Ntilde, h->offs.as<int>(), seg_start,
+                               h->items.as<PairItem>(), h->st);
   mark(3);
-  if (nch > 0) {
-    PairWork W{h->items.as<PairItem>(), h->chunks.as<int2>(), nch, nact};
+  {
+    PairWork W{h->items.as<PairItem>(), totals, h->z.as<double>(), h->B.Ntilde, nranges, np};
     PairOut O{};
     O.mode = 2;
     O.partial = h->partial.as<double>();
     O.per = per;
     if (cd.C.rec && lattice_supported(h->B, cd.C, T, true)) {
-      CU(h->itemflags.ensure(nact));
-      CU(cudaMemsetAsync(h->itemflags.p, 0, nact, h->st));
-      CU(cudaMemsetAsync(h->fbcount.as<int>() + 1, 0, sizeof(int), h->st));
-      Fallback fb{h->itemflags.as<unsigned char>(), h->fbcount.as<int>() + 1};
+      CU(h->itemflags.ensure((size_t)np));
+      Fallback fb{h->itemflags.as<unsigned char>(), h->fbcount.as<int>() + 1};   // count zeroed with the first pass's
       const int n1 = launch_lattice_full(h->B, cd.C, T, W, O, fb, h->st);
       if (n1 < 0) return fail(VBHEM_ECUDA, "lattice kernel launch configuration failed");
       launches += n1;
@@ -566,25 +617,42 @@ int estep_device(vbhem_base *h, const CentreArgs &a, double *stats_dev, double *
       const int n2 = launch_general(h->B, cd.C, T, W, O, fb.flags, fb.count, h->scratch.as<double>(), sd, h->st);
       if (n2 < 0) return fail(VBHEM_ENOMEM, "general kernel scratch too small");
       launches += n2;
-      h->counters[1] += nact;
+      h->lattice_second = true;
     } else {
       size_t sd;
-      rc = ensure_scratch(h, r, T, nch < 2368 ? nch : 2368, sd);
+      rc = ensure_scratch(h, r, T, nranges < 2368 ? nranges : 2368, sd);
       if (rc) return rc;
       const int n2 = launch_general(h->B, cd.C, T, W, O, nullptr, nullptr, h->scratch.as<double>(), sd, h->st);
       if (n2 < 0) return fail(VBHEM_ENOMEM, "general kernel scratch too small");
       launches += n2;
-      h->counters[2] += nact;
+      h->lattice_second = false;
     }
   }
   mark(4);
-  // chunk_start is all-zero when nothing is active, so the reduction writes zeros
-  launches += launch_partial_reduce(K, per, chunk_start, h->partial.as<double>(), S.nu1, S.xi, S.pr, S.mu, S.Mu, r, d,
-                                    dd, h->st);
+  // a centre without active pairs has an empty segment, so the reduction writes zeros for it
+  launches += launch_partial_reduce(K, per, seg_start, totals, h->partial.as<double>(), S.nu1, S.xi, S.pr, S.mu, S.Mu, r,
+                                    d, dd, h->st);
   mark(5);
   CU(cudaGetLastError());
   h->counters[0] = launches;
   h->lastK = K;
+  h->d_totals = totals;
+  h->totals_pending = true;
+  return VBHEM_OK;
+}
+
+// The counters that live on the device after an E-step (active pairs, fall-backs): read them now.  Synchronises.
+int settle_counters(vbhem_base *h) {
+  if (!h->totals_pending) return VBHEM_OK;
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(h->h_totals, h->d_totals, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  CU(cudaMemcpyAsync(h->h_totals + 2, h->fbcount.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  const long long nact = h->h_totals[0];
+  h->counters[3] = nact;
+  h->counters[2] += h->h_totals[2] + h->h_totals[3];
+  if (h->lattice_second) h->counters[1] += nact; else h->counters[2] += nact;
+  h->totals_pending = false;
   return VBHEM_OK;
 }
 
@@ -603,13 +671,9 @@ int estep_host(vbhem_base *h, const CentreArgs &a, double *L_elbo, double *zhat,
     if (L_elbo) CU(cudaMemcpyAsync(L_elbo, h->L.p, sizeof(double) * np, cudaMemcpyDeviceToHost, h->st));
     if (zhat) CU(cudaMemcpyAsync(zhat, h->z.p, sizeof(double) * np, cudaMemcpyDeviceToHost, h->st));
   }
-  CU(cudaStreamSynchronize(h->st));
+  rc = settle_counters(h);          // synchronises the handle's stream
+  if (rc) return rc;
   if (io && h->cout) CU(cudaStreamSynchronize(h->cout));
-  if (h->fbcount.p) {
-    int fb[2] = {0, 0};
-    CU(cudaMemcpy(fb, h->fbcount.p, sizeof fb, cudaMemcpyDeviceToHost));
-    h->counters[2] += fb[0] + fb[1];
-  }
   return VBHEM_OK;
 }
 
@@ -732,10 +796,11 @@ int vbhem_free_base(vbhem_base_t *h) {
   if (h->cout) { cudaStreamSynchronize(h->cout); cudaStreamDestroy(h->cout); }
   for (cudaEvent_t e : h->slice_ev) cudaEventDestroy(e);
   h->em.m.release(); h->em.prior.release(); h->em.lb.release(); h->em.stats.release(); h->em.frozen.release();
+  h->em.hyp.release(); h->em.ints.release(); h->fin_i.release();
   if (h->em.h_lb) cudaFreeHost(h->em.h_lb);
   DevBuf *all[] = {&h->bSb, &h->bprior, &h->bA, &h->bmu, &h->bcov, &h->bNt, &h->cen_i, &h->cen_d, &h->hyp_d, &h->rec,
                    &h->L, &h->z, &h->flags, &h->fbcount, &h->Njp, &h->lbp, &h->cnt, &h->offs, &h->segs, &h->items,
-                   &h->chunks, &h->partial, &h->itemflags, &h->scratch, &h->pairs_out, &h->stats};
+                   &h->partial, &h->itemflags, &h->scratch, &h->pairs_out, &h->stats, &h->tile_i, &h->pair_rec};
   for (DevBuf *b : all) b->release();
   if (h->h_totals) cudaFreeHost(h->h_totals);
   h->stage.release();
@@ -802,6 +867,7 @@ int vbhem_estep_pairs(vbhem_base_t *h, int K, const int32_t *Sr, int maxSr, int 
   CU(cudaSetDevice(h->device));
   long long launches = 0;
   memset(h->counters, 0, sizeof h->counters);
+  h->totals_pending = false;
   CentreDev cd;
   rc = stage_centres(h, a, cd, nullptr, launches);
   if (rc) return rc;
@@ -828,7 +894,7 @@ int vbhem_estep_pairs(vbhem_base_t *h, int K, const int32_t *Sr, int maxSr, int 
   O.pr = po; po += np * r;
   O.mu = po; po += np * r * d;
   O.Mu = po;
-  PairWork W{nullptr, nullptr, 0, (long long)np};
+  PairWork W{nullptr, nullptr, nullptr, nullptr, 0, (long long)np};
   if (cd.C.rec && lattice_supported(h->B, cd.C, tau, true)) {
     CU(h->flags.ensure(np));
     CU(h->fbcount.ensure(2 * sizeof(int)));
@@ -956,7 +1022,7 @@ namespace {
 struct HypPtrs { double *alpha, *eta, *epsilon, *W, *v, *lambda; };
 HypPtrs carve_hyp(vbhem_base *h, int K, int r) {
   const size_t nK = K, nr = (size_t)r * K, nrr = (size_t)r * r * K, dd = h->B.dd;
-  double *q = h->hyp_d.as<double>();
+  double *q = h->em.hyp.as<double>();
   HypPtrs p;
   p.alpha = q; q += nK;
   p.eta = q; q += nr;
@@ -977,7 +1043,16 @@ int em_upload_state(vbhem_base *h, int K, const int32_t *Sr, int maxSr, const in
   if (!group) em.group.clear();
   else if (group != em.group.data()) em.group.assign(group, group + K);
   const size_t nK = K, nr = (size_t)maxSr * K, nrr = (size_t)maxSr * maxSr * K;
-  CU(h->hyp_d.ensure(sizeof(double) * (nK + nr + nrr + dd * nr + nr + nr)));
+  CU(em.hyp.ensure(sizeof(double) * (nK + nr + nrr + dd * nr + nr + nr)));
+  CU(em.ints.ensure(sizeof(int) * (size_t)(K + ngroups + 1)));
+  {
+    std::vector<int> iv((size_t)K + ngroups + 1, 0);
+    for (int j = 0; j < K; j++) iv[j] = Sr[j];
+    if (group) { for (int j = 0; j < K; j++) iv[(size_t)K + group[j] + 1] = j + 1; }
+    else iv[(size_t)K + 1] = K;
+    CU(cudaMemcpyAsync(em.ints.p, iv.data(), sizeof(int) * iv.size(), cudaMemcpyHostToDevice, h->st));  // pageable: staged before return
+  }
+  em.staged = false;
   CU(em.m.ensure(sizeof(double) * d * nr));
   CU(em.lb.ensure(sizeof(double) * 12 * ngroups));
   CU(em.stats.ensure(sizeof(double) * vbhem_stats_size(K, maxSr, d, h->B.covmode, ngroups)));
@@ -1053,7 +1128,9 @@ int vbhem_em_estep(vbhem_base_t *h, int tau, double *stats_dev) {
   int rc = check_common(h, a, true);
   if (rc) return rc;
   CU(cudaSetDevice(h->device));
-  return estep_device(h, a, stats_dev ? stats_dev : h->em.stats.as<double>(), nullptr);
+  rc = estep_device(h, a, stats_dev ? stats_dev : h->em.stats.as<double>(), nullptr);
+  if (rc == VBHEM_OK) h->em.staged = true;
+  return rc;
 }
 
 namespace {
@@ -1064,7 +1141,7 @@ EmCtx em_ctx(vbhem_base *h, double *st) {
   const int K = em.K, r = em.maxSr, d = h->B.d, dd = h->B.dd, ng = em.ngroups;
   EmCtx c;
   c.S = carve_stats(st, K, r, d, dd, ng);
-  const int *dSr = h->cen_i.as<int>(), *dgs = dSr + K;           // staged by the E-step
+  const int *dSr = em.ints.as<int>(), *dgs = dSr + K;
   c.p = carve_hyp(h, K, r);
   EmView &E = c.E;
   E = EmView{};
@@ -1082,6 +1159,9 @@ EmCtx em_ctx(vbhem_base *h, double *st) {
 
 int vbhem_em_lower_bound(vbhem_base_t *h, double *stats_dev, double *lb_out) {
   if (!h || !h->em.active) return fail(VBHEM_EINVAL, "vbhem_em_begin has not been called on this handle");
+  if (!h->em.staged)
+    return fail(VBHEM_EINVAL, "vbhem_em_lower_bound needs the pre-pass of this run's own E-step: call vbhem_em_estep "
+                              "first (another E-step ran on the handle since)");
   CU(cudaSetDevice(h->device));
   auto &em = h->em;
   EmCtx c = em_ctx(h, stats_dev ? stats_dev : em.stats.as<double>());
@@ -1146,18 +1226,59 @@ int vbhem_em_fetch(vbhem_base_t *h, double *alpha, double *eta, double *epsilon,
   return VBHEM_OK;
 }
 
-// vbhem_h3m_c_step_fc.m:115-433 on one GPU, one H3M: E-step, lower bound, relative-change test from the
-// third pass on, M-step (also after the breaking pass), NaN guard.
-int vbhem_em_run(vbhem_base_t *h, int tau, int max_iter, double min_diff, double *LogLs, int *iters, int *unstable) {
+// ---- the EM loops, written once over an EmDriver: one handle (vbhem_em_run*) or the shards of a multi-GPU set
+// (vbhem_multi_em_run*, vbhem_multi.inl), where every operation fans out to all shards and the E-step is followed
+// by the all-reduce of the raw statistics.
+namespace {
+struct EmDriver {
+  virtual ~EmDriver() {}
+  virtual vbhem_base *first() = 0;                        // shapes, priors (identical on every shard)
+  // E-step from the resident hyper-parameters (+ all-reduce) + lower bound: lb[12 * ngroups] on the host
+  virtual int estep_lb(int tau, double *lb) = 0;
+  virtual int mstep_masked(const unsigned char *skip) = 0;   // skip == nullptr: every group
+  virtual int fetch(double *alpha, double *eta, double *epsilon, double *m, double *W, double *v, double *lambda) = 0;
+  virtual int upload_state(int K, const int32_t *Sr, int maxSr, const int32_t *group, int ngroups, const double *alpha,
+                           const double *eta, const double *epsilon, const double *m, const double *W, const double *v,
+                           const double *lambda) = 0;
+  virtual int sync() = 0;
+};
+
+struct SingleDriver : EmDriver {
+  vbhem_base *h;
+  explicit SingleDriver(vbhem_base *h_) : h(h_) {}
+  vbhem_base *first() override { return h; }
+  int estep_lb(int tau, double *lb) override {
+    int rc = vbhem_em_estep(h, tau, nullptr);
+    if (rc) return rc;
+    return vbhem_em_lower_bound(h, nullptr, lb);          // of the hyper-parameters this E-step used
+  }
+  int mstep_masked(const unsigned char *skip) override { return em_mstep_masked(h, nullptr, skip); }
+  int fetch(double *alpha, double *eta, double *epsilon, double *m, double *W, double *v, double *lambda) override {
+    return vbhem_em_fetch(h, alpha, eta, epsilon, m, W, v, lambda);
+  }
+  int upload_state(int K, const int32_t *Sr, int maxSr, const int32_t *group, int ngroups, const double *alpha,
+                   const double *eta, const double *epsilon, const double *m, const double *W, const double *v,
+                   const double *lambda) override {
+    return em_upload_state(h, K, Sr, maxSr, group, ngroups, alpha, eta, epsilon, m, W, v, lambda);
+  }
+  int sync() override {
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->st));
+    return VBHEM_OK;
+  }
+};
+
+// vbhem_h3m_c_step_fc.m:115-433, one H3M: E-step, lower bound, relative-change test from the third pass on,
+// M-step (also after the breaking pass), NaN guard.
+int em_run_one(EmDriver &D, int tau, int max_iter, double min_diff, double *LogLs, int *iters, int *unstable) {
+  vbhem_base *h = D.first();
   if (!h || !h->em.active) return fail(VBHEM_EINVAL, "vbhem_em_begin has not been called on this handle");
-  if (h->em.ngroups != 1) return fail(VBHEM_EINVAL, "vbhem_em_run drives one H3M; batch several with em_estep/em_mstep");
+  if (h->em.ngroups != 1) return fail(VBHEM_EINVAL, "vbhem_em_run drives one H3M; batch several with vbhem_em_run_groups");
   if (!LogLs || !iters) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: LogLs / iters is NULL");
   double lastL = -1.79769313486231570e308, lb[12];
   int it = 0, n = 0, bad = 0;
   while (true) {
-    int rc = vbhem_em_estep(h, tau, nullptr);
-    if (rc) return rc;
-    rc = vbhem_em_lower_bound(h, nullptr, lb);      // of the hyper-parameters this E-step used
+    int rc = D.estep_lb(tau, lb);
     if (rc) return rc;
     double L = lb[10];
     bool do_break = false;
@@ -1166,13 +1287,14 @@ int vbhem_em_run(vbhem_base_t *h, int tau, int max_iter, double min_diff, double
     if (L != L) { do_break = true; bad = 1; L = -INFINITY; }     // vbhem_h3m_c_step_fc.m:338-354
     LogLs[n++] = L;
     if (do_break && bad) break;                                  // keep the last stable hyper-parameters
-    rc = vbhem_em_mstep(h, nullptr);
+    rc = D.mstep_masked(nullptr);
     if (rc) return rc;
     it++;
     lastL = L;
     if (do_break) break;
   }
-  CU(cudaStreamSynchronize(h->st));
+  int rc = D.sync();
+  if (rc) return rc;
   *iters = it;
   if (unstable) *unstable = bad;
   return VBHEM_OK;
@@ -1184,14 +1306,16 @@ int vbhem_em_run(vbhem_base_t *h, int tau, int max_iter, double min_diff, double
 // to stopped groups the centre set is compacted to the running groups (the stopped ones wait in a host copy), so
 // the E-step's cost follows the work that is left; at the end the handle holds all groups again, in their
 // original order.  LogLs is [ngroups][ld], iters / unstable [ngroups].
-int vbhem_em_run_groups(vbhem_base_t *h, int tau, int max_iter, double min_diff, double *LogLs, int ld, int *iters,
-                        int *unstable) {
+int em_run_groups(EmDriver &D, int tau, int max_iter, double min_diff, double *LogLs, int ld, int *iters,
+                  int *unstable, int *ncompact_out) {
+  vbhem_base *h = D.first();
   if (!h || !h->em.active) return fail(VBHEM_EINVAL, "vbhem_em_begin has not been called on this handle");
   if (!LogLs || !iters || ld < max_iter + 2) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: LogLs[ngroups][>= max_iter + 2], iters required");
   auto &em = h->em;
   const int G = em.ngroups, K0 = em.K, r = em.maxSr, d = h->B.d, dd = h->B.dd;
   const std::vector<int32_t> Sr0 = em.Sr;
   std::vector<int32_t> grp0 = em.group;
+  const bool had_groups = G > 1 || !em.group.empty();
   if (grp0.empty()) grp0.assign(K0, 0);
   std::vector<double> lb(12 * (size_t)G), lastL(G, -1.79769313486231570e308);
   std::vector<int> it(G, 0), n(G, 0), bad(G, 0);
@@ -1206,8 +1330,8 @@ int vbhem_em_run_groups(vbhem_base_t *h, int tau, int max_iter, double min_diff,
   auto save_current = [&]() -> int {
     const int Kc = (int)cmap.size();
     cur.resize(Kc, r, d, dd);
-    int rc = vbhem_em_fetch(h, cur.alpha.data(), cur.eta.data(), cur.eps.data(), cur.m.data(), cur.W.data(),
-                            cur.v.data(), cur.lam.data());
+    int rc = D.fetch(cur.alpha.data(), cur.eta.data(), cur.eps.data(), cur.m.data(), cur.W.data(), cur.v.data(),
+                     cur.lam.data());
     if (rc) return rc;
     if (full.alpha.empty()) full.resize(K0, r, d, dd);
     for (int jc = 0; jc < Kc; jc++) full.copy_centre(cmap[jc], cur, jc, r, d, dd);
@@ -1216,9 +1340,7 @@ int vbhem_em_run_groups(vbhem_base_t *h, int tau, int max_iter, double min_diff,
   int left = G;
   while (left > 0) {
     const int Gc = (int)cur_groups.size();
-    int rc = vbhem_em_estep(h, tau, nullptr);
-    if (rc) return rc;
-    rc = vbhem_em_lower_bound(h, nullptr, lb.data());
+    int rc = D.estep_lb(tau, lb.data());
     if (rc) return rc;
     for (int gc = 0; gc < Gc; gc++) {
       const int g = cur_groups[gc];
@@ -1236,7 +1358,7 @@ int vbhem_em_run_groups(vbhem_base_t *h, int tau, int max_iter, double min_diff,
       lastL[g] = L;
       if (do_break) stop[gc] = 1;                                          // the M-step still runs once more
     }
-    rc = em_mstep_masked(h, nullptr, skip.data());
+    rc = D.mstep_masked(skip.data());
     if (rc) return rc;
     for (int gc = 0; gc < Gc; gc++)
       if (stop[gc] && !done[cur_groups[gc]]) { done[cur_groups[gc]] = 1; left--; }
@@ -1262,8 +1384,8 @@ int vbhem_em_run_groups(vbhem_base_t *h, int tau, int max_iter, double min_diff,
     const int Kc = (int)ncmap.size();
     cur.resize(Kc, r, d, dd);
     for (int jc = 0; jc < Kc; jc++) cur.copy_centre(jc, full, ncmap[jc], r, d, dd);
-    rc = em_upload_state(h, Kc, nSr.data(), r, ngrp.data(), (int)ngroups_list.size(), cur.alpha.data(), cur.eta.data(),
-                         cur.eps.data(), cur.m.data(), cur.W.data(), cur.v.data(), cur.lam.data());
+    rc = D.upload_state(Kc, nSr.data(), r, ngrp.data(), (int)ngroups_list.size(), cur.alpha.data(), cur.eta.data(),
+                        cur.eps.data(), cur.m.data(), cur.W.data(), cur.v.data(), cur.lam.data());
     if (rc) return rc;
     cur_groups.swap(ngroups_list);
     cmap.swap(ncmap);
@@ -1273,16 +1395,36 @@ int vbhem_em_run_groups(vbhem_base_t *h, int tau, int max_iter, double min_diff,
   if (compacted) {
     int rc = save_current();
     if (rc) return rc;
-    rc = em_upload_state(h, K0, Sr0.data(), r, G > 1 || !h->em.group.empty() ? grp0.data() : nullptr, G, full.alpha.data(),
-                         full.eta.data(), full.eps.data(), full.m.data(), full.W.data(), full.v.data(), full.lam.data());
+    rc = D.upload_state(K0, Sr0.data(), r, had_groups ? grp0.data() : nullptr, G, full.alpha.data(), full.eta.data(),
+                        full.eps.data(), full.m.data(), full.W.data(), full.v.data(), full.lam.data());
     if (rc) return rc;
-    h->lastK = 0;   // the pair results in the handle belong to the last compacted E-step: not fetchable
   }
-  h->counters[6] = ncompact;
+  int rc = D.sync();
+  if (rc) return rc;
+  if (ncompact_out) *ncompact_out = compacted ? ncompact : 0;
   for (int g = 0; g < G; g++) {
     iters[g] = it[g];
     if (unstable) unstable[g] = bad[g];
   }
+  return VBHEM_OK;
+}
+}  // namespace
+
+int vbhem_em_run(vbhem_base_t *h, int tau, int max_iter, double min_diff, double *LogLs, int *iters, int *unstable) {
+  if (!h) return fail(VBHEM_EINVAL, "base handle is NULL");
+  SingleDriver D(h);
+  return em_run_one(D, tau, max_iter, min_diff, LogLs, iters, unstable);
+}
+
+int vbhem_em_run_groups(vbhem_base_t *h, int tau, int max_iter, double min_diff, double *LogLs, int ld, int *iters,
+                        int *unstable) {
+  if (!h) return fail(VBHEM_EINVAL, "base handle is NULL");
+  SingleDriver D(h);
+  int ncompact = 0;
+  int rc = em_run_groups(D, tau, max_iter, min_diff, LogLs, ld, iters, unstable, &ncompact);
+  if (rc) return rc;
+  if (ncompact) h->lastK = 0;   // the pair results in the handle belong to the last compacted E-step: not fetchable
+  h->counters[6] = ncompact;
   return VBHEM_OK;
 }
 
@@ -1304,11 +1446,11 @@ int vbhem_finalize_stats(vbhem_base_t *h, int K, const int32_t *Sr, int maxSr, i
   const int d = h->B.d, dd = h->B.dd;
   const size_t ns = vbhem_stats_size(K, maxSr, d, h->B.covmode, ngroups);
   CU(h->stats.ensure(sizeof(double) * ns));
-  CU(h->cen_i.ensure(sizeof(int) * (size_t)(K + ngroups + 1)));
-  CU(cudaMemcpyAsync(h->cen_i.p, Sr, sizeof(int) * K, cudaMemcpyHostToDevice, h->st));
+  CU(h->fin_i.ensure(sizeof(int) * (size_t)K));
+  CU(cudaMemcpyAsync(h->fin_i.p, Sr, sizeof(int) * K, cudaMemcpyHostToDevice, h->st));
   CU(cudaMemcpyAsync(h->stats.p, stats, sizeof(double) * ns, cudaMemcpyHostToDevice, h->st));
   StatsPtr S = carve_stats(h->stats.as<double>(), K, maxSr, d, dd, ngroups);
-  launch_finalize(K, maxSr, d, h->B.covmode, h->cen_i.as<int>(), S.Nj, S.xi, S.pr, S.mu, S.Mu, h->st);
+  launch_finalize(K, maxSr, d, h->B.covmode, h->fin_i.as<int>(), S.Nj, S.xi, S.pr, S.mu, S.Mu, h->st);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(stats, h->stats.p, sizeof(double) * ns, cudaMemcpyDeviceToHost, h->st));
   CU(cudaStreamSynchronize(h->st));
@@ -1319,10 +1461,11 @@ int vbhem_finalize_stats_dev(vbhem_base_t *h, int K, const int32_t *Sr, int maxS
   if (!h || !Sr || !stats_dev) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: NULL argument");
   if (K < 1 || maxSr < 1 || ngroups < 1) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: bad sizes");
   CU(cudaSetDevice(h->device));
-  CU(h->cen_i.ensure(sizeof(int) * (size_t)(K + ngroups + 1)));
-  CU(cudaMemcpyAsync(h->cen_i.p, Sr, sizeof(int) * K, cudaMemcpyHostToDevice, h->st));
+  // Sr comes from pageable caller memory: the copy is staged by the runtime before the call returns
+  CU(h->fin_i.ensure(sizeof(int) * (size_t)K));
+  CU(cudaMemcpyAsync(h->fin_i.p, Sr, sizeof(int) * K, cudaMemcpyHostToDevice, h->st));
   StatsPtr S = carve_stats(stats_dev, K, maxSr, h->B.d, h->B.dd, ngroups);
-  launch_finalize(K, maxSr, h->B.d, h->B.covmode, h->cen_i.as<int>(), S.Nj, S.xi, S.pr, S.mu, S.Mu, h->st);
+  launch_finalize(K, maxSr, h->B.d, h->B.covmode, h->fin_i.as<int>(), S.Nj, S.xi, S.pr, S.mu, S.Mu, h->st);
   CU(cudaGetLastError());
   return VBHEM_OK;
 }
@@ -1362,6 +1505,8 @@ int vbhem_measure_fp64_peak(int device, double out[2]) {
 
 int vbhem_last_counters(vbhem_base_t *h, long long out[8]) {
   if (!h || !out) return fail(VBHEM_EINVAL, "NULL argument");
+  int rc = settle_counters(h);    // active pairs and fall-backs of a non-synchronising E-step are still on the device
+  if (rc) return rc;
   memcpy(out, h->counters, sizeof h->counters);
   return VBHEM_OK;
 }

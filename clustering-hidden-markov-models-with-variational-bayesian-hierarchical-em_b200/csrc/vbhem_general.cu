@@ -226,7 +226,7 @@ __device__ void store_pair(const BaseView &B, const CentreView &C, const PairOut
   for (int q = lane; q < ro * dd; q += 32) O.Mu[q + (size_t)ro * dd * p] = o_Mu[q];
 }
 
-// flags: optional per-pair (all-pairs work) or per-item (chunk work) filter; only
+// flags: optional per-pair (all-pairs work) or per-item (list work) filter; only
 // entries with a non-zero flag are processed.  count: optional device counter; the
 // kernel returns at once when it is zero (nothing was flagged).
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
@@ -250,16 +250,25 @@ k_general(BaseView B, CentreView C, int T, PairWork W, PairOut O, const unsigned
       __syncwarp();
     }
   } else {
-    for (int c = (int)warp; c < W.nchunks; c += (int)nwarps) {
-      const int2 ch = W.chunks[c];
-      double *part = O.partial + (size_t)O.per * c;
-      if (!flags)
-        for (int q = lane; q < per; q += 32) part[q] = 0.0;
-      for (int e = 0; e < ch.y; e++) {
-        if (flags && !flags[ch.x + e]) continue;
-        const PairItem it = W.items[ch.x + e];
+    // list work (PairWork): one warp per range; slot (range + centre) is owned by that warp alone
+    const int nitems = W.totals[0], ipr = W.totals[1];
+    for (int w = (int)warp; w < W.nranges; w += (int)nwarps) {
+      const int e0 = w * ipr, e1 = min(e0 + ipr, nitems);
+      int jcur = -1;
+      double *part = nullptr;
+      for (int e = e0; e < e1; e++) {
+        if (flags && !flags[e]) continue;
+        const PairItem it = W.items[e];
+        if (it.j != jcur) {
+          jcur = it.j;
+          part = O.partial + (size_t)O.per * (w + jcur);
+          if (!flags)                                   // primary path: this warp initialises the slot
+            for (int q = lane; q < per; q += 32) part[q] = 0.0;
+          __syncwarp();
+        }
+        const double wgt = W.zhat[it.i + (size_t)B.N * it.j] * W.Ntilde[it.i];
         pair_general(B, C, T, it.i, it.j, s, ro, true, lane);
-        for (int q = lane; q < per; q += 32) part[q] += it.w * s.out[q];
+        for (int q = lane; q < per; q += 32) part[q] += wgt * s.out[q];
         __syncwarp();
       }
     }
@@ -278,7 +287,8 @@ int launch_general(const BaseView &B, const CentreView &C, int T, const PairWork
                    const unsigned char *flags, const int *count, double *scratch, size_t scratch_doubles,
                    cudaStream_t st) {
   const size_t per_warp = general_scratch_per_warp(B.maxSb, C.maxSr, B.d, B.dd, T);
-  const long long units = W.items ? W.nchunks : W.npairs;
+  long long units = W.items ? W.nranges : W.npairs;
+  if (W.items && W.npairs < units) units = W.npairs;   // never more ranges in use than items
   if (units <= 0) return 0;
   long long warps = (long long)(scratch_doubles / per_warp);
   if (warps > units) warps = units;

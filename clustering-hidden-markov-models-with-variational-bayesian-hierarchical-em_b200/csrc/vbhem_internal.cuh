@@ -48,29 +48,37 @@ struct CentreView {
 };
 constexpr int kTileClasses = 4;
 
-// One unit of second-pass work.
-struct PairItem { int i, j; double w; };
+// One unit of second-pass work: the pair (base i, centre j); its weight Z = zhat[i + N j] * Ntilde[i] is read
+// where it is used.
+struct PairItem { int i, j; };
 
 // Where a pair kernel puts its results.
 //   mode 0: L_elbo only
 //   mode 1: literal per-pair outputs (Boundary-1)
-//   mode 2: weighted accumulation of the per-pair statistics into per-chunk
+//   mode 2: weighted accumulation of the per-pair statistics into per-range
 //           partial sums (deterministic second pass of the fused E-step)
 struct PairOut {
   int mode;
   double *L_elbo;                               // [N, K]
   double *nu1, *xi, *pr, *mu, *Mu;              // mode 1, leading dim maxSr, pair index p = i + N*j
-  double *partial;                              // mode 2: [nchunks][per] raw sums of one centre
+  double *partial;                              // mode 2: [nranges + K][per] raw sums, slot = range + centre
   int per;                                      // doubles per centre statistic block
 };
 
-// Work description: either every (i, j) pair or an explicit list cut in chunks
-// that never straddle two centres.
+// Work description: either every (i, j) pair or an explicit list (centre-major, base-ascending) whose LENGTH
+// LIVES ON THE DEVICE, so that the host never waits for it: totals = {#items, items per range}.  The list is cut
+// in `nranges` contiguous ranges of totals[1] items (range w = items [w * totals[1], (w + 1) * totals[1]));
+// one warp owns a range, accumulates the weighted statistics of one centre in registers and writes them to
+// partial slot (w + j) whenever the centre changes -- ranges and centres both ascend along the list, so the
+// slot is unique, at most nranges + K slots exist, and the slots of centre j are the consecutive ones of the
+// ranges that overlap [seg_start[j], seg_start[j + 1]).
 struct PairWork {
   const PairItem *items;  // nullptr => all pairs
-  const int2 *chunks;     // [nchunks] (start, len) into items; nullptr when items == nullptr
-  int nchunks;
-  long long npairs;
+  const int *totals;      // device {#items, items per range}; nullptr when items == nullptr
+  const double *zhat;     // [N, K] and
+  const double *Ntilde;   // [N]: weight of item (i, j) = zhat[i + N j] * Ntilde[i]
+  int nranges;
+  long long npairs;       // all-pairs work: N * K; list work: upper bound of the list length
 };
 
 // Pairs the lattice kernel could not finish in the linear domain: one byte per
@@ -111,15 +119,17 @@ int launch_zhat(int N, int K, int ngroups, const int *gstart, const double *L_el
                 const double *Ntilde, double *zhat, double *Nj_part, int *cnt, double *lb_part, double *Nj, double *lb,
                 cudaStream_t st, int blk0 = 0, int nblk = -1, bool reduce = true);
 int zhat_block_size();
-// deterministic (centre-major, base-ascending) list of those pairs, cut in chunks of at most chunk_len (shorter,
-// totals[2], when there are fewer than target_chunks of them); totals = {#active, #chunks, chunk length}
-int launch_list_scan(int N, int K, int chunk_len, int target_chunks, const int *cnt, int *offs, int *segcnt,
-                     int *seg_start, int *chunk_start, int *totals, cudaStream_t st);
-int launch_list_fill(int N, int K, int chunk_len, int nchunks, const double *zhat, const double *Ntilde,
-                     const int *offs, const int *seg_start, const int *chunk_start, PairItem *items, int2 *chunks,
+// deterministic (centre-major, base-ascending) list of those pairs; seg_start[K + 1] = first item of every centre,
+// totals = {#active, items per range = ceil(#active / nranges), at least 1}.  Nothing here depends on a value the
+// host would have to read back: every grid is sized by N and K alone.
+int launch_list_scan(int N, int K, int nranges, const int *cnt, int *offs, int *segcnt, int *seg_start, int *totals,
                      cudaStream_t st);
-int launch_partial_reduce(int K, int per, const int *chunk_start, const double *partial, double *S_nu1, double *S_xi,
-                          double *S_pr, double *S_mu, double *S_Mu, int r, int d, int dd, cudaStream_t st);
+int launch_list_fill(int N, int K, const double *zhat, const double *Ntilde, const int *offs, const int *seg_start,
+                     PairItem *items, cudaStream_t st);
+// S_*[., j] = sum of centre j's partial slots in range order (see PairWork)
+int launch_partial_reduce(int K, int per, const int *seg_start, const int *totals, const double *partial,
+                          double *S_nu1, double *S_xi, double *S_pr, double *S_mu, double *S_Mu, int r, int d, int dd,
+                          cudaStream_t st);
 int launch_finalize(int K, int maxSr, int d, int covmode, const int *Sr, double *Nj, double *S_xi, double *S_pr,
                     double *S_mu, double *S_Mu, cudaStream_t st);
 

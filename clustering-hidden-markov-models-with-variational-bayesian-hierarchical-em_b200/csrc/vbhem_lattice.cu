@@ -747,54 +747,67 @@ k_lattice_full(BaseView B, CentreView C, int T, PairWork W, PairOut O, Fallback 
     return;
   }
 
-  // second pass of the fused E-step: one warp per chunk (single centre), weighted sums in registers
-  for (int ch = (int)gw; ch < W.nchunks; ch += (int)nw) {
-    const int2 cr = W.chunks[ch];
-    const int j = W.items[cr.x].j;
+  // second pass of the fused E-step: one warp per range of the device-side list (PairWork), the weighted sums
+  // of one centre in registers, written to slot (range + centre) whenever the centre changes
+  const int nitems = W.totals[0], ipr = W.totals[1];
+  for (int w = (int)gw; w < W.nranges; w += (int)nw) {
+    const int e0 = w * ipr, e1 = min(e0 + ipr, nitems);
+    if (e0 >= e1) break;                                   // ranges ascend: nothing further for this warp either
+    int jcur = -1;
     CentreConst<D, FULL> c;
-    const double *rec = C.rec + (size_t)C.rec_stride * j;
-    load_centre(c, rec, g, q);
-    PairStats<D, FULL> acc;
-    acc.nu1 = acc.pr = 0.0;
-    acc.xi = Frag{0.0, 0.0};
+    const double *rec = nullptr;
+    PairStats<D, FULL> acc{};
+    auto flush = [&]() {
+      double *part = O.partial + (size_t)O.per * (w + jcur);
+      double *p_nu1 = part, *p_xi = part + ro, *p_pr = p_xi + ro * ro, *p_mu = p_pr + ro, *p_Mu = p_mu + ro * D;
+      if (g < ro) {
+        if (2 * q < ro) p_xi[(2 * q) + ro * g] = acc.xi.x0;
+        if (2 * q + 1 < ro) p_xi[(2 * q + 1) + ro * g] = acc.xi.x1;
+        if (q == 0) {
+          p_nu1[g] = acc.nu1;
+          p_pr[g] = acc.pr;
 #pragma unroll
-    for (int k = 0; k < D; k++) acc.mu[k] = 0.0;
+          for (int k = 0; k < D; k++) p_mu[g + ro * k] = acc.mu[k];
 #pragma unroll
-    for (int k = 0; k < DD; k++) acc.Mu[k] = 0.0;
-    for (int e = 0; e < cr.y; e++) {
-      const PairItem it = W.items[cr.x + e];
+          for (int k = 0; k < DD; k++) p_Mu[g + ro * k] = acc.Mu[k];
+        }
+      }
+    };
+    for (int e = e0; e < e1; e++) {
+      const PairItem it = W.items[e];
+      if (it.j != jcur) {
+        if (jcur >= 0) flush();
+        jcur = it.j;
+        rec = C.rec + (size_t)C.rec_stride * jcur;
+        load_centre(c, rec, g, q);
+        acc.nu1 = acc.pr = 0.0;
+        acc.xi = Frag{0.0, 0.0};
+#pragma unroll
+        for (int k = 0; k < D; k++) acc.mu[k] = 0.0;
+#pragma unroll
+        for (int k = 0; k < DD; k++) acc.Mu[k] = 0.0;
+      }
+      const double wgt = W.zhat[it.i + (size_t)B.N * it.j] * W.Ntilde[it.i];
       BaseConst<D, FULL> b;
       load_base(b, B, it.i, g, q);
       PairStats<D, FULL> st;
       double Le;
       const bool ok = pair_full(B, it.i, b, c, rec, T, ltab, etab, sm, g, q, Le, st);
+      if (lane == 0) fb.flags[e] = ok ? 0 : 1;             // every item: the flag array needs no clearing
       if (!ok) {
-        if (lane == 0) { fb.flags[cr.x + e] = 1; atomicAdd(fb.count, 1); }
+        if (lane == 0) atomicAdd(fb.count, 1);
         continue;
       }
-      acc.nu1 += it.w * st.nu1;
-      acc.pr += it.w * st.pr;
-      acc.xi.x0 += it.w * st.xi.x0;
-      acc.xi.x1 += it.w * st.xi.x1;
+      acc.nu1 += wgt * st.nu1;
+      acc.pr += wgt * st.pr;
+      acc.xi.x0 += wgt * st.xi.x0;
+      acc.xi.x1 += wgt * st.xi.x1;
 #pragma unroll
-      for (int k = 0; k < D; k++) acc.mu[k] += it.w * st.mu[k];
+      for (int k = 0; k < D; k++) acc.mu[k] += wgt * st.mu[k];
 #pragma unroll
-      for (int k = 0; k < DD; k++) acc.Mu[k] += it.w * st.Mu[k];
+      for (int k = 0; k < DD; k++) acc.Mu[k] += wgt * st.Mu[k];
     }
-    double *part = O.partial + (size_t)O.per * ch;
-    double *p_nu1 = part, *p_xi = part + ro, *p_pr = p_xi + ro * ro, *p_mu = p_pr + ro, *p_Mu = p_mu + ro * D;
-    if (g < ro) {
-      if (2 * q < ro) p_xi[(2 * q) + ro * g] = acc.xi.x0;
-      if (2 * q + 1 < ro) p_xi[(2 * q + 1) + ro * g] = acc.xi.x1;
-      if (q == 0) {
-        p_nu1[g] = acc.nu1;
-        p_pr[g] = acc.pr;
-#pragma unroll
-        for (int k = 0; k < D; k++) p_mu[g + ro * k] = acc.mu[k];
-#pragma unroll
-        for (int k = 0; k < DD; k++) p_Mu[g + ro * k] = acc.Mu[k];
-      }
-    }
+    flush();
   }
 }
 
@@ -898,7 +911,8 @@ int launch_lattice_full(const BaseView &B, const CentreView &C, int T, const Pai
   int wpb = (int)(kSmemBudget / pw);
   if (wpb > 16) wpb = 16;
   if (wpb < 1) return -1;
-  const long long units = W.items ? W.nchunks : W.npairs;
+  long long units = W.items ? W.nranges : W.npairs;       // list work: its length is on the device; every range gets a warp
+  if (W.items && W.npairs < units) units = W.npairs;
   if (units <= 0) return 0;
   long long blocks = (units + wpb - 1) / wpb;
   const long long cap = sm_count();

@@ -402,3 +402,56 @@ def test_split_tiles_match_one_centre_per_tile(sr_list, tiles, split, covmode, d
         assert np.array_equal(got[k], again[k]), k
     np.testing.assert_allclose(got["L_elbo"], ref["L_elbo"], rtol=1e-13, atol=0)
     check_fused(got, oracle_fused(base, cen, 7), 150)
+
+
+def test_estep_dev_returns_without_synchronising():
+    """include/vbhem_b200.h: vbhem_estep_hyp_dev / vbhem_em_estep enqueue the whole E-step -- including the second
+    pass, whose size (the pairs with Z > 1e-8) is known on the device only -- and return.  A long spin kernel is put
+    on the stream first: if any call in the E-step waited for the stream, the spin would be over when it returns."""
+    import ctypes as C
+    import torch
+    from vbhem_b200._lib import check, dp, ip, lib
+    base, hyp, cen = make_case(N=3000, K=6, Sb=4, Sr=4, d=2, covmode="full", ragged=False, seed=23, Nv=30.0)
+    with BaseSet(base) as bs:
+        want = bs.estep_hyp(hyp, 6, want_pairs=False)["buf"]
+        st = torch.cuda.current_stream()
+        bs.set_stream(st.cuda_stream)
+        K, r = hyp["eta"].shape
+        c = np.ascontiguousarray
+        Sr = c(hyp["Sr"], dtype=np.int32)
+        H = [c(hyp["alpha"]), c(hyp["eta"]), c(np.transpose(hyp["epsilon"], (0, 2, 1))), c(hyp["m"]),
+             c(np.transpose(hyp["W"], (0, 1, 3, 2))), c(hyp["v"]), c(hyp["lam"])]
+        stats = torch.zeros(bs.stats_size(K, r), dtype=torch.float64, device="cuda")
+        for _ in range(2):                                # warm: allocations of the first call may synchronise
+            check(lib().vbhem_estep_hyp_dev(bs._h, K, Sr.ctypes.data_as(ip), r, None, 1, 6,
+                                            *[h.ctypes.data_as(dp) for h in H], C.c_void_p(stats.data_ptr()), None))
+        torch.cuda.synchronize()
+        torch.cuda._sleep(int(2e9))                       # ~1 s of spinning on the stream
+        check(lib().vbhem_estep_hyp_dev(bs._h, K, Sr.ctypes.data_as(ip), r, None, 1, 6,
+                                        *[h.ctypes.data_as(dp) for h in H], C.c_void_p(stats.data_ptr()), None))
+        assert not st.query(), "the E-step waited for its stream"
+        torch.cuda.synchronize()
+        assert np.array_equal(stats.cpu().numpy(), want)
+        assert bs.counters()["active_pairs"] > 0          # read back on demand
+
+
+def test_em_state_survives_other_esteps_on_the_handle():
+    """the device-resident EM run keeps its own hyper-parameters / state counts; an ordinary E-step with a
+    different centre set in between must neither corrupt it nor be silently mixed into its lower bound."""
+    from vbhem_b200 import synth
+    from vbhem_b200._lib import VbhemError
+    base, hyp, cen = make_case(N=300, K=6, Sb=5, Sr=4, d=2, covmode="full", ragged=True, seed=31, Nv=20.0)
+    _, hyp2, _ = make_case(N=300, K=3, Sb=5, Sr=3, d=2, covmode="full", ragged=False, seed=32, Nv=20.0)
+    opt = dict(synth.DEFAULT_OPT, Nv=20.0, tau=5)
+    with BaseSet(base) as bs:
+        bs.em_begin(hyp, opt)
+        want = bs.em_run(5, 3, 0.0)
+        bs.em_begin(hyp, opt)
+        bs.em_estep(5)
+        bs.estep_hyp(hyp2, 5)                             # another centre set (K = 3) on the same handle
+        with pytest.raises(VbhemError):
+            bs.em_lower_bound()                           # its pre-pass is gone: refused, not wrong
+        got = bs.em_run(5, 3, 0.0)                        # the run itself is intact
+    np.testing.assert_array_equal(got["LogLs"], want["LogLs"])
+    for k in ("alpha", "eta", "m", "W"):
+        np.testing.assert_array_equal(got["hyp"][k], want["hyp"][k])
