@@ -73,6 +73,29 @@ SIGNATURES = {
     "vbhmm_batch_free": (C.c_int, [vp]),
     "vbhmm_gmm_fit": (C.c_int, [vp, C.c_int, ip, ip, C.c_int, ip, ip, C.c_int, C.c_double, C.c_double, dp, dp, dp, dp,
                                 ip]),
+    "vbhem_multi_unique_id": (C.c_int, [C.POINTER(C.c_ubyte)]),
+    "vbhem_multi_pack_base": (C.c_int, [C.c_int, ip, C.c_int, C.c_int, C.POINTER(C.c_ubyte), C.c_int, ip, C.c_int,
+                                        C.c_int, C.c_int, dp, dp, dp, dp, dp, C.POINTER(vp)]),
+    "vbhem_multi_free": (C.c_int, [vp]),
+    "vbhem_multi_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "vbhem_multi_shard": (C.c_int, [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                    C.POINTER(vp)]),
+    "vbhem_multi_set_kernel": (C.c_int, [vp, C.c_int]),
+    "vbhem_multi_estep": (C.c_int, [vp, C.c_int, ip, C.c_int, ip, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp,
+                                    dp, dp, dp]),
+    "vbhem_multi_estep_hyp": (C.c_int, [vp, C.c_int, ip, C.c_int, ip, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, dp,
+                                        dp, dp, dp, dp]),
+    "vbhem_multi_fetch": (C.c_int, [vp, dp, dp]),
+    "vbhem_multi_finalize_stats": (C.c_int, [vp, C.c_int, ip, C.c_int, C.c_int, dp]),
+    "vbhem_multi_em_begin": (C.c_int, [vp, C.c_int, ip, C.c_int, ip, C.c_int, C.c_double, C.c_double, C.c_double,
+                                       C.c_double, C.c_double, dp, dp, C.c_int, dp, dp, dp, dp, dp, dp, dp]),
+    "vbhem_multi_em_run": (C.c_int, [vp, C.c_int, C.c_int, C.c_double, dp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "vbhem_multi_em_run_groups": (C.c_int, [vp, C.c_int, C.c_int, C.c_double, dp, C.c_int, C.POINTER(C.c_int),
+                                            C.POINTER(C.c_int)]),
+    "vbhem_multi_em_step": (C.c_int, [vp, C.c_int, dp]),
+    "vbhem_multi_em_fetch": (C.c_int, [vp, dp, dp, dp, dp, dp, dp, dp]),
+    "vbhem_multi_last_ms": (C.c_int, [vp, dp]),
+    "vbhem_multi_counters": (C.c_int, [vp, C.POINTER(C.c_longlong)]),
     "vbhem_set_profile": (C.c_int, [vp, C.c_int]),
     "vbhem_last_timings": (C.c_int, [vp, dp]),
     "vbhem_measure_fp64_peak": (C.c_int, [C.c_int, dp]),

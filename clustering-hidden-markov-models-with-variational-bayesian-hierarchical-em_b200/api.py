@@ -265,3 +265,180 @@ class BaseSet:
         out = pack.stats_to_natural(S, self.d, self.covmode)
         return dict(Nj=out["Nj"], Nj_rho1=out["nu1"], Nj_rho2rho=out["xi"], Nj_rho=out["pr"], y_bar=out["mu"],
                     S_plus_C=out["Mu"], lb=out["lb"])
+
+
+def _hyp_arrays(hyp: dict, covmode: int):
+    """Natural centre hyper-parameters -> the C-ABI arrays of vbhem_estep_hyp (contiguous, column-major meaning)."""
+    c = np.ascontiguousarray
+    f64 = lambda a: c(a, dtype=np.float64)
+    K, r = hyp["eta"].shape
+    Sr = c(hyp.get("Sr", np.full(K, r)), dtype=np.int32)
+    W = np.asarray(hyp["W"], dtype=np.float64)
+    Wp = c(np.transpose(W, (0, 1, 3, 2))) if covmode == 1 else c(W)
+    eps = c(np.transpose(hyp["epsilon"], (0, 2, 1)), dtype=np.float64)
+    return K, r, Sr, [f64(hyp["alpha"]), f64(hyp["eta"]), eps, f64(hyp["m"]), Wp, f64(hyp["v"]), f64(hyp["lam"])]
+
+
+class MultiBaseSet:
+    """A base set sharded over several GPUs behind the C ABI (``vbhem_multi_*``): one host process drives every
+    device (the arrangement of the reference's single-session ``parfor``, vbhem_h3m_c.m:28), or -- with ``world`` /
+    ``rank_first`` / ``unique_id`` -- one process per device.  Same results as :class:`BaseSet` up to fp64
+    summation order; the raw statistics are all-reduced with NCCL inside the library."""
+
+    def __init__(self, base: dict, devices=None, packed: bool = False, world: int | None = None, rank_first: int = 0,
+                 unique_id: bytes | None = None):
+        pb = base if packed else pack.pack_base(base)
+        self.N, self.maxSb, self.d, self.covmode = pb["N"], pb["maxSb"], pb["d"], pb["covmode"]
+        self.dd = self.d * self.d if self.covmode else self.d
+        if devices is None:
+            n = C.c_int()
+            check(lib().vbhem_device_count(C.byref(n)))
+            devices = list(range(n.value))
+        self.devices = [int(x) for x in devices]
+        dv = np.ascontiguousarray(self.devices, dtype=np.int32)
+        self.world = len(self.devices) if world is None else int(world)
+        idp = None
+        if unique_id is not None:
+            self._id = (C.c_ubyte * 128).from_buffer_copy(unique_id)
+            idp = self._id
+        self._h = C.c_void_p()
+        check(lib().vbhem_multi_pack_base(len(self.devices), _i(dv), self.world, int(rank_first), idp, self.N,
+                                          _i(pb["Sb"]), self.maxSb, self.d, self.covmode, _d(pb["prior"]),
+                                          _d(pb["A"]), _d(pb["mu"]), _d(pb["cov"]), _d(pb["Ntilde"]),
+                                          C.byref(self._h)))
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_ubyte * 128)()
+        check(lib().vbhem_multi_unique_id(buf))
+        return bytes(buf)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().vbhem_multi_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_kernel(self, which: str = "auto"):
+        check(lib().vbhem_multi_set_kernel(self._h, {"auto": 0, "general": 1, "unpaired": 2, "halves": 3}[which]))
+
+    def shards(self):
+        out = []
+        for k in range(len(self.devices)):
+            dev, lo, n = C.c_int(), C.c_int(), C.c_int()
+            check(lib().vbhem_multi_shard(self._h, k, C.byref(dev), C.byref(lo), C.byref(n), None))
+            out.append((dev.value, lo.value, n.value))
+        return out
+
+    def counters(self) -> dict:
+        out = (C.c_longlong * 8)()
+        check(lib().vbhem_multi_counters(self._h, out))
+        return dict(launches=out[0], lattice_pairs=out[1], general_pairs=out[2], active_pairs=out[3], tiles=out[4],
+                    split_tiles=out[5], compactions=out[6])
+
+    def last_ms(self) -> float:
+        ms = C.c_double()
+        check(lib().vbhem_multi_last_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    _split_stats = BaseSet._split_stats
+    stats_size = BaseSet.stats_size
+
+    def estep_hyp(self, hyp: dict, tau: int, want_pairs: bool = True, group=None) -> dict:
+        """As :meth:`BaseSet.estep_hyp`; the statistics are the sums over ALL shards (and ranks)."""
+        K, r, Sr, H = _hyp_arrays(hyp, self.covmode)
+        grp = None if group is None else np.ascontiguousarray(group, dtype=np.int32)
+        ng = int(grp.max()) + 1 if grp is not None else 1
+        buf = np.zeros(self.stats_size(K, r, ng))
+        pre = np.zeros(K + r * K * (2 + r))
+        L = np.zeros((K, self.N)) if want_pairs else None
+        z = np.zeros((K, self.N)) if want_pairs else None
+        check(lib().vbhem_multi_estep_hyp(self._h, K, _i(Sr), r, _i(grp), ng, tau, *[_d(h) for h in H], _d(L), _d(z),
+                                          _d(buf), _d(pre)))
+        S = self._split_stats(buf, K, r, ng)
+        S["L_elbo"], S["zhat"] = L, z
+        out = pack.stats_to_natural(S, self.d, self.covmode)
+        out["buf"] = buf
+        return out
+
+    def estep(self, cen: dict, tau: int, want_pairs: bool = True) -> dict:
+        pc = pack.pack_centres(cen)
+        K, r = pc["K"], pc["maxSr"]
+        grp = pc.get("group")
+        ng = int(grp.max()) + 1 if grp is not None else 1
+        buf = np.zeros(self.stats_size(K, r, ng))
+        L = np.zeros((K, self.N)) if want_pairs else None
+        z = np.zeros((K, self.N)) if want_pairs else None
+        check(lib().vbhem_multi_estep(self._h, K, _i(pc["Sr"]), r, _i(grp), ng, tau, _d(pc["logPi"]), _d(pc["logA"]),
+                                      _d(pc["m"]), _d(pc["vW"]), _d(pc["cterm"]), _d(pc["logOmega"]), _d(L), _d(z),
+                                      _d(buf)))
+        S = self._split_stats(buf, K, r, ng)
+        S["L_elbo"], S["zhat"] = L, z
+        out = pack.stats_to_natural(S, self.d, self.covmode)
+        out["buf"] = buf
+        return out
+
+    def finalize(self, buf: np.ndarray, Sr, r: int, ng: int = 1) -> dict:
+        Sr = np.ascontiguousarray(Sr, dtype=np.int32)
+        K = Sr.shape[0]
+        buf = np.ascontiguousarray(buf, dtype=np.float64).copy()
+        check(lib().vbhem_multi_finalize_stats(self._h, K, _i(Sr), r, ng, _d(buf)))
+        S = self._split_stats(buf, K, r, ng)
+        out = pack.stats_to_natural(S, self.d, self.covmode)
+        return dict(Nj=out["Nj"], Nj_rho1=out["nu1"], Nj_rho2rho=out["xi"], Nj_rho=out["pr"], y_bar=out["mu"],
+                    S_plus_C=out["Mu"], lb=out["lb"])
+
+    # -- device-resident EM over the shards ----------------------------------
+    def em_begin(self, hyp: dict, opt: dict, group=None):
+        K, r, Sr, H = _hyp_arrays(hyp, self.covmode)
+        grp = None if group is None else np.ascontiguousarray(group, dtype=np.int32)
+        ng = int(grp.max()) + 1 if grp is not None else 1
+        self._em = dict(K=K, r=r, Sr=Sr, grp=grp, ng=ng)
+        m0 = np.ascontiguousarray(np.asarray(opt["m0"], float).reshape(self.d))
+        W0 = np.ascontiguousarray(np.atleast_1d(np.asarray(opt["W0"], float)))
+        check(lib().vbhem_multi_em_begin(self._h, K, _i(Sr), r, _i(grp), ng, float(opt["alpha0"]), float(opt["eta0"]),
+                                         float(opt["epsilon0"]), float(opt["lambda0"]), float(opt["v0"]), _d(m0),
+                                         _d(W0), int(W0.size), *[_d(h) for h in H]))
+
+    def em_step(self, tau: int) -> np.ndarray:
+        out = np.zeros((self._em["ng"], 12))
+        check(lib().vbhem_multi_em_step(self._h, tau, _d(out)))
+        return out
+
+    def em_fetch(self) -> dict:
+        K, r, d = self._em["K"], self._em["r"], self.d
+        o = dict(alpha=np.zeros(K), eta=np.zeros((K, r)), eps=np.zeros((K, r, r)), m=np.zeros((K, r, d)),
+                 W=np.zeros((K, r, d, d) if self.covmode else (K, r, d)), v=np.zeros((K, r)), lam=np.zeros((K, r)))
+        check(lib().vbhem_multi_em_fetch(self._h, _d(o["alpha"]), _d(o["eta"]), _d(o["eps"]), _d(o["m"]), _d(o["W"]),
+                                         _d(o["v"]), _d(o["lam"])))
+        return dict(alpha=o["alpha"], eta=o["eta"], epsilon=np.transpose(o["eps"], (0, 2, 1)).copy(), m=o["m"],
+                    W=np.transpose(o["W"], (0, 1, 3, 2)).copy() if self.covmode else o["W"], v=o["v"], lam=o["lam"],
+                    Sr=self._em["Sr"].copy())
+
+    def em_run(self, tau: int, max_iter: int = 200, min_diff: float = 1e-5) -> dict:
+        LogLs = np.zeros(max_iter + 2)
+        it, bad = C.c_int(), C.c_int()
+        check(lib().vbhem_multi_em_run(self._h, tau, max_iter, min_diff, _d(LogLs), C.byref(it), C.byref(bad)))
+        n = it.value + (1 if bad.value else 0)
+        return dict(LogLs=LogLs[:n].copy(), iters=it.value, unstable=bool(bad.value), hyp=self.em_fetch())
+
+    def em_run_groups(self, tau: int, max_iter: int = 200, min_diff: float = 1e-5) -> dict:
+        G, ld = self._em["ng"], max_iter + 2
+        LogLs = np.zeros((G, ld))
+        it, bad = np.zeros(G, np.int32), np.zeros(G, np.int32)
+        check(lib().vbhem_multi_em_run_groups(self._h, tau, max_iter, min_diff, _d(LogLs), ld,
+                                              it.ctypes.data_as(C.POINTER(C.c_int)),
+                                              bad.ctypes.data_as(C.POINTER(C.c_int))))
+        return dict(LogLs=[LogLs[g, :it[g] + (1 if bad[g] else 0)].copy() for g in range(G)], iters=it,
+                    unstable=bad.astype(bool), hyp=self.em_fetch())

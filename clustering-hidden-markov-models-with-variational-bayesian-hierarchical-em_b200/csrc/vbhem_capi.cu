@@ -785,6 +785,7 @@ int vbhem_repack_base(vbhem_base_t *h, const int32_t *Sb, const double *prior, c
   launch_sanitize_base(h->B, h->bprior.as<double>(), h->bA.as<double>(), h->bmu.as<double>(), h->bcov.as<double>(),
                        h->st);
   CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(h->st));   // page-locked caller arrays are read by DMA: keep them valid until here
   return VBHEM_OK;
 }
 
@@ -1157,7 +1158,10 @@ EmCtx em_ctx(vbhem_base *h, double *st) {
 }
 }  // namespace
 
-int vbhem_em_lower_bound(vbhem_base_t *h, double *stats_dev, double *lb_out) {
+namespace {
+// Normalise the statistics (vbhem_compute_Statistics.m:57-82) and evaluate the bound on the device; with `read`
+// the 12 * ngroups terms come back to the host (synchronises), without it everything is only enqueued.
+int em_lower_bound(vbhem_base *h, double *stats_dev, double *lb_out, bool read) {
   if (!h || !h->em.active) return fail(VBHEM_EINVAL, "vbhem_em_begin has not been called on this handle");
   if (!h->em.staged)
     return fail(VBHEM_EINVAL, "vbhem_em_lower_bound needs the pre-pass of this run's own E-step: call vbhem_em_estep "
@@ -1167,11 +1171,17 @@ int vbhem_em_lower_bound(vbhem_base_t *h, double *stats_dev, double *lb_out) {
   EmCtx c = em_ctx(h, stats_dev ? stats_dev : em.stats.as<double>());
   launch_finalize(em.K, em.maxSr, h->B.d, h->B.covmode, c.E.Sr, c.S.Nj, c.S.xi, c.S.pr, c.S.mu, c.S.Mu, h->st);
   launch_lower_bound(c.E, c.S.Nj, c.S.lb, c.dOm, c.dPi, c.dA, c.dLam, em.lb.as<double>(), h->st);
+  CU(cudaGetLastError());
+  if (!read) return VBHEM_OK;
   CU(cudaMemcpyAsync(em.h_lb, em.lb.p, sizeof(double) * 12 * em.ngroups, cudaMemcpyDeviceToHost, h->st));
   CU(cudaStreamSynchronize(h->st));
-  CU(cudaGetLastError());
   if (lb_out) memcpy(lb_out, em.h_lb, sizeof(double) * 12 * em.ngroups);
   return VBHEM_OK;
+}
+}  // namespace
+
+int vbhem_em_lower_bound(vbhem_base_t *h, double *stats_dev, double *lb_out) {
+  return em_lower_bound(h, stats_dev, lb_out, true);
 }
 
 namespace {
@@ -1512,3 +1522,5 @@ int vbhem_last_counters(vbhem_base_t *h, long long out[8]) {
 }
 
 }  // extern "C"
+
+#include "vbhem_multi.inl"

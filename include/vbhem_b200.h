@@ -73,7 +73,8 @@ int vbhem_pack_base(int device, int N, const int32_t *Sb, int maxSb, int d, int 
 int vbhem_free_base(vbhem_base_t *base);
 
 /* Re-upload a base set of the SAME shape (N, maxSb, d, covmode) into an existing handle: the
- * host-to-device copies of vbhem_pack_base without its allocations.  Ntilde may be NULL (= keep). */
+ * host-to-device copies of vbhem_pack_base without its allocations.  Ntilde may be NULL (= keep).
+ * Synchronises the handle's stream before returning, so the host arrays may be reused at once. */
 int vbhem_repack_base(vbhem_base_t *base, const int32_t *Sb, const double *prior, const double *A,
                       const double *mu, const double *cov, const double *Ntilde);
 
@@ -159,9 +160,13 @@ int vbhem_estep_hyp_stream(vbhem_base_t *base, const int32_t *Sb, const double *
 
 /* Device-resident variants for multi-GPU hosts: identical to vbhem_estep /
  * vbhem_estep_hyp, but `stats_dev` is a DEVICE pointer (e.g. a torch tensor the
- * caller then all-reduces with NCCL) and nothing is copied back; the work is
- * enqueued on the handle's stream and the call returns without synchronising.
- * L_elbo / zhat stay in the handle (vbhem_fetch). */
+ * caller then all-reduces with NCCL) and nothing is copied back; the WHOLE E-step
+ * -- including the second pass, whose size (the pairs with Z_Ni > 1e-8) is known on
+ * the device only -- is enqueued on the handle's stream and the call returns without
+ * synchronising (tests/test_gpu_parity.py::test_estep_dev_returns_without_synchronising).
+ * The centre arrays are copied to pinned staging before the call returns; `pre` is
+ * written asynchronously: synchronise before reading it.  L_elbo / zhat stay in the
+ * handle (vbhem_fetch); vbhem_last_counters synchronises to read the device-side counts. */
 int vbhem_estep_dev(vbhem_base_t *base, int K, const int32_t *Sr, int maxSr, const int32_t *group, int ngroups,
                     int tau, const double *logPi, const double *logA, const double *m, const double *vW,
                     const double *cterm, const double *logOmega, double *stats_dev);
@@ -220,6 +225,69 @@ int vbhem_em_run(vbhem_base_t *base, int tau, int max_iter, double min_diff, dou
                  int *unstable);
 int vbhem_em_run_groups(vbhem_base_t *base, int tau, int max_iter, double min_diff, double *LogLs, int ld, int *iters,
                         int *unstable);
+
+/* ---- The base set sharded over several GPUs (BASELINE north_star) -------------------------
+ * The reference's only parallelism is `parfor` inside ONE MATLAB session
+ * (/root/reference/src/vbhem/vbhem_h3m_c.m:28), so one host process must reach every GPU of the box through this
+ * boundary.  A vbhem_multi_t splits the N base HMMs contiguously over the devices (shard k = bases
+ * [k*q + min(k, N%n), ...), the first N%n shards one base longer), replicates the centres, runs the fused E-step on
+ * every shard concurrently (one host thread per device inside the library) and sums the raw per-centre statistics
+ * (vbhem_compute_Statistics.m:33-55, the buffer of vbhem_stats_size() doubles) over all shards with ONE
+ * ncclAllReduce(sum, fp64) over NVLink per E-step; the Z_Ni > 1e-8 rule is applied per shard before the sum,
+ * the normalisation of vbhem_compute_Statistics.m:57-82 after it.  Results equal the single-GPU ones up to fp64
+ * summation order (<= 1e-11 relative) and are bit-identical from run to run.
+ *
+ * Two arrangements, same entry points:
+ *   (a) one process, `nlocal` devices:  world = nlocal, rank_first = 0, id = NULL  (ncclCommInitAll);
+ *   (b) several processes (one per device, torchrun / MPI style): every process passes ITS bases, nlocal = 1 (or
+ *       more), world = total number of devices, rank_first = global rank of its first device, and the 128-byte id
+ *       that ONE process obtained from vbhem_multi_unique_id and the caller broadcast to the others.  Ntilde keeps
+ *       its global meaning (Nv * Kb_total * omega_i).
+ * NCCL is loaded at run time (libnccl.so.2, or $VBHEM_NCCL_LIB); a set with world = 1 never touches it.
+ *
+ *   vbhem_multi_pack_base     arrays as for vbhem_pack_base (HOST), N = the bases of THIS process
+ *   vbhem_multi_estep[_hyp]   as vbhem_estep[_hyp]: L_elbo / zhat [N, K] = the rows of this process's bases (may be
+ *                             NULL), stats = the RAW sums over ALL ranks (finalise with vbhem_multi_finalize_stats),
+ *                             pre as for vbhem_estep_hyp
+ *   vbhem_multi_em_begin / _em_run / _em_run_groups / _em_fetch   the device-resident EM loops of vbhem_em_* over
+ *                             the shards: every device keeps the (identical) centre hyper-parameters, only the
+ *                             statistics buffer travels; LogLs etc. as for vbhem_em_run[_groups]
+ *   vbhem_multi_em_step       one iteration (E-step + all-reduce + lower bound + M-step); lb_out[12 * ngroups]
+ *   vbhem_multi_last_ms       device time of the last E-step + all-reduce: the slowest local shard (CUDA events)
+ *   vbhem_multi_shard         shard k of this process: device, first base, number of bases, its single-GPU handle
+ *   vbhem_multi_counters      vbhem_last_counters summed over the local shards */
+#define VBHEM_UNIQUE_ID_BYTES 128
+typedef struct vbhem_multi vbhem_multi_t;
+int vbhem_multi_unique_id(unsigned char id[VBHEM_UNIQUE_ID_BYTES]);
+int vbhem_multi_pack_base(int nlocal, const int *devices, int world, int rank_first, const unsigned char *id, int N,
+                          const int32_t *Sb, int maxSb, int d, int covmode, const double *prior, const double *A,
+                          const double *mu, const double *cov, const double *Ntilde, vbhem_multi_t **out);
+int vbhem_multi_free(vbhem_multi_t *multi);
+int vbhem_multi_info(vbhem_multi_t *multi, int *nlocal, int *world, int *N);
+int vbhem_multi_shard(vbhem_multi_t *multi, int k, int *device, int *first, int *count, vbhem_base_t **handle);
+int vbhem_multi_set_kernel(vbhem_multi_t *multi, int which);
+int vbhem_multi_estep(vbhem_multi_t *multi, int K, const int32_t *Sr, int maxSr, const int32_t *group, int ngroups,
+                      int tau, const double *logPi, const double *logA, const double *m, const double *vW,
+                      const double *cterm, const double *logOmega, double *L_elbo, double *zhat, double *stats);
+int vbhem_multi_estep_hyp(vbhem_multi_t *multi, int K, const int32_t *Sr, int maxSr, const int32_t *group, int ngroups,
+                          int tau, const double *alpha, const double *eta, const double *epsilon, const double *m,
+                          const double *W, const double *v, const double *lambda, double *L_elbo, double *zhat,
+                          double *stats, double *pre);
+int vbhem_multi_fetch(vbhem_multi_t *multi, double *L_elbo, double *zhat);
+int vbhem_multi_finalize_stats(vbhem_multi_t *multi, int K, const int32_t *Sr, int maxSr, int ngroups, double *stats);
+int vbhem_multi_em_begin(vbhem_multi_t *multi, int K, const int32_t *Sr, int maxSr, const int32_t *group, int ngroups,
+                         double alpha0, double eta0, double epsilon0, double lambda0, double v0, const double *m0,
+                         const double *W0, int nW0, const double *alpha, const double *eta, const double *epsilon,
+                         const double *m, const double *W, const double *v, const double *lambda);
+int vbhem_multi_em_run(vbhem_multi_t *multi, int tau, int max_iter, double min_diff, double *LogLs, int *iters,
+                       int *unstable);
+int vbhem_multi_em_run_groups(vbhem_multi_t *multi, int tau, int max_iter, double min_diff, double *LogLs, int ld,
+                              int *iters, int *unstable);
+int vbhem_multi_em_step(vbhem_multi_t *multi, int tau, double *lb_out);
+int vbhem_multi_em_fetch(vbhem_multi_t *multi, double *alpha, double *eta, double *epsilon, double *m, double *W,
+                         double *v, double *lambda);
+int vbhem_multi_last_ms(vbhem_multi_t *multi, double *ms);
+int vbhem_multi_counters(vbhem_multi_t *multi, long long out[8]);
 
 /* ---- VB-HMM forward-backward (the toolbox's HMM learning) ----
  * Replaces the MEX plug-in of /root/reference/src/hmm/vbhmm_fb.m:99-145,

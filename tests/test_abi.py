@@ -57,6 +57,23 @@ def test_no_cpu_fallback():
     with pytest.raises(_lib.VbhemError) as ei:
         BaseSet(base)
     assert ei.value.code == -2 and "no CUDA device" in ei.value.msg
+    from vbhem_b200.api import MultiBaseSet
+    with pytest.raises(_lib.VbhemError) as ei:
+        MultiBaseSet(base, devices=[0, 1])
+    assert ei.value.code == -2 and "no CUDA device" in ei.value.msg
+
+
+def test_nccl_is_loaded_at_run_time_not_linked():
+    """The multi-GPU entry points resolve NCCL with dlopen: the library itself must not depend on libnccl, so that
+    a single-GPU MATLAB host can load it without NCCL installed."""
+    import subprocess
+    out = subprocess.run(["ldd", _lib.SO_PATH], capture_output=True, text=True).stdout
+    assert "nccl" not in out
+    uid = (C.c_ubyte * 128)()
+    rc = _lib.lib().vbhem_multi_unique_id(uid)
+    assert rc in (0, -2)                                     # -2: no libnccl.so.2 on this box
+    if rc == 0:
+        assert any(bytes(uid))
 
 
 def test_argument_checks_precede_device_use():
