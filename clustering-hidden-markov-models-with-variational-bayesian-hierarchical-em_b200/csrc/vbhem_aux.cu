@@ -11,6 +11,8 @@
 // blocks), so results are bit-identical from run to run.
 #include "vbhem_internal.cuh"
 
+#include <cstdlib>
+
 namespace vbhem {
 
 namespace {
@@ -51,12 +53,19 @@ __device__ double logdet(const double *W, int d) {
   return log(det);
 }
 
-// One block per centre.
+__device__ void build_record(const CentreView &C, int d, int dd, double *rec, int j);
+
+// One block per centre.  With C.rec_stride > 0 the block goes on to build the centre's lattice record
+// (k_build_records) from what it has just written; `counters` (may be null) are the fall-back counters of the
+// E-step this launch opens.
 __global__ void k_prepass(int K, int maxSr, int d, int covmode, const int *Sr, const int *gstart, int ngroups,
                           const double *alpha, const double *eta, const double *epsilon, const double *W,
                           const double *v, const double *lambda, double *logOmega, double *logPi, double *logA,
-                          double *logLam, double *cterm, double *vW) {
+                          double *logLam, double *cterm, double *vW, CentreView C, double *rec, int *counters) {
+  pdl_trigger();
+  pdl_wait();
   const int j = blockIdx.x;
+  if (counters && j == 0 && threadIdx.x < 3) counters[threadIdx.x] = 0;
   const int r = Sr[j];
   const int dd = covmode ? d * d : d;
   // per state: logLambdaTilde, cterm, v*W
@@ -106,11 +115,14 @@ __global__ void k_prepass(int K, int maxSr, int d, int covmode, const int *Sr, c
     for (int jj = gstart[g]; jj < gstart[g + 1]; jj++) sum += alpha[jj];
     logOmega[j] = digamma(alpha[j]) - digamma(sum);
   }
+  if (rec) {
+    __syncthreads();          // the record reads this block's own logA / logPi / cterm / vW
+    build_record(C, d, dd, rec, j);
+  }
 }
 
 // One block per centre: the padded linear-domain record of the lattice kernel.
-__global__ void k_build_records(CentreView C, int d, int dd, double *rec) {
-  const int j = blockIdx.x;
+__device__ void build_record(const CentreView &C, int d, int dd, double *rec, int j) {
   const int r = C.Sr[j], ld = C.maxSr;
   double *o = rec + (size_t)C.rec_stride * j;
   const double *logA = C.logA + (size_t)ld * ld * j;
@@ -142,8 +154,17 @@ __global__ void k_build_records(CentreView C, int d, int dd, double *rec) {
   }
 }
 
+__global__ void k_build_records(CentreView C, int d, int dd, double *rec, int *counters) {
+  pdl_trigger();
+  pdl_wait();
+  if (counters && blockIdx.x == 0 && threadIdx.x < 3) counters[threadIdx.x] = 0;
+  build_record(C, d, dd, rec, blockIdx.x);
+}
+
 // Zero everything beyond each base HMM's own state count (the kernels rely on it).
 __global__ void k_sanitize_base(BaseView B, double *prior, double *A, double *mu, double *cov, int i0, int i1) {
+  pdl_trigger();
+  pdl_wait();
   const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= i1) return;
   const int b = B.Sb[i], ld = B.maxSb;
@@ -159,9 +180,16 @@ __global__ void k_sanitize_base(BaseView B, double *prior, double *A, double *mu
 }
 
 // ---- responsibilities ---------------------------------------------------------
-constexpr int kZThreads = 256;   // bases per block
+// Four lanes share one base (lane = 4 * base-in-warp + q; lane q takes the centres j = ja + q, ja + q + 4, ...), a
+// block holds 64 bases: the per-thread chain of exp / shuffle latencies is a quarter of a thread-per-base layout's,
+// and a 12 500-base shard still makes 196 blocks (148 SMs).  The block is also the granule of the active-pair
+// list (cnt / offs) and of the slices of a streamed E-step.
+constexpr int kLPB = 4;                    // lanes per base
+constexpr int kZBases = 64;                // bases per block
+constexpr int kZThreads = kZBases * kLPB;
 constexpr int kZWarps = kZThreads / 32;
-constexpr int kJT = 32;          // centres per reduction tile
+constexpr int kJT = 32;                    // centres per reduction tile: lane l of a warp ends up with tile entry l
+constexpr double kLogFloor = -115.12925464970229;   // log(1e-50)
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -177,57 +205,74 @@ k_zhat(int N, int K, int ngroups, const int *gstart, const double *L_elbo, const
   __shared__ double red[kZWarps][kJT];
   __shared__ int redc[kZWarps][kJT];
   __shared__ double redl[kZWarps][2];
+  pdl_trigger();
+  pdl_wait();
   const int blk = blk0 + blockIdx.x;
-  const int i = blk * kZThreads + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = lane & (kLPB - 1), bw = lane / kLPB;
+  const int i = blk * kZBases + warp * (32 / kLPB) + bw;
   const bool live = i < N;
   const double Nt = live ? Ntilde[i] : 0.0;
+  const unsigned qmask = 0x11111111u << q;           // the lanes of the warp that hold the same centres
   // soft-max groups are independent: blockIdx.y strides over them (a (K,S) grid has few bases and many groups)
   for (int g = blockIdx.y; g < ngroups; g += gridDim.y) {
     const int ja = gstart[g], jb = gstart[g + 1];
     double mv = -INFINITY, lse = 0.0;
     if (live) {
-      // max shift then sum, in centre order (logtrick.m:15-18)
-      mv = Nt * (logOmega[ja] + L_elbo[i + (size_t)N * ja]);
-      for (int j = ja + 1; j < jb; j++) {
+      // max shift, then the sum (logtrick.m:15-18), each lane over its centres, then over the four lanes
+      for (int j = ja + q; j < jb; j += kLPB) {
         const double lz = Nt * (logOmega[j] + L_elbo[i + (size_t)N * j]);
-        if (lz > mv) mv = lz;
+        if (lz > mv || j < ja + kLPB) mv = lz;         // the first element as it is (a NaN stays)
       }
-      double s = 0.0;
-      for (int j = ja; j < jb; j++) s += exp(Nt * (logOmega[j] + L_elbo[i + (size_t)N * j]) - mv);
-      lse = mv + log(s);
     }
+#pragma unroll
+    for (int o = 1; o < kLPB; o <<= 1) {
+      const double other = __shfl_xor_sync(0xffffffffu, mv, o);
+      if (other > mv) mv = other;                       // a NaN on either side: the base's sum is NaN anyway
+    }
+    double s = 0.0;
+    if (live)
+      for (int j = ja + q; j < jb; j += kLPB) s += exp(Nt * (logOmega[j] + L_elbo[i + (size_t)N * j]) - mv);
+#pragma unroll
+    for (int o = 1; o < kLPB; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (live) lse = mv + log(s);
     double t1 = 0.0, t7 = 0.0;
     for (int j0 = ja; j0 < jb; j0 += kJT) {
       double mine = 0.0;
       int minec = 0;
       const int nt = min(kJT, jb - j0);
-      for (int jj = 0; jj < nt; jj++) {
-        const int j = j0 + jj;
+#pragma unroll
+      for (int c = 0; c < kJT / kLPB; c++) {
+        const int jj = q + kLPB * c, j = j0 + jj;       // uniform over the lanes with the same q
         double Z = 0.0;
         int act = 0;
-        if (live) {
+        if (live && jj < nt) {
           const double Le = L_elbo[i + (size_t)N * j];
-          const double z = exp(Nt * (logOmega[j] + Le) - lse) + 1e-50;
+          const double x = Nt * (logOmega[j] + Le) - lse;
+          const double z = exp(x) + 1e-50;
           zhat[i + (size_t)N * j] = z;
           Z = z * Nt;
           act = Z > kSkipZ;
           t1 += Z * Le;
-          t7 += z * log(z);
+          // log(z) = x up to 1e-50 / z; below z = 1e-30 the term z log z is under 1e-28 and x is as good
+          t7 += z * (x > kLogFloor ? x : kLogFloor);
         }
-        const double ws = warp_sum(Z);
-        const int wc = __popc(__ballot_sync(0xffffffffu, act));
-        if (lane == jj) { mine = ws; minec = wc; }
+        // over the eight bases of the warp that share q (fixed order)
+        Z += __shfl_xor_sync(0xffffffffu, Z, 4);
+        Z += __shfl_xor_sync(0xffffffffu, Z, 8);
+        Z += __shfl_xor_sync(0xffffffffu, Z, 16);
+        const int wc = __popc(__ballot_sync(0xffffffffu, act) & qmask);
+        if (bw == c) { mine = Z; minec = wc; }          // lane 4 c + q keeps tile entry q + 4 c = its own lane index
       }
       red[warp][lane] = mine;
       redc[warp][lane] = minec;
       __syncthreads();
       if (warp == 0 && lane < nt) {
-        double s = 0.0;
-        int c = 0;
-        for (int w = 0; w < kZWarps; w++) { s += red[w][lane]; c += redc[w][lane]; }
-        Nj_part[(size_t)blk * K + j0 + lane] = s;
-        cnt[(size_t)blk * K + j0 + lane] = c;
+        double sN = 0.0;
+        int sc = 0;
+        for (int w = 0; w < kZWarps; w++) { sN += red[w][lane]; sc += redc[w][lane]; }
+        Nj_part[(size_t)blk * K + j0 + lane] = sN;
+        cnt[(size_t)blk * K + j0 + lane] = sc;
       }
       __syncthreads();
     }
@@ -245,32 +290,32 @@ k_zhat(int N, int K, int ngroups, const int *gstart, const double *L_elbo, const
   }
 }
 
-// Sequential (fixed-order) sums over the blocks of k_zhat.
-__global__ void k_zhat_reduce(int nblocks, int K, int ngroups, const double *Nj_part, const double *lb_part,
-                              double *Nj, double *lb) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  if (x < K) {
-    double s = 0.0;
-    for (int b = 0; b < nblocks; b++) s += Nj_part[(size_t)b * K + x];
-    Nj[x] = s;
-  } else if (x < K + 2 * ngroups) {
+// Per centre j (warps 0 .. K-1): offs[blk][j] = exclusive prefix over the blocks of k_zhat of cnt[.][j] (32 blocks
+// per step), segcnt[j] = the centre's total, Nj[j] = sum over blocks of Nj_part[.][j].  Warps K .. K + 2 ngroups - 1:
+// the lower-bound sums lb[y] = sum over blocks of lb_part[.][y].  The fp64 sums run in a fixed order -- lane l adds
+// blocks l, l + 32, ... in turn, then a shuffle tree over the lanes -- so they are bit-identical from run to run.
+__global__ void k_list_scan_blocks(int nblocks, int K, int ngroups, const int *cnt, const double *Nj_part,
+                                   const double *lb_part, int *offs, int *segcnt, double *Nj, double *lb) {
+  pdl_trigger();
+  pdl_wait();
+  const int x = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (x >= K + 2 * ngroups) return;
+  if (x >= K) {
     const int y = x - K;
     double s = 0.0;
-    for (int b = 0; b < nblocks; b++) s += lb_part[(size_t)b * 2 * ngroups + y];
-    lb[y] = s;
+    for (int b = lane; b < nblocks; b += 32) s += lb_part[(size_t)b * 2 * ngroups + y];
+    s = warp_sum(s);
+    if (lane == 0) lb[y] = s;
+    return;
   }
-}
-
-// offs[blk][j]: exclusive prefix over blocks of cnt[.][j] -- one warp per centre, 32 blocks per step;
-// segcnt[j]: the centre's total.
-__global__ void k_list_scan_blocks(int nblocks, int K, const int *cnt, int *offs, int *segcnt) {
-  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (j >= K) return;
+  const int j = x;
   int run = 0;
+  double s = 0.0;
   for (int b0 = 0; b0 < nblocks; b0 += 32) {
     const int b = b0 + lane;
     const int v = b < nblocks ? cnt[(size_t)b * K + j] : 0;
+    if (b < nblocks) s += Nj_part[(size_t)b * K + j];
     int inc = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -280,11 +325,14 @@ __global__ void k_list_scan_blocks(int nblocks, int K, const int *cnt, int *offs
     if (b < nblocks) offs[(size_t)b * K + j] = run + inc - v;
     run += __shfl_sync(0xffffffffu, inc, 31);
   }
-  if (lane == 0) segcnt[j] = run;
+  s = warp_sum(s);
+  if (lane == 0) { segcnt[j] = run; Nj[j] = s; }
 }
 
 // seg_start[j] (K + 1 entries): exclusive prefix over centres; totals = {#active, items per range}.
 __global__ void k_list_scan_centres(int K, int nranges, const int *segcnt, int *seg_start, int *totals) {
+  pdl_trigger();
+  pdl_wait();
   // one warp; lane l owns the contiguous range [l * per, (l + 1) * per) of centres
   const int lane = threadIdx.x, per = (K + 31) / 32;
   const int ja = min(K, lane * per), jb = min(K, ja + per);
@@ -310,11 +358,16 @@ __global__ void k_list_scan_centres(int K, int nranges, const int *segcnt, int *
   }
 }
 
-__global__ void __launch_bounds__(kZThreads)
+// One thread per base, one block per block of k_zhat (kZBases bases): the items of centre j of this block start
+// at seg_start[j] + offs[blk][j], in base order.
+__global__ void __launch_bounds__(kZBases)
 k_list_fill(int N, int K, const double *zhat, const double *Ntilde, const int *offs, const int *seg_start,
             PairItem *items) {
-  __shared__ int wcnt[kZWarps][kJT];
-  const int i = blockIdx.x * kZThreads + threadIdx.x;
+  constexpr int kFW = kZBases / 32;
+  __shared__ int wcnt[kFW][kJT];
+  pdl_trigger();
+  pdl_wait();
+  const int i = blockIdx.x * kZBases + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool live = i < N;
   const double Nt = live ? Ntilde[i] : 0.0;
@@ -348,6 +401,8 @@ k_list_fill(int N, int K, const double *zhat, const double *Ntilde, const int *o
 __global__ void k_partial_reduce(int K, int per, const int *seg_start, const int *totals, const double *partial,
                                  double *S_nu1, double *S_xi, double *S_pr, double *S_mu, double *S_Mu, int r, int d,
                                  int dd) {
+  pdl_trigger();
+  pdl_wait();
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= K * per) return;
   const int j = x / per, q = x % per;
@@ -367,6 +422,8 @@ __global__ void k_partial_reduce(int K, int per, const int *seg_start, const int
 // vbhem_compute_Statistics.m:57-82 in place on a stats buffer; one thread per (state, centre).
 __global__ void k_finalize(int K, int r, int d, int covmode, const int *Sr, double *Nj, double *S_xi, double *S_pr,
                            double *S_mu, double *S_Mu) {
+  pdl_trigger();
+  pdl_wait();
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= K * r) return;
   const int k = x % r, j = x / r;
@@ -454,17 +511,25 @@ int measure_fp64_peak(double out[2]) {
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
+bool pdl_enabled(int cls) {
+  static const int mode = [] {
+    const char *e = getenv("VBHEM_PDL");
+    return e && *e ? atoi(e) : 2;
+  }();
+  return mode == 1 || (mode == 2 && cls == 0) || (mode == 3 && cls == 1);
+}
+
 int launch_prepass(int K, int maxSr, int d, int covmode, const int *Sr, const int *gstart, int ngroups,
                    const double *alpha, const double *eta, const double *epsilon, const double *W, const double *v,
                    const double *lambda, double *logOmega, double *logPi, double *logA, double *logLam, double *cterm,
-                   double *vW, cudaStream_t st) {
-  k_prepass<<<K, 64, 0, st>>>(K, maxSr, d, covmode, Sr, gstart, ngroups, alpha, eta, epsilon, W, v, lambda, logOmega,
-                              logPi, logA, logLam, cterm, vW);
+                   double *vW, const CentreView &C, double *rec, int *counters, cudaStream_t st) {
+  launch_chain(k_prepass, dim3(K), dim3(64), 0, st, K, maxSr, d, covmode, Sr, gstart, ngroups, alpha, eta, epsilon, W, v,
+               lambda, logOmega, logPi, logA, logLam, cterm, vW, C, rec, counters);
   return 1;
 }
 
-int launch_build_records(const CentreView &C, int d, int dd, double *rec, cudaStream_t st) {
-  k_build_records<<<C.K, 64, 0, st>>>(C, d, dd, rec);
+int launch_build_records(const CentreView &C, int d, int dd, double *rec, int *counters, cudaStream_t st) {
+  launch_chain(k_build_records, dim3(C.K), dim3(64), 0, st, C, d, dd, rec, counters);
   return 1;
 }
 
@@ -472,11 +537,11 @@ int launch_sanitize_base(BaseView B, double *prior, double *A, double *mu, doubl
                          int n) {
   if (n < 0) n = B.N - i0;
   if (n <= 0) return 0;
-  k_sanitize_base<<<(n + 127) / 128, 128, 0, st>>>(B, prior, A, mu, cov, i0, i0 + n);
+  launch_chain(k_sanitize_base, dim3((n + 127) / 128), dim3(128), 0, st, B, prior, A, mu, cov, i0, i0 + n);
   return 1;
 }
 
-int zhat_blocks(int N) { return (N + kZThreads - 1) / kZThreads; }
+int zhat_blocks(int N) { return (N + kZBases - 1) / kZBases; }
 
 // gridDim.y for kernels whose blocks over the bases each loop over `parts` independent parts: enough blocks for
 // eight per SM (B200: 148 SMs) when the base set alone gives too few
@@ -487,37 +552,33 @@ static int spread(int nblk, int parts) {
 }
 
 int launch_zhat(int N, int K, int ngroups, const int *gstart, const double *L_elbo, const double *logOmega,
-                const double *Ntilde, double *zhat, double *Nj_part, int *cnt, double *lb_part, double *Nj, double *lb,
-                cudaStream_t st, int blk0, int nblk, bool reduce) {
+                const double *Ntilde, double *zhat, double *Nj_part, int *cnt, double *lb_part, cudaStream_t st, int blk0,
+                int nblk) {
   const int nb = zhat_blocks(N);
   if (nblk < 0) nblk = nb - blk0;
-  int launched = 0;
-  if (nblk > 0) {
-    k_zhat<<<dim3(nblk, spread(nblk, ngroups)), kZThreads, 0, st>>>(N, K, ngroups, gstart, L_elbo, logOmega, Ntilde, zhat,
-                                                                    Nj_part, cnt, lb_part, blk0);
-    launched++;
-  }
-  if (reduce) {
-    const int tot = K + 2 * ngroups;
-    k_zhat_reduce<<<(tot + 127) / 128, 128, 0, st>>>(nb, K, ngroups, Nj_part, lb_part, Nj, lb);
-    launched++;
-  }
-  return launched;
+  if (nblk <= 0) return 0;
+  launch_chain(k_zhat, dim3(nblk, spread(nblk, ngroups)), dim3(kZThreads), 0, st, N, K, ngroups, gstart, L_elbo,
+               logOmega, Ntilde, zhat, Nj_part, cnt, lb_part, blk0);
+  return 1;
 }
 
-int zhat_block_size() { return kZThreads; }
+int zhat_block_size() { return kZBases; }
 
-int launch_list_scan(int N, int K, int nranges, const int *cnt, int *offs, int *segcnt, int *seg_start, int *totals,
+int launch_list_scan(int N, int K, int ngroups, int nranges, const int *cnt, const double *Nj_part,
+                     const double *lb_part, int *offs, int *segcnt, int *seg_start, int *totals, double *Nj, double *lb,
                      cudaStream_t st) {
-  k_list_scan_blocks<<<(K + 3) / 4, 128, 0, st>>>(zhat_blocks(N), K, cnt, offs, segcnt);
-  k_list_scan_centres<<<1, 32, 0, st>>>(K, nranges, segcnt, seg_start, totals);
+  const int warps = K + 2 * ngroups;
+  launch_chain(k_list_scan_blocks, dim3((warps + 3) / 4), dim3(128), 0, st, zhat_blocks(N), K, ngroups, cnt, Nj_part,
+               lb_part, offs, segcnt, Nj, lb);
+  launch_chain(k_list_scan_centres, dim3(1), dim3(32), 0, st, K, nranges, (const int *)segcnt, seg_start, totals);
   return 2;
 }
 
 int launch_list_fill(int N, int K, const double *zhat, const double *Ntilde, const int *offs, const int *seg_start,
                      PairItem *items, cudaStream_t st) {
   const int nb = zhat_blocks(N);
-  k_list_fill<<<dim3(nb, spread(nb, (K + kJT - 1) / kJT)), kZThreads, 0, st>>>(N, K, zhat, Ntilde, offs, seg_start, items);
+  launch_chain(k_list_fill, dim3(nb, spread(nb, (K + kJT - 1) / kJT)), dim3(kZBases), 0, st, N, K, zhat, Ntilde, offs,
+               seg_start, items);
   return 1;
 }
 
@@ -525,15 +586,16 @@ int launch_partial_reduce(int K, int per, const int *seg_start, const int *total
                           double *S_nu1, double *S_xi, double *S_pr, double *S_mu, double *S_Mu, int r, int d, int dd,
                           cudaStream_t st) {
   const int tot = K * per;
-  k_partial_reduce<<<(tot + 127) / 128, 128, 0, st>>>(K, per, seg_start, totals, partial, S_nu1, S_xi, S_pr, S_mu, S_Mu,
-                                                      r, d, dd);
+  launch_chain(k_partial_reduce, dim3((tot + 127) / 128), dim3(128), 0, st, K, per, seg_start, totals, partial, S_nu1,
+               S_xi, S_pr, S_mu, S_Mu, r, d, dd);
   return 1;
 }
 
 int launch_finalize(int K, int maxSr, int d, int covmode, const int *Sr, double *Nj, double *S_xi, double *S_pr,
                     double *S_mu, double *S_Mu, cudaStream_t st) {
   const int tot = K * maxSr;
-  k_finalize<<<(tot + 127) / 128, 128, 0, st>>>(K, maxSr, d, covmode, Sr, Nj, S_xi, S_pr, S_mu, S_Mu);
+  launch_chain(k_finalize, dim3((tot + 127) / 128), dim3(128), 0, st, K, maxSr, d, covmode, Sr, Nj, S_xi, S_pr, S_mu,
+               S_Mu);
   return 1;
 }
 

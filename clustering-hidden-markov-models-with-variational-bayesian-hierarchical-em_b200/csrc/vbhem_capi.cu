@@ -142,14 +142,14 @@ struct vbhem_base {
   BaseView B{};
   DevBuf bSb, bprior, bA, bmu, bcov, bNt;
   // centre set (per call)
-  DevBuf cen_i, cen_d, hyp_d, rec, tile_i, pair_rec;
+  DevBuf up, cen_d, rec, tile_i, pair_rec;   // up: the upload arena of stage_centres
   // results and work lists
   DevBuf L, z, flags, fbcount, Njp, lbp, cnt, offs, segs, items, partial, itemflags, scratch, pairs_out, stats;
   // streamed E-step (base set in host memory): copy-in / copy-out streams and per-slice events
   cudaStream_t cin = nullptr, cout = nullptr;
   std::vector<cudaEvent_t> slice_ev;
-  // device-resident EM run (vbhem_em_*): the hyper-parameters live in hyp_d (layout of stage_centres)
-  // and em_m; em_prior = m0[d] | W0inv[d]; em_lb = [12 * ngroups] lower-bound terms
+  // device-resident EM run (vbhem_em_*): the hyper-parameters live in em.hyp (alpha | eta | epsilon | W | v | lambda)
+  // and em.m; em.prior = m0[d] | W0inv[d]; em.lb = [12 * ngroups] lower-bound terms
   struct Em {
     bool active = false;
     int K = 0, maxSr = 0, ngroups = 1;
@@ -157,7 +157,7 @@ struct vbhem_base {
     double alpha0 = 0, eta0 = 0, epsilon0 = 0, lambda0 = 0, v0 = 0;
     // The run's own copies of everything it keeps between calls -- hyper-parameters (layout of stage_centres'
     // hyp block), means, state counts | group starts -- so that ordinary E-steps on the same handle (which
-    // overwrite cen_i / hyp_d) cannot corrupt it.  `staged`: cen_d holds the pre-pass of THIS run's last E-step
+    // overwrite the upload arena) cannot corrupt it.  `staged`: cen_d holds the pre-pass of THIS run's last E-step
     // (what vbhem_em_lower_bound reads); any other E-step on the handle clears it.
     DevBuf hyp, ints, m, prior, lb, stats, frozen;
     bool staged = false;
@@ -238,28 +238,95 @@ struct CentreDev {
   CentreView C{};
   int *gstart = nullptr;
   double *logLam = nullptr;
+  const double *pre_dev = nullptr;   // pre-pass results for the caller's `pre` (hyper-parameter calls)
+  size_t pre_doubles = 0;
 };
 
-// Upload the centre set (running the pre-pass on the device if it is given as
-// hyper-parameters) and build the lattice records.  `launches` is incremented.
-int stage_centres(vbhem_base *h, const CentreArgs &a, CentreDev &cd, double *pre_host, long long &launches) {
+// First-pass tiling (host): a centre of 5..7 states takes, largest first, the largest centre that still fits beside
+// it (split tile, class = the smaller one's column count 1..3); the remaining centres of <= 4 states pair up two
+// by two (halves, class 0; pairing needs >= 2 of them); everything else has a tile of its own.
+// lists = big | class 0 pairs | class 1 | class 2 | class 3 (two entries per paired tile, -1 = no partner).
+void tile_lists(const vbhem_base *h, const int32_t *Sr, int K, std::vector<int> &lists, int &nbig, int (&npairs)[kTileClasses]) {
+  std::vector<int> big, small[5], cls[kTileClasses];
+  for (int j = 0; j < K; j++) {
+    if (Sr[j] <= 4 && h->pair_centres) small[Sr[j]].push_back(j);
+    else big.push_back(j);
+  }
+  if (h->pair_centres && h->split_tiles) {
+    std::vector<int> order(big);
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return Sr[x] > Sr[y]; });
+    std::vector<int> alone;
+    for (int j : order) {
+      int sl = 8 - Sr[j];
+      if (sl > 3) sl = 3;
+      while (sl >= 1 && small[sl].empty()) sl--;
+      if (sl >= 1) {
+        cls[sl].push_back(small[sl].back());
+        cls[sl].push_back(j);
+        small[sl].pop_back();
+      } else {
+        alone.push_back(j);
+      }
+    }
+    big.swap(alone);
+    std::sort(big.begin(), big.end());
+  }
+  for (int sl = 4; sl >= 1; sl--) cls[0].insert(cls[0].end(), small[sl].begin(), small[sl].end());
+  if (cls[0].size() < 2) { big.insert(big.end(), cls[0].begin(), cls[0].end()); cls[0].clear(); std::sort(big.begin(), big.end()); }
+  if (cls[0].size() % 2) cls[0].push_back(-1);
+  lists = big;
+  nbig = (int)big.size();
+  for (int c = 0; c < kTileClasses; c++) {
+    lists.insert(lists.end(), cls[c].begin(), cls[c].end());
+    npairs[c] = (int)cls[c].size() / 2;
+  }
+}
+
+// Upload the centre set (running the pre-pass on the device if it is given as hyper-parameters) and build the
+// lattice records.  Everything the call uploads -- state counts, group starts, tile lists, means, hyper-parameters
+// or pre-pass results -- is staged in ONE pinned block and travels as ONE host-to-device copy into the handle's
+// upload arena (h->up); a device-resident EM run uploads nothing.  `launches` is incremented.
+int stage_centres(vbhem_base *h, const CentreArgs &a, CentreDev &cd, long long &launches) {
   const int K = a.K, r = a.maxSr, d = h->B.d, dd = h->B.dd;
   const size_t nK = K, nr = (size_t)r * K, nrr = (size_t)r * r * K;
-  // pinned staging: ints [Sr K | gstart ng+1 | tile lists <= 2K+2] then doubles (what this call uploads)
-  const size_t n_int = (size_t)K + a.ngroups + 1 + 2 * (size_t)K + 4;
-  const size_t int_bytes = (n_int * sizeof(int) + 15) / 16 * 16;
-  const size_t n_dbl = d * nr + (a.hyp ? nK + nr + nrr + dd * nr + nr + nr : nK + nr + nrr + nr + dd * nr);
-  void *stage_p = nullptr;
-  CU(h->stage.acquire(int_bytes + sizeof(double) * n_dbl, &stage_p));
-  int *s_int = static_cast<int *>(stage_p);
-  double *s_dbl = reinterpret_cast<double *>(static_cast<char *>(stage_p) + int_bytes);
-  int *dSr, *dgs;
-  if (a.hyp && a.resident) {          // device-resident EM run: state counts and group starts are already there
+  const bool resident = a.hyp && a.resident;
+  const bool lattice = h->kernel_choice == 0 && h->B.maxSb <= kS8 && r <= kS8 && d <= 3;
+  CU(h->fbcount.ensure(4 * sizeof(int)));
+  std::vector<int> lists;
+  int nbig = 0, npairs[kTileClasses] = {0, 0, 0, 0};
+  if (lattice) tile_lists(h, a.Sr, K, lists, nbig, npairs);
+
+  int *dSr = nullptr, *dlists = nullptr;
+  double *dm = nullptr, *dblk = nullptr;     // dblk: hyper-parameter block or log-domain block of the arena
+  const size_t th = nK + nr + nrr + dd * nr + nr + nr;        // alpha | eta | epsilon | W | v | lambda
+  const size_t tl = nK + nr + nrr + nr + dd * nr;             // logOmega | logPi | logA | cterm | vW
+  if (resident) {
+    // state counts, group starts, means and hyper-parameters are in the run's own buffers; the tile lists change
+    // only with the centre set
     dSr = h->em.ints.as<int>();
+    dm = h->em.m.as<double>();
+    dblk = h->em.hyp.as<double>();
+    if (lattice && !(h->tile_i.p && lists == h->last_lists)) {
+      void *sp = nullptr;
+      CU(h->stage.acquire(sizeof(int) * (lists.size() + 1), &sp));
+      memcpy(sp, lists.data(), sizeof(int) * lists.size());
+      CU(h->tile_i.ensure(sizeof(int) * (lists.size() + 1)));
+      CU(cudaMemcpyAsync(h->tile_i.p, sp, sizeof(int) * lists.size(), cudaMemcpyHostToDevice, h->st));
+      CU(h->stage.commit(h->st));
+      h->last_lists = lists;
+    }
+    dlists = h->tile_i.as<int>();
   } else {
     h->em.staged = false;             // cen_d is about to hold another centre set's pre-pass
-    CU(h->cen_i.ensure(sizeof(int) * (size_t)(K + a.ngroups + 1)));
-    dSr = h->cen_i.as<int>();
+    const size_t n_int = (size_t)K + a.ngroups + 1 + lists.size();
+    const size_t int_bytes = (n_int * sizeof(int) + 15) / 16 * 16;
+    const size_t n_dbl = d * nr + (a.hyp ? th : tl);
+    const size_t bytes = int_bytes + sizeof(double) * n_dbl;
+    void *sp = nullptr;
+    CU(h->stage.acquire(bytes, &sp));
+    CU(h->up.ensure(bytes));
+    int *s_int = static_cast<int *>(sp);
+    double *s_dbl = reinterpret_cast<double *>(static_cast<char *>(sp) + int_bytes);
     memcpy(s_int, a.Sr, sizeof(int) * K);
     int *gs = s_int + K;
     for (int g = 0; g <= a.ngroups; g++) gs[g] = 0;
@@ -268,131 +335,93 @@ int stage_centres(vbhem_base *h, const CentreArgs &a, CentreDev &cd, double *pre
     } else {
       gs[1] = K;
     }
-    CU(cudaMemcpyAsync(dSr, s_int, sizeof(int) * (size_t)(K + a.ngroups + 1), cudaMemcpyHostToDevice, h->st));
-  }
-  dgs = dSr + K;
-  // log-domain block: logOmega[K] | logPi[rK] | logA[rrK] | logLam[rK] | cterm[rK] | m[d r K] | vW[dd r K]
-  const size_t tot = nK + nr + nrr + nr + nr + d * nr + dd * nr;
-  CU(h->cen_d.ensure(sizeof(double) * tot));
-  double *p = h->cen_d.as<double>();
-  double *dOm = p; p += nK;
-  double *dPi = p; p += nr;
-  double *dA = p; p += nrr;
-  double *dLam = p; p += nr;
-  double *dCt = p; p += nr;
-  double *dm = p; p += d * nr;
-  double *dvW = p;
-  double *sm = s_dbl;            // staged means
-  double *srest = s_dbl + d * nr;
-  if (a.hyp && a.resident) {
-    dm = h->em.m.as<double>();        // read in place
-  } else {
-    memcpy(sm, a.m, sizeof(double) * d * nr);
-    CU(cudaMemcpyAsync(dm, sm, sizeof(double) * d * nr, cudaMemcpyHostToDevice, h->st));
-  }
-  if (a.hyp) {
-    const size_t th = nK + nr + nrr + dd * nr + nr + nr;
-    if (!a.resident) CU(h->hyp_d.ensure(sizeof(double) * th));
-    double *q = (a.resident ? h->em.hyp : h->hyp_d).as<double>();
-    double *hal = q; q += nK;
-    double *het = q; q += nr;
-    double *hep = q; q += nrr;
-    double *hW = q; q += dd * nr;
-    double *hv = q; q += nr;
-    double *hl = q;
-    if (!a.resident) {   // alpha | eta | epsilon | W | v | lambda are contiguous on the device: one upload
-      double *w = srest;
+    if (!lists.empty()) memcpy(gs + a.ngroups + 1, lists.data(), sizeof(int) * lists.size());
+    double *w = s_dbl;
+    memcpy(w, a.m, sizeof(double) * d * nr); w += d * nr;
+    if (a.hyp) {
       memcpy(w, a.alpha, sizeof(double) * nK); w += nK;
       memcpy(w, a.eta, sizeof(double) * nr); w += nr;
       memcpy(w, a.epsilon, sizeof(double) * nrr); w += nrr;
       memcpy(w, a.W, sizeof(double) * dd * nr); w += dd * nr;
       memcpy(w, a.v, sizeof(double) * nr); w += nr;
       memcpy(w, a.lambda, sizeof(double) * nr);
-      CU(cudaMemcpyAsync(hal, srest, sizeof(double) * th, cudaMemcpyHostToDevice, h->st));
+    } else {
+      if (a.logOmega) memcpy(w, a.logOmega, sizeof(double) * nK); else memset(w, 0, sizeof(double) * nK);
+      w += nK;
+      memcpy(w, a.logPi, sizeof(double) * nr); w += nr;
+      memcpy(w, a.logA, sizeof(double) * nrr); w += nrr;
+      memcpy(w, a.cterm, sizeof(double) * nr); w += nr;
+      memcpy(w, a.vW, sizeof(double) * dd * nr);
     }
-    launches += launch_prepass(K, r, d, h->B.covmode, dSr, dgs, a.ngroups, hal, het, hep, hW, hv, hl, dOm, dPi, dA,
-                               dLam, dCt, dvW, h->st);
-    if (pre_host)   // logOmega | logPi | logA | logLambdaTilde are contiguous by construction
-      CU(cudaMemcpyAsync(pre_host, dOm, sizeof(double) * (nK + nr + nrr + nr), cudaMemcpyDeviceToHost, h->st));
-  } else {
-    // logOmega | logPi | logA are contiguous on the device; cterm and vW follow separately
-    double *w = srest;
-    if (a.logOmega) memcpy(w, a.logOmega, sizeof(double) * nK); else memset(w, 0, sizeof(double) * nK);
-    memcpy(w + nK, a.logPi, sizeof(double) * nr);
-    memcpy(w + nK + nr, a.logA, sizeof(double) * nrr);
-    CU(cudaMemcpyAsync(dOm, w, sizeof(double) * (nK + nr + nrr), cudaMemcpyHostToDevice, h->st));
-    double *w2 = w + nK + nr + nrr;
-    memcpy(w2, a.cterm, sizeof(double) * nr);
-    CU(cudaMemcpyAsync(dCt, w2, sizeof(double) * nr, cudaMemcpyHostToDevice, h->st));
-    memcpy(w2 + nr, a.vW, sizeof(double) * dd * nr);
-    CU(cudaMemcpyAsync(dvW, w2 + nr, sizeof(double) * dd * nr, cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemcpyAsync(h->up.p, sp, bytes, cudaMemcpyHostToDevice, h->st));
+    CU(h->stage.commit(h->st));       // the slot is free again once the copy has run
+    h->last_lists.clear();            // tile_i is not what the next resident call expects
+    dSr = h->up.as<int>();
+    dlists = dSr + K + a.ngroups + 1;
+    dm = reinterpret_cast<double *>(h->up.as<char>() + int_bytes);
+    dblk = dm + d * nr;
   }
-  cd.C.K = K; cd.C.maxSr = r; cd.C.Sr = dSr; cd.C.group = nullptr;
-  cd.C.logPi = dPi; cd.C.logA = dA; cd.C.m = dm; cd.C.vW = dvW; cd.C.cterm = dCt; cd.C.logOmega = dOm;
-  cd.gstart = dgs; cd.logLam = dLam;
-  cd.C.rec = nullptr; cd.C.rec_stride = 0;
-  if (h->kernel_choice == 0 && h->B.maxSb <= kS8 && r <= kS8 && d <= 3) {
+  int *dgs = dSr + K;
+
+  cd.C = CentreView{};
+  cd.C.K = K; cd.C.maxSr = r; cd.C.Sr = dSr; cd.C.group = nullptr; cd.C.m = dm;
+  cd.gstart = dgs;
+  cd.logLam = nullptr;
+  if (lattice) {
     cd.C.rec_stride = lattice_rec_stride(d, dd);
     CU(h->rec.ensure(sizeof(double) * (size_t)cd.C.rec_stride * K));
     cd.C.rec = h->rec.as<double>();
-    launches += launch_build_records(cd.C, d, dd, h->rec.as<double>(), h->st);
-    // First-pass tiling.  A centre of 5..7 states takes, largest first, the largest centre that still fits beside
-    // it (split tile, class = the smaller one's column count 1..3); the remaining centres of <= 4 states pair up
-    // two by two (halves, class 0; pairing needs >= 2 of them); everything else has a tile of its own.
-    std::vector<int> big, small[5], cls[kTileClasses];
-    for (int j = 0; j < K; j++) {
-      if (a.Sr[j] <= 4 && h->pair_centres) small[a.Sr[j]].push_back(j);
-      else big.push_back(j);
-    }
-    if (h->pair_centres && h->split_tiles) {
-      std::vector<int> order(big);
-      std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return a.Sr[x] > a.Sr[y]; });
-      std::vector<int> alone;
-      for (int j : order) {
-        int s = 8 - a.Sr[j];
-        if (s > 3) s = 3;
-        while (s >= 1 && small[s].empty()) s--;
-        if (s >= 1) {
-          cls[s].push_back(small[s].back());
-          cls[s].push_back(j);
-          small[s].pop_back();
-        } else {
-          alone.push_back(j);
-        }
-      }
-      big.swap(alone);
-      std::sort(big.begin(), big.end());
-    }
-    for (int s = 4; s >= 1; s--) cls[0].insert(cls[0].end(), small[s].begin(), small[s].end());
-    if (cls[0].size() < 2) { big.insert(big.end(), cls[0].begin(), cls[0].end()); cls[0].clear(); std::sort(big.begin(), big.end()); }
-    if (cls[0].size() % 2) cls[0].push_back(-1);
-    std::vector<int> lists(big);
+  }
+  int *counters = h->fbcount.as<int>();
+  if (a.hyp) {
+    // pre-pass results: logOmega[K] | logPi[rK] | logA[rrK] | logLam[rK] | cterm[rK] | vW[dd r K] in cen_d
+    CU(h->cen_d.ensure(sizeof(double) * (nK + nr + nrr + nr + nr + dd * nr)));
+    double *p = h->cen_d.as<double>();
+    double *dOm = p; p += nK;
+    double *dPi = p; p += nr;
+    double *dA = p; p += nrr;
+    double *dLam = p; p += nr;
+    double *dCt = p; p += nr;
+    double *dvW = p;
+    double *q = dblk;
+    double *hal = q; q += nK;
+    double *het = q; q += nr;
+    double *hep = q; q += nrr;
+    double *hW = q; q += dd * nr;
+    double *hv = q; q += nr;
+    double *hl = q;
+    cd.C.logPi = dPi; cd.C.logA = dA; cd.C.vW = dvW; cd.C.cterm = dCt; cd.C.logOmega = dOm;
+    cd.logLam = dLam;
+    // one launch: pre-pass, the centres' lattice records, and the E-step's fall-back counters cleared
+    launches += launch_prepass(K, r, d, h->B.covmode, dSr, dgs, a.ngroups, hal, het, hep, hW, hv, hl, dOm, dPi, dA,
+                               dLam, dCt, dvW, cd.C, lattice ? h->rec.as<double>() : nullptr, counters, h->st);
+    cd.pre_dev = dOm;         // logOmega | logPi | logA | logLambdaTilde are contiguous by construction
+    cd.pre_doubles = nK + nr + nrr + nr;
+  } else {
+    double *q = dblk;
+    cd.C.logOmega = q; q += nK;
+    cd.C.logPi = q; q += nr;
+    cd.C.logA = q; q += nrr;
+    cd.C.cterm = q; q += nr;
+    cd.C.vW = q;
+    if (lattice) launches += launch_build_records(cd.C, d, dd, h->rec.as<double>(), counters, h->st);
+    else CU(cudaMemsetAsync(counters, 0, 4 * sizeof(int), h->st));
+  }
+  if (lattice) {
     int ntile_pairs = 0;
-    for (int c = 0; c < kTileClasses; c++) {
-      lists.insert(lists.end(), cls[c].begin(), cls[c].end());
-      cd.C.npairs[c] = (int)cls[c].size() / 2;
-      ntile_pairs += cd.C.npairs[c];
-    }
-    if (!(h->tile_i.p && lists == h->last_lists)) {        // an EM run stages the same lists every iteration
-      CU(h->tile_i.ensure(sizeof(int) * (lists.size() + 1)));
-      int *s_lists = s_int + K + a.ngroups + 1;            // same pinned slot: outlives this scope
-      memcpy(s_lists, lists.data(), sizeof(int) * lists.size());
-      CU(cudaMemcpyAsync(h->tile_i.p, s_lists, sizeof(int) * lists.size(), cudaMemcpyHostToDevice, h->st));
-      h->last_lists = lists;
-    }
-    cd.C.big_list = h->tile_i.as<int>();
-    cd.C.nbig = (int)big.size();
-    cd.C.pair_list = cd.C.big_list + big.size();
+    for (int c = 0; c < kTileClasses; c++) { cd.C.npairs[c] = npairs[c]; ntile_pairs += npairs[c]; }
+    cd.C.big_list = dlists;
+    cd.C.nbig = nbig;
+    cd.C.pair_list = dlists + nbig;
     cd.C.pair_rec = nullptr;
-    h->counters[4] = cd.C.nbig + ntile_pairs;
-    h->counters[5] = ntile_pairs - cd.C.npairs[0];
+    h->counters[4] = nbig + ntile_pairs;
+    h->counters[5] = ntile_pairs - npairs[0];
     if (ntile_pairs > 0) {
       CU(h->pair_rec.ensure(sizeof(double) * (size_t)cd.C.rec_stride * ntile_pairs));
       cd.C.pair_rec = h->pair_rec.as<double>();
       launches += launch_pair_records(cd.C, d, dd, h->pair_rec.as<double>(), h->st);
     }
   }
-  CU(h->stage.commit(h->st));   // the slot is free again once everything enqueued so far has run
   return VBHEM_OK;
 }
 
@@ -421,7 +450,16 @@ StatsPtr carve_stats(double *s, int K, int r, int d, int dd, int ng) {
   return p;
 }
 
-// L_elbo for every pair into h->L (first pass).
+// The per-pair fall-back flags: all-zero between E-steps (the general kernel clears what it serves), so they are
+// cleared only when the buffer is (re)allocated.
+int ensure_flags(vbhem_base *h, long long np) {
+  const void *before = h->flags.p;
+  CU(h->flags.ensure((size_t)np));
+  if (h->flags.p != before) CU(cudaMemsetAsync(h->flags.p, 0, h->flags.cap, h->st));
+  return VBHEM_OK;
+}
+
+// L_elbo for every pair into h->L (first pass).  The fall-back counters were cleared by stage_centres.
 int first_pass(vbhem_base *h, const CentreDev &cd, int T, long long &launches) {
   const long long np = (long long)h->B.N * cd.C.K;
   CU(h->L.ensure(sizeof(double) * np));
@@ -430,10 +468,8 @@ int first_pass(vbhem_base *h, const CentreDev &cd, int T, long long &launches) {
   O.mode = 0;
   O.L_elbo = h->L.as<double>();
   if (cd.C.rec && lattice_supported(h->B, cd.C, T, false)) {
-    CU(h->flags.ensure(np));
-    CU(h->fbcount.ensure(2 * sizeof(int)));
-    CU(cudaMemsetAsync(h->flags.p, 0, np, h->st));
-    CU(cudaMemsetAsync(h->fbcount.p, 0, 2 * sizeof(int), h->st));
+    int rf = ensure_flags(h, np);
+    if (rf) return rf;
     Fallback fb{h->flags.as<unsigned char>(), h->fbcount.as<int>()};
     launches += launch_lattice_bwd(h->B, cd.C, T, O.L_elbo, fb, h->st);
     size_t sd;
@@ -485,13 +521,11 @@ int streamed_front(vbhem_base *h, const CentreDev &cd, const CentreArgs &a, cons
     CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     h->slice_ev.push_back(e);
   }
-  CU(h->flags.ensure(np));
-  CU(h->fbcount.ensure(2 * sizeof(int)));
-  CU(cudaMemsetAsync(h->flags.p, 0, np, h->st));
-  CU(cudaMemsetAsync(h->fbcount.p, 0, 2 * sizeof(int), h->st));
+  int rc = ensure_flags(h, np);
+  if (rc) return rc;
   Fallback fb{h->flags.as<unsigned char>(), h->fbcount.as<int>()};
   size_t sd;
-  int rc = ensure_scratch(h, cd.C.maxSr, T, 296, sd);
+  rc = ensure_scratch(h, cd.C.maxSr, T, 296, sd);
   if (rc) return rc;
   // earlier work on the handle's stream may still read the base buffers
   CU(cudaEventRecord(h->slice_ev[2 * ns], h->st));
@@ -518,12 +552,14 @@ int streamed_front(vbhem_base *h, const CentreDev &cd, const CentreArgs &a, cons
     launches += launch_sanitize_base(h->B, h->bprior.as<double>(), h->bA.as<double>(), h->bmu.as<double>(),
                                      h->bcov.as<double>(), h->st, i0, n);
     launches += launch_lattice_bwd(h->B, cd.C, T, O.L_elbo, fb, h->st, i0, n);
-    const int ng = launch_general(h->B, cd.C, T, W, O, fb.flags, fb.count, h->scratch.as<double>(), sd, h->st);
+    // fall-backs of this slice only (every slice used to rescan all N*K flags)
+    const int ng = launch_general(h->B, cd.C, T, W, O, fb.flags, fb.count, h->scratch.as<double>(), sd, h->st, i0,
+                                  i0 + n);
     if (ng < 0) return fail(VBHEM_ENOMEM, "general kernel scratch too small");
     launches += ng;
     launches += launch_zhat(N, K, a.ngroups, cd.gstart, h->L.as<double>(), cd.C.logOmega, h->B.Ntilde,
-                            h->z.as<double>(), h->Njp.as<double>(), h->cnt.as<int>(), h->lbp.as<double>(), S.Nj, S.lb,
-                            h->st, i0 / zb, (n + zb - 1) / zb, c == ns - 1);
+                            h->z.as<double>(), h->Njp.as<double>(), h->cnt.as<int>(), h->lbp.as<double>(), h->st,
+                            i0 / zb, (n + zb - 1) / zb);
     CU(cudaEventRecord(h->slice_ev[2 * c + 1], h->st));
     CU(cudaStreamWaitEvent(h->cout, h->slice_ev[2 * c + 1], 0));
     const size_t pitch = sizeof(double) * (size_t)N;
@@ -549,7 +585,7 @@ int estep_device(vbhem_base *h, const CentreArgs &a, double *stats_dev, double *
   auto mark = [&](int k) { if (h->profile) cudaEventRecord(h->ev[k], h->st); };
   mark(0);
   CentreDev cd;
-  int rc = stage_centres(h, a, cd, pre_host, launches);
+  int rc = stage_centres(h, a, cd, launches);
   if (rc) return rc;
   mark(1);
   const long long np = (long long)N * K;
@@ -561,9 +597,6 @@ int estep_device(vbhem_base *h, const CentreArgs &a, double *stats_dev, double *
   CU(h->cnt.ensure(sizeof(int) * (size_t)nb * K));
   CU(h->offs.ensure(sizeof(int) * (size_t)nb * K));
   CU(h->segs.ensure(sizeof(int) * (size_t)(2 * (K + 1) + 4)));
-  CU(h->fbcount.ensure(2 * sizeof(int)));
-  if (!(cd.C.rec && lattice_supported(h->B, cd.C, T, false)))       // else the first pass clears both counters
-    CU(cudaMemsetAsync(h->fbcount.p, 0, 2 * sizeof(int), h->st));
   StatsPtr S = carve_stats(stats_dev, K, r, d, dd, a.ngroups);
   if (io && cd.C.rec && lattice_supported(h->B, cd.C, T, false)) {
     rc = streamed_front(h, cd, a, *io, S, launches);
@@ -579,8 +612,7 @@ int estep_device(vbhem_base *h, const CentreArgs &a, double *stats_dev, double *
     mark(2);
     // responsibilities + deterministic active list
     launches += launch_zhat(N, K, a.ngroups, cd.gstart, h->L.as<double>(), cd.C.logOmega, h->B.Ntilde,
-                            h->z.as<double>(), h->Njp.as<double>(), h->cnt.as<int>(), h->lbp.as<double>(), S.Nj, S.lb,
-                            h->st);
+                            h->z.as<double>(), h->Njp.as<double>(), h->cnt.as<int>(), h->lbp.as<double>(), h->st);
     if (io) {
       if (io->L_host) CU(cudaMemcpyAsync(io->L_host, h->L.p, sizeof(double) * np, cudaMemcpyDeviceToHost, h->st));
       if (io->z_host) CU(cudaMemcpyAsync(io->z_host, h->z.p, sizeof(double) * np, cudaMemcpyDeviceToHost, h->st));
@@ -595,7 +627,8 @@ int estep_device(vbhem_base *h, const CentreArgs &a, double *stats_dev, double *
   if (np >= ((long long)1 << 31)) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: N * K must be below 2^31");
   CU(h->items.ensure(sizeof(PairItem) * (size_t)np));
   CU(h->partial.ensure(sizeof(double) * (size_t)per * ((size_t)nranges + K)));
-  launches += launch_list_scan(N, K, nranges, h->cnt.as<int>(), h->offs.as<int>(), segcnt, seg_start, totals, h->st);
+  launches += launch_list_scan(N, K, a.ngroups, nranges, h->cnt.as<int>(), h->Njp.as<double>(), h->lbp.as<double>(),
+                               h->offs.as<int>(), segcnt, seg_start, totals, S.Nj, S.lb, h->st);
   launches += launch_list_fill(N, K, h->z.as<double>(), h->B.Ntilde, h->offs.as<int>(), seg_start,
                                h->items.as<PairItem>(), h->st);
   mark(3);
@@ -633,6 +666,9 @@ int estep_device(vbhem_base *h, const CentreArgs &a, double *stats_dev, double *
   launches += launch_partial_reduce(K, per, seg_start, totals, h->partial.as<double>(), S.nu1, S.xi, S.pr, S.mu, S.Mu, r,
                                     d, dd, h->st);
   mark(5);
+  // the pre-pass results for the caller leave last: a copy in the middle of the chain would sit on the critical path
+  if (pre_host && cd.pre_dev)
+    CU(cudaMemcpyAsync(pre_host, cd.pre_dev, sizeof(double) * cd.pre_doubles, cudaMemcpyDeviceToHost, h->st));
   CU(cudaGetLastError());
   h->counters[0] = launches;
   h->lastK = K;
@@ -646,11 +682,11 @@ int settle_counters(vbhem_base *h) {
   if (!h->totals_pending) return VBHEM_OK;
   CU(cudaSetDevice(h->device));
   CU(cudaMemcpyAsync(h->h_totals, h->d_totals, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
-  CU(cudaMemcpyAsync(h->h_totals + 2, h->fbcount.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  CU(cudaMemcpyAsync(h->h_totals + 2, h->fbcount.as<int>() + 1, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
   CU(cudaStreamSynchronize(h->st));
   const long long nact = h->h_totals[0];
   h->counters[3] = nact;
-  h->counters[2] += h->h_totals[2] + h->h_totals[3];
+  h->counters[2] += h->h_totals[2] + h->h_totals[3];     // fall-backs of the second and of the first pass
   if (h->lattice_second) h->counters[1] += nact; else h->counters[2] += nact;
   h->totals_pending = false;
   return VBHEM_OK;
@@ -799,7 +835,7 @@ int vbhem_free_base(vbhem_base_t *h) {
   h->em.m.release(); h->em.prior.release(); h->em.lb.release(); h->em.stats.release(); h->em.frozen.release();
   h->em.hyp.release(); h->em.ints.release(); h->fin_i.release();
   if (h->em.h_lb) cudaFreeHost(h->em.h_lb);
-  DevBuf *all[] = {&h->bSb, &h->bprior, &h->bA, &h->bmu, &h->bcov, &h->bNt, &h->cen_i, &h->cen_d, &h->hyp_d, &h->rec,
+  DevBuf *all[] = {&h->bSb, &h->bprior, &h->bA, &h->bmu, &h->bcov, &h->bNt, &h->up, &h->cen_d, &h->rec,
                    &h->L, &h->z, &h->flags, &h->fbcount, &h->Njp, &h->lbp, &h->cnt, &h->offs, &h->segs, &h->items,
                    &h->partial, &h->itemflags, &h->scratch, &h->pairs_out, &h->stats, &h->tile_i, &h->pair_rec};
   for (DevBuf *b : all) b->release();
@@ -870,7 +906,7 @@ int vbhem_estep_pairs(vbhem_base_t *h, int K, const int32_t *Sr, int maxSr, int 
   memset(h->counters, 0, sizeof h->counters);
   h->totals_pending = false;
   CentreDev cd;
-  rc = stage_centres(h, a, cd, nullptr, launches);
+  rc = stage_centres(h, a, cd, launches);
   if (rc) return rc;
   const int N = h->B.N, d = h->B.d, dd = h->B.dd, r = maxSr;
   const size_t np = (size_t)N * K;
@@ -897,11 +933,9 @@ int vbhem_estep_pairs(vbhem_base_t *h, int K, const int32_t *Sr, int maxSr, int 
   O.Mu = po;
   PairWork W{nullptr, nullptr, nullptr, nullptr, 0, (long long)np};
   if (cd.C.rec && lattice_supported(h->B, cd.C, tau, true)) {
-    CU(h->flags.ensure(np));
-    CU(h->fbcount.ensure(2 * sizeof(int)));
-    CU(cudaMemsetAsync(h->flags.p, 0, np, h->st));
-    CU(cudaMemsetAsync(h->fbcount.p, 0, 2 * sizeof(int), h->st));
-    Fallback fb{h->flags.as<unsigned char>(), h->fbcount.as<int>()};
+    rc = ensure_flags(h, (long long)np);
+    if (rc) return rc;
+    Fallback fb{h->flags.as<unsigned char>(), h->fbcount.as<int>()};   // counters cleared by stage_centres
     const int n1 = launch_lattice_full(h->B, cd.C, tau, W, O, fb, h->st);
     if (n1 < 0) return fail(VBHEM_ECUDA, "lattice kernel launch configuration failed");
     launches += n1;
@@ -930,9 +964,9 @@ int vbhem_estep_pairs(vbhem_base_t *h, int K, const int32_t *Sr, int maxSr, int 
   CU(cudaMemcpyAsync(Mu_out, O.Mu, sizeof(double) * np * r * dd, cudaMemcpyDeviceToHost, h->st));
   CU(cudaStreamSynchronize(h->st));
   if (h->fbcount.p) {
-    int fbc[2] = {0, 0};
+    int fbc[3] = {0, 0, 0};                       // {pending, second pass, served}: see k_general
     CU(cudaMemcpy(fbc, h->fbcount.p, sizeof fbc, cudaMemcpyDeviceToHost));
-    h->counters[2] += fbc[0];
+    h->counters[2] += fbc[2];
   }
   h->counters[0] = launches;
   return VBHEM_OK;

@@ -91,6 +91,8 @@ __global__ void __launch_bounds__(kLbThreads)
 k_lower_bound(EmView E, const double *Nj, const double *lbsum, const double *logOmega, const double *logPi,
               const double *logA, const double *logLam, double *out) {
   __shared__ double sh[kLbThreads][kTerms];
+  pdl_trigger();
+  pdl_wait();
   const int g = blockIdx.x;
   const int ja = E.gstart[g], jb = E.gstart[g + 1], Kg = jb - ja;
   const int r = E.maxSr, d = E.d, dd = E.covmode ? d * d : d;
@@ -182,6 +184,8 @@ k_lower_bound(EmView E, const double *Nj, const double *lbsum, const double *log
 __global__ void k_mstep(EmView E, const double *Nj, const double *nu1, const double *xi, const double *pr,
                         const double *ybar, const double *SC, double *alpha, double *eta, double *epsilon, double *m,
                         double *W, double *v, double *lambda) {
+  pdl_trigger();
+  pdl_wait();
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int r = E.maxSr, d = E.d, dd = E.covmode ? d * d : d;
   if (x >= E.K * r) return;
@@ -229,7 +233,7 @@ __global__ void k_mstep(EmView E, const double *Nj, const double *nu1, const dou
 
 int launch_lower_bound(const EmView &E, const double *Nj, const double *lbsum, const double *logOmega,
                        const double *logPi, const double *logA, const double *logLam, double *out, cudaStream_t st) {
-  k_lower_bound<<<E.ngroups, kLbThreads, 0, st>>>(E, Nj, lbsum, logOmega, logPi, logA, logLam, out);
+  launch_chain(k_lower_bound, dim3(E.ngroups), dim3(kLbThreads), 0, st, E, Nj, lbsum, logOmega, logPi, logA, logLam, out);
   return 1;
 }
 
@@ -237,7 +241,8 @@ int launch_mstep(const EmView &E, const double *Nj, const double *nu1, const dou
                  const double *ybar, const double *SC, double *alpha, double *eta, double *epsilon, double *m,
                  double *W, double *v, double *lambda, cudaStream_t st) {
   const int tot = E.K * E.maxSr;
-  k_mstep<<<(tot + 127) / 128, 128, 0, st>>>(E, Nj, nu1, xi, pr, ybar, SC, alpha, eta, epsilon, m, W, v, lambda);
+  launch_chain(k_mstep, dim3((tot + 127) / 128), dim3(128), 0, st, E, Nj, nu1, xi, pr, ybar, SC, alpha, eta, epsilon, m,
+               W, v, lambda);
   return 1;
 }
 

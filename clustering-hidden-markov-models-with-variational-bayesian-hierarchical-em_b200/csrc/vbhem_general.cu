@@ -227,11 +227,16 @@ __device__ void store_pair(const BaseView &B, const CentreView &C, const PairOut
 }
 
 // flags: optional per-pair (all-pairs work) or per-item (list work) filter; only
-// entries with a non-zero flag are processed.  count: optional device counter; the
-// kernel returns at once when it is zero (nothing was flagged).
+// entries with a non-zero flag are processed.  count: optional device counters; the
+// kernel returns at once when count[0] is zero (nothing is flagged).  All-pairs fall-back:
+// count[0] = pairs still pending, count[2] = pairs served in this E-step; a served pair's flag is
+// cleared, so the flag array is all-zero again when the last pending pair has been served.
+// Only bases [i0, i1) are looked at (a slice of a streamed E-step).
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-k_general(BaseView B, CentreView C, int T, PairWork W, PairOut O, const unsigned char *flags, const int *count,
-          double *scratch, size_t per_warp) {
+k_general(BaseView B, CentreView C, int T, PairWork W, PairOut O, unsigned char *flags, int *count,
+          double *scratch, size_t per_warp, int i0, int i1) {
+  pdl_trigger();
+  pdl_wait();
   if (count && *count == 0) return;
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
@@ -241,12 +246,18 @@ k_general(BaseView B, CentreView C, int T, PairWork W, PairOut O, const unsigned
   Slab s = carve(scratch + per_warp * warp, B.maxSb, C.maxSr, T, per);
 
   if (W.items == nullptr) {
-    for (long long p = warp; p < W.npairs; p += nwarps) {
+    const long long ni = i1 - i0, np = ni * C.K;
+    for (long long u = warp; u < np; u += nwarps) {
+      const int i = i0 + (int)(u % ni), j = (int)(u / ni);
+      const long long p = i + (long long)B.N * j;
       if (flags && !flags[p]) continue;
-      const int i = (int)(p % B.N), j = (int)(p / B.N);
       const double L = pair_general(B, C, T, i, j, s, ro, O.mode != 0, lane);
       if (lane == 0 && O.L_elbo) O.L_elbo[p] = L;
       if (O.mode == 1) store_pair(B, C, O, s, i, j, lane);
+      if (flags && lane == 0) {
+        flags[p] = 0;
+        if (count) { atomicSub(count, 1); atomicAdd(count + 2, 1); }
+      }
       __syncwarp();
     }
   } else {
@@ -284,8 +295,9 @@ size_t general_scratch_per_warp(int maxSb, int maxSr, int d, int dd, int T) {
 }
 
 int launch_general(const BaseView &B, const CentreView &C, int T, const PairWork &W, const PairOut &O,
-                   const unsigned char *flags, const int *count, double *scratch, size_t scratch_doubles,
-                   cudaStream_t st) {
+                   unsigned char *flags, int *count, double *scratch, size_t scratch_doubles, cudaStream_t st, int i0,
+                   int i1) {
+  if (i1 < 0) i1 = B.N;
   const size_t per_warp = general_scratch_per_warp(B.maxSb, C.maxSr, B.d, B.dd, T);
   long long units = W.items ? W.nranges : W.npairs;
   if (W.items && W.npairs < units) units = W.npairs;   // never more ranges in use than items
@@ -295,7 +307,8 @@ int launch_general(const BaseView &B, const CentreView &C, int T, const PairWork
   long long blocks = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
   if (blocks * kWarpsPerBlock * per_warp > scratch_doubles) blocks = warps / kWarpsPerBlock;
   if (blocks < 1) return -1;   // scratch too small for even one block
-  k_general<<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(B, C, T, W, O, flags, count, scratch, per_warp);
+  launch_chain<1>(k_general, dim3((unsigned)blocks), dim3(kWarpsPerBlock * 32), 0, st, B, C, T, W, O, flags, count, scratch,
+               per_warp, i0, i1);
   return 1;
 }
 

@@ -87,10 +87,45 @@ struct Fallback { unsigned char *flags; int *count; };
 
 inline __host__ __device__ int stat_per(int r, int d, int dd) { return r + r * r + r + r * d + r * dd; }
 
+// ---- programmatic dependent launch (PDL) --------------------------------------
+// An E-step is a chain of ~12 dependent kernels, most of them a few microseconds long, so at a 12 500-base shard
+// (8-GPU strong scaling) the launch latency between them is a visible share of the step.  Every kernel of the
+// chain is launched with cudaLaunchAttributeProgrammaticStreamSerialization: it lets its successor's CTAs be
+// scheduled at once (pdl_trigger, first statement) and waits for its predecessor's results itself (pdl_wait, before
+// the first dependent read; a no-op when launched the ordinary way).  EVERY path through EVERY chain kernel must
+// execute pdl_wait -- a kernel that returned without it would complete before its predecessor and let ITS
+// successor run too early.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// vbhem_aux.cu: kernel class 0 = the small kernels, 1 = the pair kernels (k_lattice_*, k_general);
+// VBHEM_PDL = 0 none, 1 all, 2 small only (default), 3 pair kernels only
+bool pdl_enabled(int cls);
+template <int CLS = 0, typename... KA, typename... A>
+inline cudaError_t launch_chain(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at{};
+  at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &at;
+  cfg.numAttrs = pdl_enabled(CLS) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KA>(args)...);
+}
+#endif
+
 // ---- launchers (each returns the number of kernels it launched) -------------
+// flags (fall-back mode): only flagged pairs / items are processed; the all-pairs flags are CLEARED as they are
+// served, so the flag array is all-zero again when the kernel ends (no memset per E-step)
+// count (fall-back mode): device ints; all-pairs work uses count[0] = pending, count[2] = served so far; list work
+// only reads count[0].  All-pairs work looks at bases [i0, i1) only (i1 < 0: all).
 int launch_general(const BaseView &B, const CentreView &C, int T, const PairWork &W, const PairOut &O,
-                   const unsigned char *flags, const int *count, double *scratch, size_t scratch_doubles,
-                   cudaStream_t st);
+                   unsigned char *flags, int *count, double *scratch, size_t scratch_doubles, cudaStream_t st,
+                   int i0 = 0, int i1 = -1);
 size_t general_scratch_per_warp(int maxSb, int maxSr, int d, int dd, int T);
 
 bool lattice_supported(const BaseView &B, const CentreView &C, int T, bool need_forward);
@@ -105,24 +140,27 @@ int lattice_bwd_wave();   // bases one full wave of the first-pass grid takes
 
 // aux kernels (vbhem_aux.cu)
 int zhat_blocks(int N);
+// with rec != nullptr the same launch also builds the lattice records of C (launch_build_records)
 int launch_prepass(int K, int maxSr, int d, int covmode, const int *Sr, const int *gstart, int ngroups,
                    const double *alpha, const double *eta, const double *epsilon, const double *W, const double *v,
                    const double *lambda, double *logOmega, double *logPi, double *logA, double *logLam, double *cterm,
-                   double *vW, cudaStream_t st);
-int launch_build_records(const CentreView &C, int d, int dd, double *rec, cudaStream_t st);
+                   double *vW, const CentreView &C, double *rec, int *counters, cudaStream_t st);
+// `counters`: optional device ints {first-pass fall-backs, second-pass fall-backs} cleared by the same launch
+int launch_build_records(const CentreView &C, int d, int dd, double *rec, int *counters, cudaStream_t st);
 int launch_sanitize_base(BaseView B, double *prior, double *A, double *mu, double *cov, cudaStream_t st, int i0 = 0,
                          int n = -1);
-// zhat, Nj, lb (fixed-order sums) and the per-block counts of pairs with Z > 1e-8
-// blocks [blk0, blk0 + nblk) of zhat_blocks(N) (nblk < 0: all); the fixed-order sums over all blocks run when
-// `reduce` is set (the last slice of a streamed E-step)
+// zhat and, per block of 256 bases, the partial sums of Z (Nj_part), of the lower-bound terms (lb_part) and the
+// counts of pairs with Z > 1e-8 (cnt); blocks [blk0, blk0 + nblk) of zhat_blocks(N) (nblk < 0: all)
 int launch_zhat(int N, int K, int ngroups, const int *gstart, const double *L_elbo, const double *logOmega,
-                const double *Ntilde, double *zhat, double *Nj_part, int *cnt, double *lb_part, double *Nj, double *lb,
-                cudaStream_t st, int blk0 = 0, int nblk = -1, bool reduce = true);
+                const double *Ntilde, double *zhat, double *Nj_part, int *cnt, double *lb_part, cudaStream_t st,
+                int blk0 = 0, int nblk = -1);
 int zhat_block_size();
 // deterministic (centre-major, base-ascending) list of those pairs; seg_start[K + 1] = first item of every centre,
 // totals = {#active, items per range = ceil(#active / nranges), at least 1}.  Nothing here depends on a value the
 // host would have to read back: every grid is sized by N and K alone.
-int launch_list_scan(int N, int K, int nranges, const int *cnt, int *offs, int *segcnt, int *seg_start, int *totals,
+// The same launch sums the per-block partials of launch_zhat in a fixed order: Nj[K], lb[2 * ngroups].
+int launch_list_scan(int N, int K, int ngroups, int nranges, const int *cnt, const double *Nj_part,
+                     const double *lb_part, int *offs, int *segcnt, int *seg_start, int *totals, double *Nj, double *lb,
                      cudaStream_t st);
 int launch_list_fill(int N, int K, const double *zhat, const double *Ntilde, const int *offs, const int *seg_start,
                      PairItem *items, cudaStream_t st);

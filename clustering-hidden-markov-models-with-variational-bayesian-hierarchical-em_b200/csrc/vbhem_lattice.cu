@@ -518,7 +518,9 @@ k_lattice_bwd(BaseView B, const double *__restrict__ rec_src, const int *__restr
   constexpr int RS = 80 + 8 * D + 8 * BaseConst<D, FULL>::DD;              // lattice_rec_stride(d, dd)
   int *sidx = reinterpret_cast<int *>(recs + (size_t)kc * RS);             // centre index of every tile slot
   const unsigned recs_s = (unsigned)__cvta_generic_to_shared(recs);
-  TabFirst::load(smem);
+  pdl_trigger();
+  TabFirst::load(smem);             // constants: overlaps the tail of the kernel before (PDL)
+  pdl_wait();                       // the centre records and tile lists come from the kernels before
   for (int x = threadIdx.x; x < nj * CPT; x += blockDim.x) sidx[x] = list[(size_t)j0 * CPT + x];
   for (int x = threadIdx.x; x < nj * RS; x += blockDim.x) {
     const int r = x / RS, o = x - r * RS;
@@ -530,12 +532,14 @@ k_lattice_bwd(BaseView B, const double *__restrict__ rec_src, const int *__restr
   const Split sp{2 * q < ksplit, 2 * q + 1 < ksplit, q == 0};
 
   // Work unit = one base x kUnitCentres tiles: fine enough that the last wave of warps is nearly full even
-  // for a 12 500-base shard (8-GPU strong scaling), coarse enough that re-reading the base costs < 1 %.
-  const int nuc = (nj + kUnitCentres - 1) / kUnitCentres;
+  // for a 12 500-base shard (8-GPU strong scaling), coarse enough that re-reading the base costs < 1 %
+  // (a smaller unit was measured slower: 4 tiles cost 4 % at 12 500 bases, the base loads are not hidden).
+  constexpr int unit_centres = kUnitCentres;
+  const int nuc = (nj + unit_centres - 1) / unit_centres;
   const long long nunits = (long long)(i1 - i0) * nuc, nw = (long long)gridDim.x * kBwdWarps;
   for (long long u = (long long)blockIdx.x * kBwdWarps + warp; u < nunits; u += nw) {
-    const int i = i0 + (int)(u / nuc), jc = (int)(u % nuc) * kUnitCentres;
-    const int je = min(jc + kUnitCentres, nj);
+    const int i = i0 + (int)(u / nuc), jc = (int)(u % nuc) * unit_centres;
+    const int je = min(jc + unit_centres, nj);
     BaseConst<D, FULL> b;
     load_base(b, B, i, g, q);
     const bool base_chk = base_bad(b.Ab, b.prior);
@@ -595,6 +599,8 @@ k_lattice_bwd(BaseView B, const double *__restrict__ rec_src, const int *__restr
 // One block per pair of centres that share a tile: the tile record out of the two centres' own records
 // (k_build_records): slots [0, ks) <- centre a's states 0.., slots [ks, 8) <- centre b's, expA block-diagonal.
 __global__ void k_pair_records(const double *rec, const int *pairs, int rs, int d, int dd, int ks, double *out) {
+  pdl_trigger();
+  pdl_wait();
   const int a = pairs[2 * blockIdx.x], b = pairs[2 * blockIdx.x + 1];
   double *o = out + (size_t)rs * blockIdx.x;
   for (int x = threadIdx.x; x < rs; x += blockDim.x) {
@@ -707,7 +713,9 @@ k_lattice_full(BaseView B, CentreView C, int T, PairWork W, PairOut O, Fallback 
   const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
   const int warp = threadIdx.x >> 5;
   const tab_t ltab = TabFull::log_view(smem, lane), etab = TabFull::exp_view(smem, lane);
+  pdl_trigger();
   TabFull::load(smem);
+  pdl_wait();
   __syncthreads();
   double *sm = smem + TabFull::kDoubles + (size_t)warp * ((size_t)2 * kTile * (T - 1) + kTile);
   const long long gw = (long long)blockIdx.x * warps_per_block + warp;
@@ -860,15 +868,22 @@ int launch_bwd_list(const BaseView &B, const double *rec_src, const int *list, i
   if (kc > ntiles) kc = ntiles;
   const size_t smem = sizeof(double) * ((size_t)kc * rs + TabFirst::kDoubles) + sizeof(int) * 2 * (size_t)kc + 16;
   const int ny = (ntiles + kc - 1) / kc;
+  const int cap = VB_BWD_MINB * sm_count();
   const int kcu = (kc + kUnitCentres - 1) / kUnitCentres;
   long long nxl = ((long long)n * kcu + kBwdWarps - 1) / kBwdWarps;
   int nx = nxl > (1 << 30) ? (1 << 30) : (int)nxl;
-  const int cap = VB_BWD_MINB * sm_count();
   if (nx > cap) nx = cap;
   return dispatch(B.d, B.covmode, [&](auto Dc, auto Fc) {
     auto kern = k_lattice_bwd<decltype(Dc)::value, decltype(Fc)::value, SP>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<dim3(nx, ny), kBwdWarps * 32, smem, st>>>(B, rec_src, list, ntiles, T, kc, L_elbo, fb, i0, i0 + n, ksplit);
+    static size_t smem_set[64] = {};                            // per instantiation and device (the attribute is per device)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > smem_set[dev & 63]) {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      smem_set[dev & 63] = smem;
+    }
+    launch_chain<1>(kern, dim3(nx, ny), dim3(kBwdWarps * 32), smem, st, B, rec_src, list, ntiles, T, kc, L_elbo, fb, i0,
+                 i0 + n, ksplit);
     return 1;
   });
 }
@@ -897,8 +912,8 @@ int launch_pair_records(const CentreView &C, int d, int dd, double *out, cudaStr
   int launched = 0, off = 0;
   for (int c = 0; c < kTileClasses; c++) {
     if (C.npairs[c] <= 0) continue;
-    k_pair_records<<<C.npairs[c], 128, 0, st>>>(C.rec, C.pair_list + 2 * (size_t)off, C.rec_stride, d, dd, c == 0 ? 4 : c,
-                                                out + (size_t)C.rec_stride * off);
+    launch_chain(k_pair_records, dim3(C.npairs[c]), dim3(128), 0, st, C.rec, C.pair_list + 2 * (size_t)off,
+                 C.rec_stride, d, dd, c == 0 ? 4 : c, out + (size_t)C.rec_stride * off);
     off += C.npairs[c];
     launched++;
   }
@@ -920,8 +935,14 @@ int launch_lattice_full(const BaseView &B, const CentreView &C, int T, const Pai
   const size_t smem = pw * wpb + sizeof(double) * TabFull::kDoubles;
   return dispatch(B.d, B.covmode, [&](auto Dc, auto Fc) {
     auto kern = k_lattice_full<decltype(Dc)::value, decltype(Fc)::value>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<(unsigned)blocks, wpb * 32, smem, st>>>(B, C, T, W, O, fb, wpb);
+    static size_t smem_set[64] = {};                            // per instantiation and device (the attribute is per device)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > smem_set[dev & 63]) {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      smem_set[dev & 63] = smem;
+    }
+    launch_chain<1>(kern, dim3((unsigned)blocks), dim3(wpb * 32), smem, st, B, C, T, W, O, fb, wpb);
     return 1;
   });
 }
