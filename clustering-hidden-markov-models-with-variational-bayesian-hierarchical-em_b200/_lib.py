@@ -77,6 +77,7 @@ SIGNATURES = {
     "vbhem_multi_pack_base": (C.c_int, [C.c_int, ip, C.c_int, C.c_int, C.POINTER(C.c_ubyte), C.c_int, ip, C.c_int,
                                         C.c_int, C.c_int, dp, dp, dp, dp, dp, C.POINTER(vp)]),
     "vbhem_multi_free": (C.c_int, [vp]),
+    "vbhem_multi_repack_base": (C.c_int, [vp, ip, dp, dp, dp, dp, dp]),
     "vbhem_multi_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "vbhem_multi_shard": (C.c_int, [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                     C.POINTER(vp)]),
@@ -85,6 +86,12 @@ SIGNATURES = {
                                     dp, dp, dp]),
     "vbhem_multi_estep_hyp": (C.c_int, [vp, C.c_int, ip, C.c_int, ip, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, dp,
                                         dp, dp, dp, dp]),
+    "vbhem_multi_estep_hyp_stream": (C.c_int, [vp, ip, dp, dp, dp, dp, dp, C.c_int, C.c_int, ip, C.c_int, ip, C.c_int,
+                                               C.c_int, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp]),
+    "vbhem_multi_estep_hyp_dev": (C.c_int, [vp, C.c_int, ip, C.c_int, ip, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, dp,
+                                            C.c_int]),
+    "vbhem_multi_synchronize": (C.c_int, [vp]),
+    "vbhem_multi_stats": (C.c_int, [vp, dp]),
     "vbhem_multi_fetch": (C.c_int, [vp, dp, dp]),
     "vbhem_multi_finalize_stats": (C.c_int, [vp, C.c_int, ip, C.c_int, C.c_int, dp]),
     "vbhem_multi_em_begin": (C.c_int, [vp, C.c_int, ip, C.c_int, ip, C.c_int, C.c_double, C.c_double, C.c_double,

@@ -389,6 +389,43 @@ class MultiBaseSet:
         out["buf"] = buf
         return out
 
+    # -- non-synchronising / host-streamed variants (bench.py) ---------------
+    def prepare_hyp(self, hyp: dict, group=None) -> dict:
+        """The C-ABI arrays of a centre set, converted once (the timed loops of bench.py pass them as they are)."""
+        K, r, Sr, H = _hyp_arrays(hyp, self.covmode)
+        grp = None if group is None else np.ascontiguousarray(group, dtype=np.int32)
+        return dict(K=K, r=r, Sr=Sr, H=H, grp=grp, ng=int(grp.max()) + 1 if grp is not None else 1)
+
+    def estep_hyp_dev(self, P: dict, tau: int, finalize: bool = True):
+        """Enqueue E-step + all-reduce (+ normalisation) on every shard and return (``vbhem_multi_estep_hyp_dev``)."""
+        check(lib().vbhem_multi_estep_hyp_dev(self._h, P["K"], _i(P["Sr"]), P["r"], _i(P["grp"]), P["ng"], tau,
+                                              *[_d(h) for h in P["H"]], 1 if finalize else 0))
+
+    def synchronize(self):
+        check(lib().vbhem_multi_synchronize(self._h))
+
+    def stats(self, P: dict) -> np.ndarray:
+        buf = np.zeros(self.stats_size(P["K"], P["r"], P["ng"]))
+        check(lib().vbhem_multi_stats(self._h, _d(buf)))
+        return buf
+
+    def fetch(self, K: int):
+        L, z = np.zeros((K, self.N)), np.zeros((K, self.N))
+        check(lib().vbhem_multi_fetch(self._h, _d(L), _d(z)))
+        return L, z
+
+    def estep_hyp_stream(self, pb: dict, P: dict, tau: int, nslices: int, L, z, stats, pre):
+        """Host-resident (packed, ideally pinned) base set streamed in by every shard; host outputs as given."""
+        check(lib().vbhem_multi_estep_hyp_stream(self._h, _i(pb["Sb"]), _d(pb["prior"]), _d(pb["A"]), _d(pb["mu"]),
+                                                 _d(pb["cov"]), _d(pb["Ntilde"]), nslices, P["K"], _i(P["Sr"]), P["r"],
+                                                 _i(P["grp"]), P["ng"], tau, *[_d(h) for h in P["H"]], _d(L), _d(z),
+                                                 _d(stats), _d(pre)))
+
+    def shard_handle(self, k: int = 0):
+        h = C.c_void_p()
+        check(lib().vbhem_multi_shard(self._h, k, None, None, None, C.byref(h)))
+        return h
+
     def finalize(self, buf: np.ndarray, Sr, r: int, ng: int = 1) -> dict:
         Sr = np.ascontiguousarray(Sr, dtype=np.int32)
         K = Sr.shape[0]

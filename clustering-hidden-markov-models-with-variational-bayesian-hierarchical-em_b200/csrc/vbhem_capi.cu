@@ -178,6 +178,7 @@ struct vbhem_base {
   bool split_tiles = true;    // ... including 5..7 states next to 3..1 (vbhem_set_kernel 3: halves only)
   long long counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int lastK = 0;
+  const int *last_Sr_dev = nullptr;   // state counts of the last E-step's centre set, on the device
 };
 
 namespace {
@@ -197,8 +198,10 @@ struct CentreArgs {
 struct StreamIO {
   const int32_t *Sb;
   const double *prior, *A, *mu, *cov, *Ntilde;
-  double *L_host, *z_host;
+  double *L_host, *z_host;   // first row of this handle's bases in the host arrays
   int nslices;
+  long long host_ld = 0;     // leading dimension of the host arrays (0 = the handle's N); a shard of a multi-GPU
+                             // set writes its rows into the [N_total, K] arrays of the whole set
 };
 
 int check_common(vbhem_base *h, const CentreArgs &a, bool need_omega) {
@@ -563,11 +566,12 @@ int streamed_front(vbhem_base *h, const CentreDev &cd, const CentreArgs &a, cons
     CU(cudaEventRecord(h->slice_ev[2 * c + 1], h->st));
     CU(cudaStreamWaitEvent(h->cout, h->slice_ev[2 * c + 1], 0));
     const size_t pitch = sizeof(double) * (size_t)N;
+    const size_t hpitch = sizeof(double) * (size_t)(io.host_ld ? io.host_ld : N);
     if (io.L_host)
-      CU(cudaMemcpy2DAsync(io.L_host + i0, pitch, h->L.as<double>() + i0, pitch, sizeof(double) * n, K,
+      CU(cudaMemcpy2DAsync(io.L_host + i0, hpitch, h->L.as<double>() + i0, pitch, sizeof(double) * n, K,
                            cudaMemcpyDeviceToHost, h->cout));
     if (io.z_host)
-      CU(cudaMemcpy2DAsync(io.z_host + i0, pitch, h->z.as<double>() + i0, pitch, sizeof(double) * n, K,
+      CU(cudaMemcpy2DAsync(io.z_host + i0, hpitch, h->z.as<double>() + i0, pitch, sizeof(double) * n, K,
                            cudaMemcpyDeviceToHost, h->cout));
   }
   h->counters[1] += np;
@@ -614,8 +618,10 @@ int estep_device(vbhem_base *h, const CentreArgs &a, double *stats_dev, double *
     launches += launch_zhat(N, K, a.ngroups, cd.gstart, h->L.as<double>(), cd.C.logOmega, h->B.Ntilde,
                             h->z.as<double>(), h->Njp.as<double>(), h->cnt.as<int>(), h->lbp.as<double>(), h->st);
     if (io) {
-      if (io->L_host) CU(cudaMemcpyAsync(io->L_host, h->L.p, sizeof(double) * np, cudaMemcpyDeviceToHost, h->st));
-      if (io->z_host) CU(cudaMemcpyAsync(io->z_host, h->z.p, sizeof(double) * np, cudaMemcpyDeviceToHost, h->st));
+      const size_t pitch = sizeof(double) * (size_t)N;
+      const size_t hpitch = sizeof(double) * (size_t)(io->host_ld ? io->host_ld : N);
+      if (io->L_host) CU(cudaMemcpy2DAsync(io->L_host, hpitch, h->L.p, pitch, pitch, K, cudaMemcpyDeviceToHost, h->st));
+      if (io->z_host) CU(cudaMemcpy2DAsync(io->z_host, hpitch, h->z.p, pitch, pitch, K, cudaMemcpyDeviceToHost, h->st));
     }
   }
   // Deterministic list of the pairs with Z > 1e-8 and the second pass over it.  The list's length stays on the
@@ -672,6 +678,7 @@ int estep_device(vbhem_base *h, const CentreArgs &a, double *stats_dev, double *
   CU(cudaGetLastError());
   h->counters[0] = launches;
   h->lastK = K;
+  h->last_Sr_dev = cd.C.Sr;
   h->d_totals = totals;
   h->totals_pending = true;
   return VBHEM_OK;

@@ -134,6 +134,7 @@ struct vbhem_multi {
   std::vector<Worker *> w;
   std::vector<cudaEvent_t> ev0, ev1;       // around the E-step (+ all-reduce) on every shard's stream
   int lastK = 0;
+  size_t last_ns = 0;
   // f(k) for every local shard, concurrently (one worker thread per shard); first failure wins
   int run_all(const std::function<int(int)> &f) {
     if (nlocal == 1) return f(0);
@@ -159,8 +160,10 @@ int allreduce_stats(vbhem_multi *m, int k, double *buf, size_t n) {
 }
 
 // The fused E-step of every shard + all-reduce; host outputs as for vbhem_estep[_hyp] (stats = RAW sums over ALL
-// ranks; L_elbo / zhat = the rows of this process's bases).
-int multi_estep(vbhem_multi *m, const CentreArgs &a, double *L_elbo, double *zhat, double *stats, double *pre) {
+// ranks; L_elbo / zhat = the rows of this process's bases).  With `sio` the base set comes from host memory and
+// every shard streams its own rows in (vbhem_estep*_stream).
+int multi_estep(vbhem_multi *m, const CentreArgs &a, double *L_elbo, double *zhat, double *stats, double *pre,
+                const StreamIO *sio = nullptr) {
   if (!stats) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: stats is NULL");
   const size_t ns = vbhem_stats_size(a.K, a.maxSr, m->h[0]->B.d, m->h[0]->B.covmode, a.ngroups);
   int rc = m->run_all([&](int k) -> int {
@@ -168,21 +171,63 @@ int multi_estep(vbhem_multi *m, const CentreArgs &a, double *L_elbo, double *zha
     CU(cudaSetDevice(h->device));
     CU(h->stats.ensure(sizeof(double) * ns));
     CU(cudaEventRecord(m->ev0[k], h->st));
-    int r = estep_device(h, a, h->stats.as<double>(), k == 0 ? pre : nullptr);
+    const size_t lo = (size_t)m->lo[k];
+    int r;
+    if (sio) {
+      const int ld = h->B.maxSb, d = h->B.d, dd = h->B.dd;
+      StreamIO io{sio->Sb + lo, sio->prior + lo * ld, sio->A + lo * ld * ld, sio->mu + lo * ld * d,
+                  sio->cov + lo * ld * dd, sio->Ntilde ? sio->Ntilde + lo : nullptr,
+                  L_elbo ? L_elbo + lo : nullptr, zhat ? zhat + lo : nullptr, sio->nslices, (long long)m->N};
+      r = estep_device(h, a, h->stats.as<double>(), k == 0 ? pre : nullptr, &io);
+    } else {
+      r = estep_device(h, a, h->stats.as<double>(), k == 0 ? pre : nullptr);
+    }
     if (r) return r;
     r = allreduce_stats(m, k, h->stats.as<double>(), ns);
     if (r) return r;
     CU(cudaEventRecord(m->ev1[k], h->st));
     if (k == 0) CU(cudaMemcpyAsync(stats, h->stats.p, sizeof(double) * ns, cudaMemcpyDeviceToHost, h->st));
-    const size_t hp = sizeof(double) * (size_t)m->N, dp_ = sizeof(double) * (size_t)m->cnt[k];
-    if (L_elbo)
-      CU(cudaMemcpy2DAsync(L_elbo + m->lo[k], hp, h->L.p, dp_, dp_, a.K, cudaMemcpyDeviceToHost, h->st));
-    if (zhat)
-      CU(cudaMemcpy2DAsync(zhat + m->lo[k], hp, h->z.p, dp_, dp_, a.K, cudaMemcpyDeviceToHost, h->st));
-    return settle_counters(h);   // synchronises the shard's stream
+    if (!sio) {
+      const size_t hp = sizeof(double) * (size_t)m->N, dp_ = sizeof(double) * (size_t)m->cnt[k];
+      if (L_elbo)
+        CU(cudaMemcpy2DAsync(L_elbo + lo, hp, h->L.p, dp_, dp_, a.K, cudaMemcpyDeviceToHost, h->st));
+      if (zhat)
+        CU(cudaMemcpy2DAsync(zhat + lo, hp, h->z.p, dp_, dp_, a.K, cudaMemcpyDeviceToHost, h->st));
+    }
+    r = settle_counters(h);      // synchronises the shard's stream
+    if (r) return r;
+    if (sio && h->cout) CU(cudaStreamSynchronize(h->cout));
+    return VBHEM_OK;
   });
   if (rc) return rc;
   m->lastK = a.K;
+  return VBHEM_OK;
+}
+
+// The same, everything left on the devices and nothing waited for: E-step, all-reduce and (optionally) the
+// normalisation of vbhem_compute_Statistics.m:57-82 are enqueued on every shard's stream.
+int multi_estep_dev(vbhem_multi *m, const CentreArgs &a, bool finalize) {
+  const size_t ns = vbhem_stats_size(a.K, a.maxSr, m->h[0]->B.d, m->h[0]->B.covmode, a.ngroups);
+  int rc = m->run_all([&](int k) -> int {
+    vbhem_base *h = m->h[k];
+    CU(cudaSetDevice(h->device));
+    CU(h->stats.ensure(sizeof(double) * ns));
+    CU(cudaEventRecord(m->ev0[k], h->st));
+    int r = estep_device(h, a, h->stats.as<double>(), nullptr);
+    if (r) return r;
+    r = allreduce_stats(m, k, h->stats.as<double>(), ns);
+    if (r) return r;
+    if (finalize) {
+      StatsPtr S = carve_stats(h->stats.as<double>(), a.K, a.maxSr, h->B.d, h->B.dd, a.ngroups);
+      launch_finalize(a.K, a.maxSr, h->B.d, h->B.covmode, h->last_Sr_dev, S.Nj, S.xi, S.pr, S.mu, S.Mu, h->st);
+    }
+    CU(cudaEventRecord(m->ev1[k], h->st));
+    CU(cudaGetLastError());
+    return VBHEM_OK;
+  });
+  if (rc) return rc;
+  m->lastK = a.K;
+  m->last_ns = ns;
   return VBHEM_OK;
 }
 
@@ -329,6 +374,19 @@ int vbhem_multi_pack_base(int nlocal, const int *devices, int world, int rank_fi
   return VBHEM_OK;
 }
 
+int vbhem_multi_repack_base(vbhem_multi_t *m, const int32_t *Sb, const double *prior, const double *A,
+                            const double *mu, const double *cov, const double *Ntilde) {
+  int rc = check_multi(m);
+  if (rc) return rc;
+  if (!Sb || !prior || !A || !mu || !cov) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: a base array is NULL");
+  return m->run_all([&](int k) {
+    vbhem_base *h = m->h[k];
+    const size_t lo = (size_t)m->lo[k], ld = h->B.maxSb, d = h->B.d, dd = h->B.dd;
+    return vbhem_repack_base(h, Sb + lo, prior + lo * ld, A + lo * ld * ld, mu + lo * ld * d, cov + lo * ld * dd,
+                             Ntilde ? Ntilde + lo : nullptr);
+  });
+}
+
 int vbhem_multi_info(vbhem_multi_t *m, int *nlocal, int *world, int *N) {
   int rc = check_multi(m);
   if (rc) return rc;
@@ -382,6 +440,61 @@ int vbhem_multi_estep_hyp(vbhem_multi_t *m, int K, const int32_t *Sr, int maxSr,
   rc = check_common(m->h[0], a, true);
   if (rc) return rc;
   return multi_estep(m, a, L_elbo, zhat, stats, pre);
+}
+
+int vbhem_multi_estep_hyp_stream(vbhem_multi_t *m, const int32_t *Sb, const double *prior, const double *A,
+                                 const double *mu, const double *cov, const double *Ntilde, int nslices, int K,
+                                 const int32_t *Sr, int maxSr, const int32_t *group, int ngroups, int tau,
+                                 const double *alpha, const double *eta, const double *epsilon, const double *mm,
+                                 const double *W, const double *v, const double *lambda, double *L_elbo, double *zhat,
+                                 double *stats, double *pre) {
+  int rc = check_multi(m);
+  if (rc) return rc;
+  CentreArgs a{};
+  a.K = K; a.maxSr = maxSr; a.ngroups = ngroups; a.tau = tau; a.Sr = Sr; a.group = group;
+  a.alpha = alpha; a.eta = eta; a.epsilon = epsilon; a.m = mm; a.W = W; a.v = v; a.lambda = lambda; a.hyp = true;
+  rc = check_common(m->h[0], a, true);
+  if (rc) return rc;
+  if (!Sb || !prior || !A || !mu || !cov) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: a base array is NULL");
+  for (int i = 0; i < m->N; i++)
+    if (Sb[i] < 1 || Sb[i] > m->h[0]->B.maxSb)
+      return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: Sb[%d]=%d outside 1..maxSb=%d", i, Sb[i], m->h[0]->B.maxSb);
+  StreamIO io{Sb, prior, A, mu, cov, Ntilde, nullptr, nullptr, nslices, 0};
+  return multi_estep(m, a, L_elbo, zhat, stats, pre, &io);
+}
+
+int vbhem_multi_estep_hyp_dev(vbhem_multi_t *m, int K, const int32_t *Sr, int maxSr, const int32_t *group, int ngroups,
+                              int tau, const double *alpha, const double *eta, const double *epsilon, const double *mm,
+                              const double *W, const double *v, const double *lambda, int finalize) {
+  int rc = check_multi(m);
+  if (rc) return rc;
+  CentreArgs a{};
+  a.K = K; a.maxSr = maxSr; a.ngroups = ngroups; a.tau = tau; a.Sr = Sr; a.group = group;
+  a.alpha = alpha; a.eta = eta; a.epsilon = epsilon; a.m = mm; a.W = W; a.v = v; a.lambda = lambda; a.hyp = true;
+  rc = check_common(m->h[0], a, true);
+  if (rc) return rc;
+  return multi_estep_dev(m, a, finalize != 0);
+}
+
+int vbhem_multi_synchronize(vbhem_multi_t *m) {
+  int rc = check_multi(m);
+  if (rc) return rc;
+  for (vbhem_base *h : m->h) {
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->st));
+  }
+  return VBHEM_OK;
+}
+
+int vbhem_multi_stats(vbhem_multi_t *m, double *stats) {
+  int rc = check_multi(m);
+  if (rc) return rc;
+  if (!stats || !m->last_ns) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: no vbhem_multi_estep_hyp_dev result to fetch");
+  vbhem_base *h = m->h[0];
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(stats, h->stats.p, sizeof(double) * m->last_ns, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  return VBHEM_OK;
 }
 
 int vbhem_multi_fetch(vbhem_multi_t *m, double *L_elbo, double *zhat) {

@@ -263,6 +263,9 @@ int vbhem_multi_pack_base(int nlocal, const int *devices, int world, int rank_fi
                           const int32_t *Sb, int maxSb, int d, int covmode, const double *prior, const double *A,
                           const double *mu, const double *cov, const double *Ntilde, vbhem_multi_t **out);
 int vbhem_multi_free(vbhem_multi_t *multi);
+/* Re-upload a base set of the same shape (this process's N bases) into the shards: vbhem_repack_base per shard. */
+int vbhem_multi_repack_base(vbhem_multi_t *multi, const int32_t *Sb, const double *prior, const double *A,
+                            const double *mu, const double *cov, const double *Ntilde);
 int vbhem_multi_info(vbhem_multi_t *multi, int *nlocal, int *world, int *N);
 int vbhem_multi_shard(vbhem_multi_t *multi, int k, int *device, int *first, int *count, vbhem_base_t **handle);
 int vbhem_multi_set_kernel(vbhem_multi_t *multi, int which);
@@ -273,6 +276,23 @@ int vbhem_multi_estep_hyp(vbhem_multi_t *multi, int K, const int32_t *Sr, int ma
                           int tau, const double *alpha, const double *eta, const double *epsilon, const double *m,
                           const double *W, const double *v, const double *lambda, double *L_elbo, double *zhat,
                           double *stats, double *pre);
+/* Host-resident base set: every shard streams ITS rows of the arrays (layouts of vbhem_pack_base, N = this process's
+ * bases) in slices while earlier slices compute, as vbhem_estep_hyp_stream does on one device. */
+int vbhem_multi_estep_hyp_stream(vbhem_multi_t *multi, const int32_t *Sb, const double *prior, const double *A,
+                                 const double *mu, const double *cov, const double *Ntilde, int nslices, int K,
+                                 const int32_t *Sr, int maxSr, const int32_t *group, int ngroups, int tau,
+                                 const double *alpha, const double *eta, const double *epsilon, const double *m,
+                                 const double *W, const double *v, const double *lambda, double *L_elbo, double *zhat,
+                                 double *stats, double *pre);
+/* Nothing copied back, nothing waited for: E-step, all-reduce and (finalize != 0) the normalisation of
+ * vbhem_compute_Statistics.m:57-82 are enqueued on every shard's stream.  vbhem_multi_synchronize waits for all
+ * shards; vbhem_multi_stats copies the statistics buffer (raw or normalised, as requested) to the HOST;
+ * vbhem_multi_fetch the per-pair rows. */
+int vbhem_multi_estep_hyp_dev(vbhem_multi_t *multi, int K, const int32_t *Sr, int maxSr, const int32_t *group,
+                              int ngroups, int tau, const double *alpha, const double *eta, const double *epsilon,
+                              const double *m, const double *W, const double *v, const double *lambda, int finalize);
+int vbhem_multi_synchronize(vbhem_multi_t *multi);
+int vbhem_multi_stats(vbhem_multi_t *multi, double *stats);
 int vbhem_multi_fetch(vbhem_multi_t *multi, double *L_elbo, double *zhat);
 int vbhem_multi_finalize_stats(vbhem_multi_t *multi, int K, const int32_t *Sr, int maxSr, int ngroups, double *stats);
 int vbhem_multi_em_begin(vbhem_multi_t *multi, int K, const int32_t *Sr, int maxSr, const int32_t *group, int ngroups,

@@ -38,10 +38,12 @@ for j = 1:Kr
   end
 end
 prior = [vbhemopt.alpha0 vbhemopt.eta0 vbhemopt.epsilon0 vbhemopt.lambda0 vbhemopt.v0];
+% vbhemopt.ngpus (optional): shard the base HMMs over that many GPUs of the box, 0 = all of them
+if isfield(vbhemopt, 'ngpus'), ng = {vbhemopt.ngpus}; else, ng = {}; end
 
 [alpha, eta, eps, m, W, v, lam, LogLs, info] = vbhem_em_run_mex(h3m_b.hmm, maxN, tilde_N_k, h3m_r.alpha(:)', ...
     eta, eps, m, W, v, lam, Sr(:)', prior, vbhemopt.m0(:), vbhemopt.W0(:), vbhemopt.tau, vbhemopt.max_iter, ...
-    vbhemopt.minDiff);
+    vbhemopt.minDiff, ng{:});
 
 h3m_r.alpha = alpha;
 for j = 1:Kr

@@ -20,11 +20,13 @@ dim   = h3m_b.hmm{1}.emit{1}.nin;
 T     = vbhemopt.tau;
 maxN  = max(cellfun(@(x) length(x.prior), h3m_b.hmm));
 maxN2 = max(cellfun(@(x) length(x.eta),   h3m_r.hmm));
+% vbhemopt.ngpus (optional): shard the base HMMs over that many GPUs of the box, 0 = all of them
+if isfield(vbhemopt, 'ngpus'), ng = {vbhemopt.ngpus}; else, ng = {}; end
 
 switch h3m_b.hmm{1}.emit{1}.covar_type
   case 'diag'
     [L_elbo, hat_Z, Nj, R1, R2, R, Y, SC, lb] = vbhem_estep_fused_mex( ...
-        h3m_b.hmm, h3m_r.hmm, T, maxN, maxN2, tilde_N_k(:), logOmegaTilde(:)');
+        h3m_b.hmm, h3m_r.hmm, T, maxN, maxN2, tilde_N_k(:), logOmegaTilde(:)', ng{:});
   case 'full'
     ldR = cell(1,Kr);  icR = cell(1,Kr);
     for j = 1:Kr
@@ -36,7 +38,7 @@ switch h3m_b.hmm{1}.emit{1}.covar_type
       end
     end
     [L_elbo, hat_Z, Nj, R1, R2, R, Y, SC, lb] = vbhem_estep_fused_mex( ...
-        h3m_b.hmm, h3m_r.hmm, T, maxN, maxN2, tilde_N_k(:), logOmegaTilde(:)', ldR, icR);
+        h3m_b.hmm, h3m_r.hmm, T, maxN, maxN2, tilde_N_k(:), logOmegaTilde(:)', ldR, icR, ng{:});
   otherwise
     error('not supported')
 end

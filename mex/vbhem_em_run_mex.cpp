@@ -1,7 +1,11 @@
 // mex/vbhem_em_run_mex.cpp -- MEX gateway of the device-resident EM run.
 //
 //   [alpha, eta, epsilon, m, W, v, lambda, LogLs, info] = vbhem_em_run_mex(h3m_b.hmm, maxN, tilde_N_k, ...
-//        alpha, eta, epsilon, m, W, v, lambda, Sr, prior, m0, W0, tau, max_iter, minDiff)
+//        alpha, eta, epsilon, m, W, v, lambda, Sr, prior, m0, W0, tau, max_iter, minDiff [, ngpus])
+//
+// ngpus (optional 18th argument): shard the base HMMs over that many GPUs (0 = every visible GPU); every device keeps
+// the centre hyper-parameters, only the per-centre statistics travel (one NCCL all-reduce per iteration, inside the
+// library: vbhem_multi_em_run).  Without it the run uses one GPU.
 //
 // One call replaces the whole `while 1` loop of /root/reference/src/vbhem/vbhem_h3m_c_step_fc.m:115-433 for one H3M:
 // E-step (MEX call :175-194, responsibilities :271-283, statistics vbhem_compute_Statistics.m), lower bound
@@ -18,7 +22,7 @@
 
 using namespace vbmex;
 
-static HandleCache g_cache;
+static MultiCache g_cache;
 
 static const double *dbl_arg(const mxArray *a, size_t n, const char *what) {
   if (!mxIsDouble(a) || mxIsComplex(a) || mxGetNumberOfElements(a) != n)
@@ -30,7 +34,9 @@ enum Arg { A_HB, A_MAXN, A_NTILDE, A_ALPHA, A_ETA, A_EPS, A_M, A_W, A_V, A_LAM, 
            A_MAXIT, A_MINDIFF, A_COUNT };
 
 void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
-  if (nrhs != A_COUNT) mexErrMsgIdAndTxt("MyToolbox:arrayProduct:nrhs", "17 inputs required.");
+  if (nrhs != A_COUNT && nrhs != A_COUNT + 1)
+    mexErrMsgIdAndTxt("MyToolbox:arrayProduct:nrhs", "17 inputs (+ ngpus) required.");
+  const int ngpus = nrhs == A_COUNT + 1 ? (int)scalar_arg(prhs[A_COUNT]) : 1;
   if (nlhs != 9) mexErrMsgIdAndTxt("MyToolbox:arrayProduct:nlhs", "9 output required.");
   if (!mxIsCell(prhs[A_HB])) mexErrMsgIdAndTxt("vbhem_mex:invalidinput", "1st arg must be cell");
   const int maxN = (int)scalar_arg(prhs[A_MAXN]);
@@ -67,13 +73,13 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
   if (b.d != d) mexErrMsgIdAndTxt("vbhem_mex:invalidinput", "m0 has %d entries, the base emissions %d dimensions", d, b.d);
   if ((int)mxGetNumberOfElements(prhs[A_NTILDE]) != b.N)
     mexErrMsgIdAndTxt("vbhem_mex:invalidinput", "tilde_N_k must have one entry per base HMM");
-  vbhem_base_t *h = acquire(g_cache, b, dbl_arg(prhs[A_NTILDE], b.N, "tilde_N_k"));
+  vbhem_multi_t *h = acquire_multi(g_cache, b, dbl_arg(prhs[A_NTILDE], b.N, "tilde_N_k"), ngpus);
 
-  fail_rc(vbhem_em_begin(h, K, Sr.data(), S, nullptr, 1, pr[0], pr[1], pr[2], pr[3], pr[4], m0, W0, nW0, alpha, eta, eps,
+  fail_rc(vbhem_multi_em_begin(h, K, Sr.data(), S, nullptr, 1, pr[0], pr[1], pr[2], pr[3], pr[4], m0, W0, nW0, alpha, eta, eps,
                          m, W, v, lam));
   std::vector<double> LogLs((size_t)max_iter + 2, 0.0);
   int iters = 0, unstable = 0;
-  fail_rc(vbhem_em_run(h, tau, max_iter, min_diff, LogLs.data(), &iters, &unstable));
+  fail_rc(vbhem_multi_em_run(h, tau, max_iter, min_diff, LogLs.data(), &iters, &unstable));
 
   plhs[0] = mxCreateDoubleMatrix(1, K, mxREAL);
   plhs[1] = mxCreateDoubleMatrix(S, K, mxREAL);
@@ -89,7 +95,7 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
   }
   plhs[5] = mxCreateDoubleMatrix(S, K, mxREAL);
   plhs[6] = mxCreateDoubleMatrix(S, K, mxREAL);
-  fail_rc(vbhem_em_fetch(h, mxGetPr(plhs[0]), mxGetPr(plhs[1]), mxGetPr(plhs[2]), mxGetPr(plhs[3]), mxGetPr(plhs[4]),
+  fail_rc(vbhem_multi_em_fetch(h, mxGetPr(plhs[0]), mxGetPr(plhs[1]), mxGetPr(plhs[2]), mxGetPr(plhs[3]), mxGetPr(plhs[4]),
                          mxGetPr(plhs[5]), mxGetPr(plhs[6])));
   const int n = iters + (unstable ? 1 : 0);
   plhs[7] = mxCreateDoubleMatrix(1, n, mxREAL);

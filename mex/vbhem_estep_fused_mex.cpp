@@ -2,7 +2,11 @@
 //
 //   [L_elbo, hat_Z, Nj, Nj_rho1, Nj_rho2rho, Nj_rho, y_bar, S_plus_C, lb] = ...
 //       vbhem_estep_fused_mex(h3m_b.hmm, h3m_r.hmm, T, maxN, maxN2, tilde_N_k, logOmegaTilde ...
-//                             [, logdetCovPlusDdivlamR, invCovR])
+//                             [, logdetCovPlusDdivlamR, invCovR] [, ngpus])
+//
+// ngpus (optional last argument, scalar): the base HMMs are sharded over that many GPUs of the box and the
+// per-centre statistics all-reduced with NCCL inside the library (vbhem_multi_*); 0 = every visible GPU.  Without
+// it the call uses one GPU, as in round 1.
 //
 // One call replaces, per EM iteration of /root/reference/src/vbhem/vbhem_h3m_c_step_fc.m, the MEX call
 // (:175-176 / :193-194), the responsibilities (:271-283) and -- for all centres at once -- the statistics
@@ -18,12 +22,14 @@
 
 using namespace vbmex;
 
-static HandleCache g_cache;
+static MultiCache g_cache;
 
 void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
-  if (nrhs != 7 && nrhs != 9) mexErrMsgIdAndTxt("MyToolbox:arrayProduct:nrhs", "7 or 9 inputs required.");
+  if (nrhs < 7 || nrhs > 10) mexErrMsgIdAndTxt("MyToolbox:arrayProduct:nrhs", "7 or 9 inputs (+ ngpus) required.");
   if (nlhs != 9) mexErrMsgIdAndTxt("MyToolbox:arrayProduct:nlhs", "9 output required.");
-  const int covmode = nrhs == 9 ? VBHEM_COV_FULL : VBHEM_COV_DIAG;
+  const int covmode = nrhs >= 9 ? VBHEM_COV_FULL : VBHEM_COV_DIAG;
+  const bool has_ngpus = nrhs == 8 || nrhs == 10;
+  const int ngpus = has_ngpus ? (int)scalar_arg(prhs[nrhs - 1]) : 1;
   if (!mxIsCell(prhs[0])) mexErrMsgIdAndTxt("vbhem_mex:invalidinput", "1st arg must be cell");
   if (!mxIsCell(prhs[1])) mexErrMsgIdAndTxt("vbhem_mex:invalidinput", "2nd arg must be cell");
   const int T = (int)scalar_arg(prhs[2]);
@@ -39,16 +45,17 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
     mexErrMsgIdAndTxt("vbhem_mex:invalidinput", "tilde_N_k must have one entry per base HMM");
   if ((int)mxGetNumberOfElements(prhs[6]) != c.K)
     mexErrMsgIdAndTxt("vbhem_mex:invalidinput", "logOmegaTilde must have one entry per centre HMM");
-  vbhem_base_t *h = acquire(g_cache, b, mxGetPr(prhs[5]));
+  vbhem_multi_t *h = acquire_multi(g_cache, b, mxGetPr(prhs[5]), ngpus);
 
   const int Kb = b.N, Kr = c.K, d = b.d, dd = b.dd, r = maxN2;
   plhs[0] = mxCreateDoubleMatrix(Kb, Kr, mxREAL);
   plhs[1] = mxCreateDoubleMatrix(Kb, Kr, mxREAL);
   std::vector<double> stats(vbhem_stats_size(Kr, r, d, covmode, 1));
-  fail_rc(vbhem_estep(h, Kr, c.Sr.data(), r, nullptr, 1, T, c.logPi.data(), c.logA.data(), c.m.data(), c.vW.data(),
-                      c.cterm.data(), mxGetPr(prhs[6]), mxGetPr(plhs[0]), mxGetPr(plhs[1]), stats.data()));
+  fail_rc(vbhem_multi_estep(h, Kr, c.Sr.data(), r, nullptr, 1, T, c.logPi.data(), c.logA.data(), c.m.data(),
+                            c.vW.data(), c.cterm.data(), mxGetPr(prhs[6]), mxGetPr(plhs[0]), mxGetPr(plhs[1]),
+                            stats.data()));
   std::vector<double> lbraw(stats.end() - 2, stats.end());
-  fail_rc(vbhem_finalize_stats(h, Kr, c.Sr.data(), r, 1, stats.data()));
+  fail_rc(vbhem_multi_finalize_stats(h, Kr, c.Sr.data(), r, 1, stats.data()));
   size_t off[7];
   vbhem_stats_offsets(Kr, r, d, covmode, 1, off);
 

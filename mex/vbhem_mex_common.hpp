@@ -144,4 +144,37 @@ inline vbhem_base_t *acquire(HandleCache &c, const PackedBase &b, const double *
   return c.h;
 }
 
+// The same cache for a base set sharded over `ngpus` devices (vbhem_multi_*): ngpus <= 0 = every visible device
+// (never more than there are base HMMs).  One MATLAB session thereby drives all GPUs of the box -- what the
+// reference gets from `parfor` inside one session (/root/reference/src/vbhem/vbhem_h3m_c.m:28).
+struct MultiCache {
+  vbhem_multi_t *h = nullptr;
+  int N = 0, maxSb = 0, d = 0, covmode = -1, ngpus = 0;
+};
+
+inline int resolve_ngpus(int want, int N) {
+  int have = 0;
+  fail_rc(vbhem_device_count(&have));
+  int n = want > 0 ? want : have;
+  if (n > have) mexErrMsgIdAndTxt("vbhem_mex:invalidinput", "ngpus = %d, but %d CUDA devices are visible", want, have);
+  if (n > N) n = N;
+  return n < 1 ? 1 : n;
+}
+
+inline vbhem_multi_t *acquire_multi(MultiCache &c, const PackedBase &b, const double *Ntilde, int want_gpus) {
+  const int n = resolve_ngpus(want_gpus, b.N);
+  if (c.h && (c.N != b.N || c.maxSb != b.maxSb || c.d != b.d || c.covmode != b.covmode || c.ngpus != n)) {
+    vbhem_multi_free(c.h);
+    c.h = nullptr;
+  }
+  if (!c.h) {
+    fail_rc(vbhem_multi_pack_base(n, nullptr, n, 0, nullptr, b.N, b.Sb.data(), b.maxSb, b.d, b.covmode, b.prior.data(),
+                                  b.A.data(), b.mu.data(), b.cov.data(), Ntilde, &c.h));
+    c.N = b.N; c.maxSb = b.maxSb; c.d = b.d; c.covmode = b.covmode; c.ngpus = n;
+  } else {
+    fail_rc(vbhem_multi_repack_base(c.h, b.Sb.data(), b.prior.data(), b.A.data(), b.mu.data(), b.cov.data(), Ntilde));
+  }
+  return c.h;
+}
+
 }  // namespace vbmex

@@ -317,7 +317,7 @@ int shim_estep_fused(int Kb, const int *Sb, int maxSb, int d, int covmode,
   mxArray *c5, *c6;
   mxArray *hb = make_base_tree(Kb, Sb, maxSb, d, covmode, prior, A, mu, cov);
   mxArray *hr = make_centre_tree(Kr, Sr, maxSr, d, covmode, logPi, logA, m, W, v, cterm, &c5, &c6);
-  const mxArray *prhs[9];
+  const mxArray *prhs[10];
   mxArray *plhs[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   prhs[0] = hb; prhs[1] = hr;
   prhs[2] = dbl_scalar((double)T);
@@ -326,7 +326,10 @@ int shim_estep_fused(int Kb, const int *Sb, int maxSb, int d, int covmode,
   prhs[5] = dbl_matrix(Kb, 1, Ntilde, Kb, 0);
   prhs[6] = dbl_matrix(1, Kr, logOmega, 1, 0);
   prhs[7] = c5; prhs[8] = c6;
-  mexFunction(9, plhs, covmode ? 9 : 7, prhs);
+  int nrhs = covmode ? 9 : 7;
+  const char *ng = getenv("VBHEM_SHIM_NGPUS");     /* tests: the gateway's optional trailing `ngpus` argument */
+  if (ng && *ng) prhs[nrhs++] = dbl_scalar(atof(ng));
+  mexFunction(9, plhs, nrhs, prhs);
   double *outs[9] = {L_elbo, zhat, Nj, Nj_rho1, Nj_rho2rho, Nj_rho, y_bar, S_plus_C, lb};
   for (int k = 0; k < 9; k++)
     memcpy(outs[k], mxGetPr(plhs[k]), sizeof(double) * mxGetNumberOfElements(plhs[k]));
@@ -348,7 +351,7 @@ int shim_em_run(int Kb, const int *Sb, int maxSb, int d, int covmode,
   mxArray *hb = make_base_tree(Kb, Sb, maxSb, d, covmode, prior, A, mu, cov);
   mxArray *sr = mxCreateDoubleMatrix(1, (mwSize)Kr, mxREAL);
   for (int j = 0; j < Kr; j++) sr->pr[j] = Sr[j];
-  const mxArray *prhs[17];
+  const mxArray *prhs[18];
   mxArray *plhs[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   prhs[0] = hb;
   prhs[1] = dbl_scalar((double)maxSb);
@@ -367,7 +370,10 @@ int shim_em_run(int Kb, const int *Sb, int maxSb, int d, int covmode,
   prhs[14] = dbl_scalar((double)T);
   prhs[15] = dbl_scalar((double)max_iter);
   prhs[16] = dbl_scalar(min_diff);
-  mexFunction(9, plhs, 17, prhs);
+  int nrhs = 17;
+  const char *ng = getenv("VBHEM_SHIM_NGPUS");
+  if (ng && *ng) prhs[nrhs++] = dbl_scalar(atof(ng));
+  mexFunction(9, plhs, nrhs, prhs);
   double *outs[7] = {alpha, eta, eps, m, W, v, lam};
   for (int k = 0; k < 7; k++) memcpy(outs[k], mxGetPr(plhs[k]), sizeof(double) * mxGetNumberOfElements(plhs[k]));
   const size_t n = mxGetNumberOfElements(plhs[7]);

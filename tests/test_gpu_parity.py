@@ -455,3 +455,63 @@ def test_em_state_survives_other_esteps_on_the_handle():
     np.testing.assert_array_equal(got["LogLs"], want["LogLs"])
     for k in ("alpha", "eta", "m", "W"):
         np.testing.assert_array_equal(got["hyp"][k], want["hyp"][k])
+
+
+def _oracle_chunk(args):
+    """Worker of test_full_size_parity_report: the oracle's per-pair outputs for a chunk of bases (packed)."""
+    pbc, pc, tau = args
+    from oracle import cref
+    return cref.port_estep_pairs(pbc, pc, tau)
+
+
+def test_full_size_parity_report():
+    """at the BASELINE shape (N = 100 000 x K = 64, S = 8, tau = 10) compare 2 048 bases x 64
+    centres ELEMENT-WISE with the oracle -- L_elbo and z_hat from the full run, the reduced statistics and the
+    N-sized lower-bound terms from a fused E-step over the same sample -- and print the observed errors.
+    Nv = 100 multiplies every L_elbo error by 100 before the soft-max, which is what makes z_hat the sensitive one."""
+    import os
+    from concurrent.futures import ProcessPoolExecutor
+    from oracle import cref
+    from vbhem_b200 import pack, synth
+    from util import prepass_natural
+    N, K, tau = 100_000, 64, 10
+    base, hyp, _ = synth.north_star(N=N, K=K)
+    cen = prepass_natural(hyp, "full")
+    pb, pc = pack.pack_base(base), pack.pack_centres(cen)
+    idx = np.arange(0, N, N // 2048)[:2048]
+    with BaseSet(pb, packed=True) as bs:
+        full = bs.estep(pc, tau, packed=True, raw=True)               # packed [K, N] rows
+    sub = {k: (np.ascontiguousarray(v[idx]) if isinstance(v, np.ndarray) and v.shape[:1] == (N,) else v)
+           for k, v in pb.items()}
+    sub["N"] = len(idx)
+    nw = min(os.cpu_count() or 1, 16)
+    cuts = np.linspace(0, len(idx), nw + 1).astype(int)
+    chunks = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        c = {k: (np.ascontiguousarray(v[a:b]) if isinstance(v, np.ndarray) and v.shape[:1] == (len(idx),) else v)
+             for k, v in sub.items()}
+        c["N"] = int(b - a)
+        chunks.append((c, pc, tau))
+    with ProcessPoolExecutor(nw) as ex:
+        outs = list(ex.map(_oracle_chunk, chunks))
+    o = {k: np.concatenate([x[k] for x in outs], axis=1) for k in outs[0]}
+    zz = cref.port_zhat(o["L_elbo"], pc["logOmega"], sub["Ntilde"])
+    red = cref.port_reduce(zz["Z"], o, pc["maxSr"], 2, 1)
+    want = pack.stats_to_natural(dict(red, Nj=zz["Nj"], lb=zz["lb"]), 2, 1)
+    with BaseSet(sub, packed=True) as bs:
+        got = bs.estep(pc, tau, packed=True)
+    eL = np.max(np.abs(full["L_elbo"][:, idx] - o["L_elbo"]) / np.abs(o["L_elbo"]))
+    ez_abs = np.max(np.abs(full["zhat"][:, idx] - zz["zhat"]))
+    ez_rel = np.max(np.abs(full["zhat"][:, idx] - zz["zhat"]) / np.maximum(zz["zhat"], 1e-12))
+    es = {}
+    for k in ("nu1", "xi", "pr", "mu", "Mu"):
+        g, w = got[k], want[k]
+        scale = np.maximum(np.max(np.abs(w), axis=tuple(range(1, w.ndim)), keepdims=True), 1e-300)
+        es[k] = float(np.max(np.abs(g - w) / scale))
+    eNj = float(np.max(np.abs(got["Nj"] + 1e-50 - want["Nj"])) / np.max(want["Nj"]))
+    eLt1 = float(abs(got["lb"][0] - want["lb"][0]) / abs(want["lb"][0]))
+    print(f"\nfull-size parity (2048 of 100000 bases x 64 centres): L_elbo rel {eL:.2e}, zhat abs {ez_abs:.2e} "
+          f"rel(>=1e-12) {ez_rel:.2e}, Nj rel {eNj:.2e}, Lt1 rel {eLt1:.2e}, statistics {es}")
+    assert eL <= RTOL
+    np.testing.assert_allclose(full["zhat"][:, idx], zz["zhat"], rtol=RTOL, atol=1e-12)
+    assert eNj <= RTOL and eLt1 <= RTOL and max(es.values()) <= RTOL

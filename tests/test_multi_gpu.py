@@ -161,3 +161,26 @@ def test_one_process_per_device_with_caller_passed_id(tmp_path):
     for r in range(world):
         lo, hi = shard_bounds(1501, world, r)
         assert np.array_equal(outs[r]["L"], want["L_elbo"][lo:hi])
+
+
+def test_mex_gateways_take_ngpus(monkeypatch):
+    """The MEX gateways' optional trailing `ngpus` argument (mex/vbhem_estep_fused_mex.cpp, vbhem_em_run_mex.cpp;
+    matlab/*: vbhemopt.ngpus) shards the base set inside the library: same results as the one-GPU call."""
+    devs = two()
+    from oracle import cref
+    from vbhem_b200 import pack, synth
+    base, hyp, cen = make_case(N=700, K=5, Sb=4, Sr=4, d=2, covmode="full", ragged=True, seed=21, Nv=10.0)
+    pb, pc = pack.pack_base(base), pack.pack_centres(cen)
+    opt = dict(synth.DEFAULT_OPT, Nv=10.0, tau=5, max_iter=8, minDiff=1e-6)
+    monkeypatch.delenv("VBHEM_SHIM_NGPUS", raising=False)
+    one = cref.gateway_estep_fused(pb, pc, 5)
+    em1 = cref.gateway_em_run(pb, hyp, opt)
+    for ng in (str(len(devs)), "0"):                 # 0 = every visible GPU
+        monkeypatch.setenv("VBHEM_SHIM_NGPUS", ng)
+        two_ = cref.gateway_estep_fused(pb, pc, 5)
+        em2 = cref.gateway_em_run(pb, hyp, opt)
+        assert np.array_equal(two_["L_elbo"], one["L_elbo"]) and np.array_equal(two_["zhat"], one["zhat"])
+        for k in ("Nj", "Nj_rho1", "Nj_rho2rho", "Nj_rho", "y_bar", "S_plus_C", "lb"):
+            np.testing.assert_allclose(two_[k], one[k], rtol=1e-11, atol=1e-11 * np.abs(one[k]).max(), err_msg=k)
+        assert em2["iters"] == em1["iters"]
+        np.testing.assert_allclose(em2["LogLs"], em1["LogLs"], rtol=1e-10)
