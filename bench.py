@@ -358,6 +358,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        cpu_group = dist.new_group(backend="gloo")    # host-side waits: an NCCL barrier would spin on the waiting GPUs
         box = [MultiBaseSet.unique_id() if rank == 0 else None, MultiBaseSet.unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)                       # ids of the strong / weak communicators
         uid = box
@@ -630,6 +631,7 @@ def main():
     single = None
     if world > 1 and not a.no_extras and not grid:
         barrier()
+        dist.barrier(group=cpu_group)
         if rank == 0:
             with MultiBaseSet(pb0, devices=list(range(world)), packed=True) as m1:
                 P1 = m1.prepare_hyp(hyp)
@@ -655,7 +657,7 @@ def main():
                           LL_last=float(r1["LogLs"][-1]),
                           note="one host process, one thread per device inside the library (ncclCommInitAll): device "
                                "time of the slowest shard, E-step + all-reduce + normalisation")
-        barrier()
+        dist.barrier(group=cpu_group)                 # the other ranks wait on the host, their GPUs stay idle
 
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=W,
