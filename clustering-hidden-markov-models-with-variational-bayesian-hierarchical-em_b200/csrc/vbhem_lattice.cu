@@ -531,15 +531,23 @@ k_lattice_bwd(BaseView B, const double *__restrict__ rec_src, const int *__restr
   const int src0 = (2 * q) * 4 + (SP == 1 ? (g >> 2) * 2 : (SP == 2 ? (g < ksplit ? 0 : 3) : 0)), src1 = src0 + 4;
   const Split sp{2 * q < ksplit, 2 * q + 1 < ksplit, q == 0};
 
-  // Work unit = one base x kUnitCentres tiles: fine enough that the last wave of warps is nearly full even
-  // for a 12 500-base shard (8-GPU strong scaling), coarse enough that re-reading the base costs < 1 %
-  // (a smaller unit was measured slower: 4 tiles cost 4 % at 12 500 bases, the base loads are not hidden).
-  constexpr int unit_centres = kUnitCentres;
+  // Work unit = one base x kUnitCentres tiles (re-reading the base per unit costs < 1 %; smaller units were measured
+  // slower throughout: 4 tiles per unit cost 4 % at 12 500 bases).  What is left after the last FULL round of the
+  // grid's warps -- up to a whole round for a 12 500-base shard (8-GPU strong scaling), 4 % of its first pass -- is
+  // cut in quarter units, so the ragged end of the kernel is a quarter as long.  Warp ids are SM-interleaved
+  // (warp w of CTA b is number w * gridDim.x + b): the warps with one piece more than the others are spread evenly
+  // over the SMs instead of filling the first few.
+  constexpr int unit_centres = kUnitCentres, sub = kUnitCentres / 4;
+  static_assert(sub % kNP == 0 && sub >= kNP, "quarter units hold whole groups of pairs in flight");
   const int nuc = (nj + unit_centres - 1) / unit_centres;
   const long long nunits = (long long)(i1 - i0) * nuc, nw = (long long)gridDim.x * kBwdWarps;
-  for (long long u = (long long)blockIdx.x * kBwdWarps + warp; u < nunits; u += nw) {
-    const int i = i0 + (int)(u / nuc), jc = (int)(u % nuc) * unit_centres;
-    const int je = min(jc + unit_centres, nj);
+  const long long nfull = nunits / nw * nw, nwork = nfull + 4 * (nunits - nfull);
+  for (long long w = (long long)warp * gridDim.x + blockIdx.x; w < nwork; w += nw) {
+    long long u = w;
+    int t0 = 0, tn = unit_centres;
+    if (w >= nfull) { u = nfull + ((w - nfull) >> 2); t0 = (int)((w - nfull) & 3) * sub; tn = sub; }
+    const int i = i0 + (int)(u / nuc), ju = (int)(u % nuc) * unit_centres, jc = ju + t0;
+    const int je = min(min(ju + unit_centres, nj), jc + tn);
     BaseConst<D, FULL> b;
     load_base(b, B, i, g, q);
     const bool base_chk = base_bad(b.Ab, b.prior);
