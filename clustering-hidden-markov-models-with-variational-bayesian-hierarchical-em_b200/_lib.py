@@ -10,7 +10,9 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libvbhem_b200.so")
+# VBHEM_LIB: another build of the same library (e.g. the checked build with device-side assertions,
+# scripts/checked_build.sh); never a different implementation
+SO_PATH = os.environ.get("VBHEM_LIB") or os.path.join(HERE, "libvbhem_b200.so")
 
 dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int32)
@@ -46,6 +48,8 @@ SIGNATURES = {
     "vbhem_fetch": (C.c_int, [vp, dp, dp]),
     "vbhem_em_begin": (C.c_int, [vp, C.c_int, ip, C.c_int, ip, C.c_int, C.c_double, C.c_double, C.c_double,
                                  C.c_double, C.c_double, dp, dp, C.c_int, dp, dp, dp, dp, dp, dp, dp]),
+    "vbhem_em_begin_baseem": (C.c_int, [vp, C.c_int, ip, C.c_int, ip, C.c_int, C.c_double, C.c_double, C.c_double,
+                                        C.c_double, C.c_double, dp, dp, C.c_int, ip, ip, dp, C.c_double]),
     "vbhem_em_estep": (C.c_int, [vp, C.c_int, vp]),
     "vbhem_em_lower_bound": (C.c_int, [vp, vp, dp]),
     "vbhem_em_mstep": (C.c_int, [vp, vp]),
@@ -53,6 +57,10 @@ SIGNATURES = {
     "vbhem_em_run_groups": (C.c_int, [vp, C.c_int, C.c_int, C.c_double, dp, C.c_int, C.POINTER(C.c_int),
                                       C.POINTER(C.c_int)]),
     "vbhem_em_fetch": (C.c_int, [vp, dp, dp, dp, dp, dp, dp, dp]),
+    "vbhem_em_set_group_priors": (C.c_int, [vp, dp, dp, dp, dp, dp, dp, dp, C.c_int]),
+    "vbhem_em_lb_deriv": (C.c_int, [vp, dp]),
+    "vbhem_em_run_groups_deriv": (C.c_int, [vp, C.c_int, C.c_int, C.c_double, dp, C.c_int, C.POINTER(C.c_int),
+                                            C.POINTER(C.c_int), dp]),
     "vbhem_em_run": (C.c_int, [vp, C.c_int, C.c_int, C.c_double, dp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "vbhem_finalize_stats": (C.c_int, [vp, C.c_int, ip, C.c_int, C.c_int, dp]),
     "vbhem_finalize_stats_dev": (C.c_int, [vp, C.c_int, ip, C.c_int, C.c_int, vp]),

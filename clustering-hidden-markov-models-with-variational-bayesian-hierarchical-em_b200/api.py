@@ -213,6 +213,23 @@ class BaseSet:
                                    float(opt["lambda0"]), float(opt["v0"]), _d(m0), _d(W0), int(W0.size),
                                    _d(al), _d(et), _d(eps), _d(m), _d(Wp), _d(v), _d(lam)))
 
+    def em_begin_baseem(self, Sr, group, randb, randg, omega, opt: dict):
+        """``em_begin`` with the ``baseem`` initialisation built on the device (``vbhem_em_begin_baseem``) from draws:
+        Sr[K], group[K] (or None), randb / randg [K, maxS] 0-based, omega[K] normalised per H3M."""
+        c = np.ascontiguousarray
+        Sr = c(Sr, dtype=np.int32)
+        K, r = np.shape(randb)
+        grp = None if group is None else c(group, dtype=np.int32)
+        ng = int(grp.max()) + 1 if grp is not None else 1
+        self._em = dict(K=K, r=r, Sr=Sr, grp=grp, ng=ng)
+        m0 = c(np.asarray(opt["m0"], float).reshape(self.d))
+        W0 = c(np.atleast_1d(np.asarray(opt["W0"], float)))
+        rb, rg = c(randb, dtype=np.int32), c(randg, dtype=np.int32)
+        check(lib().vbhem_em_begin_baseem(self._h, K, _i(Sr), r, _i(grp), ng, float(opt["alpha0"]), float(opt["eta0"]),
+                                          float(opt["epsilon0"]), float(opt["lambda0"]), float(opt["v0"]), _d(m0),
+                                          _d(W0), int(W0.size), _i(rb), _i(rg), _d(c(omega, dtype=np.float64)),
+                                          float(opt["Nv"]) * self.N))
+
     def em_estep(self, tau: int, stats_dev: int | None = None):
         check(lib().vbhem_em_estep(self._h, tau, C.c_void_p(stats_dev or 0)))
 
@@ -254,6 +271,36 @@ class BaseSet:
                                         it.ctypes.data_as(C.POINTER(C.c_int)), bad.ctypes.data_as(C.POINTER(C.c_int))))
         return dict(LogLs=[LogLs[g, :it[g] + (1 if bad[g] else 0)].copy() for g in range(G)], iters=it,
                     unstable=bad.astype(bool), hyp=self.em_fetch())
+
+    def em_set_group_priors(self, opts: list):
+        """Every batched H3M under its own prior (``vbhem_em_set_group_priors``): one option dict per soft-max group
+        (alpha0, eta0, epsilon0, lambda0, v0, m0, W0 -- all W0 scalars or all d-vectors)."""
+        c = np.ascontiguousarray
+        G = self._em["ng"]
+        assert len(opts) == G
+        col = lambda k: c([float(o[k]) for o in opts])
+        m0 = c(np.stack([np.asarray(o["m0"], float).reshape(self.d) for o in opts]))
+        W0 = c(np.stack([np.atleast_1d(np.asarray(o["W0"], float)) for o in opts]))
+        check(lib().vbhem_em_set_group_priors(self._h, _d(col("alpha0")), _d(col("eta0")), _d(col("epsilon0")),
+                                              _d(col("lambda0")), _d(col("v0")), _d(m0), _d(W0), int(W0.shape[1])))
+
+    def em_lb_deriv(self) -> np.ndarray:
+        """[ngroups, 21] raw derivatives of the bound (``vbhem_em_lb_deriv``): alpha0, eta0, epsilon0, v0, lambda0,
+        W0[8], m0[8]."""
+        out = np.zeros((self._em["ng"], 21))
+        check(lib().vbhem_em_lb_deriv(self._h, _d(out)))
+        return out
+
+    def em_run_groups_deriv(self, tau: int, max_iter: int = 200, min_diff: float = 1e-5) -> dict:
+        """``em_run_groups`` + the derivatives of every group's bound at its breaking pass (``dLL`` [G, 21])."""
+        G, ld = self._em["ng"], max_iter + 2
+        LogLs, dLL = np.zeros((G, ld)), np.zeros((G, 21))
+        it, bad = np.zeros(G, np.int32), np.zeros(G, np.int32)
+        check(lib().vbhem_em_run_groups_deriv(self._h, tau, max_iter, min_diff, _d(LogLs), ld,
+                                              it.ctypes.data_as(C.POINTER(C.c_int)),
+                                              bad.ctypes.data_as(C.POINTER(C.c_int)), _d(dLL)))
+        return dict(LogLs=[LogLs[g, :it[g] + (1 if bad[g] else 0)].copy() for g in range(G)], iters=it,
+                    unstable=bad.astype(bool), dLL=dLL, hyp=self.em_fetch())
 
     def finalize(self, buf: np.ndarray, Sr, r: int, ng: int = 1) -> dict:
         """vbhem_compute_Statistics.m:57-82 on a raw stats buffer (e.g. after an all-reduce)."""

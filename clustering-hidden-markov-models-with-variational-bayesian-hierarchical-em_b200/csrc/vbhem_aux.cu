@@ -350,6 +350,7 @@ __global__ void k_list_scan_centres(int K, int nranges, const int *segcnt, int *
     ra += segcnt[j];
   }
   if (lane == 31) {
+    VB_ASSERT(ia >= 0);
     seg_start[K] = ia;
     totals[0] = ia;
     // the second pass cuts the list in nranges equal ranges, one warp's serial work each
@@ -389,6 +390,7 @@ k_list_fill(int N, int K, const double *zhat, const double *Ntilde, const int *o
       if (act) {
         int pos = seg_start[j] + offs[(size_t)blockIdx.x * K + j] + __popc(bal & ((1u << lane) - 1u));
         for (int w = 0; w < warp; w++) pos += wcnt[w][jj];
+        VB_ASSERT(pos >= seg_start[j] && pos < seg_start[j + 1] && (long long)pos < (long long)N * K);
         items[pos] = PairItem{i, j};
       }
     }
@@ -410,6 +412,7 @@ __global__ void k_partial_reduce(int K, int per, const int *seg_start, const int
   double s = 0.0;
   if (b > a) {
     const int w_hi = (b - 1) / ipr;
+    VB_ASSERT(ipr >= 1 && a >= 0 && b <= totals[0] && (long long)w_hi * ipr < (long long)totals[0]);
     for (int w = a / ipr; w <= w_hi; w++) s += partial[(size_t)(w + j) * per + q];
   }
   if (q < r) S_nu1[q + (size_t)r * j] = s;

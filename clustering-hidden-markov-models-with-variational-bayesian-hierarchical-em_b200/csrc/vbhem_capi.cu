@@ -159,7 +159,9 @@ struct vbhem_base {
     // hyp block), means, state counts | group starts -- so that ordinary E-steps on the same handle (which
     // overwrite the upload arena) cannot corrupt it.  `staged`: cen_d holds the pre-pass of THIS run's last E-step
     // (what vbhem_em_lower_bound reads); any other E-step on the handle clears it.
-    DevBuf hyp, ints, m, prior, lb, stats, frozen;
+    DevBuf hyp, ints, m, prior, lb, stats, frozen, draws, gprior, deriv;
+    std::vector<double> gprior_host;   // [G0][kGroupPrior] priors of every ORIGINAL group (empty: the handle's scalars)
+    bool gprior_on = false, iid_W0 = true;
     bool staged = false;
     double *h_lb = nullptr;   // pinned
   } em;
@@ -840,7 +842,8 @@ int vbhem_free_base(vbhem_base_t *h) {
   if (h->cout) { cudaStreamSynchronize(h->cout); cudaStreamDestroy(h->cout); }
   for (cudaEvent_t e : h->slice_ev) cudaEventDestroy(e);
   h->em.m.release(); h->em.prior.release(); h->em.lb.release(); h->em.stats.release(); h->em.frozen.release();
-  h->em.hyp.release(); h->em.ints.release(); h->fin_i.release();
+  h->em.hyp.release(); h->em.ints.release(); h->em.draws.release(); h->em.gprior.release(); h->em.deriv.release();
+  h->fin_i.release();
   if (h->em.h_lb) cudaFreeHost(h->em.h_lb);
   DevBuf *all[] = {&h->bSb, &h->bprior, &h->bA, &h->bmu, &h->bcov, &h->bNt, &h->up, &h->cen_d, &h->rec,
                    &h->L, &h->z, &h->flags, &h->fbcount, &h->Njp, &h->lbp, &h->cnt, &h->offs, &h->segs, &h->items,
@@ -1099,6 +1102,7 @@ int em_upload_state(vbhem_base *h, int K, const int32_t *Sr, int maxSr, const in
   CU(em.lb.ensure(sizeof(double) * 12 * ngroups));
   CU(em.stats.ensure(sizeof(double) * vbhem_stats_size(K, maxSr, d, h->B.covmode, ngroups)));
   HypPtrs p = carve_hyp(h, K, maxSr);
+  if (!alpha) return VBHEM_OK;                 // shapes only: the caller fills the hyper-parameters on the device
   CU(cudaMemcpyAsync(p.alpha, alpha, sizeof(double) * nK, cudaMemcpyHostToDevice, h->st));
   CU(cudaMemcpyAsync(p.eta, eta, sizeof(double) * nr, cudaMemcpyHostToDevice, h->st));
   CU(cudaMemcpyAsync(p.epsilon, epsilon, sizeof(double) * nrr, cudaMemcpyHostToDevice, h->st));
@@ -1161,6 +1165,64 @@ int vbhem_em_begin(vbhem_base_t *h, int K, const int32_t *Sr, int maxSr, const i
   rc = em_upload_state(h, K, Sr, maxSr, group, ngroups, alpha, eta, epsilon, m, W, v, lambda);   // synchronises
   if (rc) return rc;
   em.active = true;
+  em.gprior_on = false;
+  em.gprior_host.clear();
+  em.iid_W0 = nW0 == 1;
+  return VBHEM_OK;
+}
+
+// vbhem_em_begin with the `baseem` initialisation (/root/reference/src/vbhem/vbhemhmm_init.m:58-100) done on the
+// device from the resident base set: the caller draws the random indices (the reference's vbhemopt.prerand, :66-74)
+// and the kernel gathers / inverts.
+int vbhem_em_begin_baseem(vbhem_base_t *h, int K, const int32_t *Sr, int maxSr, const int32_t *group, int ngroups,
+                          double alpha0, double eta0, double epsilon0, double lambda0, double v0, const double *m0,
+                          const double *W0, int nW0, const int32_t *randb, const int32_t *randg, const double *omega,
+                          double Nv) {
+  CentreArgs a{};
+  a.K = K; a.maxSr = maxSr; a.ngroups = ngroups; a.tau = 1; a.Sr = Sr; a.group = group; a.hyp = true; a.resident = true;
+  int rc = check_common(h, a, true);
+  if (rc) return rc;
+  const int d = h->B.d;
+  if (!m0 || !W0 || (nW0 != 1 && nW0 != d))
+    return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: m0[d] and W0[1 or d] are required");
+  if (!(v0 > d - 1)) return fail(VBHEM_EINVAL, "v0 not large enough");
+  if (!randb || !randg || !omega) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: randb, randg, omega are required");
+  if (d > 8) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: device initialisation supports d <= 8");
+  if (ngroups > 4096) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: at most 4096 groups in a device EM run");
+  for (int j = 0; j < K; j++)
+    for (int k = 0; k < Sr[j]; k++) {
+      const int b = randb[k + (size_t)maxSr * j];
+      if (b < 0 || b >= h->B.N) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: randb(%d,%d) = %d outside the base set", k, j, b);
+      if (randg[k + (size_t)maxSr * j] < 0 || randg[k + (size_t)maxSr * j] >= h->B.maxSb)
+        return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: randg(%d,%d) outside 0..maxSb-1", k, j);
+    }
+  CU(cudaSetDevice(h->device));
+  auto &em = h->em;
+  em.alpha0 = alpha0; em.eta0 = eta0; em.epsilon0 = epsilon0; em.lambda0 = lambda0; em.v0 = v0;
+  CU(em.prior.ensure(sizeof(double) * 2 * d));
+  if (!em.h_lb) CU(cudaMallocHost(&em.h_lb, sizeof(double) * 12 * 4096));
+  std::vector<double> pr(2 * d);
+  for (int q = 0; q < d; q++) { pr[q] = m0[q]; pr[d + q] = 1.0 / W0[nW0 == 1 ? 0 : q]; }
+  CU(cudaMemcpyAsync(em.prior.p, pr.data(), sizeof(double) * 2 * d, cudaMemcpyHostToDevice, h->st));
+  rc = em_upload_state(h, K, Sr, maxSr, group, ngroups, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+  if (rc) return rc;
+  const size_t nr = (size_t)maxSr * K;
+  CU(em.draws.ensure(sizeof(int) * 2 * nr + sizeof(double) * K + 16));
+  int *db = em.draws.as<int>(), *dg = db + nr;
+  double *dom = reinterpret_cast<double *>(em.draws.as<char>() + ((sizeof(int) * 2 * nr + 15) / 16) * 16);
+  CU(cudaMemcpyAsync(db, randb, sizeof(int) * nr, cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(dg, randg, sizeof(int) * nr, cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(dom, omega, sizeof(double) * K, cudaMemcpyHostToDevice, h->st));
+  HypPtrs p = carve_hyp(h, K, maxSr);
+  const int *dSr = em.ints.as<int>();
+  launch_init_baseem(h->B, K, maxSr, dSr, dSr + K, ngroups, alpha0, eta0, epsilon0, lambda0, v0, Nv, db, dg, dom, p.alpha,
+                     p.eta, p.epsilon, em.m.as<double>(), p.W, p.v, p.lambda, h->st);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(h->st));            // the caller's index arrays may change next
+  em.active = true;
+  em.gprior_on = false;
+  em.gprior_host.clear();
+  em.iid_W0 = nW0 == 1;
   return VBHEM_OK;
 }
 
@@ -1190,6 +1252,7 @@ EmCtx em_ctx(vbhem_base *h, double *st) {
   E.K = K; E.maxSr = r; E.d = d; E.covmode = h->B.covmode; E.ngroups = ng; E.Sr = dSr; E.gstart = dgs;
   E.alpha0 = em.alpha0; E.eta0 = em.eta0; E.epsilon0 = em.epsilon0; E.lambda0 = em.lambda0; E.v0 = em.v0;
   E.m0 = em.prior.as<double>(); E.W0inv = E.m0 + d;
+  E.gprior = em.gprior_on ? em.gprior.as<double>() : nullptr;
   E.alpha = c.p.alpha; E.eta = c.p.eta; E.epsilon = c.p.epsilon; E.m = em.m.as<double>(); E.W = c.p.W;
   E.v = c.p.v; E.lambda = c.p.lambda;
   // pre-pass results of the E-step that produced these statistics (layout of stage_centres)
@@ -1259,6 +1322,66 @@ int vbhem_em_mstep(vbhem_base_t *h, double *stats_dev) {
   return VBHEM_OK;
 }
 
+namespace {
+// rows `groups[0..n)` of the host copy of the per-group priors -> the device (current group order)
+int em_upload_gpriors(vbhem_base *h, const int *groups, int n) {
+  auto &em = h->em;
+  if (em.gprior_host.empty()) { em.gprior_on = false; return VBHEM_OK; }
+  std::vector<double> sel((size_t)kGroupPrior * n);
+  for (int g = 0; g < n; g++)
+    memcpy(sel.data() + (size_t)kGroupPrior * g, em.gprior_host.data() + (size_t)kGroupPrior * groups[g],
+           sizeof(double) * kGroupPrior);
+  CU(cudaSetDevice(h->device));
+  CU(em.gprior.ensure(sizeof(double) * sel.size()));
+  CU(cudaMemcpyAsync(em.gprior.p, sel.data(), sizeof(double) * sel.size(), cudaMemcpyHostToDevice, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  em.gprior_on = true;
+  return VBHEM_OK;
+}
+
+// raw derivatives of the bound at the current (pre-M-step) state, per current group: out[g][kDerivStride] (HOST)
+int em_lb_deriv(vbhem_base *h, double *out) {
+  if (!h || !h->em.active) return fail(VBHEM_EINVAL, "vbhem_em_begin has not been called on this handle");
+  if (!h->em.staged) return fail(VBHEM_EINVAL, "vbhem_em_lb_deriv needs this run's own E-step: call vbhem_em_estep first");
+  CU(cudaSetDevice(h->device));
+  auto &em = h->em;
+  EmCtx c = em_ctx(h, em.stats.as<double>());
+  CU(em.deriv.ensure(sizeof(double) * kDerivStride * em.ngroups));
+  launch_lb_deriv(c.E, em.iid_W0, c.dOm, c.dPi, c.dA, c.dLam, em.deriv.as<double>(), h->st);
+  CU(cudaMemcpyAsync(out, em.deriv.p, sizeof(double) * kDerivStride * em.ngroups, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  CU(cudaGetLastError());
+  return VBHEM_OK;
+}
+}  // namespace
+
+int vbhem_em_set_group_priors(vbhem_base_t *h, const double *alpha0, const double *eta0, const double *epsilon0,
+                              const double *lambda0, const double *v0, const double *m0, const double *W0, int nW0) {
+  if (!h || !h->em.active) return fail(VBHEM_EINVAL, "vbhem_em_begin has not been called on this handle");
+  if (!alpha0 || !eta0 || !epsilon0 || !lambda0 || !v0 || !m0 || !W0)
+    return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: a prior array is NULL");
+  const int d = h->B.d, G = h->em.ngroups;
+  if (nW0 != 1 && nW0 != d) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: W0 must have 1 or d entries per group");
+  if (d > 8) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: per-group priors support d <= 8");
+  auto &em = h->em;
+  em.gprior_host.assign((size_t)kGroupPrior * G, 0.0);
+  std::vector<int> all(G);
+  for (int g = 0; g < G; g++) {
+    double *p = em.gprior_host.data() + (size_t)kGroupPrior * g;
+    if (!(v0[g] > d - 1)) return fail(VBHEM_EINVAL, "v0 not large enough");
+    p[0] = alpha0[g]; p[1] = eta0[g]; p[2] = epsilon0[g]; p[3] = lambda0[g]; p[4] = v0[g];
+    for (int q = 0; q < d; q++) { p[5 + q] = m0[q + (size_t)d * g]; p[13 + q] = 1.0 / W0[nW0 == 1 ? (size_t)g : q + (size_t)d * g]; }
+    all[g] = g;
+  }
+  em.iid_W0 = nW0 == 1;
+  return em_upload_gpriors(h, all.data(), G);
+}
+
+int vbhem_em_lb_deriv(vbhem_base_t *h, double *out) {
+  if (!out) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: out is NULL");
+  return em_lb_deriv(h, out);
+}
+
 int vbhem_em_fetch(vbhem_base_t *h, double *alpha, double *eta, double *epsilon, double *m, double *W, double *v,
                    double *lambda) {
   if (!h || !h->em.active) return fail(VBHEM_EINVAL, "vbhem_em_begin has not been called on this handle");
@@ -1292,6 +1415,8 @@ struct EmDriver {
                            const double *eta, const double *epsilon, const double *m, const double *W, const double *v,
                            const double *lambda) = 0;
   virtual int sync() = 0;
+  virtual int lb_deriv(double *out) = 0;                       // [current groups][kDerivStride]
+  virtual int select_priors(const int *groups, int n) = 0;     // per-group priors of these ORIGINAL groups, in order
 };
 
 struct SingleDriver : EmDriver {
@@ -1317,6 +1442,8 @@ struct SingleDriver : EmDriver {
     CU(cudaStreamSynchronize(h->st));
     return VBHEM_OK;
   }
+  int lb_deriv(double *out) override { return em_lb_deriv(h, out); }
+  int select_priors(const int *groups, int n) override { return em_upload_gpriors(h, groups, n); }
 };
 
 // vbhem_h3m_c_step_fc.m:115-433, one H3M: E-step, lower bound, relative-change test from the third pass on,
@@ -1357,8 +1484,10 @@ int em_run_one(EmDriver &D, int tau, int max_iter, double min_diff, double *LogL
 // to stopped groups the centre set is compacted to the running groups (the stopped ones wait in a host copy), so
 // the E-step's cost follows the work that is left; at the end the handle holds all groups again, in their
 // original order.  LogLs is [ngroups][ld], iters / unstable [ngroups].
+// dLL (may be null): [ngroups][kDerivStride], the derivatives of every group's bound with respect to the prior
+// hyper-parameters at its breaking pass (vbhem_h3m_c_step_fc.m:357-368: computed before that pass's M-step).
 int em_run_groups(EmDriver &D, int tau, int max_iter, double min_diff, double *LogLs, int ld, int *iters,
-                  int *unstable, int *ncompact_out) {
+                  int *unstable, int *ncompact_out, double *dLL = nullptr) {
   vbhem_base *h = D.first();
   if (!h || !h->em.active) return fail(VBHEM_EINVAL, "vbhem_em_begin has not been called on this handle");
   if (!LogLs || !iters || ld < max_iter + 2) return fail(VBHEM_EINVAL, "vbhem_mex:invalidinput: LogLs[ngroups][>= max_iter + 2], iters required");
@@ -1375,6 +1504,7 @@ int em_run_groups(EmDriver &D, int tau, int max_iter, double min_diff, double *L
   for (int g = 0; g < G; g++) cur_groups[g] = g;
   for (int j = 0; j < K0; j++) cmap[j] = j;
   HypHost full, cur;
+  std::vector<double> dbuf;
   bool compacted = false;
   int ncompact = 0;
   // current (possibly compacted) device state -> `full`, at the centres' original positions
@@ -1409,6 +1539,19 @@ int em_run_groups(EmDriver &D, int tau, int max_iter, double min_diff, double *L
       lastL[g] = L;
       if (do_break) stop[gc] = 1;                                          // the M-step still runs once more
     }
+    if (dLL) {
+      bool any = false;
+      for (int gc = 0; gc < Gc; gc++) any = any || (stop[gc] && !done[cur_groups[gc]]);
+      if (any) {
+        dbuf.resize((size_t)kDerivStride * Gc);
+        rc = D.lb_deriv(dbuf.data());
+        if (rc) return rc;
+        for (int gc = 0; gc < Gc; gc++)
+          if (stop[gc] && !done[cur_groups[gc]])
+            memcpy(dLL + (size_t)kDerivStride * cur_groups[gc], dbuf.data() + (size_t)kDerivStride * gc,
+                   sizeof(double) * kDerivStride);
+      }
+    }
     rc = D.mstep_masked(skip.data());
     if (rc) return rc;
     for (int gc = 0; gc < Gc; gc++)
@@ -1440,6 +1583,8 @@ int em_run_groups(EmDriver &D, int tau, int max_iter, double min_diff, double *L
     if (rc) return rc;
     cur_groups.swap(ngroups_list);
     cmap.swap(ncmap);
+    rc = D.select_priors(cur_groups.data(), (int)cur_groups.size());
+    if (rc) return rc;
     compacted = true;
     ncompact++;
   }
@@ -1448,6 +1593,10 @@ int em_run_groups(EmDriver &D, int tau, int max_iter, double min_diff, double *L
     if (rc) return rc;
     rc = D.upload_state(K0, Sr0.data(), r, had_groups ? grp0.data() : nullptr, G, full.alpha.data(), full.eta.data(),
                         full.eps.data(), full.m.data(), full.W.data(), full.v.data(), full.lam.data());
+    if (rc) return rc;
+    std::vector<int> all(G);
+    for (int g = 0; g < G; g++) all[g] = g;
+    rc = D.select_priors(all.data(), G);
     if (rc) return rc;
   }
   int rc = D.sync();
@@ -1465,6 +1614,18 @@ int vbhem_em_run(vbhem_base_t *h, int tau, int max_iter, double min_diff, double
   if (!h) return fail(VBHEM_EINVAL, "base handle is NULL");
   SingleDriver D(h);
   return em_run_one(D, tau, max_iter, min_diff, LogLs, iters, unstable);
+}
+
+int vbhem_em_run_groups_deriv(vbhem_base_t *h, int tau, int max_iter, double min_diff, double *LogLs, int ld,
+                              int *iters, int *unstable, double *dLL) {
+  if (!h) return fail(VBHEM_EINVAL, "base handle is NULL");
+  SingleDriver D(h);
+  int ncompact = 0;
+  int rc = em_run_groups(D, tau, max_iter, min_diff, LogLs, ld, iters, unstable, &ncompact, dLL);
+  if (rc) return rc;
+  if (ncompact) h->lastK = 0;
+  h->counters[6] = ncompact;
+  return VBHEM_OK;
 }
 
 int vbhem_em_run_groups(vbhem_base_t *h, int tau, int max_iter, double min_diff, double *LogLs, int ld, int *iters,

@@ -71,6 +71,26 @@ __device__ double logdet_lu(const double *W, int d) {
 constexpr int kLbThreads = 256;
 constexpr int kTerms = 10;
 
+// The prior of soft-max group g: the handle's scalars, or the group's own row (EmView::gprior).
+struct Prior { double a0, e0, p0, lam0, v0; const double *m0, *W0inv; };
+__device__ __forceinline__ Prior prior_of(const EmView &E, int g) {
+  if (E.gprior) {
+    const double *p = E.gprior + (size_t)kGroupPrior * g;
+    return Prior{p[0], p[1], p[2], p[3], p[4], p + 5, p + 13};
+  }
+  return Prior{E.alpha0, E.eta0, E.epsilon0, E.lambda0, E.v0, E.m0, E.W0inv};
+}
+
+__device__ double digamma_em(double x) {      // as in vbhem_aux.cu: recurrence to x >= 10, then the asymptotic series
+  if (!(x >= 0.0)) return NAN;
+  double r = 0.0;
+  while (x < 10.0) { r -= 1.0 / x; x += 1.0; }
+  const double f = 1.0 / (x * x);
+  const double ser = f * (1.0 / 12 - f * (1.0 / 120 - f * (1.0 / 252 - f * (1.0 / 240 - f * (1.0 / 132 -
+                     f * (691.0 / 32760 - f * (1.0 / 12)))))));
+  return r + log(x) - 0.5 / x - ser;
+}
+
 // Fixed-order block sum of kTerms values per thread; result valid in thread 0.
 __device__ void block_sum_terms(double (&t)[kTerms], double (*sh)[kTerms]) {
   for (int k = 0; k < kTerms; k++) sh[threadIdx.x][k] = t[k];
@@ -96,9 +116,10 @@ k_lower_bound(EmView E, const double *Nj, const double *lbsum, const double *log
   const int g = blockIdx.x;
   const int ja = E.gstart[g], jb = E.gstart[g + 1], Kg = jb - ja;
   const int r = E.maxSr, d = E.d, dd = E.covmode ? d * d : d;
-  const double a0 = E.alpha0, e0 = E.eta0, p0 = E.epsilon0, lam0 = E.lambda0, v0 = E.v0;
+  const Prior pr = prior_of(E, g);
+  const double a0 = pr.a0, e0 = pr.e0, p0 = pr.p0, lam0 = pr.lam0, v0 = pr.v0;
   double logdetW0inv = 0.0;
-  for (int q = 0; q < d; q++) logdetW0inv += log(E.W0inv[q]);
+  for (int q = 0; q < d; q++) logdetW0inv += log(pr.W0inv[q]);
   double lg0 = 0.0;
   for (int i = 1; i <= d; i++) lg0 += lgamma(0.5 * (v0 + 1.0 - i));
   const double cB = (d * (d - 1) / 4.0) * kLogPi;
@@ -139,13 +160,13 @@ k_lower_bound(EmView E, const double *Nj, const double *lbsum, const double *log
     if (E.covmode) for (int q = 0; q < dd; q++) Wm[q] = E.W[(size_t)dd * s + q];
     else for (int q = 0; q < d; q++) Wm[q + d * q] = E.W[(size_t)dd * s + q];
     double df[kMaxDim];
-    for (int q = 0; q < d; q++) df[q] = E.m[q + d * s] - E.m0[q];
+    for (int q = 0; q < d; q++) df[q] = E.m[q + d * s] - pr.m0[q];
     double mWm = 0.0, trW = 0.0;
     for (int a = 0; a < d; a++) {
       double u = 0.0;
       for (int b = 0; b < d; b++) u += Wm[a + d * b] * df[b];
       mWm += df[a] * u;
-      trW += E.W0inv[a] * Wm[a + d * a];
+      trW += pr.W0inv[a] * Wm[a + d * a];
     }
     double logdetW;
     if (E.covmode) logdetW = logdet_lu(Wm, d);
@@ -190,27 +211,28 @@ __global__ void k_mstep(EmView E, const double *Nj, const double *nu1, const dou
   const int r = E.maxSr, d = E.d, dd = E.covmode ? d * d : d;
   if (x >= E.K * r) return;
   const int k = x % r, j = x / r;
-  if (E.frozen) {          // batched EM runs: H3Ms that have converged keep their hyper-parameters
-    int g = 0;
+  int g = 0;
+  if (E.frozen || E.gprior) {
     while (g + 1 < E.ngroups && E.gstart[g + 1] <= j) g++;
-    if (E.frozen[g]) return;
+    if (E.frozen && E.frozen[g]) return;     // batched EM runs: H3Ms that have converged keep their hyper-parameters
   }
-  if (k == 0) alpha[j] = E.alpha0 + Nj[j];
+  const Prior P0 = prior_of(E, g);
+  if (k == 0) alpha[j] = P0.a0 + Nj[j];
   if (k >= E.Sr[j]) return;
   const size_t s = x;
-  const double R = pr[s], lam0 = E.lambda0;
-  eta[s] = E.eta0 + nu1[s];
+  const double R = pr[s], lam0 = P0.lam0;
+  eta[s] = P0.e0 + nu1[s];
   for (int c = 0; c < E.Sr[j]; c++) {
     const size_t o = k + r * (c + (size_t)r * j);
-    epsilon[o] = E.epsilon0 + xi[o];
+    epsilon[o] = P0.p0 + xi[o];
   }
   lambda[s] = lam0 + R;
-  v[s] = E.v0 + R + 1.0;
+  v[s] = P0.v0 + R + 1.0;
   double yb[kMaxDim], df[kMaxDim];
   for (int q = 0; q < d; q++) {
     yb[q] = ybar[k + r * (q + (size_t)d * j)];
-    df[q] = yb[q] - E.m0[q];
-    m[q + d * s] = (lam0 * E.m0[q] + R * yb[q]) / (lam0 + R);
+    df[q] = yb[q] - P0.m0[q];
+    m[q + d * s] = (lam0 * P0.m0[q] + R * yb[q]) / (lam0 + R);
   }
   const double mult1 = lam0 * R / (lam0 + R);
   double a[kMaxDim * kMaxDim];
@@ -218,7 +240,7 @@ __global__ void k_mstep(EmView E, const double *Nj, const double *nu1, const dou
     for (int b = 0; b < d; b++) {
       const double sc = E.covmode ? SC[k + r * ((b + d * c) + (size_t)dd * j)]
                                   : (b == c ? SC[k + r * (b + (size_t)dd * j)] : 0.0);
-      a[b + d * c] = (b == c ? E.W0inv[b] : 0.0) + R * sc + mult1 * df[b] * df[c];
+      a[b + d * c] = (b == c ? P0.W0inv[b] : 0.0) + R * sc + mult1 * df[b] * df[c];
     }
   invert(a, d);
   if (E.covmode) {
@@ -229,7 +251,138 @@ __global__ void k_mstep(EmView E, const double *Nj, const double *nu1, const dou
   }
 }
 
+// vbhemh3m_lb.m:202-309 for the H3M of softmax group blockIdx.x: out[g][0..4] = d LB / d {alpha0, eta0, epsilon0,
+// v0, lambda0}, [5..13) d / d W0 (iid: entry 5 only, W0 = w I), [13..21) d / d m0.  Ragged centres: every "K S" of
+// the reference becomes the sum over the centres of their own state counts, as in k_lower_bound.
+constexpr int kDTerms = 5 + 2 * kMaxDim;
+__global__ void __launch_bounds__(kLbThreads)
+k_lb_deriv(EmView E, int iid, const double *logOmega, const double *logPi, const double *logA, const double *logLam,
+           double *out) {
+  __shared__ double sh[kLbThreads][kDTerms];
+  pdl_trigger();
+  pdl_wait();
+  const int g = blockIdx.x;
+  const int ja = E.gstart[g], jb = E.gstart[g + 1], Kg = jb - ja;
+  const int r = E.maxSr, d = E.d, dd = E.covmode ? d * d : d;
+  const Prior pr = prior_of(E, g);
+  double t[kDTerms];
+  for (int k = 0; k < kDTerms; k++) t[k] = 0.0;
+  double logdetW0inv = 0.0, sps = 0.0;
+  for (int q = 0; q < d; q++) logdetW0inv += log(pr.W0inv[q]);
+  for (int i = 1; i <= d; i++) sps += digamma_em(0.5 * (pr.v0 + 1.0 - i));
+  const double dlogB0 = 0.5 * logdetW0inv - 0.5 * d * kLog2 - 0.5 * sps;       // d logB0 / d v0
+  for (int j = ja + threadIdx.x; j < jb; j += kLbThreads) {
+    const int S = E.Sr[j];
+    t[0] += logOmega[j];
+    double sP = 0.0, sA = 0.0;
+    for (int k = 0; k < S; k++) sP += logPi[k + (size_t)r * j];
+    for (int c = 0; c < S; c++)
+      for (int k = 0; k < S; k++) sA += logA[k + r * (c + (size_t)r * j)];
+    t[1] += S * digamma_em(S * pr.e0) - S * digamma_em(pr.e0) + sP;                       // :213-217
+    t[2] += S * (S * digamma_em(S * pr.p0) - S * digamma_em(pr.p0)) + sA;                 // :221-225
+  }
+  const int nst = Kg * r;
+  for (int x = threadIdx.x; x < nst; x += kLbThreads) {
+    const int j = ja + x / r, k = x % r;
+    if (k >= E.Sr[j]) continue;
+    const size_t s = k + (size_t)r * j;
+    const double lam = E.lambda[s], v = E.v[s];
+    double Wm[kMaxDim * kMaxDim];
+    for (int q = 0; q < d * d; q++) Wm[q] = 0.0;
+    if (E.covmode) for (int q = 0; q < dd; q++) Wm[q] = E.W[(size_t)dd * s + q];
+    else for (int q = 0; q < d; q++) Wm[q + d * q] = E.W[(size_t)dd * s + q];
+    double df[kMaxDim], Wdf[kMaxDim];
+    for (int q = 0; q < d; q++) df[q] = E.m[q + d * s] - pr.m0[q];
+    double mWm = 0.0;
+    for (int a = 0; a < d; a++) {
+      double u = 0.0;
+      for (int b = 0; b < d; b++) u += Wm[a + d * b] * df[b];
+      Wdf[a] = u;
+      mWm += df[a] * u;
+    }
+    t[3] += dlogB0 + 0.5 * logLam[s];                                                     // :229-230
+    t[4] += 0.5 * (d / pr.lam0 - d / lam - v * mWm);                                      // :233-241
+    if (iid) {                                                                            // :244-267
+      double tr = 0.0;
+      for (int a = 0; a < d; a++) tr += Wm[a + d * a];
+      t[5] += -0.5 * pr.v0 * d * pr.W0inv[0] + 0.5 * v * pr.W0inv[0] * pr.W0inv[0] * tr;
+    } else {                                                                              // :270-293
+      for (int a = 0; a < d; a++)
+        t[5 + a] += -0.5 * pr.v0 * pr.W0inv[a] + 0.5 * v * pr.W0inv[a] * pr.W0inv[a] * Wm[a + d * a];
+    }
+    for (int a = 0; a < d; a++) t[5 + kMaxDim + a] += pr.lam0 * v * Wdf[a];              // :300-309
+  }
+  for (int k = 0; k < kDTerms; k++) sh[threadIdx.x][k] = t[k];
+  __syncthreads();
+  for (int s2 = kLbThreads / 2; s2 > 0; s2 >>= 1) {
+    if ((int)threadIdx.x < s2)
+      for (int k = 0; k < kDTerms; k++) sh[threadIdx.x][k] += sh[threadIdx.x + s2][k];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    double *o = out + (size_t)kDerivStride * g;
+    for (int k = 0; k < kDTerms; k++) o[k] = sh[0][k];
+    o[0] += Kg * digamma_em(Kg * pr.a0) - Kg * digamma_em(pr.a0);                         // :205-209
+  }
+}
+
+// vbhemhmm_init.m:58-100 (`baseem`): thread x = (state k, centre j).  NLr = Nv / Kr of the centre's own H3M.
+__global__ void k_init_baseem(BaseView B, int K, int r, const int *Sr, const int *gstart, int ngroups, double alpha0,
+                              double eta0, double epsilon0, double lambda0, double v0, double Nv, const int *randb,
+                              const int *randg, const double *omega, double *alpha, double *eta, double *epsilon,
+                              double *m, double *W, double *v, double *lambda) {
+  pdl_trigger();
+  pdl_wait();
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= K * r) return;
+  const int k = x % r, j = x / r, d = B.d, dd = B.dd, ld = B.maxSb;
+  int g = 0;
+  while (g + 1 < ngroups && gstart[g + 1] <= j) g++;
+  const double NLr = Nv / (double)(gstart[g + 1] - gstart[g]);
+  const int s = Sr[j];
+  if (k == 0) alpha[j] = alpha0 + omega[j] * Nv;
+  const size_t st = x;
+  for (int c = 0; c < r; c++) epsilon[k + r * (c + (size_t)r * j)] = (k < s && c < s) ? (1.0 / s) * NLr / s + epsilon0 : 0.0;
+  if (k >= s) {
+    eta[st] = 0.0; v[st] = 0.0; lambda[st] = 0.0;
+    for (int q = 0; q < d; q++) m[q + d * st] = 0.0;
+    for (int q = 0; q < dd; q++) W[(size_t)dd * st + q] = 0.0;
+    return;
+  }
+  const double per = NLr / s, vv = v0 + per + 1.0;
+  eta[st] = (1.0 / s) * NLr + eta0;
+  lambda[st] = lambda0 + per;
+  v[st] = vv;
+  const size_t src = (size_t)randg[st] + (size_t)ld * randb[st];
+  for (int q = 0; q < d; q++) m[q + d * st] = B.mu[q + d * src];
+  if (B.covmode) {
+    double a[kMaxDim * kMaxDim];
+    for (int q = 0; q < dd; q++) a[q] = (vv - d - 1.0) * B.cov[(size_t)dd * src + q];
+    invert(a, d);
+    for (int q = 0; q < dd; q++) W[(size_t)dd * st + q] = a[q];
+  } else {
+    for (int q = 0; q < d; q++) W[(size_t)dd * st + q] = 1.0 / ((vv - d - 1.0) * B.cov[(size_t)dd * src + q]);
+  }
+}
+
 }  // namespace
+
+int launch_init_baseem(const BaseView &B, int K, int maxSr, const int *Sr, const int *gstart, int ngroups, double alpha0,
+                       double eta0, double epsilon0, double lambda0, double v0, double Nv, const int *randb,
+                       const int *randg, const double *omega, double *alpha, double *eta, double *epsilon, double *m,
+                       double *W, double *v, double *lambda, cudaStream_t st) {
+  const int tot = K * maxSr;
+  launch_chain(k_init_baseem, dim3((tot + 127) / 128), dim3(128), 0, st, B, K, maxSr, Sr, gstart, ngroups, alpha0, eta0,
+               epsilon0, lambda0, v0, Nv, randb, randg, omega, alpha, eta, epsilon, m, W, v, lambda);
+  return 1;
+}
+
+int launch_lb_deriv(const EmView &E, bool iid, const double *logOmega, const double *logPi, const double *logA,
+                    const double *logLam, double *out, cudaStream_t st) {
+  static_assert(kDTerms == kDerivStride, "derivative layout");
+  launch_chain(k_lb_deriv, dim3(E.ngroups), dim3(kLbThreads), 0, st, E, iid ? 1 : 0, logOmega, logPi, logA, logLam, out);
+  return 1;
+}
 
 int launch_lower_bound(const EmView &E, const double *Nj, const double *lbsum, const double *logOmega,
                        const double *logPi, const double *logA, const double *logLam, double *out, cudaStream_t st) {

@@ -250,6 +250,7 @@ k_general(BaseView B, CentreView C, int T, PairWork W, PairOut O, unsigned char 
     for (long long u = warp; u < np; u += nwarps) {
       const int i = i0 + (int)(u % ni), j = (int)(u / ni);
       const long long p = i + (long long)B.N * j;
+      VB_ASSERT(i >= 0 && i < B.N && j >= 0 && j < C.K);
       if (flags && !flags[p]) continue;
       const double L = pair_general(B, C, T, i, j, s, ro, O.mode != 0, lane);
       if (lane == 0 && O.L_elbo) O.L_elbo[p] = L;
@@ -270,6 +271,8 @@ k_general(BaseView B, CentreView C, int T, PairWork W, PairOut O, unsigned char 
       for (int e = e0; e < e1; e++) {
         if (flags && !flags[e]) continue;
         const PairItem it = W.items[e];
+        VB_ASSERT((long long)e < W.npairs && it.i >= 0 && it.i < B.N && it.j >= 0 && it.j < C.K &&
+                  w + it.j < W.nranges + C.K);
         if (it.j != jcur) {
           jcur = it.j;
           part = O.partial + (size_t)O.per * (w + jcur);

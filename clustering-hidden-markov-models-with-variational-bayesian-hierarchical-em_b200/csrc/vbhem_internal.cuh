@@ -5,6 +5,17 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Checked build (csrc/build.sh -DVBHEM_CHECKED -o ..._checked.so): device-side bounds assertions on every index
+// the kernels compute from device-resident counts (list positions, partial slots, pair indices).  compute-sanitizer
+// is closed on the GPU pool this was developed on (profiles/README.md), so this is the memcheck stand-in: the
+// parity tests run once under the checked library (scripts/checked_build.sh).
+#ifdef VBHEM_CHECKED
+#include <cassert>
+#define VB_ASSERT(x) assert(x)
+#else
+#define VB_ASSERT(x) ((void)0)
+#endif
+
 namespace vbhem {
 
 constexpr double kTwoPi = 6.283185307179586476925286766559;
@@ -180,15 +191,33 @@ struct EmView {
   double alpha0, eta0, epsilon0, lambda0, v0;
   const double *m0;       // [d]
   const double *W0inv;    // [d] diagonal of inv(W0)
+  // Per-group priors (hyper-parameter learning evaluates every batched H3M under its OWN candidate prior,
+  // /root/reference/src/vbhem/vbhem_h3m_c_hyp.m:105-129): null, or [ngroups][kGroupPrior] =
+  // alpha0, eta0, epsilon0, lambda0, v0, m0[8], W0inv[8]; overrides the scalars above.
+  const double *gprior;
   const double *alpha, *eta, *epsilon, *m, *W, *v, *lambda;
 };
+constexpr int kGroupPrior = 5 + 8 + 8;
+// doubles per group of launch_lb_deriv's output: d/d alpha0, eta0, epsilon0, v0, lambda0, W0[8] (iid: entry 0), m0[8]
+constexpr int kDerivStride = 5 + 8 + 8;
 // out[g][12]: Lt1..Lt10, LB, sum_j Nj of softmax group g (vbhemh3m_lb.m:64-186)
 int launch_lower_bound(const EmView &E, const double *Nj, const double *lbsum, const double *logOmega,
                        const double *logPi, const double *logA, const double *logLam, double *out, cudaStream_t st);
+// vbhemh3m_lb.m:202-309: derivatives of the bound with respect to the prior hyper-parameters at the current
+// (pre-M-step) state, per group; iid: W0 is a scalar (the d x d identity times it).  out[g][kDerivStride]
+int launch_lb_deriv(const EmView &E, bool iid, const double *logOmega, const double *logPi, const double *logA,
+                    const double *logLam, double *out, cudaStream_t st);
 // vbhem_mstep_component.m:42-70 in place on the hyper-parameter arrays, from the normalised statistics
 int launch_mstep(const EmView &E, const double *Nj, const double *nu1, const double *xi, const double *pr,
                  const double *ybar, const double *SC, double *alpha, double *eta, double *epsilon, double *m,
                  double *W, double *v, double *lambda, cudaStream_t st);
+
+// `baseem` initialisation (vbhemhmm_init.m:58-100) on the device: centre state (k, j) copies the emission of base
+// state (randb, randg); arrays in the layouts of vbhem_estep_hyp
+int launch_init_baseem(const BaseView &B, int K, int maxSr, const int *Sr, const int *gstart, int ngroups, double alpha0,
+                       double eta0, double epsilon0, double lambda0, double v0, double Nv, const int *randb,
+                       const int *randg, const double *omega, double *alpha, double *eta, double *epsilon, double *m,
+                       double *W, double *v, double *lambda, cudaStream_t st);
 
 // fp64 peak micro-benchmark (vbhem_aux.cu): out[0] DMMA, out[1] DFMA TFLOP/s; returns 0 on success
 int measure_fp64_peak(double out[2]);

@@ -579,6 +579,7 @@ k_lattice_bwd(BaseView B, const double *__restrict__ rec_src, const int *__restr
         const int tile = jj + (lane & 1), slot = SP ? 2 * tile + ((lane >> 1) & 1) : tile;
         const int j = (lane < 2 * CPT && tile < nj) ? sidx[slot] : -1;
         const size_t pi = (size_t)i + (size_t)B.N * (j < 0 ? 0 : j);
+        VB_ASSERT(j < 0 || (i >= i0 && i < i1 && i < B.N && slot < CPT * kc && j < (1 << 30)));
         if (j >= 0) L_elbo[pi] = Lt[0];
         if (!all_ok) {
 #pragma unroll
@@ -774,6 +775,7 @@ k_lattice_full(BaseView B, CentreView C, int T, PairWork W, PairOut O, Fallback 
     const double *rec = nullptr;
     PairStats<D, FULL> acc{};
     auto flush = [&]() {
+      VB_ASSERT(jcur >= 0 && jcur < C.K && w + jcur < W.nranges + C.K);
       double *part = O.partial + (size_t)O.per * (w + jcur);
       double *p_nu1 = part, *p_xi = part + ro, *p_pr = p_xi + ro * ro, *p_mu = p_pr + ro, *p_Mu = p_mu + ro * D;
       if (g < ro) {
@@ -791,6 +793,7 @@ k_lattice_full(BaseView B, CentreView C, int T, PairWork W, PairOut O, Fallback 
     };
     for (int e = e0; e < e1; e++) {
       const PairItem it = W.items[e];
+      VB_ASSERT(e >= 0 && (long long)e < W.npairs && it.i >= 0 && it.i < B.N && it.j >= jcur && it.j < C.K);
       if (it.j != jcur) {
         if (jcur >= 0) flush();
         jcur = it.j;

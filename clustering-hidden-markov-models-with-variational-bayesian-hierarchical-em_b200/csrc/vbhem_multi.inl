@@ -278,6 +278,10 @@ struct MultiDriver : EmDriver {
       return VBHEM_OK;
     });
   }
+  int lb_deriv(double *out) override { return em_lb_deriv(m->h[0], out); }   // identical on every shard
+  int select_priors(const int *groups, int n) override {
+    return m->run_all([&](int k) { return em_upload_gpriors(m->h[k], groups, n); });
+  }
 };
 
 }  // namespace

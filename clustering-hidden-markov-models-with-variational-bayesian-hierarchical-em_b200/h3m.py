@@ -184,6 +184,18 @@ def vbhemh3m_lb_deriv(pre: dict, hyp: dict, opt: dict, covmode: str = "full", cl
         D["W0"] = K * S * (-0.5 * v0 * w0inv) - 0.5 * (-(v[..., None]) * w0inv ** 2 * diagW).sum((0, 1))
         myW0 = 1.0 / w0inv
     D["m0"] = lam0 * np.einsum("ks,ksij,ksj->i", v, W, df)                                                     # :300-309
+    return transform_derivs(D, opt, clipped)
+
+
+def transform_derivs(D: dict, opt: dict, clipped: dict | None = None) -> dict:
+    """vbhemh3m_lb.m:312-339: raw derivatives D[name] (alpha0, eta0, epsilon0, v0, lambda0, W0, m0; from the host
+    formulas above or from the device, ``BaseSet.em_lb_deriv``) -> zeroed where a clipped hyper-parameter would move
+    further out, then chained through the optimiser's transforms."""
+    d = len(np.atleast_1d(opt["m0"]))
+    a0, e0, p0 = float(opt["alpha0"]), float(opt["eta0"]), float(opt["epsilon0"])
+    lam0, v0 = float(opt["lambda0"]), float(opt["v0"])
+    myW0 = np.atleast_1d(np.asarray(opt["W0"], float))
+    D = {k: np.array(np.atleast_1d(v), float) for k, v in D.items()}
     for name, c in (clipped or {}).items():                                                                    # :312-327
         if name in D:
             g = D[name]
@@ -194,6 +206,13 @@ def vbhemh3m_lb_deriv(pre: dict, hyp: dict, opt: dict, covmode: str = "full", cl
                 d_logv0D1=D["v0"] * (v0 - d + 1), d_sqrtv0D1=D["v0"] * 2 * np.sqrt(v0 - d + 1),
                 d_loglambda0=D["lambda0"] * lam0, d_sqrtlambda0=D["lambda0"] * 2 * np.sqrt(lam0),
                 d_sqrtW0inv=D["W0"] * myW0 ** 1.5 * (-2), d_logW0=D["W0"] * myW0, d_m0=D["m0"], raw=D)
+
+
+def device_derivs_to_dict(row: np.ndarray, d: int, nW0: int) -> dict:
+    """One row of ``BaseSet.em_lb_deriv`` / ``em_run_groups_deriv`` ([21]: alpha0, eta0, epsilon0, v0, lambda0, W0[8],
+    m0[8]) -> the raw-derivative dict of ``transform_derivs``."""
+    return dict(alpha0=row[0:1], eta0=row[1:2], epsilon0=row[2:3], v0=row[3:4], lambda0=row[4:5],
+                W0=row[5:5 + nW0], m0=row[13:13 + d])
 
 
 def vbhem_h3m_c_step_fc(h3m_r: dict, base, vbhemopt: dict, covmode: str = "full", estep=None, verbose: int = 0,
@@ -510,8 +529,11 @@ def vbhem_h3m_cluster(hmms, K, S, vbhemopt: dict | None = None, covmode: str = "
         raise ValueError(f"vbhemopt.m0 should have dimension D={d}")
     Ks, Ss = [int(k) for k in np.atleast_1d(K)], [int(s) for s in np.atleast_1d(S)]
     trials = int(opt["trials"])
-    cand, models = [], []
+    cand, models, shapes = [], [], []
     clock = [time.perf_counter()]
+    # 'baseem' (vbhemhmm_init.m:58-100) is built on the device for all candidates at once (vbhem_em_begin_baseem);
+    # only the random draws are made here, vectorised
+    device_init = opt["initmode"] == "baseem"
     for ki, k in enumerate(Ks):
         for si, s in enumerate(Ss):
             for t in range(trials):
@@ -519,6 +541,10 @@ def vbhem_h3m_cluster(hmms, K, S, vbhemopt: dict | None = None, covmode: str = "
                 # here the trials alternate between them, which the best-trial rule then compares
                 mode = opt["initmode"] if opt["initmode"] != "auto" else ("baseem", "wtkmeans")[t % 2]
                 cand.append((ki, si, t))
+                shapes.append((k, s))
+                if device_init:      # the same draws as init_centres_baseem(seed + t + 1); gather / inverse on the device
+                    models.append(synth.baseem_draws(base, k, s, seed=int(opt["seed"]) + t + 1))
+                    continue
                 if mode == "baseem":
                     models.append(synth.init_centres_baseem(base, k, s, seed=int(opt["seed"]) + t + 1, opt=opt))
                 else:   # wtseed = seed + it (vbhem_h3m_c.m:50-52)
@@ -527,23 +553,26 @@ def vbhem_h3m_cluster(hmms, K, S, vbhemopt: dict | None = None, covmode: str = "
     N = base["mu"].shape[0]
     with BaseSet(base, device=device) as bs:
         # batches of at most 4096 H3Ms (vbhem_em_begin's limit) and 2e8 (base, centre) pairs (3.2 GB of L_elbo + z_hat)
-        finals, iters_all = [None] * len(models), np.zeros(len(models), int)
+        finals, iters_all = [None] * len(shapes), np.zeros(len(shapes), int)
         LL = np.full((len(Ks), len(Ss), trials), -np.inf)
         lo = 0
-        while lo < len(models):
+        while lo < len(shapes):
             hi, ncen = lo, 0
-            while hi < len(models) and hi - lo < 4096 and (hi == lo or (ncen + models[hi]["eta"].shape[0]) * N <= 2e8):
-                ncen += models[hi]["eta"].shape[0]
+            while hi < len(shapes) and hi - lo < 4096 and (hi == lo or (ncen + shapes[hi][0]) * N <= 2e8):
+                ncen += shapes[hi][0]
                 hi += 1
-            hyp, group = stack_h3ms(models[lo:hi])
-            bs.em_begin(hyp, opt, group=group)
+            if device_init:
+                bs.em_begin_baseem(*synth.stack_draws(models[lo:hi]), opt)
+            else:
+                hyp, group = stack_h3ms(models[lo:hi])
+                bs.em_begin(hyp, opt, group=group)
             run = bs.em_run_groups(int(opt["tau"]), int(opt["max_iter"]), float(opt["minDiff"]))
-            first = np.concatenate([[0], np.cumsum([m["eta"].shape[0] for m in models[lo:hi]])])
+            first = np.concatenate([[0], np.cumsum([k for k, _ in shapes[lo:hi]])])
             for g in range(hi - lo):
                 ki, si, t = cand[lo + g]
                 if len(run["LogLs"][g]) and not run["unstable"][g]:
                     LL[ki, si, t] = run["LogLs"][g][-1]
-                finals[lo + g] = _slice_h3m(run["hyp"], slice(int(first[g]), int(first[g + 1])), models[lo + g]["eta"].shape[1])
+                finals[lo + g] = _slice_h3m(run["hyp"], slice(int(first[g]), int(first[g + 1])), shapes[lo + g][1])
                 iters_all[lo + g] = run["iters"][g]
             lo = hi
         clock.append(time.perf_counter())
@@ -551,12 +580,14 @@ def vbhem_h3m_cluster(hmms, K, S, vbhemopt: dict | None = None, covmode: str = "
         LL_ks = np.take_along_axis(LL, best_t[:, :, None], 2)[:, :, 0]
         learnt = {}
         if opt["learn_hyps"]:                                                # vbhem_h3m_c.m:105-150
-            for ki in range(len(Ks)):
-                for si in range(len(Ss)):
-                    res = vbhem_h3m_c_hyp(finals[cand.index((ki, si, int(best_t[ki, si])))], bs, opt, covmode)
-                    if np.isfinite(res["LL"]) and res["LL"] > LL_ks[ki, si]:
-                        learnt[(ki, si)] = res
-                        LL_ks[ki, si] = res["LL"]
+            # the best trial of every (K, S) candidate; all their optimisers advance together (one batched EM loop
+            # per round of evaluations)
+            keys = [(ki, si) for ki in range(len(Ks)) for si in range(len(Ss))]
+            starts = [finals[cand.index((ki, si, int(best_t[ki, si])))] for ki, si in keys]
+            for (ki, si), res in zip(keys, vbhem_h3m_c_hyp_batch(starts, bs, opt, covmode)):
+                if np.isfinite(res["LL"]) and res["LL"] > LL_ks[ki, si]:
+                    learnt[(ki, si)] = res
+                    LL_ks[ki, si] = res["LL"]
         LL_S = LL_ks + gammaln(np.array(Ss) + 1.0)[None]                     # vbhem_h3m_cluster.m:327-331
         best_s = LL_S.argmax(1)
         LL_K = LL_ks[np.arange(len(Ks)), best_s] + gammaln(np.array(Ks) + 1.0)   # :279-283 (the run's own LL)
@@ -651,3 +682,115 @@ def vbhem_h3m_c_hyp(h3m_init: dict, base, vbhemopt: dict, covmode: str = "full",
     final["learn_hyps"] = dict(opt_transhyp=res.x, opt_L=float(-res.fun), vbopt=opt2, evals=np.array(evals),
                                hypnames=[h["optname"] for h in info])
     return final
+
+
+def vbhem_h3m_c_hyp_batch(inits: list, bs, vbhemopt: dict, covmode: str = "full", max_evals: int = 100,
+                          history: int = 8) -> list:
+    """``vbhem_h3m_c_hyp`` for MANY trials at once (vbhem_h3m_c.m:109-138 runs one optimiser per distinct trial, one
+    after the other; every evaluation of an optimiser's objective is a whole EM run, vbhem_h3m_c_hyp.m:105-129).
+
+    All trials' optimisers advance in lock-step: in every round each still-running trial proposes one point (its
+    prior hyper-parameters in the transformed coordinates of ``vbhem_get_hypinfo``), the EM runs of all proposals are
+    the soft-max groups of ONE batched device loop under per-group priors (``vbhem_em_set_group_priors`` +
+    ``vbhem_em_run_groups_deriv``), and value and gradient come back per group -- the gradient from the device
+    (``k_lb_deriv``), taken at the breaking pass as in vbhem_h3m_c_step_fc.m:357-368.  The optimiser is L-BFGS with
+    Armijo backtracking (own code, vectorised over nothing: a few dozen numbers per trial); the reference's is
+    ``minimize_new`` with 100 evaluations.  ``inits``: centre hyper-parameter dicts (their (K, S) may differ);
+    ``bs``: the resident ``BaseSet``.  Returns, per trial, the best evaluation's run (hyp, LogLs, LL, iters) plus
+    ``learn_hyps = dict(opt_transhyp, opt_L, vbopt, evals, hypnames)`` like ``vbhem_h3m_c_hyp``."""
+    opt = dict(vbhemopt)
+    lh = opt.get("learn_hyps", 1)
+    names = ["alpha0", "eta0", "epsilon0", "v0", "lambda0", "W0", "m0"] if not isinstance(lh, (list, tuple)) else list(lh)
+    info = vbhem_get_hypinfo(names, opt)
+    d = bs.d
+    nW0 = np.atleast_1d(opt["W0"]).size
+    tau, max_iter, min_diff = int(opt["tau"]), int(opt.get("max_iter", 200)), float(opt.get("minDiff", 1e-5))
+
+    def set_vbopt(X):
+        o, i = dict(opt), 0
+        for h in info:
+            val = h["hyptrans"](np.asarray(X[i:i + h["hypdims"]], float))
+            o[h["optname"]] = float(val[0]) if h["hypdims"] == 1 and h["optname"] not in ("m0", "W0") else val
+            i += h["hypdims"]
+        return o
+
+    X0 = np.concatenate([np.atleast_1d(h["hypinvtrans"](np.asarray(opt[h["optname"]], float))).ravel() for h in info])
+    n = len(inits)
+    st = [dict(x=X0.copy(), f=None, g=None, S=[], Y=[], p=None, t=1.0, tries=0, evals=[], done=False, best=None,
+               xtry=X0.copy()) for _ in range(n)]
+
+    def evaluate(idx, Xs):
+        """objective and gradient of trials idx at points Xs: one batched EM loop"""
+        opts, clips = zip(*[vbhem_clip_hyps(set_vbopt(X)) for X in Xs])
+        hyp, group = stack_h3ms([inits[i] for i in idx])
+        bs.em_begin(hyp, opt, group=group)
+        bs.em_set_group_priors(list(opts))
+        run = bs.em_run_groups_deriv(tau, max_iter, min_diff)
+        first = np.concatenate([[0], np.cumsum([inits[i]["eta"].shape[0] for i in idx])])
+        out = []
+        for g, i in enumerate(idx):
+            LL = run["LogLs"][g][-1] if len(run["LogLs"][g]) and not run["unstable"][g] else -np.inf
+            dl = transform_derivs(device_derivs_to_dict(run["dLL"][g], d, nW0), opts[g], clips[g])
+            grad = -np.concatenate([np.atleast_1d(dl[h["derivname"]]).ravel() for h in info])
+            res = dict(hyp=_slice_h3m(run["hyp"], slice(int(first[g]), int(first[g + 1])), inits[i]["eta"].shape[1]),
+                       LogLs=run["LogLs"][g], LL=float(LL), iters=int(run["iters"][g]), unstable=bool(run["unstable"][g]),
+                       vbopt=opts[g])
+            ok = np.isfinite(LL)
+            out.append((-LL if ok else 1e300, np.where(np.isfinite(grad), grad, 0.0) if ok else np.zeros_like(grad), res))
+        return out
+
+    def direction(s):
+        q, al = s["g"].copy(), []
+        for sv, yv in zip(reversed(s["S"]), reversed(s["Y"])):
+            a = float(sv @ q) / float(yv @ sv)
+            al.append(a)
+            q -= a * yv
+        if s["S"]:
+            q *= float(s["S"][-1] @ s["Y"][-1]) / float(s["Y"][-1] @ s["Y"][-1])
+        for (sv, yv), a in zip(zip(s["S"], s["Y"]), reversed(al)):
+            q += (a - float(yv @ q) / float(yv @ sv)) * sv
+        return -q
+
+    active = list(range(n))
+    for s, (f, g, res) in zip(st, evaluate(active, [s["x"] for s in st])):
+        s.update(f=f, g=g, best=res)
+        s["evals"].append(-f)
+        s["p"] = -g
+        s["t"] = min(1.0, 1.0 / max(np.abs(g).sum(), 1e-300))
+        s["done"] = not np.isfinite(res["LL"]) or np.abs(g).max() < 1e-9
+    used = 1
+    while used < max_evals:
+        active = [i for i in range(n) if not st[i]["done"]]
+        if not active:
+            break
+        for i in active:
+            st[i]["xtry"] = st[i]["x"] + st[i]["t"] * st[i]["p"]
+        ev = evaluate(active, [st[i]["xtry"] for i in active])
+        used += 1
+        for i, (f, g, res) in zip(active, ev):
+            s = st[i]
+            s["evals"].append(-f)
+            slope = float(s["g"] @ s["p"])
+            if f <= s["f"] + 1e-4 * s["t"] * slope:                       # Armijo: accept
+                sv, yv = s["xtry"] - s["x"], g - s["g"]
+                rel = abs(s["f"] - f) / max(abs(s["f"]), 1e-300)
+                if float(yv @ sv) > 1e-12 * float(yv @ yv):
+                    s["S"].append(sv)
+                    s["Y"].append(yv)
+                    s["S"], s["Y"] = s["S"][-history:], s["Y"][-history:]
+                s.update(x=s["xtry"].copy(), f=f, g=g, best=res, t=1.0, tries=0)
+                s["p"] = direction(s)
+                if float(s["g"] @ s["p"]) >= 0:                            # not a descent direction: restart
+                    s["S"], s["Y"], s["p"] = [], [], -g
+                s["done"] = rel < 1e-9 or np.abs(g).max() < 1e-9
+            else:                                                          # backtrack
+                s["t"] *= 0.5
+                s["tries"] += 1
+                s["done"] = s["tries"] >= 25
+    out = []
+    for s in st:
+        res = dict(s["best"])
+        res["learn_hyps"] = dict(opt_transhyp=s["x"], opt_L=float(-s["f"]), vbopt=res.pop("vbopt"),
+                                 evals=np.array(s["evals"]), hypnames=[h["optname"] for h in info])
+        out.append(res)
+    return out

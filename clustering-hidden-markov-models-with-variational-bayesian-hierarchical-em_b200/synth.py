@@ -82,47 +82,95 @@ def make_base_set(N, S=8, d=2, C=64, covmode="full", seed=1001, Nv=100.0, ragged
     return base, lab
 
 
-def init_centres_baseem(base, K, S, seed=1001, opt=DEFAULT_OPT, Sr=None):
-    """``baseem`` initialisation (vbhemhmm_init.m:58-100) -> centre hyper-parameter dict:
+def baseem_draws(base, K, S, seed=1001, Sr=None):
+    """The random draws of one ``baseem`` initialisation (vbhemhmm_init.m:66-74, :91-92), in the order the per-centre
+    loop makes them: (Sr[K], randb[K,S] base index, randg[K,S] state index -- both 0-based, -1 beyond a centre's own
+    states --, omega[K] normalised)."""
+    rng = np.random.Generator(np.random.PCG64(seed + 7))
+    N = base["mu"].shape[0]
+    Sr = np.full(K, S, dtype=np.int32) if Sr is None else np.asarray(Sr, dtype=np.int32)
+    Sb = base["Sb"]
+    randb, randg = -np.ones((K, S), np.int32), -np.ones((K, S), np.int32)
+    for j in range(K):
+        s = int(Sr[j])
+        rb = rng.integers(0, N, size=s)
+        randb[j, :s] = rb
+        randg[j, :s] = rng.integers(0, Sb[rb])          # the stream of one scalar draw per state, vectorised
+    omega = rng.uniform(size=K)
+    return Sr, randb, randg, omega / omega.sum()
+
+
+def stack_draws(draws):
+    """Draws of several ``baseem`` initialisations (``baseem_draws`` tuples) -> the arguments of
+    ``BaseSet.em_begin_baseem``: (Sr[Kt], group[Kt], randb[Kt,maxS], randg[Kt,maxS], omega[Kt])."""
+    maxS = max(d[1].shape[1] for d in draws)
+    pad = lambda a: np.pad(np.maximum(a, 0), ((0, 0), (0, maxS - a.shape[1])))
+    group = np.repeat(np.arange(len(draws), dtype=np.int32), [len(d[0]) for d in draws])
+    return (np.concatenate([d[0] for d in draws]).astype(np.int32), group, np.concatenate([pad(d[1]) for d in draws]),
+            np.concatenate([pad(d[2]) for d in draws]), np.concatenate([d[3] for d in draws]))
+
+
+def baseem_draws_batch(base, models, seed):
+    """The draws of MANY ``baseem`` initialisations at once, vectorised (one generator for the whole batch):
+    ``models`` = [(K, S), ...] -> (Sr[Kt], group[Kt], randb[Kt,maxS], randg[Kt,maxS], omega[Kt] normalised per model),
+    the arguments of ``BaseSet.em_begin_baseem``."""
+    rng = np.random.Generator(np.random.PCG64(seed + 7))
+    N = base["mu"].shape[0]
+    Ks = np.array([k for k, _ in models])
+    Ss = np.array([s for _, s in models])
+    group = np.repeat(np.arange(len(models), dtype=np.int32), Ks)
+    Sr = np.repeat(Ss, Ks).astype(np.int32)
+    Kt, maxS = int(Ks.sum()), int(Ss.max())
+    randb = rng.integers(0, N, size=(Kt, maxS)).astype(np.int32)
+    randg = np.floor(rng.uniform(size=(Kt, maxS)) * np.asarray(base["Sb"])[randb]).astype(np.int32)
+    live = np.arange(maxS)[None, :] < Sr[:, None]
+    randb[~live], randg[~live] = 0, 0
+    omega = rng.uniform(size=Kt)
+    omega /= np.bincount(group, weights=omega)[group]
+    return Sr, group, randb, randg, omega
+
+
+def baseem_from_draws(base, Sr, randb, randg, omega, opt=DEFAULT_OPT, group=None):
+    """``baseem`` initialisation (vbhemhmm_init.m:58-100) from given draws -> centre hyper-parameter dict:
     alpha[K], eta[K,S], epsilon[K,S,S], m[K,S,d], W[K,S,d,d]|[K,S,d], v[K,S], lam[K,S], Sr[K].
 
     Each centre state copies the emission of a random base state:
     lambda = lambda0 + NLr/S, v = v0 + NLr/S + 1, m = centres, W = inv((v-d-1) covars);
     eta = prior*NLr + eta0, epsilon = A*NLr/S + epsilon0 with uniform prior / A
-    (``makeAprior`` in its default mode), alpha = alpha0 + omega*Nv with random omega.
+    (``makeAprior`` in its default mode), alpha = alpha0 + omega*Nv with random omega; NLr = Nv / (centres of the
+    same H3M): ``group`` batches several H3Ms.
     """
-    rng = np.random.Generator(np.random.PCG64(seed + 7))
     N, Sb_max, d = base["mu"].shape
     full = base["cov"].ndim == 4
+    Sr = np.asarray(Sr, dtype=np.int32)
+    K, S = randb.shape
+    group = np.zeros(K, np.int32) if group is None else np.asarray(group)
     Nv = opt["Nv"] * N
-    NLr = Nv / K
-    Sr = np.full(K, S, dtype=np.int32) if Sr is None else np.asarray(Sr, dtype=np.int32)
-    lam = np.zeros((K, S)); v = np.zeros((K, S)); m = np.zeros((K, S, d))
+    NLr = Nv / np.bincount(group)[group]                                    # [K]
+    live = np.arange(S)[None, :] < Sr[:, None]
+    per = (NLr / Sr)[:, None]
+    lam = np.where(live, opt["lambda0"] + per, 0.0)
+    v = np.where(live, opt["v0"] + per + 1.0, 0.0)
+    eta = np.where(live, (1.0 / Sr)[:, None] * NLr[:, None] + opt["eta0"], 0.0)
+    eps = np.where(live[:, :, None] & live[:, None, :], ((1.0 / Sr) * NLr / Sr)[:, None, None] + opt["epsilon0"], 0.0)
+    jj, kk = np.nonzero(live)
+    bb, gg = randb[jj, kk], randg[jj, kk]
+    m = np.zeros((K, S, d))
     W = np.zeros((K, S, d, d)) if full else np.zeros((K, S, d))
-    eta = np.zeros((K, S)); eps = np.zeros((K, S, S))
-    Sb = base["Sb"]
-    jj, kk, bb, gg = [], [], [], []
-    for j in range(K):                       # the random draws, in the order the per-centre loop always made them
-        s = int(Sr[j])
-        rb = rng.integers(0, N, size=s)
-        rg = [rng.integers(0, Sb[b]) for b in rb]
-        jj += [j] * s; kk += range(s); bb += rb.tolist(); gg += rg
-        eta[j, :s] = (1.0 / s) * NLr + opt["eta0"]
-        eps[j, :s, :s] = (1.0 / s) * NLr / s + opt["epsilon0"]
-    jj, kk, bb, gg = (np.asarray(x, int) for x in (jj, kk, bb, gg))
-    per = NLr / Sr[jj]
-    lam[jj, kk] = opt["lambda0"] + per
-    v[jj, kk] = opt["v0"] + per + 1.0
     m[jj, kk] = base["mu"][bb, gg]
     c = base["cov"][bb, gg]
     if full:
         W[jj, kk] = np.linalg.inv((v[jj, kk, None, None] - d - 1.0) * c)
     else:
         W[jj, kk] = 1.0 / ((v[jj, kk, None] - d - 1.0) * c)
-    omega = rng.uniform(size=K)
-    omega /= omega.sum()
     alpha = opt["alpha0"] + omega * Nv
     return dict(Sr=Sr, alpha=alpha, eta=eta, epsilon=eps, m=m, W=W, v=v, lam=lam)
+
+
+def init_centres_baseem(base, K, S, seed=1001, opt=DEFAULT_OPT, Sr=None):
+    """``baseem`` initialisation of one H3M: ``baseem_from_draws(baseem_draws(...))``."""
+    Sr, randb, randg, omega = baseem_draws(base, K, S, seed, Sr)
+    return baseem_from_draws(base, Sr, np.maximum(randb, 0), np.maximum(randg, 0), omega, opt)
 
 
 def north_star(N=100_000, K=64, S=8, d=2, seed=1001, covmode="full"):

@@ -215,12 +215,40 @@ int vbhem_em_begin(vbhem_base_t *base, int K, const int32_t *Sr, int maxSr, cons
                    double alpha0, double eta0, double epsilon0, double lambda0, double v0, const double *m0,
                    const double *W0, int nW0, const double *alpha, const double *eta, const double *epsilon,
                    const double *m, const double *W, const double *v, const double *lambda);
+/* vbhem_em_begin with the toolbox's `baseem` initialisation (/root/reference/src/vbhem/vbhemhmm_init.m:58-100) done on
+ * the device from the resident base set, for every batched H3M at once: centre state (k, j) copies the emission of
+ * base state randg[k,j] of base HMM randb[k,j] (both [maxSr,K] int32, 0-BASED; the reference's vbhemopt.prerand,
+ * :66-74, or the caller's own randi draws), lambda = lambda0 + NLr/Sr, v = v0 + NLr/Sr + 1, m = centres,
+ * W = inv((v - d - 1) covars), eta = NLr/Sr + eta0, epsilon = NLr/Sr^2 + epsilon0 (makeAprior's uniform mode),
+ * alpha = alpha0 + omega Nv with omega[K] the caller's normalised rand draws, NLr = Nv / Kr of the centre's own H3M,
+ * Nv = vbhemopt.Nv * Kb.  Continue with vbhem_em_run[_groups] / vbhem_em_fetch. */
+int vbhem_em_begin_baseem(vbhem_base_t *base, int K, const int32_t *Sr, int maxSr, const int32_t *group, int ngroups,
+                          double alpha0, double eta0, double epsilon0, double lambda0, double v0, const double *m0,
+                          const double *W0, int nW0, const int32_t *randb, const int32_t *randg, const double *omega,
+                          double Nv);
 int vbhem_em_estep(vbhem_base_t *base, int tau, double *stats_dev);
 int vbhem_em_lower_bound(vbhem_base_t *base, double *stats_dev, double *lb_out);
 int vbhem_em_mstep(vbhem_base_t *base, double *stats_dev);
 int vbhem_em_mstep_masked(vbhem_base_t *base, double *stats_dev, const unsigned char *frozen);
 int vbhem_em_fetch(vbhem_base_t *base, double *alpha, double *eta, double *epsilon, double *m, double *W, double *v,
                    double *lambda);
+/* Batched hyper-parameter learning (/root/reference/src/vbhem/vbhem_h3m_c_hyp.m:105-129: every evaluation of the
+ * optimiser's objective is a whole EM run under candidate prior hyper-parameters; vbhem_h3m_c.m:109-138 runs one
+ * optimiser per trial, one after the other).  Here every batched H3M (soft-max group) can run under its OWN prior, so
+ * the evaluations of all trials' optimisers are the groups of ONE vbhem_em_run_groups_deriv call:
+ *   vbhem_em_set_group_priors  after vbhem_em_begin[_baseem]: alpha0[G], eta0[G], epsilon0[G], lambda0[G], v0[G],
+ *                              m0[d,G], W0[nW0,G] (nW0 = 1: W0 = w I, else its diagonal); replaces the common prior
+ *                              of vbhem_em_begin in the lower bound and the M-step until the next vbhem_em_begin
+ *   vbhem_em_lb_deriv          d LB / d (alpha0, eta0, epsilon0, v0, lambda0, W0[8], m0[8]) of every group at the
+ *                              current state (vbhemh3m_lb.m:202-309, before the transforms of :330-339), after
+ *                              vbhem_em_estep: out[G][21] (HOST)
+ *   vbhem_em_run_groups_deriv  vbhem_em_run_groups that also returns those derivatives taken at every group's
+ *                              breaking pass, before that pass's M-step (vbhem_h3m_c_step_fc.m:357-368): dLL[G][21] */
+int vbhem_em_set_group_priors(vbhem_base_t *base, const double *alpha0, const double *eta0, const double *epsilon0,
+                              const double *lambda0, const double *v0, const double *m0, const double *W0, int nW0);
+int vbhem_em_lb_deriv(vbhem_base_t *base, double *out);
+int vbhem_em_run_groups_deriv(vbhem_base_t *base, int tau, int max_iter, double min_diff, double *LogLs, int ld,
+                              int *iters, int *unstable, double *dLL);
 int vbhem_em_run(vbhem_base_t *base, int tau, int max_iter, double min_diff, double *LogLs, int *iters,
                  int *unstable);
 int vbhem_em_run_groups(vbhem_base_t *base, int tau, int max_iter, double min_diff, double *LogLs, int ld, int *iters,

@@ -224,3 +224,27 @@ def test_model_selection_grid_layout():
         assert len(sel) == K and (hyp["Sr"][sel] == S).all()
         assert (hyp["eta"][sel, :S] > 0).all() and not hyp["eta"][sel, S:].any()
     assert (np.diff(grp) >= 0).all() and grp[0] == 0 and grp[-1] == 8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("covmode", ["full", "diag"])
+def test_device_baseem_initialisation_equals_host(covmode):
+    """vbhem_em_begin_baseem (vbhemhmm_init.m:58-100 on the device, several H3Ms at once) against the numpy
+    restatement on the same draws; then the batched EM runs proceed from it."""
+    from vbhem_b200.api import BaseSet
+    base, _ = synth.make_base_set(90, S=4, d=2, C=3, covmode=covmode, seed=5, Nv=OPT["Nv"], ragged=True)
+    shapes = [(1, 1), (2, 3), (3, 4), (2, 2)]
+    Sr, group, randb, randg, omega = synth.baseem_draws_batch(base, shapes, seed=17)
+    opt = dict(synth.DEFAULT_OPT, Nv=OPT["Nv"], tau=5)
+    want = synth.baseem_from_draws(base, Sr, randb, randg, omega, opt, group=group)
+    with BaseSet(base) as bs:
+        bs.em_begin_baseem(Sr, group, randb, randg, omega, opt)
+        got = bs.em_fetch()
+        run = bs.em_run_groups(5, 6, 1e-5)
+        bs.em_begin(want, opt, group=group)
+        ref = bs.em_run_groups(5, 6, 1e-5)
+    for k in ("alpha", "eta", "epsilon", "m", "v", "lam"):
+        np.testing.assert_array_equal(got[k], want[k], err_msg=k)
+    np.testing.assert_allclose(got["W"], want["W"], rtol=1e-13)
+    for a, b in zip(run["LogLs"], ref["LogLs"]):
+        np.testing.assert_allclose(a, b, rtol=1e-10)

@@ -241,7 +241,8 @@ def test_cluster_with_wtkmeans_and_auto_init():
     runs = {mode: h3m.vbhem_h3m_cluster(base, [2, 3], 3, dict(common, initmode=mode)) for mode in ("baseem", "wtkmeans", "auto")}
     for out in runs.values():
         assert np.isfinite(out["LL"]) and out["Z"].shape == (90, out["K"]) and out["group_size"].sum() == 90
-    np.testing.assert_allclose(runs["auto"]["trials_LL"][:, :, 0::2], runs["baseem"]["trials_LL"][:, :, 0::2], rtol=1e-12)
+    # 'baseem' alone is initialised on the device, the baseem trials of 'auto' on the host: equal up to the last bit of W
+    np.testing.assert_allclose(runs["auto"]["trials_LL"][:, :, 0::2], runs["baseem"]["trials_LL"][:, :, 0::2], rtol=1e-9)
     np.testing.assert_allclose(runs["auto"]["trials_LL"][:, :, 1::2], runs["wtkmeans"]["trials_LL"][:, :, 1::2], rtol=1e-12)
     assert runs["auto"]["LL"] >= min(runs["baseem"]["LL"], runs["wtkmeans"]["LL"]) - 1e-9 * abs(runs["auto"]["LL"])
 

@@ -103,3 +103,56 @@ def test_cluster_with_learn_hyps():
     assert learnt["learn_hyps"]["hypnames"] == ["alpha0", "v0", "lambda0"]
     assert learnt["vbhemopt"]["v0"] != fixed["vbhemopt"]["v0"]
     assert learnt["Z"].shape == (60, learnt["K"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("W0", [0.005, (0.004, 0.007)])
+def test_device_derivatives_match_host_formulas(W0):
+    """k_lb_deriv (vbhemh3m_lb.m:202-309 on the device, one block per batched H3M, each under its OWN prior) against
+    the host restatement ``vbhemh3m_lb_deriv`` evaluated group by group."""
+    from vbhem_b200.api import BaseSet
+    base, _ = synth.make_base_set(80, S=3, d=2, C=3, seed=4, Nv=15.0, ragged=True)
+    opt = dict(synth.DEFAULT_OPT, Nv=15.0, tau=5, W0=W0)
+    models = [synth.init_centres_baseem(base, k, s, seed=30 + k, opt=opt) for k, s in ((2, 3), (3, 2), (1, 1))]
+    opts = [dict(opt, alpha0=1.0 + 0.5 * g, eta0=0.7 + g, epsilon0=1.3, lambda0=0.5 + g, v0=4.0 + g,
+                 m0=(250.0 + 10 * g, 190.0 - 5 * g), W0=np.asarray(W0) * (1 + g)) for g in range(3)]
+    hyp, group = h3m.stack_h3ms(models)
+    with BaseSet(base) as bs:
+        bs.em_begin(hyp, opt, group=group)
+        bs.em_set_group_priors(opts)
+        bs.em_estep(5)
+        lb = bs.em_lower_bound()
+        got = bs.em_lb_deriv()
+        for g, (mdl, o) in enumerate(zip(models, opts)):
+            st = bs.estep_hyp(mdl, 5)
+            pre = {k: st[k] for k in ("logOmega", "logPi", "logA", "logLambdaTilde")}
+            want = h3m.vbhemh3m_lb_deriv(pre, mdl, o)["raw"]
+            row = h3m.device_derivs_to_dict(got[g], 2, np.atleast_1d(W0).size)
+            for k in want:
+                np.testing.assert_allclose(row[k], want[k], rtol=1e-9, atol=1e-9 * max(1.0, np.abs(want[k]).max()), err_msg=f"{g}:{k}")
+            fin = bs.finalize(st["buf"], mdl["Sr"], mdl["eta"].shape[1])
+            L, _ = h3m.vbhemh3m_lb(st["lb"][0], st["lb"][1], fin["Nj"], pre, mdl, o)
+            np.testing.assert_allclose(lb[g, 10], L, rtol=1e-10)          # the bound under the group's own prior
+
+
+@pytest.mark.gpu
+def test_batched_hyper_parameter_learning():
+    """vbhem_h3m_c_hyp_batch: the optimisers of several trials in lock-step, every round of evaluations one batched EM
+    loop; each trial's bound rises, and a trial's result does not depend on what it is batched with."""
+    from vbhem_b200.api import BaseSet
+    base, _ = synth.make_base_set(60, S=2, d=2, C=2, seed=21, Nv=20.0)
+    opt = dict(h3m.CLUSTER_DEFAULTS, Nv=20.0, tau=5, max_iter=40, seed=3, learn_hyps=["alpha0", "v0", "lambda0", "m0"])
+    inits = [synth.init_centres_baseem(base, k, 2, seed=50 + k, opt=opt) for k in (1, 2, 3)]
+    with BaseSet(base) as bs:
+        plain = []
+        for h0 in inits:
+            bs.em_begin(h0, opt)
+            plain.append(bs.em_run(5, 40, 1e-5)["LogLs"][-1])
+        together = h3m.vbhem_h3m_c_hyp_batch(inits, bs, opt, max_evals=15)
+        alone = h3m.vbhem_h3m_c_hyp_batch(inits[1:2], bs, opt, max_evals=15)[0]
+    for res, L0 in zip(together, plain):
+        assert abs(res["learn_hyps"]["evals"][0] - L0) <= 1e-9 * abs(L0)      # first evaluation = the given hyps
+        assert res["LL"] > L0
+        assert res["learn_hyps"]["hypnames"] == ["alpha0", "v0", "lambda0", "m0"]
+    np.testing.assert_allclose(alone["LL"], together[1]["LL"], rtol=1e-12)
+    np.testing.assert_allclose(alone["learn_hyps"]["opt_transhyp"], together[1]["learn_hyps"]["opt_transhyp"], rtol=1e-9)
