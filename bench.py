@@ -65,7 +65,8 @@ def make_config(a, world, grid=False, K=None, models=None):
                bases_total=a.bases, centres=K, states=a.states, dim=a.dim, tau=a.tau, Nv=100,
                pairs_per_step=a.bases * K,
                parallelism=f"strong scaling: bases sharded x{world} ({a.bases // world} per GPU), centres replicated, "
-                           "one all-reduce of the per-centre statistics inside the C ABI (vbhem_multi_*)",
+                           "one all-reduce of the per-centre statistics inside the C ABI (vbhem_multi_*: over NVLink "
+                           "peer memory, NCCL where peers cannot be mapped)",
                l2="flushed between timed steps (256 MiB write)")
     if models is not None:
         cfg["models"] = models
@@ -393,8 +394,18 @@ def main():
         return out
 
     def make_set(pb_shard, which):
-        return MultiBaseSet(pb_shard, devices=[local], packed=True, world=world, rank_first=rank,
-                            unique_id=None if uid is None else uid[which])
+        ms_ = MultiBaseSet(pb_shard, devices=[local], packed=True, world=world, rank_first=rank,
+                           unique_id=None if uid is None else uid[which])
+        if dist is not None:      # all-reduce over peer memory: the ranks exchange the IPC handles of their exchange areas
+            try:
+                mine = ms_.peer_export()
+            except Exception:     # noqa: BLE001  (no peer access on this box: NCCL stays in charge)
+                mine = None
+            handles = [None] * world
+            dist.all_gather_object(handles, mine)
+            if all(h is not None for h in handles):
+                ms_.peer_import(handles)
+        return ms_
 
     def timed_run(ms, P, steps, warm, profile=False):
         """The timed region: `steps` E-steps (+ all-reduce + normalisation), each timed on the device with the
@@ -433,6 +444,7 @@ def main():
     pbs = shard_of(pb0, rank)
     ms = make_set(pbs, 0)
     P = ms.prepare_hyp(hyp, grp)
+    allreduce_mode = ms.allreduce_mode()
     tot_ms, _, launches, clocks, counters = timed_run(ms, P, a.steps, W)
     nprof = max(3, min(a.steps, 10))
     prof_ms, ph, _, _, _ = timed_run(ms, P, nprof, 1, profile=True)
@@ -663,7 +675,7 @@ def main():
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=W,
                     ms_per_step=tot_ms / a.steps, higher_is_better=True, scaling="strong", vs_baseline=None,
                     dtype="f64", data="synthetic", config=config, clocks=clocks, e2e=e2e, gpu_launches=int(launches),
-                    roofline=roofline, phases=phases, placement=placement)
+                    roofline=roofline, phases=phases, placement=placement, allreduce=allreduce_mode)
         for k, v in (("cpu_baseline", cpu), ("parity", parity), ("vbhem_iter", vbhem_iter), ("grid_em", grid_em),
                      ("weak", weak), ("single_process", single)):
             if v is not None:

@@ -85,6 +85,9 @@ SIGNATURES = {
     "vbhem_multi_pack_base": (C.c_int, [C.c_int, ip, C.c_int, C.c_int, C.POINTER(C.c_ubyte), C.c_int, ip, C.c_int,
                                         C.c_int, C.c_int, dp, dp, dp, dp, dp, C.POINTER(vp)]),
     "vbhem_multi_free": (C.c_int, [vp]),
+    "vbhem_multi_peer_export": (C.c_int, [vp, C.POINTER(C.c_ubyte)]),
+    "vbhem_multi_peer_import": (C.c_int, [vp, C.POINTER(C.c_ubyte)]),
+    "vbhem_multi_allreduce_mode": (C.c_int, [vp, C.POINTER(C.c_int)]),
     "vbhem_multi_repack_base": (C.c_int, [vp, ip, dp, dp, dp, dp, dp]),
     "vbhem_multi_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "vbhem_multi_shard": (C.c_int, [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),

@@ -380,6 +380,22 @@ class MultiBaseSet:
     def set_kernel(self, which: str = "auto"):
         check(lib().vbhem_multi_set_kernel(self._h, {"auto": 0, "general": 1, "unpaired": 2, "halves": 3}[which]))
 
+    # -- peer-memory all-reduce between processes: exchange the IPC handles once (else NCCL is used) -----------
+    def peer_export(self) -> bytes:
+        buf = (C.c_ubyte * (64 * len(self.devices)))()
+        check(lib().vbhem_multi_peer_export(self._h, buf))
+        return bytes(buf)
+
+    def peer_import(self, handles_in_rank_order: list):
+        blob = b"".join(handles_in_rank_order)
+        assert len(blob) == 64 * self.world
+        check(lib().vbhem_multi_peer_import(self._h, (C.c_ubyte * len(blob)).from_buffer_copy(blob)))
+
+    def allreduce_mode(self) -> str:
+        p = C.c_int()
+        check(lib().vbhem_multi_allreduce_mode(self._h, C.byref(p)))
+        return "peer" if p.value else ("nccl" if self.world > 1 else "none")
+
     def shards(self):
         out = []
         for k in range(len(self.devices)):

@@ -413,7 +413,14 @@ __global__ void k_partial_reduce(int K, int per, const int *seg_start, const int
   if (b > a) {
     const int w_hi = (b - 1) / ipr;
     VB_ASSERT(ipr >= 1 && a >= 0 && b <= totals[0] && (long long)w_hi * ipr < (long long)totals[0]);
-    for (int w = a / ipr; w <= w_hi; w++) s += partial[(size_t)(w + j) * per + q];
+    // eight loads in flight, added in slot order (a chain of dependent load-add pairs costs an L2 latency per slot)
+    for (int w = a / ipr; w <= w_hi; w += 8) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) v[u] = w + u <= w_hi ? partial[(size_t)(w + u + j) * per + q] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; u++) s += v[u];
+    }
   }
   if (q < r) S_nu1[q + (size_t)r * j] = s;
   else if (q < r + r * r) S_xi[(q - r) + (size_t)r * r * j] = s;

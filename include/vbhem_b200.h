@@ -283,9 +283,22 @@ int vbhem_em_run_groups(vbhem_base_t *base, int tau, int max_iter, double min_di
  *   vbhem_multi_em_step       one iteration (E-step + all-reduce + lower bound + M-step); lb_out[12 * ngroups]
  *   vbhem_multi_last_ms       device time of the last E-step + all-reduce: the slowest local shard (CUDA events)
  *   vbhem_multi_shard         shard k of this process: device, first base, number of bases, its single-GPU handle
- *   vbhem_multi_counters      vbhem_last_counters summed over the local shards */
+ *   vbhem_multi_counters      vbhem_last_counters summed over the local shards
+ *
+ * The all-reduce itself: where the devices can map each other's memory (NVLink / NVSwitch peer access) it is ONE small
+ * kernel per device that publishes the device's sums, waits for every peer's epoch flag and adds the peers' buffers
+ * in rank order straight out of their memory (deterministic, no NCCL launch; csrc/vbhem_multi.inl); otherwise, for
+ * buffers above 2 MB, or with VBHEM_ALLREDUCE=nccl in the environment, ncclAllReduce.  One process driving all
+ * devices gets the peer path automatically.  Several processes exchange the IPC handles of their exchange areas once:
+ * every process calls vbhem_multi_peer_export (handles[nlocal][64]), the host all-gathers them in rank order and
+ * every process calls vbhem_multi_peer_import (handles[world][64]; one device per process).  Without the exchange
+ * NCCL is used.  vbhem_multi_allreduce_mode: *peer = 1 when the peer path is active. */
 #define VBHEM_UNIQUE_ID_BYTES 128
+#define VBHEM_IPC_HANDLE_BYTES 64
 typedef struct vbhem_multi vbhem_multi_t;
+int vbhem_multi_peer_export(vbhem_multi_t *multi, unsigned char *handles);
+int vbhem_multi_peer_import(vbhem_multi_t *multi, const unsigned char *handles);
+int vbhem_multi_allreduce_mode(vbhem_multi_t *multi, int *peer);
 int vbhem_multi_unique_id(unsigned char id[VBHEM_UNIQUE_ID_BYTES]);
 int vbhem_multi_pack_base(int nlocal, const int *devices, int world, int rank_first, const unsigned char *id, int N,
                           const int32_t *Sb, int maxSb, int d, int covmode, const double *prior, const double *A,

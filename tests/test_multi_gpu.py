@@ -82,6 +82,22 @@ def test_multi_estep_equals_single_gpu(N):
     np.testing.assert_allclose(got["zhat"], want_or["zhat"], rtol=1e-9, atol=1e-12)
 
 
+def test_peer_and_nccl_all_reduce_agree(monkeypatch):
+    """The all-reduce over peer memory (k_allreduce_peer, the default where the devices can map each other) against
+    ncclAllReduce (VBHEM_ALLREDUCE=nccl): same sums up to the order of the additions."""
+    devs = two()
+    base, hyp, cen = make_case(N=1203, K=7, Sb=6, Sr=5, d=2, covmode="full", ragged=True, seed=13, Nv=15.0)
+    with api().MultiBaseSet(base, devices=devs) as ms:
+        assert ms.allreduce_mode() == "peer"
+        got = [ms.estep_hyp(hyp, 8, want_pairs=False)["buf"] for _ in range(3)]
+    monkeypatch.setenv("VBHEM_ALLREDUCE", "nccl")
+    with api().MultiBaseSet(base, devices=devs) as ms:
+        assert ms.allreduce_mode() == "nccl"
+        ref = ms.estep_hyp(hyp, 8, want_pairs=False)["buf"]
+    assert np.array_equal(got[0], got[1]) and np.array_equal(got[0], got[2])
+    np.testing.assert_allclose(got[0], ref, rtol=1e-12, atol=1e-12 * np.abs(ref).max())
+
+
 def test_multi_em_run_equals_single_gpu():
     devs = two()
     from vbhem_b200 import synth
@@ -131,8 +147,24 @@ from util import make_case
 rank, world, idfile, out = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3], sys.argv[4]
 base, hyp, cen = make_case(N=1501, K=6, Sb=5, Sr=4, d=2, covmode="full", ragged=True, seed=77, Nv=12.0)
 uid = open(idfile, "rb").read()
+import time
 with api.MultiBaseSet(shard_base(base, world, rank), devices=[rank], world=world, rank_first=rank, unique_id=uid) as ms:
+    nccl = ms.estep_hyp(hyp, 7)
+    assert ms.allreduce_mode() == "nccl"
+    # the peer-memory all-reduce: exchange the IPC handles of the exchange areas through files
+    open(idfile + ".h" + str(rank) + ".tmp", "wb").write(ms.peer_export())
+    os.rename(idfile + ".h" + str(rank) + ".tmp", idfile + ".h" + str(rank))
+    hs = []
+    for r in range(world):
+        while not os.path.exists(idfile + ".h" + str(r)):
+            time.sleep(0.01)
+        hs.append(open(idfile + ".h" + str(r), "rb").read())
+    ms.peer_import(hs)
+    assert ms.allreduce_mode() == "peer"
     got = ms.estep_hyp(hyp, 7)
+    again = ms.estep_hyp(hyp, 7)
+assert np.array_equal(got["buf"], again["buf"])
+np.testing.assert_allclose(got["buf"], nccl["buf"], rtol=1e-12, atol=1e-12 * np.abs(nccl["buf"]).max())
 np.savez(out, buf=got["buf"], L=got["L_elbo"])
 """
 
