@@ -134,23 +134,26 @@ def run_cpu_workers(sample, nb, cores, tau, outdir=None, keep=0):
                        f"statistics reduction are not included); slowest worker {worst:.2f} s, wall {wall:.1f} s")
 
 
-def source_sha1():
+LATTICE_SOURCES = ("vbhem_lattice.cu", "vbhem_math.cuh", "vbhem_internal.cuh")
+
+
+def source_sha1(files=LATTICE_SOURCES):
     """Identity of the kernel sources a committed ncu summary was captured from."""
     h = hashlib.sha1()
-    for f in ("vbhem_lattice.cu", "vbhem_math.cuh", "vbhem_internal.cuh"):
+    for f in files:
         with open(os.path.join(PKG, "csrc", f), "rb") as fh:
             h.update(fh.read())
     return h.hexdigest()[:16]
 
 
-def ncu_dram_bytes(path):
+def ncu_dram_bytes(path, files=LATTICE_SOURCES):
     """(dram__bytes_read.sum + dram__bytes_write.sum per launch, note) from a profiles/*_ncu.json summary; the value
     is used only when the summary says it was captured from the kernel sources as they are now."""
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
     try:
         with open(path) as f:
             nc = json.load(f)
-        if nc.get("source_sha1") != source_sha1():
+        if nc.get("source_sha1") != source_sha1(files):
             return None, f"{os.path.basename(path)} was captured from other kernel sources: not quoted"
         v = sum(float(nc[k]["value"]) * scale[nc[k]["unit"]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
         return v, f"profiles/{os.path.basename(path)} (ncu --set full of this kernel source, bytes per launch)"
@@ -305,7 +308,7 @@ def main():
         if rank != 0:
             return
         _, pc = centre_pack()
-        per_base_s = K * 60e-6                                       # ~60 us per pair and core (measured, r01)
+        per_base_s = sum(float(r) ** 2 for r in np.asarray(hyp["Sr"])) / 64.0 * 60e-6   # ~60 us per 8 x 8 pair and core
         nb = a.cpu_bases or max(256, min(3072, int(240.0 / max(1, a.steps) / per_base_s)))
         nb = min(nb, a.bases // cores)
         with tempfile.TemporaryDirectory() as td:
@@ -331,7 +334,9 @@ def main():
     if rank == 0 and world == 1 and not a.no_cpu:
         from oracle import cref
         cen, pc = centre_pack()
-        nb = a.cpu_bases or min(3072, a.bases // cores)              # ~12 s of CPU work per core
+        # ~12 s of CPU work per core (the reference's C takes ~60 us per pair of 8-state HMMs, less for smaller centres)
+        per_base_s = sum(float(r) ** 2 for r in np.asarray(hyp["Sr"])) / 64.0 * 60e-6
+        nb = a.cpu_bases or max(32, min(3072, a.bases // cores, int(12.0 / per_base_s)))
         keep = min(128, nb)
         with tempfile.TemporaryDirectory() as td:
             sample = os.path.join(td, "sample.npz")

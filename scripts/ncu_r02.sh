@@ -30,3 +30,8 @@ print(open("gpurun_out/r02_launches_summary.csv").read())
 PY
 rm -f gpurun_out/r02_full.ncu-rep gpurun_out/r02_zhat.ncu-rep
 ls -la gpurun_out/ | tail -20
+# BASELINE configs[4]: the forward-backward kernel
+python bench.py --workload fb --steps 1 --no-cpu --no-e2e > gpurun_out/r02_plain_fb.json 2> gpurun_out/r02_plain_fb.err || exit 1
+ncu --set full --clock-control none --import-source on -k regex:"k_fb<" -s 3 -c 1 -o gpurun_out/r02_fb -f python bench.py --workload fb --steps 1 --no-cpu --no-e2e > gpurun_out/r02_ncu_fb.log 2>&1
+python scripts/ncu_summary.py gpurun_out/r02_fb.ncu-rep > gpurun_out/r02_fb.summary.json
+rm -f gpurun_out/r02_fb.ncu-rep
