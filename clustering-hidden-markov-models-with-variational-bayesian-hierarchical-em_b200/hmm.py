@@ -362,8 +362,8 @@ def vbhmm_learn_batch(subjects: list, K, vbopt: dict | None = None) -> list:
     """vbhmm_learn_batch.m: one HMM per subject (``subjects[s]`` = that subject's list of [T, dim] sequences), every
     subject x candidate K x random initialisation as one run of a device-resident batch per K; per subject the best
     trial by LL, then the best K by ``LL + gammaln(K + 1)`` (vbhmm_learn.m:387-405,555).
-    ``vbopt['gmm_init'] = 'device'`` fits the random-initialisation GMMs of all runs on the GPU (``gmm_fit_batch``)
-    instead of one scikit-learn fit per run on the host."""
+    The random-initialisation GMMs of all runs are fitted on the GPU (``gmm_fit_batch``, the default);
+    ``vbopt['gmm_init'] = 'sklearn'`` takes one scikit-learn fit per run on the host instead (comparison only)."""
     opt = dict(DEFAULT_VBOPT)
     opt.update(vbopt or {})
     Ks = [int(k) for k in np.atleast_1d(K)]
@@ -373,7 +373,7 @@ def vbhmm_learn_batch(subjects: list, K, vbopt: dict | None = None) -> list:
     best = [None] * len(subjects)
     score = [-np.inf] * len(subjects)
     per_k = [[None] * len(Ks) for _ in subjects]
-    device_gmm = opt["initmode"] == "random" and opt.get("gmm_init", "sklearn") == "device"
+    device_gmm = opt["initmode"] == "random" and opt.get("gmm_init", "device") == "device"
     with _fb.SequenceSet(flat) as seqs:
         npts = [int(seqs.T[start[s]:start[s + 1]].sum()) for s in range(len(subjects))]
         for ki, k in enumerate(Ks):

@@ -38,6 +38,11 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
   const int Kb = b.N, Kr = c.K, d = b.d, dd = b.dd;
   const size_t P = (size_t)Kb * Kr, r = (size_t)maxN2;
   plhs[0] = mxCreateDoubleMatrix(Kb, Kr, mxREAL);
+  // NOTE (cost of the literal signature): the per-pair statistics cross the boundary twice -- device -> these flat
+  // staging vectors -> one freshly allocated mxArray per pair and output (5 Kb Kr arrays) -- because the reference's
+  // outputs are {Kb x Kr} cells of small matrices (vbhem_hmm_bwd_fwd_mex.c:396-409).  That is inherent to Boundary-1
+  // (1 KB and five mxArray headers per pair: 6.5 GB / 32 M arrays at N = 100 k); the fused gateway
+  // (vbhem_estep_fused_mex.cpp) returns what the EM loop consumes instead and is the fast path.
   std::vector<double> nu1(r * P), xi(r * r * P), pr(r * P), muo(r * d * P), Muo(r * dd * P);
   fail_rc(vbhem_estep_pairs(h, Kr, c.Sr.data(), maxN2, T, c.logPi.data(), c.logA.data(), c.m.data(), c.vW.data(),
                             c.cterm.data(), mxGetPr(plhs[0]), nu1.data(), xi.data(), pr.data(), muo.data(),

@@ -199,7 +199,7 @@ def test_learn_batch_equals_learning_subject_by_subject():
     subject by subject (same seeds => same initial GMMs)."""
     subjects = [make_sequences(n=10, K=2, seed=60 + s)[0] for s in range(4)]
     opt = dict(numTrials=3, seed=5, maxIter=50)
-    got = H.vbhmm_learn_batch(subjects, [1, 2, 3], opt)
+    got = H.vbhmm_learn_batch(subjects, [1, 2, 3], dict(opt, gmm_init="sklearn"))   # the host GMMs vbhmm_learn takes
     for s, sub in enumerate(subjects):
         one = H.vbhmm_learn(sub, [1, 2, 3], opt)
         assert got[s]["K"] == one["K"]

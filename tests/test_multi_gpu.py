@@ -216,3 +216,23 @@ def test_mex_gateways_take_ngpus(monkeypatch):
             np.testing.assert_allclose(two_[k], one[k], rtol=1e-11, atol=1e-11 * np.abs(one[k]).max(), err_msg=k)
         assert em2["iters"] == em1["iters"]
         np.testing.assert_allclose(em2["LogLs"], em1["LogLs"], rtol=1e-10)
+
+
+@pytest.mark.parametrize("covmode,d,kernel", [("diag", 3, "auto"), ("full", 2, "general")])
+def test_multi_other_shapes_and_groups(covmode, d, kernel):
+    """Diagonal covariances, the general kernel, several soft-max groups (a (K,S) grid) and a base count that leaves
+    the shards uneven and smaller than one responsibility block -- sharded against single GPU."""
+    devs = two()
+    from vbhem_b200 import synth
+    N = 37 * len(devs) + 3
+    base, _ = synth.make_base_set(N, S=4, d=d, C=3, covmode=covmode, seed=9, Nv=8.0, ragged=True)
+    opt = dict(synth.DEFAULT_OPT, Nv=8.0, tau=4, m0=tuple([256.0, 192.0, 128.0][:d]))
+    hyp, grp, models = synth.model_selection_grid(base, Ks=range(1, 4), Ss=range(1, 4), seed=2, opt=opt)
+    with api().BaseSet(base) as bs:
+        bs.set_kernel(kernel)
+        want = bs.estep_hyp(hyp, 4, group=grp)
+    with api().MultiBaseSet(base, devices=devs) as ms:
+        ms.set_kernel(kernel)
+        got = ms.estep_hyp(hyp, 4, group=grp)
+    assert np.array_equal(got["L_elbo"], want["L_elbo"]) and np.array_equal(got["zhat"], want["zhat"])
+    close(got, want)
