@@ -13,10 +13,10 @@
 //     emission term) and once on the way out (L_elbo).
 //  2. INTEGER SHIFT.  A lattice row needs lse_sigma(G) = c + log sum_sigma w exp(G - c) for ANY c
 //     near the row maximum, so no floating-point maximum is ever taken:
-//       exp_split(y)    -> (mant, e) with e^(y u) = mant 2^e, mant in [1, 2)     8 fp64 instructions
+//       exp_split(y)    -> (mant, e) with e^(y u) = mant 2^e, mant in [1, 2)     7 fp64 instructions
 //       row shift       =  integer max of e over the row (32-bit shuffles)
 //       exp_scale()     -> mant 2^(e - c): two integer instructions on the high word
-//       log_shift(s, c) =  ((c + exponent(s)) ln2 + log(mantissa(s))) / u         7 fp64 instructions + I2F
+//       log_shift(s, c) =  ((c + exponent(s)) ln2 + log(mantissa(s))) / u         6 fp64 instructions + I2F
 //
 // Domain: exp_split takes |y| < 2^39 (no clamp inside: the kernels clamp the emission terms
 // once per pair and the recursion cannot leave the range while its row shifts stay in
@@ -29,6 +29,16 @@
 #define VBHEM_MATHTAB "vbhem_mathtab.h"
 #endif
 #include VBHEM_MATHTAB
+// Polynomial degrees: the generator's choice keeps both functions within 2 ulp; -DVB_EXP_DEG / -DVB_LOG_DEG override
+// them for accuracy / speed experiments (scripts/sweep_math_degrees.sh).
+#ifdef VB_EXP_DEG
+#undef VBHEM_EXP_DEG
+#define VBHEM_EXP_DEG VB_EXP_DEG
+#endif
+#ifdef VB_LOG_DEG
+#undef VBHEM_LOG_DEG
+#define VBHEM_LOG_DEG VB_LOG_DEG
+#endif
 
 #ifdef __CUDACC__
 #define VB_HD __host__ __device__ __forceinline__
@@ -48,17 +58,18 @@ constexpr double kPerUnit = VBHEM_PER_UNIT;   // 1 / u
 constexpr double kUnitsFloor = -68719476736.0;          // -2^36 units (~ -1.9e8 natural)
 constexpr double kUnitsCeil = 34359738368.0;            //  2^35 units (~  9.3e7 natural)
 
-// Polynomial constants.  On the device they live in constant memory so that DFMA reads them as
-// c[bank][offset] operands (no register-file bandwidth); as literals ptxas re-materialises each one
-// with two moves per use.   [0..4] exp: u^n/n!;  [5..9] log: (-1)^(n+1)/(n u);  [10] 1.5 * 2^52
-#define VB_MATH_CONSTS { VBHEM_EXP_COEF, VBHEM_LOG_COEF, 6755399441055744.0 }
+// Polynomial constants.  On the device they live in constant memory: ptxas loads them into uniform registers
+// (LDCU) or, for a few, hoists them into vector registers; as literals it re-materialises each one with two
+// moves per use.  (Passing them as a __grid_constant__ kernel parameter gives the same SASS: sm_100 DFMA has
+// no c[bank][offset] operand form, only R / UR / 32-bit immediate.)   [0..4] exp: u^n/n!;  [5..9] log: (-1)^(n+1)/(n kappa^n u);  [10] 1.5 * 2^52;  [11] 1;  [12] -kappa
+#define VB_MATH_CONSTS { VBHEM_EXP_COEF, VBHEM_LOG_COEF, 6755399441055744.0, 1.0, -(VBHEM_LOG_KAPPA) }
 #ifdef __CUDACC__
-static __constant__ double g_mc[11] = VB_MATH_CONSTS;   // one copy per translation unit
+static __constant__ double g_mc[13] = VB_MATH_CONSTS;   // one copy per translation unit
 #endif
 #ifdef __CUDA_ARCH__
 #define VB_MC(i) g_mc[i]
 #else
-static const double h_mc[11] = VB_MATH_CONSTS;
+static const double h_mc[13] = VB_MATH_CONSTS;
 #define VB_MC(i) h_mc[i]
 #endif
 
@@ -158,7 +169,11 @@ VB_HD double exp_split(double y, tab_t etab, int &e) {
   q = fma(q, r, VB_MC(1));
 #endif
   q = fma(q, r, VB_MC(0));
-  return fma(T * r, q, T);                                 // T * e^(r u)
+#ifdef VB_EXP_TAIL_3REG
+  return fma(T * r, q, T);                                 // T * e^(r u): a DFMA with three register operands (3 cycles)
+#else
+  return T * fma(q, r, 1.0);                               // T * e^(r u), every instruction with at most two register operands
+#endif
 }
 
 // mant * 2^de for de <= 0 (clamped at -1000: ~1e-301, nothing next to the row maximum's [1, 2)).
@@ -182,7 +197,9 @@ VB_HD bool nonfinite(double x) { return ((unsigned)hi_word(x) & 0x7ff00000u) == 
 
 // (c ln2 + log s) / u for normal positive s; cb = c - 1023.  tab = VBHEM_LOG_TABLE as (invc, logc/u)
 // pairs: s = 2^e m, r = m invc - 1, log s = e ln2 + logc + log1p(r); in units, e ln2 / u = e BINS
-// exactly.  LS = stride of the table in pairs.  Error <= ~1e-13 units = 3e-16 natural.
+// exactly.  The table and the polynomial are in the scaled residual kappa r (gen_mathtab.py: the quadratic
+// coefficient becomes the DFMA immediate -128).  LS = stride of the table in pairs.
+// Error <= ~3e-12 units = 8e-15 natural (Taylor degree 4).
 VB_HD constexpr int ilog2(int x) { return x <= 1 ? 0 : 1 + ilog2(x >> 1); }
 template <int LS = 1>
 VB_HD double log_shift_biased(double s, tab_t tab, int cb, int one = 0x3ff00000) {
@@ -195,14 +212,14 @@ VB_HD double log_shift_biased(double s, tab_t tab, int cb, int one = 0x3ff00000)
   const double m = make_double(mant_hi(hi, one), lo_word(s));
   double invc, logc;
   tab_ld2(tab, off, invc, logc);
-  const double r = fma(m, invc, -1.0);
+  const double r = fma(m, invc, VB_MC(12));               // kappa (m invc_i - 1)
 #if VBHEM_LOG_DEG == 4
   double q = fma(r, VB_MC(8), VB_MC(7));
 #else
   double q = fma(r, VB_MC(9), VB_MC(8));
   q = fma(q, r, VB_MC(7));
 #endif
-  q = fma(q, r, VB_MC(6));
+  q = fma(q, r, VBHEM_LOG_C2);
   q = fma(q, r, VB_MC(5));
   return fma((double)e, (double)VBHEM_EXP_BINS, fma(q, r, logc));
 }
