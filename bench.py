@@ -466,7 +466,7 @@ def main():
     alg_bytes = nloc * (S + S * S + S * d + S * d * d) * 8 + nloc * K * 8
     traffic, traffic_src = None, "the committed capture is of the 100 000-base single-GPU launch only"
     if (nloc, K, S, d, tau) == (100_000, 64, 8, 2, 10) and not grid:
-        traffic, traffic_src = ncu_dram_bytes(os.path.join(ROOT, "profiles", "r02_k_lattice_bwd_ncu.json"))
+        traffic, traffic_src = ncu_dram_bytes(os.path.join(ROOT, "profiles", "r02d_k_lattice_bwd_ncu.json"))
     roofline = dict(bound="tensor", kernel="k_lattice_bwd (first pass: emission expectation + backward lattice + "
                                            "termination for every pair; fp64 DMMA m8n8k4)",
                     achieved=ach, peak=float(peak[0]), unit="TFLOP/s", frac=ach / float(peak[0]),

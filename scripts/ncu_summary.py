@@ -21,7 +21,20 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__warps_eligible.avg.per_cycle_active", "smsp__average_warp_latency_per_inst_issued.ratio"]
 
 
-def main(path):
+def stamp(files):
+    """SHA-1 (16 hex) of the kernel sources the capture was taken from -- what bench.py compares before quoting traffic."""
+    import hashlib
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "clustering-hidden-markov-models-with-variational-bayesian-hierarchical-em_b200", "csrc")
+    h = hashlib.sha1()
+    for f in files:
+        with open(os.path.join(pkg, f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def main(path, sources=()):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
@@ -38,8 +51,11 @@ def main(path):
                     continue
                 d[h] = {"unit": u, "value": fv} if u else fv
         res.append(d)
+    if sources and len(res) == 1:
+        res[0]["source_sha1"] = stamp(sources)
+        res[0]["source_files"] = list(sources)
     print(json.dumps(res[0] if len(res) == 1 else res, indent=1))
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    main(sys.argv[1], tuple(sys.argv[2:]))     # optional: csrc file names whose SHA-1 is stamped into the summary
