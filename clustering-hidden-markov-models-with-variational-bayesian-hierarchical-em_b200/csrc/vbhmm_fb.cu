@@ -51,15 +51,21 @@ using vbhem::fail_fb;
                      cudaGetErrorString(e_), __FILE__, __LINE__);                                             \
   } while (0)
 
-constexpr int kFbThreads = 128;
+#ifndef VB_FB_THREADS
+#define VB_FB_THREADS 128
+#endif
+constexpr int kFbThreads = VB_FB_THREADS;
 #ifndef VB_FB_MINB
-#define VB_FB_MINB 4
+#define VB_FB_MINB 2       // resident CTAs per SM: 256 sequences in flight per SM, <= 255 registers (Xi lives in registers)
 #endif
-#ifndef VB_FB_LEAN
-#define VB_FB_LEAN 0       // 1: k_fb takes c(t+1) from the backward sums and log c from the lean log (see the header note)
+#ifndef VB_FB_RING
+#define VB_FB_RING 8       // slots of the observation ring (cp.async RING - 1 steps ahead); a power of two
 #endif
-#ifndef VB_FB_BLOCKS
-#define VB_FB_BLOCKS 0     // > 0: cap the resident blocks per SM (L2 residency of the parked alpha_hat)
+#ifndef VB_FB_AHEAD
+#define VB_FB_AHEAD 6      // the backward pass copies parked alpha_hat from the scratch buffer this many steps ahead
+#endif
+#ifndef VB_FB_HINT
+#define VB_FB_HINT 1       // 1: L2 evict_last on the parked alpha_hat (scripts/sweep_fb.sh A/Bs it)
 #endif
 constexpr int kFbMaxK = 8, kFbMaxDim = 3;         // template instantiations; beyond: the generic kernel
 constexpr int kFbGenK = 32, kFbGenDim = 8;
@@ -148,147 +154,372 @@ __device__ __forceinline__ double forward_step(const FbPar<K, DIM> &P, const dou
   return c;
 }
 
-template <int K, int DIM>
-__global__ void __launch_bounds__(kFbThreads, VB_FB_MINB)
-k_fb(const __grid_constant__ FbPar<K, DIM> P, int N, int maxT, const int *__restrict__ Tn,
-     const double *__restrict__ X, double *__restrict__ logrho, double *__restrict__ gamma,
-     double *__restrict__ xi_sum, double *__restrict__ phi) {
-#if VB_FB_LEAN
-  __shared__ __align__(16) double s_tab[kFbTabDoubles];
-  vbhem::tab_t etab, ltab;
-  stage_tables<kFbThreads>(s_tab, etab, ltab);
+// 1 / x for a normal positive x: MUFU.RCP64H seed + one cubic correction (<= 1 ulp; no special-case branch)
+__device__ __forceinline__ double rcp_pos(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  const double e = fma(-x, r, 1.0);                    // |e| <= 2^-22: r (1 + e + e^2) is exact to 2^-66
+  return fma(r, fma(e, e, e), r);
+}
+
+// Accesses to the parked alpha_hat in HBM-backed scratch: the slots are re-used by every sequence a thread takes, so
+// they are meant to live in L2 (evict_last); everything else the kernel touches is streamed (ld/st .cs).
+#if VB_FB_HINT
+__device__ __forceinline__ unsigned long long l2_keep_policy() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void st_keep(double *q, double v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(q), "d"(v), "l"(pol) : "memory");
+}
 #else
-  __shared__ __align__(16) double s_etab[VBHEM_EXP_BINS];
-  for (int j = threadIdx.x; j < VBHEM_EXP_BINS; j += kFbThreads) s_etab[j] = g_fb_exp_table[j];
-  __syncthreads();
-  const vbhem::tab_t etab = (vbhem::tab_t)__cvta_generic_to_shared(s_etab);
+__device__ __forceinline__ unsigned long long l2_keep_policy() { return 0ull; }
+__device__ __forceinline__ void st_keep(double *q, double v, unsigned long long) { *q = v; }
 #endif
-  const int n = blockIdx.x * kFbThreads + threadIdx.x;
-  if (n >= N) return;
-  const int T = Tn[n];
+
+// The observations of a lane's sequence arrive through a private ring in shared memory, filled by cp.async
+// VB_FB_RING - 1 steps ahead of their use: no register holds a load in flight (rotating prefetch registers makes every
+// move wait for the youngest load: the first version of this kernel spent 16 % of its samples there).
+template <int DIM>
+struct ObsRing {
+  static constexpr int kSlot = DIM * kFbThreads;       // doubles per ring slot: [slot][thread][DIM]
+  const double *xp;                                    // the lane's observation at t = 0
+  size_t stride;                                       // N * DIM
+  unsigned base;                                       // shared address of the lane's place in slot 0
+  int T;
+  __device__ __forceinline__ void request(int u) const {              // observation u -> slot u % RING (a group either way)
+    if (u < T) {
+      const unsigned dst = base + (unsigned)(u % VB_FB_RING) * (kSlot * 8u);
+      const double *src = xp + stride * u;
+      if constexpr (DIM == 2) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+      } else {
+#pragma unroll
+        for (int d = 0; d < DIM; d++)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * d), "l"(src + d) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  __device__ __forceinline__ void start() const {
+#pragma unroll
+    for (int u = 0; u < VB_FB_RING - 1; u++) request(u);
+  }
+  // observation u (consumed in order, each once): requests u + RING - 1 into the slot read one step ago
+  __device__ __forceinline__ void take(int u, double (&x)[DIM]) const {
+    request(u + VB_FB_RING - 1);
+    asm volatile("cp.async.wait_group %0;" ::"n"(VB_FB_RING - 1) : "memory");
+    const unsigned src = base + (unsigned)(u % VB_FB_RING) * (kSlot * 8u);
+    if constexpr (DIM == 2) {
+      asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x[0]), "=d"(x[1]) : "r"(src) : "memory");
+    } else {
+#pragma unroll
+      for (int d = 0; d < DIM; d++) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x[d]) : "r"(src + 8u * d) : "memory");
+    }
+  }
+};
+
+// Where alpha_hat(t) of the running sequence waits for the backward pass.  Reverse index r = T-2-t (r = 0 is read
+// first).  The forward pass leaves the first `ts` of them in shared memory and the rest in the CTA's region of the
+// scratch buffer, both laid out [r][k][thread] (conflict-free / one contiguous run per warp, compile-time strides).
+// The backward pass reads everything from shared memory: the `ts` slots are a ring, and the entry for index
+// r + VB_FB_AHEAD is copied in from the scratch buffer by cp.async while index r is in use (its slot's previous
+// occupant, r + AHEAD - ts, was consumed earlier) -- no register waits on L2 or HBM.
+template <int K>
+struct Park {
+  double *sm, *gl;             // already offset by the thread; gl is biased by -ts rows
+  unsigned sbase;              // shared address of sm
+  int ts, last;                // last = T - 2 of the running sequence (highest index parked)
+  unsigned long long pol;
+  static constexpr int kRow = K * kFbThreads;
+  __device__ __forceinline__ void put(int r, const double (&a)[K]) const {
+    if (r < ts) {
+      double *q = sm + r * kRow;
+#pragma unroll
+      for (int k = 0; k < K; k++) q[k * kFbThreads] = a[k];
+    } else {
+      double *q = gl + (size_t)r * kRow;
+#pragma unroll
+      for (int k = 0; k < K; k++) st_keep(q + k * kFbThreads, a[k], pol);
+    }
+  }
+  // backward side: indices are requested and read in order, so the ring positions are running offsets (no modulo)
+  unsigned rq_off, rd_off;     // byte offsets of the slots of the next request / the next read
+  int rq;                      // next index to request
+  __device__ __forceinline__ void request() {                          // one cp.async group per index, empty or not
+    if (rq >= ts && rq <= last) {
+      const unsigned dst = sbase + rq_off;
+      const double *src = gl + (size_t)rq * kRow;
+#pragma unroll
+      for (int k = 0; k < K; k++)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + k * (kFbThreads * 8u)), "l"(src + k * kFbThreads)
+                     : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    rq++;
+    rq_off += kRow * 8u;
+    if (rq_off == (unsigned)ts * (kRow * 8u)) rq_off = 0;
+  }
+  __device__ __forceinline__ void start() {                            // after the forward pass
+    rq = 0; rq_off = 0; rd_off = 0;
+#pragma unroll
+    for (int r = 0; r < VB_FB_AHEAD; r++) request();
+  }
+  __device__ __forceinline__ void get(double (&a)[K]) {                // the next index
+    request();
+    asm volatile("cp.async.wait_group %0;" ::"n"(VB_FB_AHEAD) : "memory");
+    const unsigned src = sbase + rd_off;
+#pragma unroll
+    for (int k = 0; k < K; k++)
+      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a[k]) : "r"(src + k * (kFbThreads * 8u)) : "memory");
+    rd_off += kRow * 8u;
+    if (rd_off == (unsigned)ts * (kRow * 8u)) rd_off = 0;
+  }
+};
+
+// The outputs keep the reference's layout [K, N, maxT]: at one time step the 32 sequences of a warp own ONE contiguous
+// run of 32 K doubles, but a lane's K values sit K doubles apart -- stored lane by lane, every STG would touch 32
+// sectors with 8 useful bytes each (L2 write transactions, not bytes, bounded the first version of this kernel).  So
+// the warp transposes through shared memory: lane l deposits its K values at [l K + k], then store i writes elements
+// 32 i + l -- K full-line stores.  Two buffers alternate, so one __syncwarp per call orders everything.
+template <int K>
+struct RowStore {
+  static constexpr int kBuf = K * 32 + K;              // + the skew of even K
+  double *buf;                                         // this warp's two buffers
+  int lane, nvalid;                                    // nvalid = K * (#sequences of the warp's chunk that exist)
+  int flip;
+  __device__ __forceinline__ static int at(int e) { return (K % 2 == 0) ? e + (e >> 5) : e; }   // odd K: conflict-free as is
+  __device__ __forceinline__ void store(double *dst, const double (&v)[K]) {
+    double *b = buf + flip * kBuf;
+    flip ^= 1;
+#pragma unroll
+    for (int k = 0; k < K; k++) b[at(lane * K + k)] = v[k];
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < K; i++) {
+      const int e = 32 * i + lane;
+      if (e < nvalid) __stcs(dst + e, b[at(e)]);
+    }
+  }
+};
+
+// 32 consecutive sequences, one per lane: forward (vbhmm_fb.m:316-347), then backward + responsibilities + summed
+// pair marginals (:349-377).  Both loops run over the full 0..maxT-1 for the whole warp (a lane beyond its own length
+// contributes the zeros the reference's outputs start with), so that every output row is written by full-line stores.
+//
+// The backward pass never touches the emissions again.  The reference's step is
+//     beta_t(j) = sum_k A(j,k) beta_{t+1}(k) p_{t+1}(k) / c_{t+1},   xi_t(j,k) = alpha_t(j) A(j,k) beta_{t+1}(k) p_{t+1}(k) / c_{t+1}
+// and the forward pass made alpha_{t+1}(k) = pred_t(k) p_{t+1}(k) / c_{t+1} with pred_t(k) = sum_j alpha_t(j) A(j,k), so
+//     p_{t+1}(k) / c_{t+1} = alpha_{t+1}(k) / pred_t(k):
+// one 25-term product and five reciprocals replace the second evaluation of the emission densities, their exp and the
+// scale (~ 200 of the ~ 500 fp64 instructions per step) and the second read of the observations; sum_k gamma_t(k) = 1
+// is preserved exactly as before (sum_j alpha_t(j) beta_t(j) = sum_k alpha_{t+1}(k) beta_{t+1}(k)).  pred_t(k) > 0 whenever
+// A > 0; a column of exact zeros makes alpha_{t+1}(k) = 0 and the guarded quotient 0 (the state is unreachable).
+template <int K, int DIM, bool UNI>
+__device__ __forceinline__ void fb_chunk(const FbPar<K, DIM> &P, int base, int N, int maxT, int T, int Tw,
+                                         const double *__restrict__ X, double *__restrict__ logrho,
+                                         double *__restrict__ gamma, double *__restrict__ xi_sum,
+                                         double *__restrict__ phi, const Park<K> &park_of_thread, RowStore<K> &rows,
+                                         unsigned xring, vbhem::tab_t etab, vbhem::tab_t ltab) {
+  Park<K> park = park_of_thread;
+  park.last = T - 2;
+  // UNI: every lane has a sequence and all 32 have the same length T = Tw -- no per-lane conditions in the loops
+  const int n = base + rows.lane;
+  const bool exists = UNI || n < N;
   const size_t NK = (size_t)N * K, ND = (size_t)N * DIM;
-  const double *xp = X + (size_t)DIM * n;
-  double *lp = logrho ? logrho + (size_t)K * n : nullptr, *gp = gamma + (size_t)K * n;
-  double alpha[K], p[K], lr[K], x[DIM], xn[DIM];
+  double *lrow = logrho ? logrho + (size_t)K * base : nullptr, *grow = gamma + (size_t)K * base;
+  double alpha[K], p[K], lr[K];
   double sumlogc = 0.0, summax = 0.0;
 
-  // ---- forward (vbhmm_fb.m:316-347).  The next observation is requested one step ahead; logrho is a
-  // streaming store (never read again here), alpha_hat a normal one (read back below, ideally from L2).
+  // ---- forward, software-pipelined: the emission densities and their exp of step t+1 do not depend on the recursion
+  // of step t, so one step does both (two independent dependency chains per lane: with 8 warps per SM the kernel is
+  // bound by the latency of its chains).  Two steps per iteration with the roles of the (logrho, p) pairs swapped, so
+  // that nothing is moved between registers.
+  ObsRing<DIM> obs;
+  obs.xp = X + (size_t)DIM * (exists ? n : base);
+  obs.stride = ND;
+  obs.base = xring;
+  obs.T = T;
+  obs.start();
+  auto next_obs = [&](int t, double (&l)[K], double (&q)[K]) -> double {   // logrho(:, t), p(:, t), the shift; t < T
+    double x[DIM];
+    obs.take(t, x);
+    emissions<K, DIM>(P, x, l);
+    return shifted_exp<K>(l, q, etab);
+  };
+  double mxn = 0.0;
+  auto fstep = [&](int t, double (&lc)[K], double (&pc)[K], double (&ln)[K], double (&pn)[K]) {
+    if (UNI || t < T) {
+      if (t + 1 < T) mxn = next_obs(t + 1, ln, pn);
+      double delta[K], c;
+      if (t == 0) {
+        c = 0.0;
 #pragma unroll
-  for (int i = 0; i < DIM; i++) xn[i] = T > 0 ? xp[i] : 0.0;
-  for (int t = 0; t < T; t++) {
+        for (int k = 0; k < K; k++) { delta[k] = P.pz1[k] * pc[k]; c += delta[k]; }
+      } else {
+        c = forward_step<K, DIM>(P, alpha, pc, delta);
+      }
+      const double rc = rcp_pos(c);
 #pragma unroll
-    for (int i = 0; i < DIM; i++) x[i] = xn[i];
-    if (t + 1 < T) {
-#pragma unroll
-      for (int i = 0; i < DIM; i++) xn[i] = xp[ND * (t + 1) + i];
+      for (int k = 0; k < K; k++) alpha[k] = delta[k] * rc;
+      if (t < T - 1) { park.put(T - 2 - t, alpha); summax += mxn; }      // alpha_hat(T-1) stays in registers
+      sumlogc += vbhem::log_shift<1>(c, ltab, 0);
     }
-    emissions<K, DIM>(P, x, lr);
-    if (logrho) {
+    if (lrow) rows.store(lrow + NK * t, lc);
+    if (!UNI && !(t + 1 < T)) {
 #pragma unroll
-      for (int k = 0; k < K; k++) __stcs(lp + NK * t + k, lr[k]);
+      for (int k = 0; k < K; k++) ln[k] = 0.0;
     }
-    summax += shifted_exp<K>(lr, p, etab);
-    double delta[K], c;
-    if (t == 0) {
-      c = 0.0;
+  };
+  double l2[K], p2[K];
 #pragma unroll
-      for (int k = 0; k < K; k++) { delta[k] = P.pz1[k] * p[k]; c += delta[k]; }
-    } else {
-      c = forward_step<K, DIM>(P, alpha, p, delta);
-    }
-    const double rc = 1.0 / c;
-#pragma unroll
-    for (int k = 0; k < K; k++) { alpha[k] = delta[k] * rc; gp[NK * t + k] = alpha[k]; }
-#if VB_FB_LEAN
-    sumlogc += vbhem::log_shift<1>(c, ltab, 0);
+  for (int k = 0; k < K; k++) { alpha[k] = 0.0; lr[k] = 0.0; p[k] = 0.0; l2[k] = 0.0; p2[k] = 0.0; }
+  if (0 < T) summax = next_obs(0, lr, p);
+  for (int t = 0; t < Tw; t += 2) {
+    fstep(t, lr, p, l2, p2);
+    if (t + 1 < Tw) fstep(t + 1, l2, p2, lr, p);
   }
-  phi[n] = sumlogc * vbhem::kUnit + summax;
-#else
-    sumlogc += log(c);
-  }
-  phi[n] = sumlogc + summax;
-#endif
-  // zeros beyond the sequence's own length (the reference's outputs start as zeros)
-  for (int t = T; t < maxT; t++) {
+  if (exists) __stcs(phi + n, sumlogc * vbhem::kUnit + summax);
 #pragma unroll
-    for (int k = 0; k < K; k++) { if (logrho) __stcs(lp + NK * t + k, 0.0); __stcs(gp + NK * t + k, 0.0); }
+  for (int k = 0; k < K; k++) lr[k] = 0.0;
+  // rows beyond the longest sequence of the warp: the zeros the reference's outputs start with
+  for (int t = maxT - 1; t >= Tw; t--) {
+    if (lrow) rows.store(lrow + NK * t, lr);
+    rows.store(grow + NK * t, lr);
   }
 
-  // ---- backward, responsibilities, summed pair marginals (vbhmm_fb.m:349-377).  The K x K accumulator of
-  // each thread lives in shared memory ([j][k][thread]: conflict-free), which keeps the register count low
-  // enough for three to four resident blocks per SM.
-  extern __shared__ double xis[];
-  double *xi = xis + threadIdx.x;
-  double beta[K], an[K];
+  // ---- backward, software-pipelined as well: q(k) = alpha_hat_{t+1}(k) / pred_t(k) depends on parked values only, so
+  // the quotients of step t-1 are formed while step t runs; what is left on the recurrence is beta -> beta.* q -> A * (.).
+  // Two steps per iteration with the roles of the (alpha_hat, q) pairs swapped (nothing moves between registers).
+  double Xi[K][K], beta[K], a1[K], q1[K], a2[K], q2[K];
 #pragma unroll
   for (int j = 0; j < K; j++) {
-    beta[j] = 1.0;
+    beta[j] = 1.0; a1[j] = 0.0; q1[j] = 0.0; a2[j] = 0.0; q2[j] = 0.0;
 #pragma unroll
-    for (int k = 0; k < K; k++) xi[(j * K + k) * kFbThreads] = 0.0;
+    for (int k = 0; k < K; k++) Xi[j][k] = 0.0;
   }
-  // gamma(:, T) = alpha(:, T) is already in place; x holds the last observation
-  if (T >= 2) {
+  auto quotients = [&](const double (&lo)[K], const double (&hi)[K], double (&out)[K]) {   // hi(k) / sum_j lo(j) A(j,k)
 #pragma unroll
-    for (int k = 0; k < K; k++) an[k] = gp[NK * (T - 2) + k];
-  }
-  for (int t = T - 2; t >= 0; t--) {
-    // x = observation t+1 (from the previous iteration / the forward pass), alpha = alpha_hat(t)
+    for (int k = 0; k < K; k++) {
+      double pred = 1e-300;                                            // keeps the quotient finite for an unreachable state
 #pragma unroll
-    for (int k = 0; k < K; k++) alpha[k] = an[k];
-#pragma unroll
-    for (int i = 0; i < DIM; i++) xn[i] = xp[ND * t + i];             // observation t, used next iteration
-    if (t > 0) {
-#pragma unroll
-      for (int k = 0; k < K; k++) an[k] = gp[NK * (t - 1) + k];      // alpha_hat(t-1), parked by the forward pass
+      for (int j = 0; j < K; j++) pred += lo[j] * P.A[j][k];
+      out[k] = hi[k] * rcp_pos(pred);
     }
-    emissions<K, DIM>(P, x, lr);
-    shifted_exp<K>(lr, p, etab);                                      // p(x_{t+1} | z) / max
-    double bpi[K];
-#if VB_FB_LEAN
+  };
+  // ac = alpha_hat(t), qc = p_{t+1} / c_{t+1}; leaves alpha_hat(t-1) and the quotients of step t-1 in (an, qn)
+  auto bstep = [&](int t, double (&ac)[K], double (&qc)[K], double (&an)[K], double (&qn)[K], double (&g)[K]) {
+    if (t >= 1) {
+      park.get(an);                                                    // alpha_hat(t-1): the next parked index
+      quotients(an, ac, qn);
+    }
+    double bw[K];
 #pragma unroll
-    for (int k = 0; k < K; k++) bpi[k] = beta[k] * p[k];
-    double c = 0.0;   // c(t+1) = sum_j alpha_hat_t(j) eta(j): sum_k alpha_hat(k) beta_hat(k) = 1 at every step
+    for (int k = 0; k < K; k++) bw[k] = beta[k] * qc[k];               // beta_{t+1}(k) p_{t+1}(k) / c_{t+1}
 #pragma unroll
     for (int j = 0; j < K; j++) {
       double eta = 0.0;
 #pragma unroll
-      for (int k = 0; k < K; k++) eta += bpi[k] * P.A[j][k];
+      for (int k = 0; k < K; k++) eta += bw[k] * P.A[j][k];
       beta[j] = eta;
-      c += alpha[j] * eta;
-    }
-    const double rc = 1.0 / c;
 #pragma unroll
-    for (int j = 0; j < K; j++) beta[j] *= rc;
-#else
-    double delta[K];
-    const double rc = 1.0 / forward_step<K, DIM>(P, alpha, p, delta);   // 1 / c(t+1)
-#pragma unroll
-    for (int k = 0; k < K; k++) bpi[k] = beta[k] * p[k];
-#pragma unroll
-    for (int j = 0; j < K; j++) {
-      double eta = 0.0;
-#pragma unroll
-      for (int k = 0; k < K; k++) eta += bpi[k] * P.A[j][k];
-      beta[j] = eta * rc;
-    }
-#endif
-#pragma unroll
-    for (int k = 0; k < K; k++) __stcs(gp + NK * t + k, alpha[k] * beta[k]);
-#pragma unroll
-    for (int j = 0; j < K; j++) {
-      const double aj = alpha[j] * rc;
-#pragma unroll
-      for (int k = 0; k < K; k++) xi[(j * K + k) * kFbThreads] += P.A[j][k] * (aj * bpi[k]);
+      for (int k = 0; k < K; k++) Xi[j][k] = fma(ac[j], bw[k], Xi[j][k]);
     }
 #pragma unroll
-    for (int i = 0; i < DIM; i++) x[i] = xn[i];
+    for (int k = 0; k < K; k++) g[k] = ac[k] * beta[k];
+  };
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  if (UNI) {
+    double g[K];
+    if (Tw >= 1) rows.store(grow + NK * (Tw - 1), alpha);              // gamma(:, T) = alpha_hat(:, T)
+    if (Tw >= 2) {
+      park.start();
+      park.get(a1);
+      quotients(a1, alpha, q1);
+    }
+    for (int t = Tw - 2; t >= 0; t -= 2) {
+      bstep(t, a1, q1, a2, q2, g);
+      rows.store(grow + NK * t, g);
+      if (t >= 1) {
+        bstep(t - 1, a2, q2, a1, q1, g);
+        rows.store(grow + NK * (t - 1), g);
+      }
+    }
+  } else {
+    int odd = 0;                                                       // which pair holds the current step's values
+    for (int t = Tw - 1; t >= 0; t--) {
+      double g[K];
+      if (t < T - 1) {
+        if (odd) bstep(t, a2, q2, a1, q1, g);
+        else bstep(t, a1, q1, a2, q2, g);
+        odd ^= 1;
+      } else if (t == T - 1) {
+#pragma unroll
+        for (int k = 0; k < K; k++) g[k] = alpha[k];
+        if (T >= 2) {
+          park.start();
+          park.get(a1);
+          quotients(a1, alpha, q1);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < K; k++) g[k] = 0.0;
+      }
+      rows.store(grow + NK * t, g);
+    }
   }
-  double *xo = xi_sum + (size_t)K * K * n;
+  if (exists) {
+    double *xo = xi_sum + (size_t)K * K * n;
 #pragma unroll
-  for (int k = 0; k < K; k++)
+    for (int k = 0; k < K; k++)
 #pragma unroll
-    for (int j = 0; j < K; j++) __stcs(xo + j + K * k, xi[(j * K + k) * kFbThreads]);
+      for (int j = 0; j < K; j++) __stcs(xo + j + K * k, P.A[j][k] * Xi[j][k]);
+  }
+}
+
+// Persistent grid (every CTA resident): a warp takes 32 consecutive sequences at a time from a device counter, one
+// sequence per thread; a thread's parking place is the same for every sequence it takes, so the scratch buffer is
+// #resident threads x (maxT - 1 - ts) x K doubles whatever N is, and stays in L2.  A warp whose 32 sequences have one
+// length runs the loops without per-lane conditions (fb_chunk<.., true>); ragged warps take the general variant.
+template <int K, int DIM>
+__global__ void __launch_bounds__(kFbThreads, VB_FB_MINB)
+k_fb(const __grid_constant__ FbPar<K, DIM> P, int N, int maxT, int ts, const int *__restrict__ Tn,
+     const double *__restrict__ X, double *__restrict__ logrho, double *__restrict__ gamma,
+     double *__restrict__ xi_sum, double *__restrict__ phi, double *__restrict__ scratch, int *__restrict__ counter) {
+  __shared__ __align__(16) double s_tab[kFbTabDoubles];
+  __shared__ __align__(16) double s_rows[kFbThreads / 32][2 * RowStore<K>::kBuf];
+  __shared__ __align__(16) double s_obs[VB_FB_RING * ObsRing<DIM>::kSlot];
+  const unsigned xring = (unsigned)__cvta_generic_to_shared(s_obs) + threadIdx.x * (DIM * 8u);
+  extern __shared__ double s_park[];
+  vbhem::tab_t etab, ltab;
+  stage_tables<kFbThreads>(s_tab, etab, ltab);
+  Park<K> park;
+  park.ts = ts;
+  park.sm = s_park + threadIdx.x;
+  park.sbase = (unsigned)__cvta_generic_to_shared(park.sm);
+  park.last = -1;
+  park.gl = scratch + ((size_t)blockIdx.x * (maxT > 1 + ts ? maxT - 1 - ts : 0) - ts) * Park<K>::kRow + threadIdx.x;
+  park.pol = l2_keep_policy();
+  RowStore<K> rows;
+  rows.lane = threadIdx.x & 31;
+  rows.buf = s_rows[threadIdx.x >> 5];
+  rows.flip = 0;
+  rows.nvalid = 0;
+  for (;;) {
+    int base = 0;
+    if (rows.lane == 0) base = atomicAdd(counter, 32);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= N) break;
+    const int n = base + rows.lane;
+    const int T = n < N ? Tn[n] : 0;
+    const int Tw = __reduce_max_sync(0xffffffffu, T);
+    rows.nvalid = K * (N - base < 32 ? N - base : 32);
+    if (__all_sync(0xffffffffu, T == Tw && n < N))
+      fb_chunk<K, DIM, true>(P, base, N, maxT, Tw, Tw, X, logrho, gamma, xi_sum, phi, park, rows, xring, etab, ltab);
+    else
+      fb_chunk<K, DIM, false>(P, base, N, maxT, T, Tw, X, logrho, gamma, xi_sum, phi, park, rows, xring, etab, ltab);
+  }
 }
 
 // ---- M-step statistics of vbhmm_em.m:158-246 and the fb-dependent lower-bound terms (vbhmm_em_lb.m:214,217)
@@ -515,7 +746,7 @@ struct vbhmm_data {
   int device = 0, N = 0, dim = 0, maxT = 0;
   long long total = 0;         // sum_n T_n
   cudaStream_t st = nullptr;
-  Buf Tn, X, par, logrho, gamma, xi, phi, mom_partial, mom_out;
+  Buf Tn, X, par, logrho, gamma, xi, phi, mom_partial, mom_out, scratch, counter;
   cudaEvent_t ev[2] = {nullptr, nullptr};
   double last_ms = 0.0;
   int lastK = 0;
@@ -538,22 +769,35 @@ int launch_fb_t(vbhmm_data *h, const double *m, const double *W, const double *v
     for (int j = 0; j < K; j++) P.A[k][j] = A[k + K * j];
   }
   P.cden = cden;
-  const int blocks = (h->N + kFbThreads - 1) / kFbThreads;
-  size_t smem = sizeof(double) * K * K * kFbThreads;
-#if VB_FB_BLOCKS > 0
-  if (smem < (size_t)(220 * 1024) / VB_FB_BLOCKS - 1024) smem = (size_t)(220 * 1024) / VB_FB_BLOCKS - 1024;
-#endif
-  cudaFuncSetAttribute(k_fb<K, DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_fb<K, DIM><<<blocks, kFbThreads, smem, h->st>>>(P, h->N, h->maxT, h->Tn.as<int>(), h->X.as<double>(),
+  // persistent grid: every CTA resident; the last steps' alpha_hat parks in shared memory, the rest in the L2-sized scratch
+  int sms = 148, smem_sm = 227 * 1024;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+  cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, h->device);
+  const int want = (h->N + kFbThreads - 1) / kFbThreads;
+  const int blocks = want < sms * VB_FB_MINB ? want : sms * VB_FB_MINB;
+  const size_t per_step = sizeof(double) * K * kFbThreads;
+  const size_t budget = (size_t)smem_sm / VB_FB_MINB - sizeof(double) * (kFbTabDoubles + (kFbThreads / 32) * 2 * RowStore<K>::kBuf +
+                                                                                VB_FB_RING * DIM * kFbThreads) -
+                        2048;                                      // 1 KB per CTA is the system's
+  const int parked = h->maxT > 1 ? h->maxT - 1 : 0;
+  int ts = (int)(budget / per_step);
+  if (ts > parked) ts = parked;
+  if (ts < 1) ts = 1;
+  if (parked > ts && ts <= VB_FB_AHEAD) return -2;     // the ring must be longer than its look-ahead (never for K <= 8)
+  const size_t smem = per_step * (size_t)ts;
+  const size_t scratch = per_step * (size_t)(parked > ts ? parked - ts : 0) * blocks;
+  if (h->scratch.ensure(scratch) != cudaSuccess || h->counter.ensure(sizeof(int)) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(k_fb<K, DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+  cudaMemsetAsync(h->counter.p, 0, sizeof(int), h->st);
+  k_fb<K, DIM><<<blocks, kFbThreads, smem, h->st>>>(P, h->N, h->maxT, ts, h->Tn.as<int>(), h->X.as<double>(),
                                                  stats ? nullptr : h->logrho.as<double>(), h->gamma.as<double>(),
-                                                 h->xi.as<double>(), h->phi.as<double>());
+                                                 h->xi.as<double>(), h->phi.as<double>(), h->scratch.as<double>(),
+                                                 h->counter.as<int>());
   if (!stats) return 1;
   using L = MomLayout<K, DIM>;
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
   const long long tot = (long long)h->N * h->maxT;
-  long long want = (tot + kMomThreads - 1) / kMomThreads;
-  const int mb = (int)(want < 1 ? 1 : (want > 8LL * sms ? 8LL * sms : want));
+  const long long wantm = (tot + kMomThreads - 1) / kMomThreads;
+  const int mb = (int)(wantm < 1 ? 1 : (wantm > 8LL * sms ? 8LL * sms : wantm));
   if (h->mom_partial.ensure(sizeof(double) * (size_t)L::total * mb) != cudaSuccess ||
       h->mom_out.ensure(sizeof(double) * L::total) != cudaSuccess)
     return -1;
@@ -600,7 +844,8 @@ int run_fb(vbhmm_data *h, int K, const double *m, const double *W, const double 
       case 8: launched = launch_fb_k<8>(h, m, W, v, beta, lLT, cden, pz1, A, stats); break;
     }
   }
-  if (launched < 0) return fail_fb(VBHEM_ENOMEM, "out of device memory for the moment partials");
+  if (launched == -2) return fail_fb(VBHEM_ECUDA, "vbhmm_fb: shared memory too small for the alpha_hat ring");
+  if (launched < 0) return fail_fb(VBHEM_ENOMEM, "out of device memory for the scratch buffer / moment partials");
   if (!launched) {
     // model to HBM: m | W | v | dob | lLT | pz1 | A
     const size_t nd = (size_t)dim * K + (size_t)dim * dim * K + 4 * (size_t)K + (size_t)K * K;
@@ -710,7 +955,8 @@ int vbhmm_free_data(vbhmm_data_t *h) {
   cudaSetDevice(h->device);
   if (h->st) { cudaStreamSynchronize(h->st); cudaStreamDestroy(h->st); }
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
-  Buf *all[] = {&h->Tn, &h->X, &h->par, &h->logrho, &h->gamma, &h->xi, &h->phi, &h->mom_partial, &h->mom_out};
+  Buf *all[] = {&h->Tn, &h->X, &h->par, &h->logrho, &h->gamma, &h->xi, &h->phi, &h->mom_partial, &h->mom_out, &h->scratch,
+                &h->counter};
   for (Buf *b : all) b->release();
   delete h;
   return VBHEM_OK;
