@@ -59,10 +59,10 @@ constexpr int kFbThreads = VB_FB_THREADS;
 #define VB_FB_MINB 2       // resident CTAs per SM: 256 sequences in flight per SM, <= 255 registers (Xi lives in registers)
 #endif
 #ifndef VB_FB_RING
-#define VB_FB_RING 8       // slots of the observation ring (cp.async RING - 1 steps ahead); a power of two
+#define VB_FB_RING 4       // slots of the observation ring (cp.async RING - 1 steps ahead); a power of two
 #endif
 #ifndef VB_FB_AHEAD
-#define VB_FB_AHEAD 6      // the backward pass copies parked alpha_hat from the scratch buffer this many steps ahead
+#define VB_FB_AHEAD 4      // the backward pass copies parked alpha_hat from the scratch buffer this many steps ahead
 #endif
 #ifndef VB_FB_HINT
 #define VB_FB_HINT 1       // 1: L2 evict_last on the parked alpha_hat (scripts/sweep_fb.sh A/Bs it)
@@ -170,10 +170,22 @@ __device__ __forceinline__ unsigned long long l2_keep_policy() {
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
+__device__ __forceinline__ unsigned long long l2_stream_policy() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+#define VB_CP_HINT ".L2::cache_hint"
+#define VB_CP_POL(p) , "l"(p)
+#define VB_CP_ARG ", %2"
 __device__ __forceinline__ void st_keep(double *q, double v, unsigned long long pol) {
   asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(q), "d"(v), "l"(pol) : "memory");
 }
 #else
+#define VB_CP_HINT ""
+#define VB_CP_POL(p)
+#define VB_CP_ARG ""
+__device__ __forceinline__ unsigned long long l2_stream_policy() { return 0ull; }
 __device__ __forceinline__ unsigned long long l2_keep_policy() { return 0ull; }
 __device__ __forceinline__ void st_keep(double *q, double v, unsigned long long) { *q = v; }
 #endif
@@ -188,16 +200,19 @@ struct ObsRing {
   size_t stride;                                       // N * DIM
   unsigned base;                                       // shared address of the lane's place in slot 0
   int T;
+  unsigned long long pol;                              // L2 evict_first: every observation is read once
   __device__ __forceinline__ void request(int u) const {              // observation u -> slot u % RING (a group either way)
     if (u < T) {
       const unsigned dst = base + (unsigned)(u % VB_FB_RING) * (kSlot * 8u);
       const double *src = xp + stride * u;
       if constexpr (DIM == 2) {
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+        asm volatile("cp.async.cg.shared.global" VB_CP_HINT " [%0], [%1], 16" VB_CP_ARG ";" ::"r"(dst), "l"(src) VB_CP_POL(pol)
+                     : "memory");
       } else {
 #pragma unroll
         for (int d = 0; d < DIM; d++)
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * d), "l"(src + d) : "memory");
+          asm volatile("cp.async.ca.shared.global" VB_CP_HINT " [%0], [%1], 8" VB_CP_ARG ";" ::"r"(dst + 8u * d), "l"(src + d)
+                       VB_CP_POL(pol) : "memory");
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -253,8 +268,8 @@ struct Park {
       const double *src = gl + (size_t)rq * kRow;
 #pragma unroll
       for (int k = 0; k < K; k++)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + k * (kFbThreads * 8u)), "l"(src + k * kFbThreads)
-                     : "memory");
+        asm volatile("cp.async.ca.shared.global" VB_CP_HINT " [%0], [%1], 8" VB_CP_ARG ";" ::"r"(dst + k * (kFbThreads * 8u)),
+                     "l"(src + k * kFbThreads) VB_CP_POL(pol) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     rq++;
@@ -341,6 +356,7 @@ __device__ __forceinline__ void fb_chunk(const FbPar<K, DIM> &P, int base, int N
   obs.stride = ND;
   obs.base = xring;
   obs.T = T;
+  obs.pol = l2_stream_policy();
   obs.start();
   auto next_obs = [&](int t, double (&l)[K], double (&q)[K]) -> double {   // logrho(:, t), p(:, t), the shift; t < T
     double x[DIM];
