@@ -317,15 +317,27 @@ def vbhmm_em_batch(seqs: _fb.SequenceSet, runs, K: int, ini: dict, inits: list) 
         check(lib().vbhmm_batch_last_ms(h, C.byref(ms)))
     finally:
         check(lib().vbhmm_batch_free(h))
+    # point estimates of all runs at once (vbhmm_em.m:391-460; _hmm_from_varpar is the one-run form): the per-run loop
+    # below only slices
+    eps_all = np.ascontiguousarray(np.transpose(o["eps"], (0, 2, 1)))                  # [R, from, to]
+    W_all = np.ascontiguousarray(np.transpose(o["W"], (0, 1, 3, 2)))                   # [R, K, i, j]
+    M_all = np.ascontiguousarray(np.transpose(o["M"], (0, 2, 1)))
+    vv_all = o["v"]
+    Ci = np.linalg.inv(W_all) / np.where(vv_all > dim + 1, vv_all - dim - 1, vv_all)[:, :, None, None]
+    cov_all = (Ci + np.transpose(Ci, (0, 1, 3, 2))) / 2
+    prior_all = o["alpha"] / o["alpha"].sum(1, keepdims=True)
+    rs = eps_all.sum(2, keepdims=True)
+    trans_all = eps_all / np.where(rs == 0, 1.0, rs)
+    mean_all = o["m"].copy()
+    its = o["it"].astype(int)
+    LL_last = o["LLs"][np.arange(R), np.maximum(its, 1) - 1]
     out = []
     for r in range(R):
-        vp = dict(alpha=o["alpha"][r], epsilon=o["eps"][r].T.copy(), beta=o["beta"][r], v=o["v"][r], m=o["m"][r],
-                  W=np.transpose(o["W"][r], (0, 2, 1)).copy())
-        hm = _hmm_from_varpar(vp, K)
-        n = int(o["it"][r])
-        hm.update(LL=float(o["LLs"][r, n - 1]), LLs=o["LLs"][r, :n].copy(), iter=n, unstable=bool(o["bad"][r]),
-                  M=o["M"][r].T.copy(), N1=o["Nk1"][r].copy(), N=o["Nk"][r].copy())
-        out.append(hm)
+        n = its[r]
+        vp = dict(alpha=o["alpha"][r], epsilon=eps_all[r], beta=o["beta"][r], v=vv_all[r], m=o["m"][r], W=W_all[r])
+        out.append(dict(prior=prior_all[r], trans=trans_all[r], mean=mean_all[r], cov=cov_all[r], varpar=vp, K=K,
+                        LL=float(LL_last[r]), LLs=o["LLs"][r, :n], iter=int(n), unstable=bool(o["bad"][r]),
+                        M=M_all[r], N1=o["Nk1"][r], N=o["Nk"][r]))
     return out, dict(passes=passes.value, device_ms=ms.value)
 
 
