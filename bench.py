@@ -67,7 +67,9 @@ def make_config(a, world, grid=False, K=None, models=None):
                parallelism=f"strong scaling: bases sharded x{world} ({a.bases // world} per GPU), centres replicated, "
                            "one all-reduce of the per-centre statistics inside the C ABI (vbhem_multi_*: over NVLink "
                            "peer memory, NCCL where peers cannot be mapped)",
-               l2="flushed between timed steps (256 MiB write)")
+               l2="flushed between timed steps (256 MiB write)",
+               start="every timed step starts after a device-side rendezvous of the ranks (vbhem_multi_align, outside the "
+                     "timed region): an EM loop is aligned the same way by its previous iteration's all-reduce")
     if models is not None:
         cfg["models"] = models
     return cfg
@@ -429,7 +431,8 @@ def main():
         for _ in range(steps):
             flush.zero_()
             barrier()
-            ms.estep_hyp_dev(P, tau)
+            ms.align()                 # device-side rendezvous: the ranks' E-steps start together (the hosts' launch skew
+            ms.estep_hyp_dev(P, tau)   # after the NCCL barrier would otherwise be waited out inside the all-reduce)
             ms.synchronize()
             tot += ms.last_ms()
             if profile:
@@ -556,6 +559,7 @@ def main():
         for _ in range(4):
             flush.zero_()
             barrier()
+            ms.align()
             ms.estep_hyp_dev(P5, tau)
             ms.synchronize()
             late.append(ms.last_ms())
@@ -659,6 +663,7 @@ def main():
                 for _ in range(a.steps):
                     flush.zero_()
                     torch.cuda.synchronize()
+                    m1.align()
                     m1.estep_hyp_dev(P1, tau)
                     m1.synchronize()
                     dev.append(m1.last_ms())

@@ -102,6 +102,7 @@ SIGNATURES = {
     "vbhem_multi_estep_hyp_dev": (C.c_int, [vp, C.c_int, ip, C.c_int, ip, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, dp,
                                             C.c_int]),
     "vbhem_multi_synchronize": (C.c_int, [vp]),
+    "vbhem_multi_align": (C.c_int, [vp]),
     "vbhem_multi_stats": (C.c_int, [vp, dp]),
     "vbhem_multi_fetch": (C.c_int, [vp, dp, dp]),
     "vbhem_multi_finalize_stats": (C.c_int, [vp, C.c_int, ip, C.c_int, C.c_int, dp]),

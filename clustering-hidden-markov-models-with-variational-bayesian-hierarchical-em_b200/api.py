@@ -467,6 +467,11 @@ class MultiBaseSet:
     def synchronize(self):
         check(lib().vbhem_multi_synchronize(self._h))
 
+    def align(self):
+        """Device-side rendezvous of every shard of every rank (``vbhem_multi_align``): what is enqueued next starts on
+        all devices together, whatever the launch skew of the host processes."""
+        check(lib().vbhem_multi_align(self._h))
+
     def stats(self, P: dict) -> np.ndarray:
         buf = np.zeros(self.stats_size(P["K"], P["r"], P["ng"]))
         check(lib().vbhem_multi_stats(self._h, _d(buf)))

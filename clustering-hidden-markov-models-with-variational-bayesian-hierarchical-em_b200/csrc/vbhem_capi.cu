@@ -144,7 +144,7 @@ struct vbhem_base {
   // centre set (per call)
   DevBuf up, cen_d, rec, tile_i, pair_rec;   // up: the upload arena of stage_centres
   // results and work lists
-  DevBuf L, z, flags, fbcount, Njp, lbp, cnt, offs, segs, items, partial, itemflags, scratch, pairs_out, stats;
+  DevBuf L, z, flags, fbcount, Njp, lbp, cnt, offs, segs, items, partial, itemflags, scratch, pairs_out, stats, align;
   // streamed E-step (base set in host memory): copy-in / copy-out streams and per-slice events
   cudaStream_t cin = nullptr, cout = nullptr;
   std::vector<cudaEvent_t> slice_ev;
@@ -847,7 +847,7 @@ int vbhem_free_base(vbhem_base_t *h) {
   if (h->em.h_lb) cudaFreeHost(h->em.h_lb);
   DevBuf *all[] = {&h->bSb, &h->bprior, &h->bA, &h->bmu, &h->bcov, &h->bNt, &h->up, &h->cen_d, &h->rec,
                    &h->L, &h->z, &h->flags, &h->fbcount, &h->Njp, &h->lbp, &h->cnt, &h->offs, &h->segs, &h->items,
-                   &h->partial, &h->itemflags, &h->scratch, &h->pairs_out, &h->stats, &h->tile_i, &h->pair_rec};
+                   &h->partial, &h->itemflags, &h->scratch, &h->pairs_out, &h->stats, &h->tile_i, &h->pair_rec, &h->align};
   for (DevBuf *b : all) b->release();
   if (h->h_totals) cudaFreeHost(h->h_totals);
   h->stage.release();

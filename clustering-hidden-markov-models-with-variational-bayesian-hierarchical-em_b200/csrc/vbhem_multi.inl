@@ -677,6 +677,19 @@ int vbhem_multi_synchronize(vbhem_multi_t *m) {
   return VBHEM_OK;
 }
 
+int vbhem_multi_align(vbhem_multi_t *m) {
+  int rc = check_multi(m);
+  if (rc) return rc;
+  if (m->world == 1) return VBHEM_OK;
+  return m->run_all([&](int k) -> int {
+    vbhem_base *h = m->h[k];
+    CU(cudaSetDevice(h->device));
+    CU(h->align.ensure(sizeof(double)));
+    CU(cudaMemsetAsync(h->align.p, 0, sizeof(double), h->st));
+    return allreduce_stats(m, k, h->align.as<double>(), 1);
+  });
+}
+
 int vbhem_multi_stats(vbhem_multi_t *m, double *stats) {
   int rc = check_multi(m);
   if (rc) return rc;

@@ -333,6 +333,12 @@ int vbhem_multi_estep_hyp_dev(vbhem_multi_t *multi, int K, const int32_t *Sr, in
                               int ngroups, int tau, const double *alpha, const double *eta, const double *epsilon,
                               const double *m, const double *W, const double *v, const double *lambda, int finalize);
 int vbhem_multi_synchronize(vbhem_multi_t *multi);
+/* Device-side rendezvous of all shards of all ranks: enqueues a one-element all-reduce (the same exchange the E-step
+ * uses) on every shard's stream and returns.  Whatever is enqueued next starts on every device within a few
+ * microseconds of the last device arriving, whatever the hosts' launch skew: an EM loop is aligned like this by the
+ * all-reduce of its previous iteration; a caller that issues single E-steps from several processes (bench.py) calls it
+ * before the step it wants to time. */
+int vbhem_multi_align(vbhem_multi_t *multi);
 int vbhem_multi_stats(vbhem_multi_t *multi, double *stats);
 int vbhem_multi_fetch(vbhem_multi_t *multi, double *L_elbo, double *zhat);
 int vbhem_multi_finalize_stats(vbhem_multi_t *multi, int K, const int32_t *Sr, int maxSr, int ngroups, double *stats);

@@ -82,6 +82,25 @@ def test_multi_estep_equals_single_gpu(N):
     np.testing.assert_allclose(got["zhat"], want_or["zhat"], rtol=1e-9, atol=1e-12)
 
 
+def test_align_is_a_rendezvous_and_leaves_results_alone():
+    """vbhem_multi_align: a one-element all-reduce on every shard's stream (peer epochs advance with it); the E-steps
+    around it give the bits they give without it."""
+    devs = two()
+    base, hyp, cen = make_case(N=901, K=5, Sb=6, Sr=5, d=2, covmode="full", ragged=True, seed=17, Nv=15.0)
+    with api().MultiBaseSet(base, devices=devs) as ms:
+        want = ms.estep_hyp(hyp, 8, want_pairs=False)["buf"]
+        for _ in range(3):                 # odd count: the next E-step uses the other exchange buffer
+            ms.align()
+        ms.synchronize()
+        got = ms.estep_hyp(hyp, 8, want_pairs=False)["buf"]
+        ms.align()
+        got2 = ms.estep_hyp(hyp, 8, want_pairs=False)["buf"]
+    assert np.array_equal(got, want) and np.array_equal(got2, want)
+    with api().MultiBaseSet(base, devices=[0]) as one:
+        one.align()                        # one device: nothing to meet
+        one.synchronize()
+
+
 def test_peer_and_nccl_all_reduce_agree(monkeypatch):
     """The all-reduce over peer memory (k_allreduce_peer, the default where the devices can map each other) against
     ncclAllReduce (VBHEM_ALLREDUCE=nccl): same sums up to the order of the additions."""
