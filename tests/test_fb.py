@@ -191,6 +191,42 @@ def test_cuda_fb_stats_rejects_generic_shapes():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("ragged", [True, False])
+def test_cuda_fb_many_chunks_elementwise(ragged):
+    """More sequences than the persistent grid has threads (every warp takes several chunks from the device counter),
+    lengths beyond the shared-memory ring (the parked alpha_hat goes through the L2 scratch and cp.async), ragged warps
+    and uniform ones: a sample of sequences element-wise against the plain-C oracle, which is per sequence."""
+    from vbhem_b200 import fb
+    N, K, dim, maxT = 90_000, 5, 2, 41
+    rng = np.random.default_rng(77)
+    lens = rng.integers(0, maxT + 1, size=N) if ragged else np.full(N, maxT)
+    lens[0] = maxT
+    means = rng.normal(size=(K, dim)) * 60 + np.array([256.0, 192.0])
+    z = rng.integers(0, K, size=(N, maxT))
+    Xall = means[z] + rng.normal(size=(N, maxT, dim)) * 15
+    data = [Xall[n, :lens[n]] for n in range(N)]
+    _, vp = make_fb_case(N=4, K=K, dim=dim, maxT=5, seed=78)
+    vp["m"] = means + rng.normal(size=(K, dim)) * 5
+    got = fb.vbhmm_fb(data, vp)
+    pick = np.unique(np.concatenate([[0, 1, 31, 32, N - 1, N - 2], rng.integers(0, N, size=600),
+                                     np.arange(37_888 - 40, 37_888 + 40)]))      # around the grid's first full round
+    want = cref.port_vbhmm_fb(cref.pack_sequences([data[n] for n in pick]), nr.vbhmm_fb_prepass(vp))
+    sub = dict(logrho_Saved=got["logrho_Saved"][pick], gamma_all=got["gamma_all"][pick], xi_sum=got["xi_sum"][pick],
+               phi_norm=got["phi_norm"][pick])
+    # the sample's own maxT may be shorter than the full set's: compare the common steps, the rest must be zeros
+    Ts = want["gamma_all"].shape[1]
+    for k in ("logrho_Saved", "gamma_all"):
+        assert not sub[k][:, Ts:].any(), k
+        sub[k] = sub[k][:, :Ts]
+    assert_fb_close(sub, want)
+    g = got["gamma_all"]
+    live = np.arange(maxT)[None, :] < lens[:, None]
+    np.testing.assert_allclose(g.sum(2)[live], 1.0, rtol=1e-11)
+    assert not g[~live].any() and not got["logrho_Saved"][~live].any()
+    np.testing.assert_allclose(got["xi_sum"].sum((1, 2)), np.maximum(lens - 1, 0), rtol=1e-11, atol=1e-13)
+
+
+@pytest.mark.gpu
 def test_cuda_fb_full_size_properties():
     """BASELINE configs[4] scale (200 k of the 1 M sequences, T = 50, S = 5, d = 2): size-independent properties
     of the literal outputs, and the fused statistics against sums of those outputs."""
