@@ -463,26 +463,30 @@ __device__ __forceinline__ void fb_chunk(const FbPar<K, DIM> &P, int base, int N
       }
     }
   } else {
-    int odd = 0;                                                       // which pair holds the current step's values
-    for (int t = Tw - 1; t >= 0; t--) {
+    // ragged warp: a lane joins at its own t = T - 1.  Which register pair is "current" follows the parity of t, not of
+    // the lane's own step count, so the two instantiations of the step are a warp-uniform branch (with per-lane parity
+    // half of the lanes would run one, half the other, one after the other).
+    auto body = [&](int t, double (&ac)[K], double (&qc)[K], double (&an)[K], double (&qn)[K]) {
       double g[K];
       if (t < T - 1) {
-        if (odd) bstep(t, a2, q2, a1, q1, g);
-        else bstep(t, a1, q1, a2, q2, g);
-        odd ^= 1;
+        bstep(t, ac, qc, an, qn, g);
       } else if (t == T - 1) {
 #pragma unroll
         for (int k = 0; k < K; k++) g[k] = alpha[k];
-        if (T >= 2) {
+        if (T >= 2) {                                                  // what step t - 1 will find as its current pair
           park.start();
-          park.get(a1);
-          quotients(a1, alpha, q1);
+          park.get(an);
+          quotients(an, alpha, qn);
         }
       } else {
 #pragma unroll
         for (int k = 0; k < K; k++) g[k] = 0.0;
       }
       rows.store(grow + NK * t, g);
+    };
+    for (int t = Tw - 1; t >= 0; t--) {
+      if (t & 1) body(t, a2, q2, a1, q1);
+      else body(t, a1, q1, a2, q2);
     }
   }
   if (exists) {
