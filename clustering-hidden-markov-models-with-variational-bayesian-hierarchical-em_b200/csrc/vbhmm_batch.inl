@@ -115,6 +115,7 @@ __global__ void k_batch_prepass(int R, const unsigned char *__restrict__ done, c
     }
   }
   P.cden = DIM * 0.5 * 1.8378770664093454836;                         // dim * log(2 pi) / 2
+  fb_finish_par(P);
 }
 
 // k_fb for work item w = (run, sequence): the model of the item's run comes from HBM through L1 (the items of a
