@@ -353,6 +353,7 @@ def main():
         red = cref.port_reduce(zs["Z"], dict(pairs_sub, L_elbo=np.ascontiguousarray(L_ref[:, sub])), pc["maxSr"],
                                pb0["d"], pb0["covmode"])
         oracle = dict(n=cores * nb, L=L_ref, zhat=zz["zhat"], sub=sub, red=red, Nj=zs["Nj"], lb=zs["lb"], cen=cen)
+        pc_full = pc
 
     import torch
     from vbhem_b200._lib import check, lib
@@ -534,6 +535,36 @@ def main():
                 lb_ref, _ = nr.lower_bound(want["lb"][0], want["lb"][1], want["Nj"], oracle["cen"]["logOmega"],
                                            hyp["alpha"], centres, pre, opt, "full")
                 parity.update(LB_rel=float(abs(lb_dev - lb_ref) / abs(lb_ref)), LB_device=lb_dev, LB_oracle=float(lb_ref))
+            # the reference arm's OWN work on the GPU: the literal MEX boundary, all six per-pair outputs
+            # of EVERY pair (no skip rule, no z_hat, no reduction), host buffers in and out -- what cpu_baseline times
+            try:
+                pcs, ns, r_ = pc_full, len(sub), int(pc_full["maxSr"])
+                dI = lambda x: np.ascontiguousarray(x, dtype=np.int32).ctypes.data_as(C.POINTER(C.c_int32))
+                dD = lambda x: x.ctypes.data_as(C.POINTER(C.c_double))
+                o = dict(L=np.zeros((K, ns)), nu1=np.zeros((K, ns, r_)), xi=np.zeros((K, ns, r_, r_)), pr=np.zeros((K, ns, r_)),
+                         mu=np.zeros((K, ns, d, r_)), Mu=np.zeros((K, ns, d * d, r_)))      # full covariance (the bench workloads)
+                Srs = np.ascontiguousarray(pcs["Sr"], dtype=np.int32)
+                call = lambda: check(L.vbhem_estep_pairs(bsub._h, K, dI(Srs), r_, tau, dD(pcs["logPi"]), dD(pcs["logA"]),
+                                                         dD(pcs["m"]), dD(pcs["vW"]), dD(pcs["cterm"]), dD(o["L"]),
+                                                         dD(o["nu1"]), dD(o["xi"]), dD(o["pr"]), dD(o["mu"]), dD(o["Mu"])))
+                call()                                                                # warm-up
+                reps, t0 = 3, time.perf_counter()
+                for _ in range(reps):
+                    call()
+                dt = (time.perf_counter() - t0) / reps
+                lit = dict(L_elbo=o["L"].T)
+                npair = len(sub) * K
+                same_work = dict(pairs=npair, gpu_pairs_per_s=npair / dt, cpu_pairs_per_s=cpu["value"],
+                                 ratio=npair / dt / cpu["value"],
+                                 L_elbo_max_rel=rel(lit["L_elbo"].T, Lg[:, sub]),
+                                 note="vbhem_estep_pairs (Boundary-1: L_elbo, nu_1, xi, and the three emission "
+                                      "statistics of every pair, no skip rule) over stats_bases bases x all centres, wall "
+                                      "clock of the C-ABI call including the device-to-host copy of the six outputs "
+                                      "(1 KB per pair, pageable host arrays) -- the same outputs the reference arm "
+                                      "produces; the headline compares the fused E-step instead")
+                cpu["same_work"] = same_work
+            except Exception as e:  # noqa: BLE001
+                cpu["same_work"] = dict(error=f"{type(e).__name__}: {e}")
         parity["note"] = ("L_elbo, z_hat: the rows of the first bases_compared bases of the FULL run, element-wise "
                           "against the reference's C (oracle/_ref); statistics / Lt1 / Lt7 / LB: fused E-step over "
                           "stats_bases of them against the oracle's skip-rule reduction and numpy lower bound; "
