@@ -121,7 +121,7 @@ __global__ void k_batch_prepass(int R, const unsigned char *__restrict__ done, c
 // k_fb for work item w = (run, sequence): the model of the item's run comes from HBM through L1 (the items of a
 // run are neighbours, so a warp reads one or two models), gamma / xi / phi are indexed by the work item.
 template <int K, int DIM>
-__global__ void __launch_bounds__(kFbThreads, 3)
+__global__ void __launch_bounds__(kFbThreads, K <= 6 ? 3 : 2)      // the K x K pair marginals live in registers
 k_fb_batch(const FbPar<K, DIM> *__restrict__ pars, const unsigned char *__restrict__ done, int Wn, int N, int maxT,
            const int *__restrict__ run_of, const int *__restrict__ seq_of, const int *__restrict__ Tn,
            const double *__restrict__ X, double *__restrict__ gamma, double *__restrict__ xi_sum,
@@ -153,58 +153,50 @@ k_fb_batch(const FbPar<K, DIM> *__restrict__ pars, const unsigned char *__restri
     } else {
       c = forward_step<K, DIM>(P, alpha, p, delta);
     }
-    const double rc = 1.0 / c;
+    const double rc = rcp_pos(c);
 #pragma unroll
     for (int k = 0; k < K; k++) { alpha[k] = delta[k] * rc; gp[WK * t + k] = alpha[k]; }
     sumlogc += vbhem::log_shift<1>(c, ltab, 0);
   }
   phi[w] = sumlogc * vbhem::kUnit + summax;
-  // the K x K pair-marginal accumulator of each thread lives in shared memory ([j][k][thread]: conflict-free), as in k_fb
-  extern __shared__ double xis[];
-  double *xi = xis + threadIdx.x;
-  double beta[K];
+  // backward pass as in k_fb (vbhmm_fb.cu): the emissions are not evaluated again -- p_{t+1}(k) / c_{t+1} =
+  // alpha_hat_{t+1}(k) / sum_j alpha_hat_t(j) A(j,k) -- and the pair marginals accumulate in registers as
+  // sum_t alpha_hat_t (x) (beta_hat p / c), multiplied by A once at the end.  alpha = alpha_hat(t+1) on entry.
+  double Xi[K][K], beta[K];
 #pragma unroll
   for (int j = 0; j < K; j++) {
     beta[j] = 1.0;
 #pragma unroll
-    for (int k = 0; k < K; k++) xi[(j * K + k) * kFbThreads] = 0.0;
+    for (int k = 0; k < K; k++) Xi[j][k] = 0.0;
   }
   for (int t = T - 2; t >= 0; t--) {
+    double a[K], bw[K];
 #pragma unroll
-    for (int k = 0; k < K; k++) alpha[k] = gp[WK * t + k];
+    for (int k = 0; k < K; k++) a[k] = gp[WK * t + k];
 #pragma unroll
-    for (int i = 0; i < DIM; i++) x[i] = xp[ND * (t + 1) + i];
-    emissions<K, DIM>(P, x, lr);
-    shifted_exp<K>(lr, p, etab);
-    double bpi[K];
+    for (int k = 0; k < K; k++) {
+      double pred = 1e-300;
 #pragma unroll
-    for (int k = 0; k < K; k++) bpi[k] = beta[k] * p[k];
-    double c = 0.0;                                                     // c(t+1) = sum_j alpha_hat_t(j) eta(j), see k_fb
+      for (int j = 0; j < K; j++) pred += a[j] * P.A[j][k];
+      bw[k] = beta[k] * (alpha[k] * rcp_pos(pred));
+    }
 #pragma unroll
     for (int j = 0; j < K; j++) {
       double eta = 0.0;
 #pragma unroll
-      for (int k = 0; k < K; k++) eta += bpi[k] * P.A[j][k];
+      for (int k = 0; k < K; k++) eta += bw[k] * P.A[j][k];
       beta[j] = eta;
-      c += alpha[j] * eta;
+#pragma unroll
+      for (int k = 0; k < K; k++) Xi[j][k] = fma(a[j], bw[k], Xi[j][k]);
     }
-    const double rc = 1.0 / c;
 #pragma unroll
-    for (int j = 0; j < K; j++) beta[j] *= rc;
-#pragma unroll
-    for (int k = 0; k < K; k++) gp[WK * t + k] = alpha[k] * beta[k];
-#pragma unroll
-    for (int j = 0; j < K; j++) {
-      const double aj = alpha[j] * rc;
-#pragma unroll
-      for (int k = 0; k < K; k++) xi[(j * K + k) * kFbThreads] += P.A[j][k] * (aj * bpi[k]);
-    }
+    for (int k = 0; k < K; k++) { gp[WK * t + k] = a[k] * beta[k]; alpha[k] = a[k]; }
   }
   double *xo = xi_sum + (size_t)K * K * w;
 #pragma unroll
   for (int j = 0; j < K; j++)
 #pragma unroll
-    for (int k = 0; k < K; k++) xo[j * K + k] = xi[(j * K + k) * kFbThreads];   // [from][to]
+    for (int k = 0; k < K; k++) xo[j * K + k] = P.A[j][k] * Xi[j][k];   // [from][to]
 }
 
 // Per-run state of the EM loop (vbhmm_em.m:108-418).
@@ -445,9 +437,7 @@ int batch_pass(vbhmm_batch *b, int max_iter, double min_diff) {
   const int R = b->R, Wn = b->Wn;
   k_batch_prepass<K, DIM><<<(R + 127) / 128, 128, 0, h->st>>>(R, b->done.as<unsigned char>(), b->vp.as<VarPar<K, DIM>>(),
                                                            b->par.as<FbPar<K, DIM>>(), b->pre.as<PreOut<K>>());
-  const size_t smem = sizeof(double) * K * K * kFbThreads;
-  cudaFuncSetAttribute(k_fb_batch<K, DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_fb_batch<K, DIM><<<(Wn + kFbThreads - 1) / kFbThreads, kFbThreads, smem, h->st>>>(
+  k_fb_batch<K, DIM><<<(Wn + kFbThreads - 1) / kFbThreads, kFbThreads, 0, h->st>>>(
       b->par.as<FbPar<K, DIM>>(), b->done.as<unsigned char>(), Wn, h->N, h->maxT, b->run_of.as<int>(),
       b->seq_of.as<int>(), h->Tn.as<int>(), h->X.as<double>(), b->gamma.as<double>(), b->xi.as<double>(),
       b->phi.as<double>());
