@@ -82,12 +82,16 @@ def test_multi_estep_equals_single_gpu(N):
     np.testing.assert_allclose(got["zhat"], want_or["zhat"], rtol=1e-9, atol=1e-12)
 
 
-def test_align_is_a_rendezvous_and_leaves_results_alone():
+@pytest.mark.parametrize("mode", ["peer", "nccl"])
+def test_align_is_a_rendezvous_and_leaves_results_alone(mode, monkeypatch):
     """vbhem_multi_align: a one-element all-reduce on every shard's stream (peer epochs advance with it); the E-steps
     around it give the bits they give without it."""
     devs = two()
+    if mode == "nccl":
+        monkeypatch.setenv("VBHEM_ALLREDUCE", "nccl")
     base, hyp, cen = make_case(N=901, K=5, Sb=6, Sr=5, d=2, covmode="full", ragged=True, seed=17, Nv=15.0)
     with api().MultiBaseSet(base, devices=devs) as ms:
+        assert ms.allreduce_mode() == mode
         want = ms.estep_hyp(hyp, 8, want_pairs=False)["buf"]
         for _ in range(3):                 # odd count: the next E-step uses the other exchange buffer
             ms.align()
