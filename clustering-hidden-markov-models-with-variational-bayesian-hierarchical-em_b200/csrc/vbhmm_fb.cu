@@ -146,7 +146,9 @@ __device__ __forceinline__ double shifted_exp(const double (&lr)[K], double (&p)
 #pragma unroll
   for (int k = 0; k < K; k++) {
     double y = (lr[k] - mx) * vbhem::kPerUnit;
-    y = y > -4.0e8 ? y : -4.0e8;                  // exp_split's domain; far below the 2^-1000 clamp anyway
+    // exp_split's domain: y >= -4e8 units (far below the 2^-1000 clamp anyway).  y <= 0, so its magnitude grows with
+    // its high word read as unsigned: one integer minimum instead of a compare and two selects (NaN is clamped, too)
+    y = __hiloint2double((int)min((unsigned)__double2hiint(y), 0xC1B7D784u), __double2loint(y));
     int e;
     const double mant = vbhem::exp_split<1>(y, etab, e);
     p[k] = vbhem::exp_scale(mant, e);
