@@ -9,18 +9,18 @@
 // emissions, scaled forward recursion, backward recursion, responsibilities gamma and summed pair
 // marginals xi, and phi_norm = sum_t log c_t + sum_t max_k logrho.
 //
-// This path is HBM-bound (about 3 flop per byte), unlike the VBHEM E-step.  Design:
-//   * one thread per sequence; the observations are repacked once into X[dim, N, maxT], so that every
-//     load and every store of a warp at time step t is one contiguous run of 32 x (dim or K) doubles;
-//   * the model (m, W, v, dim/beta, logLambdaTilde, p(z1), p(z_t | z_t-1)) travels as a by-value kernel
-//     parameter: it sits in the constant bank and every use is a DFMA operand, never a load;
-//   * the forward pass writes logrho and parks alpha_hat in the gamma output; the backward pass reads
-//     it back in place, recomputes the emissions of step t+1 from X (cheaper than reading logrho back)
-//     and the scale c_{t+1} from alpha_t (bit-identical to the forward value, so no scale array);
-//     (taking c_{t+1} = sum_j alpha_hat_t(j) eta(j) from the backward sums and log c from the lean log saves 70 fp64
-//     instructions per step but costs registers: 2.30 -> 2.36 ms here, while the batched kernel, which is not held
-//     to 128 registers, gains 3 % from it -- vbhmm_batch.inl)
-//   * outputs beyond a sequence's own length are written as zeros by the same thread (no memset pass).
+// Unlike the VBHEM E-step this path has 5 KB of compulsory traffic per sequence against ~ 14 000 fp64 instructions:
+// HBM, the fp64 pipe, issue slots and the LSU all matter.  Design (DESIGN.md 3.7 has the measurements):
+//   * one thread per sequence, a warp takes 32 consecutive sequences at a time from a device counter (persistent
+//     grid); the observations are repacked once into X[dim, N, maxT] and arrive through a per-lane cp.async ring;
+//   * the model (m, the folded quadratic forms of the emission densities, p(z1), p(z_t | z_t-1)) travels as a
+//     by-value kernel parameter: it sits in the constant bank and every use is a DFMA operand, never a load;
+//   * alpha_hat waits for the backward pass ON CHIP: the last steps in shared memory, the rest in an L2-resident
+//     scratch buffer whose size depends on the number of resident threads only, read back by cp.async;
+//   * the backward pass does not evaluate the emissions again: p_{t+1} / c_{t+1} = alpha_hat_{t+1} / (alpha_hat_t A);
+//   * every output row (the reference's [K, N, maxT] layout) is transposed through shared memory by the warp and
+//     written as full 256-byte runs; rows beyond a sequence's own length are written as zeros by the same warp
+//     (no memset pass).
 #include "../../include/vbhem_b200.h"
 #include "vbhem_math.cuh"
 
