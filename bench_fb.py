@@ -142,6 +142,33 @@ def main_fb(a):
         if i >= W:
             stats_ms.append(ms.value)
             stats_wall.append(1e3 * dtw)
+    # real recordings are ragged: the same pass over sequences whose lengths are uniform in 1..T (every warp mixes
+    # lengths: its loops run to the longest of its 32 sequences and take the variant with per-lane conditions)
+    ragged = None
+    if not a.no_extras:
+        rng = np.random.default_rng(a.seed + 17)
+        Tr = rng.integers(1, T + 1, size=N).astype(np.int32)
+        Xr = flat.reshape(N, dim, T)
+        flat_r = np.zeros(N * T * dim)
+        keepm = np.arange(T)[None, :] < Tr[:, None]
+        for dd_ in range(dim):                    # sequence n: dim runs of Tr[n] steps from offs[n] ([Tr x dim] column-major)
+            idx = offs[:-1, None] + dd_ * Tr[:, None].astype(np.int64) + np.arange(T, dtype=np.int64)[None, :]
+            flat_r[idx[keepm]] = Xr[:, dd_, :][keepm]
+        del idx, keepm
+        with fb.SequenceSet.from_packed(Tr, offs, flat_r, dim) as sr:
+            rms = []
+            for i in range(2 + 3):
+                check(L.vbhmm_fb_dev(sr._h, *model))
+                check(L.vbhmm_fb_last_ms(sr._h, C.byref(ms)))
+                if i >= 2:
+                    rms.append(ms.value)
+        steps_r = int(Tr.sum())
+        ragged = dict(ms_per_pass=statistics.median(rms), sequence_steps=steps_r, uniform_sequence_steps=N * T,
+                      ns_per_sequence_step=statistics.median(rms) * 1e6 / steps_r,
+                      uniform_ns_per_sequence_step=tot / a.steps * 1e6 / (N * T),
+                      note="lengths uniform in 1..T: half the sequence steps of the headline workload; a lane idles while "
+                           "its warp finishes longer sequences, and ragged warps run the general variant of the loops")
+        del flat_r
     # the toolbox's actual use: one HMM per subject (vbhmm_learn_batch.m).  20 000 subjects share the N sequences;
     # every subject's whole EM run (vbhmm_em.m) executes in ONE device-resident loop (vbhmm_batch_*)
     learn = None
@@ -244,6 +271,8 @@ def main_fb(a):
                                   note="vbhmm_fb_stats: forward-backward + the M-step sums of vbhmm_em.m:158-246 + Lt63 / "
                                        "Lt64 on the device, observations resident (packed once per vbhmm_em run); wall_ms "
                                        "is host wall clock of the C-ABI call including the result copy"))
+    if ragged is not None:
+        line["ragged"] = ragged
     if learn is not None:
         line["learn_batch"] = learn
     if cpu is not None:
