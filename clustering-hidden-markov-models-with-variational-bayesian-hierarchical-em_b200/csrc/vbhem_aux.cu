@@ -413,13 +413,14 @@ __global__ void k_partial_reduce(int K, int per, const int *seg_start, const int
   if (b > a) {
     const int w_hi = (b - 1) / ipr;
     VB_ASSERT(ipr >= 1 && a >= 0 && b <= totals[0] && (long long)w_hi * ipr < (long long)totals[0]);
-    // eight loads in flight, added in slot order (a chain of dependent load-add pairs costs an L2 latency per slot)
-    for (int w = a / ipr; w <= w_hi; w += 8) {
-      double v[8];
+    // sixteen loads in flight, added in slot order (a chain of dependent load-add pairs costs an L2 latency per slot;
+    // a 12 500-base shard leaves ~ 38 slots per centre: three rounds)
+    for (int w = a / ipr; w <= w_hi; w += 16) {
+      double v[16];
 #pragma unroll
-      for (int u = 0; u < 8; u++) v[u] = w + u <= w_hi ? partial[(size_t)(w + u + j) * per + q] : 0.0;
+      for (int u = 0; u < 16; u++) v[u] = w + u <= w_hi ? partial[(size_t)(w + u + j) * per + q] : 0.0;
 #pragma unroll
-      for (int u = 0; u < 8; u++) s += v[u];
+      for (int u = 0; u < 16; u++) s += v[u];
     }
   }
   if (q < r) S_nu1[q + (size_t)r * j] = s;
@@ -596,7 +597,7 @@ int launch_partial_reduce(int K, int per, const int *seg_start, const int *total
                           double *S_nu1, double *S_xi, double *S_pr, double *S_mu, double *S_Mu, int r, int d, int dd,
                           cudaStream_t st) {
   const int tot = K * per;
-  launch_chain(k_partial_reduce, dim3((tot + 127) / 128), dim3(128), 0, st, K, per, seg_start, totals, partial, S_nu1,
+  launch_chain(k_partial_reduce, dim3((tot + 63) / 64), dim3(64), 0, st, K, per, seg_start, totals, partial, S_nu1,
                S_xi, S_pr, S_mu, S_Mu, r, d, dd);
   return 1;
 }
